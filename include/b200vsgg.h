@@ -71,6 +71,102 @@ typedef struct b200vsgg_gemm_epilogue {
 int b200vsgg_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, const void* B, int32_t ldb, int32_t b_mn,
                        int32_t M, int32_t N, int32_t K, const b200vsgg_gemm_epilogue* ep, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Segment indexing (bit-exact int32).  Replaces the per-frame Python loops that pad pair rows
+ * into [l, b, 1936] (tools/utils/transformer.py:184-192) and lib/teatgt.py:104-115.
+ * offsets[f] = first pair row with frame id >= f, f in [0, n_frames]; im_idx is sorted fp32.
+ */
+int b200vsgg_frame_offsets(const float* im_idx, int32_t n_pairs, int32_t n_frames, int32_t* offsets, void* stream);
+
+/* out[t,:] = src[idx[t],:] (idx NULL = identity); optional outputs fp32 / bf16 / bf16(row +
+ * add_table[add_idx[t],:]).  Temporal window build + position embedding add
+ * (tools/utils/transformer.py:203-215) and the 'latter' scatter-back (:236-242) are both this
+ * gather with host-planned index vectors. cols % 8 == 0. */
+int b200vsgg_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, const float* add_table,
+                         const int32_t* add_idx, int32_t rows, int32_t cols, float* out_f32, int32_t ld_f32,
+                         void* out_bf16, int32_t ld_bf16, void* out_bf16_added, int32_t ld_added, void* stream);
+
+/* Deterministic backward of a gather in which every destination row is read at most twice:
+ * out[n,:] = base[n,:] + sum_{k<2, idx2[2n+k] >= 0} src[idx2[2n+k],:]. */
+int b200vsgg_gather2_sum_rows(const float* src, int32_t ld_src, const int32_t* idx2, const float* base,
+                              int32_t ld_base, int32_t rows, int32_t cols, float* out_f32, int32_t ld_f32,
+                              void* out_bf16, int32_t ld_bf16, void* stream);
+
+/* Pair-token gather/concat (lib/tempura.py:537-563): tok[n] = so[pair_idx[n,0],0:512] |
+ * so[pair_idx[n,1],512:1024] | (vr_fc output already in tok_f32[:,1024:1536]) |
+ * embed1[labels[pair_idx[n,0]]] | embed2[labels[pair_idx[n,1]]];  writes fp32 and bf16 [N,1936].
+ * `so` is the fused subj_fc|obj_fc GEMM output over ALL boxes, [O,1024] fp32. */
+int b200vsgg_pair_concat_fwd(const float* so, const int64_t* pair_idx, const int64_t* labels, const float* embed1,
+                             const float* embed2, int32_t n_pairs, float* tok_f32, void* tok_bf16, void* stream);
+int b200vsgg_pair_concat_bwd(const float* dtok, const int64_t* pair_idx, const int64_t* labels, int32_t n_pairs,
+                             float* dso /* [O,1024], pre-zeroed */, float* dembed1 /* nullable */,
+                             float* dembed2 /* nullable */, void* stream);
+
+/* LayerNorm over the last dim (nn.LayerNorm, eps inside the sqrt), tools/utils/transformer.py:14-15,
+ * 45 and tokengt_graph_encoder_layer.py:170-191.  cols % 8 == 0, cols <= 2048. */
+int b200vsgg_layernorm_fwd(const float* x, int32_t ld_x, const float* gamma, const float* beta, int32_t rows,
+                           int32_t cols, float eps, float* y_f32, int32_t ld_y, void* y_bf16, int32_t ld_b,
+                           const float* add_table, const int32_t* add_idx, void* y_bf16_added, int32_t ld_added,
+                           float* mean, float* rstd, void* stream);
+/* dgamma / dbeta are ACCUMULATED (+=) and may be NULL; dx_bf16 (nullable) = bf16(dropout(dx)). */
+int b200vsgg_layernorm_bwd(const float* dy, int32_t ld_dy, const float* x, int32_t ld_x, const float* gamma,
+                           const float* mean, const float* rstd, int32_t rows, int32_t cols, float* dx_f32,
+                           int32_t ld_dx, void* dx_bf16, int32_t ld_b, float drop_p, uint64_t drop_seed,
+                           float* dgamma, float* dbeta, void* stream);
+
+/* out = bf16(dropout(x)) with the GEMM epilogue's mask function (index = row*cols + col). */
+int b200vsgg_cast_dropout_bf16(const float* x, int32_t ld_x, int32_t rows, int32_t cols, void* out, int32_t ld_o,
+                               float drop_p, uint64_t seed, void* stream);
+
+/* out[g, c] += sum over rows r with group_idx[r]==g of x[r,c]  (bias / position-embedding grads). */
+int b200vsgg_colsum(const void* x, int32_t x_is_bf16, int32_t ld_x, int32_t rows, int32_t cols,
+                    const int32_t* group_idx /* nullable */, int32_t n_groups /* 1 or 2 */, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Variable-length multi-head attention over short segments (one frame / one 2-frame window):
+ * nn.MultiheadAttention in tools/utils/transformer.py:23 and :50, evaluated only on real rows.
+ * q,k,v,ctx,dq,dk,dv: bf16 [rows, n_heads*head_dim] views with their own leading dimensions;
+ * seg_off: int32 [n_seg+1] row offsets; max_len >= longest segment; scale = head_dim^-0.5.
+ * drop_p: attention-probability dropout (train), regenerated from `seed` in backward. */
+int b200vsgg_attn_small_fwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                            const int32_t* seg_off, int32_t n_seg, int32_t max_len, int32_t n_heads,
+                            int32_t head_dim, float scale, void* ctx, int32_t ldc, float drop_p, uint64_t seed,
+                            void* stream);
+int b200vsgg_attn_small_bwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                            const void* dctx, int32_t ldc, const int32_t* seg_off, int32_t n_seg, int32_t max_len,
+                            int32_t n_heads, int32_t head_dim, float scale, void* dq, int32_t lddq, void* dk,
+                            int32_t lddk, void* dv, int32_t lddv, float drop_p, uint64_t seed, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GMM predicate heads (tools/utils/gmm_heads.py:37-76, uncertainty :25-35).  z = fp32 output of the
+ * packed head GEMM; head h occupies columns [col_base, col_base + K*(2C+1)) laid out as
+ * mu[K][C] | var[K][C] | pi[K].  mode 0: test (mu), 1: train (mu + sqrt(sigmoid(var))*eps),
+ * 2: uncertainty (out = aleatoric, out2 = epistemic).  eps NULL in train mode = counter-based
+ * N(0,1) from `seed` (the reference draws it on the CPU, gmm_heads.py:57). */
+typedef struct b200vsgg_gmm_head {
+    int32_t col_base;
+    int32_t num_classes;
+    int32_t softmax;   /* 1: softmax over classes (attention head), 0: sigmoid */
+    const float* eps;  /* [K, N, C] or NULL */
+    float* out;        /* [N, C] */
+    float* out2;       /* [N, C], mode 2 only */
+    const float* dout; /* [N, C], backward only */
+} b200vsgg_gmm_head;
+int b200vsgg_gmm_head_fwd(const float* z, int32_t ldz, int32_t n_rows, int32_t K, const b200vsgg_gmm_head* heads,
+                          int32_t n_heads, int32_t mode, uint64_t seed, void* stream);
+int b200vsgg_gmm_head_bwd(const float* z, int32_t ldz, int32_t n_rows, int32_t K, const b200vsgg_gmm_head* heads,
+                          int32_t n_heads, int32_t mode, uint64_t seed, void* dz_bf16, int32_t lddz,
+                          int32_t total_cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout conversion of the detector hand-off (lib/tempura.py:548): fp32 NCHW [n,channels,spatial]
+ * -> bf16 (or fp32) NHWC rows [n*spatial, channels], and back (fp32) for gradients of the mask
+ * branch.  channels % 64 == 0. */
+int b200vsgg_nchw_to_nhwc_bf16(const float* in, int32_t n, int32_t channels, int32_t spatial, void* out, void* stream);
+int b200vsgg_nchw_to_nhwc_f32(const float* in, int32_t n, int32_t channels, int32_t spatial, float* out, void* stream);
+int b200vsgg_nhwc_to_nchw_f32(const float* in, int32_t n, int32_t channels, int32_t spatial, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,11 +1,36 @@
-"""ctypes signatures for the non-GEMM entry points of include/b200vsgg.h (kept next to the header
-order so the symbol-export test can diff them)."""
+"""ctypes signatures for the non-GEMM entry points of include/b200vsgg.h (same order as the header;
+tests/test_capi_symbols.py checks that every function the header declares is exported and listed)."""
 import ctypes as C
 
 i32, i64, vp, f32, u64 = C.c_int32, C.c_int64, C.c_void_p, C.c_float, C.c_uint64
 
+
+class GmmHead(C.Structure):
+    """Mirror of struct b200vsgg_gmm_head."""
+    _fields_ = [("col_base", i32), ("num_classes", i32), ("softmax", i32), ("eps", vp), ("out", vp),
+                ("out2", vp), ("dout", vp)]
+
+
 # name -> argtypes (restype is always int32)
-SIGNATURES = {}
+SIGNATURES = {
+    "b200vsgg_frame_offsets": [vp, i32, i32, vp, vp],
+    "b200vsgg_gather_rows": [vp, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, vp, i32, vp],
+    "b200vsgg_gather2_sum_rows": [vp, i32, vp, vp, i32, i32, i32, vp, i32, vp, i32, vp],
+    "b200vsgg_pair_concat_fwd": [vp, vp, vp, vp, vp, i32, vp, vp, vp],
+    "b200vsgg_pair_concat_bwd": [vp, vp, vp, i32, vp, vp, vp, vp],
+    "b200vsgg_layernorm_fwd": [vp, i32, vp, vp, i32, i32, f32, vp, i32, vp, i32, vp, vp, vp, i32, vp, vp, vp],
+    "b200vsgg_layernorm_bwd": [vp, i32, vp, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, vp],
+    "b200vsgg_cast_dropout_bf16": [vp, i32, i32, i32, vp, i32, f32, u64, vp],
+    "b200vsgg_colsum": [vp, i32, i32, i32, i32, vp, i32, vp, vp],
+    "b200vsgg_attn_small_fwd": [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, f32, vp, i32, f32, u64, vp],
+    "b200vsgg_attn_small_bwd": [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, f32, vp, i32, vp, i32,
+                                vp, i32, f32, u64, vp],
+    "b200vsgg_gmm_head_fwd": [vp, i32, i32, i32, C.POINTER(GmmHead), i32, i32, u64, vp],
+    "b200vsgg_gmm_head_bwd": [vp, i32, i32, i32, C.POINTER(GmmHead), i32, i32, u64, vp, i32, i32, vp],
+    "b200vsgg_nchw_to_nhwc_bf16": [vp, i32, i32, i32, vp, vp],
+    "b200vsgg_nchw_to_nhwc_f32": [vp, i32, i32, i32, vp, vp],
+    "b200vsgg_nhwc_to_nchw_f32": [vp, i32, i32, i32, vp, vp],
+}
 
 
 def declare(lib):

@@ -78,3 +78,193 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, mask_src=Non
     check(rc, "gemm_bf16")
     _count()
     return out_f32 if out_f32 is not None else out_bf16
+
+
+# ------------------------------------------------------------------------------------------------
+# row kernels
+# ------------------------------------------------------------------------------------------------
+def _f32(t):
+    assert t is None or (t.dtype == torch.float32 and t.stride(-1) == 1), "expected contiguous-row fp32"
+    return t
+
+
+def _bf(t):
+    assert t is None or (t.dtype == torch.bfloat16 and t.stride(-1) == 1), "expected contiguous-row bf16"
+    return t
+
+
+def _ld(t):
+    return t.stride(0) if t is not None and t.dim() == 2 else 0
+
+
+def frame_offsets(im_idx, n_frames):
+    """int32 [F+1] exclusive offsets of the sorted fp32 frame ids (device tensor)."""
+    assert im_idx.dtype == torch.float32 and im_idx.is_contiguous()
+    out = torch.empty(n_frames + 1, dtype=torch.int32, device=im_idx.device)
+    check(_lib.lib().b200vsgg_frame_offsets(_ptr(im_idx), im_idx.numel(), n_frames, _ptr(out), _stream()),
+          "frame_offsets")
+    _count()
+    return out
+
+
+def gather_rows(src, idx=None, rows=None, add_table=None, add_idx=None, out_f32=None, out_bf16=None,
+                out_bf16_added=None):
+    _f32(src)
+    cols = src.shape[1]
+    rows = rows if rows is not None else (idx.numel() if idx is not None else src.shape[0])
+    for t in (idx, add_idx):
+        assert t is None or (t.dtype == torch.int32 and t.is_contiguous())
+    check(_lib.lib().b200vsgg_gather_rows(
+        _ptr(src), src.stride(0), _ptr(idx), _ptr(_f32(add_table)), _ptr(add_idx), rows, cols,
+        _ptr(_f32(out_f32)), _ld(out_f32), _ptr(_bf(out_bf16)), _ld(out_bf16), _ptr(_bf(out_bf16_added)),
+        _ld(out_bf16_added), _stream()), "gather_rows")
+    _count()
+
+
+def gather2_sum_rows(src, idx2, base=None, out_f32=None, out_bf16=None):
+    _f32(src)
+    assert idx2.dtype == torch.int32 and idx2.is_contiguous() and idx2.dim() == 2 and idx2.shape[1] == 2
+    rows, cols = idx2.shape[0], src.shape[1]
+    check(_lib.lib().b200vsgg_gather2_sum_rows(
+        _ptr(src), src.stride(0), _ptr(idx2), _ptr(_f32(base)), _ld(base), rows, cols, _ptr(_f32(out_f32)),
+        _ld(out_f32), _ptr(_bf(out_bf16)), _ld(out_bf16), _stream()), "gather2_sum_rows")
+    _count()
+
+
+def pair_concat_fwd(so, pair_idx, labels, embed1, embed2, tok_f32, tok_bf16):
+    assert so.is_contiguous() and so.shape[1] == 1024 and pair_idx.dtype == torch.int64 and pair_idx.is_contiguous()
+    assert labels.dtype == torch.int64 and tok_f32.is_contiguous() and tok_bf16.is_contiguous()
+    assert embed1.is_contiguous() and embed2.is_contiguous() and embed1.shape[1] == 200
+    check(_lib.lib().b200vsgg_pair_concat_fwd(_ptr(_f32(so)), _ptr(pair_idx), _ptr(labels), _ptr(_f32(embed1)),
+                                               _ptr(_f32(embed2)), pair_idx.shape[0], _ptr(_f32(tok_f32)),
+                                               _ptr(_bf(tok_bf16)), _stream()), "pair_concat_fwd")
+    _count()
+
+
+def pair_concat_bwd(dtok, pair_idx, labels, dso, dembed1=None, dembed2=None):
+    assert dtok.is_contiguous() and dso.is_contiguous()
+    check(_lib.lib().b200vsgg_pair_concat_bwd(_ptr(_f32(dtok)), _ptr(pair_idx), _ptr(labels), pair_idx.shape[0],
+                                               _ptr(_f32(dso)), _ptr(_f32(dembed1)), _ptr(_f32(dembed2)), _stream()),
+          "pair_concat_bwd")
+    _count()
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5, y_f32=None, y_bf16=None, add_table=None, add_idx=None,
+                  y_bf16_added=None, mean=None, rstd=None):
+    rows, cols = x.shape
+    check(_lib.lib().b200vsgg_layernorm_fwd(
+        _ptr(_f32(x)), x.stride(0), _ptr(_f32(gamma)), _ptr(_f32(beta)), rows, cols, eps, _ptr(_f32(y_f32)),
+        _ld(y_f32), _ptr(_bf(y_bf16)), _ld(y_bf16), _ptr(_f32(add_table)), _ptr(add_idx), _ptr(_bf(y_bf16_added)),
+        _ld(y_bf16_added), _ptr(mean), _ptr(rstd), _stream()), "layernorm_fwd")
+    _count()
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_f32=None, dx_bf16=None, drop_p=0.0, seed=0, dgamma=None, dbeta=None):
+    rows, cols = x.shape
+    check(_lib.lib().b200vsgg_layernorm_bwd(
+        _ptr(_f32(dy)), dy.stride(0), _ptr(_f32(x)), x.stride(0), _ptr(_f32(gamma)), _ptr(mean), _ptr(rstd), rows,
+        cols, _ptr(_f32(dx_f32)), _ld(dx_f32), _ptr(_bf(dx_bf16)), _ld(dx_bf16), drop_p, seed, _ptr(_f32(dgamma)),
+        _ptr(_f32(dbeta)), _stream()), "layernorm_bwd")
+    _count()
+
+
+def cast_bf16(x, out=None, drop_p=0.0, seed=0):
+    """bf16(dropout(x)) for a 2-D fp32 tensor (row stride allowed)."""
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty(rows, cols, dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().b200vsgg_cast_dropout_bf16(_ptr(_f32(x)), x.stride(0), rows, cols, _ptr(_bf(out)),
+                                                 out.stride(0), drop_p, seed, _stream()), "cast_dropout_bf16")
+    _count()
+    return out
+
+
+def colsum(x, out, group_idx=None, n_groups=1):
+    """out[g,:] += column sums of x over rows of group g."""
+    rows, cols = x.shape
+    assert x.stride(1) == 1 and out.dtype == torch.float32 and out.is_contiguous()
+    check(_lib.lib().b200vsgg_colsum(_ptr(x), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), rows, cols,
+                                      _ptr(group_idx), n_groups, _ptr(out), _stream()), "colsum")
+    _count()
+
+
+def attn_small_fwd(q, k, v, seg_off, n_seg, max_len, n_heads, head_dim, ctx, drop_p=0.0, seed=0):
+    scale = float(head_dim) ** -0.5
+    check(_lib.lib().b200vsgg_attn_small_fwd(
+        _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), _ptr(seg_off), n_seg,
+        max_len, n_heads, head_dim, scale, _ptr(_bf(ctx)), ctx.stride(0), drop_p, seed, _stream()), "attn_small_fwd")
+    _count()
+
+
+def attn_small_bwd(q, k, v, dctx, seg_off, n_seg, max_len, n_heads, head_dim, dq, dk, dv, drop_p=0.0, seed=0):
+    scale = float(head_dim) ** -0.5
+    check(_lib.lib().b200vsgg_attn_small_bwd(
+        _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), _ptr(_bf(dctx)),
+        dctx.stride(0), _ptr(seg_off), n_seg, max_len, n_heads, head_dim, scale, _ptr(_bf(dq)), dq.stride(0),
+        _ptr(_bf(dk)), dk.stride(0), _ptr(_bf(dv)), dv.stride(0), drop_p, seed, _stream()), "attn_small_bwd")
+    _count()
+
+
+def _gmm_heads_array(specs):
+    from ._decls import GmmHead
+    arr = (GmmHead * len(specs))()
+    for i, s in enumerate(specs):
+        arr[i].col_base = s["col_base"]
+        arr[i].num_classes = s["num_classes"]
+        arr[i].softmax = 1 if s["softmax"] else 0
+        for f in ("eps", "out", "out2", "dout"):
+            t = s.get(f)
+            if t is not None:
+                assert t.dtype == torch.float32 and t.is_contiguous()
+            setattr(arr[i], f, t.data_ptr() if t is not None else None)
+    return arr
+
+
+def gmm_head_fwd(z, K, specs, mode, seed=0):
+    arr = _gmm_heads_array(specs)
+    check(_lib.lib().b200vsgg_gmm_head_fwd(_ptr(_f32(z)), z.stride(0), z.shape[0], K, arr, len(specs), mode, seed,
+                                            _stream()), "gmm_head_fwd")
+    _count()
+
+
+def gmm_head_bwd(z, K, specs, mode, dz_bf16, seed=0):
+    arr = _gmm_heads_array(specs)
+    check(_lib.lib().b200vsgg_gmm_head_bwd(_ptr(_f32(z)), z.stride(0), z.shape[0], K, arr, len(specs), mode, seed,
+                                            _ptr(_bf(dz_bf16)), dz_bf16.stride(0), dz_bf16.shape[1], _stream()),
+          "gmm_head_bwd")
+    _count()
+
+
+def nchw_to_nhwc_bf16(x, out=None):
+    """fp32 [n,C,H,W] (contiguous) -> bf16 rows [n*H*W, C]."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n, c = x.shape[0], x.shape[1]
+    s = x[0, 0].numel() if n > 0 else 1
+    if out is None:
+        out = torch.empty(n * s, c, dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().b200vsgg_nchw_to_nhwc_bf16(_ptr(x), n, c, s, _ptr(out), _stream()), "nchw_to_nhwc_bf16")
+    _count(max(1, (n + 65534) // 65535))
+    return out
+
+
+def nchw_to_nhwc_f32(x, out=None):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n, c = x.shape[0], x.shape[1]
+    s = x[0, 0].numel() if n > 0 else 1
+    if out is None:
+        out = torch.empty(n * s, c, dtype=torch.float32, device=x.device)
+    check(_lib.lib().b200vsgg_nchw_to_nhwc_f32(_ptr(x), n, c, s, _ptr(out), _stream()), "nchw_to_nhwc_f32")
+    _count(max(1, (n + 65534) // 65535))
+    return out
+
+
+def nhwc_to_nchw_f32(x, n, c, hw_shape):
+    """fp32 rows [n*S, C] -> fp32 [n, C, *hw_shape]."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    s = 1
+    for d in hw_shape:
+        s *= d
+    out = torch.empty((n, c) + tuple(hw_shape), dtype=torch.float32, device=x.device)
+    check(_lib.lib().b200vsgg_nhwc_to_nchw_f32(_ptr(x), n, c, s, _ptr(out), _stream()), "nhwc_to_nchw_f32")
+    _count(max(1, (n + 65534) // 65535))
+    return out

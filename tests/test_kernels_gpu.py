@@ -1,0 +1,279 @@
+"""Row / attention / head / layout kernels of libb200vsgg.so against plain torch fp32 references
+(and the oracle's GMM head).  All through the C-ABI (ctypes).  Tolerances are written per test:
+fp32 kernels 1e-5 relative; kernels that emit bf16 are compared after rounding the reference to
+bf16 (<= 1 bf16 ulp = 2^-8 relative)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _gen(seed):
+    return torch.Generator(device=DEV).manual_seed(seed)
+
+
+def test_frame_offsets_bit_exact(cuda_lib):
+    from b200vsgg import ops
+    counts = torch.tensor([3, 1, 7, 2, 9, 1, 1, 4])
+    im_idx = torch.repeat_interleave(torch.arange(8), counts).float().to(DEV)
+    off = ops.frame_offsets(im_idx, 8)
+    ref = torch.zeros(9, dtype=torch.int32)
+    ref[1:] = torch.cumsum(counts, 0)
+    assert torch.equal(off.cpu(), ref)
+
+
+def test_gather_rows_and_sum(cuda_lib):
+    from b200vsgg import ops
+    g = _gen(1)
+    src = torch.randn(50, 1936, generator=g, device=DEV)
+    idx = torch.randint(0, 50, (77,), generator=g, device=DEV).int()
+    table = torch.randn(2, 1936, generator=g, device=DEV)
+    aidx = torch.randint(0, 2, (77,), generator=g, device=DEV).int()
+    o32 = torch.empty(77, 1936, device=DEV)
+    o16 = torch.empty(77, 1936, device=DEV, dtype=torch.bfloat16)
+    oa = torch.empty(77, 1936, device=DEV, dtype=torch.bfloat16)
+    ops.gather_rows(src, idx, add_table=table, add_idx=aidx, out_f32=o32, out_bf16=o16, out_bf16_added=oa)
+    ref = src[idx.long()]
+    assert torch.equal(o32, ref)                                   # bit-exact copy
+    assert torch.equal(o16, ref.bfloat16())
+    assert torch.equal(oa, (ref + table[aidx.long()]).bfloat16())
+    # gather2 (backward form)
+    idx2 = torch.stack([torch.randint(-1, 77, (50,), generator=g, device=DEV),
+                        torch.randint(-1, 77, (50,), generator=g, device=DEV)], 1).int().contiguous()
+    base = torch.randn(50, 1936, generator=g, device=DEV)
+    out = torch.empty(50, 1936, device=DEV)
+    ops.gather2_sum_rows(o32, idx2, base=base, out_f32=out)
+    ref2 = base.clone()
+    for k in range(2):
+        m = idx2[:, k] >= 0
+        ref2[m] += o32[idx2[m, k].long()]
+    assert torch.allclose(out, ref2, rtol=0, atol=1e-6)
+
+
+def test_pair_concat_fwd_bwd(cuda_lib):
+    from b200vsgg import ops, synthetic
+    e = synthetic.make_video_entry(2, 5, (2, 6), device=DEV)
+    N, O = e["pair_idx"].shape[0], e["labels"].shape[0]
+    g = _gen(3)
+    so = torch.randn(O, 1024, generator=g, device=DEV)
+    e1 = torch.randn(37, 200, generator=g, device=DEV)
+    e2 = torch.randn(37, 200, generator=g, device=DEV)
+    tok = torch.zeros(N, 1936, device=DEV)
+    vr = torch.randn(N, 512, generator=g, device=DEV)
+    tok[:, 1024:1536] = vr
+    tokb = torch.empty(N, 1936, device=DEV, dtype=torch.bfloat16)
+    ops.pair_concat_fwd(so, e["pair_idx"], e["labels"], e1, e2, tok, tokb)
+    pi, lab = e["pair_idx"], e["labels"]
+    ref = torch.cat([so[pi[:, 0], :512], so[pi[:, 1], 512:], vr, e1[lab[pi[:, 0]]], e2[lab[pi[:, 1]]]], 1)
+    assert torch.equal(tok, ref)
+    assert torch.equal(tokb, ref.bfloat16())
+    # backward
+    dtok = torch.randn(N, 1936, generator=g, device=DEV)
+    dso = torch.zeros(O, 1024, device=DEV)
+    de1 = torch.zeros(37, 200, device=DEV)
+    de2 = torch.zeros(37, 200, device=DEV)
+    ops.pair_concat_bwd(dtok, pi, lab, dso, de1, de2)
+    rso = torch.zeros(O, 1024, device=DEV)
+    rso[:, :512].index_add_(0, pi[:, 0], dtok[:, :512])
+    rso[:, 512:].index_add_(0, pi[:, 1], dtok[:, 512:1024])
+    r1 = torch.zeros(37, 200, device=DEV).index_add_(0, lab[pi[:, 0]], dtok[:, 1536:1736])
+    r2 = torch.zeros(37, 200, device=DEV).index_add_(0, lab[pi[:, 1]], dtok[:, 1736:])
+    assert torch.allclose(dso, rso, atol=1e-5) and torch.allclose(de1, r1, atol=1e-4) and torch.allclose(de2, r2, atol=1e-4)
+
+
+@pytest.mark.parametrize("rows,cols", [(301, 1936), (64, 768), (5, 2048)])
+def test_layernorm_fwd_bwd(cuda_lib, rows, cols):
+    from b200vsgg import ops
+    g = _gen(rows + cols)
+    x = (torch.randn(rows, cols, generator=g, device=DEV) * 2 + 0.3).requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(cols, generator=g, device=DEV)).requires_grad_(True)
+    beta = (0.1 * torch.randn(cols, generator=g, device=DEV)).requires_grad_(True)
+    table = torch.rand(2, cols, generator=g, device=DEV)
+    aidx = torch.randint(0, 2, (rows,), generator=g, device=DEV).int()
+    y = torch.empty(rows, cols, device=DEV)
+    yb = torch.empty(rows, cols, device=DEV, dtype=torch.bfloat16)
+    ya = torch.empty(rows, cols, device=DEV, dtype=torch.bfloat16)
+    mean = torch.empty(rows, device=DEV)
+    rstd = torch.empty(rows, device=DEV)
+    ops.layernorm_fwd(x.detach(), gamma.detach(), beta.detach(), 1e-5, y, yb, table, aidx, ya, mean, rstd)
+    ref = torch.nn.functional.layer_norm(x, (cols,), gamma, beta, 1e-5)
+    assert (y - ref).abs().max().item() < 2e-5
+    assert (yb.float() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item()
+    assert (ya.float() - (ref + table[aidx.long()])).abs().max().item() < 2 ** -7 * (ref.abs().max().item() + 1)
+    dy = torch.randn(rows, cols, generator=g, device=DEV)
+    ref.backward(dy)
+    dx = torch.empty(rows, cols, device=DEV)
+    dxb = torch.empty(rows, cols, device=DEV, dtype=torch.bfloat16)
+    dg = torch.zeros(cols, device=DEV)
+    db = torch.zeros(cols, device=DEV)
+    ops.layernorm_bwd(dy, x.detach(), gamma.detach(), mean, rstd, dx, dxb, 0.0, 0, dg, db)
+    assert (dx - x.grad).abs().max().item() < 5e-5
+    assert (dg - gamma.grad).abs().max().item() < 1e-4 * max(1.0, gamma.grad.abs().max().item())
+    assert (db - beta.grad).abs().max().item() < 1e-4 * max(1.0, beta.grad.abs().max().item())
+    assert torch.equal(dxb, dx.bfloat16())
+
+
+def test_cast_dropout_matches_gemm_mask(cuda_lib):
+    from b200vsgg import ops
+    M, N = 256, 512
+    x = torch.randn(M, N, device=DEV)
+    eye = torch.eye(N, device=DEV).bfloat16()
+    # GEMM with identity weight reproduces bf16(x) with the epilogue's dropout mask
+    o = torch.empty(M, N, device=DEV)
+    ops.gemm(x.bfloat16(), eye, out_f32=o, dropout_p=0.1, seed=42)
+    c = ops.cast_bf16(x, drop_p=0.1, seed=42)
+    assert torch.equal((o == 0), (c == 0) | (x.bfloat16() == 0))
+    kept = c != 0
+    assert torch.allclose(c[kept].float(), (x[kept] / 0.9), rtol=2 ** -7, atol=0)
+
+
+def test_colsum(cuda_lib):
+    from b200vsgg import ops
+    x = torch.randn(1000, 1936, device=DEV)
+    gi = torch.randint(0, 2, (1000,), device=DEV).int()
+    out = torch.zeros(2, 1936, device=DEV)
+    ops.colsum(x, out, gi, 2)
+    ref = torch.stack([x[gi == 0].sum(0), x[gi == 1].sum(0)])
+    assert torch.allclose(out, ref, atol=2e-3)
+    xb = x.bfloat16()
+    out1 = torch.ones(1, 1936, device=DEV)
+    ops.colsum(xb, out1)
+    assert torch.allclose(out1[0], xb.float().sum(0) + 1, atol=2e-3)
+
+
+def _attn_ref(q, k, v, seg_off, H, hd):
+    outs = []
+    for s in range(len(seg_off) - 1):
+        a, b = seg_off[s], seg_off[s + 1]
+        L = b - a
+        Q = q[a:b].view(L, H, hd).transpose(0, 1)
+        K = k[a:b].view(L, H, hd).transpose(0, 1)
+        V = v[a:b].view(L, H, hd).transpose(0, 1)
+        P = torch.softmax(Q @ K.transpose(1, 2) / math.sqrt(hd), -1)
+        outs.append((P @ V).transpose(0, 1).reshape(L, H * hd))
+    return torch.cat(outs)
+
+
+@pytest.mark.parametrize("H,hd,lens", [(8, 242, [8, 1, 16, 20, 3, 7]), (8, 242, [40, 5]), (4, 24, [33, 2, 9])])
+def test_attn_small_fwd_bwd(cuda_lib, H, hd, lens):
+    from b200vsgg import ops
+    D = H * hd
+    M = sum(lens)
+    seg = [0]
+    for n in lens:
+        seg.append(seg[-1] + n)
+    g = _gen(M)
+    qkv = torch.randn(M, 3 * D, generator=g, device=DEV).bfloat16()
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    seg_off = torch.tensor(seg, dtype=torch.int32, device=DEV)
+    ctx = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    ops.attn_small_fwd(q, k, v, seg_off, len(lens), max(lens), H, hd, ctx)
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qf, kf, vf, seg, H, hd)
+    assert (ctx.float() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item() + 1e-3
+    dctx = torch.randn(M, D, generator=g, device=DEV).bfloat16()
+    ref.backward(dctx.float())
+    dqkv = torch.empty(M, 3 * D, device=DEV, dtype=torch.bfloat16)
+    ops.attn_small_bwd(q, k, v, dctx, seg_off, len(lens), max(lens), H, hd, dqkv[:, :D], dqkv[:, D:2 * D],
+                       dqkv[:, 2 * D:])
+    for got, want in ((dqkv[:, :D], qf.grad), (dqkv[:, D:2 * D], kf.grad), (dqkv[:, 2 * D:], vf.grad)):
+        tol = 2 ** -7 * want.abs().max().item() + 1e-3
+        assert (got.float() - want).abs().max().item() < tol
+
+
+def test_attn_dropout_consistency(cuda_lib):
+    """With dropout the forward is a function of (seed) only, and backward uses the same mask:
+    d(ctx)/d(v) for an all-ones upstream equals column sums of the dropped P."""
+    from b200vsgg import ops
+    H, hd, lens = 8, 242, [12, 9]
+    D, M = H * hd, sum(lens)
+    seg_off = torch.tensor([0, 12, 21], dtype=torch.int32, device=DEV)
+    qkv = torch.randn(M, 3 * D, device=DEV).bfloat16()
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    c1 = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    c2 = torch.empty_like(c1)
+    c0 = torch.empty_like(c1)
+    ops.attn_small_fwd(q, k, v, seg_off, 2, 12, H, hd, c1, 0.1, 7)
+    ops.attn_small_fwd(q, k, v, seg_off, 2, 12, H, hd, c2, 0.1, 7)
+    ops.attn_small_fwd(q, k, v, seg_off, 2, 12, H, hd, c0, 0.0, 7)
+    assert torch.equal(c1, c2) and not torch.equal(c1, c0)
+
+
+def test_gmm_head_fwd_bwd_vs_oracle(cuda_lib):
+    from b200vsgg import ops
+    from oracle.tempura_oracle import GMMHeadOracle
+    torch.manual_seed(0)
+    N, K, D = 53, 6, 64
+    heads = [GMMHeadOracle(D, 3, "attention", K), GMMHeadOracle(D, 6, "spatial", K), GMMHeadOracle(D, 17, "contact", K)]
+    x = torch.randn(N, D)
+    # packed logits z exactly as the packed GEMM would produce them (fp32)
+    cols, bases = [], []
+    for h in heads:
+        bases.append(sum(c.shape[1] for c in cols))
+        mu = [h.heads["mu_%d" % i](x) for i in range(1, K + 1)]
+        var = [h.heads["var_%d" % i](x) for i in range(1, K + 1)]
+        pi = [h.heads["pi_%d" % i](x) for i in range(1, K + 1)]
+        cols += mu + var + pi
+    z = torch.cat(cols, 1).detach()
+    total = z.shape[1]
+    assert total == 330
+    zpad = torch.zeros(N, 336)
+    zpad[:, :330] = z
+    zd = zpad.to(DEV)
+    Cs = [3, 6, 17]
+    eps = [torch.randn(K, N, C) for C in Cs]
+    for mode, phase in ((0, "test"), (1, "train")):
+        outs = [torch.empty(N, C, device=DEV) for C in Cs]
+        specs = [dict(col_base=bases[i], num_classes=Cs[i], softmax=(i == 0), eps=eps[i].to(DEV), out=outs[i])
+                 for i in range(3)]
+        ops.gmm_head_fwd(zd, K, specs, mode)
+        xr = x.clone().requires_grad_(True)
+        refs = [heads[i](xr, phase, False, eps[i]) for i in range(3)]
+        for i in range(3):
+            assert (outs[i].cpu() - refs[i].detach()).abs().max().item() < 2e-6, (mode, i)
+    # uncertainty
+    o1 = [torch.empty(N, C, device=DEV) for C in Cs]
+    o2 = [torch.empty(N, C, device=DEV) for C in Cs]
+    specs = [dict(col_base=bases[i], num_classes=Cs[i], softmax=(i == 0), out=o1[i], out2=o2[i]) for i in range(3)]
+    ops.gmm_head_fwd(zd, K, specs, 2)
+    for i in range(3):
+        with torch.no_grad():
+            al, ep = heads[i](x, "test", True)
+        assert (o1[i].cpu() - al).abs().max().item() < 2e-6 and (o2[i].cpu() - ep).abs().max().item() < 2e-6
+    # backward (train mode) vs autograd through the same formulas on z
+    zr = zpad.clone().requires_grad_(True)
+
+    def mix(zz, base, C, softmax, e):
+        mu = zz[:, base:base + K * C].view(N, K, C).transpose(0, 1)
+        var = zz[:, base + K * C:base + 2 * K * C].view(N, K, C).transpose(0, 1).sigmoid()
+        pi = torch.softmax(zz[:, base + 2 * K * C:base + 2 * K * C + K], 1).t()[..., None]
+        lg = mu + var.sqrt() * e
+        a = torch.softmax(lg, -1) if softmax else torch.sigmoid(lg)
+        return (a * pi).sum(0)
+
+    douts = [torch.randn(N, C) for C in Cs]
+    loss = sum((mix(zr, bases[i], Cs[i], i == 0, eps[i]) * douts[i]).sum() for i in range(3))
+    loss.backward()
+    dz = torch.full((N, 336), 7.0, device=DEV, dtype=torch.bfloat16)
+    specs = [dict(col_base=bases[i], num_classes=Cs[i], softmax=(i == 0), eps=eps[i].to(DEV), dout=douts[i].to(DEV))
+             for i in range(3)]
+    ops.gmm_head_bwd(zd, K, specs, 1, dz)
+    err = (dz.float().cpu() - zr.grad).abs().max().item()
+    assert err < 2 ** -7 * zr.grad.abs().max().item() + 1e-4, err
+    assert dz[:, 330:].abs().max().item() == 0
+
+
+def test_layout_kernels(cuda_lib):
+    from b200vsgg import ops
+    x = torch.randn(37, 1024, 7, 7, device=DEV)
+    y = ops.nchw_to_nhwc_bf16(x)
+    ref = x.permute(0, 2, 3, 1).reshape(37 * 49, 1024)
+    assert torch.equal(y, ref.bfloat16())
+    m = torch.randn(21, 256, 7, 7, device=DEV)
+    yf = ops.nchw_to_nhwc_f32(m)
+    assert torch.equal(yf, m.permute(0, 2, 3, 1).reshape(21 * 49, 256))
+    back = ops.nhwc_to_nchw_f32(yf, 21, 256, (7, 7))
+    assert torch.equal(back, m)
