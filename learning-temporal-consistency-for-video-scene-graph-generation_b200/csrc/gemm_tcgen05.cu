@@ -36,6 +36,7 @@ struct GemmEpi {
     float alpha;
     float dropout_p;
     unsigned long long dropout_seed;
+    int vec_ok;  // all epilogue pointers / leading dimensions allow 16-byte vector access
 };
 
 constexpr int BM = 128;
@@ -205,7 +206,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         float v[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * ep.alpha;
-                        const bool full8 = (n + 8 <= N);
+                        const bool full8 = (n + 8 <= N) && ep.vec_ok;
                         if (ep.bias != nullptr) {
                             if (full8) {
                                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
@@ -428,6 +429,16 @@ extern "C" int b200vsgg_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, cons
     ep.alpha = e->alpha;
     ep.dropout_p = e->dropout_p;
     ep.dropout_seed = e->dropout_seed;
+    {
+        auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+        bool ok = true;
+        if (ep.bias) ok = ok && al16(ep.bias);
+        if (ep.residual) ok = ok && al16(ep.residual) && (ep.ldr % (ep.residual_is_bf16 ? 8 : 4) == 0);
+        if (ep.mask_src) ok = ok && al16(ep.mask_src) && (ep.ldm % 8 == 0);
+        if (ep.out_f32) ok = ok && al16(ep.out_f32) && (ep.ld_f32 % 4 == 0);
+        if (ep.out_bf16) ok = ok && al16(ep.out_bf16) && (ep.ld_bf16 % 8 == 0);
+        ep.vec_ok = ok ? 1 : 0;
+    }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     // Tile-N choice: 256-wide tiles when N is large enough to keep the padding waste small.
     const bool wide = (N >= 1024) || (N % 256 == 0);

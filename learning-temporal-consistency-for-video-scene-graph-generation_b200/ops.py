@@ -23,9 +23,18 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_DEBUG_SYNC = bool(int(__import__("os").environ.get("B200VSGG_DEBUG_SYNC", "0")))
+
+
 def _count(n=1):
     global launch_count
     launch_count += n
+    if _DEBUG_SYNC:  # debugging aid: surface asynchronous faults at the op that caused them
+        import inspect
+        try:
+            torch.cuda.synchronize()
+        except Exception as ex:
+            raise RuntimeError("CUDA fault surfaced after ops.%s: %s" % (inspect.stack()[1].function, ex))
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, mask_src=None, mask_mode=0,

@@ -1,0 +1,786 @@
+"""B200-native TEMPURA (PredCLS relation path) behind the reference's module API.
+
+Drop-in for `lib/tempura.py::TEMPURA` of the reference (constructor lib/tempura.py:428-432,
+`forward(entry, phase, unc)` :512-598): same keyword arguments, same `state_dict()` key names and
+shapes (checkpoints load with strict=True), same entry-dict keys in and out, same mutable
+attributes (`rel_memory`, `object_classifier.obj_memory`, `obj_classes`, `*_class_num`, `mode`).
+Sub-modules are constructed in the reference's order with the same torch initialisers, so the
+same `torch.manual_seed` yields the same initial weights (GloVe vectors are replaced by seeded
+N(0,1) rows unless `embed_vecs` is given — there is no network in this environment).
+
+Underneath, every tensor op of the path runs in hand-written sm_100a kernels from
+libb200vsgg.so (ops.py): tcgen05/TMA GEMMs, varlen attention, LayerNorm, gathers, GMM epilogue.
+There is NO CPU or eager-PyTorch fallback: CPU tensors raise.  Extensions over the reference API
+(all optional): a *batch* of videos can be passed (see `collate_entries`), and the P4 mask-conv
+branch (lib/tempura.py:466-474) currently runs through torch/cuDNN ops with per-video BatchNorm
+statistics (documented as not-yet-native in DESIGN.md).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .plan import SegmentPlan, plan_from_im_idx
+
+D_MODEL = 1936
+N_HEADS = 8
+HEAD_DIM = D_MODEL // N_HEADS
+FFN_DIM = 2048
+HEAD_COLS_PAD = 8  # packed head GEMM width is rounded up to a multiple of 8
+
+
+# ================================================================================================
+# parameter containers (names/shapes/initialisation order follow the reference)
+# ================================================================================================
+class GMMHead(nn.Module):
+    """Parameters of tools/utils/gmm_heads.py::GMM_head; evaluation happens in the fused kernels."""
+
+    def __init__(self, hid_dim, num_classes, rel_type=None, k=4):
+        super().__init__()
+        self.k, self.num_classes, self.rel_type = k, num_classes, rel_type
+        self.heads = nn.ModuleDict()
+        for i in range(k):
+            self.heads.update({"mu_%d" % (i + 1): nn.Linear(hid_dim, num_classes),
+                               "pi_%d" % (i + 1): nn.Linear(hid_dim, 1),
+                               "var_%d" % (i + 1): nn.Linear(hid_dim, num_classes)})
+
+    @property
+    def softmax(self):
+        return self.rel_type == "attention" or self.rel_type is None
+
+    def packed(self):
+        """([K*(2C+1), hid] weight, [K*(2C+1)] bias) in the kernel's column order mu|var|pi."""
+        K = self.k
+        order = ["mu_%d" % (i + 1) for i in range(K)] + ["var_%d" % (i + 1) for i in range(K)] + \
+                ["pi_%d" % (i + 1) for i in range(K)]
+        return (torch.cat([self.heads[n].weight for n in order], 0), torch.cat([self.heads[n].bias for n in order], 0))
+
+
+class _SpatialLayer(nn.Module):
+    def __init__(self, dim, heads, ffn, p):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(dim, heads, dropout=p)
+        self.linear1 = nn.Linear(dim, ffn)
+        self.linear2 = nn.Linear(ffn, dim)
+        self.norm1 = nn.LayerNorm(dim)
+        self.norm2 = nn.LayerNorm(dim)
+
+
+class _TemporalLayer(nn.Module):
+    def __init__(self, dim, heads, ffn, p):
+        super().__init__()
+        self.multihead2 = nn.MultiheadAttention(dim, heads, dropout=p)
+        self.linear1 = nn.Linear(dim, ffn)
+        self.linear2 = nn.Linear(ffn, dim)
+        self.norm3 = nn.LayerNorm(dim)
+
+
+class _LayerStack(nn.Module):
+    def __init__(self, first, n):
+        super().__init__()
+        import copy
+        self.layers = nn.ModuleList([copy.deepcopy(first) for _ in range(n)])
+        self.num_layers = n
+
+
+class _STTran(nn.Module):
+    """Parameters of tools/utils/transformer.py::transformer."""
+
+    def __init__(self, enc_layer_num, dec_layer_num, embed_dim, nhead, dim_feedforward, dropout, mode, mem_compute,
+                 mem_fusion, selection, selection_lambda):
+        super().__init__()
+        self.mode, self.mem_fusion, self.mem_compute, self.selection = mode, mem_fusion, mem_compute, selection
+        self.dropout_p = dropout
+        self.local_attention = _LayerStack(_SpatialLayer(embed_dim, nhead, dim_feedforward, dropout), enc_layer_num)
+        if mem_compute:
+            if mem_compute == "seperate":
+                raise NotImplementedError("rel_mem_compute='seperate' is not on the accelerated path")
+            self.mem_attention = nn.MultiheadAttention(embed_dim, 1, 0.0, bias=False)
+            if selection == "manual":
+                self.selector = selection_lambda
+            else:
+                self.selector = nn.Linear(embed_dim, 1)
+        self.global_attention = _LayerStack(_TemporalLayer(embed_dim, nhead, dim_feedforward, dropout), dec_layer_num)
+        self.position_embedding = nn.Embedding(2, embed_dim)
+        nn.init.uniform_(self.position_embedding.weight)
+
+
+class ObjectClassifier(nn.Module):
+    """lib/tempura.py:51-423.  PredCLS only needs `pred_labels = labels` (:245-247); the parameters
+    are created so that reference checkpoints load strictly (they stay frozen in PredCLS,
+    TEMPURA_train.py:106-108)."""
+
+    def __init__(self, mode="sgdet", obj_head="gmm", K=4, obj_classes=None, mem_compute=None, selection=None,
+                 selection_lambda=0.5, tracking=None, embed_vecs=None):
+        super().__init__()
+        self.classes, self.mode, self.GMM_K = obj_classes, mode, K
+        self.obj_memory = []
+        self.mem_compute, self.selection, self.tracking, self.obj_head = mem_compute, selection, tracking, obj_head
+        self.obj_embed = nn.Embedding(len(obj_classes) - 1, 200)
+        if embed_vecs is not None:
+            self.obj_embed.weight.data = embed_vecs[1:].clone()
+        self.pos_embed = nn.Sequential(nn.BatchNorm1d(4, momentum=0.01 / 10.0), nn.Linear(4, 128), nn.ReLU(inplace=True),
+                                       nn.Dropout(0.1))
+        self.obj_dim = 2048
+        mem_embed = 1024
+        if tracking:
+            raise NotImplementedError("tracking (SGCls/SGDet object branch) is a 'next' row, see DESIGN.md")
+        if mem_compute:
+            self.mem_attention = nn.MultiheadAttention(mem_embed, 1, 0.0, bias=False)
+            if selection == "manual":
+                self.selector = selection_lambda
+            else:
+                self.selector = nn.Linear(1024, 1)
+        self.intermediate = nn.Sequential(nn.Linear(self.obj_dim + 200 + 128, 1024), nn.BatchNorm1d(1024), nn.ReLU())
+        if obj_head == "gmm":
+            self.decoder_lin = GMMHead(1024, len(obj_classes), None, K)
+        else:
+            self.decoder_lin = nn.Sequential(nn.Linear(1024, len(obj_classes)))
+
+    def forward(self, entry, phase="train", unc=False):
+        if self.mode != "predcls":
+            raise NotImplementedError("only PredCLS is on the accelerated path (SURVEY.md §8)")
+        entry["pred_labels"] = entry["labels"]
+        return entry
+
+
+# ================================================================================================
+# helpers
+# ================================================================================================
+def collate_entries(entries):
+    """Concatenate per-video PredCLS entries into one batch entry (videos stay independent:
+    windows, BatchNorm statistics and losses never cross `video_frames` boundaries)."""
+    keys_cat = ["boxes", "labels", "scores", "im_idx", "pair_idx", "human_idx", "features", "union_feat", "union_box",
+                "spatial_masks"]
+    out = {}
+    box_base, frame_base = 0, 0
+    parts = {k: [] for k in keys_cat}
+    frames, gts = [], {"attention_gt": [], "spatial_gt": [], "contacting_gt": []}
+    for e in entries:
+        nf = int(e["human_idx"].shape[0]) if "human_idx" in e else int(e["im_idx"][-1].item()) + 1
+        for k in keys_cat:
+            if k not in e:
+                continue
+            t = e[k]
+            if k == "pair_idx" or k == "human_idx":
+                t = t + box_base
+            elif k == "im_idx":
+                t = t + frame_base
+            elif k in ("boxes", "union_box"):
+                t = t.clone()
+                t[:, 0] += frame_base
+            parts[k].append(t)
+        for k in gts:
+            if k in e:
+                gts[k].extend(e[k])
+        box_base += e["labels"].shape[0]
+        frame_base += nf
+        frames.append(nf)
+    for k in keys_cat:
+        if parts[k]:
+            out[k] = torch.cat(parts[k], 0)
+    for k, v in gts.items():
+        if v:
+            out[k] = v
+    out["video_frames"] = np.asarray(frames, dtype=np.int64)
+    out["video_size"] = entries[0].get("video_size")
+    return out
+
+
+class _GemmNT(torch.autograd.Function):
+    """y = a @ b^T through b200vsgg_gemm_bf16 (bf16 operands, fp32 out), differentiable in both."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ab, bb = ops.cast_bf16(a.contiguous()), ops.cast_bf16(b.contiguous())
+        ctx.save_for_backward(ab, bb)
+        out = torch.empty(a.shape[0], b.shape[0], device=a.device)
+        ops.gemm(ab, bb, out_f32=out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ab, bb = ctx.saved_tensors
+        M, N = g.shape
+        K = ab.shape[1]
+        Np = (N + 7) // 8 * 8  # TMA row pitch must be a multiple of 16 bytes
+        gb = torch.zeros(M, Np, device=g.device, dtype=torch.bfloat16)
+        ops.cast_bf16(g.contiguous(), out=gb[:, :N])
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty(M, K, device=g.device)
+            bpad = bb
+            if Np != N:
+                bpad = torch.zeros(Np, K, device=g.device, dtype=torch.bfloat16)
+                bpad[:N] = bb
+            ops.gemm(gb, bpad, b_mn=True, out_f32=da)
+        if ctx.needs_input_grad[1]:
+            dbp = torch.empty(Np, K, device=g.device)
+            ops.gemm(gb, ab, a_mn=True, b_mn=True, out_f32=dbp)
+            db = dbp[:N]
+        return da, db
+
+
+def _per_video_batchnorm(x, bn, training, video_of_pair, pairs_per_video):
+    """BatchNorm2d whose batch statistics are taken per video, because the reference's batch IS one
+    video (A.3 #9 in SURVEY.md).  Running statistics receive the V sequential momentum updates the
+    reference would have applied video by video."""
+    V = len(pairs_per_video)
+    if not training or V == 1:
+        return bn(x)
+    N, C, H, W = x.shape
+    cnt = torch.as_tensor(pairs_per_video, device=x.device, dtype=x.dtype) * (H * W)
+    s1 = torch.zeros(V, C, device=x.device, dtype=x.dtype).index_add_(0, video_of_pair, x.sum((2, 3)))
+    mean = s1 / cnt[:, None]
+    xc = x - mean[video_of_pair][:, :, None, None]
+    s2 = torch.zeros(V, C, device=x.device, dtype=x.dtype).index_add_(0, video_of_pair, (xc * xc).sum((2, 3)))
+    var = s2 / cnt[:, None]
+    y = xc * torch.rsqrt(var + bn.eps)[video_of_pair][:, :, None, None]
+    y = y * bn.weight[None, :, None, None] + bn.bias[None, :, None, None]
+    with torch.no_grad():
+        m = bn.momentum
+        w = m * (1 - m) ** torch.arange(V - 1, -1, -1, device=x.device, dtype=x.dtype)
+        unb = var * (cnt / (cnt - 1))[:, None]
+        bn.running_mean.mul_((1 - m) ** V).add_((w[:, None] * mean.detach()).sum(0))
+        bn.running_var.mul_((1 - m) ** V).add_((w[:, None] * unb.detach()).sum(0))
+        bn.num_batches_tracked += V
+    return y
+
+
+# ================================================================================================
+# the model
+# ================================================================================================
+class TEMPURA(nn.Module):
+
+    def __init__(self, mode="sgdet", attention_class_num=None, spatial_class_num=None, contact_class_num=None,
+                 obj_classes=None, rel_classes=None, enc_layer_num=None, dec_layer_num=None, obj_mem_compute=None,
+                 rel_mem_compute=None, mem_fusion=None, selection=None, selection_lambda=0.5, take_obj_mem_feat=False,
+                 obj_head="gmm", rel_head="gmm", K=None, tracking=None, embed_vecs=None):
+        super().__init__()
+        self.obj_classes, self.GMM_K, self.mem_fusion, self.rel_classes = obj_classes, K, mem_fusion, rel_classes
+        self.attention_class_num, self.spatial_class_num, self.contact_class_num = (
+            attention_class_num, spatial_class_num, contact_class_num)
+        assert mode in ("sgdet", "sgcls", "predcls")
+        if mode != "predcls" or take_obj_mem_feat or rel_head != "gmm":
+            raise NotImplementedError("b200vsgg.TEMPURA accelerates the PredCLS / GMM-head path (SURVEY.md §8); "
+                                      "got mode=%s take_obj_mem_feat=%s rel_head=%s" % (mode, take_obj_mem_feat, rel_head))
+        self.mode, self.tracking, self.take_obj_mem_feat = mode, tracking, take_obj_mem_feat
+        self.obj_head, self.rel_head = obj_head, rel_head
+        self.obj_mem_compute, self.rel_mem_compute = obj_mem_compute, rel_mem_compute
+        self.selection_lambda = float(selection_lambda)
+        self.rel_memory = []
+        if embed_vecs is None:  # stand-in for GloVe-6B-200d (tools/utils/word_vectors.py), seeded
+            embed_vecs = torch.randn(len(obj_classes), 200, generator=torch.Generator().manual_seed(len(obj_classes)))
+        self.object_classifier = ObjectClassifier(mode=mode, obj_classes=obj_classes, obj_head=obj_head,
+                                                  mem_compute=obj_mem_compute, K=K, selection=selection,
+                                                  selection_lambda=self.selection_lambda, tracking=tracking,
+                                                  embed_vecs=embed_vecs)
+        self.union_func1 = nn.Conv2d(1024, 256, 1, 1)
+        self.conv = nn.Sequential(
+            nn.Conv2d(2, 256 // 2, kernel_size=7, stride=2, padding=3, bias=True), nn.ReLU(inplace=True),
+            nn.BatchNorm2d(256 // 2, momentum=0.01), nn.MaxPool2d(kernel_size=3, stride=2, padding=1),
+            nn.Conv2d(256 // 2, 256, kernel_size=3, stride=1, padding=1, bias=True), nn.ReLU(inplace=True),
+            nn.BatchNorm2d(256, momentum=0.01))
+        self.subj_fc = nn.Linear(2048, 512)
+        self.obj_fc = nn.Linear(2048, 512)
+        self.vr_fc = nn.Linear(256 * 7 * 7, 512)
+        self.obj_embed = nn.Embedding(len(obj_classes), 200)
+        self.obj_embed.weight.data = embed_vecs.clone()
+        self.obj_embed2 = nn.Embedding(len(obj_classes), 200)
+        self.obj_embed2.weight.data = embed_vecs.clone()
+        self.glocal_transformer = _STTran(enc_layer_num, dec_layer_num, D_MODEL, N_HEADS, FFN_DIM, 0.1, "latter",
+                                          rel_mem_compute, mem_fusion, selection, self.selection_lambda)
+        self.a_rel_compress = GMMHead(D_MODEL, attention_class_num, "attention", K)
+        self.s_rel_compress = GMMHead(D_MODEL, spatial_class_num, "spatial", K)
+        self.c_rel_compress = GMMHead(D_MODEL, contact_class_num, "contact", K)
+        # knobs that are not part of the reference API
+        self.dropout_p = 0.1            # nn.Dropout(0.1) / MHA dropout=0.1 everywhere in transformer.py
+        self.gmm_eps = None             # dict head -> [K,N,C] noise to inject (parity tests); None = device RNG
+        self.last_plan = None
+
+    # ------------------------------------------------------------------------------------------
+    def _conv_branch(self, masks, plan):
+        """P4 (lib/tempura.py:466-474) — torch/cuDNN ops, BatchNorm statistics per video."""
+        c = self.conv
+        x = F.relu(c[0](masks))
+        x = _per_video_batchnorm(x, c[2], self.training, plan.video_of_pair, plan.pairs_per_video)
+        x = c[3](x)
+        x = F.relu(c[4](x))
+        return _per_video_batchnorm(x, c[6], self.training, plan.video_of_pair, plan.pairs_per_video)
+
+    def _path_params(self):
+        g = self.glocal_transformer
+        ps = [self.subj_fc.weight, self.subj_fc.bias, self.obj_fc.weight, self.obj_fc.bias, self.union_func1.weight,
+              self.union_func1.bias, self.vr_fc.weight, self.vr_fc.bias, self.obj_embed.weight, self.obj_embed2.weight,
+              g.position_embedding.weight]
+        for l in g.local_attention.layers:
+            ps += [l.self_attn.in_proj_weight, l.self_attn.in_proj_bias, l.self_attn.out_proj.weight,
+                   l.self_attn.out_proj.bias, l.linear1.weight, l.linear1.bias, l.linear2.weight, l.linear2.bias,
+                   l.norm1.weight, l.norm1.bias, l.norm2.weight, l.norm2.bias]
+        for l in g.global_attention.layers:
+            ps += [l.multihead2.in_proj_weight, l.multihead2.in_proj_bias, l.multihead2.out_proj.weight,
+                   l.multihead2.out_proj.bias, l.linear1.weight, l.linear1.bias, l.linear2.weight, l.linear2.bias,
+                   l.norm3.weight, l.norm3.bias]
+        return ps
+
+    def _hallucinate(self, feat):
+        """memory_hallucinator (tools/utils/transformer.py:143-175), joint memory, late fusion."""
+        g = self.glocal_transformer
+        if not (g.mem_compute and g.mem_fusion == "late") or len(self.rel_memory) == 0:
+            return feat
+        bank = torch.cat([v for _, v in self.rel_memory.items()], 0).to(feat.device, torch.float32)
+        D = D_MODEL
+        w = g.mem_attention.in_proj_weight
+        q = _GemmNT.apply(feat, w[:D])
+        k = _GemmNT.apply(bank, w[D:2 * D])
+        v = _GemmNT.apply(bank, w[2 * D:])
+        s = _GemmNT.apply(q, k) * (1.0 / math.sqrt(D))
+        p = torch.softmax(s, -1)
+        pad = (-p.shape[1]) % 8
+        o = _GemmNT.apply(F.pad(p, (0, pad)), F.pad(v, (0, 0, 0, pad)).t().contiguous())
+        mem = _GemmNT.apply(o, g.mem_attention.out_proj.weight)
+        e = g.selector if g.selection == "manual" else g.selector(feat).sigmoid()
+        return e * feat + (1 - e) * mem
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, entry, phase="train", unc=False):
+        entry = self.object_classifier(entry, phase=phase, unc=unc)
+        feats = entry["features"]
+        if not feats.is_cuda:
+            raise RuntimeError("b200vsgg.TEMPURA runs only on CUDA tensors (no CPU fallback for the hot path)")
+        fpv = entry.get("video_frames")
+        if fpv is None and "human_idx" in entry:
+            fpv = np.asarray([entry["human_idx"].shape[0]])
+        plan = entry.get("segment_plan")
+        if plan is None:
+            plan = plan_from_im_idx(entry["im_idx"], fpv, entry.get("frame_counts_host")).to(feats.device)
+        self.last_plan = plan
+
+        cm = self._conv_branch(entry["spatial_masks"], plan)                 # [N,256,7,7] fp32 (autograd)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._path_params())
+        runner = _PathRunner(self, entry, plan, train_dropout=self.training, save=need_grad)
+        out, local = _PathFn.apply(runner, cm, *self._path_params())
+        mixed = self._hallucinate(out)
+        g = self.glocal_transformer
+        if g.mem_compute and g.mem_fusion == "late":
+            rel_features, mem_features = out, mixed
+        else:
+            rel_features = mem_features = local
+        entry["obj_class"] = entry["pred_labels"][entry["pair_idx"][:, 1]]
+        entry["rel_features"] = rel_features
+        entry["rel_mem_features"] = mem_features
+
+        heads = [self.a_rel_compress, self.s_rel_compress, self.c_rel_compress]
+        packed = [h.packed() for h in heads]
+        Wp = torch.cat([w for w, _ in packed], 0)
+        bp = torch.cat([b for _, b in packed], 0)
+        mode = 2 if unc else (1 if phase == "train" else 0)
+        eps = self.gmm_eps or {}
+        eps_list = [eps.get(n) for n in ("attention", "spatial", "contacting")]
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        res = _HeadsFn.apply(mixed, Wp, bp, mode, self.GMM_K, [h.num_classes for h in heads],
+                             [h.softmax for h in heads], eps_list, seed)
+        if not unc:
+            entry["attention_distribution"], entry["spatial_distribution"], entry["contacting_distribution"] = res[:3]
+        else:
+            (entry["attention_al_uc"], entry["spatial_al_uc"], entry["contacting_al_uc"],
+             entry["attention_ep_uc"], entry["spatial_ep_uc"], entry["contacting_ep_uc"]) = res
+        return entry
+
+
+# ================================================================================================
+# heads: packed GEMM + fused mixture epilogue
+# ================================================================================================
+class _HeadsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, Wp, bp, mode, K, Cs, softmaxes, eps_list, seed):
+        N = feat.shape[0]
+        cols = Wp.shape[0]
+        cols_pad = (cols + HEAD_COLS_PAD - 1) // HEAD_COLS_PAD * HEAD_COLS_PAD
+        dev = feat.device
+        fb = ops.cast_bf16(feat.contiguous())
+        Wb = torch.zeros(cols_pad, Wp.shape[1], device=dev, dtype=torch.bfloat16)
+        ops.cast_bf16(Wp.contiguous(), out=Wb[:cols])
+        bias = torch.zeros(cols_pad, device=dev)
+        bias[:cols] = bp
+        z = torch.empty(N, cols_pad, device=dev)
+        ops.gemm(fb, Wb, bias=bias, out_f32=z)
+        bases, b = [], 0
+        for C in Cs:
+            bases.append(b)
+            b += K * (2 * C + 1)
+        outs = [torch.empty(N, C, device=dev) for C in Cs]
+        outs2 = [torch.empty(N, C, device=dev) for C in Cs] if mode == 2 else [None] * len(Cs)
+        eps_dev = [e.to(dev, torch.float32).contiguous() if e is not None else None for e in eps_list]
+        specs = [dict(col_base=bases[i], num_classes=Cs[i], softmax=softmaxes[i], eps=eps_dev[i], out=outs[i],
+                      out2=outs2[i]) for i in range(len(Cs))]
+        ops.gmm_head_fwd(z, K, specs, mode, seed)
+        ctx.save_for_backward(fb, Wb, z)
+        ctx.meta = (mode, K, Cs, softmaxes, eps_dev, seed, bases, cols, cols_pad)
+        if mode == 2:
+            ctx.mark_non_differentiable(*outs, *outs2)
+            return (*outs, *outs2)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        fb, Wb, z = ctx.saved_tensors
+        mode, K, Cs, softmaxes, eps_dev, seed, bases, cols, cols_pad = ctx.meta
+        N = fb.shape[0]
+        dev = fb.device
+        douts = [(g if g is not None else torch.zeros(N, C, device=dev)).contiguous().float()
+                 for g, C in zip(grads, Cs)]
+        specs = [dict(col_base=bases[i], num_classes=Cs[i], softmax=softmaxes[i], eps=eps_dev[i], dout=douts[i])
+                 for i in range(len(Cs))]
+        dz = torch.empty(N, cols_pad, device=dev, dtype=torch.bfloat16)
+        ops.gmm_head_bwd(z, K, specs, mode, dz, seed)
+        dfeat = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dfeat = torch.empty(N, Wb.shape[1], device=dev)
+            ops.gemm(dz, Wb, b_mn=True, out_f32=dfeat)
+        if ctx.needs_input_grad[1]:
+            dWp = torch.empty(cols_pad, Wb.shape[1], device=dev)
+            ops.gemm(dz, fb, a_mn=True, b_mn=True, out_f32=dWp)
+            dW = dWp[:cols]
+        if ctx.needs_input_grad[2]:
+            dbp = torch.zeros(1, cols_pad, device=dev)
+            ops.colsum(dz, dbp)
+            db = dbp[0, :cols]
+        return dfeat, dW, db, None, None, None, None, None, None
+
+
+# ================================================================================================
+# the pair-token + spatial/temporal transformer path (hand-orchestrated forward and backward)
+# ================================================================================================
+class _PathFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, cm, *params):
+        out, local = runner.forward(cm, params)
+        ctx.runner = runner
+        ctx.mark_non_differentiable(local)
+        return out, local
+
+    @staticmethod
+    def backward(ctx, d_out, _d_local):
+        runner = ctx.runner
+        needs = ctx.needs_input_grad
+        d_cm, grads = runner.backward(d_out.contiguous(), need_cm=needs[1], need_params=needs[2:])
+        ctx.runner = None
+        return (None, d_cm, *grads)
+
+
+class _PathRunner:
+    """Launch sequence of one forward (and its backward) over libb200vsgg kernels.  Holds the saved
+    activations; one instance per model call."""
+
+    def __init__(self, model, entry, plan, train_dropout, save):
+        self.model, self.entry, self.plan = model, entry, plan
+        self.p = model.dropout_p if train_dropout else 0.0
+        self.save = save
+        self.seed0 = int(torch.randint(0, 2 ** 40, (1,)).item()) if self.p > 0 else 0
+        self.n_enc = len(model.glocal_transformer.local_attention.layers)
+        self.n_dec = len(model.glocal_transformer.global_attention.layers)
+        self.saved = {}
+
+    def _seed(self, site):
+        return self.seed0 + 7919 * site
+
+    # -------------------------------------------------------------------------- parameter views
+    def _unpack(self, params):
+        it = iter(params)
+        P = {}
+        for n in ("subj_w", "subj_b", "obj_w", "obj_b", "union_w", "union_b", "vr_w", "vr_b", "emb1", "emb2", "pos"):
+            P[n] = next(it)
+        P["enc"] = [dict(zip(("in_w", "in_b", "out_w", "out_b", "w1", "b1", "w2", "b2", "g1", "be1", "g2", "be2"),
+                             [next(it) for _ in range(12)])) for _ in range(self.n_enc)]
+        P["dec"] = [dict(zip(("in_w", "in_b", "out_w", "out_b", "w1", "b1", "w2", "b2", "g3", "be3"),
+                             [next(it) for _ in range(10)])) for _ in range(self.n_dec)]
+        return P
+
+    @staticmethod
+    def _bf(w):
+        return ops.cast_bf16(w.detach().reshape(w.shape[0], -1).contiguous())
+
+    # ------------------------------------------------------------------------------ forward
+    def forward(self, cm, params):
+        P = self._unpack(params)
+        e, plan, S = self.entry, self.plan, self.saved
+        dev = e["features"].device
+        N, M2, p = plan.N, plan.M2, self.p
+        bf16, f32 = torch.bfloat16, torch.float32
+        new = lambda r, c, dt: torch.empty(r, c, device=dev, dtype=dt)
+
+        # ---- weights in bf16 (K-major [out, in]); the same copies serve dgrad via MN-major B
+        W = {"so": self._bf(torch.cat([P["subj_w"], P["obj_w"]], 0)),
+             "union": self._bf(P["union_w"]),
+             # vr_fc consumes vr in (h, w, c) order instead of the reference's (c, h, w): permute columns
+             "vr": self._bf(P["vr_w"].detach().view(512, 256, 49).permute(0, 2, 1).reshape(512, 12544))}
+        b_so = torch.cat([P["subj_b"], P["obj_b"]]).detach()
+        for i, L in enumerate(P["enc"] + P["dec"]):
+            for n in ("in_w", "out_w", "w1", "w2"):
+                W["%d%s" % (i, n)] = self._bf(L[n])
+        S["W"] = W
+
+        # ---- P1/P2: subj_fc|obj_fc over all boxes, then gather  (lib/tempura.py:537-544)
+        featb = ops.cast_bf16(e["features"].contiguous())
+        so = new(featb.shape[0], 1024, f32)
+        ops.gemm(featb, W["so"], bias=b_so, out_f32=so)
+        # ---- P3: union_func1 as GEMM over NHWC rows, mask branch added in the epilogue (:548)
+        ub = ops.nchw_to_nhwc_bf16(e["union_feat"].contiguous())
+        cm_rows = ops.nchw_to_nhwc_f32(cm.detach().contiguous())
+        vrp = new(N * 49, 256, bf16)
+        ops.gemm(ub, W["union"], bias=P["union_b"].detach(), residual=cm_rows, out_bf16=vrp)
+        # ---- P5: vr_fc straight into the token buffer (:549)
+        tok = new(N, D_MODEL, f32)
+        tokb = new(N, D_MODEL, bf16)
+        ops.gemm(vrp.view(N, 12544), W["vr"], bias=P["vr_b"].detach(), out_f32=tok[:, 1024:1536])
+        # ---- P6: gather + label embeddings + concat (:554-563)
+        ops.pair_concat_fwd(so, e["pair_idx"].contiguous(), e["pred_labels"].contiguous(), P["emb1"].detach().contiguous(),
+                            P["emb2"].detach().contiguous(), tok, tokb)
+        if self.save:
+            S.update(featb=featb, ub=ub, vrp=vrp)
+
+        # ---- T2: spatial encoder, sequences = frames (transformer.py:5-30,195)
+        x32, xb = tok, tokb
+        site = 0
+        for i, L in enumerate(P["enc"]):
+            qkv = new(N, 3 * D_MODEL, bf16)
+            ops.gemm(xb, W["%din_w" % i], bias=L["in_b"].detach(), out_bf16=qkv)
+            ctxb = new(N, D_MODEL, bf16)
+            ops.attn_small_fwd(qkv[:, :D_MODEL], qkv[:, D_MODEL:2 * D_MODEL], qkv[:, 2 * D_MODEL:], plan.frame_off,
+                               plan.F, plan.max_frame_len, N_HEADS, HEAD_DIM, ctxb, p, self._seed(site))
+            u = new(N, D_MODEL, f32)
+            ops.gemm(ctxb, W["%dout_w" % i], bias=L["out_b"].detach(), residual=x32, out_f32=u, dropout_p=p,
+                     seed=self._seed(site + 1))
+            t32, tb = new(N, D_MODEL, f32), new(N, D_MODEL, bf16)
+            m1, r1 = torch.empty(N, device=dev), torch.empty(N, device=dev)
+            ops.layernorm_fwd(u, L["g1"].detach(), L["be1"].detach(), 1e-5, t32, tb, mean=m1, rstd=r1)
+            h = new(N, FFN_DIM, bf16)
+            ops.gemm(tb, W["%dw1" % i], bias=L["b1"].detach(), act=ops.ACT_RELU, out_bf16=h, dropout_p=p,
+                     seed=self._seed(site + 2))
+            v = new(N, D_MODEL, f32)
+            ops.gemm(h, W["%dw2" % i], bias=L["b2"].detach(), residual=t32, out_f32=v, dropout_p=p,
+                     seed=self._seed(site + 3))
+            y32, yb = new(N, D_MODEL, f32), new(N, D_MODEL, bf16)
+            m2, r2 = torch.empty(N, device=dev), torch.empty(N, device=dev)
+            ops.layernorm_fwd(v, L["g2"].detach(), L["be2"].detach(), 1e-5, y32, yb, mean=m2, rstd=r2)
+            if self.save:
+                S["enc%d" % i] = dict(xb=xb, qkv=qkv, ctxb=ctxb, u=u, m1=m1, r1=r1, tb=tb, h=h, v=v, m2=m2, r2=r2,
+                                      site=site)
+            x32, xb = y32, yb
+            site += 4
+        local = x32
+
+        # ---- T3: 2-frame windows + position embedding (transformer.py:203-215)
+        pos = P["pos"].detach().contiguous()
+        g32, gb, gpb = new(M2, D_MODEL, f32), new(M2, D_MODEL, bf16), new(M2, D_MODEL, bf16)
+        ops.gather_rows(local, plan.win_src, add_table=pos, add_idx=plan.win_pos, out_f32=g32, out_bf16=gb,
+                        out_bf16_added=gpb)
+        # ---- T4: temporal decoder, sequences = windows (transformer.py:33-58,220)
+        for j, L in enumerate(P["dec"]):
+            i = self.n_enc + j
+            qkv = new(M2, 3 * D_MODEL, bf16)
+            in_b = L["in_b"].detach()
+            ops.gemm(gpb, W["%din_w" % i][:2 * D_MODEL], bias=in_b[:2 * D_MODEL], out_bf16=qkv[:, :2 * D_MODEL])
+            ops.gemm(gb, W["%din_w" % i][2 * D_MODEL:], bias=in_b[2 * D_MODEL:], out_bf16=qkv[:, 2 * D_MODEL:])
+            ctxb = new(M2, D_MODEL, bf16)
+            ops.attn_small_fwd(qkv[:, :D_MODEL], qkv[:, D_MODEL:2 * D_MODEL], qkv[:, 2 * D_MODEL:], plan.win_off,
+                               plan.W, plan.max_win_len, N_HEADS, HEAD_DIM, ctxb, p, self._seed(site))
+            u = new(M2, D_MODEL, f32)
+            ops.gemm(ctxb, W["%dout_w" % i], bias=L["out_b"].detach(), residual=g32, out_f32=u, dropout_p=p,
+                     seed=self._seed(site + 1))
+            t32, tb = new(M2, D_MODEL, f32), new(M2, D_MODEL, bf16)
+            m3, r3 = torch.empty(M2, device=dev), torch.empty(M2, device=dev)
+            ops.layernorm_fwd(u, L["g3"].detach(), L["be3"].detach(), 1e-5, t32, tb, mean=m3, rstd=r3)
+            h = new(M2, FFN_DIM, bf16)
+            ops.gemm(tb, W["%dw1" % i], bias=L["b1"].detach(), act=ops.ACT_RELU, out_bf16=h, dropout_p=p,
+                     seed=self._seed(site + 2))
+            y32 = new(M2, D_MODEL, f32)
+            ops.gemm(h, W["%dw2" % i], bias=L["b2"].detach(), residual=t32, out_f32=y32, dropout_p=p,
+                     seed=self._seed(site + 3))
+            if self.save:
+                S["dec%d" % j] = dict(gb=gb, gpb=gpb, qkv=qkv, ctxb=ctxb, u=u, m3=m3, r3=r3, tb=tb, h=h, site=site)
+            g32 = y32
+            if j + 1 < self.n_dec:
+                gb, gpb = new(M2, D_MODEL, bf16), new(M2, D_MODEL, bf16)
+                ops.gather_rows(g32, None, rows=M2, add_table=pos, add_idx=plan.win_pos, out_bf16=gb, out_bf16_added=gpb)
+            site += 4
+        # ---- T5: 'latter' scatter-back as a gather (transformer.py:236-242)
+        out = new(N, D_MODEL, f32)
+        ops.gather_rows(g32, plan.latter_src, out_f32=out)
+        return out, local
+
+    # ------------------------------------------------------------------------------ backward
+    def backward(self, d_out, need_cm, need_params):
+        S, plan, e, model = self.saved, self.plan, self.entry, self.model
+        P = self._unpack(self.model._path_params())
+        W = S["W"]
+        dev = d_out.device
+        N, M2, p = plan.N, plan.M2, self.p
+        bf16, f32 = torch.bfloat16, torch.float32
+        new = lambda r, c, dt: torch.empty(r, c, device=dev, dtype=dt)
+        zeros = lambda *s: torch.zeros(*s, device=dev, dtype=f32)
+        G = {}  # grads by the names of _unpack
+
+        def ffn_and_norm_bwd(dy32, R, L, i, rows, norm_g, norm_mean, norm_rstd, pre_norm, gkey, bkey, site):
+            """Backward of  y = t + drop(W2 drop(relu(W1 t + b1)) + b2),  t = LN(pre_norm).
+            Returns (d_pre_norm fp32, bf16(dropout_mask * d_pre_norm)) and fills weight grads."""
+            dyb = ops.cast_bf16(dy32, drop_p=p, seed=self._seed(site + 3))
+            gL = G.setdefault(i, {})
+            gL["w2"] = new(D_MODEL, FFN_DIM, f32)
+            ops.gemm(dyb, R["h"], a_mn=True, b_mn=True, out_f32=gL["w2"])
+            gL["b2"] = zeros(1, D_MODEL)
+            ops.colsum(dyb, gL["b2"])
+            dz = new(rows, FFN_DIM, bf16)
+            ops.gemm(dyb, W["%dw2" % i], b_mn=True, mask_src=R["h"], mask_mode=ops.MASK_RELU,
+                     alpha=(1.0 / (1.0 - p)) if p > 0 else 1.0, out_bf16=dz)
+            gL["w1"] = new(FFN_DIM, D_MODEL, f32)
+            ops.gemm(dz, R["tb"], a_mn=True, b_mn=True, out_f32=gL["w1"])
+            gL["b1"] = zeros(1, FFN_DIM)
+            ops.colsum(dz, gL["b1"])
+            dt = new(rows, D_MODEL, f32)
+            ops.gemm(dz, W["%dw1" % i], b_mn=True, residual=dy32, out_f32=dt)
+            du = new(rows, D_MODEL, f32)
+            dub = new(rows, D_MODEL, bf16)
+            gL[gkey], gL[bkey] = zeros(D_MODEL), zeros(D_MODEL)
+            ops.layernorm_bwd(dt, pre_norm, L[norm_g].detach(), norm_mean, norm_rstd, du, dub, p, self._seed(site + 1),
+                              gL[gkey], gL[bkey])
+            return du, dub
+
+        def attn_block_bwd(du, dub, R, L, i, rows, seg_off, n_seg, max_len, site):
+            """Backward of u = x + drop(Wo attn(q,k,v) + bo); returns dqkv bf16 [rows, 3D]."""
+            gL = G[i]
+            gL["out_w"] = new(D_MODEL, D_MODEL, f32)
+            ops.gemm(dub, R["ctxb"], a_mn=True, b_mn=True, out_f32=gL["out_w"])
+            gL["out_b"] = zeros(1, D_MODEL)
+            ops.colsum(dub, gL["out_b"])
+            dctx = new(rows, D_MODEL, bf16)
+            ops.gemm(dub, W["%dout_w" % i], b_mn=True, out_bf16=dctx)
+            qkv = R["qkv"]
+            dqkv = new(rows, 3 * D_MODEL, bf16)
+            ops.attn_small_bwd(qkv[:, :D_MODEL], qkv[:, D_MODEL:2 * D_MODEL], qkv[:, 2 * D_MODEL:], dctx, seg_off, n_seg,
+                               max_len, N_HEADS, HEAD_DIM, dqkv[:, :D_MODEL], dqkv[:, D_MODEL:2 * D_MODEL],
+                               dqkv[:, 2 * D_MODEL:], p, self._seed(site))
+            gL["in_b"] = zeros(1, 3 * D_MODEL)
+            ops.colsum(dqkv, gL["in_b"])
+            return dqkv
+
+        # ---- T5 backward: scatter d_out into window-token rows
+        dy = new(M2, D_MODEL, f32)
+        ops.gather2_sum_rows(d_out, plan.inv_latter2, out_f32=dy)
+        # ---- T4 backward
+        dpos_qk = zeros(2, 2 * D_MODEL)  # per layer: column sums of [dq|dk] grouped by position id
+        G["pos"] = zeros(2, D_MODEL)
+        for j in reversed(range(self.n_dec)):
+            i = self.n_enc + j
+            L, R = P["dec"][j], S["dec%d" % j]
+            site = R["site"]
+            du, dub = ffn_and_norm_bwd(dy, R, L, i, M2, "g3", R["m3"], R["r3"], R["u"], "g3", "be3", site)
+            dqkv = attn_block_bwd(du, dub, R, L, i, M2, plan.win_off, plan.W, plan.max_win_len, site)
+            gL = G[i]
+            gL["in_w"] = new(3 * D_MODEL, D_MODEL, f32)
+            ops.gemm(dqkv[:, :2 * D_MODEL], R["gpb"], a_mn=True, b_mn=True, out_f32=gL["in_w"][:2 * D_MODEL])
+            ops.gemm(dqkv[:, 2 * D_MODEL:], R["gb"], a_mn=True, b_mn=True, out_f32=gL["in_w"][2 * D_MODEL:])
+            # position embedding: d pos[k] = (sum over tokens with position k of [dq|dk]) @ W_qk
+            dpos_qk.zero_()
+            ops.colsum(dqkv[:, :2 * D_MODEL], dpos_qk, plan.win_pos, 2)
+            dposb = torch.zeros(8, 2 * D_MODEL, device=dev, dtype=bf16)
+            ops.cast_bf16(dpos_qk, out=dposb[:2])
+            dpos_l = new(8, D_MODEL, f32)
+            ops.gemm(dposb, W["%din_w" % i][:2 * D_MODEL], b_mn=True, out_f32=dpos_l)
+            G["pos"] += dpos_l[:2]
+            dx = new(M2, D_MODEL, f32)
+            ops.gemm(dqkv, W["%din_w" % i], b_mn=True, residual=du, out_f32=dx)
+            dy = dx
+        # ---- T3 backward: each pair row was read by <= 2 windows
+        dlocal = new(N, D_MODEL, f32)
+        ops.gather2_sum_rows(dy, plan.pair_win2, out_f32=dlocal)
+        # ---- T2 backward
+        dy = dlocal
+        for i in reversed(range(self.n_enc)):
+            L, R = P["enc"][i], S["enc%d" % i]
+            site = R["site"]
+            # y = LN2(v): first undo norm2
+            G.setdefault(i, {})
+            dv = new(N, D_MODEL, f32)
+            G[i]["g2"], G[i]["be2"] = zeros(D_MODEL), zeros(D_MODEL)
+            ops.layernorm_bwd(dy, R["v"], L["g2"].detach(), R["m2"], R["r2"], dv, None, 0.0, 0, G[i]["g2"], G[i]["be2"])
+            du, dub = ffn_and_norm_bwd(dv, R, L, i, N, "g1", R["m1"], R["r1"], R["u"], "g1", "be1", site)
+            dqkv = attn_block_bwd(du, dub, R, L, i, N, plan.frame_off, plan.F, plan.max_frame_len, site)
+            G[i]["in_w"] = new(3 * D_MODEL, D_MODEL, f32)
+            ops.gemm(dqkv, R["xb"], a_mn=True, b_mn=True, out_f32=G[i]["in_w"])
+            dx = new(N, D_MODEL, f32)
+            ops.gemm(dqkv, W["%din_w" % i], b_mn=True, residual=du, out_f32=dx)
+            dy = dx
+        dtok = dy
+        # ---- P6/P1 backward
+        O = S["featb"].shape[0]
+        dso = zeros(O, 1024)
+        G["emb1"], G["emb2"] = zeros(*P["emb1"].shape), zeros(*P["emb2"].shape)
+        ops.pair_concat_bwd(dtok, e["pair_idx"].contiguous(), e["pred_labels"].contiguous(), dso, G["emb1"], G["emb2"])
+        dsob = ops.cast_bf16(dso)
+        gso = new(1024, 2048, f32)
+        ops.gemm(dsob, S["featb"], a_mn=True, b_mn=True, out_f32=gso)
+        bso = zeros(1, 1024)
+        ops.colsum(dsob, bso)
+        G["subj_w"], G["obj_w"], G["subj_b"], G["obj_b"] = gso[:512], gso[512:], bso[0, :512], bso[0, 512:]
+        # ---- P5 backward
+        dvr = ops.cast_bf16(dtok[:, 1024:1536])
+        gvr = new(512, 12544, f32)
+        ops.gemm(dvr, S["vrp"].view(N, 12544), a_mn=True, b_mn=True, out_f32=gvr)
+        G["vr_w"] = gvr.view(512, 49, 256).permute(0, 2, 1).reshape(512, 12544)
+        G["vr_b"] = zeros(1, 512)
+        ops.colsum(dvr, G["vr_b"])
+        dvrp32 = new(N, 12544, f32)
+        dvrpb = new(N, 12544, bf16)
+        ops.gemm(dvr, W["vr"], b_mn=True, out_f32=dvrp32, out_bf16=dvrpb)
+        # ---- P3 backward (union_feat itself is a frozen detector output: no dgrad)
+        G["union_w"] = new(256, 1024, f32)
+        ops.gemm(dvrpb.view(N * 49, 256), S["ub"], a_mn=True, b_mn=True, out_f32=G["union_w"])
+        G["union_b"] = zeros(1, 256)
+        ops.colsum(dvrpb.view(N * 49, 256), G["union_b"])
+        d_cm = ops.nhwc_to_nchw_f32(dvrp32.view(N * 49, 256), N, 256, (7, 7)) if need_cm else None
+
+        # ---- assemble in _path_params order
+        out = [G["subj_w"], G["subj_b"], G["obj_w"], G["obj_b"], G["union_w"].view(256, 1024, 1, 1), G["union_b"][0],
+               G["vr_w"], G["vr_b"][0], G["emb1"], G["emb2"], G["pos"]]
+        for i in range(self.n_enc):
+            g = G[i]
+            out += [g["in_w"], g["in_b"][0], g["out_w"], g["out_b"][0], g["w1"], g["b1"][0], g["w2"], g["b2"][0],
+                    g["g1"], g["be1"], g["g2"], g["be2"]]
+        for j in range(self.n_dec):
+            g = G[self.n_enc + j]
+            out += [g["in_w"], g["in_b"][0], g["out_w"], g["out_b"][0], g["w1"], g["b1"][0], g["w2"], g["b2"][0],
+                    g["g3"], g["be3"]]
+        out = [g if need else None for g, need in zip(out, need_params)]
+        self.saved = {}
+        return d_cm, out
+
+
+def tempura_loss(pred, plan=None):
+    """The reference trainer's relation losses (TEMPURA_train.py:181-206) on the model output dict;
+    with a batch of videos each loss is the mean over videos of the per-video mean, i.e. exactly the
+    average of the losses the reference would compute video by video."""
+    dist_a, dist_s, dist_c = pred["attention_distribution"], pred["spatial_distribution"], pred["contacting_distribution"]
+    dev = dist_a.device
+    N = dist_a.shape[0]
+    att = torch.tensor([a[0] if isinstance(a, (list, tuple)) else int(a) for a in pred["attention_gt"]], device=dev)
+    spa = torch.zeros(N, dist_s.shape[1])
+    con = torch.zeros(N, dist_c.shape[1])
+    for i in range(N):
+        spa[i, pred["spatial_gt"][i]] = 1
+        con[i, pred["contacting_gt"][i]] = 1
+    spa, con = spa.to(dev), con.to(dev)
+    if plan is None or plan.V == 1:
+        w = torch.full((N,), 1.0 / N, device=dev)
+    else:
+        ppv = torch.as_tensor(plan.pairs_per_video, device=dev, dtype=torch.float32)
+        w = 1.0 / (ppv[plan.video_of_pair] * plan.V)
+    ce = F.cross_entropy(dist_a, att, reduction="none")
+    bs = F.binary_cross_entropy(dist_s, spa, reduction="none").mean(1)
+    bc = F.binary_cross_entropy(dist_c, con, reduction="none").mean(1)
+    return {"attention_relation_loss": (ce * w).sum(), "spatial_relation_loss": (bs * w).sum(),
+            "contacting_relation_loss": (bc * w).sum()}

@@ -1,0 +1,105 @@
+"""Bit-exact check of the segment plan (b200vsgg.plan) against the index artefacts the reference
+builds with Python loops (tools/utils/transformer.py:184-192 padding, :203-215 windows/position ids,
+:236-242 'latter' scatter-back) — restated here loop-for-loop on CPU.  SURVEY.md A.1."""
+import numpy as np
+import pytest
+import torch
+
+from b200vsgg.plan import SegmentPlan, plan_from_im_idx
+
+
+def reference_artifacts(im_idx):
+    """Loop restatement for ONE video; returns pair-row lists per window token etc."""
+    N = im_idx.shape[0]
+    rel_idx = torch.arange(N)
+    b = int(im_idx[-1] + 1)
+    l = int(torch.sum(im_idx == torch.mode(im_idx)[0]))
+    counts = [int(torch.sum(im_idx == i)) for i in range(b)]
+    masks = torch.zeros(b, l, dtype=torch.bool)
+    for i in range(b):
+        masks[i, counts[i]:] = 1
+    idx = -torch.ones(l * 2, b - 1)
+    idx_plus = -torch.ones(l * 2, b - 1, dtype=torch.long)
+    posid = -torch.ones(l * 2, b - 1, dtype=torch.long)
+    for j in range(b - 1):
+        sel = (im_idx == j) + (im_idx == j + 1)
+        n = int(torch.sum(sel))
+        idx[:n, j] = im_idx[sel]
+        idx_plus[:n, j] = rel_idx[sel]
+        posid[:counts[j], j] = 0
+        posid[counts[j]:counts[j] + counts[j + 1], j] = 1
+    # flattened window tokens in (window, slot) order, real slots only
+    win_src, win_pos, win_len = [], [], []
+    for j in range(b - 1):
+        real = idx_plus[:, j] >= 0
+        win_src += idx_plus[real, j].tolist()
+        win_pos += posid[real, j].tolist()
+        win_len.append(int(real.sum()))
+    # 'latter': output row n comes from (window, slot)
+    src_of_pair = {}
+    tok_base = np.concatenate([[0], np.cumsum(win_len)])
+    for j in range(b - 1):
+        if j == 0:
+            slots = torch.nonzero(idx[:, j] == j).flatten().tolist()
+            rows = torch.nonzero(im_idx == j).flatten().tolist()
+            for r, s in zip(rows, slots):
+                src_of_pair[r] = tok_base[j] + s
+        slots = torch.nonzero(idx[:, j] == j + 1).flatten().tolist()
+        rows = torch.nonzero(im_idx == j + 1).flatten().tolist()
+        for r, s in zip(rows, slots):
+            src_of_pair[r] = tok_base[j] + s
+    latter = [src_of_pair[n] for n in range(N)]
+    return dict(counts=counts, l=l, b=b, masks=masks, win_src=win_src, win_pos=win_pos, win_len=win_len, latter=latter)
+
+
+@pytest.mark.parametrize("counts", [[3, 1, 4, 1, 5], [2, 2], [1, 1, 1], [8, 6, 7, 10, 9, 6, 6, 8], [32] * 6])
+def test_plan_single_video_bit_exact(counts):
+    im_idx = torch.repeat_interleave(torch.arange(len(counts)), torch.tensor(counts)).float()
+    ref = reference_artifacts(im_idx)
+    plan = plan_from_im_idx(im_idx)
+    assert plan.counts_h.tolist() == ref["counts"]
+    assert plan.max_frame_len == ref["l"] and plan.F == ref["b"]
+    assert plan.frame_off_h.tolist() == np.concatenate([[0], np.cumsum(ref["counts"])]).tolist()
+    assert plan.win_src_h.tolist() == ref["win_src"]
+    assert plan.win_pos_h.tolist() == ref["win_pos"]
+    assert np.diff(plan.win_off_h).tolist() == ref["win_len"]
+    assert plan.latter_src_h.tolist() == ref["latter"]
+    # spatial key-padding mask [b,l]: col >= count
+    mask = np.arange(plan.max_frame_len)[None, :] >= plan.counts_h[:, None]
+    assert np.array_equal(mask, ref["masks"].numpy())
+    # backward maps are consistent inverses
+    inv = plan.inv_latter2_h
+    for n, t in enumerate(plan.latter_src_h):
+        assert inv[t, 0] == n
+    assert (inv[:, 1] == -1).all() and (inv[:, 0] >= 0).sum() == plan.N
+    for n in range(plan.N):
+        for t in plan.pair_win2_h[n]:
+            if t >= 0:
+                assert plan.win_src_h[t] == n
+    assert (plan.pair_win2_h >= 0).sum() == plan.M2
+
+
+def test_plan_multi_video_equals_concatenation():
+    vids = [[3, 1, 4], [2, 2, 5, 1], [7, 7]]
+    flat = [c for v in vids for c in v]
+    plan = SegmentPlan(flat, [len(v) for v in vids])
+    tok_base, pair_base = 0, 0
+    src, pos, lat = [], [], []
+    for v in vids:
+        p1 = SegmentPlan(v, [len(v)])
+        src += (p1.win_src_h + pair_base).tolist()
+        pos += p1.win_pos_h.tolist()
+        lat += (p1.latter_src_h + tok_base).tolist()
+        tok_base += p1.M2
+        pair_base += p1.N
+    assert plan.win_src_h.tolist() == src and plan.win_pos_h.tolist() == pos and plan.latter_src_h.tolist() == lat
+    assert plan.W == sum(len(v) - 1 for v in vids)
+    assert plan.pairs_per_video.tolist() == [sum(v) for v in vids]
+    assert plan.video_of_pair_h.tolist() == sum([[i] * sum(v) for i, v in enumerate(vids)], [])
+
+
+def test_plan_rejects_empty_frames_and_single_frame_videos():
+    with pytest.raises(AssertionError):
+        SegmentPlan([3, 0, 2], [3])
+    with pytest.raises(AssertionError):
+        SegmentPlan([3, 2, 2], [1, 2])
