@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native relation-classification path (TEMPURA PredCLS fwd+bwd).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+Metric (BASELINE.json): relation pairs / second, PredCLS forward + loss + backward (+ the gradient
+all-reduce when N > 1).  Workload per GPU = BASELINE.json configs[1]: a batch of 64 synthetic
+Action-Genome-shaped videos (32 frames, 6-10 pairs/frame, ~16.4 k pairs); N GPUs each take 64 videos
+(weak scaling; N = 8 is configs[3], 512 videos per step).  One JSON line is printed by rank 0.
+
+  value     pairs/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
+  e2e       pairs/s through the public module API with HOST inputs: every step copies the batch from
+            pinned host memory (double-buffered on a copy stream), runs forward + loss + backward and
+            reads the loss back to the host
+  roofline  the dominant kernel (tcgen05 GEMM): algorithmic 2MNK FLOPs of every GEMM launch in the
+            timed region / CUDA-event duration of those launches, vs MEASURED_PEAKS.json
+  cpu_baseline  oracle/ (CPU restatement of the reference, pinned to it by golden vectors) timed on
+            the box's host cores on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "relation pairs/sec (PredCLS fwd+bwd)"
+UNIT = "pairs/s"
+MODEL_KW = dict(mode="predcls", attention_class_num=3, spatial_class_num=6, contact_class_num=17,
+                enc_layer_num=1, dec_layer_num=3, obj_mem_compute=False, rel_mem_compute="joint",
+                mem_fusion="late", selection="manual", selection_lambda=0.5, take_obj_mem_feat=False,
+                obj_head="gmm", rel_head="gmm", K=6, tracking=False)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--videos", type=int, default=64, help="videos per GPU per step")
+    ap.add_argument("--frames", type=int, default=32)
+    ap.add_argument("--cpu-sample-videos", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gemm-log", default=None, help="write the per-shape GEMM timing table to this file")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle restatement) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(video_indices, frames, steps, warmup, seed=1123):
+    """pairs/s of oracle fwd + loss + bwd, one video per forward like the reference trainer
+    (TEMPURA_train.py:152-225), train mode (dropout + GMM noise on), all host threads."""
+    import torch
+    from b200vsgg import synthetic
+    from oracle.tempura_oracle import TempuraOracle, tempura_losses
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = TempuraOracle(obj_classes=synthetic.ag_object_classes(), dropout=0.1, **MODEL_KW)
+    synthetic.seeded_init_(model, seed)
+    model.train()
+    entries = [synthetic.make_video_entry(i, frames, (6, 10)) for i in video_indices]
+    labels = [synthetic.build_gt_tensors(e) for e in entries]
+    pairs = sum(e["pair_idx"].shape[0] for e in entries)
+
+    def one_pass():
+        for e, (att, spa, con) in zip(entries, labels):
+            model.zero_grad(set_to_none=True)
+            pred = model(dict(e), phase="train")
+            loss = sum(tempura_losses(pred, att, spa, con).values())
+            loss.backward()
+
+    for _ in range(warmup):
+        one_pass()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pass()
+    dt = time.perf_counter() - t0
+    return pairs * steps / dt, dt / steps, pairs, cores, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vids = list(range(args.cpu_sample_videos))
+    rate, sec_per_step, pairs, cores, threads = cpu_reference_rate(vids, args.frames, args.steps, min(args.warmup, 1))
+    sample = ("%d of the %d videos/GPU of the workload (%d pairs) per step, oracle/tempura_oracle.py fwd+loss+bwd, "
+              "fp32, train mode, one video per forward" % (len(vids), args.videos, pairs))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "host_cores": cores},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "TEMPURA PredCLS fwd+bwd, %d synthetic AG videos per GPU (%d frames, 6-10 pairs/frame), "
+                        "BASELINE configs[1]%s" % (args.videos, args.frames,
+                                                   "" if world == 1 else " x %d GPUs (configs[3] at 8)" % world),
+            "videos_per_gpu": args.videos, "frames_per_video": args.frames, "global_videos": args.videos * world,
+            "parallelism": "videos sharded over %d GPU(s); gradient all-reduce only" % world,
+            "l2": "inputs (3.4 GB/step/GPU) exceed the 126 MB L2",
+            "consistency_regulariser": False, "optimizer_in_step": False}
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------
+TENSOR_KEYS = ("boxes", "labels", "scores", "im_idx", "pair_idx", "human_idx", "features", "union_feat", "union_box",
+               "spatial_masks")
+
+
+def build_batch(video_indices, frames, device):
+    """Collated device batch + label tensors + host frame counts (what a loader would hand over)."""
+    import numpy as np
+    import torch
+    from b200vsgg import synthetic, tempura
+    entries = [synthetic.make_video_entry(i, frames, (6, 10), device=device, big_on_device=device)
+               for i in video_indices]
+    gts = [synthetic.build_gt_tensors(e, device) for e in entries]
+    batch = tempura.collate_entries(entries)
+    for k in ("attention_gt", "spatial_gt", "contacting_gt"):
+        batch.pop(k, None)
+    batch["gt_tensors"] = tuple(torch.cat([g[i] for g in gts]) for i in range(3))
+    batch["frame_counts_host"] = torch.bincount(batch["im_idx"].to(torch.int64)).cpu().numpy().astype(np.int64)
+    return batch
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from b200vsgg import ddp, ops, synthetic, tempura
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    # ---- model (random init of the reference architecture) and this rank's shard of videos
+    torch.manual_seed(1123)
+    model = tempura.TEMPURA(obj_classes=synthetic.ag_object_classes(), **MODEL_KW)
+    synthetic.seeded_init_(model, 1123)
+    model = model.to(dev).train()
+    for p in model.object_classifier.parameters():  # frozen in PredCLS, TEMPURA_train.py:106-108
+        p.requires_grad_(False)
+    vids = [rank * args.videos + v for v in range(args.videos)]
+    batch = build_batch(vids, args.frames, dev)
+    n_pairs = int(batch["pair_idx"].shape[0])
+    sync = ddp.GradSync(list(model.parameters())[::-1]) if world > 1 else None
+
+    def run_step(entry):
+        model.zero_grad(set_to_none=True)
+        pred = model(dict(entry), phase="train")
+        losses = tempura.tempura_loss(pred, model.last_plan)
+        loss = losses["attention_relation_loss"] + losses["spatial_relation_loss"] + losses["contacting_relation_loss"]
+        loss.backward()
+        if sync is not None:
+            sync.sync()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ============================== device-resident timing ==============================
+    for _ in range(max(args.warmup, 3)):
+        run_step(batch)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    ops.gemm_profile = []
+    launches0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = run_step(batch)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.launch_count - launches0
+    gemm_prof, ops.gemm_profile = ops.gemm_profile, None
+    clock_info = clocks.stop()
+    total_pairs = sum_over_ranks(float(n_pairs))
+    value = total_pairs * args.steps / (ms_total * 1e-3)
+    loss_val = float(loss.item())
+
+    # ---- roofline of the dominant kernel from the per-launch CUDA events
+    flops = sum(2.0 * M * N * K for (M, N, K, _, _, _, _) in gemm_prof)
+    gemm_ms = sum(a.elapsed_time(b) for (_, _, _, _, _, a, b) in gemm_prof)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained")
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+    if peak is None:
+        peak, peak_src = 1400.0, "fallback of B200_PROFILING.md (sustained ~1.4 PFLOP/s)"
+    achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "vsgg::gemm_bf16_kernel (tcgen05/TMA, all instantiations)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "launches_timed": len(gemm_prof),
+                "gemm_ms_per_step": gemm_ms / args.steps, "gemm_share_of_step": gemm_ms / (e0.elapsed_time(e1)),
+                "gemm_flops_per_step": flops / args.steps}
+    if args.gemm_log and rank == 0:
+        agg = {}
+        for (M, N, K, a_mn, b_mn, a, b) in gemm_prof:
+            r = agg.setdefault((M, N, K, a_mn, b_mn), [0, 0.0])
+            r[0] += 1
+            r[1] += a.elapsed_time(b)
+        with open(args.gemm_log, "w") as f:
+            for (M, N, K, a_mn, b_mn), (cnt, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                f.write(json.dumps({"M": M, "N": N, "K": K, "a_mn": a_mn, "b_mn": b_mn, "launches": cnt,
+                                    "ms_total": ms, "ms_avg": ms / cnt,
+                                    "tflops": 2.0 * M * N * K * cnt / (ms * 1e-3) / 1e12}) + "\n")
+
+    # ============================== end-to-end (host inputs) ==============================
+    e2e = None
+    if not args.no_e2e:
+        host = {k: batch[k].cpu().pin_memory() for k in TENSOR_KEYS if k in batch}
+        gt_host = tuple(t.cpu().pin_memory() for t in batch["gt_tensors"])
+        h2d = sum(t.numel() * t.element_size() for t in host.values()) + sum(t.numel() * t.element_size() for t in gt_host)
+        bufs = []
+        for _ in range(2):
+            bufs.append(({k: torch.empty_like(batch[k]) for k in host}, tuple(torch.empty_like(t) for t in batch["gt_tensors"])))
+        del batch["union_feat"], batch["spatial_masks"]
+        copy_stream = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def issue_copy(slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                dst, gdst = bufs[slot]
+                for k, t in host.items():
+                    dst[k].copy_(t, non_blocking=True)
+                for d, s in zip(gdst, gt_host):
+                    d.copy_(s, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def e2e_loop(n):
+            for s in range(2):
+                consumed[s].record()
+            issue_copy(0)
+            last = None
+            for i in range(n):
+                slot = i & 1
+                if i + 1 < n:
+                    issue_copy(slot ^ 1)
+                torch.cuda.current_stream().wait_event(ready[slot])
+                dst, gdst = bufs[slot]
+                entry = dict(dst)
+                entry["video_frames"] = batch["video_frames"]
+                entry["frame_counts_host"] = batch["frame_counts_host"]
+                entry["gt_tensors"] = gdst
+                loss = run_step(entry)
+                consumed[slot].record()
+                last = float(loss.item())  # device -> host read of the step's result
+            return last
+
+        e2e_loop(max(args.warmup, 3))
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        e2e_loop(args.steps)
+        t1.record()
+        barrier()
+        e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+        e2e = {"value": total_pairs * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+               "how": "model.forward(entry)+loss+backward on pinned-host inputs, H2D double-buffered on a copy stream"}
+
+    # ============================== CPU baseline (rank 0, N = 1) ==============================
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample_vids = vids[:args.cpu_sample_videos]
+        rate, sec, pairs, cores, threads = cpu_reference_rate(sample_vids, args.frames, steps=2, warmup=1)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "host_cores": cores,
+               "sample": "%d of the step's %d videos (%d pairs), 2 timed passes after 1 warm-up, oracle/tempura_oracle.py "
+                         "fwd+loss+bwd fp32 train mode, one video per forward" % (len(sample_vids), args.videos, pairs)}
+
+    if rank == 0:
+        cfg = workload_config(args, world)
+        cfg["pairs_per_step"] = int(total_pairs)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
+                "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "cpu_baseline": cpu, "loss": loss_val,
+                "model_tflops": 1.138e9 * value / 1e12}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -13,6 +13,9 @@ MASK_RELU, MASK_GELU = 1, 2
 
 # Number of kernel launches issued through this module (bench.py reports it as gpu_launches).
 launch_count = 0
+# When set to a list, every GEMM launch appends (M, N, K, a_mn, b_mn, start_event, end_event):
+# bench.py uses it to time the dominant kernel live with CUDA events on the launching stream.
+gemm_profile = None
 
 
 def _stream():
@@ -82,9 +85,16 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, mask_src=Non
     ep.alpha = alpha
     ep.dropout_p = dropout_p
     ep.dropout_seed = seed
+    prof = gemm_profile
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = _lib.lib().b200vsgg_gemm_bf16(_ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn),
                                        M, N, K, C.byref(ep), _stream())
     check(rc, "gemm_bf16")
+    if prof is not None:
+        e1.record()
+        prof.append((M, N, K, int(a_mn), int(b_mn), e0, e1))
     _count()
     return out_f32 if out_f32 is not None else out_bf16
 

@@ -767,13 +767,16 @@ def tempura_loss(pred, plan=None):
     dist_a, dist_s, dist_c = pred["attention_distribution"], pred["spatial_distribution"], pred["contacting_distribution"]
     dev = dist_a.device
     N = dist_a.shape[0]
-    att = torch.tensor([a[0] if isinstance(a, (list, tuple)) else int(a) for a in pred["attention_gt"]], device=dev)
-    spa = torch.zeros(N, dist_s.shape[1])
-    con = torch.zeros(N, dist_c.shape[1])
-    for i in range(N):
-        spa[i, pred["spatial_gt"][i]] = 1
-        con[i, pred["contacting_gt"][i]] = 1
-    spa, con = spa.to(dev), con.to(dev)
+    if "gt_tensors" in pred:  # label tensors prepared by the data loader (same values as below)
+        att, spa, con = pred["gt_tensors"]
+    else:
+        att = torch.tensor([a[0] if isinstance(a, (list, tuple)) else int(a) for a in pred["attention_gt"]], device=dev)
+        spa = torch.zeros(N, dist_s.shape[1])
+        con = torch.zeros(N, dist_c.shape[1])
+        for i in range(N):
+            spa[i, pred["spatial_gt"][i]] = 1
+            con[i, pred["contacting_gt"][i]] = 1
+        spa, con = spa.to(dev), con.to(dev)
     if plan is None or plan.V == 1:
         w = torch.full((N,), 1.0 / N, device=dev)
     else:
