@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-videos", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="1 warm-up + --steps steps, no e2e/cpu (for ncu runs)")
     ap.add_argument("--gemm-log", default=None, help="write the per-shape GEMM timing table to this file")
     return ap.parse_args()
 
@@ -256,7 +257,9 @@ def main():
         return float(t.item())
 
     # ============================== device-resident timing ==============================
-    for _ in range(max(args.warmup, 3)):
+    if args.profile:
+        args.no_e2e = args.no_cpu_baseline = True
+    for _ in range(1 if args.profile else max(args.warmup, 3)):
         run_step(batch)
     clocks = ClockSampler(local_rank)
     barrier()

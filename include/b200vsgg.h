@@ -66,6 +66,11 @@ typedef struct b200vsgg_gemm_epilogue {
     float alpha;
     float dropout_p;          /* 0 = off. keep = hash(seed, m*N+n) >= p, scaled by 1/(1-p) */
     uint64_t dropout_seed;
+    int32_t split_k;          /* 0: automatic split-K for weight-gradient shapes (few tiles, long K; partial sums are
+                                 added atomically into out_f32), 1: never split, >1: forced number of splits */
+    int32_t a_k_period;       /* 0: off. >0 (multiple of 64, K-major A only): A has only a_k_period columns and is
+                                 re-read periodically along K, i.e. D = A * (B[:, 0:p] + B[:, p:2p] + ...)^T — used with
+                                 split-precision weights B = [W_hi | W_lo] so one bf16 activation copy gives ~fp32 products */
 } b200vsgg_gemm_epilogue;
 
 int b200vsgg_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, const void* B, int32_t ldb, int32_t b_mn,
@@ -166,6 +171,34 @@ int b200vsgg_gmm_head_bwd(const float* z, int32_t ldz, int32_t n_rows, int32_t K
 int b200vsgg_nchw_to_nhwc_bf16(const float* in, int32_t n, int32_t channels, int32_t spatial, void* out, void* stream);
 int b200vsgg_nchw_to_nhwc_f32(const float* in, int32_t n, int32_t channels, int32_t spatial, float* out, void* stream);
 int b200vsgg_nhwc_to_nchw_f32(const float* in, int32_t n, int32_t channels, int32_t spatial, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Spatial-mask branch of the pair token (lib/tempura.py:466-474): Conv7x7/s2(2->128)+ReLU+BN2d ->
+ * MaxPool3/s2/p1 -> Conv3x3(128->256)+ReLU+BN2d, channels-last: both convolutions are
+ * b200vsgg_gemm_bf16 calls over im2col rows, BatchNorm statistics are taken per video (the
+ * reference's batch is one video).  All activations bf16 NHWC rows, channels % 8 == 0.
+ */
+/* masks fp32 [n,2,27,27] -> bf16 rows [n*196, ld]; column c*49+kh*7+kw for the 98 taps, zero up to ld (ld>=104). */
+int b200vsgg_mask_im2col(const float* masks, int32_t n, void* out, int32_t ld, void* stream);
+/* Segmented column statistics: chunk table int32 [n_chunks,3] = (row_begin,row_end,group);
+ * sum1[g,c] += sum_r a[r,c]; sum2[g,c] += sum_r a[r,c]*b[r,c] (b, sum2 nullable; b is bf16, or b == a for
+ * sums of squares of either type). */
+int b200vsgg_seg_colstats(const void* a, int32_t a_is_bf16, int32_t lda, const void* b, int32_t ldb, int32_t cols,
+                          const int32_t* chunks, int32_t n_chunks, float* sum1, float* sum2, void* stream);
+/* out[r,c] = bf16(k1[g,c]*a[r,c] + k2[g,c]*b[r,c] + k3[g,c]), zero where relu_mask && b[r,c] <= 0;
+ * g = group_of_unit[r / rows_per_unit]; a (and k1) may be NULL.  BN apply and BN+ReLU backward. */
+int b200vsgg_seg_affine(const void* a, const void* b, const float* k1, const float* k2, const float* k3,
+                        const int32_t* group_of_unit, int64_t rows, int32_t rows_per_unit, int32_t cols,
+                        int32_t relu_mask, void* out, void* stream);
+/* z = maxpool3x3/s2/p1(scale[g,c]*y + shift[g,c]); y bf16 or fp32 [n,hw_in,hw_in,C] -> z bf16 [n,ho,ho,C], ho=(hw_in+1)/2;
+ * argmax u8 [n,ho,ho,C] = kh*3+kw of the first maximum (torch's tie rule). */
+int b200vsgg_bn_pool_fwd(const void* y, int32_t y_is_f32, const float* scale, const float* shift, const int32_t* group_of_unit,
+                         int32_t n, int32_t hw_in, int32_t channels, void* z, uint8_t* argmax, void* stream);
+int b200vsgg_pool_bwd(const void* dz, const uint8_t* argmax, int32_t n, int32_t hw_in, int32_t channels, void* dy,
+                      void* stream);
+/* z bf16 [n,hw,hw,C] -> rows [n*hw*hw, 9*C], column (kh*3+kw)*C+c, padding 1; and its transpose (gather-sum). */
+int b200vsgg_im2col3x3(const void* z, int32_t n, int32_t hw, int32_t channels, void* out, void* stream);
+int b200vsgg_col2im3x3(const void* dcol, int32_t n, int32_t hw, int32_t channels, void* dz, void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,13 @@ SIGNATURES = {
     "b200vsgg_nchw_to_nhwc_bf16": [vp, i32, i32, i32, vp, vp],
     "b200vsgg_nchw_to_nhwc_f32": [vp, i32, i32, i32, vp, vp],
     "b200vsgg_nhwc_to_nchw_f32": [vp, i32, i32, i32, vp, vp],
+    "b200vsgg_mask_im2col": [vp, i32, vp, i32, vp],
+    "b200vsgg_seg_colstats": [vp, i32, i32, vp, i32, i32, vp, i32, vp, vp, vp],
+    "b200vsgg_seg_affine": [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp],
+    "b200vsgg_bn_pool_fwd": [vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp],
+    "b200vsgg_pool_bwd": [vp, vp, i32, i32, i32, vp, vp],
+    "b200vsgg_im2col3x3": [vp, i32, i32, i32, vp, vp],
+    "b200vsgg_col2im3x3": [vp, i32, i32, i32, vp, vp],
 }
 
 

@@ -28,6 +28,8 @@ class GemmEpilogue(C.Structure):
         ("alpha", C.c_float),
         ("dropout_p", C.c_float),
         ("dropout_seed", C.c_uint64),
+        ("split_k", C.c_int32),
+        ("a_k_period", C.c_int32),
     ]
 
 

@@ -63,7 +63,10 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const GemmEpi ep, const int M, const int N, const int K) {
+                 const GemmEpi ep, const int M, const int N, const int K, const int splits, const int kb_per,
+                 const int a_k_period) {
+    // splits > 1: split-K.  Work unit u -> (tile = u % num_tiles, split = u / num_tiles); split s reduces
+    // k-blocks [s*kb_per, min(num_kb, (s+1)*kb_per)) and its epilogue atomically adds into out_f32.
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
 
@@ -84,6 +87,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int num_n = (N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int num_kb = (K + BK - 1) / BK;
+    const int num_units = num_tiles * splits;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tma_a);
@@ -114,16 +118,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int tile = unit % num_tiles, split = unit / num_tiles;
                 const int m0 = (tile / num_n) * BM;
                 const int n0 = (tile % num_n) * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb0 = split * kb_per;
+                const int kb1 = min(num_kb, kb0 + kb_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     if (A_MN == 0) {
-                        ptx::tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m0);
+                        // a_k_period > 0: A repeats along K with that period (split-precision weights
+                        // [W_hi | W_lo] against one copy of the activations)
+                        const int ka = a_k_period > 0 ? (kb * BK) % a_k_period : kb * BK;
+                        ptx::tma_load_2d(sa, &tma_a, &full_bar[stage], ka, m0);
                     } else {
 #pragma unroll
                         for (int c = 0; c < BM / 64; ++c)
@@ -148,11 +158,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int split = unit / num_tiles;
+                const int kb0 = split * kb_per;
+                const int kb1 = min(num_kb, kb0 + kb_per);
                 ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -165,10 +178,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                                                  : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(sb + k * 2048, 64 * BK * 2, 1024)
                                                  : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        ptx::umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        ptx::umma_bf16(tmem_d, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
                     ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
-                    if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[acc]);
+                    if (kb == kb1 - 1) ptx::umma_commit(&tmem_full_bar[acc]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
                 if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
@@ -181,7 +194,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint32_t acc_phase = 0;
         const float inv_keep = ep.dropout_p > 0.f ? 1.0f / (1.0f - ep.dropout_p) : 1.0f;
         const uint32_t drop_thr = ep.dropout_p > 0.f ? static_cast<uint32_t>(ep.dropout_p * 4294967296.0) : 0u;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            const int tile = unit % num_tiles, split = unit / num_tiles;
             const int m0 = (tile / num_n) * BM;
             const int n0 = (tile % num_n) * BN;
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -207,6 +221,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * ep.alpha;
                         const bool full8 = (n + 8 <= N) && ep.vec_ok;
+                        if (splits > 1) {
+                            // split-K partial: bias once (split 0), then atomic accumulation into fp32
+                            if (ep.bias != nullptr && split == 0)
+                                for (int j = 0; j < 8 && n + j < N; ++j) v[j] += __ldg(ep.bias + n + j);
+                            float* op = ep.out_f32 + rowz * ep.ld_f32 + n;
+                            if (full8) {
+                                atomicAdd(reinterpret_cast<float4*>(op), make_float4(v[0], v[1], v[2], v[3]));
+                                atomicAdd(reinterpret_cast<float4*>(op + 4), make_float4(v[4], v[5], v[6], v[7]));
+                            } else {
+                                for (int j = 0; j < 8 && n + j < N; ++j) atomicAdd(op + j, v[j]);
+                            }
+                            continue;
+                        }
                         if (ep.bias != nullptr) {
                             if (full8) {
                                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
@@ -376,11 +403,13 @@ static int num_sms() {
 
 template <int BN, int A_MN, int B_MN>
 static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const GemmEpi& ep,
-                       cudaStream_t stream) {
+                       int split_k, int a_k_period, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     CUtensorMap ta, tb;
     int rc;
-    if (A_MN == 0) rc = make_tmap_bf16(&ta, A, K, M, lda, BK, BM);
+    if (a_k_period < 0 || (a_k_period > 0 && (A_MN != 0 || a_k_period % BK != 0 || K % a_k_period != 0)))
+        return set_error(B200VSGG_ERR_BAD_ARG, "gemm: a_k_period needs K-major A, period % 64 == 0, K % period == 0");
+    if (A_MN == 0) rc = make_tmap_bf16(&ta, A, a_k_period > 0 ? a_k_period : K, M, lda, BK, BM);
     else rc = make_tmap_bf16(&ta, A, M, K, lda, 64, BK);
     if (rc) return rc;
     if (B_MN == 0) rc = make_tmap_bf16(&tb, B, K, N, ldb, BK, BN);
@@ -395,8 +424,28 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, in
         attr_set = true;
     }
     const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, ep, M, N, K);
+    const int num_kb = (K + BK - 1) / BK;
+    // Split-K when the tile count cannot fill the machine and K is long (weight gradients whose
+    // reduction dimension is the token count): plain fp32 output only.
+    int splits = 1;
+    const bool can_split = ep.out_bf16 == nullptr && ep.act == 0 && ep.mask_src == nullptr && ep.residual == nullptr &&
+                           ep.dropout_p == 0.f && ep.out_f32 != nullptr;
+    if (split_k != 1 && can_split && num_tiles * 2 <= num_sms() && num_kb >= 32) {
+        splits = split_k > 1 ? split_k : (2 * num_sms() + num_tiles - 1) / num_tiles;
+        const int max_splits = num_kb / 8;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    }
+    int kb_per = (num_kb + splits - 1) / splits;
+    splits = (num_kb + kb_per - 1) / kb_per;  // no empty split
+    if (splits > 1 && !ep.accumulate) {
+        cudaError_t e = cudaMemset2DAsync(ep.out_f32, static_cast<size_t>(ep.ld_f32) * sizeof(float), 0,
+                                          static_cast<size_t>(N) * sizeof(float), M, stream);
+        if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+    }
+    const int num_units = num_tiles * splits;
+    int grid = num_units < num_sms() ? num_units : num_sms();
+    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, ep, M, N, K, splits, kb_per, a_k_period);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
     return 0;
@@ -443,11 +492,11 @@ extern "C" int b200vsgg_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, cons
     // Tile-N choice: 256-wide tiles when N is large enough to keep the padding waste small.
     const bool wide = (N >= 1024) || (N % 256 == 0);
     if (a_mn == 0 && b_mn == 0)
-        return wide ? launch_gemm<256, 0, 0>(A, lda, B, ldb, M, N, K, ep, s)
-                    : launch_gemm<128, 0, 0>(A, lda, B, ldb, M, N, K, ep, s);
+        return wide ? launch_gemm<256, 0, 0>(A, lda, B, ldb, M, N, K, ep, e->split_k, e->a_k_period, s)
+                    : launch_gemm<128, 0, 0>(A, lda, B, ldb, M, N, K, ep, e->split_k, e->a_k_period, s);
     if (a_mn == 0 && b_mn == 1)
-        return wide ? launch_gemm<256, 0, 1>(A, lda, B, ldb, M, N, K, ep, s)
-                    : launch_gemm<128, 0, 1>(A, lda, B, ldb, M, N, K, ep, s);
-    return wide ? launch_gemm<256, 1, 1>(A, lda, B, ldb, M, N, K, ep, s)
-                : launch_gemm<128, 1, 1>(A, lda, B, ldb, M, N, K, ep, s);
+        return wide ? launch_gemm<256, 0, 1>(A, lda, B, ldb, M, N, K, ep, e->split_k, e->a_k_period, s)
+                    : launch_gemm<128, 0, 1>(A, lda, B, ldb, M, N, K, ep, e->split_k, e->a_k_period, s);
+    return wide ? launch_gemm<256, 1, 1>(A, lda, B, ldb, M, N, K, ep, e->split_k, e->a_k_period, s)
+                : launch_gemm<128, 1, 1>(A, lda, B, ldb, M, N, K, ep, e->split_k, e->a_k_period, s);
 }

@@ -42,7 +42,7 @@ def _count(n=1):
 
 def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, mask_src=None, mask_mode=0,
          act=ACT_NONE, out_f32=None, out_bf16=None, accumulate=False, alpha=1.0,
-         dropout_p=0.0, seed=0):
+         dropout_p=0.0, seed=0, split_k=0, a_k_period=0):
     """D = epilogue(alpha * op(a) @ op(b)^T); see b200vsgg_gemm_bf16 in include/b200vsgg.h.
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] (b_mn=False) or [K,N] (b_mn=True); both
@@ -57,6 +57,9 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, mask_src=Non
         Kb, N = b.shape
     else:
         N, Kb = b.shape
+    if a_k_period:
+        assert not a_mn and K == a_k_period
+        K = Kb
     assert K == Kb, (a.shape, b.shape, a_mn, b_mn)
     ep = GemmEpilogue()
     ep.bias = bias.data_ptr() if bias is not None else None
@@ -85,6 +88,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, mask_src=Non
     ep.alpha = alpha
     ep.dropout_p = dropout_p
     ep.dropout_seed = seed
+    ep.split_k = split_k
+    ep.a_k_period = a_k_period
     prof = gemm_profile
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -198,10 +203,41 @@ def cast_bf16(x, out=None, drop_p=0.0, seed=0):
     return out
 
 
+_uniform_chunks = {}
+
+
+def uniform_chunks(rows, device, chunk_rows=1024):
+    """int32 [n,3] chunk table (row_begin, row_end, group 0) covering `rows` rows (cached)."""
+    key = (rows, chunk_rows, str(device))
+    t = _uniform_chunks.get(key)
+    if t is None:
+        starts = torch.arange(0, rows, chunk_rows, dtype=torch.int32)
+        t = torch.stack([starts, torch.clamp(starts + chunk_rows, max=rows), torch.zeros_like(starts)], 1).contiguous()
+        t = t.to(device)
+        _uniform_chunks[key] = t
+    return t
+
+
+def seg_colstats(a, chunks, sum1, b=None, sum2=None):
+    """sum1[g,:] += column sums of a over the rows of each chunk's group; sum2[g,:] += sums of a*b."""
+    rows, cols = a.shape
+    assert a.stride(1) == 1 and chunks.dtype == torch.int32 and chunks.is_contiguous() and chunks.shape[1] == 3
+    assert sum1.dtype == torch.float32 and sum1.is_contiguous() and sum1.shape[-1] == cols
+    if b is not None:
+        assert (b.dtype == torch.bfloat16 or b is a) and b.stride(1) == 1 and b.shape == a.shape and sum2 is not None
+        assert sum2.dtype == torch.float32 and sum2.is_contiguous()
+    check(_lib.lib().b200vsgg_seg_colstats(_ptr(a), 1 if a.dtype == torch.bfloat16 else 0, a.stride(0), _ptr(b),
+                                            b.stride(0) if b is not None else 0, cols, _ptr(chunks), chunks.shape[0],
+                                            _ptr(sum1), _ptr(sum2), _stream()), "seg_colstats")
+    _count()
+
+
 def colsum(x, out, group_idx=None, n_groups=1):
     """out[g,:] += column sums of x over rows of group g."""
     rows, cols = x.shape
     assert x.stride(1) == 1 and out.dtype == torch.float32 and out.is_contiguous()
+    if group_idx is None and cols % 8 == 0 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0:
+        return seg_colstats(x, uniform_chunks(rows, x.device), out)
     check(_lib.lib().b200vsgg_colsum(_ptr(x), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), rows, cols,
                                       _ptr(group_idx), n_groups, _ptr(out), _stream()), "colsum")
     _count()
@@ -287,3 +323,52 @@ def nhwc_to_nchw_f32(x, n, c, hw_shape):
     check(_lib.lib().b200vsgg_nhwc_to_nchw_f32(_ptr(x), n, c, s, _ptr(out), _stream()), "nhwc_to_nchw_f32")
     _count(max(1, (n + 65534) // 65535))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# spatial-mask branch (lib/tempura.py:466-474), channels-last
+# ------------------------------------------------------------------------------------------------
+def mask_im2col(masks, out):
+    assert masks.dtype == torch.float32 and masks.is_contiguous() and masks.shape[1:] == (2, 27, 27)
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.shape[0] == masks.shape[0] * 196
+    check(_lib.lib().b200vsgg_mask_im2col(_ptr(masks), masks.shape[0], _ptr(out), out.shape[1], _stream()), "mask_im2col")
+    _count()
+
+
+def seg_affine(a, b, k1, k2, k3, group_of_unit, rows_per_unit, out, relu_mask=False):
+    rows, cols = b.shape
+    for t in (a, b, out):
+        assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous())
+    for t in (k1, k2, k3):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.shape[-1] == cols)
+    assert group_of_unit.dtype == torch.int32
+    check(_lib.lib().b200vsgg_seg_affine(_ptr(a), _ptr(b), _ptr(k1), _ptr(k2), _ptr(k3), _ptr(group_of_unit), rows,
+                                          rows_per_unit, cols, int(relu_mask), _ptr(out), _stream()), "seg_affine")
+    _count()
+
+
+def bn_pool_fwd(y, scale, shift, group_of_unit, n, hw_in, channels, z, argmax):
+    assert y.dtype in (torch.bfloat16, torch.float32) and y.is_contiguous()
+    assert z.dtype == torch.bfloat16 and argmax.dtype == torch.uint8
+    assert scale.is_contiguous() and shift.is_contiguous() and group_of_unit.dtype == torch.int32
+    check(_lib.lib().b200vsgg_bn_pool_fwd(_ptr(y), 1 if y.dtype == torch.float32 else 0, _ptr(_f32(scale)), _ptr(_f32(shift)), _ptr(group_of_unit), n, hw_in,
+                                           channels, _ptr(z), _ptr(argmax), _stream()), "bn_pool_fwd")
+    _count()
+
+
+def pool_bwd(dz, argmax, n, hw_in, channels, dy):
+    assert dz.dtype == torch.bfloat16 and dz.is_contiguous() and dy.dtype == torch.bfloat16 and dy.is_contiguous()
+    check(_lib.lib().b200vsgg_pool_bwd(_ptr(dz), _ptr(argmax), n, hw_in, channels, _ptr(dy), _stream()), "pool_bwd")
+    _count()
+
+
+def im2col3x3(z, n, hw, channels, out):
+    assert z.dtype == torch.bfloat16 and z.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    check(_lib.lib().b200vsgg_im2col3x3(_ptr(z), n, hw, channels, _ptr(out), _stream()), "im2col3x3")
+    _count()
+
+
+def col2im3x3(dcol, n, hw, channels, dz):
+    assert dcol.dtype == torch.bfloat16 and dcol.is_contiguous() and dz.dtype == torch.bfloat16 and dz.is_contiguous()
+    check(_lib.lib().b200vsgg_col2im3x3(_ptr(dcol), n, hw, channels, _ptr(dz), _stream()), "col2im3x3")
+    _count()

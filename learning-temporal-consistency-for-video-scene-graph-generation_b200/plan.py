@@ -78,10 +78,30 @@ class SegmentPlan:
         self.inv_latter2_h = inv.astype(i32)
         self.pair_win2_h = np.stack([former_tok, latter_tok], 1).astype(i32)
         self.video_of_pair_h = video_of_frame[frame_of_pair].astype(np.int64)
+        self.video_of_pair32_h = self.video_of_pair_h.astype(i32)
+        self.pair_off_video_h = np.concatenate([[0], np.cumsum(self.pairs_per_video)]).astype(np.int64)
         self.device = None
+        self._chunks = {}
 
     _DEVICE_FIELDS = ("frame_off", "win_off", "win_src", "win_pos", "latter_src", "inv_latter2", "pair_win2",
-                      "video_of_pair")
+                      "video_of_pair32", "video_of_pair")
+
+    def stat_chunks(self, rows_per_pair, chunk_rows=2048):
+        """int32 device table [n_chunks,3] = (row_begin, row_end, video) over the rows of a
+        [N*rows_per_pair, C] activation: every chunk lies inside one video (per-video BatchNorm
+        statistics, SURVEY.md A.3 #9)."""
+        key = (rows_per_pair, chunk_rows)
+        t = self._chunks.get(key)
+        if t is None:
+            rows = []
+            for v in range(self.V):
+                r0 = int(self.pair_off_video_h[v]) * rows_per_pair
+                r1 = int(self.pair_off_video_h[v + 1]) * rows_per_pair
+                starts = np.arange(r0, r1, chunk_rows, dtype=np.int64)
+                rows.append(np.stack([starts, np.minimum(starts + chunk_rows, r1), np.full_like(starts, v)], 1))
+            t = torch.from_numpy(np.concatenate(rows).astype(np.int32)).to(self.device)
+            self._chunks[key] = t
+        return t
 
     def to(self, device):
         """One pinned staging buffer, one H2D copy for all int32 arrays (+ one for the int64 one)."""
@@ -99,6 +119,7 @@ class SegmentPlan:
             setattr(self, n, t.view(h.shape))
             pos += sz
         self.video_of_pair = torch.from_numpy(self.video_of_pair_h).to(device, non_blocking=True)
+        self.pairs_per_video_dev = torch.from_numpy(self.pairs_per_video.astype(np.float32)).to(device, non_blocking=True)
         self.device = device
         return self
 

@@ -11,9 +11,9 @@ N(0,1) rows unless `embed_vecs` is given — there is no network in this environ
 Underneath, every tensor op of the path runs in hand-written sm_100a kernels from
 libb200vsgg.so (ops.py): tcgen05/TMA GEMMs, varlen attention, LayerNorm, gathers, GMM epilogue.
 There is NO CPU or eager-PyTorch fallback: CPU tensors raise.  Extensions over the reference API
-(all optional): a *batch* of videos can be passed (see `collate_entries`), and the P4 mask-conv
-branch (lib/tempura.py:466-474) currently runs through torch/cuDNN ops with per-video BatchNorm
-statistics (documented as not-yet-native in DESIGN.md).
+(all optional): a *batch* of videos can be passed (see `collate_entries`); BatchNorm statistics of
+the mask branch (lib/tempura.py:466-474) are then taken per video, because the reference's batch is
+one video.
 """
 import math
 
@@ -224,30 +224,29 @@ class _GemmNT(torch.autograd.Function):
         return da, db
 
 
-def _per_video_batchnorm(x, bn, training, video_of_pair, pairs_per_video):
-    """BatchNorm2d whose batch statistics are taken per video, because the reference's batch IS one
-    video (A.3 #9 in SURVEY.md).  Running statistics receive the V sequential momentum updates the
-    reference would have applied video by video."""
-    V = len(pairs_per_video)
-    if not training or V == 1:
-        return bn(x)
-    N, C, H, W = x.shape
-    cnt = torch.as_tensor(pairs_per_video, device=x.device, dtype=x.dtype) * (H * W)
-    s1 = torch.zeros(V, C, device=x.device, dtype=x.dtype).index_add_(0, video_of_pair, x.sum((2, 3)))
+def _split_bf16(w):
+    """[rows, k] fp32 -> [rows, 2k] bf16 = (hi | lo) with hi + lo == w to ~2^-17 relative."""
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], 1).contiguous()
+
+
+def _bn_train_stats(s1, s2, cnt, bn):
+    """Per-video BatchNorm statistics from segmented column sums (s1 = sum x, s2 = sum x^2, [V,C]);
+    returns (mean, rstd) and applies the V sequential running-statistics updates the reference would
+    have made video by video (its batch IS one video, SURVEY.md A.3 #9; momentum 0.01)."""
     mean = s1 / cnt[:, None]
-    xc = x - mean[video_of_pair][:, :, None, None]
-    s2 = torch.zeros(V, C, device=x.device, dtype=x.dtype).index_add_(0, video_of_pair, (xc * xc).sum((2, 3)))
-    var = s2 / cnt[:, None]
-    y = xc * torch.rsqrt(var + bn.eps)[video_of_pair][:, :, None, None]
-    y = y * bn.weight[None, :, None, None] + bn.bias[None, :, None, None]
+    var = (s2 / cnt[:, None] - mean * mean).clamp_min_(0.0)
+    rstd = torch.rsqrt(var + bn.eps)
     with torch.no_grad():
+        V = s1.shape[0]
         m = bn.momentum
-        w = m * (1 - m) ** torch.arange(V - 1, -1, -1, device=x.device, dtype=x.dtype)
+        w = m * (1 - m) ** torch.arange(V - 1, -1, -1, device=s1.device, dtype=s1.dtype)
         unb = var * (cnt / (cnt - 1))[:, None]
-        bn.running_mean.mul_((1 - m) ** V).add_((w[:, None] * mean.detach()).sum(0))
-        bn.running_var.mul_((1 - m) ** V).add_((w[:, None] * unb.detach()).sum(0))
+        bn.running_mean.mul_((1 - m) ** V).add_((w[:, None] * mean).sum(0))
+        bn.running_var.mul_((1 - m) ** V).add_((w[:, None] * unb).sum(0))
         bn.num_batches_tracked += V
-    return y
+    return mean, rstd
 
 
 # ================================================================================================
@@ -302,20 +301,12 @@ class TEMPURA(nn.Module):
         self.last_plan = None
 
     # ------------------------------------------------------------------------------------------
-    def _conv_branch(self, masks, plan):
-        """P4 (lib/tempura.py:466-474) — torch/cuDNN ops, BatchNorm statistics per video."""
-        c = self.conv
-        x = F.relu(c[0](masks))
-        x = _per_video_batchnorm(x, c[2], self.training, plan.video_of_pair, plan.pairs_per_video)
-        x = c[3](x)
-        x = F.relu(c[4](x))
-        return _per_video_batchnorm(x, c[6], self.training, plan.video_of_pair, plan.pairs_per_video)
-
     def _path_params(self):
         g = self.glocal_transformer
         ps = [self.subj_fc.weight, self.subj_fc.bias, self.obj_fc.weight, self.obj_fc.bias, self.union_func1.weight,
               self.union_func1.bias, self.vr_fc.weight, self.vr_fc.bias, self.obj_embed.weight, self.obj_embed2.weight,
-              g.position_embedding.weight]
+              g.position_embedding.weight, self.conv[0].weight, self.conv[0].bias, self.conv[2].weight,
+              self.conv[2].bias, self.conv[4].weight, self.conv[4].bias, self.conv[6].weight, self.conv[6].bias]
         for l in g.local_attention.layers:
             ps += [l.self_attn.in_proj_weight, l.self_attn.in_proj_bias, l.self_attn.out_proj.weight,
                    l.self_attn.out_proj.bias, l.linear1.weight, l.linear1.bias, l.linear2.weight, l.linear2.bias,
@@ -359,10 +350,9 @@ class TEMPURA(nn.Module):
             plan = plan_from_im_idx(entry["im_idx"], fpv, entry.get("frame_counts_host")).to(feats.device)
         self.last_plan = plan
 
-        cm = self._conv_branch(entry["spatial_masks"], plan)                 # [N,256,7,7] fp32 (autograd)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._path_params())
         runner = _PathRunner(self, entry, plan, train_dropout=self.training, save=need_grad)
-        out, local = _PathFn.apply(runner, cm, *self._path_params())
+        out, local = _PathFn.apply(runner, *self._path_params())
         mixed = self._hallucinate(out)
         g = self.glocal_transformer
         if g.mem_compute and g.mem_fusion == "late":
@@ -457,8 +447,8 @@ class _HeadsFn(torch.autograd.Function):
 # ================================================================================================
 class _PathFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, runner, cm, *params):
-        out, local = runner.forward(cm, params)
+    def forward(ctx, runner, *params):
+        out, local = runner.forward(params)
         ctx.runner = runner
         ctx.mark_non_differentiable(local)
         return out, local
@@ -467,9 +457,9 @@ class _PathFn(torch.autograd.Function):
     def backward(ctx, d_out, _d_local):
         runner = ctx.runner
         needs = ctx.needs_input_grad
-        d_cm, grads = runner.backward(d_out.contiguous(), need_cm=needs[1], need_params=needs[2:])
+        grads = runner.backward(d_out.contiguous(), need_params=needs[1:])
         ctx.runner = None
-        return (None, d_cm, *grads)
+        return (None, *grads)
 
 
 class _PathRunner:
@@ -492,7 +482,8 @@ class _PathRunner:
     def _unpack(self, params):
         it = iter(params)
         P = {}
-        for n in ("subj_w", "subj_b", "obj_w", "obj_b", "union_w", "union_b", "vr_w", "vr_b", "emb1", "emb2", "pos"):
+        for n in ("subj_w", "subj_b", "obj_w", "obj_b", "union_w", "union_b", "vr_w", "vr_b", "emb1", "emb2", "pos",
+                  "c1_w", "c1_b", "bn1_g", "bn1_b", "c2_w", "c2_b", "bn2_g", "bn2_b"):
             P[n] = next(it)
         P["enc"] = [dict(zip(("in_w", "in_b", "out_w", "out_b", "w1", "b1", "w2", "b2", "g1", "be1", "g2", "be2"),
                              [next(it) for _ in range(12)])) for _ in range(self.n_enc)]
@@ -505,7 +496,109 @@ class _PathRunner:
         return ops.cast_bf16(w.detach().reshape(w.shape[0], -1).contiguous())
 
     # ------------------------------------------------------------------------------ forward
-    def forward(self, cm, params):
+    # ---------------------------------------------------------------- spatial-mask branch (P4)
+    def _bn_tables(self, y, rows_per_pair, bn, gamma, beta, tag):
+        """(scale, shift) [V,C] of the BatchNorm that follows conv+ReLU output `y` (bf16 rows)."""
+        plan, S = self.plan, self.saved
+        C = y.shape[1]
+        if self.model.training:
+            s1 = torch.zeros(plan.V, C, device=y.device)
+            s2 = torch.zeros(plan.V, C, device=y.device)
+            ops.seg_colstats(y, plan.stat_chunks(rows_per_pair), s1, y, s2)
+            cnt = plan.pairs_per_video_dev * float(rows_per_pair)
+            mean, rstd = _bn_train_stats(s1, s2, cnt, bn)
+        else:
+            mean = bn.running_mean[None].expand(plan.V, C)
+            rstd = torch.rsqrt(bn.running_var + bn.eps)[None].expand(plan.V, C)
+            cnt = None
+        scale = (gamma.detach()[None] * rstd).contiguous()
+        shift = (beta.detach()[None] - mean * scale).contiguous()
+        if self.save:
+            S[tag] = (mean.contiguous(), rstd.contiguous(), cnt)
+        return scale, shift
+
+    def _mask_branch_fwd(self, P, W):
+        """lib/tempura.py:466-474 channels-last; returns cm rows [N*49,256] bf16."""
+        e, plan, S, model = self.entry, self.plan, self.saved, self.model
+        dev = e["features"].device
+        N = plan.N
+        bf16 = torch.bfloat16
+        # conv1 decides the max-pool argmax, a discrete choice: it is evaluated to ~fp32 accuracy (the
+        # mask values are exact in bf16; the weights enter as bf16 hi + bf16 lo parts along K) and
+        # pooled from an fp32 copy, so the routing equals the reference's except for fp32-level ties.
+        A1 = torch.empty(N * 196, 128, device=dev, dtype=bf16)
+        ops.mask_im2col(e["spatial_masks"].contiguous(), A1)
+        y1 = torch.empty(N * 196, 128, device=dev, dtype=bf16)
+        y1f = torch.empty(N * 196, 128, device=dev, dtype=torch.float32)
+        ops.gemm(A1, W["c1x"], bias=P["c1_b"].detach(), act=ops.ACT_RELU, out_bf16=y1, out_f32=y1f, a_k_period=128)
+        sc1, sh1 = self._bn_tables(y1f, 196, model.conv[2], P["bn1_g"], P["bn1_b"], "bn1")
+        z = torch.empty(N * 49, 128, device=dev, dtype=bf16)
+        arg = torch.empty(N * 49, 128, device=dev, dtype=torch.uint8)
+        ops.bn_pool_fwd(y1f, sc1, sh1, plan.video_of_pair32, N, 14, 128, z, arg)
+        del y1f
+        A2 = torch.empty(N * 49, 1152, device=dev, dtype=bf16)
+        ops.im2col3x3(z, N, 7, 128, A2)
+        y2 = torch.empty(N * 49, 256, device=dev, dtype=bf16)
+        ops.gemm(A2, W["c2"], bias=P["c2_b"].detach(), act=ops.ACT_RELU, out_bf16=y2)
+        sc2, sh2 = self._bn_tables(y2, 49, model.conv[6], P["bn2_g"], P["bn2_b"], "bn2")
+        cm = torch.empty(N * 49, 256, device=dev, dtype=bf16)
+        ops.seg_affine(None, y2, None, sc2, sh2, plan.video_of_pair32, 49, cm)
+        if self.save:
+            S.update(A1=A1, y1=y1, arg=arg, A2=A2, y2=y2)
+        return cm
+
+    def _bn_relu_bwd(self, dout, y, rows_per_pair, gamma, tag, G, gkey, bkey):
+        """Backward of BN(ReLU-output y) followed by the ReLU mask: returns d(conv output) bf16."""
+        plan = self.plan
+        mean, rstd, cnt = self.saved[tag]
+        C = y.shape[1]
+        s1 = torch.zeros(plan.V, C, device=y.device)
+        s2 = torch.zeros(plan.V, C, device=y.device)
+        ops.seg_colstats(dout, plan.stat_chunks(rows_per_pair), s1, y, s2)
+        sx = (s2 - mean * s1) * rstd                     # sum dout * xhat per (video, channel)
+        G[gkey], G[bkey] = sx.sum(0), s1.sum(0)
+        g = gamma.detach()[None]
+        k1 = (g * rstd).expand(plan.V, C).contiguous()
+        if cnt is not None:                                  # batch statistics (train mode)
+            inv_n = (1.0 / cnt)[:, None]
+            k2 = (-g * rstd * rstd * sx * inv_n).contiguous()
+            k3 = (-g * rstd * s1 * inv_n - k2 * mean).contiguous()
+        else:                                                # running statistics: BN is a fixed affine map
+            k2 = torch.zeros_like(k1)
+            k3 = torch.zeros_like(k1)
+        dconv = torch.empty_like(y)
+        ops.seg_affine(dout, y, k1, k2, k3, plan.video_of_pair32, rows_per_pair, dconv, relu_mask=True)
+        return dconv
+
+    def _mask_branch_bwd(self, dcm, P, W, G):
+        """dcm: bf16 [N*49,256] gradient of the branch output; fills conv / BatchNorm parameter grads."""
+        S, plan = self.saved, self.plan
+        N = plan.N
+        dev = dcm.device
+        bf16, f32 = torch.bfloat16, torch.float32
+        d2 = self._bn_relu_bwd(dcm, S["y2"], 49, P["bn2_g"], "bn2", G, "bn2_g", "bn2_b")
+        gw2 = torch.empty(256, 1152, device=dev, dtype=f32)
+        ops.gemm(d2, S["A2"], a_mn=True, b_mn=True, out_f32=gw2)
+        G["c2_w"] = gw2.view(256, 3, 3, 128).permute(0, 3, 1, 2)
+        gb2 = torch.zeros(1, 256, device=dev)
+        ops.colsum(d2, gb2)
+        G["c2_b"] = gb2[0]
+        dA2 = torch.empty(N * 49, 1152, device=dev, dtype=bf16)
+        ops.gemm(d2, W["c2"], b_mn=True, out_bf16=dA2)
+        dz = torch.empty(N * 49, 128, device=dev, dtype=bf16)
+        ops.col2im3x3(dA2, N, 7, 128, dz)
+        del dA2
+        dpool = torch.empty(N * 196, 128, device=dev, dtype=bf16)
+        ops.pool_bwd(dz, S["arg"], N, 14, 128, dpool)
+        d1 = self._bn_relu_bwd(dpool, S["y1"], 196, P["bn1_g"], "bn1", G, "bn1_g", "bn1_b")
+        gw1 = torch.empty(128, 128, device=dev, dtype=f32)
+        ops.gemm(d1, S["A1"], a_mn=True, b_mn=True, out_f32=gw1)
+        G["c1_w"] = gw1[:, :98].reshape(128, 2, 7, 7)
+        gb1 = torch.zeros(1, 128, device=dev)
+        ops.colsum(d1, gb1)
+        G["c1_b"] = gb1[0]
+
+    def forward(self, params):
         P = self._unpack(params)
         e, plan, S = self.entry, self.plan, self.saved
         dev = e["features"].device
@@ -517,7 +610,11 @@ class _PathRunner:
         W = {"so": self._bf(torch.cat([P["subj_w"], P["obj_w"]], 0)),
              "union": self._bf(P["union_w"]),
              # vr_fc consumes vr in (h, w, c) order instead of the reference's (c, h, w): permute columns
-             "vr": self._bf(P["vr_w"].detach().view(512, 256, 49).permute(0, 2, 1).reshape(512, 12544))}
+             "vr": self._bf(P["vr_w"].detach().view(512, 256, 49).permute(0, 2, 1).reshape(512, 12544)),
+             # conv1 taps in (c, kh, kw) order padded 98 -> 104; conv2 taps in (kh, kw, c) order
+             "c1": self._bf(F.pad(P["c1_w"].detach().reshape(128, 98), (0, 6))),
+             "c1x": _split_bf16(F.pad(P["c1_w"].detach().reshape(128, 98), (0, 30))),
+             "c2": self._bf(P["c2_w"].detach().permute(0, 2, 3, 1).reshape(256, 1152))}
         b_so = torch.cat([P["subj_b"], P["obj_b"]]).detach()
         for i, L in enumerate(P["enc"] + P["dec"]):
             for n in ("in_w", "out_w", "w1", "w2"):
@@ -530,9 +627,10 @@ class _PathRunner:
         ops.gemm(featb, W["so"], bias=b_so, out_f32=so)
         # ---- P3: union_func1 as GEMM over NHWC rows, mask branch added in the epilogue (:548)
         ub = ops.nchw_to_nhwc_bf16(e["union_feat"].contiguous())
-        cm_rows = ops.nchw_to_nhwc_f32(cm.detach().contiguous())
+        cm_rows = self._mask_branch_fwd(P, W)
         vrp = new(N * 49, 256, bf16)
         ops.gemm(ub, W["union"], bias=P["union_b"].detach(), residual=cm_rows, out_bf16=vrp)
+        del cm_rows
         # ---- P5: vr_fc straight into the token buffer (:549)
         tok = new(N, D_MODEL, f32)
         tokb = new(N, D_MODEL, bf16)
@@ -614,7 +712,7 @@ class _PathRunner:
         return out, local
 
     # ------------------------------------------------------------------------------ backward
-    def backward(self, d_out, need_cm, need_params):
+    def backward(self, d_out, need_params):
         S, plan, e, model = self.saved, self.plan, self.entry, self.model
         P = self._unpack(self.model._path_params())
         W = S["W"]
@@ -734,19 +832,20 @@ class _PathRunner:
         G["vr_w"] = gvr.view(512, 49, 256).permute(0, 2, 1).reshape(512, 12544)
         G["vr_b"] = zeros(1, 512)
         ops.colsum(dvr, G["vr_b"])
-        dvrp32 = new(N, 12544, f32)
         dvrpb = new(N, 12544, bf16)
-        ops.gemm(dvr, W["vr"], b_mn=True, out_f32=dvrp32, out_bf16=dvrpb)
+        ops.gemm(dvr, W["vr"], b_mn=True, out_bf16=dvrpb)
         # ---- P3 backward (union_feat itself is a frozen detector output: no dgrad)
         G["union_w"] = new(256, 1024, f32)
         ops.gemm(dvrpb.view(N * 49, 256), S["ub"], a_mn=True, b_mn=True, out_f32=G["union_w"])
         G["union_b"] = zeros(1, 256)
         ops.colsum(dvrpb.view(N * 49, 256), G["union_b"])
-        d_cm = ops.nhwc_to_nchw_f32(dvrp32.view(N * 49, 256), N, 256, (7, 7)) if need_cm else None
+        # ---- P4 backward (the masks are inputs: no dgrad below conv1)
+        self._mask_branch_bwd(dvrpb.view(N * 49, 256), P, W, G)
 
         # ---- assemble in _path_params order
         out = [G["subj_w"], G["subj_b"], G["obj_w"], G["obj_b"], G["union_w"].view(256, 1024, 1, 1), G["union_b"][0],
-               G["vr_w"], G["vr_b"][0], G["emb1"], G["emb2"], G["pos"]]
+               G["vr_w"], G["vr_b"][0], G["emb1"], G["emb2"], G["pos"], G["c1_w"], G["c1_b"], G["bn1_g"], G["bn1_b"],
+               G["c2_w"], G["c2_b"], G["bn2_g"], G["bn2_b"]]
         for i in range(self.n_enc):
             g = G[i]
             out += [g["in_w"], g["in_b"][0], g["out_w"], g["out_b"][0], g["w1"], g["b1"][0], g["w2"], g["b2"][0],
@@ -757,7 +856,7 @@ class _PathRunner:
                     g["g3"], g["be3"]]
         out = [g if need else None for g, need in zip(out, need_params)]
         self.saved = {}
-        return d_cm, out
+        return out
 
 
 def tempura_loss(pred, plan=None):
