@@ -1,0 +1,488 @@
+// Variable-length multi-head attention over SHORT segments (one frame's pairs / one 2-frame window,
+// <= 32 tokens) with head_dim <= 248 — nn.MultiheadAttention of tools/utils/transformer.py:23,50 on
+// exactly the rows the reference keeps.  One WARP owns one (segment, head) unit:
+//   * Q/K/V (and dO) head slices are staged with 16-byte cp.async of the ALIGNED chunks that cover
+//     the head's columns (head_dim 242 puts head h at a 4-byte-aligned offset h*484 B; the chunk
+//     grid is kept, the few foreign columns at either end are zeroed in the contraction operands
+//     and never stored),
+//   * S = QK^T, O = PV (and the five backward products) are warp-level mma.sync m16n8k16 bf16 with
+//     fp32 accumulation, fragments via ldmatrix(.trans); softmax, dropout and the dS algebra stay in
+//     registers with quad shuffles.
+// Why not tcgen05 here: a unit is a 16x16x242 problem (124 kFLOP) and the kernel moves 8*D bytes per
+// token for 4*L*D flops (L/2 flop/byte, 4..16 << the ~210 flop/byte ridge of B200): it is HBM-bound,
+// the tensor pipe is idle either way, and a 128-row UMMA tile would be >85 % padding.  Roofline for
+// this kernel is therefore HBM bytes.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "../../include/b200vsgg.h"
+#include "common.cuh"
+
+namespace vsgg {
+
+constexpr int AM_PITCH_B = 528;   // 33 chunks of 16 B: odd chunk count -> conflict-free ldmatrix
+constexpr int AM_MAX_CH = 32;     // aligned 16-byte chunks per head row (head_dim <= 248)
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float am_drop_factor(uint32_t thr, float inv_keep, unsigned long long seed, int row, int head,
+                                                int j) {
+    if (thr == 0u) return 1.f;
+    const uint32_t h = hash_u32(seed, (static_cast<unsigned long long>(row) * 64ull + head) * 4096ull + j);
+    return h >= thr ? inv_keep : 0.f;
+}
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+struct HeadGeom {
+    int row0, L, col0, c_lo, phase, nch;
+};
+__device__ __forceinline__ bool head_geom(const int32_t* seg_off, int unit, int n_heads, int hd, HeadGeom& g, int& head) {
+    const int seg = unit / n_heads;
+    head = unit - seg * n_heads;
+    g.row0 = __ldg(seg_off + seg);
+    g.L = __ldg(seg_off + seg + 1) - g.row0;
+    g.col0 = head * hd;
+    g.c_lo = g.col0 >> 3;
+    g.phase = g.col0 & 7;
+    g.nch = ((g.col0 + hd - 1) >> 3) - g.c_lo + 1;
+    return g.L > 0;
+}
+
+// Stage rows [row0,row0+L) x aligned chunks [c_lo, c_lo+nch) of `src` into a [LP][33-chunk] tile.
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const __nv_bfloat16* src, int ld, const HeadGeom& g, int lane) {
+    const uint32_t t = s_u32(tile);
+    const int total = g.L * g.nch;
+    for (int i = lane; i < total; i += 32) {
+        const int r = i / g.nch, ch = i - r * g.nch;
+        cp_async16(t + r * AM_PITCH_B + ch * 16, src + static_cast<size_t>(g.row0 + r) * ld + (g.c_lo + ch) * 8);
+    }
+}
+// Zero the foreign columns (before `phase`, after phase+hd) and the next chunk of rows < L, so that a
+// contraction over whole 32-byte k-steps sees zeros outside the head.
+__device__ __forceinline__ void zero_slop(uint8_t* tile, const HeadGeom& g, int hd, int lane) {
+    for (int r = lane; r < g.L; r += 32) {
+        uint32_t* row = reinterpret_cast<uint32_t*>(tile + r * AM_PITCH_B);   // bf16 pairs
+        for (int e = 0; e < g.phase; e += 2) row[e >> 1] = 0u;
+        for (int e = g.phase + hd; e < g.nch * 8; e += 2) row[e >> 1] = 0u;
+        if (g.nch <= AM_MAX_CH) *reinterpret_cast<uint4*>(tile + r * AM_PITCH_B + g.nch * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// acc[mt][nt] += A[rows of m-tile mt] . B[rows of n-tile nt]^T over the d-chunks (both tiles K-major).
+template <int MT, int NT>
+__device__ __forceinline__ void qk_product(float (&acc)[MT][NT][4], const uint8_t* A, const uint8_t* B, int ksteps, int lane) {
+    const uint32_t a_base = s_u32(A) + (lane & 15) * AM_PITCH_B + (lane >> 4) * 16;
+    const uint32_t b_base = s_u32(B) + ((lane & 7) + ((lane >> 4) & 1) * 8) * AM_PITCH_B + ((lane >> 3) & 1) * 16;
+    for (int ks = 0; ks < ksteps; ++ks) {
+        uint32_t a[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) ldsm_x4(a[mt], a_base + mt * 16 * AM_PITCH_B + ks * 32);
+#pragma unroll
+        for (int np = 0; np < NT / 2; ++np) {
+            uint32_t b[4];
+            ldsm_x4(b, b_base + np * 16 * AM_PITCH_B + ks * 32);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                mma_bf16(acc[mt][2 * np], a[mt], b[0], b[1]);
+                mma_bf16(acc[mt][2 * np + 1], a[mt], b[2], b[3]);
+            }
+        }
+    }
+}
+
+// out[rows of m-tile mt][d] = sum_k A_frag[mt][kk] * Bt[k][d] for the d-chunk group dg (4 chunks); Bt is a
+// [k rows][d] tile read with ldmatrix.trans.  Results are scaled and stored as bf16 pairs for rows < L
+// and columns inside the head.
+template <int MT, int KK>
+__device__ __forceinline__ void av_product_store(const uint32_t (&afrag)[MT][KK][4], const uint8_t* Bt, const HeadGeom& g,
+                                                 int hd, float out_scale, __nv_bfloat16* out, int ldo, int lane) {
+    const uint32_t b_base = s_u32(Bt) + (lane & 15) * AM_PITCH_B + (lane >> 4) * 16;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int ngroups = (g.nch + 3) >> 2;
+    for (int dg = 0; dg < ngroups; ++dg) {
+        float o[MT][4][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[mt][j][e] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) {
+#pragma unroll
+            for (int dp = 0; dp < 2; ++dp) {
+                uint32_t b[4];
+                ldsm_x4_t(b, b_base + kk * 16 * AM_PITCH_B + (dg * 4 + dp * 2) * 16);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    mma_bf16(o[mt][dp * 2], afrag[mt][kk], b[0], b[1]);
+                    mma_bf16(o[mt][dp * 2 + 1], afrag[mt][kk], b[2], b[3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gcol = (g.c_lo + dg * 4 + j) * 8 + tq * 2;
+            if (gcol < g.col0 || gcol >= g.col0 + hd) continue;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int r0 = mt * 16 + gq, r1 = r0 + 8;
+                if (r0 < g.L)
+                    *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(g.row0 + r0) * ldo + gcol) =
+                        pack_bf16(o[mt][j][0] * out_scale, o[mt][j][1] * out_scale);
+                if (r1 < g.L)
+                    *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(g.row0 + r1) * ldo + gcol) =
+                        pack_bf16(o[mt][j][2] * out_scale, o[mt][j][3] * out_scale);
+            }
+        }
+    }
+}
+
+// In-register softmax over the key axis of s[mt][nt] (C-fragment layout), keys >= L masked.
+template <int MT, int NT>
+__device__ __forceinline__ void softmax_rows(float (&s)[MT][NT][4], float scale, int L, int lane) {
+    const int tq = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = nt * 8 + tq * 2 + e;
+                    const float v = col < L ? s[mt][nt][half * 2 + e] * scale : -INFINITY;
+                    s[mt][nt][half * 2 + e] = v;
+                    mx = fmaxf(mx, v);
+                }
+            mx = quad_max(mx);
+            float sum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float ex = __expf(s[mt][nt][half * 2 + e] - mx);
+                    s[mt][nt][half * 2 + e] = ex;
+                    sum += ex;
+                }
+            sum = quad_sum(sum);
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) s[mt][nt][half * 2 + e] *= inv;
+        }
+    }
+}
+
+template <int LP>
+__global__ void __launch_bounds__(LP == 16 ? 256 : 128)
+attn_mma_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
+                    const __nv_bfloat16* __restrict__ v, int ldv, const int32_t* __restrict__ seg_off, int n_units,
+                    int n_heads, int hd, float scale, __nv_bfloat16* __restrict__ ctx, int ldc, float drop_p,
+                    unsigned long long seed) {
+    constexpr int MT = LP / 16, NT = LP / 8, KK = LP / 16;
+    constexpr int TILE = LP * AM_PITCH_B;
+    extern __shared__ __align__(16) uint8_t am_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps = blockDim.x >> 5;
+    uint8_t* Qs = am_smem + warp * 3 * TILE;
+    uint8_t* Ks = Qs + TILE;
+    uint8_t* Vs = Ks + TILE;
+    for (int i = lane; i < 3 * TILE / 16; i += 32) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    const int gq = lane >> 2, tq = lane & 3;
+    for (int unit = blockIdx.x * warps + warp; unit < n_units; unit += gridDim.x * warps) {
+        HeadGeom g;
+        int head;
+        if (!head_geom(seg_off, unit, n_heads, hd, g, head)) continue;
+        stage_tile(Qs, q, ldq, g, lane);
+        stage_tile(Ks, k, ldk, g, lane);
+        stage_tile(Vs, v, ldv, g, lane);
+        cp_async_wait_all();
+        __syncwarp();
+        zero_slop(Qs, g, hd, lane);
+        __syncwarp();
+        float s[MT][NT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+        qk_product<MT, NT>(s, Qs, Ks, (g.nch + 1) >> 1, lane);
+        softmax_rows<MT, NT>(s, scale, g.L, lane);
+        uint32_t pa[MT][KK][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int kk = 0; kk < KK; ++kk) {
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int nt = 2 * kk + sub;
+                    float p[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int row = mt * 16 + gq + (e >> 1) * 8, col = nt * 8 + tq * 2 + (e & 1);
+                        p[e] = (row < g.L && col < g.L)
+                                   ? s[mt][nt][e] * am_drop_factor(thr, inv_keep, seed, g.row0 + row, head, col) : 0.f;
+                    }
+                    pa[mt][kk][sub * 2] = pack_bf16(p[0], p[1]);
+                    pa[mt][kk][sub * 2 + 1] = pack_bf16(p[2], p[3]);
+                }
+            }
+        av_product_store<MT, KK>(pa, Vs, g, hd, 1.f, ctx, ldc, lane);
+        __syncwarp();
+    }
+}
+
+// Backward: recompute P; dP~ = dO V^T; dS = P o (f*dP~ - rowsum(P o f*dP~)); dQ = scale dS K;
+// dK = scale dS^T Q; dV = (P o f)^T dO.
+template <int LP>
+__global__ void __launch_bounds__(LP == 16 ? 192 : 96)
+attn_mma_bwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
+                    const __nv_bfloat16* __restrict__ v, int ldv, const __nv_bfloat16* __restrict__ dctx, int ldc,
+                    const int32_t* __restrict__ seg_off, int n_units, int n_heads, int hd, float scale,
+                    __nv_bfloat16* __restrict__ dq, int lddq, __nv_bfloat16* __restrict__ dk, int lddk,
+                    __nv_bfloat16* __restrict__ dv, int lddv, float drop_p, unsigned long long seed) {
+    constexpr int MT = LP / 16, NT = LP / 8, KK = LP / 16;
+    constexpr int TILE = LP * AM_PITCH_B;
+    constexpr int TP = (LP + 8) * 2;            // pitch of the small [LP][LP] bf16 tiles (odd # of 16-B chunks)
+    constexpr int SMALL = LP * TP;
+    constexpr int PER_WARP = 4 * TILE + 2 * SMALL;
+    extern __shared__ __align__(16) uint8_t am_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps = blockDim.x >> 5;
+    uint8_t* Qs = am_smem + warp * PER_WARP;
+    uint8_t* Ks = Qs + TILE;
+    uint8_t* Vs = Ks + TILE;
+    uint8_t* Os = Vs + TILE;
+    uint8_t* Tds = Os + TILE;
+    uint8_t* Tp = Tds + SMALL;
+    for (int i = lane; i < PER_WARP / 16; i += 32) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    const int gq = lane >> 2, tq = lane & 3;
+    for (int unit = blockIdx.x * warps + warp; unit < n_units; unit += gridDim.x * warps) {
+        HeadGeom g;
+        int head;
+        if (!head_geom(seg_off, unit, n_heads, hd, g, head)) continue;
+        stage_tile(Qs, q, ldq, g, lane);
+        stage_tile(Ks, k, ldk, g, lane);
+        stage_tile(Vs, v, ldv, g, lane);
+        stage_tile(Os, dctx, ldc, g, lane);
+        cp_async_wait_all();
+        __syncwarp();
+        zero_slop(Qs, g, hd, lane);
+        zero_slop(Os, g, hd, lane);
+        __syncwarp();
+        const int ksteps = (g.nch + 1) >> 1;
+        float p[MT][NT][4], dp[MT][NT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { p[mt][nt][e] = 0.f; dp[mt][nt][e] = 0.f; }
+        qk_product<MT, NT>(p, Qs, Ks, ksteps, lane);
+        softmax_rows<MT, NT>(p, scale, g.L, lane);
+        qk_product<MT, NT>(dp, Os, Vs, ksteps, lane);
+        // dS and P~ (C layout) -> A fragments for dQ, and bf16 tiles for the transposed products
+        uint32_t dsa[MT][KK][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            float delta[2] = {0.f, 0.f};
+            const int r0 = mt * 16 + gq;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                float pt[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int row = r0 + (e >> 1) * 8, col = nt * 8 + tq * 2 + (e & 1);
+                    const bool ok = row < g.L && col < g.L;
+                    const float f = ok ? am_drop_factor(thr, inv_keep, seed, g.row0 + row, head, col) : 0.f;
+                    const float pe = ok ? p[mt][nt][e] : 0.f;
+                    const float dpe = ok ? dp[mt][nt][e] * f : 0.f;
+                    delta[e >> 1] += pe * dpe;
+                    p[mt][nt][e] = pe;
+                    dp[mt][nt][e] = dpe;
+                    pt[e] = pe * f;
+                }
+                const int c = nt * 8 + tq * 2;
+                *reinterpret_cast<uint32_t*>(Tp + r0 * TP + c * 2) = pack_bf16(pt[0], pt[1]);
+                *reinterpret_cast<uint32_t*>(Tp + (r0 + 8) * TP + c * 2) = pack_bf16(pt[2], pt[3]);
+            }
+            delta[0] = quad_sum(delta[0]);
+            delta[1] = quad_sum(delta[1]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                float ds[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ds[e] = p[mt][nt][e] * (dp[mt][nt][e] - delta[e >> 1]);
+                const uint32_t d01 = pack_bf16(ds[0], ds[1]), d23 = pack_bf16(ds[2], ds[3]);
+                dsa[mt][nt >> 1][(nt & 1) * 2] = d01;
+                dsa[mt][nt >> 1][(nt & 1) * 2 + 1] = d23;
+                const int c = nt * 8 + tq * 2;
+                *reinterpret_cast<uint32_t*>(Tds + r0 * TP + c * 2) = d01;
+                *reinterpret_cast<uint32_t*>(Tds + (r0 + 8) * TP + c * 2) = d23;
+            }
+        }
+        __syncwarp();
+        av_product_store<MT, KK>(dsa, Ks, g, hd, scale, dq, lddq, lane);          // dQ = scale * dS K
+        // transposed A fragments: rows = keys, k = queries
+        uint32_t ta[MT][KK][4];
+        const uint32_t t_off = ((lane & 7) + ((lane >> 4) & 1) * 8) * TP + ((lane >> 3) & 1) * 16;
+#pragma unroll
+        for (int jt = 0; jt < MT; ++jt)
+#pragma unroll
+            for (int it = 0; it < KK; ++it) ldsm_x4_t(ta[jt][it], s_u32(Tds) + t_off + it * 16 * TP + jt * 32);
+        av_product_store<MT, KK>(ta, Qs, g, hd, scale, dk, lddk, lane);           // dK = scale * dS^T Q
+#pragma unroll
+        for (int jt = 0; jt < MT; ++jt)
+#pragma unroll
+            for (int it = 0; it < KK; ++it) ldsm_x4_t(ta[jt][it], s_u32(Tp) + t_off + it * 16 * TP + jt * 32);
+        av_product_store<MT, KK>(ta, Os, g, hd, 1.f, dv, lddv, lane);             // dV = P~^T dO
+        __syncwarp();
+    }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename Kern>
+static int ensure_smem(Kern kern, size_t smem, size_t& cur) {
+    if (smem > cur) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+        cur = smem;
+    }
+    return 0;
+}
+
+static int am_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// Returns 1 if the mma path took the call, 0 if the shapes are outside its envelope, < 0 on error.
+int attn_mma_fwd_try(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const int32_t* seg_off,
+                     int n_seg, int max_len, int n_heads, int hd, float scale, void* ctx, int ldc, float drop_p,
+                     unsigned long long seed, cudaStream_t stream) {
+    if (max_len > 32 || hd > 248 || (hd & 1) || n_heads > 64) return 0;
+    {
+        const int span = (n_heads * hd + 7) / 8 * 8;   // aligned chunks never leave the row
+        if (span > ldq || span > ldk || span > ldv) return 0;
+    }
+    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || (ldq & 7) || (ldk & 7) || (ldv & 7) || (ldc & 1) ||
+        (reinterpret_cast<uintptr_t>(ctx) & 3u))
+        return 0;
+    const int n_units = n_seg * n_heads;
+    int rc;
+    if (max_len <= 16) {
+        constexpr int W = 8;
+        const size_t smem = (size_t)W * 3 * 16 * AM_PITCH_B;
+        static size_t cur = 0;
+        if ((rc = ensure_smem(attn_mma_fwd_kernel<16>, smem, cur))) return rc;
+        int grid = (n_units + W - 1) / W;
+        if (grid > am_num_sms()) grid = am_num_sms();
+        attn_mma_fwd_kernel<16><<<grid, W * 32, smem, stream>>>(
+            (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, seg_off, n_units,
+            n_heads, hd, scale, (__nv_bfloat16*)ctx, ldc, drop_p, seed);
+    } else {
+        constexpr int W = 4;
+        const size_t smem = (size_t)W * 3 * 32 * AM_PITCH_B;
+        static size_t cur = 0;
+        if ((rc = ensure_smem(attn_mma_fwd_kernel<32>, smem, cur))) return rc;
+        int grid = (n_units + W - 1) / W;
+        if (grid > am_num_sms()) grid = am_num_sms();
+        attn_mma_fwd_kernel<32><<<grid, W * 32, smem, stream>>>(
+            (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, seg_off, n_units,
+            n_heads, hd, scale, (__nv_bfloat16*)ctx, ldc, drop_p, seed);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+    return 1;
+}
+
+int attn_mma_bwd_try(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* dctx, int ldc,
+                     const int32_t* seg_off, int n_seg, int max_len, int n_heads, int hd, float scale, void* dq, int lddq,
+                     void* dk, int lddk, void* dv, int lddv, float drop_p, unsigned long long seed, cudaStream_t stream) {
+    if (max_len > 32 || hd > 248 || (hd & 1) || n_heads > 64) return 0;
+    {
+        const int span = (n_heads * hd + 7) / 8 * 8;   // aligned chunks never leave the row
+        if (span > ldq || span > ldk || span > ldv) return 0;
+    }
+    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(dctx) || (ldq & 7) || (ldk & 7) || (ldv & 7) ||
+        (ldc & 7) || (lddq & 1) || (lddk & 1) || (lddv & 1) || (reinterpret_cast<uintptr_t>(dq) & 3u) ||
+        (reinterpret_cast<uintptr_t>(dk) & 3u) || (reinterpret_cast<uintptr_t>(dv) & 3u))
+        return 0;
+    const int n_units = n_seg * n_heads;
+    int rc;
+    if (max_len <= 16) {
+        constexpr int W = 6, LP = 16;
+        const size_t smem = (size_t)W * (4 * LP * AM_PITCH_B + 2 * LP * (LP + 8) * 2);
+        static size_t cur = 0;
+        if ((rc = ensure_smem(attn_mma_bwd_kernel<16>, smem, cur))) return rc;
+        int grid = (n_units + W - 1) / W;
+        if (grid > am_num_sms()) grid = am_num_sms();
+        attn_mma_bwd_kernel<16><<<grid, W * 32, smem, stream>>>(
+            (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv,
+            (const __nv_bfloat16*)dctx, ldc, seg_off, n_units, n_heads, hd, scale, (__nv_bfloat16*)dq, lddq,
+            (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, drop_p, seed);
+    } else {
+        constexpr int W = 3, LP = 32;
+        const size_t smem = (size_t)W * (4 * LP * AM_PITCH_B + 2 * LP * (LP + 8) * 2);
+        static size_t cur = 0;
+        if ((rc = ensure_smem(attn_mma_bwd_kernel<32>, smem, cur))) return rc;
+        int grid = (n_units + W - 1) / W;
+        if (grid > am_num_sms()) grid = am_num_sms();
+        attn_mma_bwd_kernel<32><<<grid, W * 32, smem, stream>>>(
+            (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv,
+            (const __nv_bfloat16*)dctx, ldc, seg_off, n_units, n_heads, hd, scale, (__nv_bfloat16*)dq, lddq,
+            (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, drop_p, seed);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+    return 1;
+}
+
+}  // namespace vsgg

@@ -227,6 +227,15 @@ attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_b
 
 }  // namespace vsgg
 
+namespace vsgg {
+int attn_mma_fwd_try(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const int32_t* seg_off,
+                     int n_seg, int max_len, int n_heads, int hd, float scale, void* ctx, int ldc, float drop_p,
+                     unsigned long long seed, cudaStream_t stream);
+int attn_mma_bwd_try(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* dctx, int ldc,
+                     const int32_t* seg_off, int n_seg, int max_len, int n_heads, int hd, float scale, void* dq, int lddq,
+                     void* dk, int lddk, void* dv, int lddv, float drop_p, unsigned long long seed, cudaStream_t stream);
+}  // namespace vsgg
+
 using namespace vsgg;
 
 extern "C" int b200vsgg_attn_small_fwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v,
@@ -236,6 +245,11 @@ extern "C" int b200vsgg_attn_small_fwd(const void* q, int32_t ldq, const void* k
     if (!q || !k || !v || !seg_off || !ctx || n_heads <= 0 || head_dim <= 0 || (head_dim & 1) || max_len <= 0)
         return set_error(B200VSGG_ERR_BAD_ARG, "attn_small_fwd: bad arg (head_dim must be even)");
     if (n_seg == 0) return 0;
+    {   // warp-level mma path for segments <= 32 tokens (attn_mma.cu); the SIMT kernel below is the long-segment path
+        const int took = attn_mma_fwd_try(q, ldq, k, ldk, v, ldv, seg_off, n_seg, max_len, n_heads, head_dim, scale, ctx,
+                                          ldc, drop_p, seed, (cudaStream_t)stream);
+        if (took != 0) return took < 0 ? took : 0;
+    }
     const int pitch = head_dim + 1;
     const size_t smem = sizeof(float) * (2ull * max_len * pitch + ATT_WARPS * pitch + ATT_WARPS * max_len);
     if (smem > 227 * 1024) return set_error(B200VSGG_ERR_BAD_ARG, "attn_small_fwd: segment too long for shared memory");
@@ -262,6 +276,11 @@ extern "C" int b200vsgg_attn_small_bwd(const void* q, int32_t ldq, const void* k
         max_len <= 0)
         return set_error(B200VSGG_ERR_BAD_ARG, "attn_small_bwd: bad arg");
     if (n_seg == 0) return 0;
+    {
+        const int took = attn_mma_bwd_try(q, ldq, k, ldk, v, ldv, dctx, ldc, seg_off, n_seg, max_len, n_heads, head_dim,
+                                          scale, dq, lddq, dk, lddk, dv, lddv, drop_p, seed, (cudaStream_t)stream);
+        if (took != 0) return took < 0 ? took : 0;
+    }
     const int pitch = head_dim + 1;
     const size_t smem = sizeof(float) * (4ull * max_len * pitch + 2ull * max_len * max_len);
     if (smem > 227 * 1024) return set_error(B200VSGG_ERR_BAD_ARG, "attn_small_bwd: segment too long for shared memory");

@@ -2,8 +2,9 @@
 //   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> smem ring -> tcgen05.mma (cta_group::1, M=128,
 //   N=BN, K=16) accumulating fp32 in TMEM (two accumulator stages) -> tcgen05.ld epilogue with
 //   fused bias / activation / mask / dropout / residual / dual fp32+bf16 stores.
-// Roles per CTA (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
-//   warps4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+// Roles per CTA (384 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+//   warps4-11 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31 and one column half of the tile; each
+//   32x32 chunk is transposed through shared memory so every global access is row-contiguous).
 // Operand majors: K-major ([rows,K], K contiguous) or MN-major ([K,rows], rows contiguous), so the
 // same kernel serves forward (K,K), dgrad (K,MN) and wgrad (MN,MN) without transposed copies.
 #include <cuda.h>
@@ -50,7 +51,9 @@ struct GemmCfg {
     static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
     static constexpr int ACC_STAGES = 2;
     static constexpr int TMEM_COLS = (ACC_STAGES * BN <= 32) ? 32 : ((ACC_STAGES * BN <= 64) ? 64 : ((ACC_STAGES * BN <= 128) ? 128 : ((ACC_STAGES * BN <= 256) ? 256 : 512)));
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int EPI_BYTES = 8 * 4096;  // one swizzled 32x32 fp32 transpose buffer per epilogue warp
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024 /*align slack*/;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -60,8 +63,140 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return cdf + x * pdf;
 }
 
+// Epilogue state hoisted into registers once per kernel.
+struct EpiRegs {
+    float* stg;                       // this warp's swizzled 32x32 fp32 transpose buffer
+    const float* res_f32;
+    const __nv_bfloat16* res_b16;
+    const __nv_bfloat16* mask_src;
+    const float* bias;
+    float* out_f32;
+    __nv_bfloat16* out_bf16;
+    unsigned long long drop_seed;
+    float alpha, inv_keep;
+    uint32_t drop_thr;
+    int act, mask_mode, accumulate, ld_f32, ld_bf16, ldr, ldm, N, lane;
+    bool atomic, use_bias;
+};
+
+// One 32-row x 32-column chunk of the accumulator: TMEM -> registers (lane = row) -> swizzled shared
+// memory -> registers (lane = column, 32 rows) -> fused epilogue -> row-contiguous global stores.
+// FULL = all 32 rows exist (every m-tile but the last): no row guards, so each row costs ~6 instructions.
+// Loads are clamped in-bounds instead of predicated; stores sit under one lane predicate (col < N).
+template <bool FULL>
+__device__ __forceinline__ void epi_chunk(const EpiRegs& E, uint32_t taddr, int rbase, int rows_here, int nc,
+                                          uint64_t* full_bar, uint32_t full_phase, bool& waited) {
+    const int lane = E.lane;
+    const int col = nc + lane;
+    const bool col_ok = col < E.N;
+    const int colc = col_ok ? col : E.N - 1;
+    const int last = rows_here - 1;
+    // aux = the chunk's residual values, or (when there is no residual) its mask values, prefetched
+    // before the accumulator is touched.  With BOTH present the mask is read inline later (rare).
+    float aux[32];
+    const bool has_res = E.res_f32 != nullptr || E.res_b16 != nullptr;
+    const bool has_mask = E.mask_src != nullptr;
+    const __nv_bfloat16* mp = has_mask ? E.mask_src + static_cast<size_t>(rbase) * E.ldm + colc : nullptr;
+    if (E.res_f32 != nullptr) {
+        const float* rp = E.res_f32 + static_cast<size_t>(rbase) * E.ldr + colc;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) aux[i] = __ldg(rp + (FULL ? i : min(i, last)) * E.ldr);
+    } else if (E.res_b16 != nullptr) {
+        const __nv_bfloat16* rp = E.res_b16 + static_cast<size_t>(rbase) * E.ldr + colc;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) aux[i] = __bfloat162float(rp[(FULL ? i : min(i, last)) * E.ldr]);
+    } else if (has_mask) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) aux[i] = __bfloat162float(mp[(FULL ? i : min(i, last)) * E.ldm]);
+    }
+    if (!waited) {
+        ptx::mbar_wait(full_bar, full_phase);
+        ptx::tc_fence_after();
+        waited = true;
+    }
+    uint32_t r[32];
+    ptx::tmem_ld_32x32b_x32(taddr, r);
+    ptx::tmem_ld_wait();
+    float* stg = E.stg;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 v4 = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                __uint_as_float(r[4 * j + 3]));
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = v4;
+    }
+    __syncwarp();
+    const float bias_v = E.use_bias ? __ldg(E.bias + colc) : 0.f;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(stg[i * 32 + (((lane >> 2) ^ (i & 7)) << 2) + (lane & 3)], E.alpha, bias_v);
+    __syncwarp();   // the buffer may be overwritten by the next chunk from here on
+    if (E.atomic) {
+        if (col_ok) {
+            float* op = E.out_f32 + static_cast<size_t>(rbase) * E.ld_f32 + col;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (FULL || i < rows_here) atomicAdd(op + i * E.ld_f32, v[i]);
+        }
+        return;
+    }
+    if (E.act == 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else if (E.act == 2) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    }
+    if (has_mask) {
+        if (!has_res) {
+            if (E.mask_mode == 1) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = aux[i] > 0.f ? v[i] : 0.f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad(aux[i]);
+            }
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+                const float m = __bfloat162float(mp[(FULL ? i : min(i, last)) * E.ldm]);
+                v[i] = E.mask_mode == 1 ? (m > 0.f ? v[i] : 0.f) : v[i] * gelu_erf_grad(m);
+            }
+        }
+    }
+    if (E.drop_thr != 0u) {
+        const unsigned long long base_idx = static_cast<unsigned long long>(rbase) * E.N + col;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const uint32_t h = hash_u32(E.drop_seed, base_idx + static_cast<unsigned long long>(i) * E.N);
+            v[i] = (h >= E.drop_thr) ? v[i] * E.inv_keep : 0.f;
+        }
+    }
+    if (has_res) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += aux[i];
+    }
+    if (!col_ok) return;
+    if (E.out_f32 != nullptr) {
+        float* op = E.out_f32 + static_cast<size_t>(rbase) * E.ld_f32 + col;
+        if (E.accumulate) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (FULL || i < rows_here) v[i] += op[i * E.ld_f32];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (FULL || i < rows_here) op[i * E.ld_f32] = v[i];
+    }
+    if (E.out_bf16 != nullptr) {
+        __nv_bfloat16* op = E.out_bf16 + static_cast<size_t>(rbase) * E.ld_bf16 + col;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (FULL || i < rows_here) op[i * E.ld_bf16] = __float2bfloat16(v[i]);
+    }
+}
+
 template <int BN, int A_MN, int B_MN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const GemmEpi ep, const int M, const int N, const int K, const int splits, const int kb_per,
                  const int a_k_period) {
@@ -100,7 +235,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
         for (int i = 0; i < Cfg::ACC_STAGES; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
-            ptx::mbar_init(&tmem_empty_bar[i], 128);
+            ptx::mbar_init(&tmem_empty_bar[i], 256);
         }
         ptx::fence_mbar_init();
     }
@@ -188,148 +323,55 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
         }
     } else if (warp >= 4) {
-        // ================================ epilogue warps ================================
+        // ================================ epilogue warps (8) ================================
+        // Warp (4 + e): TMEM lane quadrant wq = warp % 4 (rows m0 + 32*wq ..), column half e / 4 of the tile.
+        // Per 32-column chunk: tcgen05.ld gives each lane ONE ROW x 32 columns; the chunk is transposed
+        // through a swizzled 4 KB shared-memory buffer so that global traffic is row-contiguous
+        // (lane = column: 128 B per fp32 row access, one transaction) instead of 32 rows per instruction.
+        // Residual / mask rows of the chunk are prefetched into registers before the accumulator is read.
+        const int ew = warp - 4;
         const int wq = warp & 3;
+        const int half = ew >> 2;
+        EpiRegs E;
+        E.stg = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + ew * 4096);
+        E.inv_keep = ep.dropout_p > 0.f ? 1.0f / (1.0f - ep.dropout_p) : 1.0f;
+        E.drop_thr = ep.dropout_p > 0.f ? static_cast<uint32_t>(ep.dropout_p * 4294967296.0) : 0u;
+        E.res_f32 = ep.residual_is_bf16 ? nullptr : reinterpret_cast<const float*>(ep.residual);
+        E.res_b16 = ep.residual_is_bf16 ? reinterpret_cast<const __nv_bfloat16*>(ep.residual) : nullptr;
+        E.mask_src = ep.mask_src;
+        E.bias = ep.bias;
+        E.act = ep.act; E.mask_mode = ep.mask_mode; E.accumulate = ep.accumulate;
+        E.alpha = ep.alpha;
+        E.drop_seed = ep.dropout_seed;
+        E.out_f32 = ep.out_f32; E.out_bf16 = ep.out_bf16;
+        E.ld_f32 = ep.ld_f32; E.ld_bf16 = ep.ld_bf16; E.ldr = ep.ldr; E.ldm = ep.ldm;
+        E.N = N; E.lane = lane; E.atomic = splits > 1;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const float inv_keep = ep.dropout_p > 0.f ? 1.0f / (1.0f - ep.dropout_p) : 1.0f;
-        const uint32_t drop_thr = ep.dropout_p > 0.f ? static_cast<uint32_t>(ep.dropout_p * 4294967296.0) : 0u;
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
             const int tile = unit % num_tiles, split = unit / num_tiles;
             const int m0 = (tile / num_n) * BM;
             const int n0 = (tile % num_n) * BN;
-            ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
-            ptx::tc_fence_after();
-            const int row = m0 + wq * 32 + lane;
-            const bool row_ok = row < M;
-            const size_t rowz = static_cast<size_t>(row_ok ? row : 0);
+            const int rbase = m0 + wq * 32;
+            const int rows_here = min(32, M - rbase);      // <= 0: nothing to store for this warp
+            E.use_bias = ep.bias != nullptr && (splits == 1 || split == 0);
+            bool waited = false;
+            if (rows_here > 0) {
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int nc = n0 + c * 32;
-                if (nc >= N) break;  // warp-uniform
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) +
-                                            static_cast<uint32_t>(acc * BN + c * 32),
-                                        r);
-                ptx::tmem_ld_wait();
-                if (row_ok) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int n = nc + g * 8;
-                        if (n >= N) break;
-                        float v[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) * ep.alpha;
-                        const bool full8 = (n + 8 <= N) && ep.vec_ok;
-                        if (splits > 1) {
-                            // split-K partial: bias once (split 0), then atomic accumulation into fp32
-                            if (ep.bias != nullptr && split == 0)
-                                for (int j = 0; j < 8 && n + j < N; ++j) v[j] += __ldg(ep.bias + n + j);
-                            float* op = ep.out_f32 + rowz * ep.ld_f32 + n;
-                            if (full8) {
-                                atomicAdd(reinterpret_cast<float4*>(op), make_float4(v[0], v[1], v[2], v[3]));
-                                atomicAdd(reinterpret_cast<float4*>(op + 4), make_float4(v[4], v[5], v[6], v[7]));
-                            } else {
-                                for (int j = 0; j < 8 && n + j < N; ++j) atomicAdd(op + j, v[j]);
-                            }
-                            continue;
-                        }
-                        if (ep.bias != nullptr) {
-                            if (full8) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
-                                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                            } else {
-                                for (int j = 0; j < 8 && n + j < N; ++j) v[j] += __ldg(ep.bias + n + j);
-                            }
-                        }
-                        if (ep.act == 1) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-                        } else if (ep.act == 2) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-                        }
-                        if (ep.mask_src != nullptr) {
-                            const __nv_bfloat16* mp = ep.mask_src + rowz * ep.ldm + n;
-                            float mv[8];
-                            if (full8) {
-                                load_bf16x8(mp, mv);
-                            } else {
-                                for (int j = 0; j < 8; ++j) mv[j] = (n + j < N) ? __bfloat162float(mp[j]) : 0.f;
-                            }
-                            if (ep.mask_mode == 1) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] = mv[j] > 0.f ? v[j] : 0.f;
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] *= gelu_erf_grad(mv[j]);
-                            }
-                        }
-                        if (drop_thr != 0u) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const uint32_t h = hash_u32(ep.dropout_seed, rowz * static_cast<size_t>(N) + n + j);
-                                v[j] = (h >= drop_thr) ? v[j] * inv_keep : 0.f;
-                            }
-                        }
-                        if (ep.residual != nullptr) {
-                            if (ep.residual_is_bf16) {
-                                const __nv_bfloat16* rp =
-                                    reinterpret_cast<const __nv_bfloat16*>(ep.residual) + rowz * ep.ldr + n;
-                                float rv[8];
-                                if (full8) {
-                                    load_bf16x8(rp, rv);
-                                } else {
-                                    for (int j = 0; j < 8; ++j) rv[j] = (n + j < N) ? __bfloat162float(rp[j]) : 0.f;
-                                }
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] += rv[j];
-                            } else {
-                                const float* rp = reinterpret_cast<const float*>(ep.residual) + rowz * ep.ldr + n;
-                                if (full8) {
-                                    const float4 a0 = *reinterpret_cast<const float4*>(rp);
-                                    const float4 a1 = *reinterpret_cast<const float4*>(rp + 4);
-                                    v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-                                    v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-                                } else {
-                                    for (int j = 0; j < 8 && n + j < N; ++j) v[j] += rp[j];
-                                }
-                            }
-                        }
-                        if (ep.out_f32 != nullptr) {
-                            float* op = ep.out_f32 + rowz * ep.ld_f32 + n;
-                            if (full8) {
-                                float4 o0 = make_float4(v[0], v[1], v[2], v[3]);
-                                float4 o1 = make_float4(v[4], v[5], v[6], v[7]);
-                                if (ep.accumulate) {
-                                    const float4 p0 = *reinterpret_cast<const float4*>(op);
-                                    const float4 p1 = *reinterpret_cast<const float4*>(op + 4);
-                                    o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
-                                    o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
-                                    v[0] = o0.x; v[1] = o0.y; v[2] = o0.z; v[3] = o0.w;
-                                    v[4] = o1.x; v[5] = o1.y; v[6] = o1.z; v[7] = o1.w;
-                                }
-                                *reinterpret_cast<float4*>(op) = o0;
-                                *reinterpret_cast<float4*>(op + 4) = o1;
-                            } else {
-                                for (int j = 0; j < 8 && n + j < N; ++j) {
-                                    if (ep.accumulate) v[j] += op[j];
-                                    op[j] = v[j];
-                                }
-                            }
-                        }
-                        if (ep.out_bf16 != nullptr) {
-                            __nv_bfloat16* op = ep.out_bf16 + rowz * ep.ld_bf16 + n;
-                            if (full8) {
-                                store_bf16x8(op, v);
-                            } else {
-                                for (int j = 0; j < 8 && n + j < N; ++j) op[j] = __float2bfloat16(v[j]);
-                            }
-                        }
-                    }
+                for (int c = 0; c < BN / 64; ++c) {
+                    const int nc = n0 + half * (BN / 2) + c * 32;
+                    if (nc >= N) break;  // warp-uniform
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) +
+                                           static_cast<uint32_t>(acc * BN + half * (BN / 2) + c * 32);
+                    if (rows_here == 32)
+                        epi_chunk<true>(E, taddr, rbase, 32, nc, &tmem_full_bar[acc], acc_phase, waited);
+                    else
+                        epi_chunk<false>(E, taddr, rbase, rows_here, nc, &tmem_full_bar[acc], acc_phase, waited);
                 }
+            }
+            if (!waited) {
+                ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+                ptx::tc_fence_after();
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tmem_empty_bar[acc]);
@@ -445,7 +487,7 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, in
     }
     const int num_units = num_tiles * splits;
     int grid = num_units < num_sms() ? num_units : num_sms();
-    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, ep, M, N, K, splits, kb_per, a_k_period);
+    kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(ta, tb, ep, M, N, K, splits, kb_per, a_k_period);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
     return 0;

@@ -157,7 +157,9 @@ def _attn_ref(q, k, v, seg_off, H, hd):
     return torch.cat(outs)
 
 
-@pytest.mark.parametrize("H,hd,lens", [(8, 242, [8, 1, 16, 20, 3, 7]), (8, 242, [40, 5]), (4, 24, [33, 2, 9])])
+@pytest.mark.parametrize("H,hd,lens", [(8, 242, [8, 1, 16, 20, 3, 7]), (8, 242, [40, 5]), (4, 24, [33, 2, 9]),
+                                       (8, 242, [8, 1, 16, 3, 7, 12, 9, 9, 10, 6, 16]), (8, 242, [32, 31, 17, 2]),
+                                       (4, 30, [7, 16, 2, 11]), (8, 64, [5, 16, 9, 24]), (2, 248, [16, 4])])
 def test_attn_small_fwd_bwd(cuda_lib, H, hd, lens):
     from b200vsgg import ops
     D = H * hd
@@ -200,6 +202,55 @@ def test_attn_dropout_consistency(cuda_lib):
     ops.attn_small_fwd(q, k, v, seg_off, 2, 12, H, hd, c2, 0.1, 7)
     ops.attn_small_fwd(q, k, v, seg_off, 2, 12, H, hd, c0, 0.0, 7)
     assert torch.equal(c1, c2) and not torch.equal(c1, c0)
+
+
+@pytest.mark.parametrize("lens", [[12, 9, 16], [20, 31, 5]])
+def test_attn_dropout_backward_uses_forward_mask(cuda_lib, lens):
+    """Recover the dropped probabilities P~ with one-hot values (ctx = P~ V), then check dq/dk/dv of
+    the kernel against autograd through P * mask / (1-p) with that very mask."""
+    from b200vsgg import ops
+    H, hd, p, seed = 8, 242, 0.3, 1234
+    D, M = H * hd, sum(lens)
+    seg = [0]
+    for n in lens:
+        seg.append(seg[-1] + n)
+    seg_off = torch.tensor(seg, dtype=torch.int32, device=DEV)
+    g = _gen(11)
+    qkv = torch.randn(M, 3 * D, generator=g, device=DEV).bfloat16()
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    onehot = torch.zeros(M, D, device=DEV, dtype=torch.bfloat16)
+    for s_ in range(len(lens)):
+        for j in range(lens[s_]):
+            onehot[seg[s_] + j].view(H, hd)[:, j] = 1
+    probe = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    ops.attn_small_fwd(q, k, onehot, seg_off, len(lens), max(lens), H, hd, probe, p, seed)
+    ctx = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    ops.attn_small_fwd(q, k, v, seg_off, len(lens), max(lens), H, hd, ctx, p, seed)
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    outs = []
+    kept = 0.0
+    for s_ in range(len(lens)):
+        a, b = seg[s_], seg[s_ + 1]
+        L = b - a
+        Q = qf[a:b].view(L, H, hd).transpose(0, 1)
+        K = kf[a:b].view(L, H, hd).transpose(0, 1)
+        V = vf[a:b].view(L, H, hd).transpose(0, 1)
+        P = torch.softmax(Q @ K.transpose(1, 2) / math.sqrt(hd), -1)
+        mask = (probe[a:b].float().view(L, H, hd)[:, :, :L].transpose(0, 1) != 0).float()   # [H, L(query), L(key)]
+        kept += mask.sum().item()
+        outs.append(((P * mask / (1 - p)) @ V).transpose(0, 1).reshape(L, D))
+    ref = torch.cat(outs)
+    frac = kept / sum(H * n * n for n in lens)
+    assert 0.6 < frac < 0.8                                           # ~1-p of the probabilities survive
+    assert (ctx.float() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item() + 1e-3
+    dctx = torch.randn(M, D, generator=g, device=DEV).bfloat16()
+    ref.backward(dctx.float())
+    dqkv = torch.empty(M, 3 * D, device=DEV, dtype=torch.bfloat16)
+    ops.attn_small_bwd(q, k, v, dctx, seg_off, len(lens), max(lens), H, hd, dqkv[:, :D], dqkv[:, D:2 * D],
+                       dqkv[:, 2 * D:], p, seed)
+    for got, want in ((dqkv[:, :D], qf.grad), (dqkv[:, D:2 * D], kf.grad), (dqkv[:, 2 * D:], vf.grad)):
+        tol = 2 ** -6 * want.abs().max().item() + 1e-3
+        assert (got.float() - want).abs().max().item() < tol
 
 
 def test_gmm_head_fwd_bwd_vs_oracle(cuda_lib):
