@@ -200,6 +200,51 @@ int b200vsgg_pool_bwd(const void* dz, const uint8_t* argmax, int32_t n, int32_t 
 int b200vsgg_im2col3x3(const void* z, int32_t n, int32_t hw, int32_t channels, void* out, void* stream);
 int b200vsgg_col2im3x3(const void* dcol, int32_t n, int32_t hw, int32_t channels, void* dz, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * TEAT-GT / TokenGT path (lib/teatgt.py, tools/TokenGT/tokengt).
+ */
+/* Variable-length flash attention over clip sequences: multihead_attention.py:135-183 without the [heads,T,T]
+ * maps.  q,k,v,ctx: bf16 [rows, n_heads*head_dim] views (ld in elements, 16-byte aligned, head_dim % 8 == 0,
+ * head_dim <= 64); seq_off int32 [n_seq+1]; the query/key blocking is host-planned: block b covers rows
+ * [blk_row0[b], min(blk_row0[b]+64, seq_off[blk_seq[b]+1])) of sequence blk_seq[b].  scale multiplies q.k
+ * (the reference scales q by head_dim^-0.5 after the bias: same product).  lse fp32 [rows, n_heads]
+ * (nullable in inference).  Dropout acts on the probabilities and is regenerated from `seed` in backward. */
+int b200vsgg_attn_flash_fwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                            const int32_t* seq_off, const int32_t* blk_seq, const int32_t* blk_row0, int32_t n_blocks,
+                            int32_t n_heads, int32_t head_dim, float scale, void* ctx, int32_t ldc, float* lse,
+                            float drop_p, uint64_t seed, void* stream);
+/* delta fp32 [rows, n_heads] is workspace (rowsum(dO*O), written here). */
+int b200vsgg_attn_flash_bwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                            const void* ctx, int32_t ldc, const void* dctx, int32_t lddc, const float* lse, float* delta,
+                            const int32_t* seq_off, const int32_t* blk_seq, const int32_t* blk_row0, int32_t n_blocks,
+                            int32_t n_rows, int32_t n_heads, int32_t head_dim, float scale, void* dq, int32_t lddq,
+                            void* dk, int32_t lddk, void* dv, int32_t lddv, float drop_p, uint64_t seed, void* stream);
+/* Node tokens (lib/teatgt.py:118-141): tok[i] = so[feat_row[i], half(is_person)] | embed[labels[feat_row[i]]];
+ * so = features @ [subj_fc; obj_fc]^T + bias over all boxes, [O, 2*h1] fp32. */
+int b200vsgg_node_tokens_fwd(const float* so, int32_t ld_so, const int32_t* feat_row, const int32_t* is_person,
+                             const int64_t* labels, const float* embed, int32_t n, int32_t h1, int32_t e, float* out_f32,
+                             void* out_bf16, void* stream);
+int b200vsgg_node_tokens_bwd(const float* dtok, const int32_t* feat_row, const int32_t* is_person, const int64_t* labels,
+                             int32_t n, int32_t h1, int32_t e, float* dso /* pre-zeroed */, int32_t ld_dso,
+                             float* dembed /* nullable, pre-zeroed */, void* stream);
+/* Edge predicates of the pseudo-graph (lib/teatgt.py:199-217): per frame f, uint8 [nmax,nmax] matrices
+ * spatial[a][b] (a<b, centre distance <= thr) and temporal[p][c] (cosine(prev-frame node p, node c) >= sim, only
+ * if has_prev[f]).  The edge LIST (reference order) is compacted on the host from these flags. */
+int b200vsgg_teat_pair_flags(const float* tok, int32_t d, const float* boxes, const int32_t* feat_row,
+                             const int32_t* node_off, const int32_t* has_prev, int32_t n_frames, float thr, float sim,
+                             int32_t nmax, uint8_t* spatial, uint8_t* temporal, void* stream);
+/* Token assembly (tokenizer.py:217-295): desc int32 [T,4] = (kind, a, b, c); kind 0 [graph], 1 [null],
+ * 2 node a (b = frame - first frame of clip), 3 edge (a,b) of type c.  See teat_kernels.cu. */
+int b200vsgg_teat_assemble_fwd(const int32_t* desc, int32_t n_tokens, int32_t d, const float* na, const float* pu,
+                               const float* pv, const float* temp, const float* eemb, const float* order,
+                               const float* graph_tok, const float* null_tok, float* x, void* stream);
+int b200vsgg_teat_assemble_bwd(const int32_t* desc, int32_t n_tokens, int32_t d, const float* dx, float* dna, float* dpu,
+                               float* dpv, float* dtemp, float* deemb, float* dorder, float* dgraph, float* dnull,
+                               void* stream);
+/* out = bf16(dropout(act(x))) for bf16 x (feedforward.py:31-36: GELU + activation dropout). */
+int b200vsgg_act_dropout_bf16(const void* x, int32_t ld_x, int64_t rows, int32_t cols, int32_t act, float p, uint64_t seed,
+                              void* out, int32_t ld_o, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

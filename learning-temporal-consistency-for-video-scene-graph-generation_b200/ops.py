@@ -372,3 +372,86 @@ def col2im3x3(dcol, n, hw, channels, dz):
     assert dcol.dtype == torch.bfloat16 and dcol.is_contiguous() and dz.dtype == torch.bfloat16 and dz.is_contiguous()
     check(_lib.lib().b200vsgg_col2im3x3(_ptr(dcol), n, hw, channels, _ptr(dz), _stream()), "col2im3x3")
     _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# TEAT-GT / TokenGT path
+# ------------------------------------------------------------------------------------------------
+def attn_flash_fwd(q, k, v, seq_off, blk_seq, blk_row0, n_heads, head_dim, ctx, lse=None, drop_p=0.0, seed=0):
+    scale = float(head_dim) ** -0.5
+    check(_lib.lib().b200vsgg_attn_flash_fwd(
+        _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), _ptr(seq_off), _ptr(blk_seq),
+        _ptr(blk_row0), blk_seq.numel(), n_heads, head_dim, scale, _ptr(_bf(ctx)), ctx.stride(0), _ptr(lse), drop_p, seed,
+        _stream()), "attn_flash_fwd")
+    _count()
+
+
+def attn_flash_bwd(q, k, v, ctx, dctx, lse, seq_off, blk_seq, blk_row0, n_heads, head_dim, dq, dk, dv, drop_p=0.0, seed=0):
+    scale = float(head_dim) ** -0.5
+    rows = q.shape[0]
+    delta = torch.empty(rows, n_heads, device=q.device, dtype=torch.float32)
+    check(_lib.lib().b200vsgg_attn_flash_bwd(
+        _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), _ptr(_bf(ctx)), ctx.stride(0),
+        _ptr(_bf(dctx)), dctx.stride(0), _ptr(lse), _ptr(delta), _ptr(seq_off), _ptr(blk_seq), _ptr(blk_row0),
+        blk_seq.numel(), rows, n_heads, head_dim, scale, _ptr(_bf(dq)), dq.stride(0), _ptr(_bf(dk)), dk.stride(0),
+        _ptr(_bf(dv)), dv.stride(0), drop_p, seed, _stream()), "attn_flash_bwd")
+    _count(3)
+
+
+def node_tokens_fwd(so, feat_row, is_person, labels, embed, h1, out_f32, out_bf16):
+    n = feat_row.numel()
+    assert so.stride(1) == 1 and feat_row.dtype == torch.int32 and is_person.dtype == torch.int32
+    assert labels.dtype == torch.int64 and embed.is_contiguous() and out_f32.is_contiguous()
+    check(_lib.lib().b200vsgg_node_tokens_fwd(_ptr(_f32(so)), so.stride(0), _ptr(feat_row), _ptr(is_person), _ptr(labels),
+                                               _ptr(_f32(embed)), n, h1, embed.shape[1], _ptr(_f32(out_f32)),
+                                               _ptr(_bf(out_bf16)), _stream()), "node_tokens_fwd")
+    _count()
+
+
+def node_tokens_bwd(dtok, feat_row, is_person, labels, h1, e, dso, dembed):
+    assert dtok.is_contiguous() and dso.stride(1) == 1
+    check(_lib.lib().b200vsgg_node_tokens_bwd(_ptr(_f32(dtok)), _ptr(feat_row), _ptr(is_person), _ptr(labels),
+                                               feat_row.numel(), h1, e, _ptr(_f32(dso)), dso.stride(0), _ptr(dembed),
+                                               _stream()), "node_tokens_bwd")
+    _count()
+
+
+def teat_pair_flags(tok, boxes, feat_row, node_off, has_prev, thr, sim, nmax):
+    n_frames = has_prev.numel()
+    assert tok.is_contiguous() and boxes.is_contiguous() and boxes.shape[1] == 5
+    spatial = torch.empty(n_frames, nmax, nmax, dtype=torch.uint8, device=tok.device)
+    temporal = torch.empty(n_frames, nmax, nmax, dtype=torch.uint8, device=tok.device)
+    check(_lib.lib().b200vsgg_teat_pair_flags(_ptr(_f32(tok)), tok.shape[1], _ptr(_f32(boxes)), _ptr(feat_row),
+                                               _ptr(node_off), _ptr(has_prev), n_frames, thr, sim, nmax, _ptr(spatial),
+                                               _ptr(temporal), _stream()), "teat_pair_flags")
+    _count()
+    return spatial, temporal
+
+
+def teat_assemble_fwd(desc, na, pu, pv, temp, eemb, order, graph_tok, null_tok, x):
+    for t in (na, pu, pv, temp, eemb, order, graph_tok, null_tok, x):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert desc.dtype == torch.int32 and desc.is_contiguous() and desc.shape[1] == 4
+    check(_lib.lib().b200vsgg_teat_assemble_fwd(_ptr(desc), desc.shape[0], x.shape[1], _ptr(na), _ptr(pu), _ptr(pv),
+                                                 _ptr(temp), _ptr(eemb), _ptr(order), _ptr(graph_tok), _ptr(null_tok),
+                                                 _ptr(x), _stream()), "teat_assemble_fwd")
+    _count()
+
+
+def teat_assemble_bwd(desc, dx, dna, dpu, dpv, dtemp, deemb, dorder, dgraph, dnull):
+    for t in (dx, dna, dpu, dpv, dtemp, deemb, dorder, dgraph, dnull):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    check(_lib.lib().b200vsgg_teat_assemble_bwd(_ptr(desc), desc.shape[0], dx.shape[1], _ptr(dx), _ptr(dna), _ptr(dpu),
+                                                 _ptr(dpv), _ptr(dtemp), _ptr(deemb), _ptr(dorder), _ptr(dgraph),
+                                                 _ptr(dnull), _stream()), "teat_assemble_bwd")
+    _count()
+
+
+def act_dropout(x, act, p=0.0, seed=0, out=None):
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty(rows, cols, dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().b200vsgg_act_dropout_bf16(_ptr(_bf(x)), x.stride(0), rows, cols, act, p, seed, _ptr(_bf(out)),
+                                                out.stride(0), _stream()), "act_dropout_bf16")
+    _count()
+    return out

@@ -104,14 +104,12 @@ class SegmentPlan:
         return t
 
     def to(self, device):
-        """One pinned staging buffer, one H2D copy for all int32 arrays (+ one for the int64 one)."""
+        """One H2D copy for all int32 arrays through a persistent pinned staging buffer (allocating
+        pinned memory per call would synchronise the whole device, including copy streams)."""
         names = [n for n in self._DEVICE_FIELDS if n != "video_of_pair"]
         arrays = [np.ascontiguousarray(getattr(self, n + "_h")).reshape(-1) for n in names]
         sizes = [a.shape[0] for a in arrays]
-        flat = torch.from_numpy(np.concatenate(arrays))
-        if torch.device(device).type == "cuda":
-            flat = flat.pin_memory()
-        dflat = flat.to(device, non_blocking=True)
+        dflat = _staged_h2d(np.concatenate(arrays), device)
         pos = 0
         for n, sz in zip(names, sizes):
             t = dflat[pos:pos + sz]
@@ -122,6 +120,28 @@ class SegmentPlan:
         self.pairs_per_video_dev = torch.from_numpy(self.pairs_per_video.astype(np.float32)).to(device, non_blocking=True)
         self.device = device
         return self
+
+
+_STAGE = {"buf": None, "event": None}
+
+
+def _staged_h2d(flat_np, device):
+    """int32 numpy vector -> device tensor via a reused pinned buffer (async copy on the current stream)."""
+    src = torch.from_numpy(flat_np)
+    if torch.device(device).type != "cuda":
+        return src.to(device)
+    n = src.numel()
+    st = _STAGE
+    if st["buf"] is None or st["buf"].numel() < n:
+        st["buf"] = torch.empty(max(n, 1 << 20), dtype=torch.int32).pin_memory()
+        st["event"] = None
+    if st["event"] is not None:
+        st["event"].synchronize()        # the previous copy out of the buffer has completed
+    st["buf"][:n].copy_(src)
+    out = st["buf"][:n].to(device, non_blocking=True)
+    st["event"] = torch.cuda.Event()
+    st["event"].record()
+    return out
 
 
 def plan_from_im_idx(im_idx, frames_per_video=None, counts_host=None):
@@ -141,3 +161,16 @@ def plan_from_im_idx(im_idx, frames_per_video=None, counts_host=None):
     if frames_per_video is None:
         frames_per_video = np.asarray([len(counts_host)])
     return SegmentPlan(counts_host, frames_per_video)
+
+
+def attention_blocks(seq_off_h, block=64):
+    """Host plan of the flash-attention grid: (blk_seq, blk_row0) int32 arrays — block b covers rows
+    [blk_row0[b], min(blk_row0[b] + block, seq_off[blk_seq[b] + 1])) of sequence blk_seq[b]."""
+    off = np.asarray(seq_off_h, dtype=np.int64)
+    lens = np.diff(off)
+    nblk = (lens + block - 1) // block
+    blk_seq = np.repeat(np.arange(lens.shape[0]), nblk)
+    first = np.concatenate([[0], np.cumsum(nblk)])[:-1]
+    local = np.arange(int(nblk.sum())) - np.repeat(first, nblk)
+    blk_row0 = off[blk_seq] + local * block
+    return blk_seq.astype(np.int32), blk_row0.astype(np.int32)

@@ -1,0 +1,92 @@
+"""Variable-length flash attention (csrc/attn_flash.cu) against a plain torch fp32 reference, through the
+C-ABI.  Tolerance: bf16 inputs/outputs, fp32 accumulation -> 2^-7 relative to the tensor's max + 1e-3."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _plan(lens):
+    from b200vsgg.plan import attention_blocks
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    bs, br = attention_blocks(off)
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    return off, t(off), t(bs), t(br)
+
+
+def _ref(q, k, v, off, H, hd, mask=None, p=0.0):
+    outs = []
+    for s in range(len(off) - 1):
+        a, b = int(off[s]), int(off[s + 1])
+        L = b - a
+        Q, K, V = (t[a:b].view(L, H, hd).transpose(0, 1) for t in (q, k, v))
+        P = torch.softmax(Q @ K.transpose(1, 2) / math.sqrt(hd), -1)
+        if mask is not None:
+            P = P * mask[s] / (1 - p)
+        outs.append((P @ V).transpose(0, 1).reshape(L, H * hd))
+    return torch.cat(outs)
+
+
+@pytest.mark.parametrize("H,hd,lens", [(32, 24, [130, 64, 7, 200, 1]), (16, 48, [65, 300]), (4, 64, [64, 40, 129]),
+                                       (32, 24, [447])])
+def test_flash_fwd_bwd(cuda_lib, H, hd, lens):
+    from b200vsgg import ops
+    D, M = H * hd, sum(lens)
+    off_h, off, bs, br = _plan(lens)
+    g = torch.Generator(device=DEV).manual_seed(M)
+    qkv = torch.randn(M, 3 * D, generator=g, device=DEV).bfloat16()
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    ctx = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(M, H, device=DEV)
+    ops.attn_flash_fwd(q, k, v, off, bs, br, H, hd, ctx, lse)
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    ref = _ref(qf, kf, vf, off_h, H, hd)
+    assert (ctx.float() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item() + 1e-3
+    dctx = torch.randn(M, D, generator=g, device=DEV).bfloat16()
+    ref.backward(dctx.float())
+    dqkv = torch.empty(M, 3 * D, device=DEV, dtype=torch.bfloat16)
+    ops.attn_flash_bwd(q, k, v, ctx, dctx, lse, off, bs, br, H, hd, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:])
+    for name, got, want in (("dq", dqkv[:, :D], qf.grad), ("dk", dqkv[:, D:2 * D], kf.grad), ("dv", dqkv[:, 2 * D:], vf.grad)):
+        tol = 2 ** -6 * want.abs().max().item() + 1e-3
+        err = (got.float() - want).abs().max().item()
+        assert err < tol, (name, err, tol)
+
+
+def test_flash_dropout_mask_consistent_between_fwd_and_bwd(cuda_lib):
+    """One-hot values recover the dropped probabilities (ctx = P~ V); dq/dk/dv must equal autograd through
+    P * mask / (1-p) with that mask."""
+    from b200vsgg import ops
+    H, hd, lens, p, seed = 2, 64, [64, 40], 0.25, 99
+    D, M = H * hd, sum(lens)
+    off_h, off, bs, br = _plan(lens)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    qkv = torch.randn(M, 3 * D, generator=g, device=DEV).bfloat16()
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    onehot = torch.zeros(M, D, device=DEV, dtype=torch.bfloat16)
+    for s in range(len(lens)):
+        for j in range(lens[s]):
+            onehot[int(off_h[s]) + j].view(H, hd)[:, j] = 1
+    probe = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    ops.attn_flash_fwd(q, k, onehot, off, bs, br, H, hd, probe, None, p, seed)
+    masks = []
+    for s in range(len(lens)):
+        a, L = int(off_h[s]), lens[s]
+        masks.append((probe[a:a + L].float().view(L, H, hd)[:, :, :L].transpose(0, 1) != 0).float())
+    kept = sum(m.sum().item() for m in masks) / sum(H * n * n for n in lens)
+    assert 0.65 < kept < 0.85
+    ctx = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(M, H, device=DEV)
+    ops.attn_flash_fwd(q, k, v, off, bs, br, H, hd, ctx, lse, p, seed)
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    ref = _ref(qf, kf, vf, off_h, H, hd, masks, p)
+    assert (ctx.float() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item() + 1e-3
+    dctx = torch.randn(M, D, generator=g, device=DEV).bfloat16()
+    ref.backward(dctx.float())
+    dqkv = torch.empty(M, 3 * D, device=DEV, dtype=torch.bfloat16)
+    ops.attn_flash_bwd(q, k, v, ctx, dctx, lse, off, bs, br, H, hd, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], p, seed)
+    for got, want in ((dqkv[:, :D], qf.grad), (dqkv[:, D:2 * D], kf.grad), (dqkv[:, 2 * D:], vf.grad)):
+        assert (got.float() - want).abs().max().item() < 2 ** -6 * want.abs().max().item() + 1e-3
