@@ -120,6 +120,13 @@ int b200vsgg_layernorm_bwd(const float* dy, int32_t ld_dy, const float* x, int32
                            int32_t ld_dx, void* dx_bf16, int32_t ld_b, float drop_p, uint64_t drop_seed,
                            float* dgamma, float* dbeta, void* stream);
 
+/* Same, with dx_f32 = base + (gradient through the norm): the backward of a pre-LN residual branch
+ * (tokengt_graph_encoder_layer.py:170-191); base nullable. */
+int b200vsgg_layernorm_bwd_add(const float* dy, int32_t ld_dy, const float* x, int32_t ld_x, const float* gamma,
+                               const float* mean, const float* rstd, int32_t rows, int32_t cols, float* dx_f32,
+                               int32_t ld_dx, void* dx_bf16, int32_t ld_b, float drop_p, uint64_t drop_seed,
+                               float* dgamma, float* dbeta, void* stream, const float* base, int32_t ld_base);
+
 /* out = bf16(dropout(x)) with the GEMM epilogue's mask function (index = row*cols + col). */
 int b200vsgg_cast_dropout_bf16(const float* x, int32_t ld_x, int32_t rows, int32_t cols, void* out, int32_t ld_o,
                                float drop_p, uint64_t seed, void* stream);

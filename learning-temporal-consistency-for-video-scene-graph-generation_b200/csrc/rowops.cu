@@ -237,7 +237,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, int ld_dy, co
                                      const float* __restrict__ rstd, int rows, int cols, float* __restrict__ dx_f32,
                                      int ld_dx, __nv_bfloat16* __restrict__ dx_bf16, int ld_b, float drop_p,
                                      unsigned long long drop_seed, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
+                                     float* __restrict__ dbeta, const float* __restrict__ base, int ld_base) {
     extern __shared__ float red[];  // [warps][cols] x 2: per-warp dgamma / dbeta partials
     const int warps_per_block = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5;
@@ -288,6 +288,10 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, int ld_dy, co
                 o.y = rs * (gdy[i].y - m1 - xh[i].y * m2);
                 o.z = rs * (gdy[i].z - m1 - xh[i].z * m2);
                 o.w = rs * (gdy[i].w - m1 - xh[i].w * m2);
+                if (base != nullptr) {   // pre-LN residual: dx = d(skip path) + d(through the norm)
+                    const float4 bs = reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * ld_base)[c];
+                    o.x += bs.x; o.y += bs.y; o.z += bs.z; o.w += bs.w;
+                }
                 if (dx_f32) reinterpret_cast<float4*>(dx_f32 + static_cast<size_t>(r) * ld_dx)[c] = o;
                 if (dx_bf16) {
                     float a[4] = {o.x, o.y, o.z, o.w};
@@ -457,10 +461,10 @@ extern "C" int b200vsgg_layernorm_fwd(const float* x, int32_t ld_x, const float*
     return 0;
 }
 
-extern "C" int b200vsgg_layernorm_bwd(const float* dy, int32_t ld_dy, const float* x, int32_t ld_x, const float* gamma,
+extern "C" int b200vsgg_layernorm_bwd_add(const float* dy, int32_t ld_dy, const float* x, int32_t ld_x, const float* gamma,
                                       const float* mean, const float* rstd, int32_t rows, int32_t cols, float* dx_f32,
                                       int32_t ld_dx, void* dx_bf16, int32_t ld_b, float drop_p, uint64_t drop_seed,
-                                      float* dgamma, float* dbeta, void* stream) {
+                                      float* dgamma, float* dbeta, void* stream, const float* base, int32_t ld_base) {
     if (!dy || !x || !gamma || !mean || !rstd || cols <= 0 || (cols & 7) || cols > 2048)
         return set_error(B200VSGG_ERR_BAD_ARG, "layernorm_bwd: bad arg");
     if (rows == 0) return 0;
@@ -475,9 +479,17 @@ extern "C" int b200vsgg_layernorm_bwd(const float* dy, int32_t ld_dy, const floa
     }
     kern<<<grid_for(rows, 4, 148 * 3), threads, smem, (cudaStream_t)stream>>>(
         dy, ld_dy, x, ld_x, gamma, mean, rstd, rows, cols, dx_f32, ld_dx, (__nv_bfloat16*)dx_bf16, ld_b, drop_p,
-        drop_seed, dgamma, dbeta);
+        drop_seed, dgamma, dbeta, base, ld_base);
     VSGG_CUDA_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int b200vsgg_layernorm_bwd(const float* dy, int32_t ld_dy, const float* x, int32_t ld_x, const float* gamma,
+                                      const float* mean, const float* rstd, int32_t rows, int32_t cols, float* dx_f32,
+                                      int32_t ld_dx, void* dx_bf16, int32_t ld_b, float drop_p, uint64_t drop_seed,
+                                      float* dgamma, float* dbeta, void* stream) {
+    return b200vsgg_layernorm_bwd_add(dy, ld_dy, x, ld_x, gamma, mean, rstd, rows, cols, dx_f32, ld_dx, dx_bf16, ld_b,
+                                      drop_p, drop_seed, dgamma, dbeta, stream, nullptr, 0);
 }
 
 extern "C" int b200vsgg_cast_dropout_bf16(const float* x, int32_t ld_x, int32_t rows, int32_t cols, void* out,

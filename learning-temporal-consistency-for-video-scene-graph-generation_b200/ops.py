@@ -183,12 +183,14 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, y_f32=None, y_bf16=None, add_table=N
     _count()
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_f32=None, dx_bf16=None, drop_p=0.0, seed=0, dgamma=None, dbeta=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_f32=None, dx_bf16=None, drop_p=0.0, seed=0, dgamma=None, dbeta=None,
+                  base=None):
+    """dx = LN'(dy) (+ base: the skip-path gradient of a pre-LN residual branch)."""
     rows, cols = x.shape
-    check(_lib.lib().b200vsgg_layernorm_bwd(
+    check(_lib.lib().b200vsgg_layernorm_bwd_add(
         _ptr(_f32(dy)), dy.stride(0), _ptr(_f32(x)), x.stride(0), _ptr(_f32(gamma)), _ptr(mean), _ptr(rstd), rows,
         cols, _ptr(_f32(dx_f32)), _ld(dx_f32), _ptr(_bf(dx_bf16)), _ld(dx_bf16), drop_p, seed, _ptr(_f32(dgamma)),
-        _ptr(_f32(dbeta)), _stream()), "layernorm_bwd")
+        _ptr(_f32(dbeta)), _stream(), _ptr(_f32(base)), _ld(base)), "layernorm_bwd")
     _count()
 
 

@@ -154,3 +154,15 @@ def build_gt_tensors(entry, device=None):
         spa[i, entry["spatial_gt"][i]] = 1
         con[i, entry["contacting_gt"][i]] = 1
     return att.to(dev), spa.to(dev), con.to(dev)
+
+
+def teatgt_seeded_init_(model, seed=BASE_SEED):
+    """seeded_init_ plus the zero rows that nn.Embedding(padding_idx=0) keeps in a real TokenGT model."""
+    seeded_init_(model, seed)
+    with torch.no_grad():
+        for name, p in model.state_dict().items():
+            if name.endswith("temp_encoder.weight") or name.endswith("edge_encoder.weight"):
+                p[0].zero_()
+            if name.endswith("embed_out.weight"):        # the generic rule treats "*embed*" as an N(0,1) table;
+                p.mul_(1.0 / math.sqrt(p.shape[1]))      # this one is the output projection: keep logits O(1)
+    return model

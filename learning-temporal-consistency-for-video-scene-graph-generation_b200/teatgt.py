@@ -1,0 +1,376 @@
+"""B200-native TEAT-GT (PredCLS classifier path) behind the reference's module API.
+
+Drop-in for `lib/teatgt.py::TEAT_GT` of the reference (constructor :29-30, `forward(entry, phase, unc)`
+:98-355): same keyword arguments (`args` carries the TokenGT hyper-parameters of
+tools/utils/teatgt_config.py:36-58), same `state_dict()` names for every module on the path
+(`subj_fc`, `obj_fc`, `node_label_tokenizer`, `TokenGT_encoder.*` aliased as `TokenGT_model.encoder.*`,
+`object_classifier.*`, `gate_*_nn` / `gap*`), same entry keys in and out.
+
+Everything numerical runs in libb200vsgg kernels (tokengt_fn.py); the host plans the ragged structure
+once per call (TeatPlan): node layout, 5-frame clips, edge lists in the reference's order from
+device-computed predicates, token descriptors, flash-attention block table, and the Laplacian
+eigenvectors (host LAPACK fp64 `eigh`, the reference's own call, lib/teatgt.py:253 — eigenvectors are
+not unique, so parity requires the same solver).  No CPU fallback: CPU tensors raise.
+
+Round-1 scope: rows G0-G10 of SURVEY.md §8a, forward and backward, one video or a batch
+(`tempura.collate_entries`).  The train-only consistency regulariser (R1-R3: third-party
+GraphTransformer over per-frame graphs, detached in the reference) is not on the CUDA path yet:
+`structure_temp_loss` / `semantic_temp_loss` are returned empty unless `regulariser_fn` is set.
+"""
+import math
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .tokengt_fn import AssembleTokens, AttnPlan, NodeHead, NodeTokens, PreLNAttention, PreLNFeedForward
+
+CLIP_SIZE = 5
+SPATIAL_THR = 0.5
+SIM_THR = 0.75
+
+
+# ================================================================================================
+# parameter containers (names / shapes follow tools/TokenGT/tokengt)
+# ================================================================================================
+class _Tokenizer(nn.Module):
+    def __init__(self, num_atoms, hidden, lap_k):
+        super().__init__()
+        self.atom_encoder = nn.Linear(num_atoms, hidden)
+        self.temp_encoder = nn.Embedding(100, hidden, padding_idx=0)
+        self.edge_encoder = nn.Embedding(5, hidden, padding_idx=0)
+        self.graph_token = nn.Embedding(1, hidden)
+        self.null_token = nn.Embedding(1, hidden)
+        self.lap_encoder = nn.Linear(2 * lap_k, hidden, bias=False)
+        self.order_encoder = nn.Embedding(3, hidden)
+
+
+class _MHA(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.k_proj = nn.Linear(dim, dim)
+        self.v_proj = nn.Linear(dim, dim)
+        self.q_proj = nn.Linear(dim, dim)
+        self.out_proj = nn.Linear(dim, dim)
+
+
+class _FFN(nn.Module):
+    def __init__(self, dim, ffn):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, ffn)
+        self.fc2 = nn.Linear(ffn, dim)
+
+
+class _Layer(nn.Module):
+    def __init__(self, dim, ffn):
+        super().__init__()
+        self.self_attn = _MHA(dim)
+        self.self_attn_layer_norm = nn.LayerNorm(dim)
+        self.feedforward = _FFN(dim, ffn)
+        self.final_layer_norm = nn.LayerNorm(dim)
+
+
+class _GraphEncoder(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        d = args.encoder_embed_dim
+        self.graph_feature = _Tokenizer(args.num_atoms, d, args.lap_node_id_k)
+        self.final_layer_norm = nn.LayerNorm(d)        # created by the reference, never applied
+        self.layers = nn.ModuleList([_Layer(d, args.encoder_ffn_embed_dim) for _ in range(args.encoder_layers)])
+
+
+class TokenGTEncoder(nn.Module):
+    """tools/TokenGT/tokengt/models/tokengt.py:34-97 (parameters only; evaluation is in tokengt_fn.py)."""
+
+    def __init__(self, args):
+        super().__init__()
+        d = args.encoder_embed_dim
+        for flag in ("rand_node_id", "orf_node_id", "lap_node_id_sign_flip"):
+            if getattr(args, flag, False):
+                raise NotImplementedError("%s is off in the reference's documented command and not accelerated" % flag)
+        if not args.lap_node_id or not args.type_id:
+            raise NotImplementedError("the accelerated path is the documented --lap_node_id --type_id configuration")
+        self.graph_encoder = _GraphEncoder(args)
+        self.masked_lm_pooler = nn.Linear(d, d)        # unused by the reference forward
+        self.lm_head_transform_weight = nn.Linear(d, d)
+        self.layer_norm = nn.LayerNorm(d)
+        self.lm_output_learned_bias = nn.Parameter(torch.zeros(args.num_output))
+        self.embed_out = nn.Linear(d, args.num_output, bias=False)
+
+
+class _ObjectClassifier(nn.Module):
+    """tools/utils/object_classifier.py (obj_head='linear'); PredCLS forward is pred_labels = labels."""
+
+    def __init__(self, num_classes, mode):
+        super().__init__()
+        self.mode = mode
+        self.obj_memory = []
+        self.obj_embed = nn.Embedding(num_classes - 1, 200)
+        self.pos_embed = nn.Sequential(nn.BatchNorm1d(4, momentum=0.001), nn.Linear(4, 128), nn.ReLU(inplace=True),
+                                       nn.Dropout(0.1))
+        self.intermediate = nn.Sequential(nn.Linear(2048 + 200 + 128, 1024), nn.BatchNorm1d(1024), nn.ReLU())
+        self.decoder_lin = nn.Sequential(nn.Linear(1024, num_classes))
+
+    def forward(self, entry, phase="train", unc=False):
+        entry["pred_labels"] = entry["labels"]
+        return entry
+
+
+# ================================================================================================
+# host plan of the ragged structure
+# ================================================================================================
+def edge_threshold(video_size):
+    return float(np.round(np.sqrt(video_size[0] ** 2 + video_size[1] ** 2) * SPATIAL_THR, 4))
+
+
+class TeatPlan:
+    """Integer artefacts of lib/teatgt.py:104-240 + tokenizer.py:98-109 for a batch of videos.
+
+    Stage 1 (constructor, from per-frame pair counts and pair_idx): node layout in the reference's
+    token order (per frame: person, then objects in pair order), clips of 5 frames per video.
+    Stage 2 (`build_graph`, from the device-computed edge predicates): per-clip edge lists in the
+    reference's order, token descriptors, sequence offsets, Laplacian eigenvectors."""
+
+    def __init__(self, counts, frames_per_video, pair_idx_h):
+        c = np.asarray(counts, dtype=np.int64)
+        fpv = np.asarray(frames_per_video, dtype=np.int64)
+        assert (c > 0).all(), "every frame needs at least one pair"
+        F = c.shape[0]
+        off = np.zeros(F + 1, dtype=np.int64)
+        off[1:] = np.cumsum(c)
+        self.N, self.F, self.V = int(off[-1]), F, fpv.shape[0]
+        nodes_pf = c + 1
+        node_off = np.zeros(F + 1, dtype=np.int64)
+        node_off[1:] = np.cumsum(nodes_pf)
+        n_nodes = int(node_off[-1])
+        frame_of_node = np.repeat(np.arange(F), nodes_pf)
+        local = np.arange(n_nodes) - node_off[frame_of_node]
+        is_person = (local == 0)
+        pair_of_node = off[frame_of_node] + np.maximum(local - 1, 0)
+        pidx = np.asarray(pair_idx_h, dtype=np.int64)
+        feat_row = np.where(is_person, pidx[pair_of_node, 0], pidx[pair_of_node, 1])
+        vf_off = np.zeros(self.V + 1, dtype=np.int64)
+        vf_off[1:] = np.cumsum(fpv)
+        video_of_frame = np.repeat(np.arange(self.V), fpv)
+        frame_in_video = np.arange(F) - vf_off[video_of_frame]
+        clips_pv = (fpv + CLIP_SIZE - 1) // CLIP_SIZE
+        clip_base = np.concatenate([[0], np.cumsum(clips_pv)])
+        self.clip_of_frame = clip_base[video_of_frame] + frame_in_video // CLIP_SIZE
+        self.n_clips = int(clip_base[-1])
+        self.frame_rel = frame_in_video % CLIP_SIZE
+        self.has_prev_h = (self.frame_rel != 0).astype(np.int32)
+        self.node_off_h = node_off
+        self.frame_of_node = frame_of_node
+        self.n_nodes, self.nmax = n_nodes, int(nodes_pf.max())
+        self.feat_row_h = feat_row.astype(np.int32)
+        self.is_person_h = is_person.astype(np.int32)
+        self.clip_of_node = self.clip_of_frame[frame_of_node]
+        nodes_pc = np.bincount(self.clip_of_node, minlength=self.n_clips)
+        self.clip_node_off = np.concatenate([[0], np.cumsum(nodes_pc)])
+        self.obj_node = (node_off[np.repeat(np.arange(F), c)] + 1 + (np.arange(self.N) - np.repeat(off[:-1], c)))
+        self.edges = None
+
+    def to(self, device):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.feat_row, self.is_person = t(self.feat_row_h), t(self.is_person_h)
+        self.node_off, self.has_prev = t(self.node_off_h.astype(np.int32)), t(self.has_prev_h)
+        self.device = device
+        return self
+
+    # ---------------------------------------------------------------------------------------
+    def build_graph(self, spatial, temporal, lap_k, eig_threads=8):
+        """spatial / temporal: uint8 [F, nmax, nmax] predicate matrices (host numpy)."""
+        node_off, F = self.node_off_h, self.F
+        sf, sa, sb = np.nonzero(spatial)                        # row-major = itertools.combinations order
+        tf, tp, tc = np.nonzero(temporal)                       # row-major = itertools.product(prev, cur) order
+        ev_frame = np.concatenate([sf, tf])
+        ev_kind = np.concatenate([np.zeros_like(sf), np.ones_like(tf)])
+        ev_u = np.concatenate([node_off[sf] + sa, node_off[np.maximum(tf - 1, 0)] + tp])
+        ev_v = np.concatenate([node_off[sf] + sb, node_off[tf] + tc])
+        order = np.lexsort((np.arange(ev_frame.shape[0]), ev_kind, ev_frame))
+        ev_frame, ev_kind, ev_u, ev_v = ev_frame[order], ev_kind[order], ev_u[order], ev_v[order]
+        # every undirected hit yields (u,v) then (v,u)
+        e_u = np.stack([ev_u, ev_v], 1).reshape(-1)
+        e_v = np.stack([ev_v, ev_u], 1).reshape(-1)
+        e_kind = np.repeat(ev_kind, 2)
+        e_clip = np.repeat(self.clip_of_frame[ev_frame], 2)
+        edges_pc = np.bincount(e_clip, minlength=self.n_clips)
+        if (edges_pc == 0).any():
+            raise RuntimeError("edge-less clip: the reference's fallback reads stale loop variables "
+                               "(lib/teatgt.py:229-234); not reproduced")
+        edge_off = np.concatenate([[0], np.cumsum(edges_pc)])
+        nodes_pc = np.diff(self.clip_node_off)
+        T_c = 2 + nodes_pc + edges_pc
+        seq_off = np.concatenate([[0], np.cumsum(T_c)])
+        T = int(seq_off[-1])
+        desc = np.zeros((T, 4), dtype=np.int32)
+        desc[seq_off[:-1], 0] = 0
+        desc[seq_off[:-1] + 1, 0] = 1
+        node_tok = seq_off[self.clip_of_node] + 2 + (np.arange(self.n_nodes) - self.clip_node_off[self.clip_of_node])
+        desc[node_tok, 0] = 2
+        desc[node_tok, 1] = np.arange(self.n_nodes)
+        desc[node_tok, 2] = self.frame_rel[self.frame_of_node]
+        edge_tok = seq_off[e_clip] + 2 + nodes_pc[e_clip] + (np.arange(e_u.shape[0]) - edge_off[e_clip])
+        desc[edge_tok, 0] = 3
+        desc[edge_tok, 1] = e_u
+        desc[edge_tok, 2] = e_v
+        desc[edge_tok, 3] = e_kind
+        self.seq_off_h, self.desc_h, self.node_tok_h = seq_off, desc, node_tok.astype(np.int32)
+        self.edges = (e_u, e_v, e_kind, e_clip, edge_off)
+        self.T, self.max_T = T, int(T_c.max())
+        # ---- Laplacian eigenvectors per clip (lib/teatgt.py:243-254), host LAPACK like the reference
+        kp = (lap_k + 7) // 8 * 8
+        ev_all = np.zeros((self.n_nodes, kp), dtype=np.float32)
+        lu = e_u - self.clip_node_off[e_clip]
+        lv = e_v - self.clip_node_off[e_clip]
+
+        def solve(cl):
+            n = int(nodes_pc[cl])
+            a, b = int(edge_off[cl]), int(edge_off[cl + 1])
+            A = np.zeros((n, n), dtype=np.float64)
+            np.add.at(A, (lv[a:b], lu[a:b]), 1.0)
+            deg = np.bincount(lv[a:b], minlength=n)
+            nm = (torch.from_numpy(deg).clip(1) ** -0.5).numpy()      # float32 values, like the reference
+            Nm = np.diag(nm)
+            L = np.eye(n) - Nm @ A @ Nm
+            _, vec = np.linalg.eigh(L)
+            vec = vec.astype(np.float32)
+            k = min(lap_k, n)
+            ev_all[self.clip_node_off[cl]:self.clip_node_off[cl + 1], :k] = vec[:, :k]
+
+        if self.n_clips <= 4 or eig_threads <= 1:
+            for cl in range(self.n_clips):
+                solve(cl)
+        else:
+            with ThreadPoolExecutor(eig_threads) as pool:
+                list(pool.map(solve, range(self.n_clips)))
+        self.eigvec_h = ev_all
+        return self
+
+    def clip_edge_index(self, cl):
+        """(edge_index [2,E] int64 clip-local, edge_data [E] int32) of clip `cl` — the parity artefacts."""
+        e_u, e_v, e_kind, e_clip, edge_off = self.edges
+        a, b = int(edge_off[cl]), int(edge_off[cl + 1])
+        base = self.clip_node_off[cl]
+        return (torch.from_numpy(np.stack([e_u[a:b] - base, e_v[a:b] - base]).astype(np.int64)),
+                torch.from_numpy(e_kind[a:b].astype(np.int32)))
+
+
+# ================================================================================================
+# the model
+# ================================================================================================
+class TEAT_GT(nn.Module):
+
+    def __init__(self, mode="predcls", attention_class_num=None, spatial_class_num=None, contact_class_num=None,
+                 obj_classes=None, tracking=None, args=None, embed_vecs=None):
+        super().__init__()
+        if mode != "predcls" or tracking:
+            raise NotImplementedError("b200vsgg.TEAT_GT accelerates the PredCLS path (SURVEY.md §8); SGCls/SGDet need "
+                                      "the tracking object branch (row S1), a 'next' row")
+        self.obj_classes, self.mode, self.tracking, self.args = obj_classes, mode, tracking, args
+        self.attention_class_num, self.spatial_class_num, self.contact_class_num = (
+            attention_class_num, spatial_class_num, contact_class_num)
+        self.object_classifier = _ObjectClassifier(len(obj_classes), mode)
+        self.subj_fc = nn.Linear(2048, 968)
+        self.obj_fc = nn.Linear(2048, 968)
+        if embed_vecs is None:  # stand-in for GloVe-6B-200d, seeded
+            embed_vecs = torch.randn(len(obj_classes), 200, generator=torch.Generator().manual_seed(len(obj_classes)))
+        self.node_label_tokenizer = nn.Embedding(len(obj_classes), 200)
+        self.node_label_tokenizer.weight.data = embed_vecs.clone()
+        self.TokenGT_encoder = TokenGTEncoder(args)
+        self.TokenGT_model = nn.Module()
+        self.TokenGT_model.encoder = self.TokenGT_encoder              # alias, lib/teatgt.py:61-62
+        self.gate_nn = nn.Linear(10, 1)
+        self.gate_sem_nn = nn.Linear(768, 1)
+        self.gate_gru_nn = nn.Linear(768, 1)
+        for alias, lin in (("gap", self.gate_nn), ("gap_sem", self.gate_sem_nn), ("gap_gru", self.gate_gru_nn)):
+            holder = nn.Module()
+            holder.gate_nn = lin
+            setattr(self, alias, holder)
+        self.n_heads = args.encoder_attention_heads
+        self.lap_k = args.lap_node_id_k
+        self.eig_dropout = float(getattr(args, "lap_node_id_eig_dropout", 0.0))
+        self.dropout_p = 0.1            # dropout = attention_dropout = activation_dropout = 0.1 (models/tokengt.py:69-71)
+        self.eig_threads = 8
+        self.last_plan = None
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, entry, phase="train", unc=False):
+        entry = self.object_classifier(entry, phase=phase, unc=unc)
+        feats = entry["features"]
+        if not feats.is_cuda:
+            raise RuntimeError("b200vsgg.TEAT_GT runs only on CUDA tensors (no CPU fallback for the hot path)")
+        dev = feats.device
+        fpv = entry.get("video_frames")
+        counts = entry.get("frame_counts_host")
+        if counts is None:
+            n_frames = int(fpv.sum()) if fpv is not None else int(entry["im_idx"][-1].item()) + 1
+            offs = ops.frame_offsets(entry["im_idx"].contiguous(), n_frames).cpu().numpy().astype(np.int64)
+            counts = np.diff(offs)
+        if fpv is None:
+            fpv = np.asarray([len(counts)])
+        pair_h = entry.get("pair_idx_host")
+        if pair_h is None:
+            pair_h = entry["pair_idx"].cpu().numpy()
+        plan = TeatPlan(counts, fpv, pair_h).to(dev)
+        self.last_plan = plan
+        enc = self.TokenGT_encoder
+        tk = enc.graph_encoder.graph_feature
+        train = self.training
+        p = self.dropout_p if train else 0.0
+        seed0 = int(torch.randint(0, 2 ** 40, (1,)).item()) if train else 0
+
+        # ---- G1/G2: node tokens in the reference's order
+        featb = ops.cast_bf16(feats.contiguous())
+        tok, tokb = NodeTokens.apply(featb, self.subj_fc.weight, self.subj_fc.bias, self.obj_fc.weight, self.obj_fc.bias,
+                                     self.node_label_tokenizer.weight, entry["pred_labels"].contiguous(), plan.feat_row,
+                                     plan.is_person)
+        # ---- G4: edge predicates on the device, edge lists + G5 eigenvectors on the host
+        thr = edge_threshold(entry["video_size"])
+        sp, tp = ops.teat_pair_flags(tok.detach(), entry["boxes"].contiguous(), plan.feat_row, plan.node_off,
+                                     plan.has_prev, thr, SIM_THR, plan.nmax)
+        plan.build_graph(sp.cpu().numpy(), tp.cpu().numpy(), self.lap_k, self.eig_threads)
+        desc = torch.from_numpy(plan.desc_h).to(dev)
+        ev = torch.from_numpy(plan.eigvec_h).to(dev)
+        evb = ops.cast_bf16(ev, drop_p=self.eig_dropout if train else 0.0, seed=seed0 + 17)
+        aplan = AttnPlan(plan.seq_off_h, dev)
+        node_rows = torch.from_numpy(plan.node_tok_h).to(dev)
+
+        # ---- G6: tokenizer
+        x = AssembleTokens.apply(tok, tokb, evb, tk.atom_encoder.weight, tk.atom_encoder.bias, tk.lap_encoder.weight,
+                                 tk.temp_encoder.weight, tk.edge_encoder.weight, tk.order_encoder.weight,
+                                 tk.graph_token.weight, tk.null_token.weight, desc, self.lap_k)
+        dbg = getattr(self, "_debug", None)
+        if dbg is not None:
+            dbg["tok"], dbg["x0"], dbg["layers"] = tok.detach(), x.detach(), []
+        if p > 0:
+            x = torch.nn.functional.dropout(x, p, True)
+        # ---- G7: encoder
+        for i, layer in enumerate(enc.graph_encoder.layers):
+            a, f = layer.self_attn, layer.feedforward
+            x = PreLNAttention.apply(x, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias,
+                                     a.q_proj.weight, a.q_proj.bias, a.k_proj.weight, a.k_proj.bias, a.v_proj.weight,
+                                     a.v_proj.bias, a.out_proj.weight, a.out_proj.bias, aplan, self.n_heads, p, p,
+                                     seed0 + 1000 * (i + 1))
+            x = PreLNFeedForward.apply(x, layer.final_layer_norm.weight, layer.final_layer_norm.bias, f.fc1.weight,
+                                       f.fc1.bias, f.fc2.weight, f.fc2.bias, p, p, seed0 + 1000 * (i + 1) + 500)
+            if dbg is not None:
+                dbg["layers"].append(x.detach())
+        # ---- G8: head on the node rows; objects only in the output
+        logits, hidden = NodeHead.apply(x, node_rows, enc.lm_head_transform_weight.weight,
+                                        enc.lm_head_transform_weight.bias, enc.layer_norm.weight, enc.layer_norm.bias,
+                                        enc.embed_out.weight, enc.lm_output_learned_bias)
+        if dbg is not None:
+            dbg["logits"], dbg["hidden"] = logits.detach(), hidden.detach()
+        obj = torch.from_numpy(plan.obj_node).to(dev)
+        g = logits[obj]
+        # ---- G10
+        entry["attention_distribution"] = torch.softmax(g[:, :3], -1)
+        entry["spatial_distribution"] = torch.sigmoid(g[:, 3:9])
+        entry["contacting_distribution"] = torch.sigmoid(g[:, 9:])
+        entry["hidden_x"] = hidden                     # [nodes, 768] (extension: what the regulariser consumes)
+        entry["structure_temp_loss"] = torch.zeros(0, device=dev)
+        entry["semantic_temp_loss"] = torch.zeros(0, device=dev)
+        return entry

@@ -48,17 +48,6 @@ def import_reference_teatgt():
     return ref
 
 
-def teatgt_seeded_init_(model, seed):
-    """seeded_init_ + the zero rows that nn.Embedding(padding_idx=0) keeps in the real model."""
-    from b200vsgg import synthetic
-    synthetic.seeded_init_(model, seed)
-    with torch.no_grad():
-        for name, p in model.state_dict().items():
-            if name.endswith("temp_encoder.weight") or name.endswith("edge_encoder.weight"):
-                p[0].zero_()
-    return model
-
-
 def main():
     from b200vsgg import synthetic
     from oracle.teatgt_oracle import TeatgtOracle
@@ -66,7 +55,7 @@ def main():
     classes = synthetic.ag_object_classes()
     args = types.SimpleNamespace(**ARGS)
     ref = ref_mod.TEAT_GT(obj_classes=classes, args=args, **MODEL_KW)
-    teatgt_seeded_init_(ref, synthetic.BASE_SEED)
+    synthetic.teatgt_seeded_init_(ref, synthetic.BASE_SEED)
     ref.eval()
     orc = TeatgtOracle(obj_classes=classes, args=args, **MODEL_KW)
     print("state_dict interchange (strict):", orc.load_state_dict(ref.state_dict(), strict=True))

@@ -1,0 +1,137 @@
+"""Parity of b200vsgg.TEAT_GT (CUDA path through the C-ABI) against the golden vectors written by the
+UNMODIFIED reference (tests/golden/teatgt_*.pt) and against the CPU oracle, forward and backward.
+
+Stated tolerances (bf16 operands, fp32 accumulation, fp32 residual stream, 12 pre-LN layers):
+  distributions   max-abs <= 5e-3, identical top-1 wherever the reference's margin exceeds the tolerance
+  edge lists      bit-exact (edge_index / edge_data per clip, reference order)
+  gradients       rel-L2 <= 6e-2 per parameter tensor (<= 1e-1 for q_proj / k_proj, see QK_GRAD_REL_TOL)
+"""
+import os
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DIST_TOL = 5e-3
+GRAD_REL_TOL = 6e-2
+QK_GRAD_REL_TOL = 1e-1   # q/k projections: gradients flow only through the softmax Jacobian of near-uniform
+                         # attention (tiny, cancellation-prone), so bf16 noise is relatively larger there
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+
+
+def _entry(case, device=None):
+    from b200vsgg import synthetic
+    e = synthetic.make_video_entry(**case)
+    e.pop("union_feat"), e.pop("spatial_masks")
+    if device:
+        e = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in e.items()}
+    return e
+
+
+@pytest.fixture(scope="module")
+def pair(cuda_lib):
+    from b200vsgg import synthetic, teatgt
+    from oracle.teatgt_oracle import TeatgtOracle
+    gold = _load("teatgt_small")
+    args = types.SimpleNamespace(**gold["args"])
+    classes = synthetic.ag_object_classes()
+    m = teatgt.TEAT_GT(obj_classes=classes, args=args, **gold["model_kw"])
+    synthetic.teatgt_seeded_init_(m, gold["seed"])
+    o = TeatgtOracle(obj_classes=classes, args=args, with_regulariser=False, **gold["model_kw"])
+    o.load_state_dict(m.state_dict(), strict=True)
+    return m.cuda(), o
+
+
+@pytest.mark.parametrize("name", ["teatgt_small", "teatgt_ragged"])
+def test_forward_matches_reference_golden(pair, name):
+    m, _ = pair
+    gold = _load(name)
+    m.eval()
+    with torch.no_grad():
+        out = m(_entry(gold["case"], "cuda"), phase="test")
+    plan = m.last_plan
+    assert plan.n_clips == len(gold["clips"])
+    for cl, ref in enumerate(gold["clips"]):
+        ei, ed = plan.clip_edge_index(cl)
+        assert torch.equal(ei, ref["edge_index"]) and torch.equal(ed, ref["edge_data"]), cl
+    for k in ("attention_distribution", "spatial_distribution", "contacting_distribution"):
+        got, ref = out[k].float().cpu(), gold["test/" + k]
+        err = (got - ref).abs().max().item()
+        assert err <= DIST_TOL, (k, err)
+        top2 = ref.topk(2, dim=1).values
+        sure = (top2[:, 0] - top2[:, 1]) > 2 * DIST_TOL
+        assert torch.equal(got.argmax(1)[sure], ref.argmax(1)[sure])
+
+
+def test_backward_matches_oracle(pair):
+    from b200vsgg import synthetic
+    from oracle.teatgt_oracle import teatgt_losses
+    m, o = pair
+    case = dict(video_index=7, num_frames=8, pairs_per_frame=(2, 5))
+    entry = _entry(case)
+    att, spa, con = synthetic.build_gt_tensors(entry)
+    o.train()
+    o.TokenGT_encoder.p = 0.0
+    o.zero_grad()
+    po = o(dict(entry), phase="train")
+    lo = sum(teatgt_losses(po, att, spa, con).values())
+    lo.backward()
+    m.train()
+    m.dropout_p, m.eig_dropout = 0.0, 0.0
+    m.zero_grad()
+    pm = m(_entry(case, "cuda"), phase="train")
+    lm = sum(teatgt_losses(pm, att.cuda(), spa.cuda(), con.cuda()).values())
+    lm.backward()
+    m.dropout_p, m.eig_dropout = 0.1, 0.2
+    assert abs(lm.item() - lo.item()) < 2e-3 * abs(lo.item()), (lm.item(), lo.item())
+    og = dict(o.named_parameters())
+    errs, unused = [], []
+    for name, p in m.named_parameters():
+        ref = og[name].grad
+        if ref is None or ref.norm().item() < 1e-7:   # unused, or mathematically zero (key bias under softmax)
+            assert p.grad is None or p.grad.norm().item() < 1e-4, name
+            unused.append(name)
+            continue
+        assert p.grad is not None, name
+        rel = (p.grad.float().cpu() - ref).norm().item() / ref.norm().item()
+        errs.append((rel, name))
+    errs.sort(reverse=True)
+    print("largest gradient rel-L2 errors:", errs[:8], "params without gradient:", len(unused))
+    for rel, name in errs:
+        tol = QK_GRAD_REL_TOL if (".q_proj." in name or ".k_proj." in name) else GRAD_REL_TOL
+        assert rel <= tol, (name, rel, errs[:5])
+    assert len(errs) > 190
+    m.eval()
+
+
+def test_batched_videos_equal_per_video_runs(pair):
+    from b200vsgg import tempura
+    m, _ = pair
+    m.eval()
+    cases = [dict(video_index=30 + i, num_frames=f, pairs_per_frame=ppf) for i, (f, ppf) in enumerate([(6, (2, 4)), (11, (1, 3)), (5, 3)])]
+    with torch.no_grad():
+        singles = [m(_entry(c, "cuda"), phase="test") for c in cases]
+        batch = tempura.collate_entries([_entry(c, "cuda") for c in cases])
+        outb = m(batch, phase="test")
+    for k in ("attention_distribution", "spatial_distribution", "contacting_distribution"):
+        cat = torch.cat([s[k] for s in singles])
+        assert (outb[k] - cat).abs().max().item() <= 1e-3, k
+
+
+def test_train_mode_runs_with_dropout(pair):
+    m, _ = pair
+    m.train()
+    m.zero_grad()
+    torch.manual_seed(0)
+    out = m(_entry(dict(video_index=50, num_frames=7, pairs_per_frame=(2, 6)), "cuda"), phase="train")
+    loss = out["attention_distribution"].log().mean() + out["spatial_distribution"].mean() + out["contacting_distribution"].mean()
+    loss.backward()
+    assert torch.isfinite(loss)
+    g = m.TokenGT_encoder.graph_encoder.layers[0].self_attn.q_proj.weight.grad
+    assert g is not None and torch.isfinite(g).all()
+    m.eval()
