@@ -252,6 +252,12 @@ int b200vsgg_teat_assemble_bwd(const int32_t* desc, int32_t n_tokens, int32_t d,
 int b200vsgg_act_dropout_bf16(const void* x, int32_t ld_x, int64_t rows, int32_t cols, int32_t act, float p, uint64_t seed,
                               void* out, int32_t ld_o, void* stream);
 
+/* Pairwise graph temporal-consistency reduction (lib/teatgt.py:325-334): out[p] =
+ * KLDiv_batchmean(log_softmax(g[pair_u[p]]), softmax(g[pair_v[p]])) / (pair_v[p] - pair_u[p]); g fp32 [frames, d]
+ * (frame indices are absolute, so v - u is the frame distance inside the clip). */
+int b200vsgg_consistency_kl(const float* g, int32_t d, const int32_t* pair_u, const int32_t* pair_v, int32_t n_pairs,
+                            float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -457,3 +457,13 @@ def act_dropout(x, act, p=0.0, seed=0, out=None):
                                                 out.stride(0), _stream()), "act_dropout_bf16")
     _count()
     return out
+
+
+def consistency_kl(g, pair_u, pair_v):
+    """out[p] = KL(softmax(g[v]) || softmax(g[u])) / (v - u) for the frame pairs (u < v) of each clip."""
+    assert g.dtype == torch.float32 and g.is_contiguous() and pair_u.dtype == torch.int32 and pair_v.dtype == torch.int32
+    out = torch.empty(pair_u.numel(), device=g.device, dtype=torch.float32)
+    check(_lib.lib().b200vsgg_consistency_kl(_ptr(g), g.shape[1], _ptr(pair_u), _ptr(pair_v), pair_u.numel(), _ptr(out),
+                                              _stream()), "consistency_kl")
+    _count()
+    return out

@@ -1,0 +1,183 @@
+"""Adjacent-frame graph temporal-consistency regulariser (rows R1-R3 of SURVEY.md §8a;
+lib/teatgt.py:285-334, 350-351 of the reference), batched over every frame of every clip.
+
+As released, the reference detaches both loss vectors (`torch.tensor(list_of_scalars)`,
+lib/teatgt.py:350-351), so they carry no gradient; this implementation is forward-only to match.
+
+Per frame: spatial-only graph -> normalised Laplacian -> eigenvectors (host LAPACK, the reference's call
+:300) -> first 10 columns -> GraphTransformer(dim 10) -> attention pooling -> structure embedding [10];
+clip hidden rows [0:n_f] (the reference's `savor` never advances, :312-314) -> GraphTransformer(dim 768)
+-> attention pooling -> semantic embedding [768].  All frame pairs of a clip: KL / frame distance
+(b200vsgg_consistency_kl, warp-shuffle reduction), kept where >= 0.
+
+PARITY UNPINNED: GraphTransformer / GlobalAttentionPooling come from `graph_transformer_pytorch` and `dgl`,
+absent from the reference tree and unversioned there; the arithmetic restates their published algorithms
+ and is checked against the oracle's restatement only.  The 768-wide projections run on
+the tcgen05 GEMM; the per-frame attention cores ([frames, 8, <=11, <=11]) and the 10-wide branch are
+batched torch ops on padded tensors (tiny, not on the roofline).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, dim_head, heads, edge_dim):
+        super().__init__()
+        inner = dim_head * heads
+        self.heads, self.dim_head = heads, dim_head
+        self.to_q = nn.Linear(dim, inner)
+        self.to_kv = nn.Linear(dim, inner * 2)
+        self.edges_to_kv = nn.Linear(edge_dim, inner)
+        self.to_out = nn.Linear(inner, dim)
+
+
+class _PreNorm(nn.Module):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.fn, self.norm = fn, nn.LayerNorm(dim)
+
+
+class _GatedResidual(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.proj = nn.Sequential(nn.Linear(dim * 3, 1, bias=False), nn.Sigmoid())
+
+
+class GraphTransformer(nn.Module):
+    """Parameters of graph_transformer_pytorch.GraphTransformer(dim, depth, edge_dim=1, with_feedforwards=True,
+    gated_residual=True, rel_pos_emb=True) (defaults dim_head 64, heads 8); evaluation in `run_batched`."""
+
+    def __init__(self, dim, depth, dim_head=64, heads=8, edge_dim=1):
+        super().__init__()
+        self.dim, self.dim_head, self.heads = dim, dim_head, heads
+        self.layers = nn.ModuleList()
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                nn.ModuleList([_PreNorm(dim, _Attention(dim, dim_head, heads, edge_dim)), _GatedResidual(dim)]),
+                nn.ModuleList([_PreNorm(dim, nn.Sequential(nn.Linear(dim, dim * 4), nn.GELU(), nn.Linear(dim * 4, dim))),
+                               _GatedResidual(dim)])]))
+
+
+def _linear(x, lin):
+    """y = x W^T + b on [rows, in]; tcgen05 GEMM when the shapes allow TMA (in % 8 == 0), else torch (10-wide)."""
+    w, b = lin.weight, lin.bias
+    if x.is_cuda and w.shape[1] % 8 == 0 and w.shape[0] % 8 == 0:
+        out = torch.empty(x.shape[0], w.shape[0], device=x.device, dtype=torch.float32)
+        ops.gemm(ops.cast_bf16(x.contiguous()), ops.cast_bf16(w.detach().contiguous()),
+                 bias=b.detach() if b is not None else None, out_f32=out)
+        return out
+    return F.linear(x, w, b)
+
+
+def _rotary(n, dim_head, device):
+    inv = 1.0 / (10000 ** (torch.arange(0, dim_head, 2, device=device).float() / dim_head))
+    freqs = torch.einsum("i,j->ij", torch.arange(n, device=device).float(), inv)
+    return torch.repeat_interleave(freqs, 2, dim=-1)           # [n, dim_head]
+
+
+def _rot_half(x):
+    x = x.reshape(*x.shape[:-1], -1, 2)
+    x1, x2 = x.unbind(-1)
+    return torch.stack((-x2, x1), -1).flatten(-2)
+
+
+@torch.no_grad()
+def run_batched(gt, nodes, adj, counts):
+    """nodes [B, n, dim] (zero padded), adj [B, n, n] (edge feature = adjacency value), counts [B] -> [B, n, dim]."""
+    B, n, dim = nodes.shape
+    h, dh = gt.heads, gt.dim_head
+    key_ok = (torch.arange(n, device=nodes.device)[None, :] < counts[:, None])          # [B, n]
+    fr = _rotary(n, dh, nodes.device)
+    cos, sin = fr.cos()[None, None], fr.sin()[None, None]
+    x = nodes
+    for attn_block, ff_block in gt.layers:
+        pre, gate = attn_block
+        a = pre.fn
+        xn = F.layer_norm(x, (dim,), pre.norm.weight, pre.norm.bias)
+        flat = xn.reshape(B * n, dim)
+        q = _linear(flat, a.to_q).view(B, n, h, dh).permute(0, 2, 1, 3)
+        kv = _linear(flat, a.to_kv).view(B, n, 2, h, dh)
+        k, v = kv[:, :, 0].permute(0, 2, 1, 3), kv[:, :, 1].permute(0, 2, 1, 3)
+        q = q * cos + _rot_half(q) * sin
+        k = k * cos + _rot_half(k) * sin
+        we = a.edges_to_kv.weight[:, 0].view(h, dh)                 # e_ij = A_ij * we + be   (edge_dim = 1)
+        be = a.edges_to_kv.bias.view(h, dh)
+        qw = (q * we[None, :, None, :]).sum(-1)                     # [B, h, n]
+        qb = (q * be[None, :, None, :]).sum(-1)
+        sim = (q @ k.transpose(-1, -2) + qw[..., None] * adj[:, None] + qb[..., None]) * (dh ** -0.5)
+        sim = sim.masked_fill(~key_ok[:, None, None, :], float("-inf"))
+        att = sim.softmax(-1)
+        out = att @ v + (att * adj[:, None]).sum(-1, keepdim=True) * we[None, :, None, :] + be[None, :, None, :]
+        out = _linear(out.permute(0, 2, 1, 3).reshape(B * n, h * dh), a.to_out).view(B, n, dim)
+        g = torch.sigmoid(F.linear(torch.cat((out, x, out - x), -1), gate.proj[0].weight))
+        x = out * g + x * (1 - g)
+        pre2, gate2 = ff_block
+        xn = F.layer_norm(x, (dim,), pre2.norm.weight, pre2.norm.bias).reshape(B * n, dim)
+        ffo = _linear(F.gelu(_linear(xn, pre2.fn[0])), pre2.fn[2]).view(B, n, dim)
+        g = torch.sigmoid(F.linear(torch.cat((ffo, x, ffo - x), -1), gate2.proj[0].weight))
+        x = ffo * g + x * (1 - g)
+    return x
+
+
+def _pool(x, counts, gate_nn):
+    """dgl GlobalAttentionPooling: softmax over the frame's nodes of gate_nn(x), weighted sum -> [B, dim]."""
+    n = x.shape[1]
+    ok = torch.arange(n, device=x.device)[None, :] < counts[:, None]
+    gate = gate_nn(x).squeeze(-1).masked_fill(~ok, float("-inf")).softmax(-1)
+    return (gate[..., None] * x).sum(1)
+
+
+@torch.no_grad()
+def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_flags, hidden):
+    """Returns (structure_temp_loss [P], semantic_temp_loss [P']) for the batch described by `plan`
+    (teatgt.TeatPlan after build_graph); spatial_flags uint8 [F, nmax, nmax] (host); hidden [nodes, d_sem]."""
+    dev = hidden.device
+    F_, nmax = plan.F, plan.nmax
+    counts_h = np.diff(plan.node_off_h)
+    up = np.asarray(spatial_flags, dtype=np.float64)
+    A = up + up.transpose(0, 2, 1)                                   # both directions were added as edges
+    # ---- R1: per-frame Laplacian eigenvectors, grouped by node count (stacked LAPACK calls)
+    k = 10
+    ev = np.zeros((F_, nmax, k), dtype=np.float32)
+    for nf in np.unique(counts_h):
+        idx = np.nonzero(counts_h == nf)[0]
+        a = A[idx][:, :nf, :nf]
+        deg = a.sum(1)                                              # in-degree (symmetric)
+        nm = (torch.from_numpy(deg.astype(np.int64)).clip(1) ** -0.5).numpy().astype(np.float64)
+        L = np.eye(nf)[None] - nm[:, :, None] * a * nm[:, None, :]
+        _, vec = np.linalg.eigh(L)
+        vec = vec.astype(np.float32)
+        if k > nf:
+            vec = np.tile(vec, (1, 1, int(k / 2)))[:, :, :k]         # lib/teatgt.py:304-305
+        else:
+            vec = vec[:, :, :k]
+        ev[idx, :nf] = vec
+    counts = torch.from_numpy(counts_h).to(dev)
+    adj = torch.from_numpy(A.astype(np.float32)).to(dev)
+    nodes = torch.from_numpy(ev).to(dev)
+    sym = _pool(run_batched(gat, nodes, adj, counts), counts, gate_nn)                   # [F, 10]
+    # ---- R2: semantic nodes = the clip's hidden rows [0:n_f] (`savor` never advances)
+    clip_first_node = torch.from_numpy(plan.clip_node_off[plan.clip_of_frame]).to(dev)   # [F]
+    ar = torch.arange(nmax, device=dev)
+    rows = (clip_first_node[:, None] + ar[None, :]).clamp(max=hidden.shape[0] - 1)
+    ok = ar[None, :] < counts[:, None]
+    sem_nodes = hidden[rows] * ok[..., None]
+    sem = _pool(run_batched(gat_semantic, sem_nodes, adj, counts), counts, gate_sem_nn)  # [F, d_sem]
+    # ---- R3: all frame pairs u < v inside each clip, reference order
+    pu, pv = [], []
+    frames_pc = np.bincount(plan.clip_of_frame, minlength=plan.n_clips)
+    f0 = 0
+    for nf in frames_pc:
+        iu, iv = np.triu_indices(int(nf), 1)
+        pu.append(f0 + iu)
+        pv.append(f0 + iv)
+        f0 += int(nf)
+    pu = torch.from_numpy(np.concatenate(pu).astype(np.int32)).to(dev)
+    pv = torch.from_numpy(np.concatenate(pv).astype(np.int32)).to(dev)
+    s = ops.consistency_kl(sym.contiguous(), pu, pv)
+    m = ops.consistency_kl(sem.contiguous(), pu, pv)
+    return s[s >= 0], m[m >= 0]

@@ -13,9 +13,8 @@ eigenvectors (host LAPACK fp64 `eigh`, the reference's own call, lib/teatgt.py:2
 not unique, so parity requires the same solver).  No CPU fallback: CPU tensors raise.
 
 Round-1 scope: rows G0-G10 of SURVEY.md §8a, forward and backward, one video or a batch
-(`tempura.collate_entries`).  The train-only consistency regulariser (R1-R3: third-party
-GraphTransformer over per-frame graphs, detached in the reference) is not on the CUDA path yet:
-`structure_temp_loss` / `semantic_temp_loss` are returned empty unless `regulariser_fn` is set.
+(`tempura.collate_entries`), plus the train-only consistency regulariser R1-R3 (regulariser.py;
+detached like the reference, parity unpinned: third-party arithmetic).
 """
 import math
 from concurrent.futures import ThreadPoolExecutor
@@ -25,6 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .regulariser import GraphTransformer, consistency_losses
 from .tokengt_fn import AssembleTokens, AttnPlan, NodeHead, NodeTokens, PreLNAttention, PreLNFeedForward
 
 CLIP_SIZE = 5
@@ -282,6 +282,9 @@ class TEAT_GT(nn.Module):
         self.TokenGT_encoder = TokenGTEncoder(args)
         self.TokenGT_model = nn.Module()
         self.TokenGT_model.encoder = self.TokenGT_encoder              # alias, lib/teatgt.py:61-62
+        d_model = args.encoder_embed_dim
+        self.gat = GraphTransformer(dim=10, depth=4)                    # lib/teatgt.py:65-72
+        self.gat_semantic = GraphTransformer(dim=d_model, depth=4)      # lib/teatgt.py:74-81
         self.gate_nn = nn.Linear(10, 1)
         self.gate_sem_nn = nn.Linear(768, 1)
         self.gate_gru_nn = nn.Linear(768, 1)
@@ -294,6 +297,7 @@ class TEAT_GT(nn.Module):
         self.eig_dropout = float(getattr(args, "lap_node_id_eig_dropout", 0.0))
         self.dropout_p = 0.1            # dropout = attention_dropout = activation_dropout = 0.1 (models/tokengt.py:69-71)
         self.eig_threads = 8
+        self.compute_consistency = True  # phase='train' fills structure_temp_loss / semantic_temp_loss (R1-R3)
         self.last_plan = None
 
     # ------------------------------------------------------------------------------------------
@@ -331,7 +335,8 @@ class TEAT_GT(nn.Module):
         thr = edge_threshold(entry["video_size"])
         sp, tp = ops.teat_pair_flags(tok.detach(), entry["boxes"].contiguous(), plan.feat_row, plan.node_off,
                                      plan.has_prev, thr, SIM_THR, plan.nmax)
-        plan.build_graph(sp.cpu().numpy(), tp.cpu().numpy(), self.lap_k, self.eig_threads)
+        sp_h = sp.cpu().numpy()
+        plan.build_graph(sp_h, tp.cpu().numpy(), self.lap_k, self.eig_threads)
         desc = torch.from_numpy(plan.desc_h).to(dev)
         ev = torch.from_numpy(plan.eigvec_h).to(dev)
         evb = ops.cast_bf16(ev, drop_p=self.eig_dropout if train else 0.0, seed=seed0 + 17)
@@ -371,6 +376,11 @@ class TEAT_GT(nn.Module):
         entry["spatial_distribution"] = torch.sigmoid(g[:, 3:9])
         entry["contacting_distribution"] = torch.sigmoid(g[:, 9:])
         entry["hidden_x"] = hidden                     # [nodes, 768] (extension: what the regulariser consumes)
-        entry["structure_temp_loss"] = torch.zeros(0, device=dev)
-        entry["semantic_temp_loss"] = torch.zeros(0, device=dev)
+        if phase == "train" and self.compute_consistency:
+            # R1-R3, detached like the reference (lib/teatgt.py:350-351)
+            entry["structure_temp_loss"], entry["semantic_temp_loss"] = consistency_losses(
+                self.gat, self.gat_semantic, self.gate_nn, self.gate_sem_nn, plan, sp_h, hidden.detach())
+        else:
+            entry["structure_temp_loss"] = torch.zeros(0, device=dev)
+            entry["semantic_temp_loss"] = torch.zeros(0, device=dev)
         return entry

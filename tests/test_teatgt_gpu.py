@@ -42,7 +42,7 @@ def pair(cuda_lib):
     classes = synthetic.ag_object_classes()
     m = teatgt.TEAT_GT(obj_classes=classes, args=args, **gold["model_kw"])
     synthetic.teatgt_seeded_init_(m, gold["seed"])
-    o = TeatgtOracle(obj_classes=classes, args=args, with_regulariser=False, **gold["model_kw"])
+    o = TeatgtOracle(obj_classes=classes, args=args, with_regulariser=True, **gold["model_kw"])
     o.load_state_dict(m.state_dict(), strict=True)
     return m.cuda(), o
 
@@ -89,6 +89,13 @@ def test_backward_matches_oracle(pair):
     lm.backward()
     m.dropout_p, m.eig_dropout = 0.1, 0.2
     assert abs(lm.item() - lo.item()) < 2e-3 * abs(lo.item()), (lm.item(), lo.item())
+    # consistency regulariser (R1-R3; unpinned third-party arithmetic -> compared with the oracle's restatement):
+    # same number of frame pairs, values within 5 % (bf16 GEMMs in the 768-wide branch) + 1e-6 absolute
+    for key in ("structure_temp_loss", "semantic_temp_loss"):
+        got, ref = pm[key].float().cpu(), po[key]
+        assert got.shape == ref.shape and got.numel() > 0, (key, got.shape, ref.shape)
+        assert (got - ref).abs().max().item() <= 5e-2 * ref.abs().max().item() + 1e-6, (key, got[:6], ref[:6])
+        assert not pm[key].requires_grad
     og = dict(o.named_parameters())
     errs, unused = [], []
     for name, p in m.named_parameters():

@@ -1,0 +1,67 @@
+"""Secondary benchmark (not the driver's bench.py contract): TEAT-GT PredCLS fwd+loss+bwd on a batch of
+synthetic AG videos (BASELINE configs[2]-shaped graphs, PredCLS heads).  Prints one JSON line."""
+import argparse, json, os, sys, time, types
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from b200vsgg import ops, synthetic, teatgt, tempura
+
+ARGS = dict(num_atoms=1168, num_edges=1, num_output=26, lap_node_id=True, lap_node_id_k=50, lap_node_id_sign_flip=False,
+            lap_node_id_eig_dropout=0.2, rand_node_id=False, rand_node_id_dim=50, orf_node_id=False, orf_node_id_dim=50,
+            type_id=True, encoder_embed_dim=768, encoder_layers=12, encoder_attention_heads=32, encoder_ffn_embed_dim=768,
+            return_attention=True)
+ap = argparse.ArgumentParser()
+ap.add_argument("--videos", type=int, default=64)
+ap.add_argument("--frames", type=int, default=32)
+ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--infer", action="store_true")
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+m = teatgt.TEAT_GT(mode="predcls", attention_class_num=3, spatial_class_num=6, contact_class_num=17,
+                   obj_classes=synthetic.ag_object_classes(), tracking=False, args=types.SimpleNamespace(**ARGS))
+synthetic.teatgt_seeded_init_(m, 1123)
+m = m.to(dev)
+for p in m.object_classifier.parameters():
+    p.requires_grad_(False)
+entries = []
+for i in range(a.videos):
+    e = synthetic.make_video_entry(i, a.frames, (6, 10))
+    e.pop("union_feat"), e.pop("spatial_masks")
+    entries.append({k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in e.items()})
+gts = [synthetic.build_gt_tensors(e, dev) for e in entries]
+batch = tempura.collate_entries(entries)
+for k in ("attention_gt", "spatial_gt", "contacting_gt"):
+    batch.pop(k, None)
+att, spa, con = (torch.cat([g[i] for g in gts]) for i in range(3))
+batch["frame_counts_host"] = torch.bincount(batch["im_idx"].long()).cpu().numpy()
+batch["pair_idx_host"] = batch["pair_idx"].cpu().numpy()
+N = batch["pair_idx"].shape[0]
+
+def step():
+    if a.infer:
+        with torch.no_grad():
+            return m(dict(batch), phase="test")["attention_distribution"].sum()
+    m.zero_grad(set_to_none=True)
+    out = m(dict(batch), phase="train")
+    loss = (torch.nn.functional.cross_entropy(out["attention_distribution"], att)
+            + torch.nn.functional.binary_cross_entropy(out["spatial_distribution"], spa)
+            + torch.nn.functional.binary_cross_entropy(out["contacting_distribution"], con))
+    loss.backward()
+    return loss
+
+m.train(not a.infer)
+for _ in range(a.warmup):
+    step()
+torch.cuda.synchronize()
+l0 = ops.launch_count
+t0 = time.perf_counter()
+for _ in range(a.steps):
+    loss = step()
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / a.steps
+plan = m.last_plan
+print(json.dumps({"workload": "TEAT-GT PredCLS %s, %d videos x %d frames" % ("inference" if a.infer else "fwd+bwd", a.videos, a.frames),
+                  "pairs_per_s": N / dt, "ms_per_step": dt * 1e3, "pairs": N, "clips": plan.n_clips, "tokens": plan.T,
+                  "max_tokens_per_clip": plan.max_T, "launches_per_step": (ops.launch_count - l0) // a.steps,
+                  "loss": float(loss)}))

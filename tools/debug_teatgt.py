@@ -8,7 +8,7 @@ args = types.SimpleNamespace(**gold["args"])
 classes = synthetic.ag_object_classes()
 m = teatgt.TEAT_GT(obj_classes=classes, args=args, **gold["model_kw"])
 synthetic.teatgt_seeded_init_(m, gold["seed"])
-o = TO.TeatgtOracle(obj_classes=classes, args=args, with_regulariser=False, **gold["model_kw"])
+o = TO.TeatgtOracle(obj_classes=classes, args=args, with_regulariser=True, **gold["model_kw"])
 o.load_state_dict(m.state_dict(), strict=True)
 m = m.cuda().eval(); o.eval()
 e = synthetic.make_video_entry(**gold["case"]); e.pop("union_feat"); e.pop("spatial_masks")
