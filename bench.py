@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-videos", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-consistency", action="store_true", help="leave out the temporal-consistency regulariser")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + --steps steps, no e2e/cpu (for ncu runs)")
     ap.add_argument("--gemm-log", default=None, help="write the per-shape GEMM timing table to this file")
     return ap.parse_args()
@@ -168,7 +169,10 @@ def workload_config(args, world):
             "videos_per_gpu": args.videos, "frames_per_video": args.frames, "global_videos": args.videos * world,
             "parallelism": "videos sharded over %d GPU(s); gradient all-reduce only" % world,
             "l2": "inputs (3.4 GB/step/GPU) exceed the 126 MB L2",
-            "consistency_regulariser": False, "optimizer_in_step": False}
+            "consistency_regulariser": ("off" if getattr(args, "no_consistency", False) else
+                                        "on: TEAT-GT regulariser R1-R3 on TEMPURA's graphs, detached as in the reference "
+                                        "(lib/teatgt.py:350-351); extension, the reference's TEMPURA never fills these keys"),
+            "optimizer_in_step": False}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -191,6 +195,7 @@ def build_batch(video_indices, frames, device):
         batch.pop(k, None)
     batch["gt_tensors"] = tuple(torch.cat([g[i] for g in gts]) for i in range(3))
     batch["frame_counts_host"] = torch.bincount(batch["im_idx"].to(torch.int64)).cpu().numpy().astype(np.int64)
+    batch["pair_idx_host"] = batch["pair_idx"].cpu().numpy()      # the loader knows the pairing on the host
     return batch
 
 
@@ -217,7 +222,8 @@ def main():
 
     # ---- model (random init of the reference architecture) and this rank's shard of videos
     torch.manual_seed(1123)
-    model = tempura.TEMPURA(obj_classes=synthetic.ag_object_classes(), **MODEL_KW)
+    model = tempura.TEMPURA(obj_classes=synthetic.ag_object_classes(), consistency_regulariser=not args.no_consistency,
+                            **MODEL_KW)
     synthetic.seeded_init_(model, 1123)
     model = model.to(dev).train()
     for p in model.object_classifier.parameters():  # frozen in PredCLS, TEMPURA_train.py:106-108
@@ -232,6 +238,8 @@ def main():
         pred = model(dict(entry), phase="train")
         losses = tempura.tempura_loss(pred, model.last_plan)
         loss = losses["attention_relation_loss"] + losses["spatial_relation_loss"] + losses["contacting_relation_loss"]
+        if "structure_temp_loss" in pred:    # TEMPURA_train.py:215-218 (x2500; detached, so it only shifts the value)
+            loss = loss + 2500.0 * (pred["structure_temp_loss"].mean() + pred["semantic_temp_loss"].mean())
         loss.backward()
         if sync is not None:
             sync.sync()
@@ -350,6 +358,8 @@ def main():
                 entry = dict(dst)
                 entry["video_frames"] = batch["video_frames"]
                 entry["frame_counts_host"] = batch["frame_counts_host"]
+                entry["pair_idx_host"] = batch["pair_idx_host"]
+                entry["video_size"] = batch["video_size"]
                 entry["gt_tensors"] = gdst
                 loss = run_step(entry)
                 consumed[slot].record()

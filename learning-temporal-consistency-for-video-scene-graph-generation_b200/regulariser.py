@@ -85,42 +85,87 @@ def _rot_half(x):
     return torch.stack((-x2, x1), -1).flatten(-2)
 
 
+def _attention_core(q, k, v, a, adj, key_ok, cos, sin):
+    """q,k,v [B,h,n,dh] -> [B,h,n,dh]: rotary on q/k, per-edge key/value offsets e_ij = A_ij*we + be."""
+    h, dh = a.heads, a.dim_head
+    q = q * cos + _rot_half(q) * sin
+    k = k * cos + _rot_half(k) * sin
+    we = a.edges_to_kv.weight[:, 0].view(h, dh)
+    be = a.edges_to_kv.bias.view(h, dh)
+    qw = (q * we[None, :, None, :]).sum(-1)                         # [B, h, n]
+    qb = (q * be[None, :, None, :]).sum(-1)
+    sim = (q @ k.transpose(-1, -2) + qw[..., None] * adj[:, None] + qb[..., None]) * (dh ** -0.5)
+    sim = sim.masked_fill(~key_ok[:, None, None, :], float("-inf"))
+    att = sim.softmax(-1)
+    return att @ v + (att * adj[:, None]).sum(-1, keepdim=True) * we[None, :, None, :] + be[None, :, None, :]
+
+
+def _gate(out, res, proj_w):
+    """GatedResidual: sigmoid(W [out, res, out-res]) folded into two dot products."""
+    d = out.shape[-1]
+    w1, w2, w3 = proj_w[0, :d], proj_w[0, d:2 * d], proj_w[0, 2 * d:]
+    g = torch.sigmoid(out @ (w1 + w3) + res @ (w2 - w3))[..., None]
+    return out * g + res * (1 - g)
+
+
 @torch.no_grad()
 def run_batched(gt, nodes, adj, counts):
-    """nodes [B, n, dim] (zero padded), adj [B, n, n] (edge feature = adjacency value), counts [B] -> [B, n, dim]."""
+    """nodes [B, n, dim] (zero padded), adj [B, n, n] (edge feature = adjacency value), counts [B] -> [B, n, dim].
+    Wide graphs (dim % 8 == 0, CUDA) run row-compacted: LayerNorm and every projection through the C-ABI
+    kernels (bf16 operands, GELU fused in the GEMM epilogue); the 10-wide structure branch stays in torch."""
     B, n, dim = nodes.shape
     h, dh = gt.heads, gt.dim_head
-    key_ok = (torch.arange(n, device=nodes.device)[None, :] < counts[:, None])          # [B, n]
-    fr = _rotary(n, dh, nodes.device)
+    dev = nodes.device
+    key_ok = (torch.arange(n, device=dev)[None, :] < counts[:, None])                   # [B, n]
+    fr = _rotary(n, dh, dev)
     cos, sin = fr.cos()[None, None], fr.sin()[None, None]
-    x = nodes
+    fast = nodes.is_cuda and dim % 8 == 0
+    if not fast:
+        x = nodes
+        for attn_block, ff_block in gt.layers:
+            pre, gate = attn_block
+            a = pre.fn
+            flat = F.layer_norm(x, (dim,), pre.norm.weight, pre.norm.bias).reshape(B * n, dim)
+            q = F.linear(flat, a.to_q.weight, a.to_q.bias).view(B, n, h, dh).permute(0, 2, 1, 3)
+            kv = F.linear(flat, a.to_kv.weight, a.to_kv.bias).view(B, n, 2, h, dh)
+            out = _attention_core(q, kv[:, :, 0].permute(0, 2, 1, 3), kv[:, :, 1].permute(0, 2, 1, 3), a, adj, key_ok, cos, sin)
+            out = F.linear(out.permute(0, 2, 1, 3).reshape(B * n, h * dh), a.to_out.weight, a.to_out.bias).view(B, n, dim)
+            x = _gate(out, x, gate.proj[0].weight)
+            pre2, gate2 = ff_block
+            xn = F.layer_norm(x, (dim,), pre2.norm.weight, pre2.norm.bias)
+            x = _gate(pre2.fn[2](F.gelu(pre2.fn[0](xn))), x, gate2.proj[0].weight)
+        return x
+    rows = key_ok.reshape(-1).nonzero().flatten()                   # compact: valid node rows only
+    R = rows.numel()
+    x = nodes.reshape(B * n, dim)[rows].contiguous()
+    inner = h * dh
+    bf = lambda w: ops.cast_bf16(w.detach().contiguous())
     for attn_block, ff_block in gt.layers:
         pre, gate = attn_block
         a = pre.fn
-        xn = F.layer_norm(x, (dim,), pre.norm.weight, pre.norm.bias)
-        flat = xn.reshape(B * n, dim)
-        q = _linear(flat, a.to_q).view(B, n, h, dh).permute(0, 2, 1, 3)
-        kv = _linear(flat, a.to_kv).view(B, n, 2, h, dh)
-        k, v = kv[:, :, 0].permute(0, 2, 1, 3), kv[:, :, 1].permute(0, 2, 1, 3)
-        q = q * cos + _rot_half(q) * sin
-        k = k * cos + _rot_half(k) * sin
-        we = a.edges_to_kv.weight[:, 0].view(h, dh)                 # e_ij = A_ij * we + be   (edge_dim = 1)
-        be = a.edges_to_kv.bias.view(h, dh)
-        qw = (q * we[None, :, None, :]).sum(-1)                     # [B, h, n]
-        qb = (q * be[None, :, None, :]).sum(-1)
-        sim = (q @ k.transpose(-1, -2) + qw[..., None] * adj[:, None] + qb[..., None]) * (dh ** -0.5)
-        sim = sim.masked_fill(~key_ok[:, None, None, :], float("-inf"))
-        att = sim.softmax(-1)
-        out = att @ v + (att * adj[:, None]).sum(-1, keepdim=True) * we[None, :, None, :] + be[None, :, None, :]
-        out = _linear(out.permute(0, 2, 1, 3).reshape(B * n, h * dh), a.to_out).view(B, n, dim)
-        g = torch.sigmoid(F.linear(torch.cat((out, x, out - x), -1), gate.proj[0].weight))
-        x = out * g + x * (1 - g)
+        xn = torch.empty(R, dim, device=dev, dtype=torch.bfloat16)
+        ops.layernorm_fwd(x, pre.norm.weight.detach(), pre.norm.bias.detach(), 1e-5, None, xn)
+        qkv = torch.empty(R, 3 * inner, device=dev)
+        ops.gemm(xn, bf(torch.cat([a.to_q.weight, a.to_kv.weight], 0)),
+                 bias=torch.cat([a.to_q.bias, a.to_kv.bias]).detach(), out_f32=qkv)
+        pad = torch.zeros(B * n, 3 * inner, device=dev)
+        pad[rows] = qkv
+        pad = pad.view(B, n, 3, h, dh)
+        out = _attention_core(pad[:, :, 0].permute(0, 2, 1, 3), pad[:, :, 1].permute(0, 2, 1, 3),
+                              pad[:, :, 2].permute(0, 2, 1, 3), a, adj, key_ok, cos, sin)
+        out = out.permute(0, 2, 1, 3).reshape(B * n, inner)[rows].contiguous()
+        o = torch.empty(R, dim, device=dev)
+        ops.gemm(ops.cast_bf16(out), bf(a.to_out.weight), bias=a.to_out.bias.detach(), out_f32=o)
+        x = _gate(o, x, gate.proj[0].weight)
         pre2, gate2 = ff_block
-        xn = F.layer_norm(x, (dim,), pre2.norm.weight, pre2.norm.bias).reshape(B * n, dim)
-        ffo = _linear(F.gelu(_linear(xn, pre2.fn[0])), pre2.fn[2]).view(B, n, dim)
-        g = torch.sigmoid(F.linear(torch.cat((ffo, x, ffo - x), -1), gate2.proj[0].weight))
-        x = ffo * g + x * (1 - g)
-    return x
+        ops.layernorm_fwd(x, pre2.norm.weight.detach(), pre2.norm.bias.detach(), 1e-5, None, xn)
+        hid = torch.empty(R, 4 * dim, device=dev, dtype=torch.bfloat16)
+        ops.gemm(xn, bf(pre2.fn[0].weight), bias=pre2.fn[0].bias.detach(), act=ops.ACT_GELU, out_bf16=hid)
+        ops.gemm(hid, bf(pre2.fn[2].weight), bias=pre2.fn[2].bias.detach(), out_f32=o)
+        x = _gate(o, x, gate2.proj[0].weight)
+    full = torch.zeros(B * n, dim, device=dev)
+    full[rows] = x
+    return full.view(B, n, dim)
 
 
 def _pool(x, counts, gate_nn):
@@ -132,9 +177,12 @@ def _pool(x, counts, gate_nn):
 
 
 @torch.no_grad()
-def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_flags, hidden):
+def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_flags, hidden, clip_first_row=None,
+                       clip_rows=None):
     """Returns (structure_temp_loss [P], semantic_temp_loss [P']) for the batch described by `plan`
-    (teatgt.TeatPlan after build_graph); spatial_flags uint8 [F, nmax, nmax] (host); hidden [nodes, d_sem]."""
+    (teatgt.TeatPlan); spatial_flags uint8 [F, nmax, nmax] (host); hidden [rows, d_sem] = per-clip feature rows
+    (TEAT-GT: node order, the default; clip_first_row / clip_rows [F] override where a frame's clip starts in
+    `hidden` and how many rows that clip owns)."""
     dev = hidden.device
     F_, nmax = plan.F, plan.nmax
     counts_h = np.diff(plan.node_off_h)
@@ -161,10 +209,14 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
     nodes = torch.from_numpy(ev).to(dev)
     sym = _pool(run_batched(gat, nodes, adj, counts), counts, gate_nn)                   # [F, 10]
     # ---- R2: semantic nodes = the clip's hidden rows [0:n_f] (`savor` never advances)
-    clip_first_node = torch.from_numpy(plan.clip_node_off[plan.clip_of_frame]).to(dev)   # [F]
+    if clip_first_row is None:
+        clip_first_row = plan.clip_node_off[plan.clip_of_frame]
+        clip_rows = np.diff(plan.clip_node_off)[plan.clip_of_frame]
+    clip_first_node = torch.from_numpy(np.asarray(clip_first_row, dtype=np.int64)).to(dev)   # [F]
+    avail = torch.from_numpy(np.asarray(clip_rows, dtype=np.int64)).to(dev)
     ar = torch.arange(nmax, device=dev)
     rows = (clip_first_node[:, None] + ar[None, :]).clamp(max=hidden.shape[0] - 1)
-    ok = ar[None, :] < counts[:, None]
+    ok = ar[None, :] < torch.minimum(counts, avail)[:, None]
     sem_nodes = hidden[rows] * ok[..., None]
     sem = _pool(run_batched(gat_semantic, sem_nodes, adj, counts), counts, gate_sem_nn)  # [F, d_sem]
     # ---- R3: all frame pairs u < v inside each clip, reference order

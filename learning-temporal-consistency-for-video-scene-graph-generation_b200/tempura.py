@@ -257,7 +257,7 @@ class TEMPURA(nn.Module):
     def __init__(self, mode="sgdet", attention_class_num=None, spatial_class_num=None, contact_class_num=None,
                  obj_classes=None, rel_classes=None, enc_layer_num=None, dec_layer_num=None, obj_mem_compute=None,
                  rel_mem_compute=None, mem_fusion=None, selection=None, selection_lambda=0.5, take_obj_mem_feat=False,
-                 obj_head="gmm", rel_head="gmm", K=None, tracking=None, embed_vecs=None):
+                 obj_head="gmm", rel_head="gmm", K=None, tracking=None, embed_vecs=None, consistency_regulariser=False):
         super().__init__()
         self.obj_classes, self.GMM_K, self.mem_fusion, self.rel_classes = obj_classes, K, mem_fusion, rel_classes
         self.attention_class_num, self.spatial_class_num, self.contact_class_num = (
@@ -295,6 +295,16 @@ class TEMPURA(nn.Module):
         self.a_rel_compress = GMMHead(D_MODEL, attention_class_num, "attention", K)
         self.s_rel_compress = GMMHead(D_MODEL, spatial_class_num, "spatial", K)
         self.c_rel_compress = GMMHead(D_MODEL, contact_class_num, "contact", K)
+        # EXTENSION (not in the reference's lib/tempura.py, which never fills the *_temp_loss keys its trainer
+        # reads, TEMPURA_train.py:215-218): the TEAT-GT regulariser R1-R3 on TEMPURA's graphs.  Adds parameters,
+        # so it is opt-in and reference checkpoints still load strictly without it.
+        self.consistency_regulariser = bool(consistency_regulariser)
+        if self.consistency_regulariser:
+            from .regulariser import GraphTransformer
+            self.gat = GraphTransformer(dim=10, depth=4)
+            self.gat_semantic = GraphTransformer(dim=D_MODEL, depth=4)
+            self.gate_nn = nn.Linear(10, 1)
+            self.gate_sem_nn = nn.Linear(D_MODEL, 1)
         # knobs that are not part of the reference API
         self.dropout_p = 0.1            # nn.Dropout(0.1) / MHA dropout=0.1 everywhere in transformer.py
         self.gmm_eps = None             # dict head -> [K,N,C] noise to inject (parity tests); None = device RNG
@@ -336,6 +346,28 @@ class TEMPURA(nn.Module):
         e = g.selector if g.selection == "manual" else g.selector(feat).sigmoid()
         return e * feat + (1 - e) * mem
 
+    def _consistency(self, entry, plan, rel_feats):
+        """EXTENSION, see __init__: structure / semantic temporal-consistency losses (detached, like
+        lib/teatgt.py:350-351) over 5-frame clips.  Graph nodes per frame = person + objects with spatial edges
+        by box-centre distance (lib/teatgt.py:199-209); the semantic branch reads the clip's relation-feature
+        rows [0:n_f] in place of TokenGT's hidden_x (same `savor` indexing, lib/teatgt.py:312-314)."""
+        from .regulariser import consistency_losses
+        from .teatgt import TeatPlan, edge_threshold
+        dev = rel_feats.device
+        pair_h = entry.get("pair_idx_host")
+        if pair_h is None:
+            pair_h = entry["pair_idx"].cpu().numpy()
+        tp = TeatPlan(plan.counts_h, plan.frames_per_video, pair_h).to(dev)
+        no_prev = torch.zeros_like(tp.has_prev)
+        sp, _ = ops.teat_pair_flags(rel_feats.contiguous(), entry["boxes"].contiguous(), tp.feat_row, tp.node_off,
+                                    no_prev, edge_threshold(entry["video_size"]), 2.0, tp.nmax)
+        clips = tp.clip_of_frame
+        pairs_pc = np.bincount(clips, weights=plan.counts_h.astype(np.float64), minlength=tp.n_clips).astype(np.int64)
+        clip_pair_off = np.concatenate([[0], np.cumsum(pairs_pc)])
+        entry["structure_temp_loss"], entry["semantic_temp_loss"] = consistency_losses(
+            self.gat, self.gat_semantic, self.gate_nn, self.gate_sem_nn, tp, sp.cpu().numpy(), rel_feats,
+            clip_first_row=clip_pair_off[clips], clip_rows=pairs_pc[clips])
+
     # ------------------------------------------------------------------------------------------
     def forward(self, entry, phase="train", unc=False):
         entry = self.object_classifier(entry, phase=phase, unc=unc)
@@ -363,6 +395,8 @@ class TEMPURA(nn.Module):
         entry["rel_features"] = rel_features
         entry["rel_mem_features"] = mem_features
 
+        if self.consistency_regulariser and phase == "train":
+            self._consistency(entry, plan, mixed.detach())
         heads = [self.a_rel_compress, self.s_rel_compress, self.c_rel_compress]
         packed = [h.packed() for h in heads]
         Wp = torch.cat([w for w, _ in packed], 0)

@@ -204,3 +204,29 @@ def test_train_mode_batch_backward_runs_and_is_finite(pair):
     assert not torch.equal(m.conv[2].running_mean, state["conv.2.running_mean"])
     m.load_state_dict(state)
     m.eval()
+
+
+def test_consistency_regulariser_extension(cuda_lib):
+    """Opt-in extension (the reference's TEMPURA never fills these keys): the TEAT-GT regulariser R1-R3 on
+    TEMPURA's graphs.  Checks the contract: detached, one value per frame pair of every 5-frame clip (minus
+    negative KLs), finite and >= 0; without the flag no parameter is added (strict checkpoint loading)."""
+    from b200vsgg import synthetic, tempura
+    gold = torch.load(os.path.join(GOLDEN, "tempura_small.pt"), weights_only=False)
+    classes = synthetic.ag_object_classes()
+    plain = tempura.TEMPURA(obj_classes=classes, **gold["model_kw"])
+    m = tempura.TEMPURA(obj_classes=classes, consistency_regulariser=True, **gold["model_kw"])
+    extra = set(m.state_dict()) - set(plain.state_dict())
+    assert extra and all(k.split(".")[0] in ("gat", "gat_semantic", "gate_nn", "gate_sem_nn") for k in extra)
+    synthetic.seeded_init_(m, 3)
+    m = m.cuda().train()
+    frames = [12, 7]
+    entries = [synthetic.make_video_entry(70 + i, f, (2, 5), device="cuda") for i, f in enumerate(frames)]
+    out = m(tempura.collate_entries(entries), phase="train")
+    n_pairs = sum(sum(c * (c - 1) // 2 for c in [5] * (f // 5) + ([f % 5] if f % 5 else [])) for f in frames)
+    for k in ("structure_temp_loss", "semantic_temp_loss"):
+        t = out[k]
+        assert not t.requires_grad and 0 < t.numel() <= n_pairs
+        assert torch.isfinite(t).all() and (t >= 0).all()
+    loss = sum(tempura.tempura_loss(out, m.last_plan).values())
+    loss.backward()
+    assert m.gat_semantic.layers[0][0][0].fn.to_q.weight.grad is None      # detached: no gradient reaches it
