@@ -258,6 +258,15 @@ int b200vsgg_act_dropout_bf16(const void* x, int32_t ld_x, int64_t rows, int32_t
 int b200vsgg_consistency_kl(const float* g, int32_t d, const int32_t* pair_u, const int32_t* pair_v, int32_t n_pairs,
                             float* out, void* stream);
 
+/* Per-frame graph attention core of the regulariser's GraphTransformer (8 heads x 64, rotary q/k, per-edge
+ * key/value offsets from the adjacency; lib/teatgt.py:316-317 via graph_transformer_pytorch): qkv fp32
+ * [rows, >= 1536] = q | k | v of the compact node rows, node_off int32 [frames+1], upper = uint8 predicate
+ * matrices of b200vsgg_teat_pair_flags; out bf16 [rows, 512]. */
+int b200vsgg_graph_attn_core(const float* qkv, int32_t ld, const int32_t* node_off, const uint8_t* upper, int32_t nmax,
+                             const float* we, const float* be, int32_t n_frames, void* out, int32_t ldo, void* stream);
+/* GatedResidual: res <- o*g + res*(1-g), g = sigmoid(W [o, res, o-res]); w fp32 [3*dim]. */
+int b200vsgg_gated_residual(const float* o, float* res, const float* w, int32_t rows, int32_t dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -467,3 +467,19 @@ def consistency_kl(g, pair_u, pair_v):
                                               _stream()), "consistency_kl")
     _count()
     return out
+
+
+def graph_attn_core(qkv, node_off, upper, nmax, we, be, out):
+    assert qkv.dtype == torch.float32 and qkv.stride(1) == 1 and upper.dtype == torch.uint8 and upper.is_contiguous()
+    assert we.is_contiguous() and be.is_contiguous() and out.dtype == torch.bfloat16
+    check(_lib.lib().b200vsgg_graph_attn_core(_ptr(qkv), qkv.stride(0), _ptr(node_off), _ptr(upper), nmax, _ptr(_f32(we)),
+                                               _ptr(_f32(be)), node_off.numel() - 1, _ptr(out), out.stride(0), _stream()),
+          "graph_attn_core")
+    _count()
+
+
+def gated_residual(o, res, w):
+    assert o.is_contiguous() and res.is_contiguous() and w.is_contiguous() and w.numel() == 3 * o.shape[1]
+    check(_lib.lib().b200vsgg_gated_residual(_ptr(_f32(o)), _ptr(_f32(res)), _ptr(_f32(w)), o.shape[0], o.shape[1],
+                                              _stream()), "gated_residual")
+    _count()

@@ -119,8 +119,7 @@ def run_batched(gt, nodes, adj, counts):
     key_ok = (torch.arange(n, device=dev)[None, :] < counts[:, None])                   # [B, n]
     fr = _rotary(n, dh, dev)
     cos, sin = fr.cos()[None, None], fr.sin()[None, None]
-    fast = nodes.is_cuda and dim % 8 == 0
-    if not fast:
+    if True:
         x = nodes
         for attn_block, ff_block in gt.layers:
             pre, gate = attn_block
@@ -135,37 +134,49 @@ def run_batched(gt, nodes, adj, counts):
             xn = F.layer_norm(x, (dim,), pre2.norm.weight, pre2.norm.bias)
             x = _gate(pre2.fn[2](F.gelu(pre2.fn[0](xn))), x, gate2.proj[0].weight)
         return x
-    rows = key_ok.reshape(-1).nonzero().flatten()                   # compact: valid node rows only
-    R = rows.numel()
-    x = nodes.reshape(B * n, dim)[rows].contiguous()
-    inner = h * dh
+
+
+@torch.no_grad()
+def run_compact(gt, x, node_off, upper, nmax):
+    """Row-compacted GraphTransformer forward on the C-ABI kernels: x fp32 [R, dim] (dim % 8 == 0) = node rows of
+    all frames back to back, node_off int32 [frames+1], upper uint8 [frames, nmax, nmax] (adjacency = U + U^T).
+    LayerNorm, every projection (bf16 tcgen05 GEMMs, GELU fused), the per-frame attention core and the gated
+    residuals are library kernels; nothing of the padded [frames, nmax, ...] shape is materialised."""
+    R, dim = x.shape
+    dev = x.device
+    inner = gt.heads * gt.dim_head
     bf = lambda w: ops.cast_bf16(w.detach().contiguous())
+    x = x.contiguous().clone()
+    xn = torch.empty(R, dim, device=dev, dtype=torch.bfloat16)
+    qkv = torch.empty(R, 3 * inner, device=dev)
+    att = torch.empty(R, inner, device=dev, dtype=torch.bfloat16)
+    o = torch.empty(R, dim, device=dev)
+    hid = torch.empty(R, 4 * dim, device=dev, dtype=torch.bfloat16)
     for attn_block, ff_block in gt.layers:
         pre, gate = attn_block
         a = pre.fn
-        xn = torch.empty(R, dim, device=dev, dtype=torch.bfloat16)
         ops.layernorm_fwd(x, pre.norm.weight.detach(), pre.norm.bias.detach(), 1e-5, None, xn)
-        qkv = torch.empty(R, 3 * inner, device=dev)
         ops.gemm(xn, bf(torch.cat([a.to_q.weight, a.to_kv.weight], 0)),
                  bias=torch.cat([a.to_q.bias, a.to_kv.bias]).detach(), out_f32=qkv)
-        pad = torch.zeros(B * n, 3 * inner, device=dev)
-        pad[rows] = qkv
-        pad = pad.view(B, n, 3, h, dh)
-        out = _attention_core(pad[:, :, 0].permute(0, 2, 1, 3), pad[:, :, 1].permute(0, 2, 1, 3),
-                              pad[:, :, 2].permute(0, 2, 1, 3), a, adj, key_ok, cos, sin)
-        out = out.permute(0, 2, 1, 3).reshape(B * n, inner)[rows].contiguous()
-        o = torch.empty(R, dim, device=dev)
-        ops.gemm(ops.cast_bf16(out), bf(a.to_out.weight), bias=a.to_out.bias.detach(), out_f32=o)
-        x = _gate(o, x, gate.proj[0].weight)
+        ops.graph_attn_core(qkv, node_off, upper, nmax, a.edges_to_kv.weight.detach()[:, 0].contiguous(),
+                            a.edges_to_kv.bias.detach().contiguous(), att)
+        ops.gemm(att, bf(a.to_out.weight), bias=a.to_out.bias.detach(), out_f32=o)
+        ops.gated_residual(o, x, gate.proj[0].weight.detach().reshape(-1).contiguous())
         pre2, gate2 = ff_block
         ops.layernorm_fwd(x, pre2.norm.weight.detach(), pre2.norm.bias.detach(), 1e-5, None, xn)
-        hid = torch.empty(R, 4 * dim, device=dev, dtype=torch.bfloat16)
         ops.gemm(xn, bf(pre2.fn[0].weight), bias=pre2.fn[0].bias.detach(), act=ops.ACT_GELU, out_bf16=hid)
         ops.gemm(hid, bf(pre2.fn[2].weight), bias=pre2.fn[2].bias.detach(), out_f32=o)
-        x = _gate(o, x, gate2.proj[0].weight)
-    full = torch.zeros(B * n, dim, device=dev)
-    full[rows] = x
-    return full.view(B, n, dim)
+        ops.gated_residual(o, x, gate2.proj[0].weight.detach().reshape(-1).contiguous())
+    return x
+
+
+def _pool_compact(x, frame_of_row, n_frames, gate_nn):
+    """GlobalAttentionPooling over compact rows: per-frame softmax of gate_nn(x), weighted sum -> [frames, dim]."""
+    logit = gate_nn(x).squeeze(-1)
+    mx = torch.full((n_frames,), float("-inf"), device=x.device).scatter_reduce(0, frame_of_row, logit, "amax")
+    w = torch.exp(logit - mx[frame_of_row])
+    den = torch.zeros(n_frames, device=x.device).index_add_(0, frame_of_row, w)
+    return torch.zeros(n_frames, x.shape[1], device=x.device).index_add_(0, frame_of_row, (w / den[frame_of_row])[:, None] * x)
 
 
 def _pool(x, counts, gate_nn):
@@ -178,53 +189,85 @@ def _pool(x, counts, gate_nn):
 
 @torch.no_grad()
 def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_flags, hidden, clip_first_row=None,
-                       clip_rows=None):
+                       clip_rows=None, flags_host=None):
     """Returns (structure_temp_loss [P], semantic_temp_loss [P']) for the batch described by `plan`
-    (teatgt.TeatPlan); spatial_flags uint8 [F, nmax, nmax] (host); hidden [rows, d_sem] = per-clip feature rows
-    (TEAT-GT: node order, the default; clip_first_row / clip_rows [F] override where a frame's clip starts in
-    `hidden` and how many rows that clip owns)."""
+    (teatgt.TeatPlan); spatial_flags uint8 [F, nmax, nmax] on the DEVICE (b200vsgg_teat_pair_flags); hidden
+    [rows, d_sem] = per-clip feature rows (TEAT-GT: node order, the default; clip_first_row / clip_rows [F] override
+    where a frame's clip starts in `hidden` and how many rows that clip owns)."""
     dev = hidden.device
     F_, nmax = plan.F, plan.nmax
     counts_h = np.diff(plan.node_off_h)
-    up = np.asarray(spatial_flags, dtype=np.float64)
+    n_nodes = int(plan.node_off_h[-1])
+    frame_of_row = torch.from_numpy(np.repeat(np.arange(F_), counts_h)).to(dev)
+    # ---- R2 first (device only, asynchronous): semantic nodes = the clip's hidden rows [0:n_f] (`savor` quirk)
+    if clip_first_row is None:
+        clip_first_row = plan.clip_node_off[plan.clip_of_frame]
+        clip_rows = np.diff(plan.clip_node_off)[plan.clip_of_frame]
+    local = np.arange(n_nodes) - np.repeat(plan.node_off_h[:-1], counts_h)
+    src = np.repeat(np.asarray(clip_first_row, dtype=np.int64), counts_h) + local
+    valid = local < np.repeat(np.asarray(clip_rows, dtype=np.int64), counts_h)
+    src_t = torch.from_numpy(np.where(valid, src, 0)).to(dev)
+    x = hidden[src_t]
+    if not valid.all():
+        x = x * torch.from_numpy(valid.astype(np.float32)).to(dev)[:, None]
+    wide = hidden.is_cuda and hidden.shape[1] % 8 == 0 and nmax <= 32
+    if wide:
+        sem_rows = run_compact(gat_semantic, x, plan.node_off, spatial_flags, nmax)
+        sem = _pool_compact(sem_rows, frame_of_row, F_, gate_sem_nn)
+    # ---- R1: per-frame Laplacian eigenvectors on the host (the reference's LAPACK call), grouped by node count;
+    #      this runs while the device works on the semantic branch
+    if flags_host is not None:        # (pinned host copy, event): the D2H was issued before the main path
+        flags_host[1].synchronize()
+        up = flags_host[0].numpy().astype(np.float64)
+    else:
+        up = spatial_flags.cpu().numpy().astype(np.float64)
     A = up + up.transpose(0, 2, 1)                                   # both directions were added as edges
-    # ---- R1: per-frame Laplacian eigenvectors, grouped by node count (stacked LAPACK calls)
     k = 10
     ev = np.zeros((F_, nmax, k), dtype=np.float32)
-    for nf in np.unique(counts_h):
-        idx = np.nonzero(counts_h == nf)[0]
+
+    def solve(idx):
+        nf = int(counts_h[idx[0]])
         a = A[idx][:, :nf, :nf]
         deg = a.sum(1)                                              # in-degree (symmetric)
         nm = (torch.from_numpy(deg.astype(np.int64)).clip(1) ** -0.5).numpy().astype(np.float64)
         L = np.eye(nf)[None] - nm[:, :, None] * a * nm[:, None, :]
-        _, vec = np.linalg.eigh(L)
+        _, vec = np.linalg.eigh(L)                                   # stacked LAPACK calls, GIL released
         vec = vec.astype(np.float32)
         if k > nf:
             vec = np.tile(vec, (1, 1, int(k / 2)))[:, :, :k]         # lib/teatgt.py:304-305
         else:
             vec = vec[:, :, :k]
         ev[idx, :nf] = vec
+
+    jobs = []
+    for nf in np.unique(counts_h):
+        idx = np.nonzero(counts_h == nf)[0]
+        jobs += [idx[i:i + 256] for i in range(0, idx.shape[0], 256)]
+    if len(jobs) <= 2:
+        for j in jobs:
+            solve(j)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(8) as pool:
+            list(pool.map(solve, jobs))
     counts = torch.from_numpy(counts_h).to(dev)
     adj = torch.from_numpy(A.astype(np.float32)).to(dev)
     nodes = torch.from_numpy(ev).to(dev)
     sym = _pool(run_batched(gat, nodes, adj, counts), counts, gate_nn)                   # [F, 10]
-    # ---- R2: semantic nodes = the clip's hidden rows [0:n_f] (`savor` never advances)
-    if clip_first_row is None:
-        clip_first_row = plan.clip_node_off[plan.clip_of_frame]
-        clip_rows = np.diff(plan.clip_node_off)[plan.clip_of_frame]
-    clip_first_node = torch.from_numpy(np.asarray(clip_first_row, dtype=np.int64)).to(dev)   # [F]
-    avail = torch.from_numpy(np.asarray(clip_rows, dtype=np.int64)).to(dev)
-    ar = torch.arange(nmax, device=dev)
-    rows = (clip_first_node[:, None] + ar[None, :]).clamp(max=hidden.shape[0] - 1)
-    ok = ar[None, :] < torch.minimum(counts, avail)[:, None]
-    sem_nodes = hidden[rows] * ok[..., None]
-    sem = _pool(run_batched(gat_semantic, sem_nodes, adj, counts), counts, gate_sem_nn)  # [F, d_sem]
+    if not wide:
+        ar = torch.arange(nmax, device=dev)
+        pad_rows = (torch.from_numpy(plan.node_off_h[:-1]).to(dev)[:, None] + ar[None, :]).clamp(max=n_nodes - 1)
+        ok = ar[None, :] < counts[:, None]
+        sem = _pool(run_batched(gat_semantic, x[pad_rows] * ok[..., None], adj, counts), counts, gate_sem_nn)
     # ---- R3: all frame pairs u < v inside each clip, reference order
     pu, pv = [], []
     frames_pc = np.bincount(plan.clip_of_frame, minlength=plan.n_clips)
     f0 = 0
+    tri = {}
     for nf in frames_pc:
-        iu, iv = np.triu_indices(int(nf), 1)
+        if int(nf) not in tri:
+            tri[int(nf)] = np.triu_indices(int(nf), 1)
+        iu, iv = tri[int(nf)]
         pu.append(f0 + iu)
         pv.append(f0 + iv)
         f0 += int(nf)

@@ -379,7 +379,7 @@ class TEAT_GT(nn.Module):
         if phase == "train" and self.compute_consistency:
             # R1-R3, detached like the reference (lib/teatgt.py:350-351)
             entry["structure_temp_loss"], entry["semantic_temp_loss"] = consistency_losses(
-                self.gat, self.gat_semantic, self.gate_nn, self.gate_sem_nn, plan, sp_h, hidden.detach())
+                self.gat, self.gat_semantic, self.gate_nn, self.gate_sem_nn, plan, sp, hidden.detach())
         else:
             entry["structure_temp_loss"] = torch.zeros(0, device=dev)
             entry["semantic_temp_loss"] = torch.zeros(0, device=dev)

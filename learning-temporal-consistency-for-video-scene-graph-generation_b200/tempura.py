@@ -299,6 +299,7 @@ class TEMPURA(nn.Module):
         # reads, TEMPURA_train.py:215-218): the TEAT-GT regulariser R1-R3 on TEMPURA's graphs.  Adds parameters,
         # so it is opt-in and reference checkpoints still load strictly without it.
         self.consistency_regulariser = bool(consistency_regulariser)
+        self._flags_pin = None
         if self.consistency_regulariser:
             from .regulariser import GraphTransformer
             self.gat = GraphTransformer(dim=10, depth=4)
@@ -346,27 +347,41 @@ class TEMPURA(nn.Module):
         e = g.selector if g.selection == "manual" else g.selector(feat).sigmoid()
         return e * feat + (1 - e) * mem
 
-    def _consistency(self, entry, plan, rel_feats):
-        """EXTENSION, see __init__: structure / semantic temporal-consistency losses (detached, like
-        lib/teatgt.py:350-351) over 5-frame clips.  Graph nodes per frame = person + objects with spatial edges
-        by box-centre distance (lib/teatgt.py:199-209); the semantic branch reads the clip's relation-feature
-        rows [0:n_f] in place of TokenGT's hidden_x (same `savor` indexing, lib/teatgt.py:312-314)."""
-        from .regulariser import consistency_losses
+    def _consistency_prepare(self, entry, plan):
+        """Issue everything of the regulariser that depends on the boxes only (node layout, spatial edge
+        predicates, their copy to pinned host memory) BEFORE the main path is launched, so that the host-side
+        Laplacian eigen-decompositions later overlap the device's forward work."""
         from .teatgt import TeatPlan, edge_threshold
-        dev = rel_feats.device
+        dev = entry["features"].device
         pair_h = entry.get("pair_idx_host")
         if pair_h is None:
             pair_h = entry["pair_idx"].cpu().numpy()
         tp = TeatPlan(plan.counts_h, plan.frames_per_video, pair_h).to(dev)
         no_prev = torch.zeros_like(tp.has_prev)
-        sp, _ = ops.teat_pair_flags(rel_feats.contiguous(), entry["boxes"].contiguous(), tp.feat_row, tp.node_off,
-                                    no_prev, edge_threshold(entry["video_size"]), 2.0, tp.nmax)
+        dummy = entry["boxes"].contiguous()
+        sp, _ = ops.teat_pair_flags(dummy[:, :4].contiguous(), dummy, tp.feat_row, tp.node_off, no_prev,
+                                    edge_threshold(entry["video_size"]), 2.0, tp.nmax)
+        host = torch.empty(sp.shape, dtype=torch.uint8).pin_memory() if self._flags_pin is None or \
+            self._flags_pin.shape != sp.shape else self._flags_pin
+        self._flags_pin = host
+        host.copy_(sp, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return tp, sp, (host, ev)
+
+    def _consistency(self, entry, plan, rel_feats, prep):
+        """EXTENSION, see __init__: structure / semantic temporal-consistency losses (detached, like
+        lib/teatgt.py:350-351) over 5-frame clips.  Graph nodes per frame = person + objects with spatial edges
+        by box-centre distance (lib/teatgt.py:199-209); the semantic branch reads the clip's relation-feature
+        rows [0:n_f] in place of TokenGT's hidden_x (same `savor` indexing, lib/teatgt.py:312-314)."""
+        from .regulariser import consistency_losses
+        tp, sp, flags_host = prep
         clips = tp.clip_of_frame
         pairs_pc = np.bincount(clips, weights=plan.counts_h.astype(np.float64), minlength=tp.n_clips).astype(np.int64)
         clip_pair_off = np.concatenate([[0], np.cumsum(pairs_pc)])
         entry["structure_temp_loss"], entry["semantic_temp_loss"] = consistency_losses(
-            self.gat, self.gat_semantic, self.gate_nn, self.gate_sem_nn, tp, sp.cpu().numpy(), rel_feats,
-            clip_first_row=clip_pair_off[clips], clip_rows=pairs_pc[clips])
+            self.gat, self.gat_semantic, self.gate_nn, self.gate_sem_nn, tp, sp, rel_feats,
+            clip_first_row=clip_pair_off[clips], clip_rows=pairs_pc[clips], flags_host=flags_host)
 
     # ------------------------------------------------------------------------------------------
     def forward(self, entry, phase="train", unc=False):
@@ -382,6 +397,8 @@ class TEMPURA(nn.Module):
             plan = plan_from_im_idx(entry["im_idx"], fpv, entry.get("frame_counts_host")).to(feats.device)
         self.last_plan = plan
 
+        cons_prep = (self._consistency_prepare(entry, plan)
+                     if self.consistency_regulariser and phase == "train" else None)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._path_params())
         runner = _PathRunner(self, entry, plan, train_dropout=self.training, save=need_grad)
         out, local = _PathFn.apply(runner, *self._path_params())
@@ -395,8 +412,8 @@ class TEMPURA(nn.Module):
         entry["rel_features"] = rel_features
         entry["rel_mem_features"] = mem_features
 
-        if self.consistency_regulariser and phase == "train":
-            self._consistency(entry, plan, mixed.detach())
+        if cons_prep is not None:
+            self._consistency(entry, plan, mixed.detach(), cons_prep)
         heads = [self.a_rel_compress, self.s_rel_compress, self.c_rel_compress]
         packed = [h.packed() for h in heads]
         Wp = torch.cat([w for w, _ in packed], 0)

@@ -28,3 +28,9 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=50))
 print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=10, max_name_column_width=50))
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+with torch.no_grad():
+    orig(dict(batch), m.last_plan, torch.randn(batch["pair_idx"].shape[0], 1936, device=dev))
+torch.cuda.synchronize(); pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
