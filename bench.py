@@ -339,7 +339,15 @@ def main():
                 copy_stream.wait_event(consumed[slot])
                 dst, gdst = bufs[slot]
                 for k, t in host.items():
-                    dst[k].copy_(t, non_blocking=True)
+                    # bulk tensors go in 16 MB slices: the small (pageable) index uploads that the step issues on
+                    # the compute stream share the H2D copy engine and would otherwise wait for the whole 3.3 GB
+                    n, chunk = t.numel(), (16 << 20) // t.element_size()
+                    if n <= chunk:
+                        dst[k].copy_(t, non_blocking=True)
+                    else:
+                        df, sf = dst[k].view(-1), t.view(-1)
+                        for i in range(0, n, chunk):
+                            df[i:i + chunk].copy_(sf[i:i + chunk], non_blocking=True)
                 for d, s in zip(gdst, gt_host):
                     d.copy_(s, non_blocking=True)
                 ready[slot].record(copy_stream)

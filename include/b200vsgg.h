@@ -267,6 +267,11 @@ int b200vsgg_graph_attn_core(const float* qkv, int32_t ld, const int32_t* node_o
 /* GatedResidual: res <- o*g + res*(1-g), g = sigmoid(W [o, res, o-res]); w fp32 [3*dim]. */
 int b200vsgg_gated_residual(const float* o, float* res, const float* w, int32_t rows, int32_t dim, void* stream);
 
+/* Upload `bytes` (multiple of 16) from PINNED host memory to the device with a kernel on `stream` instead of the
+ * copy engine (see frontend.cu): used for the per-batch index vectors so they never queue behind a bulk
+ * input prefetch. h_pinned_src must stay untouched until the kernel has run. */
+int b200vsgg_upload(const void* h_pinned_src, void* dst, int64_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

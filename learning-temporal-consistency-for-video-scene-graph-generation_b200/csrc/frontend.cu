@@ -156,3 +156,31 @@ extern "C" int b200vsgg_nhwc_to_nchw_f32(const float* in, int32_t n, int32_t cha
     VSGG_CUDA_CHECK_LAUNCH();
     return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Small host -> device uploads (index vectors of the segment plans) WITHOUT the copy engine: the source is
+// pinned host memory, which is device-addressable under unified addressing, and a kernel on the compute
+// stream reads it over PCIe.  DMA queues are FIFO: a cudaMemcpyAsync issued while a multi-GB input batch is
+// being prefetched on another stream would wait for the whole batch; this does not.
+// ------------------------------------------------------------------------------------------------
+namespace vsgg {
+__global__ void upload_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n16;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        dst[i] = src[i];
+}
+}  // namespace vsgg
+
+extern "C" int b200vsgg_upload(const void* h_pinned_src, void* dst, int64_t bytes, void* stream) {
+    if (!h_pinned_src || !dst || bytes < 0 || (bytes & 15) || (reinterpret_cast<uintptr_t>(h_pinned_src) & 15) ||
+        (reinterpret_cast<uintptr_t>(dst) & 15))
+        return vsgg::set_error(B200VSGG_ERR_BAD_ARG, "upload: pointers and size must be 16-byte multiples");
+    if (bytes == 0) return 0;
+    const long long n16 = bytes / 16;
+    long long g = (n16 + 255) / 256;
+    if (g > 592) g = 592;
+    vsgg::upload_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>((const uint4*)h_pinned_src, (uint4*)dst, n16);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}

@@ -483,3 +483,64 @@ def gated_residual(o, res, w):
     check(_lib.lib().b200vsgg_gated_residual(_ptr(_f32(o)), _ptr(_f32(res)), _ptr(_f32(w)), o.shape[0], o.shape[1],
                                               _stream()), "gated_residual")
     _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# zero-copy uploads of small host arrays (segment plans) through a pinned ring buffer
+# ------------------------------------------------------------------------------------------------
+class _UploadRing:
+    """Pinned staging ring (default 64 MB).  upload(): memcpy into the ring on the host, then a kernel on the
+    current stream reads it over PCIe (b200vsgg_upload).  A slot is reused only after the event recorded behind
+    its last reader has completed."""
+
+    def __init__(self, nbytes=64 << 20):
+        self.buf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        self.np = self.buf.numpy()
+        self.pos = 0
+        self.events = []          # (end_offset, event) in issue order
+
+    def _reserve(self, n):
+        if n > self.buf.numel():
+            raise RuntimeError("upload of %d bytes exceeds the pinned ring" % n)
+        if self.pos + n > self.buf.numel():
+            self.pos = 0
+            for _, ev in self.events:          # wrap-around: everything issued so far must have been read
+                ev.synchronize()
+            self.events = []
+        start = self.pos
+        self.pos += n
+        return start
+
+
+_ring = None
+
+
+def upload(arr, device, dtype=None):
+    """numpy array -> device tensor of the same shape/dtype (or `dtype`), without using the DMA copy engine."""
+    import numpy as np
+    global _ring
+    a = np.ascontiguousarray(arr if dtype is None else np.asarray(arr).astype(dtype))
+    t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].reshape(-1)).dtype, device=device)
+    nbytes = a.nbytes
+    if nbytes == 0:
+        return t
+    if torch.device(device).type != "cuda":
+        t.copy_(torch.from_numpy(a))
+        return t
+    if _ring is None:
+        _ring = _UploadRing()
+    padded = (nbytes + 15) // 16 * 16
+    out = t if nbytes == padded and t.data_ptr() % 16 == 0 else None
+    start = _ring._reserve(padded)
+    _ring.np[start:start + nbytes] = a.reshape(-1).view(np.uint8)
+    dst = out if out is not None else torch.empty(padded, dtype=torch.uint8, device=device)
+    check(_lib.lib().b200vsgg_upload(C.c_void_p(_ring.buf.data_ptr() + start), _ptr(dst), padded, _stream()), "upload")
+    ev = torch.cuda.Event()
+    ev.record()
+    _ring.events.append((start + padded, ev))
+    if len(_ring.events) > 4096:
+        _ring.events = _ring.events[-2048:]
+    _count()
+    if out is None:
+        t = dst[:nbytes].view(t.dtype).view(a.shape)
+    return t

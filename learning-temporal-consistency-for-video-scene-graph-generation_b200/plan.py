@@ -99,7 +99,8 @@ class SegmentPlan:
                 r1 = int(self.pair_off_video_h[v + 1]) * rows_per_pair
                 starts = np.arange(r0, r1, chunk_rows, dtype=np.int64)
                 rows.append(np.stack([starts, np.minimum(starts + chunk_rows, r1), np.full_like(starts, v)], 1))
-            t = torch.from_numpy(np.concatenate(rows).astype(np.int32)).to(self.device)
+            from . import ops
+            t = ops.upload(np.concatenate(rows).astype(np.int32), self.device)
             self._chunks[key] = t
         return t
 
@@ -116,8 +117,9 @@ class SegmentPlan:
             h = getattr(self, n + "_h")
             setattr(self, n, t.view(h.shape))
             pos += sz
-        self.video_of_pair = torch.from_numpy(self.video_of_pair_h).to(device, non_blocking=True)
-        self.pairs_per_video_dev = torch.from_numpy(self.pairs_per_video.astype(np.float32)).to(device, non_blocking=True)
+        from . import ops
+        self.video_of_pair = ops.upload(self.video_of_pair_h, device)
+        self.pairs_per_video_dev = ops.upload(self.pairs_per_video.astype(np.float32), device)
         self.device = device
         return self
 
@@ -127,21 +129,8 @@ _STAGE = {"buf": None, "event": None}
 
 def _staged_h2d(flat_np, device):
     """int32 numpy vector -> device tensor via a reused pinned buffer (async copy on the current stream)."""
-    src = torch.from_numpy(flat_np)
-    if torch.device(device).type != "cuda":
-        return src.to(device)
-    n = src.numel()
-    st = _STAGE
-    if st["buf"] is None or st["buf"].numel() < n:
-        st["buf"] = torch.empty(max(n, 1 << 20), dtype=torch.int32).pin_memory()
-        st["event"] = None
-    if st["event"] is not None:
-        st["event"].synchronize()        # the previous copy out of the buffer has completed
-    st["buf"][:n].copy_(src)
-    out = st["buf"][:n].to(device, non_blocking=True)
-    st["event"] = torch.cuda.Event()
-    st["event"].record()
-    return out
+    from . import ops
+    return ops.upload(flat_np, device)
 
 
 def plan_from_im_idx(im_idx, frames_per_video=None, counts_host=None):

@@ -198,7 +198,8 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
     F_, nmax = plan.F, plan.nmax
     counts_h = np.diff(plan.node_off_h)
     n_nodes = int(plan.node_off_h[-1])
-    frame_of_row = torch.from_numpy(np.repeat(np.arange(F_), counts_h)).to(dev)
+    up_ = lambda a: ops.upload(a, dev)
+    frame_of_row = up_(np.repeat(np.arange(F_), counts_h))
     # ---- R2 first (device only, asynchronous): semantic nodes = the clip's hidden rows [0:n_f] (`savor` quirk)
     if clip_first_row is None:
         clip_first_row = plan.clip_node_off[plan.clip_of_frame]
@@ -206,10 +207,10 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
     local = np.arange(n_nodes) - np.repeat(plan.node_off_h[:-1], counts_h)
     src = np.repeat(np.asarray(clip_first_row, dtype=np.int64), counts_h) + local
     valid = local < np.repeat(np.asarray(clip_rows, dtype=np.int64), counts_h)
-    src_t = torch.from_numpy(np.where(valid, src, 0)).to(dev)
+    src_t = up_(np.where(valid, src, 0))
     x = hidden[src_t]
     if not valid.all():
-        x = x * torch.from_numpy(valid.astype(np.float32)).to(dev)[:, None]
+        x = x * up_(valid.astype(np.float32))[:, None]
     wide = hidden.is_cuda and hidden.shape[1] % 8 == 0 and nmax <= 32
     if wide:
         sem_rows = run_compact(gat_semantic, x, plan.node_off, spatial_flags, nmax)
@@ -250,13 +251,13 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(8) as pool:
             list(pool.map(solve, jobs))
-    counts = torch.from_numpy(counts_h).to(dev)
-    adj = torch.from_numpy(A.astype(np.float32)).to(dev)
-    nodes = torch.from_numpy(ev).to(dev)
+    counts = up_(counts_h)
+    adj = up_(A.astype(np.float32))
+    nodes = up_(ev)
     sym = _pool(run_batched(gat, nodes, adj, counts), counts, gate_nn)                   # [F, 10]
     if not wide:
         ar = torch.arange(nmax, device=dev)
-        pad_rows = (torch.from_numpy(plan.node_off_h[:-1]).to(dev)[:, None] + ar[None, :]).clamp(max=n_nodes - 1)
+        pad_rows = (up_(plan.node_off_h[:-1])[:, None] + ar[None, :]).clamp(max=n_nodes - 1)
         ok = ar[None, :] < counts[:, None]
         sem = _pool(run_batched(gat_semantic, x[pad_rows] * ok[..., None], adj, counts), counts, gate_sem_nn)
     # ---- R3: all frame pairs u < v inside each clip, reference order
@@ -271,8 +272,8 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
         pu.append(f0 + iu)
         pv.append(f0 + iv)
         f0 += int(nf)
-    pu = torch.from_numpy(np.concatenate(pu).astype(np.int32)).to(dev)
-    pv = torch.from_numpy(np.concatenate(pv).astype(np.int32)).to(dev)
+    pu = up_(np.concatenate(pu).astype(np.int32))
+    pv = up_(np.concatenate(pv).astype(np.int32))
     s = ops.consistency_kl(sym.contiguous(), pu, pv)
     m = ops.consistency_kl(sem.contiguous(), pu, pv)
     return s[s >= 0], m[m >= 0]

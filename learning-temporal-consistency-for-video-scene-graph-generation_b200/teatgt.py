@@ -173,7 +173,7 @@ class TeatPlan:
         self.edges = None
 
     def to(self, device):
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        t = lambda a: ops.upload(a, device)
         self.feat_row, self.is_person = t(self.feat_row_h), t(self.is_person_h)
         self.node_off, self.has_prev = t(self.node_off_h.astype(np.int32)), t(self.has_prev_h)
         self.device = device
@@ -337,11 +337,11 @@ class TEAT_GT(nn.Module):
                                      plan.has_prev, thr, SIM_THR, plan.nmax)
         sp_h = sp.cpu().numpy()
         plan.build_graph(sp_h, tp.cpu().numpy(), self.lap_k, self.eig_threads)
-        desc = torch.from_numpy(plan.desc_h).to(dev)
-        ev = torch.from_numpy(plan.eigvec_h).to(dev)
+        desc = ops.upload(plan.desc_h, dev)
+        ev = ops.upload(plan.eigvec_h, dev)
         evb = ops.cast_bf16(ev, drop_p=self.eig_dropout if train else 0.0, seed=seed0 + 17)
         aplan = AttnPlan(plan.seq_off_h, dev)
-        node_rows = torch.from_numpy(plan.node_tok_h).to(dev)
+        node_rows = ops.upload(plan.node_tok_h, dev)
 
         # ---- G6: tokenizer
         x = AssembleTokens.apply(tok, tokb, evb, tk.atom_encoder.weight, tk.atom_encoder.bias, tk.lap_encoder.weight,
@@ -369,7 +369,7 @@ class TEAT_GT(nn.Module):
                                         enc.embed_out.weight, enc.lm_output_learned_bias)
         if dbg is not None:
             dbg["logits"], dbg["hidden"] = logits.detach(), hidden.detach()
-        obj = torch.from_numpy(plan.obj_node).to(dev)
+        obj = ops.upload(plan.obj_node, dev)
         g = logits[obj]
         # ---- G10
         entry["attention_distribution"] = torch.softmax(g[:, :3], -1)

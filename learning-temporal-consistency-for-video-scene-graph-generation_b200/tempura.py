@@ -930,7 +930,7 @@ def tempura_loss(pred, plan=None):
     if plan is None or plan.V == 1:
         w = torch.full((N,), 1.0 / N, device=dev)
     else:
-        ppv = torch.as_tensor(plan.pairs_per_video, device=dev, dtype=torch.float32)
+        ppv = plan.pairs_per_video_dev
         w = 1.0 / (ppv[plan.video_of_pair] * plan.V)
     ce = F.cross_entropy(dist_a, att, reduction="none")
     bs = F.binary_cross_entropy(dist_s, spa, reduction="none").mean(1)

@@ -34,9 +34,9 @@ class AttnPlan:
         import numpy as np
         from .plan import attention_blocks
         bs, br = attention_blocks(seq_off_h)
-        self.seq_off = torch.from_numpy(np.asarray(seq_off_h, dtype=np.int32)).to(device)
-        self.blk_seq = torch.from_numpy(bs).to(device)
-        self.blk_row0 = torch.from_numpy(br).to(device)
+        self.seq_off = ops.upload(np.asarray(seq_off_h, dtype=np.int32), device)
+        self.blk_seq = ops.upload(bs, device)
+        self.blk_row0 = ops.upload(br, device)
 
 
 class PreLNAttention(torch.autograd.Function):

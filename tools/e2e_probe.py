@@ -21,7 +21,13 @@ def copy_all():
     with torch.cuda.stream(cs):
         e0.record(cs)
         for k, t in host.items():
-            dst[k].copy_(t, non_blocking=True)
+            n, chunk = t.numel(), (16 << 20) // t.element_size()
+            if n <= chunk:
+                dst[k].copy_(t, non_blocking=True)
+            else:
+                df, sf = dst[k].view(-1), t.view(-1)
+                for i in range(0, n, chunk):
+                    df[i:i + chunk].copy_(sf[i:i + chunk], non_blocking=True)
         e1.record(cs)
     return e0, e1
 def step():
