@@ -4,8 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
 
-Metric (BASELINE.json): relation pairs / second, PredCLS forward + loss + backward (+ the gradient
-all-reduce when N > 1).  Workload per GPU = BASELINE.json configs[1]: a batch of 64 synthetic
+Metric (BASELINE.json): relation pairs / second of a full training step: PredCLS forward + loss + backward
+(+ the gradient all-reduce when N > 1) + gradient clipping + AdamW update.  Workload per GPU = BASELINE.json configs[1]: a batch of 64 synthetic
 Action-Genome-shaped videos (32 frames, 6-10 pairs/frame, ~16.4 k pairs); N GPUs each take 64 videos
 (weak scaling; N = 8 is configs[3], 512 videos per step).  One JSON line is printed by rank 0.
 
@@ -172,7 +172,7 @@ def workload_config(args, world):
             "consistency_regulariser": ("off" if getattr(args, "no_consistency", False) else
                                         "on: TEAT-GT regulariser R1-R3 on TEMPURA's graphs, detached as in the reference "
                                         "(lib/teatgt.py:350-351); extension, the reference's TEMPURA never fills these keys"),
-            "optimizer_in_step": False}
+            "optimizer_in_step": "fused AdamW + clip_grad_norm_(5) (tools/utils/AdamW.py semantics) after the all-reduce"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -232,6 +232,10 @@ def main():
     batch = build_batch(vids, args.frames, dev)
     n_pairs = int(batch["pair_idx"].shape[0])
     sync = ddp.GradSync(list(model.parameters())[::-1]) if world > 1 else None
+    # TEMPURA_train.py:111,224-225: AdamW(lr, weight_decay=0.1) after clip_grad_norm_(5) — fused, 2 launches
+    from b200vsgg.optim import FusedAdamW
+    opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-5, betas=(0.9, 0.999), eps=1e-8,
+                     weight_decay=0.1, max_grad_norm=5.0)
 
     def run_step(entry):
         model.zero_grad(set_to_none=True)
@@ -243,6 +247,7 @@ def main():
         loss.backward()
         if sync is not None:
             sync.sync()
+        opt.step()
         return loss
 
     def barrier():

@@ -272,6 +272,27 @@ int b200vsgg_gated_residual(const float* o, float* res, const float* w, int32_t 
  * input prefetch. h_pinned_src must stay untouched until the kernel has run. */
 int b200vsgg_upload(const void* h_pinned_src, void* dst, int64_t bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-tensor optimiser step: tools/utils/AdamW.py:53-113 (weight decay before the moment update) with
+ * torch.nn.utils.clip_grad_norm_ (TEMPURA_train.py:224) folded in.  `tensors` is a DEVICE array; the work is
+ * split into chunks of chunk_elems elements: chunk c covers tensor chunk_tensor[c] from element chunk_off[c].
+ * sq_norm: device scalar, pre-zeroed by the caller, filled by b200vsgg_grad_sqnorm and consumed by the step
+ * (NULL = no clipping). */
+typedef struct b200vsgg_opt_tensor {
+    float* p;                 /* parameter, updated in place */
+    const float* g;           /* gradient */
+    float* m;                 /* exp_avg */
+    float* v;                 /* exp_avg_sq */
+    int64_t n;                /* elements */
+    float bias_correction1;   /* 1 - beta1^step of this tensor */
+    float bias_correction2;   /* 1 - beta2^step */
+} b200vsgg_opt_tensor;
+int b200vsgg_grad_sqnorm(const b200vsgg_opt_tensor* tensors, const int32_t* chunk_tensor, const int64_t* chunk_off,
+                         int32_t n_chunks, int32_t chunk_elems, float* sq_norm, void* stream);
+int b200vsgg_adamw_clip_step(const b200vsgg_opt_tensor* tensors, const int32_t* chunk_tensor, const int64_t* chunk_off,
+                             int32_t n_chunks, int32_t chunk_elems, const float* sq_norm, float max_norm, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

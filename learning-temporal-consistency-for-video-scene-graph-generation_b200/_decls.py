@@ -48,6 +48,8 @@ SIGNATURES = {
     "b200vsgg_teat_assemble_bwd": [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "b200vsgg_graph_attn_core": [vp, i32, vp, vp, i32, vp, vp, i32, vp, i32, vp],
     "b200vsgg_gated_residual": [vp, vp, vp, i32, i32, vp],
+    "b200vsgg_grad_sqnorm": [vp, vp, vp, i32, i32, vp, vp],
+    "b200vsgg_adamw_clip_step": [vp, vp, vp, i32, i32, vp, f32, f32, f32, f32, f32, f32, vp],
     "b200vsgg_upload": [vp, vp, i64, vp],
     "b200vsgg_consistency_kl": [vp, i32, vp, vp, i32, vp, vp],
     "b200vsgg_act_dropout_bf16": [vp, i32, i64, i32, i32, f32, u64, vp, i32, vp],

@@ -544,3 +544,16 @@ def upload(arr, device, dtype=None):
     if out is None:
         t = dst[:nbytes].view(t.dtype).view(a.shape)
     return t
+
+
+def grad_sqnorm(tensors, chunk_tensor, chunk_off, chunk_elems, sq_norm):
+    check(_lib.lib().b200vsgg_grad_sqnorm(_ptr(tensors), _ptr(chunk_tensor), _ptr(chunk_off), chunk_tensor.numel(),
+                                           chunk_elems, _ptr(sq_norm), _stream()), "grad_sqnorm")
+    _count()
+
+
+def adamw_clip_step(tensors, chunk_tensor, chunk_off, chunk_elems, sq_norm, max_norm, lr, beta1, beta2, eps, weight_decay):
+    check(_lib.lib().b200vsgg_adamw_clip_step(_ptr(tensors), _ptr(chunk_tensor), _ptr(chunk_off), chunk_tensor.numel(),
+                                               chunk_elems, _ptr(sq_norm), max_norm, lr, beta1, beta2, eps, weight_decay,
+                                               _stream()), "adamw_clip_step")
+    _count()
