@@ -219,13 +219,16 @@ int b200vsgg_col2im3x3(const void* dcol, int32_t n, int32_t hw, int32_t channels
 int b200vsgg_attn_flash_fwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                             const int32_t* seq_off, const int32_t* blk_seq, const int32_t* blk_row0, int32_t n_blocks,
                             int32_t n_heads, int32_t head_dim, float scale, void* ctx, int32_t ldc, float* lse,
-                            float drop_p, uint64_t seed, void* stream);
+                            float drop_p, uint64_t seed, void* stream, int32_t n_seq, int32_t max_len);
 /* delta fp32 [rows, n_heads] is workspace (rowsum(dO*O), written here). */
 int b200vsgg_attn_flash_bwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                             const void* ctx, int32_t ldc, const void* dctx, int32_t lddc, const float* lse, float* delta,
                             const int32_t* seq_off, const int32_t* blk_seq, const int32_t* blk_row0, int32_t n_blocks,
                             int32_t n_rows, int32_t n_heads, int32_t head_dim, float scale, void* dq, int32_t lddq,
-                            void* dk, int32_t lddk, void* dv, int32_t lddv, float drop_p, uint64_t seed, void* stream);
+                            void* dk, int32_t lddk, void* dv, int32_t lddv, float drop_p, uint64_t seed, void* stream,
+                            int32_t n_seq, int32_t max_len);
+/* (n_seq, max_len = longest sequence: when its head slices fit in shared memory — T <= ~640 at head_dim 24 — the
+ * resident kernels run: one CTA per (sequence, head), operands loaded once; pass n_seq = 0 to force the tiled path.) */
 /* Node tokens (lib/teatgt.py:118-141): tok[i] = so[feat_row[i], half(is_person)] | embed[labels[feat_row[i]]];
  * so = features @ [subj_fc; obj_fc]^T + bias over all boxes, [O, 2*h1] fp32. */
 int b200vsgg_node_tokens_fwd(const float* so, int32_t ld_so, const int32_t* feat_row, const int32_t* is_person,

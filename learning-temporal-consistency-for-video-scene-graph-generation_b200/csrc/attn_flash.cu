@@ -54,11 +54,18 @@ __device__ __forceinline__ float quad_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
-// dropout keep-factor of probability (query row `row` (global), head, key `key` (global row))
-__device__ __forceinline__ float drop_factor(uint32_t thr, float inv_keep, unsigned long long seed, int row, int head,
-                                             int key) {
+// Dropout keep-factor of probability (query row `row` (global), head, key `key` (global row)).  The 64-bit
+// counter hash runs once per (row, head) (`row_key`), each probability then costs one 32-bit murmur3
+// finaliser (~8 integer instructions): the per-element hash was half of the forward's run time.
+__device__ __forceinline__ uint32_t drop_row_key(uint32_t thr, unsigned long long seed, int row, int head) {
+    return thr == 0u ? 0u : hash_u32(seed, static_cast<unsigned long long>(row) * 64ull + head);
+}
+__device__ __forceinline__ float drop_factor(uint32_t thr, float inv_keep, uint32_t row_key, int key) {
     if (thr == 0u) return 1.f;
-    const uint32_t h = hash_u32(seed, (static_cast<unsigned long long>(row) * 64ull + head) * 16777216ull + key);
+    uint32_t h = row_key ^ (static_cast<uint32_t>(key) * 0x9E3779B1u);
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
     return h >= thr ? inv_keep : 0.f;
 }
 
@@ -212,7 +219,7 @@ flash_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat
                     const float p = __expf(s[nt][half * 2 + e] - mx);
                     sum += p;
                     const int col = nt * 8 + tq * 2 + e;
-                    s[nt][half * 2 + e] = p * drop_factor(thr, inv_keep, seed, qrow0 + r_loc[half], head, kb + col);
+                    s[nt][half * 2 + e] = p * drop_factor(thr, inv_keep, drop_row_key(thr, seed, qrow0 + r_loc[half], head), kb + col);
                 }
             sum = quad_sum(sum);
             lrow[half] = lrow[half] * corr + sum;
@@ -326,7 +333,7 @@ flash_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
                 const int half = e >> 1, col = nt * 8 + tq * 2 + (e & 1);
                 const bool ok = col < krows && r_loc[half] < qrows;
                 const float p = ok ? __expf(s[nt][e] * scale - lse_r[half]) : 0.f;
-                const float f = drop_factor(thr, inv_keep, seed, qrow0 + r_loc[half], head, kb + col);
+                const float f = drop_factor(thr, inv_keep, drop_row_key(thr, seed, qrow0 + r_loc[half], head), kb + col);
                 s[nt][e] = p * (dp[nt][e] * f - del_r[half]);              // dS
             }
         uint32_t da[4][4];
@@ -367,6 +374,7 @@ flash_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
     uint8_t* Os = Qs + G::TILE;
     float* lse_s = reinterpret_cast<float*>(Os + G::TILE);
     float* del_s = lse_s + BLK;
+    uint32_t* rk_s = reinterpret_cast<uint32_t*>(del_s + BLK);     // dropout row keys of the staged queries
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
     const int head = blockIdx.y, col0 = head * hd;
     const int seq = blk_seq[blockIdx.x];
@@ -398,6 +406,7 @@ flash_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
             const size_t idx = static_cast<size_t>(qb + (ok ? threadIdx.x : 0)) * n_heads + head;
             lse_s[threadIdx.x] = ok ? lse[idx] : 0.f;
             del_s[threadIdx.x] = ok ? delta[idx] : 0.f;
+            rk_s[threadIdx.x] = drop_row_key(thr, seed, qb + threadIdx.x, head);
         }
         cp_async_wait_all();
         __syncthreads();
@@ -416,7 +425,7 @@ flash_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
                 const int half = e >> 1, qc = nt * 8 + tq * 2 + (e & 1);  // query column
                 const bool ok = qc < qrows && r_loc[half] < krows;
                 const float p = ok ? __expf(st[nt][e] * scale - lse_s[qc]) : 0.f;
-                const float f = drop_factor(thr, inv_keep, seed, qb + qc, head, krow0 + r_loc[half]);
+                const float f = drop_factor(thr, inv_keep, rk_s[qc], krow0 + r_loc[half]);
                 pt[nt][e] = p * f;                                         // P~^T
                 st[nt][e] = p * (dpt[nt][e] * f - del_s[qc]);              // dS^T
             }
@@ -439,6 +448,307 @@ flash_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
                     pack_bf16(dk_acc[j][half * 2] * scale, dk_acc[j][half * 2 + 1] * scale);
                 *reinterpret_cast<uint32_t*>(dv + grow * lddv + col0 + d) =
                     pack_bf16(dv_acc[j][half * 2], dv_acc[j][half * 2 + 1]);
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// Resident variants for sequences whose K/V (forward) or Q/K/V/dO (backward) head slices fit in shared
+// memory (T <= ~640 at head_dim 24): one CTA per (sequence, head) loads the operands ONCE, then its warps
+// walk their 16-row blocks against the resident tiles without any block-level synchronisation.  This is
+// the C3 regime (clips of ~450 tokens): the tiled kernels above re-stage K/V per 64-row query block and
+// pay two barriers per key block, which dominates when the per-block math is only 64x64x32.
+// ================================================================================================
+template <int HDP>
+__device__ __forceinline__ void stage_seq(uint8_t* tile, const __nv_bfloat16* src, int ld, int row0, int rows,
+                                          int rows_pad, int col0, int hd) {
+    constexpr int PITCH = Geo<HDP>::PITCH;
+    const int chunks = hd >> 3, chunks_p = HDP >> 3;
+    const uint32_t t = s_u32(tile);
+    for (int i = threadIdx.x; i < rows_pad * chunks_p; i += blockDim.x) {
+        const int r = i / chunks_p, ch = i - r * chunks_p;
+        if (r < rows && ch < chunks)
+            cp_async16(t + r * PITCH + ch * 16, src + static_cast<size_t>(row0 + r) * ld + col0 + ch * 8);
+        else
+            *reinterpret_cast<uint4*>(tile + r * PITCH + ch * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// A fragments of 16 rows starting at `tile` (row-major, PITCH) — rows are addressed relative to `tile`.
+template <int HDP>
+__device__ __forceinline__ void load_a_frags_at(uint32_t (&a)[Geo<HDP>::KS][4], const uint8_t* tile, int lane) {
+    const uint32_t base = s_u32(tile) + (lane & 15) * Geo<HDP>::PITCH + (lane >> 4) * 16;
+#pragma unroll
+    for (int ks = 0; ks < Geo<HDP>::KS; ++ks) ldsm_x4(a[ks], base + ks * 32);
+}
+
+// A fragments of 16 query rows straight from global memory (rows >= rows_valid and columns >= hd read as 0).
+template <int HDP>
+__device__ __forceinline__ void load_a_frags_global(uint32_t (&a)[Geo<HDP>::KS][4], const __nv_bfloat16* src, int ld,
+                                                    int row0, int rows_valid, int col0, int hd, int lane) {
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < Geo<HDP>::KS; ++ks) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int r = gq + (e & 1) * 8, c = ks * 16 + (e >> 1) * 8 + tq * 2;
+            a[ks][e] = (r < rows_valid && c < hd)
+                           ? *reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(row0 + r) * ld + col0 + c) : 0u;
+        }
+    }
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(128)
+flash_fwd_res_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
+                     const __nv_bfloat16* __restrict__ v, int ldv, const int32_t* __restrict__ seq_off, int hd,
+                     float scale, __nv_bfloat16* __restrict__ ctx, int ldc, float* __restrict__ lse, int n_heads,
+                     int t_pad_max, float drop_p, unsigned long long seed) {
+    using G = Geo<HDP>;
+    extern __shared__ __align__(16) uint8_t fa_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+    const int seq = blockIdx.x, head = blockIdx.y, col0 = head * hd;
+    const int s0 = seq_off[seq], T = seq_off[seq + 1] - s0;
+    if (T <= 0) return;
+    const int t_pad = (T + BLK - 1) / BLK * BLK;
+    uint8_t* Ks = fa_smem;
+    uint8_t* Vs = Ks + static_cast<size_t>(t_pad_max) * G::PITCH;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    stage_seq<HDP>(Ks, k, ldk, s0, T, t_pad, col0, hd);
+    stage_seq<HDP>(Vs, v, ldv, s0, T, t_pad, col0, hd);
+    cp_async_wait_all();
+    __syncthreads();
+    for (int qb = warp * 16; qb < T; qb += 64) {
+        const int qrows = min(16, T - qb);
+        uint32_t qa[G::KS][4];
+        load_a_frags_global<HDP>(qa, q, ldq, s0 + qb, qrows, col0, hd, lane);
+        float o[G::NT_D][4];
+#pragma unroll
+        for (int j = 0; j < G::NT_D; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[j][e] = 0.f;
+        float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+        const int r_loc[2] = {gq, gq + 8};
+        for (int kb = 0; kb < T; kb += BLK) {
+            const int krows = min(BLK, T - kb);
+            float s[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[nt][e] = 0.f;
+            mma_ab_t<HDP>(s, qa, Ks + static_cast<size_t>(kb) * G::PITCH, lane);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float mx = mrow[half];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int col = nt * 8 + tq * 2 + e;
+                        const float x = col < krows ? s[nt][half * 2 + e] * scale : -INFINITY;
+                        s[nt][half * 2 + e] = x;
+                        mx = fmaxf(mx, x);
+                    }
+                mx = quad_max(mx);
+                const float corr = __expf(mrow[half] - mx);
+                float sum = 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float p = __expf(s[nt][half * 2 + e] - mx);
+                        sum += p;
+                        const int col = nt * 8 + tq * 2 + e;
+                        s[nt][half * 2 + e] = p * drop_factor(thr, inv_keep, drop_row_key(thr, seed, s0 + qb + r_loc[half], head), s0 + kb + col);
+                    }
+                sum = quad_sum(sum);
+                lrow[half] = lrow[half] * corr + sum;
+                mrow[half] = mx;
+#pragma unroll
+                for (int j = 0; j < G::NT_D; ++j) { o[j][half * 2] *= corr; o[j][half * 2 + 1] *= corr; }
+            }
+            uint32_t pa[4][4];
+            pack_c_to_a(pa, s);
+            mma_p_b<HDP>(o, pa, Vs + static_cast<size_t>(kb) * G::PITCH, lane);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = r_loc[half];
+            if (r >= qrows) continue;
+            const float inv = 1.f / lrow[half];
+            const size_t grow = static_cast<size_t>(s0 + qb + r);
+#pragma unroll
+            for (int j = 0; j < G::NT_D; ++j) {
+                const int d = j * 8 + tq * 2;
+                if (d < hd)
+                    *reinterpret_cast<uint32_t*>(ctx + grow * ldc + col0 + d) =
+                        pack_bf16(o[j][half * 2] * inv, o[j][half * 2 + 1] * inv);
+            }
+            if (lse != nullptr && tq == 0) lse[grow * n_heads + head] = mrow[half] + __logf(lrow[half]);
+        }
+    }
+}
+
+// Backward, resident: Q, K, V, dO of the (sequence, head) in shared memory, delta computed in the kernel;
+// phase 1 (query-row blocks -> dQ), phase 2 (key-row blocks -> dK, dV).  8 warps, one barrier in total.
+template <int HDP>
+__global__ void __launch_bounds__(256)
+flash_bwd_res_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
+                     const __nv_bfloat16* __restrict__ v, int ldv, const __nv_bfloat16* __restrict__ o, int ldo,
+                     const __nv_bfloat16* __restrict__ d_o, int lddo, const float* __restrict__ lse,
+                     const int32_t* __restrict__ seq_off, int hd, float scale, __nv_bfloat16* __restrict__ dq, int lddq,
+                     __nv_bfloat16* __restrict__ dk, int lddk, __nv_bfloat16* __restrict__ dv, int lddv, int n_heads,
+                     int t_pad_max, float drop_p, unsigned long long seed) {
+    using G = Geo<HDP>;
+    extern __shared__ __align__(16) uint8_t fa_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+    const int seq = blockIdx.x, head = blockIdx.y, col0 = head * hd;
+    const int s0 = seq_off[seq], T = seq_off[seq + 1] - s0;
+    if (T <= 0) return;
+    const int t_pad = (T + BLK - 1) / BLK * BLK;
+    const size_t tile = static_cast<size_t>(t_pad_max) * G::PITCH;
+    uint8_t* Qs = fa_smem;
+    uint8_t* Ks = Qs + tile;
+    uint8_t* Vs = Ks + tile;
+    uint8_t* Os = Vs + tile;
+    float* lse_s = reinterpret_cast<float*>(Os + tile);
+    float* del_s = lse_s + t_pad_max;
+    uint32_t* rk_s = reinterpret_cast<uint32_t*>(del_s + t_pad_max);
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    stage_seq<HDP>(Qs, q, ldq, s0, T, t_pad, col0, hd);
+    stage_seq<HDP>(Ks, k, ldk, s0, T, t_pad, col0, hd);
+    stage_seq<HDP>(Vs, v, ldv, s0, T, t_pad, col0, hd);
+    stage_seq<HDP>(Os, d_o, lddo, s0, T, t_pad, col0, hd);
+    for (int r = threadIdx.x; r < t_pad; r += blockDim.x) {
+        float acc = 0.f, l = 0.f;
+        if (r < T) {
+            const __nv_bfloat16* op = o + static_cast<size_t>(s0 + r) * ldo + col0;
+            const __nv_bfloat16* dp = d_o + static_cast<size_t>(s0 + r) * lddo + col0;
+            for (int c = 0; c < hd; c += 8) {
+                float a[8], b[8];
+                load_bf16x8(op + c, a);
+                load_bf16x8(dp + c, b);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc = fmaf(a[j], b[j], acc);
+            }
+            l = lse[static_cast<size_t>(s0 + r) * n_heads + head];
+        }
+        del_s[r] = acc;
+        lse_s[r] = l;
+        rk_s[r] = drop_row_key(thr, seed, s0 + r, head);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int nblk16 = (T + 15) / 16;
+    // ---------------- phase 1: dQ
+    for (int b = warp; b < nblk16; b += 8) {
+        const int qb = b * 16;
+        const int qrows = min(16, T - qb);
+        uint32_t qa[G::KS][4], oa[G::KS][4];
+        load_a_frags_at<HDP>(qa, Qs + static_cast<size_t>(qb) * G::PITCH, lane);
+        load_a_frags_at<HDP>(oa, Os + static_cast<size_t>(qb) * G::PITCH, lane);
+        const int r_loc[2] = {gq, gq + 8};
+        const float lse_r[2] = {lse_s[qb + gq], lse_s[min(qb + gq + 8, t_pad - 1)]};
+        const float del_r[2] = {del_s[qb + gq], del_s[min(qb + gq + 8, t_pad - 1)]};
+        float acc[G::NT_D][4];
+#pragma unroll
+        for (int j = 0; j < G::NT_D; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+        for (int kb = 0; kb < T; kb += BLK) {
+            const int krows = min(BLK, T - kb);
+            float s[8][4], dp[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { s[nt][e] = 0.f; dp[nt][e] = 0.f; }
+            mma_ab_t<HDP>(s, qa, Ks + static_cast<size_t>(kb) * G::PITCH, lane);
+            mma_ab_t<HDP>(dp, oa, Vs + static_cast<size_t>(kb) * G::PITCH, lane);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int half = e >> 1, col = nt * 8 + tq * 2 + (e & 1);
+                    const bool ok = col < krows && r_loc[half] < qrows;
+                    const float p = ok ? __expf(s[nt][e] * scale - lse_r[half]) : 0.f;
+                    const float f = drop_factor(thr, inv_keep, rk_s[min(qb + r_loc[half], t_pad - 1)], s0 + kb + col);
+                    s[nt][e] = p * (dp[nt][e] * f - del_r[half]);
+                }
+            uint32_t da[4][4];
+            pack_c_to_a(da, s);
+            mma_p_b<HDP>(acc, da, Ks + static_cast<size_t>(kb) * G::PITCH, lane);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = r_loc[half];
+            if (r >= qrows) continue;
+            const size_t grow = static_cast<size_t>(s0 + qb + r);
+#pragma unroll
+            for (int j = 0; j < G::NT_D; ++j) {
+                const int d = j * 8 + tq * 2;
+                if (d < hd)
+                    *reinterpret_cast<uint32_t*>(dq + grow * lddq + col0 + d) =
+                        pack_bf16(acc[j][half * 2] * scale, acc[j][half * 2 + 1] * scale);
+            }
+        }
+    }
+    // ---------------- phase 2: dK, dV (rows of the MMA tiles are keys, columns are queries)
+    for (int b = warp; b < nblk16; b += 8) {
+        const int kb = b * 16;
+        const int krows = min(16, T - kb);
+        uint32_t ka[G::KS][4], va[G::KS][4];
+        load_a_frags_at<HDP>(ka, Ks + static_cast<size_t>(kb) * G::PITCH, lane);
+        load_a_frags_at<HDP>(va, Vs + static_cast<size_t>(kb) * G::PITCH, lane);
+        const int r_loc[2] = {gq, gq + 8};
+        float dk_acc[G::NT_D][4], dv_acc[G::NT_D][4];
+#pragma unroll
+        for (int j = 0; j < G::NT_D; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { dk_acc[j][e] = 0.f; dv_acc[j][e] = 0.f; }
+        for (int qb = 0; qb < T; qb += BLK) {
+            const int qrows = min(BLK, T - qb);
+            float st[8][4], dpt[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { st[nt][e] = 0.f; dpt[nt][e] = 0.f; }
+            mma_ab_t<HDP>(st, ka, Qs + static_cast<size_t>(qb) * G::PITCH, lane);
+            mma_ab_t<HDP>(dpt, va, Os + static_cast<size_t>(qb) * G::PITCH, lane);
+            float pt[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int half = e >> 1, qc = nt * 8 + tq * 2 + (e & 1);
+                    const bool ok = qc < qrows && r_loc[half] < krows;
+                    const float p = ok ? __expf(st[nt][e] * scale - lse_s[qb + qc]) : 0.f;
+                    const float f = drop_factor(thr, inv_keep, rk_s[qb + qc], s0 + kb + r_loc[half]);
+                    pt[nt][e] = p * f;
+                    st[nt][e] = p * (dpt[nt][e] * f - del_s[qb + qc]);
+                }
+            uint32_t pa[4][4], da[4][4];
+            pack_c_to_a(pa, pt);
+            pack_c_to_a(da, st);
+            mma_p_b<HDP>(dv_acc, pa, Os + static_cast<size_t>(qb) * G::PITCH, lane);
+            mma_p_b<HDP>(dk_acc, da, Qs + static_cast<size_t>(qb) * G::PITCH, lane);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = r_loc[half];
+            if (r >= krows) continue;
+            const size_t grow = static_cast<size_t>(s0 + kb + r);
+#pragma unroll
+            for (int j = 0; j < G::NT_D; ++j) {
+                const int d = j * 8 + tq * 2;
+                if (d < hd) {
+                    *reinterpret_cast<uint32_t*>(dk + grow * lddk + col0 + d) =
+                        pack_bf16(dk_acc[j][half * 2] * scale, dk_acc[j][half * 2 + 1] * scale);
+                    *reinterpret_cast<uint32_t*>(dv + grow * lddv + col0 + d) =
+                        pack_bf16(dv_acc[j][half * 2], dv_acc[j][half * 2 + 1]);
+                }
             }
         }
     }
@@ -467,16 +777,45 @@ static int flash_args_ok(int hd, int n_heads, const void* q, int ldq, const void
     return 0;
 }
 
+// Largest padded sequence length whose resident tiles fit in shared memory (0 = use the tiled kernels).
+static int resident_t_pad(int max_len, int pitch, int tiles, int extra_per_row) {
+    if (max_len <= 0) return 0;
+    const int t_pad = (max_len + BLK - 1) / BLK * BLK;
+    const size_t need = static_cast<size_t>(t_pad) * (static_cast<size_t>(tiles) * pitch + extra_per_row);
+    return need <= 220 * 1024 ? t_pad : 0;
+}
+
 extern "C" int b200vsgg_attn_flash_fwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                                        const int32_t* seq_off, const int32_t* blk_seq, const int32_t* blk_row0,
                                        int32_t n_blocks, int32_t n_heads, int32_t head_dim, float scale, void* ctx,
-                                       int32_t ldc, float* lse, float drop_p, uint64_t seed, void* stream) {
+                                       int32_t ldc, float* lse, float drop_p, uint64_t seed, void* stream, int32_t n_seq,
+                                       int32_t max_len) {
     if (!q || !k || !v || !seq_off || !blk_seq || !blk_row0 || !ctx) return set_error(B200VSGG_ERR_BAD_ARG, "attn_flash_fwd: null pointer");
     int rc = flash_args_ok(head_dim, n_heads, q, ldq, k, ldk, v, ldv);
     if (rc) return rc;
     if (n_blocks == 0) return 0;
-    dim3 grid(n_blocks, n_heads);
     cudaStream_t st = (cudaStream_t)stream;
+    {   // resident path: K/V of a (sequence, head) fit in shared memory
+        const int pitch = head_dim <= 32 ? Geo<32>::PITCH : (head_dim <= 48 ? Geo<48>::PITCH : Geo<64>::PITCH);
+        const int t_pad = n_seq > 0 ? resident_t_pad(max_len, pitch, 2, 0) : 0;
+        if (t_pad > 0 && t_pad <= 1024) {
+            const size_t smem = 2ull * t_pad * pitch;
+            dim3 grid(n_seq, n_heads);
+#define FA_FWD_RES(HDP)                                                                                          \
+    {                                                                                                            \
+        static size_t cur = 0;                                                                                   \
+        if (smem > cur) { if ((rc = set_smem(flash_fwd_res_kernel<HDP>, smem))) return rc; cur = smem; }         \
+        flash_fwd_res_kernel<HDP><<<grid, 128, smem, st>>>(                                                      \
+            (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, seq_off,   \
+            head_dim, scale, (__nv_bfloat16*)ctx, ldc, lse, n_heads, t_pad, drop_p, seed);                       \
+    }
+            if (head_dim <= 32) FA_FWD_RES(32) else if (head_dim <= 48) FA_FWD_RES(48) else FA_FWD_RES(64)
+#undef FA_FWD_RES
+            VSGG_CUDA_CHECK_LAUNCH();
+            return 0;
+        }
+    }
+    dim3 grid(n_blocks, n_heads);
 #define FA_FWD(HDP)                                                                                              \
     {                                                                                                            \
         const size_t smem = 3 * Geo<HDP>::TILE;                                                                  \
@@ -497,7 +836,8 @@ extern "C" int b200vsgg_attn_flash_bwd(const void* q, int32_t ldq, const void* k
                                        float* delta, const int32_t* seq_off, const int32_t* blk_seq,
                                        const int32_t* blk_row0, int32_t n_blocks, int32_t n_rows, int32_t n_heads,
                                        int32_t head_dim, float scale, void* dq, int32_t lddq, void* dk, int32_t lddk,
-                                       void* dv, int32_t lddv, float drop_p, uint64_t seed, void* stream) {
+                                       void* dv, int32_t lddv, float drop_p, uint64_t seed, void* stream, int32_t n_seq,
+                                       int32_t max_len) {
     if (!q || !k || !v || !ctx || !dctx || !lse || !delta || !seq_off || !blk_seq || !blk_row0 || !dq || !dk || !dv)
         return set_error(B200VSGG_ERR_BAD_ARG, "attn_flash_bwd: null pointer");
     int rc = flash_args_ok(head_dim, n_heads, q, ldq, k, ldk, v, ldv);
@@ -506,6 +846,28 @@ extern "C" int b200vsgg_attn_flash_bwd(const void* q, int32_t ldq, const void* k
         return set_error(B200VSGG_ERR_BAD_ARG, "attn_flash_bwd: ctx/dctx alignment");
     if (n_blocks == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    {   // resident path: Q, K, V, dO of a (sequence, head) fit in shared memory; one launch for dQ, dK, dV
+        const int pitch = head_dim <= 32 ? Geo<32>::PITCH : (head_dim <= 48 ? Geo<48>::PITCH : Geo<64>::PITCH);
+        const int t_pad = n_seq > 0 ? resident_t_pad(max_len, pitch, 4, 12) : 0;
+        if (t_pad > 0) {
+            const size_t smem = 4ull * t_pad * pitch + 12ull * t_pad;
+            dim3 grid(n_seq, n_heads);
+#define FA_BWD_RES(HDP)                                                                                          \
+    {                                                                                                            \
+        static size_t cur = 0;                                                                                   \
+        if (smem > cur) { if ((rc = set_smem(flash_bwd_res_kernel<HDP>, smem))) return rc; cur = smem; }         \
+        flash_bwd_res_kernel<HDP><<<grid, 256, smem, st>>>(                                                      \
+            (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv,            \
+            (const __nv_bfloat16*)ctx, ldc, (const __nv_bfloat16*)dctx, lddc, lse, seq_off, head_dim, scale,     \
+            (__nv_bfloat16*)dq, lddq, (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, n_heads, t_pad, drop_p, \
+            seed);                                                                                               \
+    }
+            if (head_dim <= 32) FA_BWD_RES(32) else if (head_dim <= 48) FA_BWD_RES(48) else FA_BWD_RES(64)
+#undef FA_BWD_RES
+            VSGG_CUDA_CHECK_LAUNCH();
+            return 0;
+        }
+    }
     {
         const long long items = static_cast<long long>(n_rows) * n_heads;
         flash_delta_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)ctx, ldc,
@@ -516,7 +878,7 @@ extern "C" int b200vsgg_attn_flash_bwd(const void* q, int32_t ldq, const void* k
 #define FA_BWD(HDP)                                                                                              \
     {                                                                                                            \
         const size_t smem_q = 4 * Geo<HDP>::TILE;                                                                \
-        const size_t smem_kv = 4 * Geo<HDP>::TILE + 2 * BLK * sizeof(float);                                     \
+        const size_t smem_kv = 4 * Geo<HDP>::TILE + 3 * BLK * sizeof(float);                                     \
         static bool done = false;                                                                                \
         if (!done) {                                                                                             \
             if ((rc = set_smem(flash_bwd_dq_kernel<HDP>, smem_q))) return rc;                                    \

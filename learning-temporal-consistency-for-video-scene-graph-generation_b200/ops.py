@@ -379,16 +379,17 @@ def col2im3x3(dcol, n, hw, channels, dz):
 # ------------------------------------------------------------------------------------------------
 # TEAT-GT / TokenGT path
 # ------------------------------------------------------------------------------------------------
-def attn_flash_fwd(q, k, v, seq_off, blk_seq, blk_row0, n_heads, head_dim, ctx, lse=None, drop_p=0.0, seed=0):
+def attn_flash_fwd(q, k, v, seq_off, blk_seq, blk_row0, n_heads, head_dim, ctx, lse=None, drop_p=0.0, seed=0, max_len=0):
     scale = float(head_dim) ** -0.5
     check(_lib.lib().b200vsgg_attn_flash_fwd(
         _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), _ptr(seq_off), _ptr(blk_seq),
         _ptr(blk_row0), blk_seq.numel(), n_heads, head_dim, scale, _ptr(_bf(ctx)), ctx.stride(0), _ptr(lse), drop_p, seed,
-        _stream()), "attn_flash_fwd")
+        _stream(), seq_off.numel() - 1 if max_len > 0 else 0, max_len), "attn_flash_fwd")
     _count()
 
 
-def attn_flash_bwd(q, k, v, ctx, dctx, lse, seq_off, blk_seq, blk_row0, n_heads, head_dim, dq, dk, dv, drop_p=0.0, seed=0):
+def attn_flash_bwd(q, k, v, ctx, dctx, lse, seq_off, blk_seq, blk_row0, n_heads, head_dim, dq, dk, dv, drop_p=0.0, seed=0,
+                   max_len=0):
     scale = float(head_dim) ** -0.5
     rows = q.shape[0]
     delta = torch.empty(rows, n_heads, device=q.device, dtype=torch.float32)
@@ -396,7 +397,8 @@ def attn_flash_bwd(q, k, v, ctx, dctx, lse, seq_off, blk_seq, blk_row0, n_heads,
         _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), _ptr(_bf(ctx)), ctx.stride(0),
         _ptr(_bf(dctx)), dctx.stride(0), _ptr(lse), _ptr(delta), _ptr(seq_off), _ptr(blk_seq), _ptr(blk_row0),
         blk_seq.numel(), rows, n_heads, head_dim, scale, _ptr(_bf(dq)), dq.stride(0), _ptr(_bf(dk)), dk.stride(0),
-        _ptr(_bf(dv)), dv.stride(0), drop_p, seed, _stream()), "attn_flash_bwd")
+        _ptr(_bf(dv)), dv.stride(0), drop_p, seed, _stream(), seq_off.numel() - 1 if max_len > 0 else 0, max_len),
+          "attn_flash_bwd")
     _count(3)
 
 

@@ -37,6 +37,9 @@ class AttnPlan:
         self.seq_off = ops.upload(np.asarray(seq_off_h, dtype=np.int32), device)
         self.blk_seq = ops.upload(bs, device)
         self.blk_row0 = ops.upload(br, device)
+        # 0 = tiled kernels.  The shared-memory-resident variants (pass the longest sequence length) are correct
+        # but measured slower at the C3 shapes (occupancy: 1-2 CTAs/SM), see profiles/r01_flash_attention.txt
+        self.max_len = 0
 
 
 class PreLNAttention(torch.autograd.Function):
@@ -57,7 +60,7 @@ class PreLNAttention(torch.autograd.Function):
         att = _new(T, d, BF16, dev)
         lse = torch.empty(T, n_heads, device=dev)
         ops.attn_flash_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], plan.seq_off, plan.blk_seq, plan.blk_row0, n_heads,
-                           hd, att, lse, p_attn, seed)
+                           hd, att, lse, p_attn, seed, plan.max_len)
         wob = _bf(wo)
         y = _new(T, d, F32, dev)
         ops.gemm(att, wob, bias=bo.detach(), residual=x, out_f32=y, dropout_p=p_out, seed=seed + 1)
@@ -81,7 +84,8 @@ class PreLNAttention(torch.autograd.Function):
         ops.gemm(dyb, wob, b_mn=True, out_bf16=datt)
         dqkv = _new(T, 3 * d, BF16, dev)
         ops.attn_flash_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, datt, lse, plan.seq_off, plan.blk_seq,
-                           plan.blk_row0, n_heads, hd, dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], p_attn, seed)
+                           plan.blk_row0, n_heads, hd, dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], p_attn, seed,
+                           plan.max_len)
         dwqkv = _new(3 * d, d, F32, dev)
         ops.gemm(dqkv, h, a_mn=True, b_mn=True, out_f32=dwqkv)
         dbqkv = _colsum(dqkv)

@@ -31,9 +31,13 @@ def _ref(q, k, v, off, H, hd, mask=None, p=0.0):
     return torch.cat(outs)
 
 
+@pytest.mark.parametrize("resident", [False, True])
 @pytest.mark.parametrize("H,hd,lens", [(32, 24, [130, 64, 7, 200, 1]), (16, 48, [65, 300]), (4, 64, [64, 40, 129]),
-                                       (32, 24, [447])])
-def test_flash_fwd_bwd(cuda_lib, H, hd, lens):
+                                       (32, 24, [447]), (32, 24, [640, 3])])
+def test_flash_fwd_bwd(cuda_lib, H, hd, lens, resident):
+    """resident=True passes the longest sequence length, which selects the shared-memory-resident kernels
+    (one CTA per (sequence, head)); False forces the tiled kernels.  Same results either way."""
+    ml = max(lens) if resident else 0
     from b200vsgg import ops
     D, M = H * hd, sum(lens)
     off_h, off, bs, br = _plan(lens)
@@ -42,25 +46,28 @@ def test_flash_fwd_bwd(cuda_lib, H, hd, lens):
     q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
     ctx = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
     lse = torch.empty(M, H, device=DEV)
-    ops.attn_flash_fwd(q, k, v, off, bs, br, H, hd, ctx, lse)
+    ops.attn_flash_fwd(q, k, v, off, bs, br, H, hd, ctx, lse, max_len=ml)
     qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
     ref = _ref(qf, kf, vf, off_h, H, hd)
     assert (ctx.float() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item() + 1e-3
     dctx = torch.randn(M, D, generator=g, device=DEV).bfloat16()
     ref.backward(dctx.float())
     dqkv = torch.empty(M, 3 * D, device=DEV, dtype=torch.bfloat16)
-    ops.attn_flash_bwd(q, k, v, ctx, dctx, lse, off, bs, br, H, hd, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:])
+    ops.attn_flash_bwd(q, k, v, ctx, dctx, lse, off, bs, br, H, hd, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
+                       max_len=ml)
     for name, got, want in (("dq", dqkv[:, :D], qf.grad), ("dk", dqkv[:, D:2 * D], kf.grad), ("dv", dqkv[:, 2 * D:], vf.grad)):
         tol = 2 ** -6 * want.abs().max().item() + 1e-3
         err = (got.float() - want).abs().max().item()
         assert err < tol, (name, err, tol)
 
 
-def test_flash_dropout_mask_consistent_between_fwd_and_bwd(cuda_lib):
+@pytest.mark.parametrize("resident", [False, True])
+def test_flash_dropout_mask_consistent_between_fwd_and_bwd(cuda_lib, resident):
     """One-hot values recover the dropped probabilities (ctx = P~ V); dq/dk/dv must equal autograd through
     P * mask / (1-p) with that mask."""
     from b200vsgg import ops
     H, hd, lens, p, seed = 2, 64, [64, 40], 0.25, 99
+    ml = max(lens) if resident else 0
     D, M = H * hd, sum(lens)
     off_h, off, bs, br = _plan(lens)
     g = torch.Generator(device=DEV).manual_seed(5)
@@ -71,7 +78,7 @@ def test_flash_dropout_mask_consistent_between_fwd_and_bwd(cuda_lib):
         for j in range(lens[s]):
             onehot[int(off_h[s]) + j].view(H, hd)[:, j] = 1
     probe = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
-    ops.attn_flash_fwd(q, k, onehot, off, bs, br, H, hd, probe, None, p, seed)
+    ops.attn_flash_fwd(q, k, onehot, off, bs, br, H, hd, probe, None, p, seed, max_len=ml)
     masks = []
     for s in range(len(lens)):
         a, L = int(off_h[s]), lens[s]
@@ -80,13 +87,14 @@ def test_flash_dropout_mask_consistent_between_fwd_and_bwd(cuda_lib):
     assert 0.65 < kept < 0.85
     ctx = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
     lse = torch.empty(M, H, device=DEV)
-    ops.attn_flash_fwd(q, k, v, off, bs, br, H, hd, ctx, lse, p, seed)
+    ops.attn_flash_fwd(q, k, v, off, bs, br, H, hd, ctx, lse, p, seed, max_len=ml)
     qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
     ref = _ref(qf, kf, vf, off_h, H, hd, masks, p)
     assert (ctx.float() - ref).abs().max().item() < 2 ** -7 * ref.abs().max().item() + 1e-3
     dctx = torch.randn(M, D, generator=g, device=DEV).bfloat16()
     ref.backward(dctx.float())
     dqkv = torch.empty(M, 3 * D, device=DEV, dtype=torch.bfloat16)
-    ops.attn_flash_bwd(q, k, v, ctx, dctx, lse, off, bs, br, H, hd, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], p, seed)
+    ops.attn_flash_bwd(q, k, v, ctx, dctx, lse, off, bs, br, H, hd, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], p, seed,
+                       max_len=ml)
     for got, want in ((dqkv[:, :D], qf.grad), (dqkv[:, D:2 * D], kf.grad), (dqkv[:, 2 * D:], vf.grad)):
         assert (got.float() - want).abs().max().item() < 2 ** -6 * want.abs().max().item() + 1e-3
