@@ -180,8 +180,12 @@ class TeatPlan:
         return self
 
     # ---------------------------------------------------------------------------------------
-    def build_graph(self, spatial, temporal, lap_k, eig_threads=8):
-        """spatial / temporal: uint8 [F, nmax, nmax] predicate matrices (host numpy)."""
+    def build_graph(self, spatial, temporal, lap_k, eig_threads=8, eig_backend="host"):
+        """spatial / temporal: uint8 [F, nmax, nmax] predicate matrices (host numpy).
+        eig_backend: "host" = numpy/LAPACK fp64 eigh, the reference's own call (bit-identical eigenvectors);
+        "device" = batched cuSOLVER eigh (torch.linalg.eigh, fp64) on the padded Laplacians — same eigenvalues and
+        eigenspaces, but the basis inside degenerate eigenspaces and the signs are solver-dependent (as they are
+        between LAPACK builds), so outputs are not comparable element-wise with the reference's."""
         node_off, F = self.node_off_h, self.F
         sf, sa, sb = np.nonzero(spatial)                        # row-major = itertools.combinations order
         tf, tp, tc = np.nonzero(temporal)                       # row-major = itertools.product(prev, cur) order
@@ -226,26 +230,41 @@ class TeatPlan:
         lu = e_u - self.clip_node_off[e_clip]
         lv = e_v - self.clip_node_off[e_clip]
 
-        def solve(cl):
-            n = int(nodes_pc[cl])
-            a, b = int(edge_off[cl]), int(edge_off[cl + 1])
-            A = np.zeros((n, n), dtype=np.float64)
-            np.add.at(A, (lv[a:b], lu[a:b]), 1.0)
-            deg = np.bincount(lv[a:b], minlength=n)
-            nm = (torch.from_numpy(deg).clip(1) ** -0.5).numpy()      # float32 values, like the reference
-            Nm = np.diag(nm)
-            L = np.eye(n) - Nm @ A @ Nm
-            _, vec = np.linalg.eigh(L)
-            vec = vec.astype(np.float32)
-            k = min(lap_k, n)
-            ev_all[self.clip_node_off[cl]:self.clip_node_off[cl + 1], :k] = vec[:, :k]
+        # all clip adjacencies at once (padded), then one stacked LAPACK call per node count: numpy's stacked
+        # eigh runs the reference's per-matrix routine without the GIL, so the groups parallelise over threads
+        nmaxc = int(nodes_pc.max())
+        A = np.zeros((self.n_clips, nmaxc, nmaxc), dtype=np.float64)
+        np.add.at(A, (e_clip, lv, lu), 1.0)
+        deg = A.sum(2).astype(np.int64)                                  # in-degree (row = destination)
+        nm = (torch.from_numpy(deg).clip(1) ** -0.5).numpy().astype(np.float64)   # float32 values, like the reference
+        L = np.eye(nmaxc)[None] - nm[:, :, None] * A * nm[:, None, :]
 
-        if self.n_clips <= 4 or eig_threads <= 1:
-            for cl in range(self.n_clips):
-                solve(cl)
+        def solve(n):
+            idx = np.nonzero(nodes_pc == n)[0]
+            _, vec = np.linalg.eigh(L[idx][:, :n, :n])
+            vec = vec.astype(np.float32)
+            k = min(lap_k, int(n))
+            for j, cl in enumerate(idx):
+                ev_all[self.clip_node_off[cl]:self.clip_node_off[cl + 1], :k] = vec[j, :, :k]
+
+        sizes = [int(n) for n in np.unique(nodes_pc)]
+        if eig_backend == "device":
+            pad = np.arange(nmaxc)[None, :] >= nodes_pc[:, None]            # padded rows/cols: isolated, eigenvalue 10
+            Lp = L.copy()
+            Lp[pad[:, :, None] & pad[:, None, :] & np.eye(nmaxc, dtype=bool)[None]] = 10.0
+            _, vec = torch.linalg.eigh(torch.from_numpy(Lp).to(self.device))
+            vec = vec.to(torch.float32).cpu().numpy()
+            k = min(lap_k, nmaxc)
+            local = np.arange(self.n_nodes) - self.clip_node_off[self.clip_of_node]
+            ev_all[:, :k] = vec[self.clip_of_node, local, :k]
+            kk = np.minimum(lap_k, nodes_pc)[self.clip_of_node]            # columns >= n_c belong to the padding
+            ev_all[np.arange(kp)[None, :] >= kk[:, None]] = 0.0
+        elif len(sizes) <= 2 or eig_threads <= 1:
+            for n in sizes:
+                solve(n)
         else:
             with ThreadPoolExecutor(eig_threads) as pool:
-                list(pool.map(solve, range(self.n_clips)))
+                list(pool.map(solve, sizes))
         self.eigvec_h = ev_all
         return self
 
@@ -297,6 +316,7 @@ class TEAT_GT(nn.Module):
         self.eig_dropout = float(getattr(args, "lap_node_id_eig_dropout", 0.0))
         self.dropout_p = 0.1            # dropout = attention_dropout = activation_dropout = 0.1 (models/tokengt.py:69-71)
         self.eig_threads = 8
+        self.eig_backend = "host"        # "device": batched cuSOLVER eigh (fast mode, see TeatPlan.build_graph)
         self.compute_consistency = True  # phase='train' fills structure_temp_loss / semantic_temp_loss (R1-R3)
         self.last_plan = None
 
@@ -336,7 +356,7 @@ class TEAT_GT(nn.Module):
         sp, tp = ops.teat_pair_flags(tok.detach(), entry["boxes"].contiguous(), plan.feat_row, plan.node_off,
                                      plan.has_prev, thr, SIM_THR, plan.nmax)
         sp_h = sp.cpu().numpy()
-        plan.build_graph(sp_h, tp.cpu().numpy(), self.lap_k, self.eig_threads)
+        plan.build_graph(sp_h, tp.cpu().numpy(), self.lap_k, self.eig_threads, self.eig_backend)
         desc = ops.upload(plan.desc_h, dev)
         ev = ops.upload(plan.eigvec_h, dev)
         evb = ops.cast_bf16(ev, drop_p=self.eig_dropout if train else 0.0, seed=seed0 + 17)

@@ -16,12 +16,14 @@ ap.add_argument("--frames", type=int, default=32)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--infer", action="store_true")
+ap.add_argument("--eig", default="host", choices=["host", "device"])
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 m = teatgt.TEAT_GT(mode="predcls", attention_class_num=3, spatial_class_num=6, contact_class_num=17,
                    obj_classes=synthetic.ag_object_classes(), tracking=False, args=types.SimpleNamespace(**ARGS))
 synthetic.teatgt_seeded_init_(m, 1123)
 m = m.to(dev)
+m.eig_backend = a.eig
 for p in m.object_classifier.parameters():
     p.requires_grad_(False)
 entries = []
@@ -62,6 +64,6 @@ torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / a.steps
 plan = m.last_plan
 print(json.dumps({"workload": "TEAT-GT PredCLS %s, %d videos x %d frames" % ("inference" if a.infer else "fwd+bwd", a.videos, a.frames),
-                  "pairs_per_s": N / dt, "ms_per_step": dt * 1e3, "pairs": N, "clips": plan.n_clips, "tokens": plan.T,
+                  "eig_backend": a.eig, "pairs_per_s": N / dt, "ms_per_step": dt * 1e3, "pairs": N, "clips": plan.n_clips, "tokens": plan.T,
                   "max_tokens_per_clip": plan.max_T, "launches_per_step": (ops.launch_count - l0) // a.steps,
                   "loss": float(loss)}))
