@@ -1,0 +1,245 @@
+// Pieces shared by the 1-CTA and the 2-CTA (cta_group::2) tcgen05 GEMM kernels: epilogue parameter block,
+// the fused chunk epilogue (TMEM -> swizzled smem transpose -> row-contiguous global access), and the TMA
+// tensor-map helpers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/b200vsgg.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vsgg {
+
+struct GemmEpi {
+    const float* bias;
+    const void* residual;
+    int residual_is_bf16;
+    int ldr;
+    const __nv_bfloat16* mask_src;
+    int ldm;
+    int mask_mode;
+    int act;
+    float* out_f32;
+    int ld_f32;
+    __nv_bfloat16* out_bf16;
+    int ld_bf16;
+    int accumulate;
+    float alpha;
+    float dropout_p;
+    unsigned long long dropout_seed;
+    int vec_ok;  // all epilogue pointers / leading dimensions allow 16-byte vector access
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+    static constexpr int ACC_STAGES = 2;
+    static constexpr int TMEM_COLS = (ACC_STAGES * BN <= 32) ? 32 : ((ACC_STAGES * BN <= 64) ? 64 : ((ACC_STAGES * BN <= 128) ? 128 : ((ACC_STAGES * BN <= 256) ? 256 : 512)));
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int EPI_BYTES = 8 * 4096;  // one swizzled 32x32 fp32 transpose buffer per epilogue warp
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024 /*align slack*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// Epilogue state hoisted into registers once per kernel.
+struct EpiRegs {
+    float* stg;                       // this warp's swizzled 32x32 fp32 transpose buffer
+    const float* res_f32;
+    const __nv_bfloat16* res_b16;
+    const __nv_bfloat16* mask_src;
+    const float* bias;
+    float* out_f32;
+    __nv_bfloat16* out_bf16;
+    unsigned long long drop_seed;
+    float alpha, inv_keep;
+    uint32_t drop_thr;
+    int act, mask_mode, accumulate, ld_f32, ld_bf16, ldr, ldm, N, lane;
+    bool atomic, use_bias;
+};
+
+// One 32-row x 32-column chunk of the accumulator: TMEM -> registers (lane = row) -> swizzled shared
+// memory -> registers (lane = column, 32 rows) -> fused epilogue -> row-contiguous global stores.
+// FULL = all 32 rows exist (every m-tile but the last): no row guards, so each row costs ~6 instructions.
+// Loads are clamped in-bounds instead of predicated; stores sit under one lane predicate (col < N).
+template <bool FULL>
+__device__ __forceinline__ void epi_chunk(const EpiRegs& E, uint32_t taddr, int rbase, int rows_here, int nc,
+                                          uint64_t* full_bar, uint32_t full_phase, bool& waited) {
+    const int lane = E.lane;
+    const int col = nc + lane;
+    const bool col_ok = col < E.N;
+    const int colc = col_ok ? col : E.N - 1;
+    const int last = rows_here - 1;
+    // aux = the chunk's residual values, or (when there is no residual) its mask values, prefetched
+    // before the accumulator is touched.  With BOTH present the mask is read inline later (rare).
+    float aux[32];
+    const bool has_res = E.res_f32 != nullptr || E.res_b16 != nullptr;
+    const bool has_mask = E.mask_src != nullptr;
+    const __nv_bfloat16* mp = has_mask ? E.mask_src + static_cast<size_t>(rbase) * E.ldm + colc : nullptr;
+    if (E.res_f32 != nullptr) {
+        const float* rp = E.res_f32 + static_cast<size_t>(rbase) * E.ldr + colc;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) aux[i] = __ldg(rp + (FULL ? i : min(i, last)) * E.ldr);
+    } else if (E.res_b16 != nullptr) {
+        const __nv_bfloat16* rp = E.res_b16 + static_cast<size_t>(rbase) * E.ldr + colc;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) aux[i] = __bfloat162float(rp[(FULL ? i : min(i, last)) * E.ldr]);
+    } else if (has_mask) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) aux[i] = __bfloat162float(mp[(FULL ? i : min(i, last)) * E.ldm]);
+    }
+    if (!waited) {
+        ptx::mbar_wait(full_bar, full_phase);
+        ptx::tc_fence_after();
+        waited = true;
+    }
+    uint32_t r[32];
+    ptx::tmem_ld_32x32b_x32(taddr, r);
+    ptx::tmem_ld_wait();
+    float* stg = E.stg;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 v4 = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                __uint_as_float(r[4 * j + 3]));
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = v4;
+    }
+    __syncwarp();
+    const float bias_v = E.use_bias ? __ldg(E.bias + colc) : 0.f;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(stg[i * 32 + (((lane >> 2) ^ (i & 7)) << 2) + (lane & 3)], E.alpha, bias_v);
+    __syncwarp();   // the buffer may be overwritten by the next chunk from here on
+    if (E.atomic) {
+        if (col_ok) {
+            float* op = E.out_f32 + static_cast<size_t>(rbase) * E.ld_f32 + col;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (FULL || i < rows_here) atomicAdd(op + i * E.ld_f32, v[i]);
+        }
+        return;
+    }
+    if (E.act == 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else if (E.act == 2) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    }
+    if (has_mask) {
+        if (!has_res) {
+            if (E.mask_mode == 1) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = aux[i] > 0.f ? v[i] : 0.f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad(aux[i]);
+            }
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+                const float m = __bfloat162float(mp[(FULL ? i : min(i, last)) * E.ldm]);
+                v[i] = E.mask_mode == 1 ? (m > 0.f ? v[i] : 0.f) : v[i] * gelu_erf_grad(m);
+            }
+        }
+    }
+    if (E.drop_thr != 0u) {
+        const unsigned long long base_idx = static_cast<unsigned long long>(rbase) * E.N + col;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const uint32_t h = hash_u32(E.drop_seed, base_idx + static_cast<unsigned long long>(i) * E.N);
+            v[i] = (h >= E.drop_thr) ? v[i] * E.inv_keep : 0.f;
+        }
+    }
+    if (has_res) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += aux[i];
+    }
+    if (!col_ok) return;
+    if (E.out_f32 != nullptr) {
+        float* op = E.out_f32 + static_cast<size_t>(rbase) * E.ld_f32 + col;
+        if (E.accumulate) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (FULL || i < rows_here) v[i] += op[i * E.ld_f32];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (FULL || i < rows_here) op[i * E.ld_f32] = v[i];
+    }
+    if (E.out_bf16 != nullptr) {
+        __nv_bfloat16* op = E.out_bf16 + static_cast<size_t>(rbase) * E.ld_bf16 + col;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (FULL || i < rows_here) op[i * E.ld_bf16] = __float2bfloat16(v[i]);
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2D bf16 tensor map: `inner` contiguous elements, `outer` rows with pitch ld (elements); box = box_inner x box_outer.
+static inline int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                          uint32_t box_inner, uint32_t box_outer) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (enc == nullptr) return set_error(B200VSGG_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || ((ld * 2) & 15u) != 0)
+        return set_error(B200VSGG_ERR_BAD_ARG, "gemm operand must be 16-byte aligned with ld % 8 == 0");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu ld=%llu", (int)r,
+                 (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+        return set_error(B200VSGG_ERR_TMAP, msg);
+    }
+    return 0;
+}
+
+static inline int num_sms() {
+    static int g_num_sms = 0;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+}  // namespace vsgg

@@ -96,3 +96,28 @@ def test_gemm_dropout_determinism(cuda_lib):
     assert 0.08 < frac < 0.12, frac
     kept = ~dropped
     assert torch.allclose(o1[kept], o0[kept] / 0.9, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(31799, 1936, 1936), (16419, 5808, 1936), (20000, 2048, 600)])
+def test_gemm_two_cta_path(cuda_lib, M, N, K, a_mn, b_mn):
+    """Shapes large enough for the cta_group::2 kernel (256x256 tiles on CTA pairs), ragged in M and N, with
+    the fused epilogue (bias + fp32 residual + dual fp32/bf16 stores) — against torch fp32 matmul of the same
+    bf16 operands."""
+    from b200vsgg import ops
+    if a_mn:
+        M = (M + 7) // 8 * 8          # an MN-major operand's leading dimension must be a multiple of 8 (TMA)
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn((K, M) if a_mn else (M, K), generator=g, device="cuda").bfloat16()
+    b = torch.randn((K, N) if b_mn else (N, K), generator=g, device="cuda").bfloat16()
+    bias = torch.randn(N, generator=g, device="cuda")
+    res = torch.randn(M, N, generator=g, device="cuda")
+    o32 = torch.empty(M, N, device="cuda")
+    o16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, bias=bias, residual=res, out_f32=o32, out_bf16=o16)
+    af = a.float().t() if a_mn else a.float()
+    bf = b.float() if b_mn else b.float().t()
+    ref = af @ bf + bias[None, :] + res
+    tol = 2e-3 * ref.abs().max().item()
+    assert (o32 - ref).abs().max().item() <= tol
+    assert (o16.float() - ref).abs().max().item() <= tol + 2 ** -7 * ref.abs().max().item()
