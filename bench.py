@@ -231,7 +231,7 @@ def main():
     vids = [rank * args.videos + v for v in range(args.videos)]
     batch = build_batch(vids, args.frames, dev)
     n_pairs = int(batch["pair_idx"].shape[0])
-    sync = ddp.GradSync(list(model.parameters())[::-1]) if world > 1 else None
+    sync = ddp.GradSync(list(model.parameters())[::-1]).attach(model) if world > 1 else None
     # TEMPURA_train.py:111,224-225: AdamW(lr, weight_decay=0.1) after clip_grad_norm_(5) — fused, 2 launches
     from b200vsgg.optim import FusedAdamW
     opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-5, betas=(0.9, 0.999), eps=1e-8,

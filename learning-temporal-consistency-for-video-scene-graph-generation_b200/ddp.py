@@ -39,6 +39,34 @@ class GradSync:
         self.stream = torch.cuda.Stream(device=dev) if self.cuda else None
         self._flat = {}
 
+    # ------------------------------------------------------------------ overlap with backward
+    def attach(self, model):
+        """Let `model` (b200vsgg TEMPURA) hand over gradient tensors the moment its hand-written backward has
+        finished them: they are all-reduced (AVG) asynchronously on NCCL's stream while the remaining backward
+        kernels run.  `sync()` later waits for these and reduces whatever is left (heads, small tensors)."""
+        self._early_works, self._early_ptrs = [], set()
+        if self.world > 1:
+            model._grad_ready_hook = self._on_ready
+            model._grad_flush_hook = self._flush
+        return self
+
+    def _flush(self):
+        """Order the compute stream after every early all-reduce (called at the end of the model's backward,
+        before autograd copies or accumulates the returned tensors)."""
+        for work, _ in self._early_works:
+            work.wait()
+
+    def _on_ready(self, tensors):
+        for t in tensors:
+            if t is None or t.numel() * t.element_size() < (256 << 10):
+                continue                                  # small ones ride in the flat buckets of sync()
+            base = t._base if t._base is not None else t
+            ptr = base.data_ptr()
+            if ptr in self._early_ptrs or not base.is_contiguous():
+                continue
+            self._early_ptrs.add(ptr)
+            self._early_works.append((dist.all_reduce(base, op=dist.ReduceOp.AVG, group=self.group, async_op=True), base))
+
     def _buckets(self, with_grad):
         cur, size, out = [], 0, []
         for p in with_grad:
@@ -56,7 +84,20 @@ class GradSync:
         """Average `.grad` of every parameter that has one over all ranks (in place)."""
         if self.world == 1:
             return
-        with_grad = [p for p in self.params if p.grad is not None]
+        early = getattr(self, "_early_works", [])
+        early_ptrs = getattr(self, "_early_ptrs", set())
+        for work, _ in early:
+            work.wait()                                   # stream-level wait: the host does not block
+        with_grad = []
+        for p in self.params:
+            if p.grad is None:
+                continue
+            g = p.grad
+            base = g._base if g._base is not None else g
+            if base.data_ptr() in early_ptrs:
+                continue                                  # already averaged during backward
+            with_grad.append(p)
+        self._early_works, self._early_ptrs = [], set()
         buckets = self._buckets(with_grad)
         if self.cuda:
             self.stream.wait_stream(torch.cuda.current_stream())

@@ -773,6 +773,11 @@ class _PathRunner:
         new = lambda r, c, dt: torch.empty(r, c, device=dev, dtype=dt)
         zeros = lambda *s: torch.zeros(*s, device=dev, dtype=f32)
         G = {}  # grads by the names of _unpack
+        hook = getattr(model, "_grad_ready_hook", None)   # ddp.GradSync: start all-reducing finished gradients
+
+        def ready(*tensors):
+            if hook is not None:
+                hook(tensors)
 
         def ffn_and_norm_bwd(dy32, R, L, i, rows, norm_g, norm_mean, norm_rstd, pre_norm, gkey, bkey, site):
             """Backward of  y = t + drop(W2 drop(relu(W1 t + b1)) + b2),  t = LN(pre_norm).
@@ -844,6 +849,7 @@ class _PathRunner:
             dx = new(M2, D_MODEL, f32)
             ops.gemm(dqkv, W["%din_w" % i], b_mn=True, residual=du, out_f32=dx)
             dy = dx
+            ready(gL["in_w"], gL["out_w"], gL["w1"], gL["w2"])
         # ---- T3 backward: each pair row was read by <= 2 windows
         dlocal = new(N, D_MODEL, f32)
         ops.gather2_sum_rows(dy, plan.pair_win2, out_f32=dlocal)
@@ -864,6 +870,7 @@ class _PathRunner:
             dx = new(N, D_MODEL, f32)
             ops.gemm(dqkv, W["%din_w" % i], b_mn=True, residual=du, out_f32=dx)
             dy = dx
+            ready(G[i]["in_w"], G[i]["out_w"], G[i]["w1"], G[i]["w2"])
         dtok = dy
         # ---- P6/P1 backward
         O = S["featb"].shape[0]
@@ -876,6 +883,7 @@ class _PathRunner:
         bso = zeros(1, 1024)
         ops.colsum(dsob, bso)
         G["subj_w"], G["obj_w"], G["subj_b"], G["obj_b"] = gso[:512], gso[512:], bso[0, :512], bso[0, 512:]
+        ready(gso)
         # ---- P5 backward
         dvr = ops.cast_bf16(dtok[:, 1024:1536])
         gvr = new(512, 12544, f32)
@@ -907,6 +915,9 @@ class _PathRunner:
                     g["g3"], g["be3"]]
         out = [g if need else None for g, need in zip(out, need_params)]
         self.saved = {}
+        flush = getattr(model, "_grad_flush_hook", None)
+        if flush is not None:
+            flush()
         return out
 
 

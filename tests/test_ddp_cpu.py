@@ -53,3 +53,35 @@ def test_grad_sync_gloo_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def _worker_early(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200vsgg.ddp import GradSync
+
+    class Dummy:
+        pass
+
+    model = Dummy()
+    big = torch.nn.Parameter(torch.zeros(400, 400))          # >= 256 kB: reduced early through the hook
+    small = torch.nn.Parameter(torch.zeros(10))
+    sync = GradSync([big, small], bucket_bytes=4096).attach(model)
+    gbig = torch.full((400, 400), float(rank + 1))
+    model._grad_ready_hook((gbig, None, torch.ones(3)))       # as the model's backward does
+    model._grad_flush_hook()
+    big.grad = gbig                                           # autograd keeps the (already averaged) buffer
+    small.grad = torch.full((10,), float(rank + 1))
+    sync.sync()
+    out[rank] = bool(torch.allclose(big.grad, torch.full((400, 400), 1.5)) and
+                     torch.allclose(small.grad, torch.full((10,), 1.5)))
+    dist.destroy_process_group()
+
+
+def test_grad_sync_early_hook_gloo_world2():
+    """Gradients handed over during backward are averaged once (not again in sync()), the rest in sync()."""
+    world = 2
+    port = _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_worker_early, args=(world, port, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))
