@@ -227,98 +227,97 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, int ld_x, cons
 }
 
 // LayerNorm backward.  dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)).
-// dgamma/dbeta: per-lane column partials over the rows a warp visits, reduced across the CTA's
-// warps in shared memory, then one atomicAdd per column per CTA (grid is ~2 CTAs/SM).
 // Optional: dx_bf16 = bf16(dropout(dx)) for the next backward GEMM (dropout of the branch that fed
 // the residual sum); dx_f32 is the undropped gradient of the skip path.
-template <int LN_MAX_VEC>
-__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, int ld_dy, const float* __restrict__ x, int ld_x,
-                                     const float* __restrict__ gamma, const float* __restrict__ mean,
-                                     const float* __restrict__ rstd, int rows, int cols, float* __restrict__ dx_f32,
-                                     int ld_dx, __nv_bfloat16* __restrict__ dx_bf16, int ld_b, float drop_p,
-                                     unsigned long long drop_seed, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta, const float* __restrict__ base, int ld_base) {
-    extern __shared__ float red[];  // [warps][cols] x 2: per-warp dgamma / dbeta partials
-    const int warps_per_block = blockDim.x >> 5;
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward, v2: the row gradient (two light passes per row, second pass re-reads the row from
+// L1/L2 instead of holding it in ~130 registers: 8x the resident warps of the register-blocked version)
+// and the parameter gradients (column sums, seg_colstats-style) are separate kernels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(
+    const float* __restrict__ dy, int ld_dy, const float* __restrict__ x, int ld_x, const float* __restrict__ gamma,
+    const float* __restrict__ mean, const float* __restrict__ rstd, int rows, int cols, float* __restrict__ dx_f32,
+    int ld_dx, __nv_bfloat16* __restrict__ dx_bf16, int ld_b, float drop_p, unsigned long long drop_seed,
+    const float* __restrict__ base, int ld_base) {
+    const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
     const int nvec = cols >> 2;
-    float4* ag = reinterpret_cast<float4*>(red + static_cast<size_t>(warp) * cols);
-    float4* ab = reinterpret_cast<float4*>(red + static_cast<size_t>(warps_per_block + warp) * cols);
-    if (dgamma != nullptr) {
-        for (int c = lane; c < nvec; c += 32) {
-            ag[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-            ab[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
     const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
-    for (int r = blockIdx.x * warps_per_block + warp; r < rows; r += gridDim.x * warps_per_block) {
+    const float4* gp = reinterpret_cast<const float4*>(gamma);
+    for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
         const float4* dyp = reinterpret_cast<const float4*>(dy + static_cast<size_t>(r) * ld_dy);
         const float4* xp = reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * ld_x);
         const float mu = mean[r], rs = rstd[r];
-        float4 gdy[LN_MAX_VEC], xh[LN_MAX_VEC];
         float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < LN_MAX_VEC; ++i) {
-            const int c = lane + i * 32;
-            if (c < nvec) {
-                const float4 d = dyp[c];
-                const float4 xv = xp[c];
-                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-                xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-                gdy[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-                s1 += (gdy[i].x + gdy[i].y) + (gdy[i].z + gdy[i].w);
-                s2 += (gdy[i].x * xh[i].x + gdy[i].y * xh[i].y) + (gdy[i].z * xh[i].z + gdy[i].w * xh[i].w);
-                if (dgamma != nullptr) {
-                    float4 g0 = ag[c], b0 = ab[c];
-                    g0.x += d.x * xh[i].x; g0.y += d.y * xh[i].y; g0.z += d.z * xh[i].z; g0.w += d.w * xh[i].w;
-                    b0.x += d.x; b0.y += d.y; b0.z += d.z; b0.w += d.w;
-                    ag[c] = g0; ab[c] = b0;
-                }
-            }
+        for (int c = lane; c < nvec; c += 32) {
+            const float4 d = dyp[c], xv = xp[c], g = __ldg(gp + c);
+            const float g0 = d.x * g.x, g1 = d.y * g.y, g2 = d.z * g.z, g3 = d.w * g.w;
+            s1 += (g0 + g1) + (g2 + g3);
+            s2 += (g0 * (xv.x - mu) + g1 * (xv.y - mu)) + (g2 * (xv.z - mu) + g3 * (xv.w - mu));
         }
-        const float m1 = warp_sum(s1) / cols, m2 = warp_sum(s2) / cols;
+        const float m1 = warp_sum(s1) / cols, m2 = warp_sum(s2) * rs / cols;
+        for (int c = lane; c < nvec; c += 32) {
+            const float4 d = dyp[c], xv = xp[c], g = __ldg(gp + c);
+            float4 o;
+            o.x = rs * (d.x * g.x - m1 - (xv.x - mu) * rs * m2);
+            o.y = rs * (d.y * g.y - m1 - (xv.y - mu) * rs * m2);
+            o.z = rs * (d.z * g.z - m1 - (xv.z - mu) * rs * m2);
+            o.w = rs * (d.w * g.w - m1 - (xv.w - mu) * rs * m2);
+            if (base != nullptr) {
+                const float4 bs = reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * ld_base)[c];
+                o.x += bs.x; o.y += bs.y; o.z += bs.z; o.w += bs.w;
+            }
+            if (dx_f32) reinterpret_cast<float4*>(dx_f32 + static_cast<size_t>(r) * ld_dx)[c] = o;
+            if (dx_bf16) {
+                float a[4] = {o.x, o.y, o.z, o.w};
+                if (thr) {
 #pragma unroll
-        for (int i = 0; i < LN_MAX_VEC; ++i) {
-            const int c = lane + i * 32;
-            if (c < nvec) {
-                float4 o;
-                o.x = rs * (gdy[i].x - m1 - xh[i].x * m2);
-                o.y = rs * (gdy[i].y - m1 - xh[i].y * m2);
-                o.z = rs * (gdy[i].z - m1 - xh[i].z * m2);
-                o.w = rs * (gdy[i].w - m1 - xh[i].w * m2);
-                if (base != nullptr) {   // pre-LN residual: dx = d(skip path) + d(through the norm)
-                    const float4 bs = reinterpret_cast<const float4*>(base + static_cast<size_t>(r) * ld_base)[c];
-                    o.x += bs.x; o.y += bs.y; o.z += bs.z; o.w += bs.w;
-                }
-                if (dx_f32) reinterpret_cast<float4*>(dx_f32 + static_cast<size_t>(r) * ld_dx)[c] = o;
-                if (dx_bf16) {
-                    float a[4] = {o.x, o.y, o.z, o.w};
-                    if (thr) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t h = hash_u32(drop_seed, static_cast<size_t>(r) * cols + c * 4 + j);
-                            a[j] = h >= thr ? a[j] * inv_keep : 0.f;
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t h = hash_u32(drop_seed, static_cast<size_t>(r) * cols + c * 4 + j);
+                        a[j] = h >= thr ? a[j] * inv_keep : 0.f;
                     }
-                    store_bf16x4(dx_bf16 + static_cast<size_t>(r) * ld_b + c * 4, a);
                 }
+                store_bf16x4(dx_bf16 + static_cast<size_t>(r) * ld_b + c * 4, a);
             }
         }
     }
-    if (dgamma == nullptr) return;
-    float* rg = red;
-    float* rb = red + static_cast<size_t>(warps_per_block) * cols;
-    __syncthreads();
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-        float sg = 0.f, sb = 0.f;
-        for (int w = 0; w < warps_per_block; ++w) {
-            sg += rg[static_cast<size_t>(w) * cols + c];
-            sb += rb[static_cast<size_t>(w) * cols + c];
+}
+
+// dgamma[c] += sum_r dy[r,c] * (x[r,c] - mean[r]) * rstd[r];  dbeta[c] += sum_r dy[r,c].
+// block = (32 float4 column vectors, 8 row phases); grid = (ceil(cols/128), row chunks of 256).
+__global__ void __launch_bounds__(256) layernorm_bwd_param_kernel(const float* __restrict__ dy, int ld_dy,
+                                                                  const float* __restrict__ x, int ld_x,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd, int rows, int cols,
+                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = (blockIdx.x * 32 + tx) * 4;
+    const int r0 = blockIdx.y * 256, r1 = min(rows, r0 + 256);
+    float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sb = sg;
+    if (col < cols) {
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += 8) {
+            const float4 d = *reinterpret_cast<const float4*>(dy + static_cast<size_t>(r) * ld_dy + col);
+            const float4 xv = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * ld_x + col);
+            const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+            sg.x += d.x * (xv.x - mu) * rs; sg.y += d.y * (xv.y - mu) * rs;
+            sg.z += d.z * (xv.z - mu) * rs; sg.w += d.w * (xv.w - mu) * rs;
+            sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
         }
-        atomicAdd(dgamma + c, sg);
-        atomicAdd(dbeta + c, sb);
+    }
+    __shared__ float4 red[2][8][32];
+    red[0][ty][tx] = sg;
+    red[1][ty][tx] = sb;
+    __syncthreads();
+    if (ty < 2 && col < cols) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+            const float4 v = red[ty][y][tx];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        float* dst = (ty == 0 ? dgamma : dbeta) + col;
+        atomicAdd(dst, s.x); atomicAdd(dst + 1, s.y); atomicAdd(dst + 2, s.z); atomicAdd(dst + 3, s.w);
     }
 }
 
@@ -465,21 +464,22 @@ extern "C" int b200vsgg_layernorm_bwd_add(const float* dy, int32_t ld_dy, const 
                                       const float* mean, const float* rstd, int32_t rows, int32_t cols, float* dx_f32,
                                       int32_t ld_dx, void* dx_bf16, int32_t ld_b, float drop_p, uint64_t drop_seed,
                                       float* dgamma, float* dbeta, void* stream, const float* base, int32_t ld_base) {
-    if (!dy || !x || !gamma || !mean || !rstd || cols <= 0 || (cols & 7) || cols > 2048)
+    if (!dy || !x || !gamma || !mean || !rstd || cols <= 0 || (cols & 7) || (dgamma == nullptr) != (dbeta == nullptr) ||
+        (rows + 255) / 256 > 65535)
         return set_error(B200VSGG_ERR_BAD_ARG, "layernorm_bwd: bad arg");
     if (rows == 0) return 0;
-    const int threads = 128;
-    const size_t smem = static_cast<size_t>(threads / 32) * cols * 2 * sizeof(float);
-    auto kern = cols <= 1024 ? layernorm_bwd_kernel<8> : layernorm_bwd_kernel<16>;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * 2 * 4);
-        cudaFuncSetAttribute(layernorm_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 2048 * 2 * 4);
-        attr = true;
+    {
+        int grid = (rows + 7) / 8;
+        if (grid > 148 * 8) grid = 148 * 8;
+        layernorm_bwd_dx_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, ld_dy, x, ld_x, gamma, mean, rstd, rows, cols,
+                                                                      dx_f32, ld_dx, (__nv_bfloat16*)dx_bf16, ld_b, drop_p,
+                                                                      drop_seed, base, ld_base);
+        if (dgamma != nullptr && dbeta != nullptr) {
+            dim3 pgrid((cols + 127) / 128, (rows + 255) / 256);
+            layernorm_bwd_param_kernel<<<pgrid, 256, 0, (cudaStream_t)stream>>>(dy, ld_dy, x, ld_x, mean, rstd, rows, cols,
+                                                                              dgamma, dbeta);
+        }
     }
-    kern<<<grid_for(rows, 4, 148 * 3), threads, smem, (cudaStream_t)stream>>>(
-        dy, ld_dy, x, ld_x, gamma, mean, rstd, rows, cols, dx_f32, ld_dx, (__nv_bfloat16*)dx_bf16, ld_b, drop_p,
-        drop_seed, dgamma, dbeta, base, ld_base);
     VSGG_CUDA_CHECK_LAUNCH();
     return 0;
 }
