@@ -105,6 +105,19 @@ def make_video_entry(video_index=0, num_frames=32, pairs_per_frame=(6, 10), devi
     return entry
 
 
+def add_sgcls_inputs(entry, video_index=0, sharpness=3.0):
+    """SGCls detector hand-off on top of a PredCLS entry (tools/utils/object_detector.py:415-430 of the
+    reference): `distribution` [O,36] = the detector's posterior over the 36 non-background classes, peaked at
+    the ground-truth class (logit + `sharpness`) so that the arg-max class sequences of
+    tools/utils/ds_track.py:18-39 look like object tracks with a realistic share of misdetections."""
+    g = torch.Generator().manual_seed(BASE_SEED * 7 + int(video_index))
+    labels = entry["labels"].cpu()
+    logits = torch.randn(labels.shape[0], AG_NUM_OBJ_CLASSES - 1, generator=g)
+    logits[torch.arange(labels.shape[0]), labels - 1] += sharpness
+    entry["distribution"] = torch.softmax(logits, 1).to(entry["labels"].device)
+    return entry
+
+
 def seeded_init_(module, seed=BASE_SEED):
     """Deterministic, construction-order-independent parameter fill: every tensor of the state_dict
     is drawn from a generator keyed by (seed, crc32(name)).  Applied to the reference modules when

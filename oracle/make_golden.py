@@ -50,7 +50,8 @@ def import_reference_tempura():
               "tools.utils.draw_rectangles"):
         stub(n)
     stub("tools.fasterRCNN.lib.model.roi_layers", ROIAlign=_InertROIAlign, nms=None)
-    stub("tools.utils.fpn.box_utils", center_size=None)
+    from oracle.tempura_oracle import center_size   # absent from the reference tree: injected (3 lines, unpinned)
+    stub("tools.utils.fpn.box_utils", center_size=center_size)
     stub("tools.utils.draw_rectangles.draw_rectangles", draw_union_boxes=None)
 
     import tools.utils.word_vectors as wv

@@ -14,6 +14,9 @@ What is restated, with the reference lines each piece follows (paths relative to
   GMMHeadOracle      tools/utils/gmm_heads.py:3-76
   STTranOracle       tools/utils/transformer.py:5-58 (layers), :104-253 (windows, scatter-back, memory)
   TempuraOracle      lib/tempura.py:465-510 (layer definitions), :537-596 (forward)
+  ObjectClassifierOracle  lib/tempura.py:51-255 (SGCls-train object branch: feature build, class-sequence
+                     encoder, intermediate + head), get_sequence = tools/utils/ds_track.py:18-39; pinned by
+                     oracle/make_golden_sgcls.py the same way (tests/golden/sgcls_*.pt)
   tempura_losses     TEMPURA_train.py:181-206
 The state_dict key names equal the reference's so checkpoints interchange (strict=True).
 
@@ -257,24 +260,155 @@ class GMMHeadOracle(nn.Module):
 # --------------------------------------------------------------------------------------------
 # the PredCLS model
 # --------------------------------------------------------------------------------------------
-class ObjectClassifierShell(nn.Module):
-    """Holds ObjectClassifier's parameters for state_dict compatibility (lib/tempura.py:73-114).
-    PredCLS forward is `pred_labels = labels` (lib/tempura.py:245-247); nothing else is restated."""
+def center_size(boxes):
+    """(x1,y1,x2,y2) -> (cx,cy,w,h).  tools/utils/fpn/box_utils.py is ABSENT from the reference tree
+    (imported at lib/tempura.py:18); this is the neural-motifs definition that file is copied from
+    upstream.  UNPINNED for these three lines: the golden generator injects the same function."""
+    wh = boxes[:, 2:] - boxes[:, :2] + 1.0
+    return torch.cat((boxes[:, :2] + 0.5 * wh, wh), 1)
 
-    def __init__(self, num_classes, obj_head="gmm", K=4, mem_compute=None, selection=None):
+
+def sinusoid_table(d_model, max_len):
+    """PositionalEncoding.pe (lib/tempura.py:31-36)."""
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(1, max_len, d_model)
+    pe[0, :, 0::2] = torch.sin(position * div_term)
+    pe[0, :, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def get_sequence(entry, task="sgcls"):
+    """tools/utils/ds_track.py:18-39: boxes grouped by the detector's arg-max class; entry['indices'][0] =
+    all single-box groups concatenated, entry['indices'][1:] = the longer groups in class order."""
+    if task == "predcls":
+        return
+    indices = [[]]
+    pred = torch.argmax(entry["distribution"], 1)
+    for c in pred.unique():
+        index = torch.where(pred == c)[0]
+        (indices[0] if len(index) == 1 else indices).append(index)
+    indices[0] = torch.cat(indices[0]) if len(indices[0]) > 0 else torch.tensor([])
+    entry["indices"] = indices
+
+
+class _PE(nn.Module):
+    def __init__(self, d_model, max_len):
         super().__init__()
+        self.register_buffer("pe", sinusoid_table(d_model, max_len))
+
+
+class ObjectClassifierOracle(nn.Module):
+    """ObjectClassifier (lib/tempura.py:51-255; TEAT-GT's copy tools/utils/object_classifier.py:43-233 is
+    line-for-line the same arithmetic).  Restated: PredCLS (:245-247), the SGCls feature build (:249-252),
+    `classify` (:185-241) with and without the class-sequence encoder (`tracking`), for phase='train' and for
+    the classification part of phase='test' (the relabel / NMS / ROIAlign tail :257-307 needs the reference's
+    absent CUDA ops and is out of scope)."""
+
+    def __init__(self, num_classes, mode="predcls", obj_head="gmm", K=4, mem_compute=None, selection=None,
+                 selection_lambda=0.5, tracking=None, dropout=0.1):
+        super().__init__()
+        self.mode, self.obj_head, self.tracking, self.mem_compute, self.selection = (
+            mode, obj_head, tracking, mem_compute, selection)
+        self.obj_memory, self.p = [], dropout
         self.obj_embed = nn.Embedding(num_classes - 1, 200)
         self.pos_embed = nn.Sequential(nn.BatchNorm1d(4, momentum=0.001), nn.Linear(4, 128), nn.ReLU(inplace=True),
-                                       nn.Dropout(0.1))
+                                       nn.Dropout(dropout))
+        d_model = 2048 + 200 + 128
+        mem_embed = 1024
+        if tracking:
+            self.positional_encoder = _PE(d_model, 600 if mode == "sgdet" else 400)
+            self.encoder_tran = LayerStack(lambda: SpatialLayer(d_model, 8, 1024, dropout), 3)
+            mem_embed = d_model
         if mem_compute:
-            self.mem_attention = PackedMHA(1024, 1, bias=False)
-            if selection != "manual":
+            self.mem_attention = PackedMHA(mem_embed, 1, bias=False)
+            if selection == "manual":
+                self.selector = selection_lambda
+            else:
                 self.selector = nn.Linear(1024, 1)
-        self.intermediate = nn.Sequential(nn.Linear(2048 + 200 + 128, 1024), nn.BatchNorm1d(1024), nn.ReLU())
+        self.intermediate = nn.Sequential(nn.Linear(d_model, 1024), nn.BatchNorm1d(1024), nn.ReLU())
         if obj_head == "gmm":
             self.decoder_lin = GMMHeadOracle(1024, num_classes, None, K)
         else:
             self.decoder_lin = nn.Sequential(nn.Linear(1024, num_classes))
+
+    def hallucinate(self, feat):
+        """lib/tempura.py:165-182."""
+        if len(self.obj_memory) == 0:
+            return feat
+        e = self.selector if self.selection == "manual" else self.selector(feat).sigmoid()
+        mem = self.mem_attention.attend(feat[None], self.obj_memory[None], self.obj_memory[None])[0]
+        return e * feat + (1 - e) * mem if e is not None else feat + mem
+
+    def encode_sequences(self, entry, x):
+        """lib/tempura.py:186-210: every class sequence is one padded batch row; position = rank of the box's
+        frame among the sequence's frames; single-box sequences run as length-1 batch rows at position 0."""
+        indices = entry["indices"]
+        pe = self.positional_encoder.pe[0]
+        final = torch.zeros_like(x)
+        seqs = [ix.long() for ix in indices[1:]]
+        if seqs:
+            L = max(len(ix) for ix in seqs)
+            S = len(seqs)
+            pad = torch.zeros(S, L, x.shape[1], dtype=x.dtype)
+            pos = torch.zeros(S, L, dtype=torch.int64)
+            mask = torch.ones(S, L, dtype=torch.bool)
+            for s, ix in enumerate(seqs):
+                _, counts = torch.unique(entry["boxes"][ix][:, 0].view(-1), return_counts=True, sorted=True)
+                pos[s, :len(ix)] = torch.repeat_interleave(torch.arange(len(counts)), counts)
+                pad[s, :len(ix)] = x[ix]
+                mask[s, :len(ix)] = False
+            h = F.dropout(pad + pe[pos], self.p, self.training)
+            for layer in self.encoder_tran.layers:
+                h = layer(h, mask)
+            final[torch.cat(seqs)] = torch.cat([h[s, :len(ix)] for s, ix in enumerate(seqs)])
+        if len(indices[0]) > 0:
+            ix = indices[0].long()
+            h = F.dropout(x[ix].unsqueeze(1) + pe[None, :1], self.p, self.training)
+            for layer in self.encoder_tran.layers:
+                h = layer(h, None)
+            final[ix] = h[:, 0]
+        return final
+
+    def classify(self, entry, x, phase, unc, eps=None):
+        if self.tracking:
+            x = self.encode_sequences(entry, x)
+            entry["object_features"] = x
+            if self.mem_compute:
+                x = self.hallucinate(x)
+            entry["object_mem_features"] = x
+            x = self.intermediate(x)
+        else:
+            x = self.intermediate(x)
+            entry["object_features"] = x
+            if self.mem_compute:
+                x = self.hallucinate(x)
+            entry["object_mem_features"] = x
+        gmm = self.obj_head == "gmm"
+        if phase == "train":
+            if not gmm:
+                entry["distribution"] = self.decoder_lin(x)
+            elif not unc:
+                entry["distribution"] = self.decoder_lin(x, phase, False, eps)
+            else:
+                entry["distribution"] = self.decoder_lin(x, "test", False)
+                entry["obj_al_uc"], entry["obj_ep_uc"] = self.decoder_lin(x, unc=True)
+            entry["pred_labels"] = entry["labels"]
+        elif gmm:
+            entry["distribution"] = self.decoder_lin(x, phase, unc, eps)
+        else:
+            entry["distribution"] = torch.softmax(self.decoder_lin(x)[:, 1:], dim=1)
+        return entry
+
+    def forward(self, entry, phase="train", unc=False, eps=None):
+        if self.mode == "predcls":
+            entry["pred_labels"] = entry["labels"]
+            return entry
+        assert self.mode == "sgcls"
+        obj_embed = entry["distribution"] @ self.obj_embed.weight
+        pos_embed = self.pos_embed(center_size(entry["boxes"][:, 1:]))
+        x = torch.cat((entry["features"], obj_embed, pos_embed), 1)
+        return self.classify(entry, x, phase, unc, eps)
 
 
 class TempuraOracle(nn.Module):
@@ -283,12 +417,13 @@ class TempuraOracle(nn.Module):
                  rel_mem_compute=None, mem_fusion=None, selection=None, selection_lambda=0.5,
                  take_obj_mem_feat=False, obj_head="gmm", rel_head="gmm", K=6, tracking=None, dropout=0.1):
         super().__init__()
-        assert mode == "predcls" and not take_obj_mem_feat and not tracking and rel_head == "gmm"
+        assert mode in ("predcls", "sgcls") and not take_obj_mem_feat and rel_head == "gmm"
         self.mode, self.obj_classes, self.rel_memory = mode, obj_classes, []
         self.attention_class_num, self.spatial_class_num, self.contact_class_num = (
             attention_class_num, spatial_class_num, contact_class_num)
         ncls = len(obj_classes)
-        self.object_classifier = ObjectClassifierShell(ncls, obj_head, K, obj_mem_compute, selection)
+        self.object_classifier = ObjectClassifierOracle(ncls, mode, obj_head, K, obj_mem_compute, selection,
+                                                        selection_lambda, tracking, dropout)
         self.union_func1 = nn.Conv2d(1024, 256, kernel_size=1)
         self.conv = nn.Sequential(
             nn.Conv2d(2, 128, kernel_size=7, stride=2, padding=3), nn.ReLU(inplace=True),
@@ -318,14 +453,15 @@ class TempuraOracle(nn.Module):
         return torch.cat([s, o, vr, self.obj_embed(lab[pi[:, 0]]), self.obj_embed2(lab[pi[:, 1]])], 1)
 
     def forward(self, entry, phase="train", unc=False, eps=None):
-        entry["pred_labels"] = entry["labels"]
+        e = eps or {}
+        assert self.mode == "predcls" or phase == "train", "SGCls test-time relabel/NMS tail is not restated"
+        entry = self.object_classifier(entry, phase, unc, e.get("object"))
         tok = self.pair_tokens(entry)
         out, rel_feats, mem_feats = self.glocal_transformer(tok, entry["im_idx"], self.rel_memory)
         entry["obj_class"] = entry["pred_labels"][entry["pair_idx"][:, 1]]
         entry["rel_features"] = rel_feats
         entry["rel_mem_features"] = mem_feats
         entry["global_output"] = out  # oracle-only key, used by parity tests
-        e = eps or {}
         if not unc:
             entry["attention_distribution"] = self.a_rel_compress(out, phase, False, e.get("attention"))
             entry["spatial_distribution"] = self.s_rel_compress(out, phase, False, e.get("spatial"))
@@ -335,6 +471,16 @@ class TempuraOracle(nn.Module):
             entry["spatial_al_uc"], entry["spatial_ep_uc"] = self.s_rel_compress(out, phase, True)
             entry["contacting_al_uc"], entry["contacting_ep_uc"] = self.c_rel_compress(out, phase, True)
         return entry
+
+
+def object_loss(pred, eos_coef=1.0):
+    """TEMPURA_train.py:97-100,191-195 / TEATGT_train.py:163-165: class-weighted CrossEntropyLoss
+    (weight[0] = eos_coef, reduction='none') on `distribution` exactly as the model returns it (for the GMM
+    head that is already a probability mixture), then a plain mean over the boxes."""
+    dist = pred["distribution"]
+    w = torch.ones(dist.shape[1], device=dist.device)
+    w[0] = eos_coef
+    return F.cross_entropy(dist, pred["labels"], weight=w, reduction="none").mean()
 
 
 def tempura_losses(pred, attention_label, spatial_label, contact_label):
