@@ -109,7 +109,7 @@ int b200vsgg_pair_concat_bwd(const float* dtok, const int64_t* pair_idx, const i
                              float* dembed2 /* nullable */, void* stream);
 
 /* LayerNorm over the last dim (nn.LayerNorm, eps inside the sqrt), tools/utils/transformer.py:14-15,
- * 45 and tokengt_graph_encoder_layer.py:170-191.  cols % 8 == 0, cols <= 2048. */
+ * 45 and tokengt_graph_encoder_layer.py:170-191.  cols % 8 == 0, cols <= 2560. */
 int b200vsgg_layernorm_fwd(const float* x, int32_t ld_x, const float* gamma, const float* beta, int32_t rows,
                            int32_t cols, float eps, float* y_f32, int32_t ld_y, void* y_bf16, int32_t ld_b,
                            const float* add_table, const int32_t* add_idx, void* y_bf16_added, int32_t ld_added,
@@ -192,7 +192,8 @@ int b200vsgg_mask_im2col(const float* masks, int32_t n, void* out, int32_t ld, v
  * sums of squares of either type). */
 int b200vsgg_seg_colstats(const void* a, int32_t a_is_bf16, int32_t lda, const void* b, int32_t ldb, int32_t cols,
                           const int32_t* chunks, int32_t n_chunks, float* sum1, float* sum2, void* stream);
-/* out[r,c] = bf16(k1[g,c]*a[r,c] + k2[g,c]*b[r,c] + k3[g,c]), zero where relu_mask && b[r,c] <= 0;
+/* out[r,c] = bf16(k1[g,c]*a[r,c] + k2[g,c]*b[r,c] + k3[g,c]), zero where relu_mask == 1 && b[r,c] <= 0; relu_mask == 2:
+ * out = max(out, 0) (Linear -> BatchNorm1d -> ReLU of lib/tempura.py:103-105);
  * g = group_of_unit[r / rows_per_unit]; a (and k1) may be NULL.  BN apply and BN+ReLU backward. */
 int b200vsgg_seg_affine(const void* a, const void* b, const float* k1, const float* k2, const float* k3,
                         const int32_t* group_of_unit, int64_t rows, int32_t rows_per_unit, int32_t cols,
@@ -269,6 +270,36 @@ int b200vsgg_graph_attn_core(const float* qkv, int32_t ld, const int32_t* node_o
                              const float* we, const float* be, int32_t n_frames, void* out, int32_t ldo, void* stream);
 /* GatedResidual: res <- o*g + res*(1-g), g = sigmoid(W [o, res, o-res]); w fp32 [3*dim]. */
 int b200vsgg_gated_residual(const float* o, float* res, const float* w, int32_t rows, int32_t dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SGCls object branch (lib/tempura.py:185-255 / tools/utils/object_classifier.py:177-233).
+ * Object tokens: row r <- box s = src[r] (src NULL = identity):
+ *   x[r] = drop_pe([features[s] | dist[s] @ embed | drop_pos(relu(wp * bn(center_size(box_s)) + bp))] + pe[pos[r]])
+ * = lib/tempura.py:249-252 (feature build) fused with the pad_sequence gather (:197) and PositionalEncoding.forward
+ * (:39-48).  pos NULL: no position term / no drop_pe (the non-tracking path).  BatchNorm1d(4) enters as per-video
+ * (mean, rstd) [V,4] (+ gamma, beta [4]); video_of_box int32 [O].  All tensors fp32; feat_dim, e, h multiples of 4.
+ * The class-sequence encoder itself (3 x nn.TransformerEncoderLayer, :88-92) runs on b200vsgg_gemm_bf16 /
+ * b200vsgg_attn_small_* / b200vsgg_layernorm_* with heads padded 297 -> 304 columns in the weight copies. */
+typedef struct b200vsgg_obj_tokens {
+    const float* features; int32_t feat_dim;   /* [O, feat_dim] */
+    const float* dist; int32_t n_cls;          /* [O, n_cls] detector posterior */
+    const float* embed; int32_t e;             /* obj_embed.weight [n_cls, e] */
+    const float* boxes;                        /* [O,5] = (frame, x1, y1, x2, y2) */
+    const float *bn_mean, *bn_rstd;            /* [V,4] */
+    const float *bn_gamma, *bn_beta;           /* [4] */
+    const int32_t* video_of_box;               /* [O] */
+    const float *wp, *bp; int32_t h;           /* pos_embed Linear: [h,4], [h] */
+    const float* pe;                           /* [max_len, feat_dim+e+h] sinusoid table (nullable with pos) */
+    const int32_t *src, *pos;                  /* [rows] (nullable) */
+    int32_t rows;
+    float p_pos; uint64_t seed_pos;            /* nn.Dropout(0.1) inside pos_embed (indexed by box) */
+    float p_pe; uint64_t seed_pe;              /* dropout of PositionalEncoding (indexed by row) */
+} b200vsgg_obj_tokens;
+int b200vsgg_obj_tokens_fwd(const b200vsgg_obj_tokens* p, float* x_f32, void* x_bf16, void* stream);
+/* Parameter gradients only (features / dist / boxes are frozen detector outputs); outputs pre-zeroed, accumulated:
+ * dembed [n_cls,e], dwp [h,4], dbp [h], dgamma [4], dbeta [4]; dx fp32 [rows, feat_dim+e+h]. */
+int b200vsgg_obj_tokens_bwd(const b200vsgg_obj_tokens* p, const float* dx, float* dembed, float* dwp, float* dbp,
+                            float* dgamma, float* dbeta, void* stream);
 
 /* Upload `bytes` (multiple of 16) from PINNED host memory to the device with a kernel on `stream` instead of the
  * copy engine (see frontend.cu): used for the per-batch index vectors so they never queue behind a bulk

@@ -11,6 +11,14 @@ class GmmHead(C.Structure):
                 ("out2", vp), ("dout", vp)]
 
 
+class ObjTokens(C.Structure):
+    """Mirror of struct b200vsgg_obj_tokens."""
+    _fields_ = [("features", vp), ("feat_dim", i32), ("dist", vp), ("n_cls", i32), ("embed", vp), ("e", i32),
+                ("boxes", vp), ("bn_mean", vp), ("bn_rstd", vp), ("bn_gamma", vp), ("bn_beta", vp), ("video_of_box", vp),
+                ("wp", vp), ("bp", vp), ("h", i32), ("pe", vp), ("src", vp), ("pos", vp), ("rows", i32),
+                ("p_pos", f32), ("seed_pos", u64), ("p_pe", f32), ("seed_pe", u64)]
+
+
 # name -> argtypes (restype is always int32)
 SIGNATURES = {
     "b200vsgg_frame_offsets": [vp, i32, i32, vp, vp],
@@ -51,6 +59,8 @@ SIGNATURES = {
     "b200vsgg_gated_residual": [vp, vp, vp, i32, i32, vp],
     "b200vsgg_grad_sqnorm": [vp, vp, vp, i32, i32, vp, vp],
     "b200vsgg_adamw_clip_step": [vp, vp, vp, i32, i32, vp, f32, f32, f32, f32, f32, f32, vp],
+    "b200vsgg_obj_tokens_fwd": [C.POINTER(ObjTokens), vp, vp, vp],
+    "b200vsgg_obj_tokens_bwd": [C.POINTER(ObjTokens), vp, vp, vp, vp, vp, vp, vp],
     "b200vsgg_upload": [vp, vp, i64, vp],
     "b200vsgg_consistency_kl": [vp, i32, vp, vp, i32, vp, vp],
     "b200vsgg_act_dropout_bf16": [vp, i32, i64, i32, i32, f32, u64, vp, i32, vp],

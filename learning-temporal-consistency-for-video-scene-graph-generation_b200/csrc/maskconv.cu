@@ -153,9 +153,12 @@ __global__ void __launch_bounds__(256) seg_affine_kernel(const __nv_bfloat16* __
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = fmaf(kk1[j], av[j], o[j]);
         }
-        if (relu_mask) {
+        if (relu_mask == 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = bv[j] > 0.f ? o[j] : 0.f;
+        } else if (relu_mask == 2) {   // ReLU of the result itself (Linear -> BatchNorm1d -> ReLU, lib/tempura.py:103-105)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
         }
         store_bf16x8(out + off, o);
     }

@@ -160,7 +160,8 @@ __global__ void pair_concat_bwd_kernel(const float* __restrict__ dtok, const int
 // variance — torch.nn.LayerNorm).  One warp per row, row cached in registers (cols <= 4096).
 // Optional outputs: y fp32, y bf16, bf16(y + add_table[add_idx[row]]).  Saves mean / rstd.
 // ------------------------------------------------------------------------------------------------
-// LN_MAX_VEC = float4 per lane (template): 8 -> cols <= 1024, 16 -> cols <= 2048.
+// LN_MAX_VEC = float4 per lane (template): 8 -> cols <= 1024, 16 -> cols <= 2048, 20 -> cols <= 2560 (the
+// 2376-wide object-sequence encoder, lib/tempura.py:88-92).
 template <int LN_MAX_VEC>
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, int rows, int cols, float eps,
@@ -449,10 +450,10 @@ extern "C" int b200vsgg_layernorm_fwd(const float* x, int32_t ld_x, const float*
                                       int32_t cols, float eps, float* y_f32, int32_t ld_y, void* y_bf16, int32_t ld_b,
                                       const float* add_table, const int32_t* add_idx, void* y_bf16_added,
                                       int32_t ld_added, float* mean, float* rstd, void* stream) {
-    if (!x || !gamma || !beta || cols <= 0 || (cols & 7) || cols > 2048)
-        return set_error(B200VSGG_ERR_BAD_ARG, "layernorm_fwd: cols must be a multiple of 8 and <= 2048");
+    if (!x || !gamma || !beta || cols <= 0 || (cols & 7) || cols > 2560)
+        return set_error(B200VSGG_ERR_BAD_ARG, "layernorm_fwd: cols must be a multiple of 8 and <= 2560");
     if (rows == 0) return 0;
-    auto kern = cols <= 1024 ? layernorm_fwd_kernel<8> : layernorm_fwd_kernel<16>;
+    auto kern = cols <= 1024 ? layernorm_fwd_kernel<8> : (cols <= 2048 ? layernorm_fwd_kernel<16> : layernorm_fwd_kernel<20>);
     kern<<<grid_for(rows, 4, 148 * 32), 128, 0, (cudaStream_t)stream>>>(
         x, ld_x, gamma, beta, rows, cols, eps, y_f32, ld_y, (__nv_bfloat16*)y_bf16, ld_b, add_table, add_idx,
         (__nv_bfloat16*)y_bf16_added, ld_added, mean, rstd);

@@ -245,16 +245,18 @@ def colsum(x, out, group_idx=None, n_groups=1):
     _count()
 
 
-def attn_small_fwd(q, k, v, seg_off, n_seg, max_len, n_heads, head_dim, ctx, drop_p=0.0, seed=0):
-    scale = float(head_dim) ** -0.5
+def attn_small_fwd(q, k, v, seg_off, n_seg, max_len, n_heads, head_dim, ctx, drop_p=0.0, seed=0, scale=None):
+    """scale defaults to head_dim^-0.5; pass it when heads are zero-padded (objbranch: 297 -> 304 columns)."""
+    scale = float(head_dim) ** -0.5 if scale is None else float(scale)
     check(_lib.lib().b200vsgg_attn_small_fwd(
         _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), _ptr(seg_off), n_seg,
         max_len, n_heads, head_dim, scale, _ptr(_bf(ctx)), ctx.stride(0), drop_p, seed, _stream()), "attn_small_fwd")
     _count()
 
 
-def attn_small_bwd(q, k, v, dctx, seg_off, n_seg, max_len, n_heads, head_dim, dq, dk, dv, drop_p=0.0, seed=0):
-    scale = float(head_dim) ** -0.5
+def attn_small_bwd(q, k, v, dctx, seg_off, n_seg, max_len, n_heads, head_dim, dq, dk, dv, drop_p=0.0, seed=0,
+                   scale=None):
+    scale = float(head_dim) ** -0.5 if scale is None else float(scale)
     check(_lib.lib().b200vsgg_attn_small_bwd(
         _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), _ptr(_bf(dctx)),
         dctx.stride(0), _ptr(seg_off), n_seg, max_len, n_heads, head_dim, scale, _ptr(_bf(dq)), dq.stride(0),
@@ -490,6 +492,45 @@ def gated_residual(o, res, w):
 # ------------------------------------------------------------------------------------------------
 # zero-copy uploads of small host arrays (segment plans) through a pinned ring buffer
 # ------------------------------------------------------------------------------------------------
+def _obj_tokens_struct(a):
+    from ._decls import ObjTokens
+    st = ObjTokens()
+    for name in ("features", "dist", "embed", "boxes", "bn_mean", "bn_rstd", "bn_gamma", "bn_beta", "wp", "bp", "pe"):
+        t = a.get(name)
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous(), name
+        setattr(st, name, t.data_ptr() if t is not None else None)
+    for name in ("video_of_box", "src", "pos"):
+        t = a.get(name)
+        if t is not None:
+            assert t.dtype == torch.int32 and t.is_contiguous(), name
+        setattr(st, name, t.data_ptr() if t is not None else None)
+    st.feat_dim, st.n_cls, st.e, st.h = a["features"].shape[1], a["dist"].shape[1], a["embed"].shape[1], a["wp"].shape[0]
+    assert a["embed"].shape[0] == st.n_cls and a["wp"].shape[1] == 4 and a["boxes"].shape[1] == 5
+    st.rows = a["rows"]
+    st.p_pos, st.seed_pos, st.p_pe, st.seed_pe = a.get("p_pos", 0.0), a.get("seed_pos", 0), a.get("p_pe", 0.0), a.get("seed_pe", 0)
+    return st
+
+
+def obj_tokens_fwd(args, x_f32=None, x_bf16=None):
+    """b200vsgg_obj_tokens_fwd; `args` is a dict with the fields of struct b200vsgg_obj_tokens (tensors)."""
+    st = _obj_tokens_struct(args)
+    for t in (x_f32, x_bf16):
+        assert t is None or (t.is_contiguous() and t.shape == (st.rows, st.feat_dim + st.e + st.h))
+    check(_lib.lib().b200vsgg_obj_tokens_fwd(C.byref(st), _ptr(x_f32), _ptr(x_bf16), _stream()), "obj_tokens_fwd")
+    _count()
+
+
+def obj_tokens_bwd(args, dx, dembed, dwp, dbp, dgamma, dbeta):
+    st = _obj_tokens_struct(args)
+    assert dx.dtype == torch.float32 and dx.is_contiguous() and dx.shape == (st.rows, st.feat_dim + st.e + st.h)
+    for t in (dembed, dwp, dbp, dgamma, dbeta):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    check(_lib.lib().b200vsgg_obj_tokens_bwd(C.byref(st), _ptr(dx), _ptr(dembed), _ptr(dwp), _ptr(dbp), _ptr(dgamma),
+                                              _ptr(dbeta), _stream()), "obj_tokens_bwd")
+    _count()
+
+
 class _UploadRing:
     """Pinned staging ring (default 64 MB).  upload(): memcpy into the ring on the host, then a kernel on the
     current stream reads it over PCIe (b200vsgg_upload).  A slot is reused only after the event recorded behind

@@ -108,10 +108,20 @@ class _STTran(nn.Module):
         nn.init.uniform_(self.position_embedding.weight)
 
 
+class _PositionalEncoding(nn.Module):
+    """Holds PositionalEncoding.pe (lib/tempura.py:26-37), a registered buffer of the reference's state_dict."""
+
+    def __init__(self, d_model, max_len):
+        super().__init__()
+        from .objbranch import sinusoid_table
+        self.register_buffer("pe", sinusoid_table(d_model, max_len))
+
+
 class ObjectClassifier(nn.Module):
-    """lib/tempura.py:51-423.  PredCLS only needs `pred_labels = labels` (:245-247); the parameters
-    are created so that reference checkpoints load strictly (they stay frozen in PredCLS,
-    TEMPURA_train.py:106-108)."""
+    """lib/tempura.py:51-423 (and TEAT-GT's copy tools/utils/object_classifier.py).  PredCLS: `pred_labels =
+    labels` (:245-247).  SGCls, phase='train': the object branch of objbranch.py (feature build, class-sequence
+    encoder when `tracking`, intermediate, GMM / linear head; :185-255).  Parameters are created in the
+    reference's order with its names, so reference checkpoints load strictly."""
 
     def __init__(self, mode="sgdet", obj_head="gmm", K=4, obj_classes=None, mem_compute=None, selection=None,
                  selection_lambda=0.5, tracking=None, embed_vecs=None):
@@ -127,7 +137,11 @@ class ObjectClassifier(nn.Module):
         self.obj_dim = 2048
         mem_embed = 1024
         if tracking:
-            raise NotImplementedError("tracking (SGCls/SGDet object branch) is a 'next' row, see DESIGN.md")
+            d_model = self.obj_dim + 200 + 128
+            first = _SpatialLayer(d_model, 8, 1024, 0.1)   # = nn.TransformerEncoderLayer(d_model, 8, 1024, batch_first)
+            self.positional_encoder = _PositionalEncoding(d_model, 600 if mode == "sgdet" else 400)
+            self.encoder_tran = _LayerStack(first, 3)
+            mem_embed = d_model
         if mem_compute:
             self.mem_attention = nn.MultiheadAttention(mem_embed, 1, 0.0, bias=False)
             if selection == "manual":
@@ -139,12 +153,37 @@ class ObjectClassifier(nn.Module):
             self.decoder_lin = GMMHead(1024, len(obj_classes), None, K)
         else:
             self.decoder_lin = nn.Sequential(nn.Linear(1024, len(obj_classes)))
+        self.dropout_p = 0.1
+        self.gmm_eps = None             # {"object": [K,O,C]} noise to inject (parity tests); None = device RNG
+
+    def hallucinate(self, feat):
+        """memory_hallucinator (lib/tempura.py:165-182) against `obj_memory` [n_mem, d]."""
+        bank = self.obj_memory.to(feat.device, torch.float32)
+        D = feat.shape[1]
+        w = self.mem_attention.in_proj_weight
+        q = _GemmNT.apply(feat, w[:D])
+        k = _GemmNT.apply(bank, w[D:2 * D])
+        v = _GemmNT.apply(bank, w[2 * D:])
+        p = torch.softmax(_GemmNT.apply(q, k) * (1.0 / math.sqrt(D)), -1)
+        pad = (-p.shape[1]) % 8
+        o = _GemmNT.apply(F.pad(p, (0, pad)), F.pad(v, (0, 0, 0, pad)).t().contiguous())
+        mem = _GemmNT.apply(o, self.mem_attention.out_proj.weight)
+        e = self.selector if self.selection == "manual" else self.selector(feat).sigmoid()
+        return e * feat + (1 - e) * mem if e is not None else feat + mem
 
     def forward(self, entry, phase="train", unc=False):
-        if self.mode != "predcls":
-            raise NotImplementedError("only PredCLS is on the accelerated path (SURVEY.md §8)")
-        entry["pred_labels"] = entry["labels"]
-        return entry
+        if self.mode == "predcls":
+            entry["pred_labels"] = entry["labels"]
+            return entry
+        if self.mode != "sgcls" or phase != "train" or unc:
+            raise NotImplementedError(
+                "object branch: only mode='sgcls', phase='train', unc=False is on the accelerated path — the test-time "
+                "relabel / NMS / ROIAlign tail (lib/tempura.py:257-307, :310-421) needs the reference's absent CUDA ops")
+        from .objbranch import run_object_branch
+        fpv = entry.get("video_frames")
+        if fpv is None:
+            fpv = np.asarray([entry["human_idx"].shape[0] if "human_idx" in entry else int(entry["boxes"][-1, 0].item()) + 1])
+        return run_object_branch(self, entry, phase, fpv, _HeadsFn.apply, self.dropout_p, self.gmm_eps)
 
 
 # ================================================================================================
@@ -154,11 +193,12 @@ def collate_entries(entries):
     """Concatenate per-video PredCLS entries into one batch entry (videos stay independent:
     windows, BatchNorm statistics and losses never cross `video_frames` boundaries)."""
     keys_cat = ["boxes", "labels", "scores", "im_idx", "pair_idx", "human_idx", "features", "union_feat", "union_box",
-                "spatial_masks"]
+                "spatial_masks", "distribution"]
     out = {}
     box_base, frame_base = 0, 0
     parts = {k: [] for k in keys_cat}
     frames, gts = [], {"attention_gt": [], "spatial_gt": [], "contacting_gt": []}
+    singles, seqs = [], []     # SGCls class sequences (tools/utils/ds_track.py): never cross a video
     for e in entries:
         nf = int(e["human_idx"].shape[0]) if "human_idx" in e else int(e["im_idx"][-1].item()) + 1
         for k in keys_cat:
@@ -176,6 +216,10 @@ def collate_entries(entries):
         for k in gts:
             if k in e:
                 gts[k].extend(e[k])
+        if "indices" in e:
+            if len(e["indices"][0]) > 0:
+                singles.append(e["indices"][0].long() + box_base)
+            seqs.extend(ix.long() + box_base for ix in e["indices"][1:])
         box_base += e["labels"].shape[0]
         frame_base += nf
         frames.append(nf)
@@ -185,6 +229,8 @@ def collate_entries(entries):
     for k, v in gts.items():
         if v:
             out[k] = v
+    if singles or seqs:
+        out["indices"] = [torch.cat(singles) if singles else torch.tensor([])] + seqs
     out["video_frames"] = np.asarray(frames, dtype=np.int64)
     out["video_size"] = entries[0].get("video_size")
     return out
@@ -263,9 +309,10 @@ class TEMPURA(nn.Module):
         self.attention_class_num, self.spatial_class_num, self.contact_class_num = (
             attention_class_num, spatial_class_num, contact_class_num)
         assert mode in ("sgdet", "sgcls", "predcls")
-        if mode != "predcls" or take_obj_mem_feat or rel_head != "gmm":
-            raise NotImplementedError("b200vsgg.TEMPURA accelerates the PredCLS / GMM-head path (SURVEY.md §8); "
-                                      "got mode=%s take_obj_mem_feat=%s rel_head=%s" % (mode, take_obj_mem_feat, rel_head))
+        if mode == "sgdet" or take_obj_mem_feat or rel_head != "gmm":
+            raise NotImplementedError("b200vsgg.TEMPURA accelerates the PredCLS and SGCls-train / GMM-head paths "
+                                      "(SURVEY.md §8); got mode=%s take_obj_mem_feat=%s rel_head=%s"
+                                      % (mode, take_obj_mem_feat, rel_head))
         self.mode, self.tracking, self.take_obj_mem_feat = mode, tracking, take_obj_mem_feat
         self.obj_head, self.rel_head = obj_head, rel_head
         self.obj_mem_compute, self.rel_mem_compute = obj_mem_compute, rel_mem_compute
@@ -385,6 +432,7 @@ class TEMPURA(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def forward(self, entry, phase="train", unc=False):
+        self.object_classifier.gmm_eps = self.gmm_eps
         entry = self.object_classifier(entry, phase=phase, unc=unc)
         feats = entry["features"]
         if not feats.is_cuda:
@@ -921,10 +969,11 @@ class _PathRunner:
         return out
 
 
-def tempura_loss(pred, plan=None):
-    """The reference trainer's relation losses (TEMPURA_train.py:181-206) on the model output dict;
-    with a batch of videos each loss is the mean over videos of the per-video mean, i.e. exactly the
-    average of the losses the reference would compute video by video."""
+def tempura_loss(pred, plan=None, eos_coef=1.0):
+    """The reference trainer's losses (TEMPURA_train.py:181-206) on the model output dict; with a batch of
+    videos each loss is the mean over videos of the per-video mean, i.e. exactly the average of the losses
+    the reference would compute video by video.  SGCls outputs (the object branch ran) add `object_loss`
+    (:191-195, class-weighted CE with weight[0] = eos_coef)."""
     dist_a, dist_s, dist_c = pred["attention_distribution"], pred["spatial_distribution"], pred["contacting_distribution"]
     dev = dist_a.device
     N = dist_a.shape[0]
@@ -946,5 +995,11 @@ def tempura_loss(pred, plan=None):
     ce = F.cross_entropy(dist_a, att, reduction="none")
     bs = F.binary_cross_entropy(dist_s, spa, reduction="none").mean(1)
     bc = F.binary_cross_entropy(dist_c, con, reduction="none").mean(1)
-    return {"attention_relation_loss": (ce * w).sum(), "spatial_relation_loss": (bs * w).sum(),
-            "contacting_relation_loss": (bc * w).sum()}
+    losses = {}
+    if "box_groups" in pred:
+        from .objbranch import object_loss
+        grp = pred["box_groups"]
+        losses["object_loss"] = object_loss(pred, eos_coef, grp.count if grp.V > 1 else None, grp.video_of_box64)
+    losses.update({"attention_relation_loss": (ce * w).sum(), "spatial_relation_loss": (bs * w).sum(),
+                   "contacting_relation_loss": (bc * w).sum()})
+    return losses
