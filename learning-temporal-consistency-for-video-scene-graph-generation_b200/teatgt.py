@@ -100,24 +100,6 @@ class TokenGTEncoder(nn.Module):
         self.embed_out = nn.Linear(d, args.num_output, bias=False)
 
 
-class _ObjectClassifier(nn.Module):
-    """tools/utils/object_classifier.py (obj_head='linear'); PredCLS forward is pred_labels = labels."""
-
-    def __init__(self, num_classes, mode):
-        super().__init__()
-        self.mode = mode
-        self.obj_memory = []
-        self.obj_embed = nn.Embedding(num_classes - 1, 200)
-        self.pos_embed = nn.Sequential(nn.BatchNorm1d(4, momentum=0.001), nn.Linear(4, 128), nn.ReLU(inplace=True),
-                                       nn.Dropout(0.1))
-        self.intermediate = nn.Sequential(nn.Linear(2048 + 200 + 128, 1024), nn.BatchNorm1d(1024), nn.ReLU())
-        self.decoder_lin = nn.Sequential(nn.Linear(1024, num_classes))
-
-    def forward(self, entry, phase="train", unc=False):
-        entry["pred_labels"] = entry["labels"]
-        return entry
-
-
 # ================================================================================================
 # host plan of the ragged structure
 # ================================================================================================
@@ -285,13 +267,16 @@ class TEAT_GT(nn.Module):
     def __init__(self, mode="predcls", attention_class_num=None, spatial_class_num=None, contact_class_num=None,
                  obj_classes=None, tracking=None, args=None, embed_vecs=None):
         super().__init__()
-        if mode != "predcls" or tracking:
-            raise NotImplementedError("b200vsgg.TEAT_GT accelerates the PredCLS path (SURVEY.md §8); SGCls/SGDet need "
-                                      "the tracking object branch (row S1), a 'next' row")
+        if mode == "sgdet":
+            raise NotImplementedError("b200vsgg.TEAT_GT accelerates the PredCLS and SGCls-train paths (SURVEY.md §8); "
+                                      "SGDet needs the detector-side ops that are absent from the reference tree")
         self.obj_classes, self.mode, self.tracking, self.args = obj_classes, mode, tracking, args
         self.attention_class_num, self.spatial_class_num, self.contact_class_num = (
             attention_class_num, spatial_class_num, contact_class_num)
-        self.object_classifier = _ObjectClassifier(len(obj_classes), mode)
+        from .tempura import ObjectClassifier
+        # lib/teatgt.py:44-46 (SGCls, phase='train': the object branch of objbranch.py)
+        self.object_classifier = ObjectClassifier(mode=mode, obj_classes=obj_classes, obj_head="linear", mem_compute=None,
+                                                  K=4, selection=None, selection_lambda=None, tracking=tracking)
         self.subj_fc = nn.Linear(2048, 968)
         self.obj_fc = nn.Linear(2048, 968)
         if embed_vecs is None:  # stand-in for GloVe-6B-200d, seeded

@@ -48,6 +48,62 @@ def import_reference_teatgt():
     return ref
 
 
+SGCLS_ARGS = dict(ARGS, encoder_layers=6, encoder_attention_heads=16)      # tools/utils/teatgt_config.py:11-14
+SGCLS_KW = dict(MODEL_KW, mode="sgcls", tracking=True)
+SGCLS_CASES = [("teatgt_sgcls", 6, 7, (2, 4))]
+
+
+def main_sgcls():
+    """SGCls, phase='train' (the SGCls test tail needs the reference's absent CUDA ops): dropout probabilities are
+    set to 0 on both sides; the regulariser outputs (third-party arithmetic, unpinned) are not stored."""
+    from b200vsgg import synthetic
+    from oracle.teatgt_oracle import TeatgtOracle
+    from oracle.tempura_oracle import get_sequence
+    torch.backends.mha.set_fastpath_enabled(False)
+    torch.Tensor.cuda = lambda self, *a, **k: self      # tools/utils/object_classifier.py hard-codes masks.cuda()
+    ref_mod = import_reference_teatgt()
+    from tools.utils.ds_track import get_sequence as ref_get_sequence
+    classes = synthetic.ag_object_classes()
+    args = types.SimpleNamespace(**SGCLS_ARGS)
+    ref = ref_mod.TEAT_GT(obj_classes=classes, args=args, **SGCLS_KW)
+    synthetic.teatgt_seeded_init_(ref, synthetic.BASE_SEED)
+    orc = TeatgtOracle(obj_classes=classes, args=args, **SGCLS_KW)
+    print("sgcls state_dict interchange (strict):", orc.load_state_dict(ref.state_dict(), strict=True))
+    ref.train(); orc.train()
+    for model in (ref, orc):
+        for m in model.modules():
+            if hasattr(m, "p") and isinstance(getattr(m, "p"), float):
+                m.p = 0.0
+            if isinstance(m, torch.nn.MultiheadAttention):
+                m.dropout = 0.0
+            if hasattr(m, "dropout") and isinstance(getattr(m, "dropout"), float):
+                m.dropout = 0.0
+    worst = 0.0
+    for name, vid, frames, ppf in SGCLS_CASES:
+        entry = synthetic.add_sgcls_inputs(synthetic.make_video_entry(vid, frames, ppf), vid)
+        for k in ("union_feat", "spatial_masks"):
+            entry.pop(k)
+        e_ref = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in entry.items()}
+        e_orc = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in entry.items()}
+        ref_get_sequence(e_ref, None, None, "sgcls")
+        get_sequence(e_orc, "sgcls")
+        with torch.no_grad():
+            r = ref(e_ref, phase="train")
+            o = orc(e_orc, phase="train")
+        gold = {"case": dict(video_index=vid, num_frames=frames, pairs_per_frame=ppf), "args": SGCLS_ARGS,
+                "model_kw": SGCLS_KW, "seed": synthetic.BASE_SEED}
+        for k in ("distribution", "attention_distribution", "spatial_distribution", "contacting_distribution"):
+            d = (r[k] - o[k]).abs().max().item()
+            worst = max(worst, d)
+            print("   %-26s %s |oracle-ref| %.2e" % (k, tuple(r[k].shape), d))
+            gold["train/" + k] = r[k].clone()
+        path = os.path.join(GOLDEN_DIR, name + ".pt")
+        torch.save(gold, path)
+        print(name, "->", path, "%.1f kB" % (os.path.getsize(path) / 1e3))
+    print("sgcls max |oracle - reference|: %.3e" % worst)
+    assert worst <= 2e-5, worst
+
+
 def main():
     from b200vsgg import synthetic
     from oracle.teatgt_oracle import TeatgtOracle
@@ -94,4 +150,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--sgcls" in sys.argv:
+        main_sgcls()
+    else:
+        main()

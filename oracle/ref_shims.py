@@ -258,7 +258,8 @@ def install_reference_native_stubs():
               "tools.utils.draw_rectangles"):
         _mod(n)
     _mod("tools.fasterRCNN.lib.model.roi_layers", ROIAlign=_InertROIAlign, nms=None)
-    _mod("tools.utils.fpn.box_utils", center_size=None)
+    from oracle.tempura_oracle import center_size   # absent from the reference tree: injected (3 lines, unpinned)
+    _mod("tools.utils.fpn.box_utils", center_size=center_size)
     _mod("tools.utils.draw_rectangles.draw_rectangles", draw_union_boxes=None)
 
 

@@ -222,28 +222,20 @@ class TokenGTEncoderOracle(nn.Module):
         return self.embed_out(h) + self.lm_output_learned_bias, h
 
 
-class _ObjectClassifierShell(nn.Module):
-    """tools/utils/object_classifier.py:42-105 parameters (PredCLS forward is pred_labels = labels)."""
-
-    def __init__(self, num_classes):
-        super().__init__()
-        self.obj_embed = nn.Embedding(num_classes - 1, 200)
-        self.pos_embed = nn.Sequential(nn.BatchNorm1d(4, momentum=0.001), nn.Linear(4, 128), nn.ReLU(inplace=True),
-                                       nn.Dropout(0.1))
-        self.intermediate = nn.Sequential(nn.Linear(2048 + 200 + 128, 1024), nn.BatchNorm1d(1024), nn.ReLU())
-        self.decoder_lin = nn.Sequential(nn.Linear(1024, num_classes))
-
-
 class TeatgtOracle(nn.Module):
     def __init__(self, mode="predcls", attention_class_num=3, spatial_class_num=6, contact_class_num=17,
                  obj_classes=None, tracking=None, args=None, with_regulariser=True):
         super().__init__()
-        assert mode == "predcls" and not tracking
+        assert mode in ("predcls", "sgcls")
         from oracle import ref_shims
+        from oracle.tempura_oracle import ObjectClassifierOracle
         self.mode, self.obj_classes, self.args = mode, obj_classes, args
         self.attention_class_num, self.spatial_class_num, self.contact_class_num = (
             attention_class_num, spatial_class_num, contact_class_num)
-        self.object_classifier = _ObjectClassifierShell(len(obj_classes))
+        # lib/teatgt.py:44-46: obj_head='linear', K=4, no object memory (restated in oracle/tempura_oracle.py; the
+        # SGCls-train branch is the same arithmetic as TEMPURA's, tools/utils/object_classifier.py:177-233)
+        self.object_classifier = ObjectClassifierOracle(len(obj_classes), mode, "linear", 4, None, None, None, tracking,
+                                                        dropout=0.0)
         self.subj_fc = nn.Linear(2048, 968)
         self.obj_fc = nn.Linear(2048, 968)
         self.node_label_tokenizer = nn.Embedding(len(obj_classes), 200)
@@ -272,7 +264,8 @@ class TeatgtOracle(nn.Module):
         return torch.cat([rep, self.node_label_tokenizer(lab)], 1)                     # [O', 1168]
 
     def forward(self, entry, phase="train", eig_keep=None, return_artifacts=False):
-        entry["pred_labels"] = entry["labels"]
+        assert self.mode == "predcls" or phase == "train", "SGCls test-time relabel/NMS tail is not restated"
+        entry = self.object_classifier(entry, phase)
         lay = node_layout(entry)
         tok = self.node_tokens(entry, lay)
         box = entry["boxes"][lay["feat_row"]][:, 1:]

@@ -93,3 +93,26 @@ def test_host_plan_reproduces_reference_graph(oracle_model, name):
     # token descriptors: [graph], [null], nodes (u == v), edges
     assert plan.T == sum(2 + c["node_num"] + c["edge_index"].shape[1] for c in gold["clips"])
     assert (plan.desc_h[plan.seq_off_h[:-1], 0] == 0).all() and (plan.desc_h[plan.seq_off_h[:-1] + 1, 0] == 1).all()
+
+
+def test_sgcls_oracle_matches_reference_golden():
+    """TEAT-GT SGCls, phase='train' (6 layers / 16 heads + the object branch): oracle vs the unmodified reference."""
+    import os
+    import types
+    import torch
+    from b200vsgg import synthetic
+    from oracle.teatgt_oracle import TeatgtOracle
+    from oracle.tempura_oracle import get_sequence
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "teatgt_sgcls.pt"), weights_only=False)
+    o = TeatgtOracle(obj_classes=synthetic.ag_object_classes(), args=types.SimpleNamespace(**gold["args"]),
+                     with_regulariser=False, **gold["model_kw"])
+    synthetic.teatgt_seeded_init_(o, gold["seed"])
+    o.train()
+    o.TokenGT_encoder.p = 0.0            # dropout off on both sides when the golden vectors were made
+    vid = gold["case"]["video_index"]
+    e = synthetic.add_sgcls_inputs(synthetic.make_video_entry(**gold["case"]), vid)
+    get_sequence(e, "sgcls")
+    with torch.no_grad():
+        out = o(e, phase="train")
+    for k in ("distribution", "attention_distribution", "spatial_distribution", "contacting_distribution"):
+        assert (out[k] - gold["train/" + k]).abs().max().item() <= 2e-5, k
