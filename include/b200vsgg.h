@@ -150,6 +150,19 @@ int b200vsgg_attn_small_bwd(const void* q, int32_t ldq, const void* k, int32_t l
                             int32_t n_heads, int32_t head_dim, float scale, void* dq, int32_t lddq, void* dk,
                             int32_t lddk, void* dv, int32_t lddv, float drop_p, uint64_t seed, void* stream);
 
+/* Same operation for sequences of any length (< 4096) and head_dim <= 320 (even): the class-sequence encoder of the
+ * SGCls object branch (lib/tempura.py:88-92,201; head_dim 297 zero-padded to 304 by the caller, sequences = object
+ * tracks as long as the video).  Flash-style: lse fp32 [rows, n_heads] is written by the forward (nullable in
+ * inference) and read by the backward; delta fp32 [rows, n_heads] is backward workspace (rowsum(dO*O)). */
+int b200vsgg_attn_rows_fwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                           const int32_t* seg_off, int32_t n_seg, int32_t n_heads, int32_t head_dim, float scale,
+                           void* ctx, int32_t ldc, float* lse, float drop_p, uint64_t seed, void* stream);
+int b200vsgg_attn_rows_bwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                           const void* ctx, int32_t ldc, const void* dctx, int32_t lddc, const float* lse, float* delta,
+                           const int32_t* seg_off, int32_t n_seg, int32_t n_heads, int32_t head_dim, float scale,
+                           void* dq, int32_t lddq, void* dk, int32_t lddk, void* dv, int32_t lddv, float drop_p,
+                           uint64_t seed, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * GMM predicate heads (tools/utils/gmm_heads.py:37-76, uncertainty :25-35).  z = fp32 output of the
  * packed head GEMM; head h occupies columns [col_base, col_base + K*(2C+1)) laid out as

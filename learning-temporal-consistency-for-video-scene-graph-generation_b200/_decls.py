@@ -34,6 +34,9 @@ SIGNATURES = {
     "b200vsgg_attn_small_fwd": [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, f32, vp, i32, f32, u64, vp],
     "b200vsgg_attn_small_bwd": [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, f32, vp, i32, vp, i32,
                                 vp, i32, f32, u64, vp],
+    "b200vsgg_attn_rows_fwd": [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, f32, vp, i32, vp, f32, u64, vp],
+    "b200vsgg_attn_rows_bwd": [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, f32, vp, i32, vp, i32,
+                               vp, i32, f32, u64, vp],
     "b200vsgg_gmm_head_fwd": [vp, i32, i32, i32, C.POINTER(GmmHead), i32, i32, u64, vp],
     "b200vsgg_gmm_head_bwd": [vp, i32, i32, i32, C.POINTER(GmmHead), i32, i32, u64, vp, i32, i32, vp],
     "b200vsgg_nchw_to_nhwc_bf16": [vp, i32, i32, i32, vp, vp],

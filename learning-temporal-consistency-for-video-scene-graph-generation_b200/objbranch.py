@@ -220,8 +220,9 @@ class PostLNEncoderLayer(torch.autograd.Function):
         qkv = _new(M, 3 * dp, BF16, dev)
         ops.gemm(xb, wqkv, bias=bqkv, out_bf16=qkv)
         ctxb = _new(M, dp, BF16, dev)
-        ops.attn_small_fwd(qkv[:, :dp], qkv[:, dp:2 * dp], qkv[:, 2 * dp:], seg_off, n_seg, max_len, n_heads, hdp, ctxb, p,
-                           seed, scale=scale)
+        lse = torch.empty(M, n_heads, device=dev)
+        ops.attn_rows_fwd(qkv[:, :dp], qkv[:, dp:2 * dp], qkv[:, 2 * dp:], seg_off, n_seg, n_heads, hdp, ctxb, lse, p, seed,
+                          scale=scale)
         u = _new(M, d, F32, dev)
         ops.gemm(ctxb, wo, bias=out_b.detach(), residual=x32, out_f32=u, dropout_p=p, seed=seed + 1)
         t32, tb = _new(M, d, F32, dev), _new(M, d, BF16, dev)
@@ -234,14 +235,14 @@ class PostLNEncoderLayer(torch.autograd.Function):
         y32, yb = _new(M, d, F32, dev), _new(M, d, BF16, dev)
         m2, r2 = torch.empty(M, device=dev), torch.empty(M, device=dev)
         ops.layernorm_fwd(v, g2.detach(), be2.detach(), 1e-5, y32, yb, mean=m2, rstd=r2)
-        ctx.save_for_backward(xb, qkv, ctxb, u, m1, r1, tb, h, v, m2, r2, wqkv, wo, w1b, w2b, g1, g2, seg_off)
+        ctx.save_for_backward(xb, qkv, ctxb, lse, u, m1, r1, tb, h, v, m2, r2, wqkv, wo, w1b, w2b, g1, g2, seg_off)
         ctx.meta = (n_seg, max_len, n_heads, hd, hdp, p, seed, scale)
         ctx.mark_non_differentiable(yb)
         return y32, yb
 
     @staticmethod
     def backward(ctx, dy, _dyb):
-        xb, qkv, ctxb, u, m1, r1, tb, h, v, m2, r2, wqkv, wo, w1b, w2b, g1, g2, seg_off = ctx.saved_tensors
+        xb, qkv, ctxb, lse, u, m1, r1, tb, h, v, m2, r2, wqkv, wo, w1b, w2b, g1, g2, seg_off = ctx.saved_tensors
         n_seg, max_len, n_heads, hd, hdp, p, seed, scale = ctx.meta
         M, d = u.shape
         dev = u.device
@@ -276,8 +277,8 @@ class PostLNEncoderLayer(torch.autograd.Function):
         dctx = _new(M, dp, BF16, dev)
         ops.gemm(dub, wo, b_mn=True, out_bf16=dctx)
         dqkv = _new(M, 3 * dp, BF16, dev)
-        ops.attn_small_bwd(qkv[:, :dp], qkv[:, dp:2 * dp], qkv[:, 2 * dp:], dctx, seg_off, n_seg, max_len, n_heads, hdp,
-                           dqkv[:, :dp], dqkv[:, dp:2 * dp], dqkv[:, 2 * dp:], p, seed, scale=scale)
+        ops.attn_rows_bwd(qkv[:, :dp], qkv[:, dp:2 * dp], qkv[:, 2 * dp:], ctxb, dctx, lse, seg_off, n_seg, n_heads, hdp,
+                          dqkv[:, :dp], dqkv[:, dp:2 * dp], dqkv[:, 2 * dp:], p, seed, scale=scale)
         dwqkv_p = _new(3 * dp, d, F32, dev)
         ops.gemm(dqkv, xb, a_mn=True, b_mn=True, out_f32=dwqkv_p)
         dbqkv_p = _colsum(dqkv)

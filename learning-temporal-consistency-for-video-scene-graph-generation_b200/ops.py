@@ -264,6 +264,26 @@ def attn_small_bwd(q, k, v, dctx, seg_off, n_seg, max_len, n_heads, head_dim, dq
     _count()
 
 
+def attn_rows_fwd(q, k, v, seg_off, n_seg, n_heads, head_dim, ctx, lse=None, drop_p=0.0, seed=0, scale=None):
+    """Varlen attention for sequences of any length / head_dim <= 320 (b200vsgg_attn_rows_fwd)."""
+    scale = float(head_dim) ** -0.5 if scale is None else float(scale)
+    check(_lib.lib().b200vsgg_attn_rows_fwd(
+        _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), _ptr(seg_off), n_seg, n_heads,
+        head_dim, scale, _ptr(_bf(ctx)), ctx.stride(0), _ptr(lse), drop_p, seed, _stream()), "attn_rows_fwd")
+    _count()
+
+
+def attn_rows_bwd(q, k, v, ctx, dctx, lse, seg_off, n_seg, n_heads, head_dim, dq, dk, dv, drop_p=0.0, seed=0, scale=None):
+    scale = float(head_dim) ** -0.5 if scale is None else float(scale)
+    delta = torch.empty_like(lse)
+    check(_lib.lib().b200vsgg_attn_rows_bwd(
+        _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), _ptr(_bf(ctx)), ctx.stride(0),
+        _ptr(_bf(dctx)), dctx.stride(0), _ptr(lse), _ptr(delta), _ptr(seg_off), n_seg, n_heads, head_dim, scale,
+        _ptr(_bf(dq)), dq.stride(0), _ptr(_bf(dk)), dk.stride(0), _ptr(_bf(dv)), dv.stride(0), drop_p, seed, _stream()),
+        "attn_rows_bwd")
+    _count(2)
+
+
 def _gmm_heads_array(specs):
     from ._decls import GmmHead
     arr = (GmmHead * len(specs))()

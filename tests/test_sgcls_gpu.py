@@ -234,3 +234,46 @@ def test_train_step_with_dropout_is_finite(cuda_lib):
             assert p.grad is not None and torch.isfinite(p.grad).all(), pname
             n += 1
     assert n > 40
+
+
+@pytest.mark.parametrize("hd,n_heads,lens", [(304, 8, [1, 70, 5, 33, 1, 130]), (48, 4, [17, 1, 64, 32]), (242, 2, [40, 9])])
+def test_attn_rows_kernel_matches_torch(cuda_lib, hd, n_heads, lens):
+    """b200vsgg_attn_rows_{fwd,bwd} (any sequence length, head_dim <= 320) vs fp32 torch attention per segment.
+    Tolerances: bf16 in/out -> ctx max-abs <= 2e-2 * max|ref|, gradients rel-L2 <= 2e-2."""
+    from b200vsgg import ops
+    g = torch.Generator().manual_seed(hd + len(lens))
+    M, D = sum(lens), n_heads * hd
+    q, k, v, do = (torch.randn(M, D, generator=g).bfloat16() for _ in range(4))
+    scale = 0.7 * hd ** -0.5
+    off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    outs = []
+    for s in range(len(lens)):
+        a, b = int(off[s]), int(off[s + 1])
+        Q, K, V = (t[a:b].view(b - a, n_heads, hd).transpose(0, 1) for t in (qf, kf, vf))
+        P = torch.softmax(Q @ K.transpose(1, 2) * scale, -1)
+        outs.append((P @ V).transpose(0, 1).reshape(b - a, D))
+    ref = torch.cat(outs)
+    ref.backward(do.float())
+    cu = lambda t: t.cuda().contiguous()
+    qc, kc, vc, doc, offc = cu(q), cu(k), cu(v), cu(do), cu(off)
+    ctx = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(M, n_heads, device="cuda")
+    ops.attn_rows_fwd(qc, kc, vc, offc, len(lens), n_heads, hd, ctx, lse, scale=scale)
+    assert (ctx.float().cpu() - ref.detach()).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    dq, dk, dv = (torch.empty(M, D, device="cuda", dtype=torch.bfloat16) for _ in range(3))
+    ops.attn_rows_bwd(qc, kc, vc, ctx, doc, lse, offc, len(lens), n_heads, hd, dq, dk, dv, scale=scale)
+    for got, want in ((dq, qf.grad), (dk, kf.grad), (dv, vf.grad)):
+        rel = (got.float().cpu() - want).norm().item() / want.norm().item()
+        assert rel <= 2e-2, rel
+    # dropout: forward/backward regenerate the same mask -> finite differences are not needed, check the identity
+    # sum(dV) = sum_i (sum_j P~_ij) dO_i is consistent with the forward's P~ on V = ones
+    ones = torch.ones_like(vc)
+    ctx1 = torch.empty_like(ctx)
+    ops.attn_rows_fwd(qc, kc, ones, offc, len(lens), n_heads, hd, ctx1, lse, drop_p=0.3, seed=5, scale=scale)
+    rowsum = ctx1.float().view(M, n_heads, hd)[:, :, 0]                     # sum_j P~_ij per (row, head)
+    ops.attn_rows_bwd(qc, kc, ones, ctx1, doc, lse, offc, len(lens), n_heads, hd, dq, dk, dv, drop_p=0.3, seed=5, scale=scale)
+    lhs = dv.float().view(M, n_heads, hd).sum(0)                            # sum_j dV_j  [heads, hd]
+    rhs = (rowsum[:, :, None] * doc.float().view(M, n_heads, hd)).sum(0)
+    assert (lhs - rhs).abs().max().item() <= 3e-2 * rhs.abs().max().item()
+    assert 0.5 < rowsum.mean().item() < 1.5 and (rowsum == 0).float().mean().item() < 0.5
