@@ -314,6 +314,28 @@ int b200vsgg_obj_tokens_fwd(const b200vsgg_obj_tokens* p, float* x_f32, void* x_
 int b200vsgg_obj_tokens_bwd(const b200vsgg_obj_tokens* p, const float* dx, float* dembed, float* dwp, float* dbp,
                             float* dgamma, float* dbeta, void* stream);
 
+/* Trainer loss block of the relation heads, loss AND gradient in one launch (TEMPURA_train.py:181-206,
+ * TEATGT_train.py:153-175): losses[0] += sum_i w_i * CE(att[i,:] used as logits, att_label[i]);
+ * losses[1] += sum_i w_i * mean_c BCE(spa[i,c], t[i,c]); losses[2] likewise for con.  The multi-hot targets come
+ * either dense (fp32 [n,C]) or as the ragged label lists the dataloader yields (CSR: off int32 [n+1], idx int32).
+ * row_w carries the reduction (1/n for one video).  d_* (nullable) receive d(sum of the three losses)/d(input). */
+int b200vsgg_rel_loss(const float* att, const float* spa, const float* con, int32_t n, int32_t ca, int32_t cs, int32_t cc,
+                      const int64_t* att_label, const float* spa_dense, const float* con_dense, const int32_t* spa_off,
+                      const int32_t* spa_idx, const int32_t* con_off, const int32_t* con_idx, const float* row_w,
+                      float* losses /* [3], pre-zeroed */, float* d_att, float* d_spa, float* d_con, void* stream);
+
+/* Structure branch of the regulariser, whole network in one launch (lib/teatgt.py:291-311,316,319 via
+ * graph_transformer_pytorch.GraphTransformer(dim, depth, heads x 64, edge_dim 1, feed-forwards, gated residuals,
+ * rotary) + dgl GlobalAttentionPooling): nodes fp32 [frames, nmax, dim] (first `dim` Laplacian eigenvector columns),
+ * upper uint8 [frames, nmax, nmax] (b200vsgg_teat_pair_flags; adjacency = U + U^T), counts int32 [frames] ->
+ * out fp32 [frames, dim].  params = `depth` packed layers of b200vsgg_graph_small_params_per_layer(dim, heads)
+ * floats each, in the order ln1.w ln1.b to_q.w to_q.b to_kv.w to_kv.b edges_to_kv.w edges_to_kv.b to_out.w to_out.b
+ * gate1.w ln2.w ln2.b ff1.w ff1.b ff2.w ff2.b gate2.w.  nmax <= 16, dim <= 16. */
+int b200vsgg_graph_small_params_per_layer(int32_t dim, int32_t heads);
+int b200vsgg_graph_small_fwd(const float* nodes, const uint8_t* upper, const int32_t* counts, int32_t n_frames,
+                             int32_t nmax, int32_t dim, int32_t heads, int32_t depth, const float* params,
+                             const float* pool_w, const float* pool_b, float* out, void* stream);
+
 /* Upload `bytes` (multiple of 16) from PINNED host memory to the device with a kernel on `stream` instead of the
  * copy engine (see frontend.cu): used for the per-batch index vectors so they never queue behind a bulk
  * input prefetch. h_pinned_src must stay untouched until the kernel has run. */

@@ -551,6 +551,50 @@ def obj_tokens_bwd(args, dx, dembed, dwp, dbp, dgamma, dbeta):
     _count()
 
 
+def rel_loss(att, spa, con, att_label, spa_t, con_t, row_w, want_grad=True):
+    """b200vsgg_rel_loss.  spa_t / con_t: dense fp32 multi-hot [n,C] or a CSR pair (off int32 [n+1], idx int32).
+    Returns (losses [3], d_att, d_spa, d_con) — gradients of the summed losses (None if not wanted)."""
+    n = att.shape[0]
+    for t in (att, spa, con, row_w):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert att_label.dtype == torch.int64 and att_label.is_contiguous()
+
+    def lab(t):
+        if isinstance(t, (tuple, list)):
+            off, idx = t
+            assert off.dtype == torch.int32 and idx.dtype == torch.int32 and off.numel() == n + 1
+            return None, off, idx
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        return t, None, None
+
+    sd, so, si = lab(spa_t)
+    cd, co, ci = lab(con_t)
+    losses = torch.zeros(3, device=att.device)
+    grads = [torch.empty_like(t) if want_grad else None for t in (att, spa, con)]
+    check(_lib.lib().b200vsgg_rel_loss(_ptr(att), _ptr(spa), _ptr(con), n, att.shape[1], spa.shape[1], con.shape[1],
+                                        _ptr(att_label), _ptr(sd), _ptr(cd), _ptr(so), _ptr(si), _ptr(co), _ptr(ci),
+                                        _ptr(row_w), _ptr(losses), _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]),
+                                        _stream()), "rel_loss")
+    _count()
+    return (losses, *grads)
+
+
+def graph_small_fwd(nodes, upper, counts, dim, heads, depth, params, pool_w, pool_b):
+    """b200vsgg_graph_small_fwd: nodes fp32 [F, nmax, dim], upper uint8 [F, nmax, nmax], counts int32 [F] -> [F, dim]."""
+    F_, nmax = nodes.shape[0], nodes.shape[1]
+    assert nodes.dtype == torch.float32 and nodes.is_contiguous() and nodes.shape[2] == dim
+    assert upper.dtype == torch.uint8 and upper.is_contiguous() and upper.shape == (F_, nmax, nmax)
+    assert counts.dtype == torch.int32 and params.dtype == torch.float32 and params.is_contiguous()
+    per_layer = _lib.lib().b200vsgg_graph_small_params_per_layer(dim, heads)
+    assert params.numel() == depth * per_layer, (params.numel(), depth, per_layer)
+    out = torch.empty(F_, dim, device=nodes.device)
+    check(_lib.lib().b200vsgg_graph_small_fwd(_ptr(nodes), _ptr(upper), _ptr(counts), F_, nmax, dim, heads, depth,
+                                               _ptr(params), _ptr(_f32(pool_w)), _ptr(_f32(pool_b)), _ptr(out), _stream()),
+          "graph_small_fwd")
+    _count()
+    return out
+
+
 class _UploadRing:
     """Pinned staging ring (default 64 MB).  upload(): memcpy into the ring on the host, then a kernel on the
     current stream reads it over PCIe (b200vsgg_upload).  A slot is reused only after the event recorded behind

@@ -136,6 +136,20 @@ def run_batched(gt, nodes, adj, counts):
         return x
 
 
+def pack_small_params(gt):
+    """GraphTransformer parameters in the packed order b200vsgg_graph_small_fwd reads (one torch.cat per call)."""
+    parts = []
+    for attn_block, ff_block in gt.layers:
+        pre, gate = attn_block
+        a = pre.fn
+        pre2, gate2 = ff_block
+        parts += [pre.norm.weight, pre.norm.bias, a.to_q.weight, a.to_q.bias, a.to_kv.weight, a.to_kv.bias,
+                  a.edges_to_kv.weight, a.edges_to_kv.bias, a.to_out.weight, a.to_out.bias, gate.proj[0].weight,
+                  pre2.norm.weight, pre2.norm.bias, pre2.fn[0].weight, pre2.fn[0].bias, pre2.fn[2].weight,
+                  pre2.fn[2].bias, gate2.proj[0].weight]
+    return torch.cat([p.detach().reshape(-1).float() for p in parts])
+
+
 @torch.no_grad()
 def run_compact(gt, x, node_off, upper, nmax):
     """Row-compacted GraphTransformer forward on the C-ABI kernels: x fp32 [R, dim] (dim % 8 == 0) = node rows of
@@ -252,9 +266,17 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
         with ThreadPoolExecutor(8) as pool:
             list(pool.map(solve, jobs))
     counts = up_(counts_h)
-    adj = up_(A.astype(np.float32))
     nodes = up_(ev)
-    sym = _pool(run_batched(gat, nodes, adj, counts), counts, gate_nn)                   # [F, 10]
+    small = hidden.is_cuda and nmax <= 16 and gat.dim <= 16 and gat.dim_head == 64
+    if not (small and wide):
+        adj = up_(A.astype(np.float32))
+    if small:
+        # R1 in one launch: 4-layer GraphTransformer(dim 10) + attention pooling, one CTA per frame
+        sym = ops.graph_small_fwd(nodes, spatial_flags.contiguous(), counts.int(), gat.dim, gat.heads, len(gat.layers),
+                                  pack_small_params(gat), gate_nn.weight.detach().reshape(-1).contiguous(),
+                                  gate_nn.bias.detach().contiguous())
+    else:
+        sym = _pool(run_batched(gat, nodes, adj, counts), counts, gate_nn)               # [F, 10]
     if not wide:
         ar = torch.arange(nmax, device=dev)
         pad_rows = (up_(plan.node_off_h[:-1])[:, None] + ar[None, :]).clamp(max=n_nodes - 1)

@@ -969,6 +969,40 @@ class _PathRunner:
         return out
 
 
+class _RelLossFn(torch.autograd.Function):
+    """The three relation losses and their gradients from ONE kernel launch (b200vsgg_rel_loss)."""
+
+    @staticmethod
+    def forward(ctx, dist_a, dist_s, dist_c, att, spa, con, w):
+        want = any(t.requires_grad for t in (dist_a, dist_s, dist_c))
+        losses, da, ds, dc = ops.rel_loss(dist_a.contiguous().float(), dist_s.contiguous().float(),
+                                          dist_c.contiguous().float(), att.contiguous(), spa, con, w.contiguous(), want)
+        ctx.grads = (da, ds, dc)
+        return losses[0], losses[1], losses[2]
+
+    @staticmethod
+    def backward(ctx, ga, gs, gc):
+        da, ds, dc = ctx.grads
+        return da * ga, ds * gs, dc * gc, None, None, None, None
+
+
+def gt_label_csr(entry, device):
+    """Ragged predicate labels as the dataloader yields them (lists of class ids per pair) -> what the loss kernel
+    consumes: attention class index int64 [N] and CSR (offsets int32 [N+1], ids int32) for spatial / contacting.
+    Replaces the per-pair Python loop that builds multi-hot matrices (TEMPURA_train.py:181-187)."""
+    import itertools
+    att = np.fromiter((a[0] if isinstance(a, (list, tuple)) else int(a) for a in entry["attention_gt"]), dtype=np.int64)
+
+    def csr(lists):
+        lens = np.fromiter((len(l) for l in lists), dtype=np.int64, count=len(lists))
+        off = np.zeros(len(lists) + 1, dtype=np.int32)
+        off[1:] = np.cumsum(lens)
+        idx = np.fromiter(itertools.chain.from_iterable(lists), dtype=np.int32, count=int(off[-1]))
+        return ops.upload(off, device), ops.upload(idx, device)
+
+    return ops.upload(att, device), csr(entry["spatial_gt"]), csr(entry["contacting_gt"])
+
+
 def tempura_loss(pred, plan=None, eos_coef=1.0):
     """The reference trainer's losses (TEMPURA_train.py:181-206) on the model output dict; with a batch of
     videos each loss is the mean over videos of the per-video mean, i.e. exactly the average of the losses
@@ -979,6 +1013,8 @@ def tempura_loss(pred, plan=None, eos_coef=1.0):
     N = dist_a.shape[0]
     if "gt_tensors" in pred:  # label tensors prepared by the data loader (same values as below)
         att, spa, con = pred["gt_tensors"]
+    elif dist_a.is_cuda:      # ragged label lists go to the loss kernel as CSR, no multi-hot matrices
+        att, spa, con = gt_label_csr(pred, dev)
     else:
         att = torch.tensor([a[0] if isinstance(a, (list, tuple)) else int(a) for a in pred["attention_gt"]], device=dev)
         spa = torch.zeros(N, dist_s.shape[1])
@@ -992,14 +1028,16 @@ def tempura_loss(pred, plan=None, eos_coef=1.0):
     else:
         ppv = plan.pairs_per_video_dev
         w = 1.0 / (ppv[plan.video_of_pair] * plan.V)
-    ce = F.cross_entropy(dist_a, att, reduction="none")
-    bs = F.binary_cross_entropy(dist_s, spa, reduction="none").mean(1)
-    bc = F.binary_cross_entropy(dist_c, con, reduction="none").mean(1)
+    if dist_a.is_cuda:
+        la, ls, lc = _RelLossFn.apply(dist_a, dist_s, dist_c, att, spa, con, w)
+    else:
+        la = (F.cross_entropy(dist_a, att, reduction="none") * w).sum()
+        ls = (F.binary_cross_entropy(dist_s, spa, reduction="none").mean(1) * w).sum()
+        lc = (F.binary_cross_entropy(dist_c, con, reduction="none").mean(1) * w).sum()
     losses = {}
     if "box_groups" in pred:
         from .objbranch import object_loss
         grp = pred["box_groups"]
         losses["object_loss"] = object_loss(pred, eos_coef, grp.count if grp.V > 1 else None, grp.video_of_box64)
-    losses.update({"attention_relation_loss": (ce * w).sum(), "spatial_relation_loss": (bs * w).sum(),
-                   "contacting_relation_loss": (bc * w).sum()})
+    losses.update({"attention_relation_loss": la, "spatial_relation_loss": ls, "contacting_relation_loss": lc})
     return losses

@@ -328,3 +328,68 @@ def test_layout_kernels(cuda_lib):
     assert torch.equal(yf, m.permute(0, 2, 3, 1).reshape(21 * 49, 256))
     back = ops.nhwc_to_nchw_f32(yf, 21, 256, (7, 7))
     assert torch.equal(back, m)
+
+
+def test_rel_loss_kernel_matches_trainer_formulas(cuda_lib):
+    """b200vsgg_rel_loss (loss + gradient, one launch) vs the nn modules the reference trainer instantiates
+    (TEMPURA_train.py:100-102,196-205), dense and CSR labels, including saturated probabilities (BCE clamp)."""
+    from b200vsgg import ops
+    g = torch.Generator().manual_seed(4)
+    N = 700
+    att = torch.softmax(torch.randn(N, 3, generator=g), 1)
+    spa = torch.sigmoid(3 * torch.randn(N, 6, generator=g))
+    con = torch.sigmoid(3 * torch.randn(N, 17, generator=g))
+    spa[0, 0], spa[1, 1], con[2, 3] = 0.0, 1.0, 1.0        # log clamps at -100 in nn.BCELoss
+    y = torch.randint(0, 3, (N,), generator=g)
+    sl = [sorted(set(torch.randint(0, 6, (int(torch.randint(1, 3, (1,), generator=g)),), generator=g).tolist())) for _ in range(N)]
+    cl = [sorted(set(torch.randint(0, 17, (int(torch.randint(1, 4, (1,), generator=g)),), generator=g).tolist())) for _ in range(N)]
+    st, ct = torch.zeros(N, 6), torch.zeros(N, 17)
+    for i in range(N):
+        st[i, sl[i]] = 1
+        ct[i, cl[i]] = 1
+    w = torch.rand(N, generator=g) / N
+    a_, s_, c_ = (t.clone().requires_grad_(True) for t in (att, spa, con))
+    ref = [(torch.nn.CrossEntropyLoss(reduction="none")(a_, y) * w).sum(),
+           (torch.nn.BCELoss(reduction="none")(s_, st).mean(1) * w).sum(),
+           (torch.nn.BCELoss(reduction="none")(c_, ct).mean(1) * w).sum()]
+    sum(ref).backward()
+    cu = lambda t: t.cuda().contiguous()
+    off = lambda ls: cu(torch.tensor([0] + list(torch.tensor([len(l) for l in ls]).cumsum(0)), dtype=torch.int32))
+    flat = lambda ls: cu(torch.tensor([c for l in ls for c in l], dtype=torch.int32))
+    for labels in ((cu(st), cu(ct)), ((off(sl), flat(sl)), (off(cl), flat(cl)))):
+        losses, da, ds, dc = ops.rel_loss(cu(att), cu(spa), cu(con), cu(y), labels[0], labels[1], cu(w))
+        for got, want in zip(losses.cpu(), ref):
+            assert abs(got.item() - want.item()) <= 1e-5 * abs(want.item()) + 1e-7
+        for got, want in ((da, a_.grad), (ds, s_.grad), (dc, c_.grad)):
+            finite = torch.isfinite(want)
+            rel = (got.cpu()[finite] - want[finite]).norm().item() / want[finite].norm().item()
+            assert rel <= 1e-5, rel
+
+
+def test_graph_small_kernel_matches_torch_graph_transformer(cuda_lib):
+    """b200vsgg_graph_small_fwd (R1: 4-layer GraphTransformer(dim 10) + attention pooling in one launch) vs the
+    batched torch evaluation of the same modules (regulariser.run_batched + _pool), fp32 both: max-abs <= 2e-4."""
+    from b200vsgg import ops, regulariser
+    torch.manual_seed(3)
+    gt = regulariser.GraphTransformer(dim=10, depth=4).cuda()
+    for p in gt.parameters():                       # default inits are tiny for biases / gates: exercise everything
+        torch.nn.init.normal_(p, std=0.3)
+    gate_nn = torch.nn.Linear(10, 1).cuda()
+    F_, nmax = 37, 11
+    g = torch.Generator().manual_seed(9)
+    counts = torch.randint(2, nmax + 1, (F_,), generator=g)
+    counts[0], counts[1] = nmax, 2
+    nodes = torch.randn(F_, nmax, 10, generator=g)
+    upper = torch.triu((torch.rand(F_, nmax, nmax, generator=g) < 0.6), 1).to(torch.uint8)
+    ar = torch.arange(nmax)
+    ok = ar[None, :] < counts[:, None]
+    nodes = nodes * ok[..., None]
+    upper = upper * (ok[:, :, None] & ok[:, None, :]).to(torch.uint8)
+    adj = (upper + upper.transpose(1, 2)).float()
+    with torch.no_grad():
+        ref = regulariser._pool(regulariser.run_batched(gt, nodes.cuda(), adj.cuda(), counts.cuda()), counts.cuda(), gate_nn)
+        got = ops.graph_small_fwd(nodes.cuda().contiguous(), upper.cuda().contiguous(), counts.int().cuda(), 10, gt.heads, 4,
+                                  regulariser.pack_small_params(gt), gate_nn.weight.detach().reshape(-1).contiguous(),
+                                  gate_nn.bias.detach().contiguous())
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-4 * max(1.0, ref.abs().max().item()), err
