@@ -89,7 +89,7 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
 template <int A_MN, int B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                  const GemmEpi ep, const int M, const int N, const int K) {
+                  const __grid_constant__ CUtensorMap tma_c, const GemmEpi ep, const int M, const int N, const int K) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -137,6 +137,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Warpgroup register reallocation: warps 0-3 (TMA producer, MMA issuer, TMEM allocator, idle) need almost no
+    // registers; the two epilogue warpgroups take them over (384 x 168 at launch -> 128 x 40 + 256 x 232), so the
+    // epilogue's three 32-element register arrays and its state no longer spill to local memory.
+    if (warp < 4) {
+    ptx::setmaxnreg_dec<40>();
     if (warp == 0) {
         // ================================ TMA producer (both CTAs) ================================
         if (lane == 0) {
@@ -201,7 +206,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
                 if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
             }
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        ptx::setmaxnreg_inc<232>();
         // ================================ epilogue warps (8 per CTA) ================================
         const int ew = warp - 4;
         const int wq = warp & 3;
@@ -225,13 +232,26 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const uint32_t empty_remote1 = mapa(ptx::smem_u32(&tmem_empty_bar[1]), 0);
         int acc = 0;
         uint32_t acc_phase = 0;
+        int issued = 0;                                   // TMA stores issued by this warp (epi_chunk_tma)
         for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
             const int m0 = (tile / num_n) * BM2 + static_cast<int>(rank) * 128;
             const int n0 = (tile % num_n) * BN2;
             const int rbase = m0 + wq * 32;
             const int rows_here = min(32, M - rbase);
             bool waited = false;
-            if (rows_here > 0) {
+            if (rows_here > 0 && ep.tma_store) {
+                uint32_t r[32];
+                bool loaded = false;
+#pragma unroll 1
+                for (int c = 0; c < BN2 / 64; ++c) {
+                    const int nc = n0 + half * (BN2 / 2) + c * 32;
+                    if (nc >= N) break;
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) +
+                                           static_cast<uint32_t>(acc * BN2 + half * (BN2 / 2) + c * 32);
+                    epi_chunk_tma(E, &tma_c, taddr, 0xffffffffu, r, loaded, rbase, M, nc,
+                                  reinterpret_cast<uint8_t*>(E.stg), issued, &tmem_full_bar[acc], acc_phase, waited);
+                }
+            } else if (rows_here > 0) {
 #pragma unroll 1
                 for (int c = 0; c < BN2 / 64; ++c) {
                     const int nc = n0 + half * (BN2 / 2) + c * 32;
@@ -252,6 +272,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             mbar_arrive_cluster(acc == 0 ? empty_remote0 : empty_remote1);   // leader's "accumulator free" barrier
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
+        if (issued > 0 && lane == 0) ptx::bulk_wait_all();   // staging boxes stay valid until every store has drained
     }
 
     // ================================ teardown ================================
@@ -275,6 +296,11 @@ static int launch_gemm2(const void* A, int lda, const void* B, int ldb, int M, i
     if (B_MN == 0) rc = make_tmap_bf16(&tb, B, K, N, ldb, BK2, 128);
     else rc = make_tmap_bf16(&tb, B, N, K, ldb, 64, BK2);
     if (rc) return rc;
+    CUtensorMap tc = ta;                                   // placeholder when the TMA-store epilogue is off
+    if (ep.tma_store) {
+        rc = make_tmap_bf16(&tc, ep.out_bf16, N, M, ep.ld_bf16, 32, 32, false);
+        if (rc) return rc;
+    }
     auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -285,7 +311,7 @@ static int launch_gemm2(const void* A, int lda, const void* B, int ldb, int M, i
     const int num_tiles = ((M + BM2 - 1) / BM2) * ((N + BN2 - 1) / BN2);
     int clusters = num_sms() / 2;
     if (clusters > num_tiles) clusters = num_tiles;
-    kern<<<clusters * 2, 384, SMEM_BYTES, stream>>>(ta, tb, ep, M, N, K);
+    kern<<<clusters * 2, 384, SMEM_BYTES, stream>>>(ta, tb, tc, ep, M, N, K);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
     return 0;

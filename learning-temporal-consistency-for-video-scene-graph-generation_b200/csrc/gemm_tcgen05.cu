@@ -14,7 +14,7 @@ namespace vsgg {
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(384, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const GemmEpi ep, const int M, const int N, const int K, const int splits, const int kb_per,
+                 const __grid_constant__ CUtensorMap tma_c, const GemmEpi ep, const int M, const int N, const int K, const int splits, const int kb_per,
                  const int a_k_period) {
     // splits > 1: split-K.  Work unit u -> (tile = u % num_tiles, split = u / num_tiles); split s reduces
     // k-blocks [s*kb_per, min(num_kb, (s+1)*kb_per)) and its epilogue atomically adds into out_f32.
@@ -64,6 +64,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Warpgroup register reallocation: warps 0-3 (TMA producer, MMA issuer, TMEM allocator, idle) need almost no
+    // registers; the two epilogue warpgroups take them over (384 x 168 at launch -> 128 x 40 + 256 x 232), so the
+    // epilogue's three 32-element register arrays and its state no longer spill to local memory.
+    if (warp < 4) {
+    ptx::setmaxnreg_dec<40>();
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
@@ -138,7 +143,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
             }
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        ptx::setmaxnreg_inc<232>();
         // ================================ epilogue warps (8) ================================
         // Warp (4 + e): TMEM lane quadrant wq = warp % 4 (rows m0 + 32*wq ..), column half e / 4 of the tile.
         // Per 32-column chunk: tcgen05.ld gives each lane ONE ROW x 32 columns; the chunk is transposed
@@ -164,6 +171,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         E.N = N; E.lane = lane; E.atomic = splits > 1;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int issued = 0;                                   // TMA stores issued by this warp (epi_chunk_tma)
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
             const int tile = unit % num_tiles, split = unit / num_tiles;
             const int m0 = (tile / num_n) * BM;
@@ -172,7 +180,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const int rows_here = min(32, M - rbase);      // <= 0: nothing to store for this warp
             E.use_bias = ep.bias != nullptr && (splits == 1 || split == 0);
             bool waited = false;
-            if (rows_here > 0) {
+            if (rows_here > 0 && ep.tma_store) {
+                uint32_t r[32];
+                bool loaded = false;
+#pragma unroll 1
+                for (int c = 0; c < BN / 64; ++c) {
+                    const int nc = n0 + half * (BN / 2) + c * 32;
+                    if (nc >= N) break;  // warp-uniform
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) +
+                                           static_cast<uint32_t>(acc * BN + half * (BN / 2) + c * 32);
+                    epi_chunk_tma(E, &tma_c, taddr, 0xffffffffu, r, loaded, rbase, M, nc,
+                                  reinterpret_cast<uint8_t*>(E.stg), issued, &tmem_full_bar[acc], acc_phase, waited);
+                }
+            } else if (rows_here > 0) {
 #pragma unroll 1
                 for (int c = 0; c < BN / 64; ++c) {
                     const int nc = n0 + half * (BN / 2) + c * 32;
@@ -193,6 +213,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             ptx::mbar_arrive(&tmem_empty_bar[acc]);
             if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         }
+        if (issued > 0 && lane == 0) ptx::bulk_wait_all();   // staging boxes stay valid until every store has drained
     }
 
     // ================================ teardown ================================
@@ -221,6 +242,11 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, in
     if (B_MN == 0) rc = make_tmap_bf16(&tb, B, K, N, ldb, BK, BN);
     else rc = make_tmap_bf16(&tb, B, N, K, ldb, 64, BK);
     if (rc) return rc;
+    CUtensorMap tc = ta;                                   // placeholder when the TMA-store epilogue is off
+    if (ep.tma_store) {
+        rc = make_tmap_bf16(&tc, ep.out_bf16, N, M, ep.ld_bf16, 32, 32, false);
+        if (rc) return rc;
+    }
 
     auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
     static bool attr_set = false;
@@ -251,7 +277,7 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, in
     }
     const int num_units = num_tiles * splits;
     int grid = num_units < num_sms() ? num_units : num_sms();
-    kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(ta, tb, ep, M, N, K, splits, kb_per, a_k_period);
+    kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, ep, M, N, K, splits, kb_per, a_k_period);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
     return 0;
@@ -308,6 +334,10 @@ extern "C" int b200vsgg_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, cons
         ep.vec_ok = ok ? 1 : 0;
     }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    // bf16-only output without residual / accumulation / split-K: TMA-store epilogue
+    static const bool tma_epi = []() { const char* v = getenv("B200VSGG_GEMM_TMA_EPI"); return !(v && v[0] == '0'); }();
+    ep.tma_store = (tma_epi && ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.residual == nullptr && !ep.accumulate &&
+                    ep.vec_ok && e->split_k <= 1) ? 1 : 0;
     // Large problems: 256x256 tiles on CTA pairs (cta_group::2), 2/3 of the operand traffic per flop.
     if (use_2cta() && e->a_k_period == 0 && e->split_k <= 1) {
         const long long tiles2 = static_cast<long long>((M + 255) / 256) * ((N + 255) / 256);
