@@ -23,7 +23,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // per CTA
 constexpr int STAGES = 6;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
-constexpr int BAR_BYTES = 256;
+constexpr int BAR_BYTES = 1024;   // keeps the epilogue staging boxes 1024-byte aligned (swizzled TMA stores)
 constexpr int EPI_BYTES = 8 * 4096;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;
 
@@ -89,7 +89,8 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
 template <int A_MN, int B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                  const __grid_constant__ CUtensorMap tma_c, const GemmEpi ep, const int M, const int N, const int K) {
+                  const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_d,
+                 const GemmEpi ep, const int M, const int N, const int K) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -240,16 +241,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             const int rows_here = min(32, M - rbase);
             bool waited = false;
             if (rows_here > 0 && ep.tma_store) {
-                uint32_t r[32];
-                bool loaded = false;
 #pragma unroll 1
                 for (int c = 0; c < BN2 / 64; ++c) {
                     const int nc = n0 + half * (BN2 / 2) + c * 32;
                     if (nc >= N) break;
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) +
                                            static_cast<uint32_t>(acc * BN2 + half * (BN2 / 2) + c * 32);
-                    epi_chunk_tma(E, &tma_c, taddr, 0xffffffffu, r, loaded, rbase, M, nc,
-                                  reinterpret_cast<uint8_t*>(E.stg), issued, &tmem_full_bar[acc], acc_phase, waited);
+                    epi_chunk_tma(E, &tma_c, &tma_d, taddr, rbase, M, nc, reinterpret_cast<uint8_t*>(E.stg), issued,
+                                  &tmem_full_bar[acc], acc_phase, waited);
                 }
             } else if (rows_here > 0) {
 #pragma unroll 1
@@ -296,11 +295,9 @@ static int launch_gemm2(const void* A, int lda, const void* B, int ldb, int M, i
     if (B_MN == 0) rc = make_tmap_bf16(&tb, B, K, N, ldb, BK2, 128);
     else rc = make_tmap_bf16(&tb, B, N, K, ldb, 64, BK2);
     if (rc) return rc;
-    CUtensorMap tc = ta;                                   // placeholder when the TMA-store epilogue is off
-    if (ep.tma_store) {
-        rc = make_tmap_bf16(&tc, ep.out_bf16, N, M, ep.ld_bf16, 32, 32, false);
-        if (rc) return rc;
-    }
+    CUtensorMap tc = ta, td = ta;                          // placeholders when the TMA-store epilogue is off
+    if (ep.tma_store && ep.out_bf16 != nullptr && (rc = make_tmap_out(&tc, ep.out_bf16, false, N, M, ep.ld_bf16))) return rc;
+    if (ep.tma_store && ep.out_f32 != nullptr && (rc = make_tmap_out(&td, ep.out_f32, true, N, M, ep.ld_f32))) return rc;
     auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -311,7 +308,7 @@ static int launch_gemm2(const void* A, int lda, const void* B, int ldb, int M, i
     const int num_tiles = ((M + BM2 - 1) / BM2) * ((N + BN2 - 1) / BN2);
     int clusters = num_sms() / 2;
     if (clusters > num_tiles) clusters = num_tiles;
-    kern<<<clusters * 2, 384, SMEM_BYTES, stream>>>(ta, tb, tc, ep, M, N, K);
+    kern<<<clusters * 2, 384, SMEM_BYTES, stream>>>(ta, tb, tc, td, ep, M, N, K);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
     return 0;

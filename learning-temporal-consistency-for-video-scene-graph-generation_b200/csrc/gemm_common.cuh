@@ -33,7 +33,7 @@ struct GemmEpi {
     float dropout_p;
     unsigned long long dropout_seed;
     int vec_ok;  // all epilogue pointers / leading dimensions allow 16-byte vector access
-    int tma_store;  // bf16-only output without residual: the epilogue writes through TMA stores (epi_chunk_tma)
+    int tma_store;  // the epilogue writes through TMA stores (epi_chunk_tma)
 };
 
 constexpr int BM = 128;
@@ -47,7 +47,7 @@ struct GemmCfg {
     static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
     static constexpr int ACC_STAGES = 2;
     static constexpr int TMEM_COLS = (ACC_STAGES * BN <= 32) ? 32 : ((ACC_STAGES * BN <= 64) ? 64 : ((ACC_STAGES * BN <= 128) ? 128 : ((ACC_STAGES * BN <= 256) ? 256 : 512)));
-    static constexpr int BAR_BYTES = 256;
+    static constexpr int BAR_BYTES = 1024;   // keeps the epilogue staging boxes 1024-byte aligned (swizzled TMA stores)
     static constexpr int EPI_BYTES = 8 * 4096;  // one swizzled 32x32 fp32 transpose buffer per epilogue warp
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024 /*align slack*/;
 };
@@ -191,39 +191,47 @@ __device__ __forceinline__ void epi_chunk(const EpiRegs& E, uint32_t taddr, int 
     }
 }
 
-// bf16-only output (no residual / accumulate / split-K): one 32 x 32 chunk straight from the TMEM layout (lane = row)
-// through a 2 KB shared-memory box to a TMA store.  ~70 instructions per chunk instead of ~400: no transpose, no
-// per-row address arithmetic, no 2-byte stores; rows >= M and columns >= N are clipped by the tensor map.
-// `box` = this warp's two 2 KB staging boxes (128-byte aligned); `issued` counts the stores of this warp so far
-// (lane 0 owns the bulk groups).  The next chunk's tcgen05.ld is issued as soon as r[] has been consumed.
-__device__ __forceinline__ void epi_chunk_tma(const EpiRegs& E, const CUtensorMap* tmc, uint32_t taddr, uint32_t taddr_next,
-                                              uint32_t (&r)[32], bool& loaded, int rbase, int M, int nc, uint8_t* box,
-                                              int& issued, uint64_t* full_bar, uint32_t full_phase, bool& waited) {
+// TMA-store epilogue (everything except split-K atomics, in-place accumulation and residual+mask together): one
+// 32 x 32 chunk goes straight from the TMEM layout (lane = row, 32 consecutive columns in registers) through a
+// hardware-swizzled shared-memory box to cp.async.bulk.tensor stores.  ~80-120 instructions per chunk instead of
+// ~400: no transpose, no per-row address arithmetic, no 2- or 4-byte stores; rows >= M and columns >= N are clipped
+// by the tensor map.  Residual / mask rows are read in the same layout (16-byte vector loads along the row).
+//   fp32 output : box 32 rows x 128 B, SWIZZLE_128B (16-byte piece k of row r sits at piece k ^ (r & 7))
+//   bf16 output : box 32 rows x  64 B, SWIZZLE_64B  (piece k of row r at k ^ ((r >> 1) & 3)); bf16-only outputs
+//                 alternate between two boxes so the store of chunk c overlaps the math of chunk c + 1
+// `box` = this warp's 4 KB staging area (1024-byte aligned); lane 0 owns the bulk groups.
+__device__ __forceinline__ void epi_chunk_tma(const EpiRegs& E, const CUtensorMap* tm_bf16, const CUtensorMap* tm_f32,
+                                              uint32_t taddr, int rbase, int M, int nc, uint8_t* box, int& issued,
+                                              uint64_t* full_bar, uint32_t full_phase, bool& waited) {
     const int lane = E.lane;
     const int row = min(rbase + lane, M - 1);
     const bool has_mask = E.mask_src != nullptr;
-    uint4 mk[4];
-    if (has_mask) {
-        const __nv_bfloat16* mp = E.mask_src + static_cast<size_t>(row) * E.ldm + nc;
+    // ---- prefetch this lane's row segment of the residual / mask before the accumulator is waited for
+    float4 ax[8];
+    uint4 ab[4];
+    if (E.res_f32 != nullptr) {
+        const float4* rp = reinterpret_cast<const float4*>(E.res_f32 + static_cast<size_t>(row) * E.ldr + nc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ax[j] = (nc + 4 * j + 4 <= E.N) ? __ldg(rp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (E.res_b16 != nullptr || has_mask) {
+        const __nv_bfloat16* bp = E.res_b16 != nullptr ? E.res_b16 + static_cast<size_t>(row) * E.ldr + nc
+                                                      : E.mask_src + static_cast<size_t>(row) * E.ldm + nc;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            mk[j] = (nc + 8 * j + 8 <= E.N) ? __ldg(reinterpret_cast<const uint4*>(mp) + j) : make_uint4(0u, 0u, 0u, 0u);
+            ab[j] = (nc + 8 * j + 8 <= E.N) ? __ldg(reinterpret_cast<const uint4*>(bp) + j) : make_uint4(0u, 0u, 0u, 0u);
     }
     const float bias_l = (E.use_bias && nc + lane < E.N) ? __ldg(E.bias + nc + lane) : 0.f;
-    if (!loaded) {
-        if (!waited) {
-            ptx::mbar_wait(full_bar, full_phase);
-            ptx::tc_fence_after();
-            waited = true;
-        }
-        ptx::tmem_ld_32x32b_x32(taddr, r);
+    if (!waited) {
+        ptx::mbar_wait(full_bar, full_phase);
+        ptx::tc_fence_after();
+        waited = true;
     }
+    uint32_t r[32];
+    ptx::tmem_ld_32x32b_x32(taddr, r);
     ptx::tmem_ld_wait();
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), E.alpha, __shfl_sync(0xffffffffu, bias_l, j));
-    loaded = taddr_next != 0xffffffffu;
-    if (loaded) ptx::tmem_ld_32x32b_x32(taddr_next, r);        // overlaps with the math / stores below
     if (E.act == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -234,7 +242,7 @@ __device__ __forceinline__ void epi_chunk_tma(const EpiRegs& E, const CUtensorMa
     if (has_mask) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&mk[j]);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&ab[j]);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const float2 m = __bfloat1622float2(h[t]);
@@ -257,36 +265,69 @@ __device__ __forceinline__ void epi_chunk_tma(const EpiRegs& E, const CUtensorMa
             v[j] = (h >= E.drop_thr) ? v[j] * E.inv_keep : 0.f;
         }
     }
-    uint8_t* dst = box + (issued & 1) * 2048;
-    if (issued >= 2) {                      // the store issued two chunks ago must have read this box
-        if (lane == 0) ptx::bulk_wait_read<1>();
-        __syncwarp();
-    }
-    // row-major [32 rows][32 bf16]; the four 16-byte pieces of a row are written in a lane-rotated order so that the
-    // eight lanes of one shared-memory phase hit eight different 16-byte bank groups
+    if (E.res_f32 != nullptr) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int piece = (k + (lane >> 1)) & 3;
-        uint4 u;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            // piece is runtime: select with predicated moves over the 4 candidates (registers stay statically indexed)
-            float a = 0.f, b = 0.f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (piece == q) { a = v[8 * q + 2 * t]; b = v[8 * q + 2 * t + 1]; }
-            h[t] = __floats2bfloat162_rn(a, b);
+        for (int j = 0; j < 8; ++j) {
+            v[4 * j] += ax[j].x; v[4 * j + 1] += ax[j].y; v[4 * j + 2] += ax[j].z; v[4 * j + 3] += ax[j].w;
         }
-        *reinterpret_cast<uint4*>(dst + lane * 64 + piece * 16) = u;
+    } else if (E.res_b16 != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&ab[j]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 m = __bfloat1622float2(h[t]);
+                v[8 * j + 2 * t] += m.x;
+                v[8 * j + 2 * t + 1] += m.y;
+            }
+        }
     }
-    ptx::fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-        ptx::tma_store_2d(tmc, dst, nc, rbase);
-        ptx::bulk_commit();
+    const bool f32_out = E.out_f32 != nullptr, b16_out = E.out_bf16 != nullptr;
+    if (f32_out) {
+        if (issued > 0) {                      // single 4 KB box: the previous store must have read it
+            if (lane == 0) ptx::bulk_wait_read<0>();
+            __syncwarp();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(box + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            ptx::tma_store_2d(tm_f32, box, nc, rbase);
+            ptx::bulk_commit();
+        }
+        ++issued;
     }
-    ++issued;
+    if (b16_out) {
+        uint8_t* dst = box;
+        if (f32_out) {
+            if (lane == 0) ptx::bulk_wait_read<0>();
+            __syncwarp();
+        } else {
+            dst = box + (issued & 1) * 2048;
+            if (issued >= 2) {                  // the store issued two chunks ago must have read this box
+                if (lane == 0) ptx::bulk_wait_read<1>();
+                __syncwarp();
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[8 * k + 2 * t], v[8 * k + 2 * t + 1]);
+            *reinterpret_cast<uint4*>(dst + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = u;
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            ptx::tma_store_2d(tm_bf16, dst, nc, rbase);
+            ptx::bulk_commit();
+        }
+        ++issued;
+    }
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -305,6 +346,25 @@ static inline PFN_encodeTiled get_encode_fn() {
             fn = reinterpret_cast<PFN_encodeTiled>(p);
     }
     return fn;
+}
+
+// Output tensor maps of the TMA-store epilogue: 32 x 32 boxes of a row-major [M, N] matrix (pitch ld elements).
+static inline int make_tmap_out(CUtensorMap* tm, const void* base, bool is_f32, uint64_t N, uint64_t M, uint64_t ld) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (enc == nullptr) return set_error(B200VSGG_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+    const uint64_t es = is_f32 ? 4 : 2;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || ((ld * es) & 15u) != 0)
+        return set_error(B200VSGG_ERR_BAD_ARG, "gemm output must be 16-byte aligned with a 16-byte multiple pitch");
+    cuuint64_t dims[2] = {N, M};
+    cuuint64_t strides[1] = {ld * es};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(B200VSGG_ERR_TMAP, "cuTensorMapEncodeTiled failed for a GEMM output");
+    return 0;
 }
 
 // 2D bf16 tensor map: `inner` contiguous elements, `outer` rows with pitch ld (elements); box = box_inner x box_outer.

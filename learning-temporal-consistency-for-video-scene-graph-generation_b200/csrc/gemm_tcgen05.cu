@@ -14,7 +14,8 @@ namespace vsgg {
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(384, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const __grid_constant__ CUtensorMap tma_c, const GemmEpi ep, const int M, const int N, const int K, const int splits, const int kb_per,
+                 const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_d,
+                 const GemmEpi ep, const int M, const int N, const int K, const int splits, const int kb_per,
                  const int a_k_period) {
     // splits > 1: split-K.  Work unit u -> (tile = u % num_tiles, split = u / num_tiles); split s reduces
     // k-blocks [s*kb_per, min(num_kb, (s+1)*kb_per)) and its epilogue atomically adds into out_f32.
@@ -180,17 +181,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const int rows_here = min(32, M - rbase);      // <= 0: nothing to store for this warp
             E.use_bias = ep.bias != nullptr && (splits == 1 || split == 0);
             bool waited = false;
-            if (rows_here > 0 && ep.tma_store) {
-                uint32_t r[32];
-                bool loaded = false;
+            if (rows_here > 0 && ep.tma_store && splits == 1) {
 #pragma unroll 1
                 for (int c = 0; c < BN / 64; ++c) {
                     const int nc = n0 + half * (BN / 2) + c * 32;
                     if (nc >= N) break;  // warp-uniform
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) +
                                            static_cast<uint32_t>(acc * BN + half * (BN / 2) + c * 32);
-                    epi_chunk_tma(E, &tma_c, taddr, 0xffffffffu, r, loaded, rbase, M, nc,
-                                  reinterpret_cast<uint8_t*>(E.stg), issued, &tmem_full_bar[acc], acc_phase, waited);
+                    epi_chunk_tma(E, &tma_c, &tma_d, taddr, rbase, M, nc, reinterpret_cast<uint8_t*>(E.stg), issued,
+                                  &tmem_full_bar[acc], acc_phase, waited);
                 }
             } else if (rows_here > 0) {
 #pragma unroll 1
@@ -242,11 +241,9 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, in
     if (B_MN == 0) rc = make_tmap_bf16(&tb, B, K, N, ldb, BK, BN);
     else rc = make_tmap_bf16(&tb, B, N, K, ldb, 64, BK);
     if (rc) return rc;
-    CUtensorMap tc = ta;                                   // placeholder when the TMA-store epilogue is off
-    if (ep.tma_store) {
-        rc = make_tmap_bf16(&tc, ep.out_bf16, N, M, ep.ld_bf16, 32, 32, false);
-        if (rc) return rc;
-    }
+    CUtensorMap tc = ta, td = ta;                          // placeholders when the TMA-store epilogue is off
+    if (ep.tma_store && ep.out_bf16 != nullptr && (rc = make_tmap_out(&tc, ep.out_bf16, false, N, M, ep.ld_bf16))) return rc;
+    if (ep.tma_store && ep.out_f32 != nullptr && (rc = make_tmap_out(&td, ep.out_f32, true, N, M, ep.ld_f32))) return rc;
 
     auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
     static bool attr_set = false;
@@ -277,7 +274,7 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, int M, in
     }
     const int num_units = num_tiles * splits;
     int grid = num_units < num_sms() ? num_units : num_sms();
-    kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, ep, M, N, K, splits, kb_per, a_k_period);
+    kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(ta, tb, tc, td, ep, M, N, K, splits, kb_per, a_k_period);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
     return 0;
@@ -334,10 +331,10 @@ extern "C" int b200vsgg_gemm_bf16(const void* A, int32_t lda, int32_t a_mn, cons
         ep.vec_ok = ok ? 1 : 0;
     }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    // bf16-only output without residual / accumulation / split-K: TMA-store epilogue
+    // TMA-store epilogue unless the call may split K (atomics), accumulates in place, or has residual AND mask
     static const bool tma_epi = []() { const char* v = getenv("B200VSGG_GEMM_TMA_EPI"); return !(v && v[0] == '0'); }();
-    ep.tma_store = (tma_epi && ep.out_bf16 != nullptr && ep.out_f32 == nullptr && ep.residual == nullptr && !ep.accumulate &&
-                    ep.vec_ok && e->split_k <= 1) ? 1 : 0;
+    ep.tma_store = (tma_epi && !ep.accumulate && ep.vec_ok && (N & 7) == 0 &&
+                    !(ep.residual != nullptr && ep.mask_src != nullptr)) ? 1 : 0;
     // Large problems: 256x256 tiles on CTA pairs (cta_group::2), 2/3 of the operand traffic per flop.
     if (use_2cta() && e->a_k_period == 0 && e->split_k <= 1) {
         const long long tiles2 = static_cast<long long>((M + 255) / 256) * ((N + 255) / 256);
