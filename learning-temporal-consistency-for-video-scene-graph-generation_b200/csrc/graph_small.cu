@@ -18,7 +18,7 @@
 
 namespace vsgg {
 
-constexpr int GS_NMAX = 16;       // nodes per frame (person + objects); larger frames use the generic path
+constexpr int GS_NMAX_LIMIT = 16; // nodes per frame (person + objects); larger frames use the generic path
 constexpr int GS_DMAX = 16;       // feature width (10 in the reference)
 constexpr int GS_DH = 64;         // dim_head of graph_transformer_pytorch (one rotary pair per lane)
 constexpr int GS_THREADS = 256;
@@ -69,7 +69,8 @@ __device__ __forceinline__ void gs_gate(const float* o, float* x, int n, int D, 
     }
 }
 
-__global__ void __launch_bounds__(GS_THREADS) graph_small_kernel(
+template <int GS_NMAX>
+__global__ void __launch_bounds__(GS_THREADS, (GS_NMAX <= 12 ? 2 : 1)) graph_small_kernel(
     const float* __restrict__ nodes, const uint8_t* __restrict__ upper, const int32_t* __restrict__ counts, int nmax,
     int D, int heads, int depth, const float* __restrict__ params, const float* __restrict__ pool_w,
     const float* __restrict__ pool_b, float* __restrict__ out) {
@@ -112,19 +113,30 @@ __global__ void __launch_bounds__(GS_THREADS) graph_small_kernel(
             float q[GS_NMAX][2], k[GS_NMAX][2], v[GS_NMAX][2];
 #pragma unroll
             for (int i = 0; i < GS_NMAX; ++i) {
-                if (i < n) {
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        const int e = e0 + s;
-                        float aq = __ldg(P + L.bq + e), ak = __ldg(P + L.bkv + e), av = __ldg(P + L.bkv + I + e);
-                        for (int c = 0; c < D; ++c) {
-                            const float xv = xn[i * GS_DMAX + c];
-                            aq = fmaf(xv, __ldg(P + L.wq + e * D + c), aq);
-                            ak = fmaf(xv, __ldg(P + L.wkv + e * D + c), ak);
-                            av = fmaf(xv, __ldg(P + L.wkv + (I + e) * D + c), av);
-                        }
-                        q[i][s] = aq; k[i][s] = ak; v[i][s] = av;
+                for (int s = 0; s < 2; ++s) {
+                    q[i][s] = __ldg(P + L.bq + e0 + s);
+                    k[i][s] = __ldg(P + L.bkv + e0 + s);
+                    v[i][s] = __ldg(P + L.bkv + I + e0 + s);
+                }
+            }
+            for (int c = 0; c < D; ++c) {             // weights of this lane's two channels: read once per layer
+                const float wq0 = __ldg(P + L.wq + e0 * D + c), wq1 = __ldg(P + L.wq + (e0 + 1) * D + c);
+                const float wk0 = __ldg(P + L.wkv + e0 * D + c), wk1 = __ldg(P + L.wkv + (e0 + 1) * D + c);
+                const float wv0 = __ldg(P + L.wkv + (I + e0) * D + c), wv1 = __ldg(P + L.wkv + (I + e0 + 1) * D + c);
+#pragma unroll
+                for (int i = 0; i < GS_NMAX; ++i) {
+                    if (i < n) {
+                        const float xv = xn[i * GS_DMAX + c];
+                        q[i][0] = fmaf(xv, wq0, q[i][0]); q[i][1] = fmaf(xv, wq1, q[i][1]);
+                        k[i][0] = fmaf(xv, wk0, k[i][0]); k[i][1] = fmaf(xv, wk1, k[i][1]);
+                        v[i][0] = fmaf(xv, wv0, v[i][0]); v[i][1] = fmaf(xv, wv1, v[i][1]);
                     }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < GS_NMAX; ++i) {
+                if (i < n) {
                     float sn, cs;
                     __sincosf(static_cast<float>(i) * inv_freq, &sn, &cs);   // rotary position = node index in the frame
                     const float q0 = q[i][0], q1 = q[i][1], k0 = k[i][0], k1 = k[i][1];
@@ -169,12 +181,13 @@ __global__ void __launch_bounds__(GS_THREADS) graph_small_kernel(
             }
         }
         __syncthreads();
-        for (int idx = t; idx < n * D; idx += GS_THREADS) {       // to_out: [n, I] -> [n, D]
+        for (int idx = warp; idx < n * D; idx += n_warps) {       // to_out: [n, I] -> [n, D], one warp per output
             const int i = idx / D, c = idx - i * D;
-            float acc = __ldg(P + L.bo + c);
             const float* w = P + L.wo + static_cast<size_t>(c) * I;
-            for (int e = 0; e < I; ++e) acc = fmaf(att[i * I + e], __ldg(w + e), acc);
-            o[i * GS_DMAX + c] = acc;
+            float acc = 0.f;
+            for (int e = lane; e < I; e += 32) acc = fmaf(att[i * I + e], __ldg(w + e), acc);
+            acc = warp_sum(acc);
+            if (lane == 0) o[i * GS_DMAX + c] = acc + __ldg(P + L.bo + c);
         }
         __syncthreads();
         gs_gate(o, x, n, D, P + L.g1);
@@ -225,20 +238,20 @@ extern "C" int b200vsgg_graph_small_params_per_layer(int32_t dim, int32_t heads)
 extern "C" int b200vsgg_graph_small_fwd(const float* nodes, const uint8_t* upper, const int32_t* counts, int32_t n_frames,
                                         int32_t nmax, int32_t dim, int32_t heads, int32_t depth, const float* params,
                                         const float* pool_w, const float* pool_b, float* out, void* stream) {
-    if (!nodes || !upper || !counts || !params || !pool_w || !pool_b || !out || nmax < 1 || nmax > GS_NMAX || dim < 1 ||
+    if (!nodes || !upper || !counts || !params || !pool_w || !pool_b || !out || nmax < 1 || nmax > GS_NMAX_LIMIT || dim < 1 ||
         dim > GS_DMAX || heads < 1 || heads > 16 || depth < 1)
         return set_error(B200VSGG_ERR_BAD_ARG, "graph_small_fwd: bad arg (nmax <= 16, dim <= 16, heads <= 16)");
     if (n_frames == 0) return 0;
-    const size_t smem = sizeof(float) * (3 * GS_NMAX * GS_DMAX + GS_NMAX * GS_NMAX + GS_NMAX * 4 * GS_DMAX +
-                                         static_cast<size_t>(GS_NMAX) * heads * GS_DH);
-    static size_t cur = 0;
-    if (smem > cur) {
-        cudaError_t e = cudaFuncSetAttribute(graph_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto launch = [&](auto kern, int NM) -> int {
+        const size_t smem = sizeof(float) * (3 * NM * GS_DMAX + NM * NM + NM * 4 * GS_DMAX + static_cast<size_t>(NM) * heads * GS_DH);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
-        cur = smem;
-    }
-    graph_small_kernel<<<n_frames, GS_THREADS, smem, (cudaStream_t)stream>>>(nodes, upper, counts, nmax, dim, heads, depth,
-                                                                            params, pool_w, pool_b, out);
+        kern<<<n_frames, GS_THREADS, smem, (cudaStream_t)stream>>>(nodes, upper, counts, nmax, dim, heads, depth, params,
+                                                                   pool_w, pool_b, out);
+        return 0;
+    };
+    int rc = nmax <= 12 ? launch(graph_small_kernel<12>, 12) : launch(graph_small_kernel<16>, 16);
+    if (rc) return rc;
     VSGG_CUDA_CHECK_LAUNCH();
     return 0;
 }

@@ -208,7 +208,7 @@ def cast_bf16(x, out=None, drop_p=0.0, seed=0):
 _uniform_chunks = {}
 
 
-def uniform_chunks(rows, device, chunk_rows=1024):
+def uniform_chunks(rows, device, chunk_rows=256):
     """int32 [n,3] chunk table (row_begin, row_end, group 0) covering `rows` rows (cached)."""
     key = (rows, chunk_rows, str(device))
     t = _uniform_chunks.get(key)
