@@ -313,6 +313,19 @@ def main():
                 "peak_source": peak_src, "launches_timed": len(gemm_prof),
                 "gemm_ms_per_step": gemm_ms / args.steps, "gemm_share_of_step": gemm_ms / (e0.elapsed_time(e1)),
                 "gemm_flops_per_step": flops / args.steps}
+    # DRAM traffic of the kernel from the committed `ncu --set full` capture (never measured under this run)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")) as f:
+            tr = json.load(f)
+        rep = max(tr["launches"], key=lambda l: l["shape"][0] * l["shape"][1] * l["shape"][2])
+        roofline["traffic"] = rep["traffic_bytes"] / 1e9
+        roofline["traffic_detail"] = {
+            "unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "shape_MNK": rep["shape"],
+            "algorithmic_GB": rep["algorithmic_bytes"] / 1e9, "traffic_over_algorithmic": rep["traffic_over_algorithmic"],
+            "all_captured": [[l["shape"], round(l["traffic_over_algorithmic"], 3)] for l in tr["launches"]],
+            "source": "profiles/r01_ncu_gemm_traffic.json (" + tr["source"] + ")"}
+    except Exception:
+        pass
     if args.gemm_log and rank == 0:
         agg = {}
         for (M, N, K, a_mn, b_mn, a, b) in gemm_prof:
