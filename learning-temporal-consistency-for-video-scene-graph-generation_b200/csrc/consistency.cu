@@ -122,17 +122,38 @@ __global__ void __launch_bounds__(256) graph_attn_core_kernel(const float* __res
 __global__ void gated_residual_kernel(const float* __restrict__ o, float* __restrict__ res, const float* __restrict__ w,
                                       int rows, int dim) {
     const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const bool vec = (dim & 3) == 0;       // rows are 16-byte aligned: float4 accesses
     for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
         const float* op = o + static_cast<size_t>(r) * dim;
         float* rp = res + static_cast<size_t>(r) * dim;
         float acc = 0.f;
-        for (int c = lane; c < dim; c += 32) {
-            const float w1 = __ldg(w + c), w2 = __ldg(w + dim + c), w3 = __ldg(w + 2 * dim + c);
-            acc += op[c] * (w1 + w3) + rp[c] * (w2 - w3);
+        if (vec) {
+            const int nv = dim >> 2;
+            const float4* o4 = reinterpret_cast<const float4*>(op);
+            float4* r4 = reinterpret_cast<float4*>(rp);
+            const float4* w1 = reinterpret_cast<const float4*>(w);
+            const float4* w2 = reinterpret_cast<const float4*>(w + dim);
+            const float4* w3 = reinterpret_cast<const float4*>(w + 2 * dim);
+            for (int c = lane; c < nv; c += 32) {
+                const float4 a = o4[c], b = r4[c], x1 = __ldg(w1 + c), x2 = __ldg(w2 + c), x3 = __ldg(w3 + c);
+                acc += a.x * (x1.x + x3.x) + b.x * (x2.x - x3.x) + a.y * (x1.y + x3.y) + b.y * (x2.y - x3.y) +
+                       a.z * (x1.z + x3.z) + b.z * (x2.z - x3.z) + a.w * (x1.w + x3.w) + b.w * (x2.w - x3.w);
+            }
+            acc = warp_sum(acc);
+            const float g = 1.f / (1.f + __expf(-acc)), h = 1.f - g;
+            for (int c = lane; c < nv; c += 32) {
+                const float4 a = o4[c], b = r4[c];
+                r4[c] = make_float4(a.x * g + b.x * h, a.y * g + b.y * h, a.z * g + b.z * h, a.w * g + b.w * h);
+            }
+        } else {
+            for (int c = lane; c < dim; c += 32) {
+                const float w1 = __ldg(w + c), w2 = __ldg(w + dim + c), w3 = __ldg(w + 2 * dim + c);
+                acc += op[c] * (w1 + w3) + rp[c] * (w2 - w3);
+            }
+            acc = warp_sum(acc);
+            const float g = 1.f / (1.f + __expf(-acc));
+            for (int c = lane; c < dim; c += 32) rp[c] = op[c] * g + rp[c] * (1.f - g);
         }
-        acc = warp_sum(acc);
-        const float g = 1.f / (1.f + __expf(-acc));
-        for (int c = lane; c < dim; c += 32) rp[c] = op[c] * g + rp[c] * (1.f - g);
     }
 }
 

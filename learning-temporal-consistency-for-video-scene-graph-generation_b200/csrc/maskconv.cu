@@ -276,6 +276,61 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const __nv_bfloat16* __re
     }
 }
 
+// Same for even `hin`: one thread owns a 2x2 block of input positions.  The <= 4 pooling windows that touch the block
+// are loaded once and serve all four positions (9 (window, position) combinations instead of 9 separate loads),
+// and the index arithmetic is shared: ~2x fewer instructions per output than the position-centric kernel above.
+__global__ void __launch_bounds__(256) pool_bwd2x2_kernel(const __nv_bfloat16* __restrict__ dz,
+                                                          const uint8_t* __restrict__ argmax, int n, int hin, int C,
+                                                          __nv_bfloat16* __restrict__ dy) {
+    const int hout = hin >> 1, vec = C >> 3;
+    const long long total = static_cast<long long>(n) * hout * hout * vec;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % vec) * 8;
+        long long t = i / vec;
+        const int b = static_cast<int>(t % hout); t /= hout;
+        const int a = static_cast<int>(t % hout);
+        const int p = static_cast<int>(t / hout);
+        float acc[2][2][8];
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+            for (int dw = 0; dw < 2; ++dw)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[dh][dw][j] = 0.f;
+#pragma unroll
+        for (int eh = 0; eh < 2; ++eh) {
+#pragma unroll
+            for (int ew = 0; ew < 2; ++ew) {
+                const int oh = a + eh, ow = b + ew;
+                if (oh >= hout || ow >= hout) continue;
+                const size_t o = ((static_cast<size_t>(p) * hout + oh) * hout + ow) * C + c;
+                const uint2 packed = *reinterpret_cast<const uint2*>(argmax + o);
+                float v[8];
+                load_bf16x8(dz + o, v);
+#pragma unroll
+                for (int dh = eh; dh < 2; ++dh) {          // window row oh reaches input row 2a+dh iff eh == 0 or dh == 1
+#pragma unroll
+                    for (int dw = ew; dw < 2; ++dw) {
+                        const int code = (dh - 2 * eh + 1) * 3 + (dw - 2 * ew + 1);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t word = j < 4 ? packed.x : packed.y;
+                            const int am = (word >> ((j & 3) * 8)) & 0xff;
+                            if (am == code) acc[dh][dw][j] += v[j];
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+            for (int dw = 0; dw < 2; ++dw)
+                store_bf16x8(dy + ((static_cast<size_t>(p) * hin + 2 * a + dh) * hin + 2 * b + dw) * C + c, acc[dh][dw]);
+    }
+}
+
 // z bf16 [n,hw,hw,C] -> rows [n*hw*hw, 9*C], column (kh*3+kw)*C + c, padding 1.
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __restrict__ z, int n, int hw, int C,
                                                         __nv_bfloat16* __restrict__ out) {
@@ -395,8 +450,12 @@ extern "C" int b200vsgg_pool_bwd(const void* dz, const uint8_t* argmax, int32_t 
         return set_error(B200VSGG_ERR_BAD_ARG, "pool_bwd: bad arg");
     if (n == 0) return 0;
     const long long items = static_cast<long long>(n) * hw_in * hw_in * (channels >> 3);
-    pool_bwd_kernel<<<blocks_for(items, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dz, argmax, n, hw_in, channels, (__nv_bfloat16*)dy);
+    if ((hw_in & 1) == 0)
+        pool_bwd2x2_kernel<<<blocks_for(items / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)dz, argmax, n, hw_in, channels, (__nv_bfloat16*)dy);
+    else
+        pool_bwd_kernel<<<blocks_for(items, 256 * 2), 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)dz, argmax, n, hw_in, channels, (__nv_bfloat16*)dy);
     VSGG_CUDA_CHECK_LAUNCH();
     return 0;
 }

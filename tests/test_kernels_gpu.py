@@ -393,3 +393,17 @@ def test_graph_small_kernel_matches_torch_graph_transformer(cuda_lib):
                                   gate_nn.bias.detach().contiguous())
     err = (got - ref).abs().max().item()
     assert err <= 2e-4 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("dim", [1936, 768, 10])
+def test_gated_residual_matches_torch(cuda_lib, dim):
+    """b200vsgg_gated_residual (float4 path for dim % 4 == 0, scalar otherwise) vs the GatedResidual formula."""
+    from b200vsgg import ops
+    g = torch.Generator().manual_seed(dim)
+    o, res = torch.randn(301, dim, generator=g), torch.randn(301, dim, generator=g)
+    w = torch.randn(3 * dim, generator=g) / dim ** 0.5
+    gate = torch.sigmoid(torch.cat([o, res, o - res], 1) @ w)[:, None]
+    ref = o * gate + res * (1 - gate)
+    x = res.cuda().contiguous()
+    ops.gated_residual(o.cuda().contiguous(), x, w.cuda().contiguous())
+    assert (x.cpu() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
