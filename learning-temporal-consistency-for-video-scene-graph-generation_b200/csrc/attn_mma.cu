@@ -79,12 +79,19 @@ __device__ __forceinline__ bool head_geom(const int32_t* seg_off, int unit, int 
 }
 
 // Stage rows [row0,row0+L) x aligned chunks [c_lo, c_lo+nch) of `src` into a [LP][33-chunk] tile.
-__device__ __forceinline__ void stage_tile(uint8_t* tile, const __nv_bfloat16* src, int ld, const HeadGeom& g, int lane) {
-    const uint32_t t = s_u32(tile);
-    const int total = g.L * g.nch;
-    for (int i = lane; i < total; i += 32) {
-        const int r = i / g.nch, ch = i - r * g.nch;
-        cp_async16(t + r * AM_PITCH_B + ch * 16, src + static_cast<size_t>(g.row0 + r) * ld + (g.c_lo + ch) * 8);
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const __nv_bfloat16* src, int ld, const HeadGeom& g, int lane,
+                                           int nthreads = 32) {
+    // lane = 16-byte chunk of the row (nch <= 32), warps stride over the rows: one cp.async per (thread, row) with
+    // add-only address arithmetic (a flat index with a division per chunk cost more than the copy itself)
+    const int ch = lane & 31, r0 = lane >> 5, rstep = nthreads >> 5;
+    if (ch < g.nch) {
+        const __nv_bfloat16* sp = src + static_cast<size_t>(g.row0 + r0) * ld + (g.c_lo + ch) * 8;
+        uint32_t dp = s_u32(tile) + r0 * AM_PITCH_B + ch * 16;
+        for (int r = r0; r < g.L; r += rstep) {
+            cp_async16(dp, sp);
+            sp += static_cast<size_t>(rstep) * ld;
+            dp += rstep * AM_PITCH_B;
+        }
     }
 }
 // Zero the foreign columns (before `phase`, after phase+hd) and the next chunk of rows < L, so that a
@@ -100,10 +107,11 @@ __device__ __forceinline__ void zero_slop(uint8_t* tile, const HeadGeom& g, int 
 
 // acc[mt][nt] += A[rows of m-tile mt] . B[rows of n-tile nt]^T over the d-chunks (both tiles K-major).
 template <int MT, int NT>
-__device__ __forceinline__ void qk_product(float (&acc)[MT][NT][4], const uint8_t* A, const uint8_t* B, int ksteps, int lane) {
+__device__ __forceinline__ void qk_product(float (&acc)[MT][NT][4], const uint8_t* A, const uint8_t* B, int ksteps, int lane,
+                                           int ks0 = 0) {
     const uint32_t a_base = s_u32(A) + (lane & 15) * AM_PITCH_B + (lane >> 4) * 16;
     const uint32_t b_base = s_u32(B) + ((lane & 7) + ((lane >> 4) & 1) * 8) * AM_PITCH_B + ((lane >> 3) & 1) * 16;
-    for (int ks = 0; ks < ksteps; ++ks) {
+    for (int ks = ks0; ks < ksteps; ++ks) {
         uint32_t a[MT][4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) ldsm_x4(a[mt], a_base + mt * 16 * AM_PITCH_B + ks * 32);
@@ -125,11 +133,12 @@ __device__ __forceinline__ void qk_product(float (&acc)[MT][NT][4], const uint8_
 // and columns inside the head.
 template <int MT, int KK>
 __device__ __forceinline__ void av_product_store(const uint32_t (&afrag)[MT][KK][4], const uint8_t* Bt, const HeadGeom& g,
-                                                 int hd, float out_scale, __nv_bfloat16* out, int ldo, int lane) {
+                                                 int hd, float out_scale, __nv_bfloat16* out, int ldo, int lane,
+                                                 int dg0 = 0, int dg1 = -1) {
     const uint32_t b_base = s_u32(Bt) + (lane & 15) * AM_PITCH_B + (lane >> 4) * 16;
     const int gq = lane >> 2, tq = lane & 3;
-    const int ngroups = (g.nch + 3) >> 2;
-    for (int dg = 0; dg < ngroups; ++dg) {
+    const int ngroups = dg1 < 0 ? (g.nch + 3) >> 2 : dg1;
+    for (int dg = dg0; dg < ngroups; ++dg) {
         float o[MT][4][4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
@@ -380,6 +389,226 @@ attn_mma_bwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Warp-PAIR variants for 17..32-token segments (the 2-frame temporal windows).  With one warp per unit the three /
+// four 17 KB operand tiles allow only 4 (forward) / 3 (backward) warps per SM: ncu showed 6 % / 4.7 % active warps,
+// 9 % tensor pipe, 16 % / 11.5 % of DRAM bandwidth — latency-bound with nothing to hide it.  Here two warps share
+// one unit's tiles and split the HEAD DIMENSION: each contracts half of the d-chunks for S = Q K^T (and dP = dO V^T),
+// the partial scores are exchanged through shared memory (C-fragment layout, identical in both warps), softmax is
+// done redundantly, and each warp then produces half of the output columns of P V (dQ, dK, dV).  Every product is
+// split evenly and 6 / 4 warps fit per SM.  Measured (31.8 k window tokens, dropout 0.1, tools/attn_bench.py): forward
+// 0.353 -> 0.293 ms, backward 0.870 -> 0.734 ms together with the add-only cp.async addressing of stage_tile.  The unit
+// time is still dominated by staging (issue + exposed latency, nothing prefetched) and the 4-byte output stores,
+// not by the MMAs; the next step is TMA slab staging with a prefetched second buffer.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+
+template <int MT, int NT>
+__device__ __forceinline__ void pair_exchange_add(float (&s)[MT][NT][4], float* X, int pw, int lane, int pair) {
+    float* mine = X + pw * (MT * NT * 4 * 32);
+    const float* other = X + (pw ^ 1) * (MT * NT * 4 * 32);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) mine[((mt * NT + nt) * 4 + e) * 32 + lane] = s[mt][nt][e];
+    pair_sync(pair);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s[mt][nt][e] += other[((mt * NT + nt) * 4 + e) * 32 + lane];
+}
+
+constexpr int AM_PAIR_LP = 32;
+constexpr int AM_PAIR_X = 2 * (AM_PAIR_LP / 16) * (AM_PAIR_LP / 8) * 4 * 32 * 4;   // bytes: two warps' partial scores
+
+__global__ void __launch_bounds__(192)
+attn_mma_fwd2_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
+                     const __nv_bfloat16* __restrict__ v, int ldv, const int32_t* __restrict__ seg_off, int n_units,
+                     int n_heads, int hd, float scale, __nv_bfloat16* __restrict__ ctx, int ldc, float drop_p,
+                     unsigned long long seed) {
+    constexpr int LP = AM_PAIR_LP, MT = LP / 16, NT = LP / 8, KK = LP / 16;
+    constexpr int TILE = LP * AM_PITCH_B;
+    constexpr int PER_PAIR = 3 * TILE + AM_PAIR_X;
+    extern __shared__ __align__(16) uint8_t am_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = warp >> 1, pw = warp & 1, pairs = blockDim.x >> 6, l2 = pw * 32 + lane;
+    uint8_t* Qs = am_smem + pair * PER_PAIR;
+    uint8_t* Ks = Qs + TILE;
+    uint8_t* Vs = Ks + TILE;
+    float* X = reinterpret_cast<float*>(Vs + TILE);
+    for (int i = l2; i < 3 * TILE / 16; i += 64) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0u, 0u, 0u, 0u);
+    pair_sync(pair);
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    const int gq = lane >> 2, tq = lane & 3;
+    for (int unit = blockIdx.x * pairs + pair; unit < n_units; unit += gridDim.x * pairs) {
+        HeadGeom g;
+        int head;
+        if (!head_geom(seg_off, unit, n_heads, hd, g, head)) continue;      // uniform within the pair
+        stage_tile(Qs, q, ldq, g, l2, 64);
+        stage_tile(Ks, k, ldk, g, l2, 64);
+        stage_tile(Vs, v, ldv, g, l2, 64);
+        cp_async_wait_all();
+        pair_sync(pair);
+        if (pw == 0) zero_slop(Qs, g, hd, lane);
+        pair_sync(pair);
+        float s[MT][NT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+        const int ksteps = (g.nch + 1) >> 1, kh = ksteps >> 1;
+        qk_product<MT, NT>(s, Qs, Ks, pw ? ksteps : kh, lane, pw ? kh : 0);
+        pair_exchange_add<MT, NT>(s, X, pw, lane, pair);
+        softmax_rows<MT, NT>(s, scale, g.L, lane);
+        uint32_t pa[MT][KK][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int kk = 0; kk < KK; ++kk) {
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int nt = 2 * kk + sub;
+                    float p[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int row = mt * 16 + gq + (e >> 1) * 8, col = nt * 8 + tq * 2 + (e & 1);
+                        p[e] = (row < g.L && col < g.L)
+                                   ? s[mt][nt][e] * am_drop_factor(thr, inv_keep, seed, g.row0 + row, head, col) : 0.f;
+                    }
+                    pa[mt][kk][sub * 2] = pack_bf16(p[0], p[1]);
+                    pa[mt][kk][sub * 2 + 1] = pack_bf16(p[2], p[3]);
+                }
+            }
+        const int ngroups = (g.nch + 3) >> 2, gh = (ngroups + 1) >> 1;
+        av_product_store<MT, KK>(pa, Vs, g, hd, 1.f, ctx, ldc, lane, pw ? gh : 0, pw ? ngroups : gh);
+        pair_sync(pair);          // tiles and the exchange buffer are reused by the next unit
+    }
+}
+
+__global__ void __launch_bounds__(128)
+attn_mma_bwd2_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
+                     const __nv_bfloat16* __restrict__ v, int ldv, const __nv_bfloat16* __restrict__ dctx, int ldc,
+                     const int32_t* __restrict__ seg_off, int n_units, int n_heads, int hd, float scale,
+                     __nv_bfloat16* __restrict__ dq, int lddq, __nv_bfloat16* __restrict__ dk, int lddk,
+                     __nv_bfloat16* __restrict__ dv, int lddv, float drop_p, unsigned long long seed) {
+    constexpr int LP = AM_PAIR_LP, MT = LP / 16, NT = LP / 8, KK = LP / 16;
+    constexpr int TILE = LP * AM_PITCH_B;
+    constexpr int TP = (LP + 8) * 2;
+    constexpr int SMALL = LP * TP;
+    constexpr int PER_PAIR = 4 * TILE + 2 * SMALL + 2 * AM_PAIR_X;
+    extern __shared__ __align__(16) uint8_t am_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = warp >> 1, pw = warp & 1, pairs = blockDim.x >> 6, l2 = pw * 32 + lane;
+    uint8_t* Qs = am_smem + pair * PER_PAIR;
+    uint8_t* Ks = Qs + TILE;
+    uint8_t* Vs = Ks + TILE;
+    uint8_t* Os = Vs + TILE;
+    uint8_t* Tds = Os + TILE;
+    uint8_t* Tp = Tds + SMALL;
+    float* Xp = reinterpret_cast<float*>(Tp + SMALL);
+    float* Xd = Xp + AM_PAIR_X / 4;
+    for (int i = l2; i < (4 * TILE + 2 * SMALL) / 16; i += 64) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0u, 0u, 0u, 0u);
+    pair_sync(pair);
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    const int gq = lane >> 2, tq = lane & 3;
+    for (int unit = blockIdx.x * pairs + pair; unit < n_units; unit += gridDim.x * pairs) {
+        HeadGeom g;
+        int head;
+        if (!head_geom(seg_off, unit, n_heads, hd, g, head)) continue;
+        stage_tile(Qs, q, ldq, g, l2, 64);
+        stage_tile(Ks, k, ldk, g, l2, 64);
+        stage_tile(Vs, v, ldv, g, l2, 64);
+        stage_tile(Os, dctx, ldc, g, l2, 64);
+        cp_async_wait_all();
+        pair_sync(pair);
+        if (pw == 0) zero_slop(Qs, g, hd, lane); else zero_slop(Os, g, hd, lane);
+        pair_sync(pair);
+        const int ksteps = (g.nch + 1) >> 1, kh = ksteps >> 1;
+        float p[MT][NT][4], dp[MT][NT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { p[mt][nt][e] = 0.f; dp[mt][nt][e] = 0.f; }
+        qk_product<MT, NT>(p, Qs, Ks, pw ? ksteps : kh, lane, pw ? kh : 0);
+        qk_product<MT, NT>(dp, Os, Vs, pw ? ksteps : kh, lane, pw ? kh : 0);
+        pair_exchange_add<MT, NT>(p, Xp, pw, lane, pair);
+        pair_exchange_add<MT, NT>(dp, Xd, pw, lane, pair);
+        softmax_rows<MT, NT>(p, scale, g.L, lane);
+        // identical in both warps from here to the products: both write the same values into the small tiles
+        uint32_t dsa[MT][KK][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            float delta[2] = {0.f, 0.f};
+            const int r0 = mt * 16 + gq;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                float pt[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int row = r0 + (e >> 1) * 8, col = nt * 8 + tq * 2 + (e & 1);
+                    const bool ok = row < g.L && col < g.L;
+                    const float f = ok ? am_drop_factor(thr, inv_keep, seed, g.row0 + row, head, col) : 0.f;
+                    const float pe = ok ? p[mt][nt][e] : 0.f;
+                    const float dpe = ok ? dp[mt][nt][e] * f : 0.f;
+                    delta[e >> 1] += pe * dpe;
+                    p[mt][nt][e] = pe;
+                    dp[mt][nt][e] = dpe;
+                    pt[e] = pe * f;
+                }
+                const int c = nt * 8 + tq * 2;
+                if (pw == 0) {
+                    *reinterpret_cast<uint32_t*>(Tp + r0 * TP + c * 2) = pack_bf16(pt[0], pt[1]);
+                    *reinterpret_cast<uint32_t*>(Tp + (r0 + 8) * TP + c * 2) = pack_bf16(pt[2], pt[3]);
+                }
+            }
+            delta[0] = quad_sum(delta[0]);
+            delta[1] = quad_sum(delta[1]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                float ds[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ds[e] = p[mt][nt][e] * (dp[mt][nt][e] - delta[e >> 1]);
+                const uint32_t d01 = pack_bf16(ds[0], ds[1]), d23 = pack_bf16(ds[2], ds[3]);
+                dsa[mt][nt >> 1][(nt & 1) * 2] = d01;
+                dsa[mt][nt >> 1][(nt & 1) * 2 + 1] = d23;
+                const int c = nt * 8 + tq * 2;
+                if (pw == 1) {
+                    *reinterpret_cast<uint32_t*>(Tds + r0 * TP + c * 2) = d01;
+                    *reinterpret_cast<uint32_t*>(Tds + (r0 + 8) * TP + c * 2) = d23;
+                }
+            }
+        }
+        pair_sync(pair);
+        const int ngroups = (g.nch + 3) >> 2, gh = (ngroups + 1) >> 1;
+        const int dg0 = pw ? gh : 0, dg1 = pw ? ngroups : gh;
+        av_product_store<MT, KK>(dsa, Ks, g, hd, scale, dq, lddq, lane, dg0, dg1);          // dQ = scale * dS K
+        uint32_t ta[MT][KK][4];
+        const uint32_t t_off = ((lane & 7) + ((lane >> 4) & 1) * 8) * TP + ((lane >> 3) & 1) * 16;
+#pragma unroll
+        for (int jt = 0; jt < MT; ++jt)
+#pragma unroll
+            for (int it = 0; it < KK; ++it) ldsm_x4_t(ta[jt][it], s_u32(Tds) + t_off + it * 16 * TP + jt * 32);
+        av_product_store<MT, KK>(ta, Qs, g, hd, scale, dk, lddk, lane, dg0, dg1);           // dK = scale * dS^T Q
+#pragma unroll
+        for (int jt = 0; jt < MT; ++jt)
+#pragma unroll
+            for (int it = 0; it < KK; ++it) ldsm_x4_t(ta[jt][it], s_u32(Tp) + t_off + it * 16 * TP + jt * 32);
+        av_product_store<MT, KK>(ta, Os, g, hd, 1.f, dv, lddv, lane, dg0, dg1);             // dV = P~^T dO
+        pair_sync(pair);
+    }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename Kern>
@@ -428,13 +657,13 @@ int attn_mma_fwd_try(const void* q, int ldq, const void* k, int ldk, const void*
             (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, seg_off, n_units,
             n_heads, hd, scale, (__nv_bfloat16*)ctx, ldc, drop_p, seed);
     } else {
-        constexpr int W = 4;
-        const size_t smem = (size_t)W * 3 * 32 * AM_PITCH_B;
+        constexpr int PAIRS = 3;      // 3 warp pairs x (3 tiles + exchange) = 176 KB
+        const size_t smem = (size_t)PAIRS * (3 * 32 * AM_PITCH_B + AM_PAIR_X);
         static size_t cur = 0;
-        if ((rc = ensure_smem(attn_mma_fwd_kernel<32>, smem, cur))) return rc;
-        int grid = (n_units + W - 1) / W;
+        if ((rc = ensure_smem(attn_mma_fwd2_kernel, smem, cur))) return rc;
+        int grid = (n_units + PAIRS - 1) / PAIRS;
         if (grid > am_num_sms()) grid = am_num_sms();
-        attn_mma_fwd_kernel<32><<<grid, W * 32, smem, stream>>>(
+        attn_mma_fwd2_kernel<<<grid, PAIRS * 64, smem, stream>>>(
             (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, seg_off, n_units,
             n_heads, hd, scale, (__nv_bfloat16*)ctx, ldc, drop_p, seed);
     }
@@ -469,13 +698,13 @@ int attn_mma_bwd_try(const void* q, int ldq, const void* k, int ldk, const void*
             (const __nv_bfloat16*)dctx, ldc, seg_off, n_units, n_heads, hd, scale, (__nv_bfloat16*)dq, lddq,
             (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, drop_p, seed);
     } else {
-        constexpr int W = 3, LP = 32;
-        const size_t smem = (size_t)W * (4 * LP * AM_PITCH_B + 2 * LP * (LP + 8) * 2);
+        constexpr int PAIRS = 2, LP = 32;   // 2 warp pairs x (4 tiles + 2 small tiles + 2 exchanges) = 177 KB
+        const size_t smem = (size_t)PAIRS * (4 * LP * AM_PITCH_B + 2 * LP * (LP + 8) * 2 + 2 * AM_PAIR_X);
         static size_t cur = 0;
-        if ((rc = ensure_smem(attn_mma_bwd_kernel<32>, smem, cur))) return rc;
-        int grid = (n_units + W - 1) / W;
+        if ((rc = ensure_smem(attn_mma_bwd2_kernel, smem, cur))) return rc;
+        int grid = (n_units + PAIRS - 1) / PAIRS;
         if (grid > am_num_sms()) grid = am_num_sms();
-        attn_mma_bwd_kernel<32><<<grid, W * 32, smem, stream>>>(
+        attn_mma_bwd2_kernel<<<grid, PAIRS * 64, smem, stream>>>(
             (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv,
             (const __nv_bfloat16*)dctx, ldc, seg_off, n_units, n_heads, hd, scale, (__nv_bfloat16*)dq, lddq,
             (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, drop_p, seed);
