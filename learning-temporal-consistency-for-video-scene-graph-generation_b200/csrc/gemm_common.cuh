@@ -295,7 +295,8 @@ __device__ __forceinline__ void epi_chunk_tma(const EpiRegs& E, const CUtensorMa
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-            ptx::tma_store_2d(tm_f32, box, nc, rbase);
+            if (E.atomic) ptx::tma_reduce_add_2d(tm_f32, box, nc, rbase);     // split-K / stream-K partial tile
+            else ptx::tma_store_2d(tm_f32, box, nc, rbase);
             ptx::bulk_commit();
         }
         ++issued;

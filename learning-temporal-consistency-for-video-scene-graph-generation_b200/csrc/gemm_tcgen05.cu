@@ -181,7 +181,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const int rows_here = min(32, M - rbase);      // <= 0: nothing to store for this warp
             E.use_bias = ep.bias != nullptr && (splits == 1 || split == 0);
             bool waited = false;
-            if (rows_here > 0 && ep.tma_store && splits == 1) {
+            if (rows_here > 0 && ep.tma_store) {   // split-K partial tiles: TMA reduce-add instead of per-element atomics
 #pragma unroll 1
                 for (int c = 0; c < BN / 64; ++c) {
                     const int nc = n0 + half * (BN / 2) + c * 32;

@@ -22,7 +22,7 @@ __device__ __forceinline__ float bce_row(const float* __restrict__ p, float* __r
                                          const int32_t* idx, const float* dense, int row, float w) {
     uint32_t hot = 0u;
     if (off) {
-        for (int e = off[row]; e < off[row + 1]; ++e) hot |= 1u << idx[e];
+        for (int e = off[row]; e < off[row + 1]; ++e) hot |= 1u << (idx[e] & 31);   // class ids are < C <= 32
     } else {
         for (int c = 0; c < C; ++c) hot |= (dense[static_cast<size_t>(row) * C + c] > 0.5f ? 1u : 0u) << c;
     }
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) rel_loss_kernel(
         for (int c = 0; c < ca; ++c) { x[c] = att[static_cast<size_t>(row) * ca + c]; mx = fmaxf(mx, x[c]); }
         float den = 0.f;
         for (int c = 0; c < ca; ++c) den += expf(x[c] - mx);
-        const int y = static_cast<int>(att_label[row]);
+        const int y = min(max(static_cast<int>(att_label[row]), 0), ca - 1);   // never index outside x[]
         la = w * (mx + logf(den) - x[y]);
         if (d_att)
             for (int c = 0; c < ca; ++c)
