@@ -12,9 +12,11 @@ clip hidden rows [0:n_f] (the reference's `savor` never advances, :312-314) -> G
 
 PARITY UNPINNED: GraphTransformer / GlobalAttentionPooling come from `graph_transformer_pytorch` and `dgl`,
 absent from the reference tree and unversioned there; the arithmetic restates their published algorithms
- and is checked against the oracle's restatement only.  The 768-wide projections run on
-the tcgen05 GEMM; the per-frame attention cores ([frames, 8, <=11, <=11]) and the 10-wide branch are
-batched torch ops on padded tensors (tiny, not on the roofline).
+ and is checked against the oracle's restatement only.  The 768/1936-wide semantic branch runs
+row-compacted on the tcgen05 GEMM + `graph_attn_core` / `gated_residual` kernels; the 10-wide structure branch
+(4 layers + pooling) is ONE launch of `b200vsgg_graph_small_fwd` (one CTA per frame) for frames of <= 16 nodes.
+Frames with more nodes (the 33-node long-clip config) take `run_batched` below — batched torch ops on padded
+device tensors, kept as the reference formulation the kernel is unit-tested against.
 """
 import numpy as np
 import torch
