@@ -103,3 +103,72 @@ def test_plan_rejects_empty_frames_and_single_frame_videos():
         SegmentPlan([3, 0, 2], [3])
     with pytest.raises(AssertionError):
         SegmentPlan([3, 2, 2], [1, 2])
+
+
+# ------------------------------------------------------------------------------------------------
+# SGCls object branch: class sequences (tools/utils/ds_track.py:18-39) and their positions (lib/tempura.py:186-199)
+# ------------------------------------------------------------------------------------------------
+def _reference_sequence_layout(entry):
+    """The reference's own construction (lib/tempura.py:189-199): per sequence, unique(sorted) frame counts ->
+    position = rank repeated count times; pad_sequence order = indices[1:] then the singles of indices[0]."""
+    import torch
+    from torch.nn.utils.rnn import pad_sequence
+    indices = entry["indices"]
+    pos_index = []
+    for index in indices[1:]:
+        _, counts = torch.unique(entry["boxes"][index][:, 0].view(-1), return_counts=True, sorted=True)
+        counts = counts.tolist()
+        pos_index.append(torch.cat([torch.LongTensor([im] * count) for im, count in zip(range(len(counts)), counts)]))
+    padded = pad_sequence(pos_index, batch_first=True) if pos_index else torch.zeros(0, 0, dtype=torch.long)
+    return indices, padded
+
+
+@pytest.mark.parametrize("vid,frames,ppf", [(5, 7, (2, 5)), (8, 6, (3, 4)), (31, 20, (1, 9))])
+def test_object_sequence_plan_bit_exact(vid, frames, ppf, monkeypatch):
+    import numpy as np
+    import torch
+    from b200vsgg import objbranch, ops, synthetic
+    from oracle.tempura_oracle import get_sequence as oracle_get_sequence
+    monkeypatch.setattr(ops, "upload", lambda arr, dev, dtype=None: torch.as_tensor(np.asarray(arr)))
+    e = synthetic.add_sgcls_inputs(synthetic.make_video_entry(vid, frames, ppf), vid)
+    e2 = dict(e)
+    objbranch.get_sequence(e, None, None, "sgcls")
+    oracle_get_sequence(e2, "sgcls")
+    assert len(e["indices"]) == len(e2["indices"])
+    for a, b in zip(e["indices"], e2["indices"]):
+        assert torch.equal(torch.as_tensor(a).long(), torch.as_tensor(b).long())
+    plan = objbranch.ObjSeqPlan(e["indices"], e["boxes"][:, 0].numpy()).to("cpu")
+    indices, padded = _reference_sequence_layout(e2)
+    O = e["labels"].shape[0]
+    # a permutation of the boxes: sequences first (class order), then the single-box classes
+    want_src = torch.cat([ix.long() for ix in indices[1:]] + ([indices[0].long()] if len(indices[0]) else []))
+    assert np.array_equal(plan.seq_src_h, want_src.numpy().astype(np.int32))
+    assert np.array_equal(np.sort(plan.seq_src_h), np.arange(O))
+    assert np.array_equal(plan.inv_h[plan.seq_src_h], np.arange(O))
+    lens = [len(ix) for ix in indices[1:]] + [1] * len(indices[0])
+    assert np.array_equal(plan.seq_off_h, np.concatenate([[0], np.cumsum(lens)]).astype(np.int32))
+    r = 0
+    for s, ix in enumerate(indices[1:]):
+        assert np.array_equal(plan.pos_h[r:r + len(ix)], padded[s, :len(ix)].numpy().astype(np.int32)), s
+        r += len(ix)
+    assert (plan.pos_h[r:] == 0).all()                       # single-box sequences sit at position 0 (:205-207)
+    assert plan.max_len == max(lens) and plan.S == len(lens)
+
+
+def test_collate_keeps_sequences_inside_videos():
+    import torch
+    from b200vsgg import objbranch, synthetic, tempura
+    entries = []
+    for i, (f, ppf) in enumerate([(4, (1, 3)), (6, (2, 5)), (3, 4)]):
+        e = synthetic.add_sgcls_inputs(synthetic.make_video_entry(60 + i, f, ppf), 60 + i)
+        objbranch.get_sequence(e, None, None, "sgcls")
+        entries.append(e)
+    batch = tempura.collate_entries(entries)
+    O = batch["labels"].shape[0]
+    rows = torch.cat([ix.long() for ix in batch["indices"] if len(ix) > 0])
+    assert torch.equal(rows.sort().values, torch.arange(O))
+    bounds = torch.tensor([0] + [e["labels"].shape[0] for e in entries]).cumsum(0)
+    video_of_box = torch.bucketize(torch.arange(O), bounds[1:], right=True)
+    for ix in batch["indices"][1:]:
+        assert video_of_box[ix.long()].unique().numel() == 1      # a class sequence never crosses a video
+    assert batch["distribution"].shape == (O, 36)
