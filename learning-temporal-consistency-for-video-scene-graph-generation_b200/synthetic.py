@@ -118,6 +118,34 @@ def add_sgcls_inputs(entry, video_index=0, sharpness=3.0):
     return entry
 
 
+AG_ATTENTION = ["looking_at", "not_looking_at", "unsure"]
+AG_SPATIAL = ["above", "beneath", "in_front_of", "behind", "on_the_side_of", "in"]
+AG_CONTACTING = ["carrying", "covered_by", "drinking_from", "eating", "have_it_on_the_back", "holding", "leaning_on",
+                 "lying_on", "not_contacting", "other_relationship", "sitting_on", "standing_on", "touching", "twisting",
+                 "wearing", "wiping", "writing_on"]
+
+
+def make_gt_annotation(entry):
+    """The per-frame ground-truth structure the AG dataloader hands to the evaluator (dataloader/AG/action_genome.py:
+    one list per frame = [{'person_bbox', 'frame'}, {'class', 'bbox', 'attention_relationship',
+    'spatial_relationship', 'contacting_relationship'}, ...]) rebuilt from a synthetic entry's labels."""
+    boxes, labels = entry["boxes"].cpu(), entry["labels"].cpu()
+    pair, im = entry["pair_idx"].cpu(), entry["im_idx"].cpu().long()
+    frames = []
+    for f in range(int(im.max()) + 1):
+        rows = (im == f).nonzero().flatten().tolist()
+        human = int(pair[rows[0], 0])
+        fr = [{"person_bbox": boxes[human, 1:].numpy()[None].copy(), "frame": "%s/%06d.png" % (entry.get("video_id", "v"), f)}]
+        for r in rows:
+            o = int(pair[r, 1])
+            fr.append({"class": int(labels[o]), "bbox": boxes[o, 1:].numpy().copy(),
+                       "attention_relationship": torch.tensor(entry["attention_gt"][r], dtype=torch.long),
+                       "spatial_relationship": torch.tensor(entry["spatial_gt"][r], dtype=torch.long),
+                       "contacting_relationship": torch.tensor(entry["contacting_gt"][r], dtype=torch.long)})
+        frames.append(fr)
+    return frames
+
+
 def seeded_init_(module, seed=BASE_SEED):
     """Deterministic, construction-order-independent parameter fill: every tensor of the state_dict
     is drawn from a generator keyed by (seed, crc32(name)).  Applied to the reference modules when
