@@ -71,5 +71,56 @@ def main():
     print("->", GOLDEN, "%.1f kB" % (os.path.getsize(GOLDEN) / 1e3))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--tc" not in sys.argv:
     main()
+
+
+# ------------------------------------------------------------------------------------------------
+# eval-time temporal-consistency score (tools/utils/temporal_consistency.py): golden from the unmodified reference
+# ------------------------------------------------------------------------------------------------
+TC_GOLDEN = os.path.join(ROOT, "tests", "golden", "temporal_consistency.pt")
+TC_CASES = [(3, 12), (11, 30), (21, 9)]
+
+
+def tc_prediction(vid, frames):
+    """Track-like video: every frame holds the same object slots, ground-truth labels change slowly, so the flattened
+    pair list contains runs of >= 6 equal labels for some classes (and a run that reaches the end of the list)."""
+    from b200vsgg import synthetic
+    e = synthetic.make_video_entry(vid, frames, 1)
+    for k in ("union_feat", "spatial_masks", "features"):
+        e.pop(k)
+    g = torch.Generator().manual_seed(500 + vid)
+    N = e["pair_idx"].shape[0]
+    seg = torch.arange(N) // 8
+    e["spatial_gt"] = [[int((s + vid) % 6)] for s in seg]
+    e["contacting_gt"] = [[int((s * 3 + vid) % 17), int((s + 1) % 17)] for s in seg]
+    e["labels"][e["pair_idx"][:, 1]] = 2 + (torch.arange(N) // 20) % 3          # a few classes, long stretches each
+    e["pred_labels"] = e["labels"].clone()
+    e["spatial_distribution"] = torch.sigmoid(torch.randn(N, 6, generator=g))
+    e["contacting_distribution"] = torch.sigmoid(torch.randn(N, 17, generator=g))
+    return e
+
+
+def main_tc():
+    for n in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(n, types.ModuleType(n))
+    sys.path.insert(0, REF)
+    import tools.utils.temporal_consistency as ref
+    ref.device = torch.device("cpu")            # hard-coded cuda:0 at module level (:6)
+    gold = {}
+    s, c = torch.tensor([]), torch.tensor([])
+    for vid, frames in TC_CASES:
+        pred = tc_prediction(vid, frames)
+        s, c = ref.evaluate_temp_cons(pred, s, c, "predcls")
+        gold["after_%d" % vid] = (s.clone(), c.clone())
+        print(vid, frames, "spatial intervals", len(s), "contact intervals", len(c))
+        obj_cls = pred["pred_labels"][pred["pred_labels"] != 1]
+        sgt = torch.tensor([i[0] for i in pred["spatial_gt"]])
+        gold["itv_%d" % vid] = {int(k): ref.find_consecutive_duplicates(obj_cls == k, sgt, pred["spatial_distribution"])
+                                for k in torch.unique(obj_cls)}
+    torch.save(gold, TC_GOLDEN)
+    print("->", TC_GOLDEN)
+
+
+if __name__ == "__main__" and "--tc" in sys.argv:
+    main_tc()

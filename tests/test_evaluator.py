@@ -46,3 +46,28 @@ def test_bbox_overlaps_definition():
     assert iou[0, 0] == 1.0
     assert abs(iou[0, 1] - 25.0 / (100 + 100 - 25)) < 1e-12
     assert iou[1, 1] == 0.0 and iou[2, 0] == 0.0 and iou[2, 1] == 0.0
+
+
+def test_temporal_consistency_score_matches_reference_golden():
+    """Eval-time temporal-consistency score (tools/utils/temporal_consistency.py): intervals and KL scores identical to
+    the unmodified reference, including its end-of-list interval quirk."""
+    import numpy as np
+    from make_golden_eval import TC_CASES, tc_prediction
+    from b200vsgg import temporal_consistency as tc
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "temporal_consistency.pt"), weights_only=False)
+    s, c = torch.tensor([]), torch.tensor([])
+    n_end = 0
+    for vid, frames in TC_CASES:
+        pred = tc_prediction(vid, frames)
+        labels = pred["pred_labels"].numpy()
+        obj_cls = labels[labels != 1]
+        sgt = np.asarray([i[0] for i in pred["spatial_gt"]])
+        for k, ref_itv in gold["itv_%d" % vid].items():
+            got = tc.find_consecutive_duplicates(obj_cls == k, sgt)
+            assert got == [list(map(int, iv)) for iv in ref_itv], (vid, k, got, ref_itv)
+            n_end += sum(1 for iv in got if iv[1] == len(sgt) - 1)
+        s, c = tc.evaluate_temp_cons(pred, s, c, "predcls")
+        rs, rc = gold["after_%d" % vid]
+        assert torch.equal(s, rs) and torch.equal(c, rc), vid
+    assert len(s) > 0 and len(c) > 0 and n_end > 0        # the end-of-list case is exercised
+    assert tc.evaluate_temp_cons(pred, s, c, "sgdet") == (None, None)
