@@ -172,3 +172,21 @@ def test_collate_keeps_sequences_inside_videos():
     for ix in batch["indices"][1:]:
         assert video_of_box[ix.long()].unique().numel() == 1      # a class sequence never crosses a video
     assert batch["distribution"].shape == (O, 36)
+
+
+def test_gt_label_csr_equals_trainer_multi_hot(monkeypatch):
+    """Ragged label lists -> CSR (what b200vsgg_rel_loss consumes) describe exactly the multi-hot matrices the
+    reference trainer builds with its per-pair loop (TEMPURA_train.py:181-187)."""
+    import numpy as np
+    import torch
+    from b200vsgg import ops, synthetic, tempura
+    monkeypatch.setattr(ops, "upload", lambda arr, dev, dtype=None: torch.as_tensor(np.asarray(arr)))
+    e = synthetic.make_video_entry(13, 6, (2, 6))
+    att, (s_off, s_idx), (c_off, c_idx) = tempura.gt_label_csr(e, "cpu")
+    ref_att, ref_spa, ref_con = synthetic.build_gt_tensors(e)
+    assert torch.equal(att, ref_att)
+    for (off, idx), ref in (((s_off, s_idx), ref_spa), ((c_off, c_idx), ref_con)):
+        dense = torch.zeros_like(ref)
+        rows = torch.repeat_interleave(torch.arange(ref.shape[0]), torch.diff(off.long()))
+        dense[rows, idx.long()] = 1
+        assert torch.equal(dense, ref)
