@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=32)
     ap.add_argument("--cpu-sample-videos", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lib-sample-videos", type=int, default=16, help="videos of the PyTorch-eager library baseline")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-consistency", action="store_true", help="leave out the temporal-consistency regulariser")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + --steps steps, no e2e/cpu (for ncu runs)")
@@ -139,6 +141,66 @@ def cpu_reference_rate(video_indices, frames, steps, warmup, seed=1123):
         one_pass()
     dt = time.perf_counter() - t0
     return pairs * steps / dt, dt / steps, pairs, cores, torch.get_num_threads()
+
+
+def library_baseline_rates(video_indices, frames, dev, seed=1123, passes=2):
+    """The "library baseline to beat" of SURVEY.md §2a / §8(d): the SAME modules as the CPU arm (oracle/, the
+    vectorised restatement of the reference — no per-frame Python loops or host syncs, so it is a stronger opponent
+    than the reference's own GPU code) moved to the B200 and run by PyTorch eager through cuBLAS / cuDNN / ATen:
+    fp32 with TF32 tensor cores, and bf16 autocast.  One video per forward + loss + backward like the reference
+    trainer (TEMPURA_train.py:152-225), gradients accumulated, then clip_grad_norm_(5) + torch.optim.AdamW once per
+    pass (generous: the reference steps its Python-loop AdamW after every video; no consistency regulariser — the
+    reference's TEMPURA has none).  CUDA events, outside the headline timed region.  Checker code, never product."""
+    import torch
+    import torch.nn.functional as F
+    from b200vsgg import synthetic
+    from oracle.tempura_oracle import TempuraOracle
+    model = TempuraOracle(obj_classes=synthetic.ag_object_classes(), dropout=0.1, **MODEL_KW)
+    synthetic.seeded_init_(model, seed)
+    model = model.to(dev).train()
+    for p in model.object_classifier.parameters():
+        p.requires_grad_(False)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.1)
+    entries = [synthetic.make_video_entry(i, frames, (6, 10), device=dev, big_on_device=dev) for i in video_indices]
+    labels = [synthetic.build_gt_tensors(e, dev) for e in entries]
+    pairs = sum(e["pair_idx"].shape[0] for e in entries)
+
+    def one_pass(autocast):
+        opt.zero_grad(set_to_none=True)
+        for e, (att, spa, con) in zip(entries, labels):
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                pred = model(dict(e), phase="train")
+            loss = (F.cross_entropy(pred["attention_distribution"].float(), att)
+                    + F.binary_cross_entropy(pred["spatial_distribution"].float(), spa)
+                    + F.binary_cross_entropy(pred["contacting_distribution"].float(), con))
+            loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 5.0)
+        opt.step()
+
+    out = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+    try:
+        for name, autocast in (("eager_fp32_tf32", False), ("eager_bf16_autocast", True)):
+            one_pass(autocast)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(passes):
+                one_pass(autocast)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / passes
+            out[name] = {"value": pairs / (ms * 1e-3), "unit": UNIT, "ms_per_pass": ms}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    out["sample"] = ("%d of the step's videos (%d pairs), 1 warm-up + %d timed passes per precision; oracle/tempura_oracle.py "
+                     "modules on cuda (PyTorch %s eager: cuBLAS/cuDNN/ATen), one video per forward+loss+backward, "
+                     "one clip+AdamW per pass, no regulariser" % (len(entries), pairs, passes, torch.__version__))
+    del model, opt, entries, labels
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference_arm(args):
@@ -414,6 +476,18 @@ def main():
                "sample": "%d of the step's %d videos (%d pairs), 2 timed passes after 1 warm-up, oracle/tempura_oracle.py "
                          "fwd+loss+bwd fp32 train mode, one video per forward" % (len(sample_vids), args.videos, pairs)}
 
+    # ============================== library baseline (rank 0, N = 1) ==============================
+    lib = None
+    if rank == 0 and world == 1 and not args.no_library_baseline and not args.profile:
+        try:
+            lib = library_baseline_rates(vids[:args.lib_sample_videos], args.frames, dev)
+            for k in ("eager_fp32_tf32", "eager_bf16_autocast"):
+                lib[k]["b200_value_over_this"] = value / lib[k]["value"]
+                if e2e is not None:
+                    lib[k]["b200_e2e_over_this"] = e2e["value"] / lib[k]["value"]
+        except Exception as ex:  # the baseline is a report, never a reason to lose the headline line
+            lib = {"error": "%s: %s" % (type(ex).__name__, ex)}
+
     if rank == 0:
         cfg = workload_config(args, world)
         cfg["pairs_per_step"] = int(total_pairs)
@@ -421,7 +495,7 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
                 "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu, "loss": loss_val,
+                "cpu_baseline": cpu, "library_baseline": lib, "loss": loss_val,
                 "model_tflops": 1.138e9 * value / 1e12}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -131,6 +131,12 @@ int b200vsgg_layernorm_bwd_add(const float* dy, int32_t ld_dy, const float* x, i
 int b200vsgg_cast_dropout_bf16(const float* x, int32_t ld_x, int32_t rows, int32_t cols, void* out, int32_t ld_o,
                                float drop_p, uint64_t seed, void* stream);
 
+/* Split-precision operand copy for the predicate-head GEMM (tools/utils/gmm_heads.py:37-76, one packed
+ * [N,1936]x[1936,330] product): out[r] = [hi | lo | hi] (3*cols bf16), hi = bf16(x), lo = bf16(x - hi); against
+ * [W_hi | W_hi | W_lo] the tensor-core product equals the fp32 one to ~2^-17. */
+int b200vsgg_split3_bf16(const float* x, int32_t ld_x, int32_t rows, int32_t cols, void* out, int32_t ld_o,
+                         void* stream);
+
 /* out[g, c] += sum over rows r with group_idx[r]==g of x[r,c]  (bias / position-embedding grads). */
 int b200vsgg_colsum(const void* x, int32_t x_is_bf16, int32_t ld_x, int32_t rows, int32_t cols,
                     const int32_t* group_idx /* nullable */, int32_t n_groups /* 1 or 2 */, float* out, void* stream);

@@ -30,6 +30,7 @@ SIGNATURES = {
     "b200vsgg_layernorm_bwd": [vp, i32, vp, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, vp],
     "b200vsgg_layernorm_bwd_add": [vp, i32, vp, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, f32, u64, vp, vp, vp, vp, i32],
     "b200vsgg_cast_dropout_bf16": [vp, i32, i32, i32, vp, i32, f32, u64, vp],
+    "b200vsgg_split3_bf16": [vp, i32, i32, i32, vp, i32, vp],
     "b200vsgg_colsum": [vp, i32, i32, i32, i32, vp, i32, vp, vp],
     "b200vsgg_attn_small_fwd": [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, f32, vp, i32, f32, u64, vp],
     "b200vsgg_attn_small_bwd": [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, f32, vp, i32, vp, i32,

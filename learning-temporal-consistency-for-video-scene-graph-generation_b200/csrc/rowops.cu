@@ -348,6 +348,32 @@ __global__ void cast_dropout_kernel(const float* __restrict__ x, int ld_x, int r
     }
 }
 
+// Split-precision operand copy: out[r] = [ hi | lo | hi ] (3 * cols bf16) with hi = bf16(x), lo = bf16(x - hi), so that
+// a bf16 tensor-core GEMM against [ W_hi | W_hi | W_lo ] evaluates x.W to ~2^-17 relative (the hi*hi, lo*hi and
+// hi*lo terms; lo*lo ~ 2^-18 is dropped).  Used for the predicate-head GEMM (tools/utils/gmm_heads.py:37-76):
+// 0.1 % of the step's flops, but its logits feed softmax / sigmoid outputs compared at 1e-3.
+__global__ void split3_bf16_kernel(const float* __restrict__ x, int ld_x, int rows, int cols,
+                                   __nv_bfloat16* __restrict__ out, int ld_o) {
+    const int nvec = cols >> 2;
+    const long long total = static_cast<long long>(rows) * nvec;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / nvec), c = static_cast<int>(i % nvec);
+        const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * ld_x + c * 4);
+        float hi[4] = {v.x, v.y, v.z, v.w}, lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float h = __bfloat162float(__float2bfloat16_rn(hi[j]));
+            lo[j] = hi[j] - h;
+            hi[j] = h;
+        }
+        __nv_bfloat16* o = out + static_cast<size_t>(r) * ld_o + c * 4;
+        store_bf16x4(o, hi);
+        store_bf16x4(o + cols, lo);
+        store_bf16x4(o + 2 * cols, hi);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // column sums of a bf16 or fp32 [rows, cols] matrix into fp32 out[group, cols] (+=), where
 // group = group_idx[row] (or 0).  Used for bias gradients and the position-embedding gradient.
@@ -499,6 +525,17 @@ extern "C" int b200vsgg_cast_dropout_bf16(const float* x, int32_t ld_x, int32_t 
     if (rows == 0) return 0;
     cast_dropout_kernel<<<grid_for(static_cast<long long>(rows) * (cols / 4), 256), 256, 0, (cudaStream_t)stream>>>(
         x, ld_x, rows, cols, (__nv_bfloat16*)out, ld_o, drop_p, seed);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200vsgg_split3_bf16(const float* x, int32_t ld_x, int32_t rows, int32_t cols, void* out, int32_t ld_o,
+                                    void* stream) {
+    if (!x || !out || cols <= 0 || (cols & 3) || ld_o < 3 * cols)
+        return set_error(B200VSGG_ERR_BAD_ARG, "split3_bf16: cols % 4 != 0 or ld_o < 3 * cols");
+    if (rows == 0) return 0;
+    split3_bf16_kernel<<<grid_for(static_cast<long long>(rows) * (cols / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        x, ld_x, rows, cols, (__nv_bfloat16*)out, ld_o);
     VSGG_CUDA_CHECK_LAUNCH();
     return 0;
 }

@@ -205,6 +205,17 @@ def cast_bf16(x, out=None, drop_p=0.0, seed=0):
     return out
 
 
+def split3_bf16(x, out=None):
+    """[rows, cols] fp32 -> [rows, 3*cols] bf16 = (hi | lo | hi), hi + lo == x to ~2^-17 (b200vsgg_split3_bf16)."""
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty(rows, 3 * cols, dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().b200vsgg_split3_bf16(_ptr(_f32(x)), x.stride(0), rows, cols, _ptr(_bf(out)), out.stride(0),
+                                           _stream()), "split3_bf16")
+    _count()
+    return out
+
+
 _uniform_chunks = {}
 
 

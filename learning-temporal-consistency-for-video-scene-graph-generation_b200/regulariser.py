@@ -14,14 +14,14 @@ PARITY UNPINNED: GraphTransformer / GlobalAttentionPooling come from `graph_tran
 absent from the reference tree and unversioned there; the arithmetic restates their published algorithms
  and is checked against the oracle's restatement only.  The 768/1936-wide semantic branch runs
 row-compacted on the tcgen05 GEMM + `graph_attn_core` / `gated_residual` kernels; the 10-wide structure branch
-(4 layers + pooling) is ONE launch of `b200vsgg_graph_small_fwd` (one CTA per frame) for frames of <= 16 nodes.
-Frames with more nodes (the 33-node long-clip config) take `run_batched` below — batched torch ops on padded
-device tensors, kept as the reference formulation the kernel is unit-tested against.
+(4 layers + pooling) is ONE launch of `b200vsgg_graph_small_fwd` (one CTA per frame).  Both kernels hold a frame's
+graph on chip: frames with more than MAX_NODES_STRUCT / MAX_NODES_SEM nodes (person + objects) RAISE — there is no
+eager-PyTorch or CPU route around the kernels (Action Genome frames have <= 10 annotated objects; the regulariser is
+train-only, so the 33-node long-clip inference config never reaches it).
 """
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 
@@ -51,7 +51,8 @@ class _GatedResidual(nn.Module):
 
 class GraphTransformer(nn.Module):
     """Parameters of graph_transformer_pytorch.GraphTransformer(dim, depth, edge_dim=1, with_feedforwards=True,
-    gated_residual=True, rel_pos_emb=True) (defaults dim_head 64, heads 8); evaluation in `run_batched`."""
+    gated_residual=True, rel_pos_emb=True) (defaults dim_head 64, heads 8); evaluated by `run_compact` (wide graphs)
+    or b200vsgg_graph_small_fwd (the 10-wide structure branch)."""
 
     def __init__(self, dim, depth, dim_head=64, heads=8, edge_dim=1):
         super().__init__()
@@ -64,78 +65,8 @@ class GraphTransformer(nn.Module):
                                _GatedResidual(dim)])]))
 
 
-def _linear(x, lin):
-    """y = x W^T + b on [rows, in]; tcgen05 GEMM when the shapes allow TMA (in % 8 == 0), else torch (10-wide)."""
-    w, b = lin.weight, lin.bias
-    if x.is_cuda and w.shape[1] % 8 == 0 and w.shape[0] % 8 == 0:
-        out = torch.empty(x.shape[0], w.shape[0], device=x.device, dtype=torch.float32)
-        ops.gemm(ops.cast_bf16(x.contiguous()), ops.cast_bf16(w.detach().contiguous()),
-                 bias=b.detach() if b is not None else None, out_f32=out)
-        return out
-    return F.linear(x, w, b)
-
-
-def _rotary(n, dim_head, device):
-    inv = 1.0 / (10000 ** (torch.arange(0, dim_head, 2, device=device).float() / dim_head))
-    freqs = torch.einsum("i,j->ij", torch.arange(n, device=device).float(), inv)
-    return torch.repeat_interleave(freqs, 2, dim=-1)           # [n, dim_head]
-
-
-def _rot_half(x):
-    x = x.reshape(*x.shape[:-1], -1, 2)
-    x1, x2 = x.unbind(-1)
-    return torch.stack((-x2, x1), -1).flatten(-2)
-
-
-def _attention_core(q, k, v, a, adj, key_ok, cos, sin):
-    """q,k,v [B,h,n,dh] -> [B,h,n,dh]: rotary on q/k, per-edge key/value offsets e_ij = A_ij*we + be."""
-    h, dh = a.heads, a.dim_head
-    q = q * cos + _rot_half(q) * sin
-    k = k * cos + _rot_half(k) * sin
-    we = a.edges_to_kv.weight[:, 0].view(h, dh)
-    be = a.edges_to_kv.bias.view(h, dh)
-    qw = (q * we[None, :, None, :]).sum(-1)                         # [B, h, n]
-    qb = (q * be[None, :, None, :]).sum(-1)
-    sim = (q @ k.transpose(-1, -2) + qw[..., None] * adj[:, None] + qb[..., None]) * (dh ** -0.5)
-    sim = sim.masked_fill(~key_ok[:, None, None, :], float("-inf"))
-    att = sim.softmax(-1)
-    return att @ v + (att * adj[:, None]).sum(-1, keepdim=True) * we[None, :, None, :] + be[None, :, None, :]
-
-
-def _gate(out, res, proj_w):
-    """GatedResidual: sigmoid(W [out, res, out-res]) folded into two dot products."""
-    d = out.shape[-1]
-    w1, w2, w3 = proj_w[0, :d], proj_w[0, d:2 * d], proj_w[0, 2 * d:]
-    g = torch.sigmoid(out @ (w1 + w3) + res @ (w2 - w3))[..., None]
-    return out * g + res * (1 - g)
-
-
-@torch.no_grad()
-def run_batched(gt, nodes, adj, counts):
-    """nodes [B, n, dim] (zero padded), adj [B, n, n] (edge feature = adjacency value), counts [B] -> [B, n, dim].
-    Wide graphs (dim % 8 == 0, CUDA) run row-compacted: LayerNorm and every projection through the C-ABI
-    kernels (bf16 operands, GELU fused in the GEMM epilogue); the 10-wide structure branch stays in torch."""
-    B, n, dim = nodes.shape
-    h, dh = gt.heads, gt.dim_head
-    dev = nodes.device
-    key_ok = (torch.arange(n, device=dev)[None, :] < counts[:, None])                   # [B, n]
-    fr = _rotary(n, dh, dev)
-    cos, sin = fr.cos()[None, None], fr.sin()[None, None]
-    if True:
-        x = nodes
-        for attn_block, ff_block in gt.layers:
-            pre, gate = attn_block
-            a = pre.fn
-            flat = F.layer_norm(x, (dim,), pre.norm.weight, pre.norm.bias).reshape(B * n, dim)
-            q = F.linear(flat, a.to_q.weight, a.to_q.bias).view(B, n, h, dh).permute(0, 2, 1, 3)
-            kv = F.linear(flat, a.to_kv.weight, a.to_kv.bias).view(B, n, 2, h, dh)
-            out = _attention_core(q, kv[:, :, 0].permute(0, 2, 1, 3), kv[:, :, 1].permute(0, 2, 1, 3), a, adj, key_ok, cos, sin)
-            out = F.linear(out.permute(0, 2, 1, 3).reshape(B * n, h * dh), a.to_out.weight, a.to_out.bias).view(B, n, dim)
-            x = _gate(out, x, gate.proj[0].weight)
-            pre2, gate2 = ff_block
-            xn = F.layer_norm(x, (dim,), pre2.norm.weight, pre2.norm.bias)
-            x = _gate(pre2.fn[2](F.gelu(pre2.fn[0](xn))), x, gate2.proj[0].weight)
-        return x
+MAX_NODES_STRUCT = 16   # b200vsgg_graph_small_fwd: q/k/v of every node of a frame live in one warp's registers
+MAX_NODES_SEM = 32      # b200vsgg_graph_attn_core: lane j of a warp keeps the score of key j
 
 
 def pack_small_params(gt):
@@ -195,14 +126,6 @@ def _pool_compact(x, frame_of_row, n_frames, gate_nn):
     return torch.zeros(n_frames, x.shape[1], device=x.device).index_add_(0, frame_of_row, (w / den[frame_of_row])[:, None] * x)
 
 
-def _pool(x, counts, gate_nn):
-    """dgl GlobalAttentionPooling: softmax over the frame's nodes of gate_nn(x), weighted sum -> [B, dim]."""
-    n = x.shape[1]
-    ok = torch.arange(n, device=x.device)[None, :] < counts[:, None]
-    gate = gate_nn(x).squeeze(-1).masked_fill(~ok, float("-inf")).softmax(-1)
-    return (gate[..., None] * x).sum(1)
-
-
 @torch.no_grad()
 def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_flags, hidden, clip_first_row=None,
                        clip_rows=None, flags_host=None):
@@ -227,10 +150,14 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
     x = hidden[src_t]
     if not valid.all():
         x = x * up_(valid.astype(np.float32))[:, None]
-    wide = hidden.is_cuda and hidden.shape[1] % 8 == 0 and nmax <= 32
-    if wide:
-        sem_rows = run_compact(gat_semantic, x, plan.node_off, spatial_flags, nmax)
-        sem = _pool_compact(sem_rows, frame_of_row, F_, gate_sem_nn)
+    if not hidden.is_cuda:
+        raise RuntimeError("consistency_losses runs only on CUDA tensors (no CPU fallback for the hot path)")
+    if nmax > MAX_NODES_STRUCT or nmax > MAX_NODES_SEM or gat.dim > 16 or gat.dim_head != 64 or hidden.shape[1] % 8:
+        raise RuntimeError("consistency regulariser: a frame has %d nodes / widths (%d, %d); the on-chip graph kernels "
+                           "take <= %d nodes per frame, structure width <= 16, semantic width %% 8 == 0 (no eager "
+                           "fallback)" % (nmax, gat.dim, hidden.shape[1], min(MAX_NODES_STRUCT, MAX_NODES_SEM)))
+    sem_rows = run_compact(gat_semantic, x, plan.node_off, spatial_flags, nmax)
+    sem = _pool_compact(sem_rows, frame_of_row, F_, gate_sem_nn)
     # ---- R1: per-frame Laplacian eigenvectors on the host (the reference's LAPACK call), grouped by node count;
     #      this runs while the device works on the semantic branch
     if flags_host is not None:        # (pinned host copy, event): the D2H was issued before the main path
@@ -269,21 +196,10 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
             list(pool.map(solve, jobs))
     counts = up_(counts_h)
     nodes = up_(ev)
-    small = hidden.is_cuda and nmax <= 16 and gat.dim <= 16 and gat.dim_head == 64
-    if not (small and wide):
-        adj = up_(A.astype(np.float32))
-    if small:
-        # R1 in one launch: 4-layer GraphTransformer(dim 10) + attention pooling, one CTA per frame
-        sym = ops.graph_small_fwd(nodes, spatial_flags.contiguous(), counts.int(), gat.dim, gat.heads, len(gat.layers),
-                                  pack_small_params(gat), gate_nn.weight.detach().reshape(-1).contiguous(),
-                                  gate_nn.bias.detach().contiguous())
-    else:
-        sym = _pool(run_batched(gat, nodes, adj, counts), counts, gate_nn)               # [F, 10]
-    if not wide:
-        ar = torch.arange(nmax, device=dev)
-        pad_rows = (up_(plan.node_off_h[:-1])[:, None] + ar[None, :]).clamp(max=n_nodes - 1)
-        ok = ar[None, :] < counts[:, None]
-        sem = _pool(run_batched(gat_semantic, x[pad_rows] * ok[..., None], adj, counts), counts, gate_sem_nn)
+    # R1 in one launch: 4-layer GraphTransformer(dim 10) + attention pooling, one CTA per frame
+    sym = ops.graph_small_fwd(nodes, spatial_flags.contiguous(), counts.int(), gat.dim, gat.heads, len(gat.layers),
+                              pack_small_params(gat), gate_nn.weight.detach().reshape(-1).contiguous(),
+                              gate_nn.bias.detach().contiguous())
     # ---- R3: all frame pairs u < v inside each clip, reference order
     pu, pv = [], []
     frames_pc = np.bincount(plan.clip_of_frame, minlength=plan.n_clips)

@@ -490,13 +490,21 @@ class _HeadsFn(torch.autograd.Function):
         cols = Wp.shape[0]
         cols_pad = (cols + HEAD_COLS_PAD - 1) // HEAD_COLS_PAD * HEAD_COLS_PAD
         dev = feat.device
-        fb = ops.cast_bf16(feat.contiguous())
-        Wb = torch.zeros(cols_pad, Wp.shape[1], device=dev, dtype=torch.bfloat16)
-        ops.cast_bf16(Wp.contiguous(), out=Wb[:cols])
+        # Split-precision product (SURVEY.md "fp32-accumulated logits ... max-abs <= 1e-3"): the head logits feed
+        # softmax / sigmoid outputs that are compared at 1e-3, and a plain bf16 x bf16 product costs ~6e-4 of that
+        # budget by itself (tools/parity_breakdown.py).  x = hi + lo, W = hi + lo, z = hi.hi + lo.hi + hi.lo as ONE
+        # tcgen05 GEMM with K' = 3K over [hi|lo|hi] x [W_hi|W_hi|W_lo] — 0.3 % of the step's flops.
+        K_in = Wp.shape[1]
+        fb3 = ops.split3_bf16(feat.contiguous())
+        fb = fb3[:, :K_in]                                   # bf16(feat): operand of the weight-gradient GEMM
+        Wf = torch.zeros(cols_pad, K_in, device=dev)
+        Wf[:cols] = Wp.detach()
+        Wb = Wf.to(torch.bfloat16)
+        Wb3 = torch.cat([Wb, Wb, (Wf - Wb.float()).to(torch.bfloat16)], 1)
         bias = torch.zeros(cols_pad, device=dev)
         bias[:cols] = bp
         z = torch.empty(N, cols_pad, device=dev)
-        ops.gemm(fb, Wb, bias=bias, out_f32=z)
+        ops.gemm(fb3, Wb3, bias=bias, out_f32=z)
         bases, b = [], 0
         for C in Cs:
             bases.append(b)

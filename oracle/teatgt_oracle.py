@@ -310,39 +310,99 @@ class TeatgtOracle(nn.Module):
     # ------------------------------------------------------------------------------------- R1-R3
     def regulariser(self, clip_frames, spatial_uv, hidden):
         """lib/teatgt.py:285-334 (UNPINNED third-party arithmetic, see header)."""
-        f0 = int(clip_frames.min())
-        sym, sem = [], []
-        for i, (su, sv) in enumerate(spatial_uv):
-            nf = int((clip_frames == f0 + i).sum())
-            A = np.zeros((nf, nf))
-            if su:
-                np.add.at(A, (np.asarray(sv), np.asarray(su)), 1.0)
-            deg = torch.bincount(torch.tensor(sv, dtype=torch.int64), minlength=nf) if su else torch.zeros(nf, dtype=torch.int64)
-            Nm = np.diag(deg.clip(1) ** -0.5)
-            L = np.eye(nf) - Nm @ A @ Nm
-            _, vec = np.linalg.eigh(L)
-            vec = torch.tensor(vec).type(torch.float32)
-            k = 10
-            ev = vec.repeat(1, int(k / 2))[:, :k] if k > nf else vec[:, :k]
-            nodes = ev[None]
-            edges = torch.tensor(A.reshape(1, nf, nf, -1)).type(torch.float32)
-            node_sem = hidden[0:nf]                                  # `savor` never advances (quirk kept)
-            no, _ = self.gat(nodes, edges)
-            so, _ = self.gat_semantic(node_sem[None], edges)
-            no, so = no.squeeze(0), so.squeeze(0)
-            sym.append((torch.softmax(self.gate_nn(no), 0) * no).sum(0, keepdim=True))
-            sem.append((torch.softmax(self.gate_sem_nn(so), 0) * so).sum(0, keepdim=True))
-        s_out, m_out = [], []
-        kl = nn.KLDivLoss(reduction="batchmean")
-        for u in range(len(sym)):
-            for v in range(u + 1, len(sym)):
-                sc = kl(F.log_softmax(sym[u], 1), F.softmax(sym[v], 1)) / (v - u)
-                ms = kl(F.log_softmax(sem[u], 1), F.softmax(sem[v], 1)) / (v - u)
-                if sc >= 0:
-                    s_out.append(sc)
-                if ms >= 0:
-                    m_out.append(ms)
-        return s_out, m_out
+        return regulariser_clip(self.gat, self.gat_semantic, self.gate_nn, self.gate_sem_nn, clip_frames, spatial_uv,
+                                hidden)
+
+
+def regulariser_clip(gat, gat_semantic, gate_nn, gate_sem_nn, clip_frames, spatial_uv, hidden):
+    """lib/teatgt.py:285-334 for one clip: per-frame structure / semantic graph embeddings, then KL / frame distance
+    over all frame pairs u < v, kept where >= 0.  `hidden` = the clip's feature rows; the semantic graph of every
+    frame reads hidden[0:n_f] (`savor` never advances, :312-314).  If the clip owns fewer than n_f rows (possible
+    only in the TEMPURA extension, where a clip's rows are its PAIRS while a frame has pairs + 1 nodes) the missing
+    rows are zeros."""
+    f0 = int(clip_frames.min())
+    sym, sem = [], []
+    for i, (su, sv) in enumerate(spatial_uv):
+        nf = int((clip_frames == f0 + i).sum())
+        A = np.zeros((nf, nf))
+        if su:
+            np.add.at(A, (np.asarray(sv), np.asarray(su)), 1.0)
+        deg = torch.bincount(torch.tensor(sv, dtype=torch.int64), minlength=nf) if su else torch.zeros(nf, dtype=torch.int64)
+        Nm = np.diag(deg.clip(1) ** -0.5)
+        L = np.eye(nf) - Nm @ A @ Nm
+        _, vec = np.linalg.eigh(L)
+        vec = torch.tensor(vec).type(torch.float32)
+        k = 10
+        ev = vec.repeat(1, int(k / 2))[:, :k] if k > nf else vec[:, :k]
+        nodes = ev[None]
+        edges = torch.tensor(A.reshape(1, nf, nf, -1)).type(torch.float32)
+        node_sem = hidden[0:nf]                                  # `savor` never advances (quirk kept)
+        if node_sem.shape[0] < nf:
+            node_sem = torch.cat([node_sem, node_sem.new_zeros(nf - node_sem.shape[0], node_sem.shape[1])], 0)
+        no, _ = gat(nodes, edges)
+        so, _ = gat_semantic(node_sem[None], edges)
+        no, so = no.squeeze(0), so.squeeze(0)
+        sym.append((torch.softmax(gate_nn(no), 0) * no).sum(0, keepdim=True))
+        sem.append((torch.softmax(gate_sem_nn(so), 0) * so).sum(0, keepdim=True))
+    s_out, m_out = [], []
+    kl = nn.KLDivLoss(reduction="batchmean")
+    for u in range(len(sym)):
+        for v in range(u + 1, len(sym)):
+            sc = kl(F.log_softmax(sym[u], 1), F.softmax(sym[v], 1)) / (v - u)
+            ms = kl(F.log_softmax(sem[u], 1), F.softmax(sem[v], 1)) / (v - u)
+            if sc >= 0:
+                s_out.append(sc)
+            if ms >= 0:
+                m_out.append(ms)
+    return s_out, m_out
+
+
+def tempura_consistency(entry, rel_feats, gat, gat_semantic, gate_nn, gate_sem_nn):
+    """Restatement of the build's TEMPURA EXTENSION (SURVEY.md A.3 #8 — the reference's lib/tempura.py never fills
+    the *_temp_loss keys its trainer reads): the TEAT-GT regulariser R1-R3 unchanged on ONE video's graphs —
+    5-frame clips, nodes per frame = person + objects in pair order, spatial edges by box-centre distance
+    (lib/teatgt.py:199-209), structure branch on Laplacian eigenvectors, semantic branch on the clip's relation
+    feature rows `rel_feats[pairs of the clip]` in place of TokenGT's hidden_x.  Returns two lists of scalars."""
+    lay = node_layout(entry)
+    box = entry["boxes"][lay["feat_row"]][:, 1:]
+    centers = torch.stack([(box[:, 0] + box[:, 2]) / 2, (box[:, 1] + box[:, 3]) / 2], 1)
+    thr = edge_threshold(entry["video_size"])
+    frames = lay["frame"]
+    pair_frame = entry["im_idx"].to(torch.int64)
+    n_clips = math.ceil((int(frames.max()) + 1) / CLIP_SIZE)
+    s_all, m_all = [], []
+    for c in range(n_clips):
+        sel = ((frames >= c * CLIP_SIZE) & (frames < (c + 1) * CLIP_SIZE)).nonzero().flatten()
+        if sel.numel() == 0:
+            continue
+        cf, cc = frames[sel], centers[sel]
+        # temporal edges play no role here: orthogonal dummy tokens keep build_clip_graph from adding any
+        _, _, spatial_uv = _spatial_only(cf, cc, thr)
+        rows = ((pair_frame >= c * CLIP_SIZE) & (pair_frame < (c + 1) * CLIP_SIZE)).nonzero().flatten()
+        s, m = regulariser_clip(gat, gat_semantic, gate_nn, gate_sem_nn, cf, spatial_uv, rel_feats[rows])
+        s_all += s
+        m_all += m
+    return s_all, m_all
+
+
+def _spatial_only(frames, centers, edge_thr):
+    """The spatial half of build_clip_graph (lib/teatgt.py:199-209): per frame, frame-local (u, v) edge lists."""
+    thr = torch.tensor(edge_thr, dtype=torch.float32)
+    out = []
+    for f in range(int(frames.min()), int(frames.max()) + 1):
+        idx = (frames == f).nonzero().flatten()
+        n = idx.numel()
+        su, sv = [], []
+        if n > 1:
+            c = centers[idx]
+            iu, iv = torch.triu_indices(n, n, offset=1)
+            dist = torch.sqrt((c[iu, 0] - c[iv, 0]) ** 2 + (c[iu, 1] - c[iv, 1]) ** 2)
+            keep = dist <= thr
+            for a, b in zip(iu[keep].tolist(), iv[keep].tolist()):
+                su += [a, b]
+                sv += [b, a]
+        out.append((su, sv))
+    return None, None, out
 
 
 def teatgt_losses(pred, attention_label, spatial_label, contact_label):

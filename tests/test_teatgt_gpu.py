@@ -2,7 +2,8 @@
 UNMODIFIED reference (tests/golden/teatgt_*.pt) and against the CPU oracle, forward and backward.
 
 Stated tolerances (bf16 operands, fp32 accumulation, fp32 residual stream, 12 pre-LN layers):
-  distributions   max-abs <= 5e-3, identical top-1 wherever the reference's margin exceeds the tolerance
+  distributions   max-abs <= DIST_TOL, and the full predicate ranking of every pair (each adjacent pair of the
+                  reference ranking whose gap exceeds the tolerance keeps its order, k = all classes)
   edge lists      bit-exact (edge_index / edge_data per clip, reference order)
   gradients       rel-L2 <= 6e-2 per parameter tensor (<= 1e-1 for q_proj / k_proj, see QK_GRAD_REL_TOL)
 """
@@ -12,9 +13,11 @@ import types
 import pytest
 import torch
 
+from _parity import check_full_ranking
+
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-DIST_TOL = 5e-3
+DIST_TOL = 1e-3
 GRAD_REL_TOL = 6e-2
 QK_GRAD_REL_TOL = 1e-1   # q/k projections: gradients flow only through the softmax Jacobian of near-uniform
                          # attention (tiny, cancellation-prone), so bf16 noise is relatively larger there
@@ -63,16 +66,18 @@ def test_forward_matches_reference_golden(pair, name):
         got, ref = out[k].float().cpu(), gold["test/" + k]
         err = (got - ref).abs().max().item()
         assert err <= DIST_TOL, (k, err)
-        top2 = ref.topk(2, dim=1).values
-        sure = (top2[:, 0] - top2[:, 1]) > 2 * DIST_TOL
-        assert torch.equal(got.argmax(1)[sure], ref.argmax(1)[sure])
+        check_full_ranking(got, ref, DIST_TOL)
 
 
-def test_backward_matches_oracle(pair):
+@pytest.mark.parametrize("case", [dict(video_index=7, num_frames=8, pairs_per_frame=(2, 5)),
+                                  dict(video_index=9, num_frames=32, pairs_per_frame=(6, 10))],
+                         ids=["8f_2-5p", "32f_6-10p"])
+def test_backward_matches_oracle(pair, case):
+    """Forward distributions, losses, regulariser values and parameter gradients vs the oracle; the second case is
+    one video of the headline shape (32 frames, 6-10 pairs per frame: 7 clips of ~45 nodes / ~450 tokens)."""
     from b200vsgg import synthetic
     from oracle.teatgt_oracle import teatgt_losses
     m, o = pair
-    case = dict(video_index=7, num_frames=8, pairs_per_frame=(2, 5))
     entry = _entry(case)
     att, spa, con = synthetic.build_gt_tensors(entry)
     o.train()
@@ -89,6 +94,12 @@ def test_backward_matches_oracle(pair):
     lm.backward()
     m.dropout_p, m.eig_dropout = 0.1, 0.2
     assert abs(lm.item() - lo.item()) < 2e-3 * abs(lo.item()), (lm.item(), lo.item())
+    for k in ("attention_distribution", "spatial_distribution", "contacting_distribution"):
+        got, ref = pm[k].detach().float().cpu(), po[k].detach()
+        err = (got - ref).abs().max().item()
+        print(k, "max-abs err %.3e" % err)
+        assert err <= DIST_TOL, (k, err)
+        check_full_ranking(got, ref, DIST_TOL)
     # consistency regulariser (R1-R3; unpinned third-party arithmetic -> compared with the oracle's restatement):
     # same number of frame pairs, values within 5 % (bf16 GEMMs in the 768-wide branch) + 1e-6 absolute
     for key in ("structure_temp_loss", "semantic_temp_loss"):
@@ -96,7 +107,8 @@ def test_backward_matches_oracle(pair):
         # the reference keeps a pair only if its KL >= 0: pairs whose embeddings coincide (KL = +-1e-9, common
         # because `savor` never advances) fall on either side of the filter, so compare the non-trivial values
         assert got.numel() > 0 and abs(got.numel() - ref.numel()) <= 4, (key, got.shape, ref.shape)
-        gs, rs = got[got > 1e-6].sort().values, ref[ref > 1e-6].sort().values
+        floor = max(1e-6, 1e-3 * ref.abs().max().item())
+        gs, rs = got[got > floor].sort().values, ref[ref > floor].sort().values
         assert gs.shape == rs.shape, (key, gs.shape, rs.shape)
         if rs.numel():
             assert (gs - rs).abs().max().item() <= 5e-2 * rs.abs().max().item() + 1e-6, (key, gs[:6], rs[:6])

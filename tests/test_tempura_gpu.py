@@ -3,21 +3,24 @@
   (2) the CPU oracle on the same seeded inputs, forward and backward, single video and batches.
 
 Stated tolerances (bf16 tensor-core operands, fp32 accumulation, fp32 residual stream):
-  distributions (probabilities in [0,1])   max-abs <= 4e-3
+  distributions (probabilities in [0,1])   max-abs <= 1e-3 (BASELINE.json north_star), and the FULL predicate
+                                           ranking of every pair: each adjacent pair of the reference ranking whose
+                                           gap exceeds the tolerance keeps its order (k = all classes)
   feature tensors [N,1936]                 max-abs <= 3e-2 * max|ref|   (a few bf16 ulps after 4 layers)
   gradients                                rel-L2  <= 6e-2 per parameter tensor (bf16 operands in every
                                            backward GEMM; errors grow towards the earliest layers);
                                            <= 0.15 for the mask-branch conv/BN tensors (ReLU-gate flips)
-  top-1 predicate per pair identical wherever the reference's top-2 margin exceeds the tolerance.
 """
 import os
 
 import pytest
 import torch
 
+from _parity import check_full_ranking
+
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-DIST_TOL = 4e-3
+DIST_TOL = 1e-3
 FEAT_REL_TOL = 3e-2
 GRAD_REL_TOL = 6e-2
 MASK_GRAD_REL_TOL = 0.15
@@ -44,13 +47,6 @@ def pair(cuda_lib):
     gold = torch.load(os.path.join(GOLDEN, "tempura_small.pt"), weights_only=False)
     m, o = _models(gold["model_kw"], gold["seed"])
     return m, o
-
-
-def _check_rank(got, ref, tol):
-    top2 = ref.topk(2, dim=1).values
-    sure = (top2[:, 0] - top2[:, 1]) > 2 * tol
-    assert torch.equal(got.argmax(1)[sure], ref.argmax(1)[sure])
-    return int(sure.sum())
 
 
 @pytest.mark.parametrize("name", ["tempura_small", "tempura_ragged"])
@@ -90,17 +86,19 @@ def test_forward_matches_reference_golden(pair, name):
             err = (got - ref).abs().max().item()
             assert err <= tol, (key, err, tol)
             if k.endswith("_distribution"):
-                _check_rank(got, ref, DIST_TOL)
+                check_full_ranking(got, ref, DIST_TOL)
             n_checked += 1
     assert n_checked >= 24
 
 
-def test_backward_matches_oracle(pair):
-    """d(loss)/d(parameters) through the hand-written backward vs autograd through the oracle."""
+@pytest.mark.parametrize("case", [(5, 7, (2, 6)), (9, 32, (6, 10))], ids=["7f_2-6p", "32f_6-10p"])
+def test_backward_matches_oracle(pair, case):
+    """d(loss)/d(parameters) through the hand-written backward vs autograd through the oracle; the second case is
+    one video of the headline configuration (32 frames, 6-10 pairs per frame)."""
     from b200vsgg import synthetic, tempura
     from oracle.tempura_oracle import tempura_losses
     m, o = pair
-    entry = synthetic.make_video_entry(5, 7, (2, 6))
+    entry = synthetic.make_video_entry(*case)
     N = entry["pair_idx"].shape[0]
     g = torch.Generator().manual_seed(3)
     eps = {"attention": torch.randn(6, N, 3, generator=g), "spatial": torch.randn(6, N, 6, generator=g),
@@ -127,6 +125,10 @@ def test_backward_matches_oracle(pair):
     m.dropout_p = 0.1
     m.gmm_eps = None
     assert abs(lm.item() - lo.item()) < 2e-3 * abs(lo.item()), (lm.item(), lo.item())
+    for k in ("attention_distribution", "spatial_distribution", "contacting_distribution"):
+        got, ref = pm[k].detach().float().cpu(), po[k].detach()
+        assert (got - ref).abs().max().item() <= DIST_TOL, k
+        check_full_ranking(got, ref, DIST_TOL)
     og = dict(o.named_parameters())
     worst, n, errs = 0.0, 0, []
     for name, p in m.named_parameters():
@@ -174,8 +176,8 @@ def test_batched_videos_equal_per_video_runs(pair):
     for k in ("attention_distribution", "spatial_distribution", "contacting_distribution"):
         cat_single = torch.cat([s[k] for s in singles])
         cat_ref = torch.cat([r[k] for r in refs])
-        # not bit-identical: cuDNN picks batch-size dependent conv algorithms in the (still torch) mask
-        # branch; 1e-7 differences there flip individual bf16 roundings downstream
+        # not bit-identical: split-K / tile schedules of the GEMMs depend on the row count, and fp32 sums in a
+        # different order flip individual bf16 roundings downstream
         assert (outb[k] - cat_single).abs().max().item() <= 1e-3, k
         assert (outb[k].cpu() - cat_ref).abs().max().item() <= DIST_TOL, k
     plan = m.last_plan
@@ -230,3 +232,59 @@ def test_consistency_regulariser_extension(cuda_lib):
     loss = sum(tempura.tempura_loss(out, m.last_plan).values())
     loss.backward()
     assert m.gat_semantic.layers[0][0][0].fn.to_q.weight.grad is None      # detached: no gradient reaches it
+
+
+def test_consistency_regulariser_extension_matches_oracle_restatement(cuda_lib):
+    """NUMERIC check of the extension the headline benchmark runs every step: structure / semantic temporal-
+    consistency losses of a multi-video batch (one 32-frame video of the headline shape among them) against the
+    oracle's restatement (oracle/teatgt_oracle.py::tempura_consistency — PARITY UNPINNED: GraphTransformer /
+    GlobalAttentionPooling restate absent third-party packages) fed with the CUDA path's own relation features.
+    Structure branch (fp32 kernel): 2e-3 relative; semantic branch (4 GraphTransformer layers on bf16 GEMMs at
+    width 1936): 5e-2 of the largest value."""
+    import torch.nn as nn
+    from b200vsgg import synthetic, tempura
+    from oracle import ref_shims
+    from oracle.teatgt_oracle import tempura_consistency
+    gold = torch.load(os.path.join(GOLDEN, "tempura_small.pt"), weights_only=False)
+    classes = synthetic.ag_object_classes()
+    m = tempura.TEMPURA(obj_classes=classes, consistency_regulariser=True, **gold["model_kw"])
+    synthetic.seeded_init_(m, 3)
+    gat = ref_shims.GraphTransformer(dim=10, depth=4, edge_dim=1, with_feedforwards=True, gated_residual=True,
+                                     rel_pos_emb=True)
+    gat_sem = ref_shims.GraphTransformer(dim=1936, depth=4, edge_dim=1, with_feedforwards=True, gated_residual=True,
+                                         rel_pos_emb=True)
+    gate_nn, gate_sem_nn = nn.Linear(10, 1), nn.Linear(1936, 1)
+    gat.load_state_dict(m.gat.state_dict(), strict=True)
+    gat_sem.load_state_dict(m.gat_semantic.state_dict(), strict=True)
+    gate_nn.load_state_dict(m.gate_nn.state_dict())
+    gate_sem_nn.load_state_dict(m.gate_sem_nn.state_dict())
+    m = m.cuda().train()
+    m.dropout_p = 0.0
+    cases = [(70, 12, (2, 5)), (71, 7, (1, 4)), (72, 32, (6, 10))]
+    entries = [synthetic.make_video_entry(*c) for c in cases]
+    with torch.no_grad():
+        out = m(tempura.collate_entries([_clone(e, "cuda") for e in entries]), phase="train")
+    feats = out["rel_mem_features"].float().cpu()
+    ref_s, ref_m, p0 = [], [], 0
+    with torch.no_grad():
+        for e in entries:
+            n = e["pair_idx"].shape[0]
+            e = dict(e, pred_labels=e["labels"])
+            s_, m_ = tempura_consistency(e, feats[p0:p0 + n], gat, gat_sem, gate_nn, gate_sem_nn)
+            ref_s += [float(x) for x in s_]
+            ref_m += [float(x) for x in m_]
+            p0 += n
+    for key, ref, rtol in (("structure_temp_loss", ref_s, 2e-3), ("semantic_temp_loss", ref_m, 5e-2)):
+        got, ref = out[key].float().cpu(), torch.tensor(ref)
+        assert not out[key].requires_grad
+        # the reference keeps a frame pair only if its KL >= 0: pairs with coinciding embeddings (KL = +-1e-9) fall on
+        # either side of that filter, so the non-trivial values are compared (in order when the counts agree)
+        assert got.numel() > 0 and abs(got.numel() - ref.numel()) <= 4, (key, got.shape, ref.shape)
+        floor = 1e-3 * ref.abs().max().item()
+        gs, rs = got[got > floor], ref[ref > floor]
+        assert gs.shape == rs.shape and rs.numel() > 20, (key, gs.shape, rs.shape)
+        if got.numel() != ref.numel():
+            gs, rs = gs.sort().values, rs.sort().values
+        err = (gs - rs).abs().max().item()
+        print(key, "pairs", rs.numel(), "max-abs err %.3e of max %.3e" % (err, rs.abs().max().item()))
+        assert err <= rtol * rs.abs().max().item() + 1e-6, (key, err, gs[:6], rs[:6])
