@@ -230,6 +230,18 @@ int b200vsgg_col2im3x3(const void* dcol, int32_t n, int32_t hw, int32_t channels
 /* ------------------------------------------------------------------------------------------
  * TEAT-GT / TokenGT path (lib/teatgt.py, tools/TokenGT/tokengt).
  */
+/* Blackwell-native forward of the same attention (csrc/attn_tc.cu): 128-query x 128-key tiles, S = Q K^T and
+ * O += P V on tcgen05.mma with S / P / O in tensor memory, Q / K / V tiles fetched by 3-D TMA maps
+ * {head_dim, row, head} whose out-of-range columns zero-pad a 24- / 48-wide head to the 128-byte swizzled rows,
+ * thread = query row softmax on tcgen05.ld with lazy rescaling.  Same arguments as b200vsgg_attn_flash_fwd except
+ * that the host-planned blocks are 128 rows and `rows` (= total token rows of q/k/v) is passed for the tensor maps.
+ * Writes the same lse and uses the same dropout mask function, so b200vsgg_attn_flash_bwd is its backward.
+ * Replaces multihead_attention.py:135-183 (incl. the [heads,T,T] maps kept by tokengt_graph_encoder_layer.py:170-191). */
+int b200vsgg_attn_tc_fwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, int32_t rows,
+                         const int32_t* seq_off, const int32_t* blk_seq, const int32_t* blk_row0, int32_t n_blocks,
+                         int32_t n_heads, int32_t head_dim, float scale, void* ctx, int32_t ldc, float* lse, float drop_p,
+                         uint64_t seed, void* stream);
+
 /* Variable-length flash attention over clip sequences: multihead_attention.py:135-183 without the [heads,T,T]
  * maps.  q,k,v,ctx: bf16 [rows, n_heads*head_dim] views (ld in elements, 16-byte aligned, head_dim % 8 == 0,
  * head_dim <= 64); seq_off int32 [n_seq+1]; the query/key blocking is host-planned: block b covers rows

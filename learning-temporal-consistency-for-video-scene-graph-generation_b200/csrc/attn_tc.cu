@@ -1,0 +1,359 @@
+// Blackwell-native variable-length attention for the TokenGT encoder (tools/TokenGT/tokengt/modules/
+// multihead_attention.py:135-183 and tokengt_graph_encoder_layer.py:170-191 of the reference): sequences = 5-frame
+// clips (T = 2 + nodes + edges: 250-600 tokens at the AG shapes, up to ~5.3 k in the long-clip config), 32 heads x 24
+// or 16 heads x 48, fp32 softmax, attention dropout.  The reference keeps [heads, T, T] maps for all 12 layers;
+// nothing of size T^2 leaves the SM here.
+//
+// One CTA = one 128-query tile of one (clip, head); 192 threads, two CTAs per SM:
+//   warp 0    TMA producer: Q once, then a 2-stage ring of K tiles and one of V tiles.  The tensor maps are
+//             3-D {head_dim, token row, head} views of the [rows, heads*head_dim] activations with a {64, 128, 1} box:
+//             the columns head_dim..63 of a box lie outside dimension 0 and arrive as ZEROS, so a 24- or 48-wide
+//             head lands directly in the 128-byte SWIZZLE_128B rows that tcgen05.mma consumes.
+//   warp 1    MMA issuer (one thread): S = Q K^T  (M128 x N128, K = head_dim rounded to 16) into TMEM columns
+//             [0,128); O += P V (M128 x N{32,64}, K = 128 keys) with P read FROM TENSOR MEMORY (tcgen05.mma, A in
+//             TMEM) and V as an MN-major shared-memory operand — the same 16 KB tile format as K.
+//   warps 2-5 softmax: thread = query row (tcgen05.ld 32x32b: lane = row), so the row maximum and the row sum are
+//             thread-local — no shuffles.  The whole S row (128 fp32) is pulled into registers, the S buffer is
+//             released at once (the next S MMA overlaps this block's exponentials), P goes back to TMEM as packed
+//             bf16 (tcgen05.st) in columns [128,192).  The running maximum is only raised when it grew by more than
+//             2^8 (lazy rescaling): O in TMEM columns [192,256) is rescaled by the row's own thread in that case.
+// Pipeline barriers: q_full, k_full/k_empty[2], v_full/v_empty[2], s_full (MMA -> softmax), s_free, p_full
+// (softmax -> MMA, 128 arrivals), o_done (tcgen05.commit after every P V).
+//
+// Roofline: 4 T^2 hd flops per (clip, head); per 128 x 128 tile the tensor pipe needs ~128 + 128 cycles, the 16 k
+// exponentials need 1024 cycles of the SM's 16/clk MUFU: the kernel is SFU-bound at head_dim 24/48 (ceiling
+// ~430 / ~860 TFLOP/s of algorithmic flops), not tensor- or HBM-bound.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "gemm_common.cuh"
+
+namespace vsgg {
+namespace atc {
+
+constexpr int BQ = 128;                 // queries per CTA
+constexpr int BKV = 128;                // keys per block
+constexpr int TILE_BYTES = 128 * 128;   // 128 rows x 128-byte swizzled rows (64 bf16, head_dim zero-padded by TMA)
+constexpr int KV_STAGES = 2;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 256;
+constexpr int COL_S = 0, COL_P = 128, COL_O = 192;
+constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES) + 256 + 1024;   // tiles + barriers + alignment slack
+constexpr float RESCALE_THRESHOLD = 8.f;   // log2 domain: P stays below 2^8, exact in fp32 sums and fine in bf16
+
+// same mask function as the mma.sync backward kernels (attn_flash.cu): they regenerate it from (seed, row, head, key)
+__device__ __forceinline__ float drop_factor(uint32_t thr, float inv_keep, uint32_t row_key, int key) {
+    uint32_t h = row_key ^ (static_cast<uint32_t>(key) * 0x9E3779B1u);
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h >= thr ? inv_keep : 0.f;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <int HDN>   // accumulator width of O: 32 (head_dim <= 32) or 64
+__global__ void __launch_bounds__(THREADS, 2)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                   const __grid_constant__ CUtensorMap tv, const int32_t* __restrict__ seq_off,
+                   const int32_t* __restrict__ blk_seq, const int32_t* __restrict__ blk_row0, int n_blocks, int n_heads,
+                   int hd, float scale_log2, __nv_bfloat16* __restrict__ ctx, int ldc, float* __restrict__ lse,
+                   float drop_p, unsigned long long seed) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* Qs = smem;
+    uint8_t* Ks = Qs + TILE_BYTES;
+    uint8_t* Vs = Ks + KV_STAGES * TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + KV_STAGES * TILE_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = k_full + KV_STAGES;
+    uint64_t* v_full = k_empty + KV_STAGES;
+    uint64_t* v_empty = v_full + KV_STAGES;
+    uint64_t* s_full = v_empty + KV_STAGES;
+    uint64_t* s_free = s_full + 1;
+    uint64_t* p_full = s_free + 1;
+    uint64_t* o_done = p_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // consecutive CTAs = the heads of one query tile's neighbours: unit u -> (block = u / n_heads, head = u % n_heads)
+    // keeps the K/V rows of a clip hot in L2 while its query tiles and heads are in flight
+    const int blk = blockIdx.x / n_heads, head = blockIdx.x - blk * n_heads;
+    const int seq = blk_seq[blk];
+    const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
+    const int qrow0 = blk_row0[blk];
+    const int qrows = min(BQ, s1 - qrow0);
+    const int nkb = (s1 - s0 + BKV - 1) / BKV;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tq);
+        ptx::prefetch_tmap(&tk);
+        ptx::prefetch_tmap(&tv);
+        ptx::mbar_init(q_full, 1);
+        for (int i = 0; i < KV_STAGES; ++i) {
+            ptx::mbar_init(&k_full[i], 1);
+            ptx::mbar_init(&k_empty[i], 1);
+            ptx::mbar_init(&v_full[i], 1);
+            ptx::mbar_init(&v_empty[i], 1);
+        }
+        ptx::mbar_init(s_full, 1);
+        ptx::mbar_init(s_free, 128);
+        ptx::mbar_init(p_full, 128);
+        ptx::mbar_init(o_done, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            ptx::mbar_expect_tx(q_full, TILE_BYTES);
+            ptx::tma_load_3d(Qs, &tq, q_full, 0, qrow0, head);
+            for (int j = 0; j < nkb; ++j) {
+                const int st = j % KV_STAGES;
+                const uint32_t ph = static_cast<uint32_t>(j / KV_STAGES) & 1u;
+                ptx::mbar_wait(&k_empty[st], ph ^ 1u);
+                ptx::mbar_expect_tx(&k_full[st], TILE_BYTES);
+                ptx::tma_load_3d(Ks + st * TILE_BYTES, &tk, &k_full[st], 0, s0 + j * BKV, head);
+                ptx::mbar_wait(&v_empty[st], ph ^ 1u);
+                ptx::mbar_expect_tx(&v_full[st], TILE_BYTES);
+                ptx::tma_load_3d(Vs + st * TILE_BYTES, &tv, &v_full[st], 0, s0 + j * BKV, head);
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV, 0, 0);      // Q, K: K-major
+            constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HDN, 0, 1);      // P: TMEM (K-major), V: MN-major
+            const int ks_s = (hd + 15) >> 4;                                       // k-steps over head_dim
+            const uint32_t t_s = tmem_base + COL_S, t_p = tmem_base + COL_P, t_o = tmem_base + COL_O;
+            const uint32_t qa = ptx::smem_u32(Qs);
+            auto issue_s = [&](int j) {
+                const int st = j % KV_STAGES;
+                ptx::mbar_wait(&k_full[st], static_cast<uint32_t>(j / KV_STAGES) & 1u);
+                if (j > 0) ptx::mbar_wait(s_free, static_cast<uint32_t>(j - 1) & 1u);   // S_{j-1} sits in registers
+                ptx::tc_fence_after();
+                const uint32_t kb = ptx::smem_u32(Ks + st * TILE_BYTES);
+                for (int k = 0; k < ks_s; ++k)
+                    ptx::umma_bf16(t_s, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                                   ptx::make_smem_desc_sw128(kb + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+                ptx::umma_commit(&k_empty[st]);
+                ptx::umma_commit(s_full);
+            };
+            ptx::mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < nkb; ++j) {
+                if (j + 1 < nkb) issue_s(j + 1);
+                const int st = j % KV_STAGES;
+                const int kvalid = min(BKV, s1 - (s0 + j * BKV));
+                const int ks_o = (kvalid + 15) >> 4;                               // k-steps over the block's keys
+                ptx::mbar_wait(&v_full[st], static_cast<uint32_t>(j / KV_STAGES) & 1u);
+                ptx::mbar_wait(p_full, static_cast<uint32_t>(j) & 1u);
+                ptx::tc_fence_after();
+                const uint32_t vb = ptx::smem_u32(Vs + st * TILE_BYTES);
+                for (int k = 0; k < ks_o; ++k)
+                    ptx::umma_bf16_ts(t_o, t_p + k * 8, ptx::make_smem_desc_sw128(vb + k * 2048, 8192, 1024), idesc_o,
+                                      (j != 0 || k != 0) ? 1u : 0u);
+                ptx::umma_commit(&v_empty[st]);
+                ptx::umma_commit(o_done);
+            }
+        }
+    } else {
+        // ================================ softmax warps: thread = query row ================================
+        const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;               // row of the tile
+        const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+        const uint32_t t_s = tmem_base + lane_addr + COL_S, t_p = tmem_base + lane_addr + COL_P,
+                       t_o = tmem_base + lane_addr + COL_O;
+        const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+        const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+        const uint32_t row_key = thr ? hash_u32(seed, static_cast<unsigned long long>(qrow0 + row) * 64ull + head) : 0u;
+        float m_ref = 0.f, l = 0.f;
+        for (int j = 0; j < nkb; ++j) {
+            const int kb = s0 + j * BKV;
+            const int kvalid = min(BKV, s1 - kb);
+            uint32_t r[128];
+            ptx::mbar_wait(s_full, static_cast<uint32_t>(j) & 1u);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                ptx::tmem_ld_32x32b_x32(t_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(r[c * 32]));
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(s_free);                   // the next S MMA may overwrite the buffer
+            float mx = -INFINITY;
+            if (kvalid == BKV) {
+#pragma unroll
+                for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 128; ++i) {
+                    if (i >= kvalid) r[i] = 0xff800000u;   // -inf: keys beyond the clip
+                    mx = fmaxf(mx, __uint_as_float(r[i]));
+                }
+            }
+            mx *= scale_log2;
+            float alpha = 1.f;
+            bool rescale = false;
+            if (j == 0) {
+                m_ref = mx;
+            } else if (mx > m_ref + RESCALE_THRESHOLD) {
+                alpha = ptx::ex2_approx(m_ref - mx);
+                m_ref = mx;
+                rescale = true;
+            }
+            float sum = 0.f;
+            uint32_t pk[64];
+            if (thr == 0u) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i]), scale_log2, -m_ref));
+                    const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m_ref));
+                    sum += p0 + p1;
+                    pk[i] = pack2(p0, p1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i]), scale_log2, -m_ref));
+                    const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m_ref));
+                    sum += p0 + p1;
+                    pk[i] = pack2(p0 * drop_factor(thr, inv_keep, row_key, kb + 2 * i),
+                                  p1 * drop_factor(thr, inv_keep, row_key, kb + 2 * i + 1));
+                }
+            }
+            l = l * alpha + sum;
+            if (j > 0) {                                // P and O are free once the previous P V has retired
+                ptx::mbar_wait(o_done, static_cast<uint32_t>(j - 1) & 1u);
+                ptx::tc_fence_after();
+                if (__any_sync(0xffffffffu, rescale)) {
+                    uint32_t o[HDN];
+#pragma unroll
+                    for (int c = 0; c < HDN / 32; ++c)
+                        ptx::tmem_ld_32x32b_x32(t_o + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < HDN; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+#pragma unroll
+                    for (int c = 0; c < HDN / 32; ++c)
+                        ptx::tmem_st_32x32b_x32(t_o + c * 32, reinterpret_cast<const uint32_t(&)[32]>(o[c * 32]));
+                }
+            }
+            ptx::tmem_st_32x32b_x32(t_p, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
+            ptx::tmem_st_32x32b_x32(t_p + 32, reinterpret_cast<const uint32_t(&)[32]>(pk[32]));
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / l -> bf16 context rows, log-sum-exp for the backward
+        ptx::mbar_wait(o_done, static_cast<uint32_t>(nkb - 1) & 1u);
+        ptx::tc_fence_after();
+        uint32_t o[HDN];
+#pragma unroll
+        for (int c = 0; c < HDN / 32; ++c)
+            ptx::tmem_ld_32x32b_x32(t_o + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
+        ptx::tmem_ld_wait();
+        if (row < qrows) {
+            const float inv = 1.f / l;
+            const size_t grow = static_cast<size_t>(qrow0 + row);
+            __nv_bfloat16* dst = ctx + grow * ldc + head * hd;
+#pragma unroll
+            for (int c = 0; c < HDN / 8; ++c) {
+                if (c * 8 < hd) {
+                    uint4 u;
+                    u.x = pack2(__uint_as_float(o[c * 8]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
+                    u.y = pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
+                    u.z = pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
+                    u.w = pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c * 8) = u;
+                }
+            }
+            if (lse != nullptr) lse[grow * n_heads + head] = (m_ref + __log2f(l)) * 0.6931471805599453f;
+        }
+    }
+    // ================================ teardown ================================
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// {head_dim, rows, heads} view of a [rows, heads * head_dim] bf16 matrix (pitch ld), box {64, 128, 1}, SWIZZLE_128B.
+static int make_tmap_heads(CUtensorMap* tm, const void* base, uint64_t hd, uint64_t rows, uint64_t heads, uint64_t ld) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (enc == nullptr) return set_error(B200VSGG_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || ((ld * 2) & 15u) != 0 || ((hd * 2) & 15u) != 0)
+        return set_error(B200VSGG_ERR_BAD_ARG, "attn_tc: q/k/v must be 16-byte aligned, ld % 8 == 0, head_dim % 8 == 0");
+    cuuint64_t dims[3] = {hd, rows, heads};
+    cuuint64_t strides[2] = {ld * 2, hd * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d) for an attention operand hd=%llu rows=%llu ld=%llu",
+                 (int)r, (unsigned long long)hd, (unsigned long long)rows, (unsigned long long)ld);
+        return set_error(B200VSGG_ERR_TMAP, msg);
+    }
+    return 0;
+}
+
+}  // namespace atc
+}  // namespace vsgg
+
+using namespace vsgg;
+
+extern "C" int b200vsgg_attn_tc_fwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                                    int32_t rows, const int32_t* seq_off, const int32_t* blk_seq, const int32_t* blk_row0,
+                                    int32_t n_blocks, int32_t n_heads, int32_t head_dim, float scale, void* ctx, int32_t ldc,
+                                    float* lse, float drop_p, uint64_t seed, void* stream) {
+    if (!q || !k || !v || !seq_off || !blk_seq || !blk_row0 || !ctx || rows <= 0 || n_heads <= 0 || n_heads > 64 ||
+        head_dim < 8 || head_dim > 64 || (head_dim & 7) || (ldc & 7) || (reinterpret_cast<uintptr_t>(ctx) & 15u))
+        return set_error(B200VSGG_ERR_BAD_ARG, "attn_tc_fwd: bad arg (head_dim in 8..64, % 8 == 0; <= 64 heads)");
+    if (n_blocks == 0) return 0;
+    CUtensorMap tq, tk, tv;
+    int rc;
+    if ((rc = atc::make_tmap_heads(&tq, q, head_dim, rows, n_heads, ldq))) return rc;
+    if ((rc = atc::make_tmap_heads(&tk, k, head_dim, rows, n_heads, ldk))) return rc;
+    if ((rc = atc::make_tmap_heads(&tv, v, head_dim, rows, n_heads, ldv))) return rc;
+    const float scale_log2 = scale * 1.4426950408889634f;
+    const long long units = static_cast<long long>(n_blocks) * n_heads;
+    if (units > 0x7fffffffLL) return set_error(B200VSGG_ERR_BAD_ARG, "attn_tc_fwd: too many (tile, head) units");
+    static bool attr_set = false;
+    if (!attr_set) {     // both instantiations share one function-pointer type: set the attribute on each explicitly
+        cudaError_t e = cudaFuncSetAttribute(atc::attn_tc_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             atc::SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(atc::attn_tc_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     atc::SMEM_BYTES);
+        if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    auto launch = [&](auto kern) -> int {
+        kern<<<static_cast<unsigned>(units), atc::THREADS, atc::SMEM_BYTES, (cudaStream_t)stream>>>(
+            tq, tk, tv, seq_off, blk_seq, blk_row0, n_blocks, n_heads, head_dim, scale_log2,
+            reinterpret_cast<__nv_bfloat16*>(ctx), ldc, lse, drop_p, seed);
+        return 0;
+    };
+    rc = head_dim <= 32 ? launch(atc::attn_tc_fwd_kernel<32>) : launch(atc::attn_tc_fwd_kernel<64>);
+    if (rc) return rc;
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}

@@ -421,6 +421,18 @@ def attn_flash_fwd(q, k, v, seq_off, blk_seq, blk_row0, n_heads, head_dim, ctx, 
     _count()
 
 
+def attn_tc_fwd(q, k, v, seq_off, blk_seq128, blk_row0_128, n_heads, head_dim, ctx, lse=None, drop_p=0.0, seed=0):
+    """tcgen05 / TMEM / TMA forward (b200vsgg_attn_tc_fwd); the block table has 128-row blocks."""
+    scale = float(head_dim) ** -0.5
+    rows = q.shape[0]
+    assert k.shape[0] == rows and v.shape[0] == rows and ctx.shape[0] == rows
+    check(_lib.lib().b200vsgg_attn_tc_fwd(
+        _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), rows, _ptr(seq_off),
+        _ptr(blk_seq128), _ptr(blk_row0_128), blk_seq128.numel(), n_heads, head_dim, scale, _ptr(_bf(ctx)), ctx.stride(0),
+        _ptr(lse), drop_p, seed, _stream()), "attn_tc_fwd")
+    _count()
+
+
 def attn_flash_bwd(q, k, v, ctx, dctx, lse, seq_off, blk_seq, blk_row0, n_heads, head_dim, dq, dk, dv, drop_p=0.0, seed=0,
                    max_len=0):
     scale = float(head_dim) ** -0.5
