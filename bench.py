@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lib-sample-videos", type=int, default=16, help="videos of the PyTorch-eager library baseline")
     ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--no-teatgt", action="store_true", help="leave out the TEAT-GT (TokenGT) section of the line")
+    ap.add_argument("--longclip", action="store_true", help="also run BASELINE configs[4] (always run at 8 GPUs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-consistency", action="store_true", help="leave out the temporal-consistency regulariser")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + --steps steps, no e2e/cpu (for ncu runs)")
@@ -222,6 +224,257 @@ def run_reference_arm(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# TEAT-GT (TokenGT) arm: BASELINE configs[2] (SGCls fwd+bwd) and the PredCLS fwd+bwd+regulariser step; configs[4]
+# (long-clip inference, videos sharded over the ranks) with --longclip or at 8 GPUs
+# ------------------------------------------------------------------------------------------------
+TEAT_ARGS = dict(num_atoms=1168, num_edges=1, num_output=26, lap_node_id=True, lap_node_id_k=50,
+                 lap_node_id_sign_flip=False, lap_node_id_eig_dropout=0.2, rand_node_id=False, rand_node_id_dim=50,
+                 orf_node_id=False, orf_node_id_dim=50, type_id=True, encoder_embed_dim=768, encoder_layers=12,
+                 encoder_attention_heads=32, encoder_ffn_embed_dim=768, return_attention=True)
+
+
+def _teat_batch(video_indices, frames, ppf, dev, sgcls):
+    import numpy as np
+    import torch
+    from b200vsgg import objbranch, synthetic, tempura
+    entries = []
+    for i in video_indices:
+        e = synthetic.make_video_entry(i, frames, ppf)
+        e.pop("union_feat"), e.pop("spatial_masks")          # TEAT-GT never reads them (lib/teatgt.py:98-141)
+        e = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in e.items()}
+        if sgcls:
+            synthetic.add_sgcls_inputs(e, i)
+            objbranch.get_sequence(e, None, None, "sgcls")
+        entries.append(e)
+    gts = [synthetic.build_gt_tensors(e, dev) for e in entries]
+    batch = tempura.collate_entries(entries)
+    for k in ("attention_gt", "spatial_gt", "contacting_gt"):
+        batch.pop(k, None)
+    batch["frame_counts_host"] = torch.bincount(batch["im_idx"].long()).cpu().numpy()
+    batch["pair_idx_host"] = batch["pair_idx"].cpu().numpy()
+    batch["box_frames_host"] = batch["boxes"][:, 0].cpu().numpy()
+    return batch, tuple(torch.cat([g[i] for g in gts]) for i in range(3))
+
+
+def teatgt_cpu_rate(video_indices, frames, sgcls, seed=1123):
+    """pairs/s of the TEAT-GT oracle (oracle/teatgt_oracle.py: the reference's per-clip Python loops, fp32 torch on the
+    host cores) for forward + losses + backward, one video per forward like TEATGT_train.py:140-190."""
+    import types
+    import torch
+    from b200vsgg import synthetic
+    from oracle.teatgt_oracle import TeatgtOracle, teatgt_losses
+    from oracle.tempura_oracle import get_sequence, object_loss
+    torch.set_num_threads(os.cpu_count() or 1)
+    targs = dict(TEAT_ARGS)
+    if sgcls:
+        targs.update(encoder_layers=6, encoder_attention_heads=16)
+    o = TeatgtOracle(mode="sgcls" if sgcls else "predcls", attention_class_num=3, spatial_class_num=6, contact_class_num=17,
+                     obj_classes=synthetic.ag_object_classes(), tracking=sgcls, args=types.SimpleNamespace(**targs),
+                     with_regulariser=not sgcls)
+    synthetic.teatgt_seeded_init_(o, seed)
+    o.train()
+    pairs, t = 0, 0.0
+    for n, i in enumerate([video_indices[0]] + list(video_indices)):      # first pass = warm-up
+        e = synthetic.make_video_entry(i, frames, (6, 10))
+        e.pop("union_feat"), e.pop("spatial_masks")
+        if sgcls:
+            synthetic.add_sgcls_inputs(e, i)
+            get_sequence(e, "sgcls")
+        att, spa, con = synthetic.build_gt_tensors(e)
+        t0 = time.perf_counter()
+        o.zero_grad(set_to_none=True)
+        pred = o(dict(e), phase="train")
+        loss = sum(teatgt_losses(pred, att, spa, con).values())
+        if sgcls:
+            loss = loss + object_loss(pred)
+        loss.backward()
+        if n > 0:
+            t += time.perf_counter() - t0
+            pairs += e["pair_idx"].shape[0]
+    return pairs / t, pairs, torch.get_num_threads()
+
+
+def teatgt_section(args, dev, rank, world, peaks):
+    """One dict for the bench line: 'sgcls' = BASELINE configs[2] (TEAT-GT SGCls fwd+bwd: object branch + 6-layer /
+    16-head TokenGT + regulariser), 'predcls' = TEAT-GT PredCLS fwd+bwd with the consistency regulariser (12 layers / 32
+    heads), each a FULL training step (losses, backward, gradient all-reduce when N > 1, clip + AdamW) on 64 videos per
+    GPU; 'longclip' = configs[4] (inference, 8 videos x 256 frames x 32 pairs per GPU, no collective)."""
+    import types
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from b200vsgg import ddp, ops, synthetic, teatgt
+    from b200vsgg.optim import FusedAdamW
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    out = {"note": "same rules as the headline: CUDA events, max over ranks, whole-job pairs/s, synthetic AG-shaped videos, "
+                   "inputs resident in HBM; roofline fractions vs %.0f TFLOP/s (%s)" % (
+                       peak_tf, "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback")}
+
+    def run_train(mode):
+        sgcls = mode == "sgcls"
+        targs = dict(TEAT_ARGS)
+        if sgcls:
+            targs.update(encoder_layers=6, encoder_attention_heads=16)     # teatgt_config.py:11-14
+        m = teatgt.TEAT_GT(mode=mode, attention_class_num=3, spatial_class_num=6, contact_class_num=17,
+                           obj_classes=synthetic.ag_object_classes(), tracking=sgcls, args=types.SimpleNamespace(**targs))
+        synthetic.teatgt_seeded_init_(m, 1123)
+        m = m.to(dev).train()
+        if not sgcls:
+            for p in m.object_classifier.parameters():
+                p.requires_grad_(False)
+        vids = [rank * args.videos + v for v in range(args.videos)]
+        batch, (att, spa, con) = _teat_batch(vids, args.frames, (6, 10), dev, sgcls)
+        n_pairs = int(batch["pair_idx"].shape[0])
+        params = [p for p in m.parameters() if p.requires_grad]
+        sync = ddp.GradSync(params[::-1]) if world > 1 else None
+        opt = FusedAdamW(params, lr=1e-5, weight_decay=0.1, max_grad_norm=5.0)
+        host_ms = []
+
+        def step():
+            m.zero_grad(set_to_none=True)
+            pred = m(dict(batch), phase="train")
+            loss = (F.cross_entropy(pred["attention_distribution"], att) + F.binary_cross_entropy(pred["spatial_distribution"], spa)
+                    + F.binary_cross_entropy(pred["contacting_distribution"], con))
+            if sgcls:
+                from b200vsgg.objbranch import object_loss
+                grp = pred["box_groups"]
+                loss = loss + object_loss(pred, 1.0, grp.count, grp.video_of_box64)
+            loss = loss + 2500.0 * (pred["structure_temp_loss"].mean() + pred["semantic_temp_loss"].mean())  # TEATGT_train.py:182-185
+            loss.backward()
+            if sync is not None:
+                sync.sync()
+            opt.step()
+            host_ms.append(m.last_host_graph_ms)
+            return loss
+
+        for _ in range(2):
+            step()
+        steps = max(3, min(args.steps, 5))
+        barrier()
+        ops.gemm_profile, ops.attn_profile = [], []
+        l0 = ops.launch_count
+        del host_ms[:]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        barrier()
+        ms = reduce(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None) / steps
+        gp, ap = ops.gemm_profile, ops.attn_profile
+        ops.gemm_profile = ops.attn_profile = None
+        pairs = reduce(float(n_pairs), dist.ReduceOp.SUM if world > 1 else None)
+        gf = sum(2.0 * M * N * K for (M, N, K, _, _, _, _) in gp)
+        gms = sum(a.elapsed_time(b) for (_, _, _, _, _, a, b) in gp)
+        res = {"value": pairs / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "pairs_per_step": int(pairs),
+               "tokens_per_gpu": int(m.last_plan.T), "clips_per_gpu": int(m.last_plan.n_clips),
+               "gpu_launches_per_step": (ops.launch_count - l0) // steps, "loss": float(loss.item()),
+               "host_graph_ms_per_step": float(np.mean(host_ms)),
+               "host_graph_what": "reference-ordered edge-list compaction + LAPACK eigh of the clip Laplacians on the host "
+                                  "(parity requires the reference's own eigensolver); the device waits for it",
+               "gemm": {"achieved_tflops": gf / (gms * 1e-3) / 1e12 if gms else 0.0, "frac": gf / (gms * 1e-3) / 1e12 / peak_tf if gms else 0.0,
+                        "ms_per_step": gms / steps, "launches": len(gp) // steps}}
+        for kind, label in (("fwd", "attention_fwd_tcgen05"), ("bwd", "attention_bwd_tcgen05")):
+            fl = sum(f for (k, f, _, _) in ap if k == kind)
+            tms = sum(a.elapsed_time(b) for (k, _, a, b) in ap if k == kind)
+            res[label] = {"achieved_tflops": fl / (tms * 1e-3) / 1e12 if tms else 0.0,
+                          "frac_of_tensor_peak": fl / (tms * 1e-3) / 1e12 / peak_tf if tms else 0.0,
+                          "ms_per_step": tms / steps, "launches": sum(1 for a in ap if a[0] == kind) // steps,
+                          "bound": "SFU (16 k exp per 128x128 tile = 1024 clk vs ~256 clk of tcgen05.mma at head_dim %d)"
+                                   % (768 // targs["encoder_attention_heads"])}
+        del m, opt, batch
+        torch.cuda.empty_cache()
+        return res
+
+    for mode in ("sgcls", "predcls"):
+        try:
+            out[mode] = run_train(mode)
+        except Exception as ex:
+            out[mode] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    out["sgcls"]["config"] = "BASELINE configs[2]: TEAT-GT SGCls fwd+bwd, %d videos/GPU x %d frames x 6-10 pairs" % (args.videos, args.frames)
+    out["predcls"]["config"] = "TEAT-GT PredCLS fwd+bwd + consistency regulariser, %d videos/GPU x %d frames x 6-10 pairs" % (args.videos, args.frames)
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            rate, pairs, threads = teatgt_cpu_rate([0], args.frames, sgcls=True)
+            out["sgcls"]["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                            "sample": "1 video (%d pairs) after 1 warm-up pass, oracle/teatgt_oracle.py SGCls "
+                                                      "fwd+loss+bwd fp32 train mode" % pairs}
+            rate, pairs, threads = teatgt_cpu_rate([0], args.frames, sgcls=False)
+            out["predcls"]["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                              "sample": "1 video (%d pairs) after 1 warm-up pass, oracle/teatgt_oracle.py PredCLS "
+                                                        "fwd+regulariser+loss+bwd fp32 train mode" % pairs}
+        except Exception as ex:
+            out["cpu_baseline_error"] = "%s: %s" % (type(ex).__name__, ex)
+
+    if args.longclip or world == 8:
+        try:
+            m = teatgt.TEAT_GT(mode="predcls", attention_class_num=3, spatial_class_num=6, contact_class_num=17,
+                               obj_classes=synthetic.ag_object_classes(), tracking=False,
+                               args=types.SimpleNamespace(**TEAT_ARGS))
+            synthetic.teatgt_seeded_init_(m, 1123)
+            m = m.to(dev).eval()
+            nv = 8
+            batch, _ = _teat_batch([rank * nv + v for v in range(nv)], 256, 32, dev, False)
+            n_pairs = int(batch["pair_idx"].shape[0])
+
+            def infer():
+                with torch.no_grad():
+                    return m(dict(batch), phase="test")
+
+            infer()
+            barrier()
+            ops.attn_profile = []
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                pred = infer()
+            e1.record()
+            barrier()
+            ms = reduce(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None) / 2
+            ap, ops.attn_profile = ops.attn_profile, None
+            fl = sum(f for (_, f, _, _) in ap)
+            tms = sum(a.elapsed_time(b) for (_, _, a, b) in ap)
+            pairs = reduce(float(n_pairs), dist.ReduceOp.SUM if world > 1 else None)
+            # outputs gathered on rank 0 (the only exchange of the config: no data-path collective)
+            gathered = None
+            if world > 1:
+                parts = [torch.empty_like(pred["attention_distribution"]) for _ in range(world)] if rank == 0 else None
+                dist.gather(pred["attention_distribution"].contiguous(), parts, dst=0)
+                gathered = sum(p.shape[0] for p in parts) if rank == 0 else None
+            out["longclip"] = {
+                "config": "BASELINE configs[4]: TEAT-GT PredCLS long-clip inference, %d videos x 256 frames x 32 pairs per GPU, "
+                          "videos sharded over %d GPU(s), no collective; outputs gathered on rank 0" % (nv, world),
+                "value": pairs / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "pairs_per_step": int(pairs),
+                "tokens_per_gpu": int(m.last_plan.T), "max_tokens_per_clip": int(m.last_plan.max_T),
+                "host_graph_ms_per_step": float(m.last_host_graph_ms), "rows_gathered_on_rank0": gathered,
+                "attention_fwd_tcgen05": {"achieved_tflops": fl / (tms * 1e-3) / 1e12 if tms else 0.0,
+                                          "frac_of_tensor_peak": fl / (tms * 1e-3) / 1e12 / peak_tf if tms else 0.0,
+                                          "ms_per_step": tms / 2, "per_gpu": "rank 0"},
+                "reference": "cannot run this config: it keeps 12 x [32,T,T] fp32 attention maps per clip (T = 5337: 43.7 GB)"}
+            del m, batch
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            out["longclip"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    return out
+
 
 
 def workload_config(args, world):
@@ -488,6 +741,17 @@ def main():
         except Exception as ex:  # the baseline is a report, never a reason to lose the headline line
             lib = {"error": "%s: %s" % (type(ex).__name__, ex)}
 
+    # ============================== TEAT-GT section (all ranks) ==============================
+    teat = None
+    if not args.no_teatgt and not args.profile:
+        del batch
+        model.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        try:
+            teat = teatgt_section(args, dev, rank, world, peaks)
+        except Exception as ex:
+            teat = {"error": "%s: %s" % (type(ex).__name__, ex)}
+
     if rank == 0:
         cfg = workload_config(args, world)
         cfg["pairs_per_step"] = int(total_pairs)
@@ -495,7 +759,7 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
                 "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu, "library_baseline": lib, "loss": loss_val,
+                "cpu_baseline": cpu, "library_baseline": lib, "teatgt": teat, "loss": loss_val,
                 "model_tflops": 1.138e9 * value / 1e12}
         print(json.dumps(line), flush=True)
     if world > 1:

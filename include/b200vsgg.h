@@ -242,6 +242,16 @@ int b200vsgg_attn_tc_fwd(const void* q, int32_t ldq, const void* k, int32_t ldk,
                          int32_t n_heads, int32_t head_dim, float scale, void* ctx, int32_t ldc, float* lse, float drop_p,
                          uint64_t seed, void* stream);
 
+/* Blackwell-native backward (csrc/attn_tc_bwd.cu): a dQ kernel (128-query tiles) and a dK/dV kernel (128-key tiles),
+ * both with the S-type products and the accumulating products on tcgen05.mma (A operand of the latter read from tensor
+ * memory), probabilities recomputed from `lse`, dropout regenerated from `seed`.  ctx / dctx: the forward output and its
+ * gradient (bf16 [rows, n_heads*head_dim]); delta: fp32 workspace [rows, n_heads]; the block table has 128-row blocks. */
+int b200vsgg_attn_tc_bwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                         const void* ctx, int32_t ldc, const void* dctx, int32_t lddc, const float* lse, float* delta,
+                         int32_t rows, const int32_t* seq_off, const int32_t* blk_seq, const int32_t* blk_row0,
+                         int32_t n_blocks, int32_t n_heads, int32_t head_dim, float scale, void* dq, int32_t lddq, void* dk,
+                         int32_t lddk, void* dv, int32_t lddv, float drop_p, uint64_t seed, void* stream);
+
 /* Variable-length flash attention over clip sequences: multihead_attention.py:135-183 without the [heads,T,T]
  * maps.  q,k,v,ctx: bf16 [rows, n_heads*head_dim] views (ld in elements, 16-byte aligned, head_dim % 8 == 0,
  * head_dim <= 64); seq_off int32 [n_seq+1]; the query/key blocking is host-planned: block b covers rows

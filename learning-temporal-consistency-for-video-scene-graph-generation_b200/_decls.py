@@ -51,6 +51,8 @@ SIGNATURES = {
     "b200vsgg_im2col3x3": [vp, i32, i32, i32, vp, vp],
     "b200vsgg_col2im3x3": [vp, i32, i32, i32, vp, vp],
     "b200vsgg_attn_tc_fwd": [vp, i32, vp, i32, vp, i32, i32, vp, vp, vp, i32, i32, i32, f32, vp, i32, vp, f32, u64, vp],
+    "b200vsgg_attn_tc_bwd": [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, i32, i32, i32, f32, vp, i32,
+                             vp, i32, vp, i32, f32, u64, vp],
     "b200vsgg_attn_flash_fwd": [vp, i32, vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, f32, vp, i32, vp, f32, u64, vp, i32,
                                 i32],
     "b200vsgg_attn_flash_bwd": [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32,

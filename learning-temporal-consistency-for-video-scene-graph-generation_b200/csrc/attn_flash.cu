@@ -18,6 +18,7 @@
 
 #include "../../include/b200vsgg.h"
 #include "common.cuh"
+#include "attn_dropout.cuh"
 
 namespace vsgg {
 namespace fa {
@@ -54,19 +55,15 @@ __device__ __forceinline__ float quad_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
-// Dropout keep-factor of probability (query row `row` (global), head, key `key` (global row)).  The 64-bit
-// counter hash runs once per (row, head) (`row_key`), each probability then costs one 32-bit murmur3
-// finaliser (~8 integer instructions): the per-element hash was half of the forward's run time.
+// Dropout keep-factor of probability (query row `row` (global), head, key `key_rel` relative to the sequence start):
+// the shared counter-based mask of attn_dropout.cuh in its generic per-element form (these mma.sync kernels are the
+// reference implementation / fallback for head_dim > 64; the tcgen05 kernels evaluate the same bits four at a time).
 __device__ __forceinline__ uint32_t drop_row_key(uint32_t thr, unsigned long long seed, int row, int head) {
-    return thr == 0u ? 0u : hash_u32(seed, static_cast<unsigned long long>(row) * 64ull + head);
+    return thr == 0u ? 0u : adrop::row_key(seed, row, head);
 }
-__device__ __forceinline__ float drop_factor(uint32_t thr, float inv_keep, uint32_t row_key, int key) {
+__device__ __forceinline__ float drop_factor(uint32_t thr, float inv_keep, uint32_t row_key, int key_rel) {
     if (thr == 0u) return 1.f;
-    uint32_t h = row_key ^ (static_cast<uint32_t>(key) * 0x9E3779B1u);
-    h ^= h >> 16; h *= 0x85EBCA6Bu;
-    h ^= h >> 13; h *= 0xC2B2AE35u;
-    h ^= h >> 16;
-    return h >= thr ? inv_keep : 0.f;
+    return adrop::keep(thr, row_key, key_rel) ? inv_keep : 0.f;
 }
 
 constexpr int BLK = 64;       // rows per query / key block
@@ -168,8 +165,8 @@ flash_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat
     const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
     const int qrow0 = blk_row0[blockIdx.x];
     const int qrows = min(BLK, s1 - qrow0);
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    const uint32_t thr = adrop::thr8_of(drop_p);
+    const float inv_keep = adrop::inv_keep_of(thr);
 
     stage<HDP>(Qs, q, ldq, qrow0, qrows, col0, hd);
     cp_async_wait_all();
@@ -219,7 +216,7 @@ flash_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat
                     const float p = __expf(s[nt][half * 2 + e] - mx);
                     sum += p;
                     const int col = nt * 8 + tq * 2 + e;
-                    s[nt][half * 2 + e] = p * drop_factor(thr, inv_keep, drop_row_key(thr, seed, qrow0 + r_loc[half], head), kb + col);
+                    s[nt][half * 2 + e] = p * drop_factor(thr, inv_keep, drop_row_key(thr, seed, qrow0 + r_loc[half], head), kb - s0 + col);
                 }
             sum = quad_sum(sum);
             lrow[half] = lrow[half] * corr + sum;
@@ -289,8 +286,8 @@ flash_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
     const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
     const int qrow0 = blk_row0[blockIdx.x];
     const int qrows = min(BLK, s1 - qrow0);
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    const uint32_t thr = adrop::thr8_of(drop_p);
+    const float inv_keep = adrop::inv_keep_of(thr);
     stage<HDP>(Qs, q, ldq, qrow0, qrows, col0, hd);
     stage<HDP>(Os, d_o, lddo, qrow0, qrows, col0, hd);
     cp_async_wait_all();
@@ -333,7 +330,7 @@ flash_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
                 const int half = e >> 1, col = nt * 8 + tq * 2 + (e & 1);
                 const bool ok = col < krows && r_loc[half] < qrows;
                 const float p = ok ? __expf(s[nt][e] * scale - lse_r[half]) : 0.f;
-                const float f = drop_factor(thr, inv_keep, drop_row_key(thr, seed, qrow0 + r_loc[half], head), kb + col);
+                const float f = drop_factor(thr, inv_keep, drop_row_key(thr, seed, qrow0 + r_loc[half], head), kb - s0 + col);
                 s[nt][e] = p * (dp[nt][e] * f - del_r[half]);              // dS
             }
         uint32_t da[4][4];
@@ -381,8 +378,8 @@ flash_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
     const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
     const int krow0 = blk_row0[blockIdx.x];
     const int krows = min(BLK, s1 - krow0);
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    const uint32_t thr = adrop::thr8_of(drop_p);
+    const float inv_keep = adrop::inv_keep_of(thr);
     stage<HDP>(Ks, k, ldk, krow0, krows, col0, hd);
     stage<HDP>(Vs, v, ldv, krow0, krows, col0, hd);
     cp_async_wait_all();
@@ -425,7 +422,7 @@ flash_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
                 const int half = e >> 1, qc = nt * 8 + tq * 2 + (e & 1);  // query column
                 const bool ok = qc < qrows && r_loc[half] < krows;
                 const float p = ok ? __expf(st[nt][e] * scale - lse_s[qc]) : 0.f;
-                const float f = drop_factor(thr, inv_keep, rk_s[qc], krow0 + r_loc[half]);
+                const float f = drop_factor(thr, inv_keep, rk_s[qc], krow0 - s0 + r_loc[half]);
                 pt[nt][e] = p * f;                                         // P~^T
                 st[nt][e] = p * (dpt[nt][e] * f - del_s[qc]);              // dS^T
             }
@@ -514,8 +511,8 @@ flash_fwd_res_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
     const int t_pad = (T + BLK - 1) / BLK * BLK;
     uint8_t* Ks = fa_smem;
     uint8_t* Vs = Ks + static_cast<size_t>(t_pad_max) * G::PITCH;
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    const uint32_t thr = adrop::thr8_of(drop_p);
+    const float inv_keep = adrop::inv_keep_of(thr);
     stage_seq<HDP>(Ks, k, ldk, s0, T, t_pad, col0, hd);
     stage_seq<HDP>(Vs, v, ldv, s0, T, t_pad, col0, hd);
     cp_async_wait_all();
@@ -561,7 +558,7 @@ flash_fwd_res_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
                         const float p = __expf(s[nt][half * 2 + e] - mx);
                         sum += p;
                         const int col = nt * 8 + tq * 2 + e;
-                        s[nt][half * 2 + e] = p * drop_factor(thr, inv_keep, drop_row_key(thr, seed, s0 + qb + r_loc[half], head), s0 + kb + col);
+                        s[nt][half * 2 + e] = p * drop_factor(thr, inv_keep, drop_row_key(thr, seed, s0 + qb + r_loc[half], head), kb + col);
                     }
                 sum = quad_sum(sum);
                 lrow[half] = lrow[half] * corr + sum;
@@ -616,8 +613,8 @@ flash_bwd_res_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
     float* lse_s = reinterpret_cast<float*>(Os + tile);
     float* del_s = lse_s + t_pad_max;
     uint32_t* rk_s = reinterpret_cast<uint32_t*>(del_s + t_pad_max);
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    const uint32_t thr = adrop::thr8_of(drop_p);
+    const float inv_keep = adrop::inv_keep_of(thr);
     stage_seq<HDP>(Qs, q, ldq, s0, T, t_pad, col0, hd);
     stage_seq<HDP>(Ks, k, ldk, s0, T, t_pad, col0, hd);
     stage_seq<HDP>(Vs, v, ldv, s0, T, t_pad, col0, hd);
@@ -674,7 +671,7 @@ flash_bwd_res_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
                     const int half = e >> 1, col = nt * 8 + tq * 2 + (e & 1);
                     const bool ok = col < krows && r_loc[half] < qrows;
                     const float p = ok ? __expf(s[nt][e] * scale - lse_r[half]) : 0.f;
-                    const float f = drop_factor(thr, inv_keep, rk_s[min(qb + r_loc[half], t_pad - 1)], s0 + kb + col);
+                    const float f = drop_factor(thr, inv_keep, rk_s[min(qb + r_loc[half], t_pad - 1)], kb + col);
                     s[nt][e] = p * (dp[nt][e] * f - del_r[half]);
                 }
             uint32_t da[4][4];
@@ -725,7 +722,7 @@ flash_bwd_res_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
                     const int half = e >> 1, qc = nt * 8 + tq * 2 + (e & 1);
                     const bool ok = qc < qrows && r_loc[half] < krows;
                     const float p = ok ? __expf(st[nt][e] * scale - lse_s[qb + qc]) : 0.f;
-                    const float f = drop_factor(thr, inv_keep, rk_s[qb + qc], s0 + kb + r_loc[half]);
+                    const float f = drop_factor(thr, inv_keep, rk_s[qb + qc], kb + r_loc[half]);
                     pt[nt][e] = p * f;
                     st[nt][e] = p * (dpt[nt][e] * f - del_s[qb + qc]);
                 }

@@ -28,33 +28,17 @@
 #include <cuda_bf16.h>
 #include <cstdint>
 
-#include "gemm_common.cuh"
+#include "attn_tc_common.cuh"
 
 namespace vsgg {
 namespace atc {
 
-constexpr int BQ = 128;                 // queries per CTA
-constexpr int BKV = 128;                // keys per block
-constexpr int TILE_BYTES = 128 * 128;   // 128 rows x 128-byte swizzled rows (64 bf16, head_dim zero-padded by TMA)
 constexpr int KV_STAGES = 2;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 256;
 constexpr int COL_S = 0, COL_P = 128, COL_O = 192;
 constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES) + 256 + 1024;   // tiles + barriers + alignment slack
 constexpr float RESCALE_THRESHOLD = 8.f;   // log2 domain: P stays below 2^8, exact in fp32 sums and fine in bf16
-
-// same mask function as the mma.sync backward kernels (attn_flash.cu): they regenerate it from (seed, row, head, key)
-__device__ __forceinline__ float drop_factor(uint32_t thr, float inv_keep, uint32_t row_key, int key) {
-    uint32_t h = row_key ^ (static_cast<uint32_t>(key) * 0x9E3779B1u);
-    h ^= h >> 16; h *= 0x85EBCA6Bu;
-    h ^= h >> 13; h *= 0xC2B2AE35u;
-    h ^= h >> 16;
-    return h >= thr ? inv_keep : 0.f;
-}
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t*>(&v);
-}
 
 template <int HDN>   // accumulator width of O: 32 (head_dim <= 32) or 64
 __global__ void __launch_bounds__(THREADS, 2)
@@ -178,9 +162,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
         const uint32_t t_s = tmem_base + lane_addr + COL_S, t_p = tmem_base + lane_addr + COL_P,
                        t_o = tmem_base + lane_addr + COL_O;
-        const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
-        const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-        const uint32_t row_key = thr ? hash_u32(seed, static_cast<unsigned long long>(qrow0 + row) * 64ull + head) : 0u;
+        // attention dropout (attn_dropout.cuh): one LCG draw per four keys, SWAR compare, the keep masks are ANDed into
+        // the packed bf16 pairs; the 1/(1-p) of the survivors is folded into the final normalisation of O
+        const uint32_t thr = adrop::thr8_of(drop_p);
+        const float inv_keep = thr ? adrop::inv_keep_of(thr) : 1.f;
+        const uint32_t K8 = (256u - thr) * 0x00010001u;
+        const uint32_t row_key = thr ? adrop::row_key(seed, qrow0 + row, head) : 0u;
         float m_ref = 0.f, l = 0.f;
         for (int j = 0; j < nkb; ++j) {
             const int kb = s0 + j * BKV;
@@ -226,13 +213,20 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                     pk[i] = pack2(p0, p1);
                 }
             } else {
+                const uint32_t kb64 = static_cast<uint32_t>(j) * 2u;      // key block of 64 relative to the clip start
+                const uint32_t sd[2] = {adrop::stream_seed(row_key, kb64), adrop::stream_seed(row_key, kb64 + 1u)};
 #pragma unroll
-                for (int i = 0; i < 64; ++i) {
-                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i]), scale_log2, -m_ref));
-                    const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m_ref));
-                    sum += p0 + p1;
-                    pk[i] = pack2(p0 * drop_factor(thr, inv_keep, row_key, kb + 2 * i),
-                                  p1 * drop_factor(thr, inv_keep, row_key, kb + 2 * i + 1));
+                for (int g4 = 0; g4 < 32; ++g4) {                          // groups of four keys
+                    float p[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        p[e] = ptx::ex2_approx(fmaf(__uint_as_float(r[4 * g4 + e]), scale_log2, -m_ref));
+                        sum += p[e];
+                    }
+                    uint32_t lo, hi;
+                    adrop::keep_masks4(adrop::draw(sd[g4 >> 4], (g4 & 15) >> 1, g4 & 1), K8, lo, hi);
+                    pk[2 * g4] = pack2(p[0], p[1]) & lo;
+                    pk[2 * g4 + 1] = pack2(p[2], p[3]) & hi;
                 }
             }
             l = l * alpha + sum;
@@ -267,7 +261,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             ptx::tmem_ld_32x32b_x32(t_o + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
         ptx::tmem_ld_wait();
         if (row < qrows) {
-            const float inv = 1.f / l;
+            const float inv = inv_keep / l;
             const size_t grow = static_cast<size_t>(qrow0 + row);
             __nv_bfloat16* dst = ctx + grow * ldc + head * hd;
 #pragma unroll
@@ -291,28 +285,6 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
-}
-
-// {head_dim, rows, heads} view of a [rows, heads * head_dim] bf16 matrix (pitch ld), box {64, 128, 1}, SWIZZLE_128B.
-static int make_tmap_heads(CUtensorMap* tm, const void* base, uint64_t hd, uint64_t rows, uint64_t heads, uint64_t ld) {
-    PFN_encodeTiled enc = get_encode_fn();
-    if (enc == nullptr) return set_error(B200VSGG_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
-    if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || ((ld * 2) & 15u) != 0 || ((hd * 2) & 15u) != 0)
-        return set_error(B200VSGG_ERR_BAD_ARG, "attn_tc: q/k/v must be 16-byte aligned, ld % 8 == 0, head_dim % 8 == 0");
-    cuuint64_t dims[3] = {hd, rows, heads};
-    cuuint64_t strides[2] = {ld * 2, hd * 2};
-    cuuint32_t box[3] = {64, 128, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        char msg[160];
-        snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d) for an attention operand hd=%llu rows=%llu ld=%llu",
-                 (int)r, (unsigned long long)hd, (unsigned long long)rows, (unsigned long long)ld);
-        return set_error(B200VSGG_ERR_TMAP, msg);
-    }
-    return 0;
 }
 
 }  // namespace atc

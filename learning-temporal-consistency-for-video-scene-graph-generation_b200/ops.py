@@ -16,6 +16,9 @@ launch_count = 0
 # When set to a list, every GEMM launch appends (M, N, K, a_mn, b_mn, start_event, end_event):
 # bench.py uses it to time the dominant kernel live with CUDA events on the launching stream.
 gemm_profile = None
+# Same for the TokenGT attention kernels: (kind, algorithmic flops, start_event, end_event); the caller passes the flops
+# (4 * sum T^2 * heads * head_dim forward, 2.5x that backward).
+attn_profile = None
 
 
 def _stream():
@@ -421,29 +424,65 @@ def attn_flash_fwd(q, k, v, seq_off, blk_seq, blk_row0, n_heads, head_dim, ctx, 
     _count()
 
 
-def attn_tc_fwd(q, k, v, seq_off, blk_seq128, blk_row0_128, n_heads, head_dim, ctx, lse=None, drop_p=0.0, seed=0):
+def _attn_prof_begin():
+    if attn_profile is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _attn_prof_end(kind, flops, e0):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        attn_profile.append((kind, flops, e0, e1))
+
+
+def attn_tc_fwd(q, k, v, seq_off, blk_seq128, blk_row0_128, n_heads, head_dim, ctx, lse=None, drop_p=0.0, seed=0,
+                flops=0.0):
     """tcgen05 / TMEM / TMA forward (b200vsgg_attn_tc_fwd); the block table has 128-row blocks."""
     scale = float(head_dim) ** -0.5
     rows = q.shape[0]
     assert k.shape[0] == rows and v.shape[0] == rows and ctx.shape[0] == rows
+    e0 = _attn_prof_begin()
     check(_lib.lib().b200vsgg_attn_tc_fwd(
         _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), rows, _ptr(seq_off),
         _ptr(blk_seq128), _ptr(blk_row0_128), blk_seq128.numel(), n_heads, head_dim, scale, _ptr(_bf(ctx)), ctx.stride(0),
         _ptr(lse), drop_p, seed, _stream()), "attn_tc_fwd")
+    _attn_prof_end("fwd", flops, e0)
     _count()
 
 
-def attn_flash_bwd(q, k, v, ctx, dctx, lse, seq_off, blk_seq, blk_row0, n_heads, head_dim, dq, dk, dv, drop_p=0.0, seed=0,
-                   max_len=0):
+def attn_tc_bwd(q, k, v, ctx, dctx, lse, seq_off, blk_seq128, blk_row0_128, n_heads, head_dim, dq, dk, dv, drop_p=0.0, seed=0,
+                flops=0.0):
+    """tcgen05 / TMEM backward (b200vsgg_attn_tc_bwd): delta, dQ and dK/dV kernels."""
     scale = float(head_dim) ** -0.5
     rows = q.shape[0]
     delta = torch.empty(rows, n_heads, device=q.device, dtype=torch.float32)
+    e0 = _attn_prof_begin()
+    check(_lib.lib().b200vsgg_attn_tc_bwd(
+        _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), _ptr(_bf(ctx)), ctx.stride(0),
+        _ptr(_bf(dctx)), dctx.stride(0), _ptr(lse), _ptr(delta), rows, _ptr(seq_off), _ptr(blk_seq128), _ptr(blk_row0_128),
+        blk_seq128.numel(), n_heads, head_dim, scale, _ptr(_bf(dq)), dq.stride(0), _ptr(_bf(dk)), dk.stride(0),
+        _ptr(_bf(dv)), dv.stride(0), drop_p, seed, _stream()), "attn_tc_bwd")
+    _attn_prof_end("bwd", flops, e0)
+    _count(3)
+
+
+def attn_flash_bwd(q, k, v, ctx, dctx, lse, seq_off, blk_seq, blk_row0, n_heads, head_dim, dq, dk, dv, drop_p=0.0, seed=0,
+                   max_len=0, flops=0.0):
+    scale = float(head_dim) ** -0.5
+    rows = q.shape[0]
+    delta = torch.empty(rows, n_heads, device=q.device, dtype=torch.float32)
+    e0 = _attn_prof_begin()
     check(_lib.lib().b200vsgg_attn_flash_bwd(
         _ptr(_bf(q)), q.stride(0), _ptr(_bf(k)), k.stride(0), _ptr(_bf(v)), v.stride(0), _ptr(_bf(ctx)), ctx.stride(0),
         _ptr(_bf(dctx)), dctx.stride(0), _ptr(lse), _ptr(delta), _ptr(seq_off), _ptr(blk_seq), _ptr(blk_row0),
         blk_seq.numel(), rows, n_heads, head_dim, scale, _ptr(_bf(dq)), dq.stride(0), _ptr(_bf(dk)), dk.stride(0),
         _ptr(_bf(dv)), dv.stride(0), drop_p, seed, _stream(), seq_off.numel() - 1 if max_len > 0 else 0, max_len),
           "attn_flash_bwd")
+    _attn_prof_end("bwd", flops, e0)
     _count(3)
 
 

@@ -341,7 +341,12 @@ class TEAT_GT(nn.Module):
         sp, tp = ops.teat_pair_flags(tok.detach(), entry["boxes"].contiguous(), plan.feat_row, plan.node_off,
                                      plan.has_prev, thr, SIM_THR, plan.nmax)
         sp_h = sp.cpu().numpy()
-        plan.build_graph(sp_h, tp.cpu().numpy(), self.lap_k, self.eig_threads, self.eig_backend)
+        tp_h = tp.cpu().numpy()
+        import time as _time
+        t_host = _time.perf_counter()
+        plan.build_graph(sp_h, tp_h, self.lap_k, self.eig_threads, self.eig_backend)
+        # host time of the reference-ordered edge compaction + LAPACK eigh (the device waits for it): bench.py reports it
+        self.last_host_graph_ms = (_time.perf_counter() - t_host) * 1e3
         desc = ops.upload(plan.desc_h, dev)
         ev = ops.upload(plan.eigvec_h, dev)
         evb = ops.cast_bf16(ev, drop_p=self.eig_dropout if train else 0.0, seed=seed0 + 17)

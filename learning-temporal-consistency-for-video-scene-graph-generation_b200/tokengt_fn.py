@@ -28,7 +28,8 @@ def _colsum(x):
 
 
 class AttnPlan:
-    """Device copies of the varlen attention plan (sequence offsets + 64-row block table)."""
+    """Device copies of the varlen attention plan: sequence offsets, the 64-row block table of the mma.sync backward
+    kernels and the 128-row block table of the tcgen05 forward (csrc/attn_tc.cu)."""
 
     def __init__(self, seq_off_h, device):
         import numpy as np
@@ -37,6 +38,11 @@ class AttnPlan:
         self.seq_off = ops.upload(np.asarray(seq_off_h, dtype=np.int32), device)
         self.blk_seq = ops.upload(bs, device)
         self.blk_row0 = ops.upload(br, device)
+        lens = np.diff(np.asarray(seq_off_h, dtype=np.float64))
+        self.sum_t2 = float((lens * lens).sum())       # algorithmic attention flops = 4 * sum_t2 * heads * head_dim
+        bs128, br128 = attention_blocks(seq_off_h, block=128)
+        self.blk_seq128 = ops.upload(bs128, device)
+        self.blk_row0_128 = ops.upload(br128, device)
         # 0 = tiled kernels.  The shared-memory-resident variants (pass the longest sequence length) are correct
         # but measured slower at the C3 shapes (occupancy: 1-2 CTAs/SM), see profiles/r01_flash_attention.txt
         self.max_len = 0
@@ -59,8 +65,9 @@ class PreLNAttention(torch.autograd.Function):
         ops.gemm(h, wqkv, bias=bqkv, out_bf16=qkv)
         att = _new(T, d, BF16, dev)
         lse = torch.empty(T, n_heads, device=dev)
-        ops.attn_flash_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], plan.seq_off, plan.blk_seq, plan.blk_row0, n_heads,
-                           hd, att, lse, p_attn, seed, plan.max_len)
+        # tcgen05 / TMEM / TMA forward; it writes the lse and uses the dropout mask function the backward kernels expect
+        ops.attn_tc_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], plan.seq_off, plan.blk_seq128, plan.blk_row0_128,
+                        n_heads, hd, att, lse, p_attn, seed, flops=4.0 * plan.sum_t2 * d)
         wob = _bf(wo)
         y = _new(T, d, F32, dev)
         ops.gemm(att, wob, bias=bo.detach(), residual=x, out_f32=y, dropout_p=p_out, seed=seed + 1)
@@ -83,9 +90,9 @@ class PreLNAttention(torch.autograd.Function):
         datt = _new(T, d, BF16, dev)
         ops.gemm(dyb, wob, b_mn=True, out_bf16=datt)
         dqkv = _new(T, 3 * d, BF16, dev)
-        ops.attn_flash_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, datt, lse, plan.seq_off, plan.blk_seq,
-                           plan.blk_row0, n_heads, hd, dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], p_attn, seed,
-                           plan.max_len)
+        ops.attn_tc_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], att, datt, lse, plan.seq_off, plan.blk_seq128,
+                        plan.blk_row0_128, n_heads, hd, dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:], p_attn, seed,
+                        flops=10.0 * plan.sum_t2 * d)
         dwqkv = _new(3 * d, d, F32, dev)
         ops.gemm(dqkv, h, a_mn=True, b_mn=True, out_f32=dwqkv)
         dbqkv = _colsum(dqkv)

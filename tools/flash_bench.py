@@ -31,5 +31,6 @@ for tag, lens, H, hd in (("C3 32x24", rng.integers(250, 460, 448), 32, 24), ("C3
         f = timeit(lambda: ops.attn_flash_fwd(q, k, v, offd, bsd, brd, H, hd, ctx, lse, p, 7))
         c = timeit(lambda: ops.attn_tc_fwd(q, k, v, offd, bs128d, br128d, H, hd, ctx, lse, p, 7))
         b = timeit(lambda: ops.attn_flash_bwd(q, k, v, ctx, dctx, lse, offd, bsd, brd, H, hd, dqkv[:, :D], dqkv[:, D:2*D], dqkv[:, 2*D:], p, 7))
-        print("%-10s p=%.1f  mma.sync fwd %.3f ms (%.1f TF/s) | tcgen05 fwd %.3f ms (%.1f TF/s) | mma.sync bwd %.3f ms (%.1f TF/s)  tokens %d" % (
-            tag, p, f, flops / f / 1e9, c, flops / c / 1e9, b, 2.5 * flops / b / 1e9, M), flush=True)
+        d = timeit(lambda: ops.attn_tc_bwd(q, k, v, ctx, dctx, lse, offd, bs128d, br128d, H, hd, dqkv[:, :D], dqkv[:, D:2*D], dqkv[:, 2*D:], p, 7))
+        print("%-10s p=%.1f  fwd mma.sync %.3f ms (%.1f TF/s) | fwd tcgen05 %.3f ms (%.1f TF/s) | bwd mma.sync %.3f ms (%.1f TF/s) | bwd tcgen05 %.3f ms (%.1f TF/s)  tokens %d" % (
+            tag, p, f, flops / f / 1e9, c, flops / c / 1e9, b, 2.5 * flops / b / 1e9, d, 2.5 * flops / d / 1e9, M), flush=True)
