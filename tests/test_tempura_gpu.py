@@ -282,9 +282,10 @@ def test_consistency_regulariser_extension_matches_oracle_restatement(cuda_lib):
         assert got.numel() > 0 and abs(got.numel() - ref.numel()) <= 4, (key, got.shape, ref.shape)
         floor = 1e-3 * ref.abs().max().item()
         gs, rs = got[got > floor], ref[ref > floor]
-        assert gs.shape == rs.shape and rs.numel() > 20, (key, gs.shape, rs.shape)
-        if got.numel() != ref.numel():
-            gs, rs = gs.sort().values, rs.sort().values
+        assert abs(gs.numel() - rs.numel()) <= 4 and rs.numel() > 20, (key, gs.shape, rs.shape)
+        if gs.numel() != rs.numel():      # values right at the floor fall on either side: compare from the largest down
+            n = min(gs.numel(), rs.numel())
+            gs, rs = gs.sort(descending=True).values[:n], rs.sort(descending=True).values[:n]
         err = (gs - rs).abs().max().item()
         print(key, "pairs", rs.numel(), "max-abs err %.3e of max %.3e" % (err, rs.abs().max().item()))
         assert err <= rtol * rs.abs().max().item() + 1e-6, (key, err, gs[:6], rs[:6])
