@@ -4,7 +4,8 @@
 // or 16 heads x 48, fp32 softmax, attention dropout.  The reference keeps [heads, T, T] maps for all 12 layers;
 // nothing of size T^2 leaves the SM here.
 //
-// One CTA = one 128-query tile of one (clip, head); 192 threads, two CTAs per SM:
+// Work unit = one 128-query tile of one (clip, head); PERSISTENT CTAs (two per SM, 192 threads) walk the unit list with
+// running barrier phases, so the pipeline never drains between units:
 //   warp 0    TMA producer: Q once, then a 2-stage ring of K tiles and one of V tiles.  The tensor maps are
 //             3-D {head_dim, token row, head} views of the [rows, heads*head_dim] activations with a {64, 128, 1} box:
 //             the columns head_dim..63 of a box lie outside dimension 0 and arrive as ZEROS, so a 24- or 48-wide
@@ -29,6 +30,7 @@
 #include <cstdint>
 
 #include "attn_tc_common.cuh"
+#include <cstdlib>
 
 namespace vsgg {
 namespace atc {
@@ -37,25 +39,26 @@ constexpr int KV_STAGES = 2;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 256;
 constexpr int COL_S = 0, COL_P = 128, COL_O = 192;
-constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES) + 256 + 1024;   // tiles + barriers + alignment slack
+constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 256 + 1024;   // tiles + barriers + alignment slack
 constexpr float RESCALE_THRESHOLD = 8.f;   // log2 domain: P stays below 2^8, exact in fp32 sums and fine in bf16
 
 template <int HDN>   // accumulator width of O: 32 (head_dim <= 32) or 64
 __global__ void __launch_bounds__(THREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const int32_t* __restrict__ seq_off,
-                   const int32_t* __restrict__ blk_seq, const int32_t* __restrict__ blk_row0, int n_blocks, int n_heads,
+                   const int32_t* __restrict__ blk_seq, const int32_t* __restrict__ blk_row0, int n_units, int n_heads,
                    int hd, float scale_log2, __nv_bfloat16* __restrict__ ctx, int ldc, float* __restrict__ lse,
                    float drop_p, unsigned long long seed) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-    uint8_t* Qs = smem;
-    uint8_t* Ks = Qs + TILE_BYTES;
+    uint8_t* Qs = smem;                                  // [2]: the next unit's queries land while this one computes
+    uint8_t* Ks = Qs + 2 * TILE_BYTES;
     uint8_t* Vs = Ks + KV_STAGES * TILE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + KV_STAGES * TILE_BYTES);
-    uint64_t* q_full = bars;
-    uint64_t* k_full = bars + 1;
+    uint64_t* q_full = bars;                             // [2]
+    uint64_t* q_empty = q_full + 2;                      // [2]
+    uint64_t* k_full = q_empty + 2;
     uint64_t* k_empty = k_full + KV_STAGES;
     uint64_t* v_full = k_empty + KV_STAGES;
     uint64_t* v_empty = v_full + KV_STAGES;
@@ -66,20 +69,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // consecutive CTAs = the heads of one query tile's neighbours: unit u -> (block = u / n_heads, head = u % n_heads)
-    // keeps the K/V rows of a clip hot in L2 while its query tiles and heads are in flight
-    const int blk = blockIdx.x / n_heads, head = blockIdx.x - blk * n_heads;
-    const int seq = blk_seq[blk];
-    const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
-    const int qrow0 = blk_row0[blk];
-    const int qrows = min(BQ, s1 - qrow0);
-    const int nkb = (s1 - s0 + BKV - 1) / BKV;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tq);
         ptx::prefetch_tmap(&tk);
         ptx::prefetch_tmap(&tv);
-        ptx::mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&q_full[i], 1);
+            ptx::mbar_init(&q_empty[i], 1);
+        }
         for (int i = 0; i < KV_STAGES; ++i) {
             ptx::mbar_init(&k_full[i], 1);
             ptx::mbar_init(&k_empty[i], 1);
@@ -101,20 +99,32 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // PERSISTENT: every role walks the same unit sequence u = blockIdx.x, + gridDim.x, ... (unit = 128-query tile x head;
+    // consecutive units = the heads of one tile, so a clip's K/V rows stay hot in L2) with RUNNING barrier phases: the
+    // producer is already fetching the next unit's Q / K / V and the MMA thread has issued its first S while the softmax
+    // warps still write this unit's output — no pipeline drain, TMEM allocation or barrier setup per tile.
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            ptx::mbar_expect_tx(q_full, TILE_BYTES);
-            ptx::tma_load_3d(Qs, &tq, q_full, 0, qrow0, head);
-            for (int j = 0; j < nkb; ++j) {
-                const int st = j % KV_STAGES;
-                const uint32_t ph = static_cast<uint32_t>(j / KV_STAGES) & 1u;
-                ptx::mbar_wait(&k_empty[st], ph ^ 1u);
-                ptx::mbar_expect_tx(&k_full[st], TILE_BYTES);
-                ptx::tma_load_3d(Ks + st * TILE_BYTES, &tk, &k_full[st], 0, s0 + j * BKV, head);
-                ptx::mbar_wait(&v_empty[st], ph ^ 1u);
-                ptx::mbar_expect_tx(&v_full[st], TILE_BYTES);
-                ptx::tma_load_3d(Vs + st * TILE_BYTES, &tv, &v_full[st], 0, s0 + j * BKV, head);
+            uint32_t qc = 0, kc = 0;                          // units / key tiles issued so far
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++qc) {
+                const int blk = u / n_heads, head = u - blk * n_heads;
+                const int seq = blk_seq[blk];
+                const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
+                const int nkb = (s1 - s0 + BKV - 1) / BKV;
+                const uint32_t qs = qc & 1u;
+                ptx::mbar_wait(&q_empty[qs], ((qc >> 1) & 1u) ^ 1u);
+                ptx::mbar_expect_tx(&q_full[qs], TILE_BYTES);
+                ptx::tma_load_3d(Qs + qs * TILE_BYTES, &tq, &q_full[qs], 0, blk_row0[blk], head);
+                for (int j = 0; j < nkb; ++j, ++kc) {
+                    const uint32_t st = kc % KV_STAGES, ph = (kc / KV_STAGES) & 1u;
+                    ptx::mbar_wait(&k_empty[st], ph ^ 1u);
+                    ptx::mbar_expect_tx(&k_full[st], TILE_BYTES);
+                    ptx::tma_load_3d(Ks + st * TILE_BYTES, &tk, &k_full[st], 0, s0 + j * BKV, head);
+                    ptx::mbar_wait(&v_empty[st], ph ^ 1u);
+                    ptx::mbar_expect_tx(&v_full[st], TILE_BYTES);
+                    ptx::tma_load_3d(Vs + st * TILE_BYTES, &tv, &v_full[st], 0, s0 + j * BKV, head);
+                }
             }
         }
     } else if (warp == 1) {
@@ -124,35 +134,45 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HDN, 0, 1);      // P: TMEM (K-major), V: MN-major
             const int ks_s = (hd + 15) >> 4;                                       // k-steps over head_dim
             const uint32_t t_s = tmem_base + COL_S, t_p = tmem_base + COL_P, t_o = tmem_base + COL_O;
-            const uint32_t qa = ptx::smem_u32(Qs);
-            auto issue_s = [&](int j) {
-                const int st = j % KV_STAGES;
-                ptx::mbar_wait(&k_full[st], static_cast<uint32_t>(j / KV_STAGES) & 1u);
-                if (j > 0) ptx::mbar_wait(s_free, static_cast<uint32_t>(j - 1) & 1u);   // S_{j-1} sits in registers
-                ptx::tc_fence_after();
-                const uint32_t kb = ptx::smem_u32(Ks + st * TILE_BYTES);
-                for (int k = 0; k < ks_s; ++k)
-                    ptx::umma_bf16(t_s, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024),
-                                   ptx::make_smem_desc_sw128(kb + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
-                ptx::umma_commit(&k_empty[st]);
-                ptx::umma_commit(s_full);
-            };
-            ptx::mbar_wait(q_full, 0);
-            issue_s(0);
-            for (int j = 0; j < nkb; ++j) {
-                if (j + 1 < nkb) issue_s(j + 1);
-                const int st = j % KV_STAGES;
-                const int kvalid = min(BKV, s1 - (s0 + j * BKV));
-                const int ks_o = (kvalid + 15) >> 4;                               // k-steps over the block's keys
-                ptx::mbar_wait(&v_full[st], static_cast<uint32_t>(j / KV_STAGES) & 1u);
-                ptx::mbar_wait(p_full, static_cast<uint32_t>(j) & 1u);
-                ptx::tc_fence_after();
-                const uint32_t vb = ptx::smem_u32(Vs + st * TILE_BYTES);
-                for (int k = 0; k < ks_o; ++k)
-                    ptx::umma_bf16_ts(t_o, t_p + k * 8, ptx::make_smem_desc_sw128(vb + k * 2048, 8192, 1024), idesc_o,
-                                      (j != 0 || k != 0) ? 1u : 0u);
-                ptx::umma_commit(&v_empty[st]);
-                ptx::umma_commit(o_done);
+            uint32_t qc = 0, g0 = 0;                          // units done, key tiles done before this unit
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++qc) {
+                const int blk = u / n_heads;
+                const int seq = blk_seq[blk];
+                const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
+                const int nkb = (s1 - s0 + BKV - 1) / BKV;
+                const uint32_t qs = qc & 1u;
+                const uint32_t qa = ptx::smem_u32(Qs + qs * TILE_BYTES);
+                auto issue_s = [&](int j) {
+                    const uint32_t g = g0 + j, st = g % KV_STAGES;
+                    ptx::mbar_wait(&k_full[st], (g / KV_STAGES) & 1u);
+                    if (g > 0) ptx::mbar_wait(s_free, (g - 1) & 1u);          // the previous S tile sits in registers
+                    ptx::tc_fence_after();
+                    const uint32_t kb = ptx::smem_u32(Ks + st * TILE_BYTES);
+                    for (int k = 0; k < ks_s; ++k)
+                        ptx::umma_bf16(t_s, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                                       ptx::make_smem_desc_sw128(kb + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+                    ptx::umma_commit(&k_empty[st]);
+                    if (j == nkb - 1) ptx::umma_commit(&q_empty[qs]);        // last product that reads this Q tile
+                    ptx::umma_commit(s_full);
+                };
+                ptx::mbar_wait(&q_full[qs], (qc >> 1) & 1u);
+                issue_s(0);
+                for (int j = 0; j < nkb; ++j) {
+                    if (j + 1 < nkb) issue_s(j + 1);
+                    const uint32_t g = g0 + j, st = g % KV_STAGES;
+                    const int kvalid = min(BKV, s1 - (s0 + j * BKV));
+                    const int ks_o = (kvalid + 15) >> 4;                           // k-steps over the block's keys
+                    ptx::mbar_wait(&v_full[st], (g / KV_STAGES) & 1u);
+                    ptx::mbar_wait(p_full, g & 1u);
+                    ptx::tc_fence_after();
+                    const uint32_t vb = ptx::smem_u32(Vs + st * TILE_BYTES);
+                    for (int k = 0; k < ks_o; ++k)
+                        ptx::umma_bf16_ts(t_o, t_p + k * 8, ptx::make_smem_desc_sw128(vb + k * 2048, 8192, 1024), idesc_o,
+                                          (j != 0 || k != 0) ? 1u : 0u);
+                    ptx::umma_commit(&v_empty[st]);
+                    ptx::umma_commit(o_done);
+                }
+                g0 += nkb;
             }
         }
     } else {
@@ -167,115 +187,125 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         const uint32_t thr = adrop::thr8_of(drop_p);
         const float inv_keep = thr ? adrop::inv_keep_of(thr) : 1.f;
         const uint32_t K8 = (256u - thr) * 0x00010001u;
-        const uint32_t row_key = thr ? adrop::row_key(seed, qrow0 + row, head) : 0u;
-        float m_ref = 0.f, l = 0.f;
-        for (int j = 0; j < nkb; ++j) {
-            const int kb = s0 + j * BKV;
-            const int kvalid = min(BKV, s1 - kb);
-            uint32_t r[128];
-            ptx::mbar_wait(s_full, static_cast<uint32_t>(j) & 1u);
-            ptx::tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                ptx::tmem_ld_32x32b_x32(t_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(r[c * 32]));
-            ptx::tmem_ld_wait();
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(s_free);                   // the next S MMA may overwrite the buffer
-            float mx = -INFINITY;
-            if (kvalid == BKV) {
-#pragma unroll
-                for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-            } else {
-#pragma unroll
-                for (int i = 0; i < 128; ++i) {
-                    if (i >= kvalid) r[i] = 0xff800000u;   // -inf: keys beyond the clip
-                    mx = fmaxf(mx, __uint_as_float(r[i]));
-                }
-            }
-            mx *= scale_log2;
-            float alpha = 1.f;
-            bool rescale = false;
-            if (j == 0) {
-                m_ref = mx;
-            } else if (mx > m_ref + RESCALE_THRESHOLD) {
-                alpha = ptx::ex2_approx(m_ref - mx);
-                m_ref = mx;
-                rescale = true;
-            }
-            float sum = 0.f;
-            uint32_t pk[64];
-            if (thr == 0u) {
-#pragma unroll
-                for (int i = 0; i < 64; ++i) {
-                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i]), scale_log2, -m_ref));
-                    const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m_ref));
-                    sum += p0 + p1;
-                    pk[i] = pack2(p0, p1);
-                }
-            } else {
-                const uint32_t kb64 = static_cast<uint32_t>(j) * 2u;      // key block of 64 relative to the clip start
-                const uint32_t sd[2] = {adrop::stream_seed(row_key, kb64), adrop::stream_seed(row_key, kb64 + 1u)};
-#pragma unroll
-                for (int g4 = 0; g4 < 32; ++g4) {                          // groups of four keys
-                    float p[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        p[e] = ptx::ex2_approx(fmaf(__uint_as_float(r[4 * g4 + e]), scale_log2, -m_ref));
-                        sum += p[e];
-                    }
-                    uint32_t lo, hi;
-                    adrop::keep_masks4(adrop::draw(sd[g4 >> 4], (g4 & 15) >> 1, g4 & 1), K8, lo, hi);
-                    pk[2 * g4] = pack2(p[0], p[1]) & lo;
-                    pk[2 * g4 + 1] = pack2(p[2], p[3]) & hi;
-                }
-            }
-            l = l * alpha + sum;
-            if (j > 0) {                                // P and O are free once the previous P V has retired
-                ptx::mbar_wait(o_done, static_cast<uint32_t>(j - 1) & 1u);
+        uint32_t g = 0;                                 // key tiles processed so far (barrier phases)
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int blk = u / n_heads, head = u - blk * n_heads;
+            const int seq = blk_seq[blk];
+            const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
+            const int qrow0 = blk_row0[blk];
+            const int qrows = min(BQ, s1 - qrow0);
+            const int nkb = (s1 - s0 + BKV - 1) / BKV;
+            const uint32_t row_key = thr ? adrop::row_key(seed, qrow0 + row, head) : 0u;
+            float m_ref = 0.f, l = 0.f;
+            for (int j = 0; j < nkb; ++j, ++g) {
+                const int kvalid = min(BKV, s1 - (s0 + j * BKV));
+                uint32_t r[128];
+                ptx::mbar_wait(s_full, g & 1u);
                 ptx::tc_fence_after();
-                if (__any_sync(0xffffffffu, rescale)) {
-                    uint32_t o[HDN];
 #pragma unroll
-                    for (int c = 0; c < HDN / 32; ++c)
-                        ptx::tmem_ld_32x32b_x32(t_o + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
-                    ptx::tmem_ld_wait();
+                for (int c = 0; c < 4; ++c)
+                    ptx::tmem_ld_32x32b_x32(t_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(r[c * 32]));
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(s_free);                   // the next S MMA may overwrite the buffer
+                float mx = -INFINITY;
+                if (kvalid == BKV) {
 #pragma unroll
-                    for (int i = 0; i < HDN; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                } else {
 #pragma unroll
-                    for (int c = 0; c < HDN / 32; ++c)
-                        ptx::tmem_st_32x32b_x32(t_o + c * 32, reinterpret_cast<const uint32_t(&)[32]>(o[c * 32]));
+                    for (int i = 0; i < 128; ++i) {
+                        if (i >= kvalid) r[i] = 0xff800000u;   // -inf: keys beyond the clip
+                        mx = fmaxf(mx, __uint_as_float(r[i]));
+                    }
                 }
-            }
-            ptx::tmem_st_32x32b_x32(t_p, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
-            ptx::tmem_st_32x32b_x32(t_p + 32, reinterpret_cast<const uint32_t(&)[32]>(pk[32]));
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(p_full);
-        }
-        // ---- epilogue: O / l -> bf16 context rows, log-sum-exp for the backward
-        ptx::mbar_wait(o_done, static_cast<uint32_t>(nkb - 1) & 1u);
-        ptx::tc_fence_after();
-        uint32_t o[HDN];
-#pragma unroll
-        for (int c = 0; c < HDN / 32; ++c)
-            ptx::tmem_ld_32x32b_x32(t_o + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
-        ptx::tmem_ld_wait();
-        if (row < qrows) {
-            const float inv = inv_keep / l;
-            const size_t grow = static_cast<size_t>(qrow0 + row);
-            __nv_bfloat16* dst = ctx + grow * ldc + head * hd;
-#pragma unroll
-            for (int c = 0; c < HDN / 8; ++c) {
-                if (c * 8 < hd) {
-                    uint4 u;
-                    u.x = pack2(__uint_as_float(o[c * 8]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
-                    u.y = pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
-                    u.z = pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
-                    u.w = pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
-                    *reinterpret_cast<uint4*>(dst + c * 8) = u;
+                mx *= scale_log2;
+                float alpha = 1.f;
+                bool rescale = false;
+                if (j == 0) {
+                    m_ref = mx;
+                } else if (mx > m_ref + RESCALE_THRESHOLD) {
+                    alpha = ptx::ex2_approx(m_ref - mx);
+                    m_ref = mx;
+                    rescale = true;
                 }
+                float sum = 0.f;
+                uint32_t pk[64];
+                if (thr == 0u) {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) {
+                        const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i]), scale_log2, -m_ref));
+                        const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m_ref));
+                        sum += p0 + p1;
+                        pk[i] = pack2(p0, p1);
+                    }
+                } else {
+                    const uint32_t kb64 = static_cast<uint32_t>(j) * 2u;      // key block of 64 relative to the clip start
+                    const uint32_t sd[2] = {adrop::stream_seed(row_key, kb64), adrop::stream_seed(row_key, kb64 + 1u)};
+#pragma unroll
+                    for (int g4 = 0; g4 < 32; ++g4) {                          // groups of four keys
+                        float p[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            p[e] = ptx::ex2_approx(fmaf(__uint_as_float(r[4 * g4 + e]), scale_log2, -m_ref));
+                            sum += p[e];
+                        }
+                        uint32_t lo, hi;
+                        adrop::keep_masks4(adrop::draw(sd[g4 >> 4], (g4 & 15) >> 1, g4 & 1), K8, lo, hi);
+                        pk[2 * g4] = pack2(p[0], p[1]) & lo;
+                        pk[2 * g4 + 1] = pack2(p[2], p[3]) & hi;
+                    }
+                }
+                l = l * alpha + sum;
+                if (j > 0) {                                // P and O are free once the previous P V has retired
+                    ptx::mbar_wait(o_done, (g - 1) & 1u);
+                    ptx::tc_fence_after();
+                    if (__any_sync(0xffffffffu, rescale)) {
+                        uint32_t o[HDN];
+#pragma unroll
+                        for (int c = 0; c < HDN / 32; ++c)
+                            ptx::tmem_ld_32x32b_x32(t_o + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < HDN; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+#pragma unroll
+                        for (int c = 0; c < HDN / 32; ++c)
+                            ptx::tmem_st_32x32b_x32(t_o + c * 32, reinterpret_cast<const uint32_t(&)[32]>(o[c * 32]));
+                    }
+                }
+                // (j == 0: the previous unit's epilogue below already waited for its last P V)
+                ptx::tmem_st_32x32b_x32(t_p, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
+                ptx::tmem_st_32x32b_x32(t_p + 32, reinterpret_cast<const uint32_t(&)[32]>(pk[32]));
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(p_full);
             }
-            if (lse != nullptr) lse[grow * n_heads + head] = (m_ref + __log2f(l)) * 0.6931471805599453f;
+            // ---- epilogue: O / l -> bf16 context rows, log-sum-exp for the backward.  The next unit's first P V comes
+            //      after this thread's next p_full arrival, i.e. after these loads of O.
+            ptx::mbar_wait(o_done, (g - 1) & 1u);
+            ptx::tc_fence_after();
+            uint32_t o[HDN];
+#pragma unroll
+            for (int c = 0; c < HDN / 32; ++c)
+                ptx::tmem_ld_32x32b_x32(t_o + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
+            ptx::tmem_ld_wait();
+            if (row < qrows) {
+                const float inv = inv_keep / l;
+                const size_t grow = static_cast<size_t>(qrow0 + row);
+                __nv_bfloat16* dst = ctx + grow * ldc + head * hd;
+#pragma unroll
+                for (int c = 0; c < HDN / 8; ++c) {
+                    if (c * 8 < hd) {
+                        uint4 v4;
+                        v4.x = pack2(__uint_as_float(o[c * 8]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
+                        v4.y = pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
+                        v4.z = pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
+                        v4.w = pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
+                        *reinterpret_cast<uint4*>(dst + c * 8) = v4;
+                    }
+                }
+                if (lse != nullptr) lse[grow * n_heads + head] = (m_ref + __log2f(l)) * 0.6931471805599453f;
+            }
         }
     }
     // ================================ teardown ================================
@@ -319,8 +349,16 @@ extern "C" int b200vsgg_attn_tc_fwd(const void* q, int32_t ldq, const void* k, i
         attr_set = true;
     }
     auto launch = [&](auto kern) -> int {
-        kern<<<static_cast<unsigned>(units), atc::THREADS, atc::SMEM_BYTES, (cudaStream_t)stream>>>(
-            tq, tk, tv, seq_off, blk_seq, blk_row0, n_blocks, n_heads, head_dim, scale_log2,
+        // Persistent (two CTAs per SM walk the unit list) when the softmax warps carry the dropout work; one unit per
+        // CTA otherwise.  Measured on B200 (tools/flash_bench.py, 32 heads x 24): training p = 0.1  1.90 -> 1.78 ms at the
+        // AG shapes; inference p = 0  1.50 ms per-unit vs 1.76 ms persistent (2.97 vs 3.38 ms on long clips) — with the
+        // cheaper softmax the hardware's dynamic CTA dispatch balances the ragged units better than the static stride.
+        // B200VSGG_ATTN_PERSIST=0/1 overrides (A/B timing).
+        static const int force = []() { const char* e = getenv("B200VSGG_ATTN_PERSIST"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+        const bool persist = force >= 0 ? force == 1 : drop_p > 0.f;
+        const long long resident = persist ? 2LL * num_sms() : units;
+        kern<<<static_cast<unsigned>(units < resident ? units : resident), atc::THREADS, atc::SMEM_BYTES, (cudaStream_t)stream>>>(
+            tq, tk, tv, seq_off, blk_seq, blk_row0, static_cast<int>(units), n_heads, head_dim, scale_log2,
             reinterpret_cast<__nv_bfloat16*>(ctx), ldc, lse, drop_p, seed);
         return 0;
     };

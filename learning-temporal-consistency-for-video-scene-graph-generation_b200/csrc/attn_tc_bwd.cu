@@ -22,6 +22,7 @@
 // Roofline: SFU/issue-bound like the forward (one exp per element and kernel: 2 x 1024 clk per tile pair of MUFU, ~9 and
 // ~13 issue slots per element with dropout) against 5 x 128 clk of tcgen05.mma per kernel.
 #include "attn_tc_common.cuh"
+#include <cstdlib>
 
 namespace vsgg {
 namespace atc {
@@ -54,26 +55,28 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int ldo, 
 // ================================================================================================================
 constexpr int DQ_COL_S = 0, DQ_COL_DP = 128, DQ_COL_DS = 256, DQ_COL_DQ = 320;
 constexpr int DQ_KST = 3;   // K_j feeds S_j (early) AND dQ_j (a whole softmax period later): 2 stages would stall the next S on the TMA
-constexpr int DQ_SMEM_BYTES = TILE_BYTES * (4 + DQ_KST) + 256 + 1024;
+constexpr int DQ_SMEM_BYTES = TILE_BYTES * (4 + DQ_KST + 2) + 256 + 1024;   // Q[2], dO[2], K[DQ_KST], V[2]
 
+// PERSISTENT like the forward: one CTA per SM walks units u = blockIdx.x, + gridDim.x, ... with running barrier phases.
 template <int HDN>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                   const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
                   const int32_t* __restrict__ seq_off, const int32_t* __restrict__ blk_seq,
-                  const int32_t* __restrict__ blk_row0, int n_heads, int hd, float scale,
+                  const int32_t* __restrict__ blk_row0, int n_units, int n_heads, int hd, float scale,
                   const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dq, int lddq,
                   float drop_p, unsigned long long seed) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-    uint8_t* Qs = smem;
-    uint8_t* dOs = Qs + TILE_BYTES;
-    uint8_t* Ks = dOs + TILE_BYTES;          // [DQ_KST]
-    uint8_t* Vs = Ks + DQ_KST * TILE_BYTES;  // [2]
+    uint8_t* Qs = smem;                       // [2]
+    uint8_t* dOs = Qs + 2 * TILE_BYTES;       // [2]
+    uint8_t* Ks = dOs + 2 * TILE_BYTES;       // [DQ_KST]
+    uint8_t* Vs = Ks + DQ_KST * TILE_BYTES;   // [2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + 2 * TILE_BYTES);
-    uint64_t* qo_full = bars;
-    uint64_t* k_full = bars + 1;
+    uint64_t* qo_full = bars;                 // [2]
+    uint64_t* qo_empty = qo_full + 2;         // [2]
+    uint64_t* k_full = qo_empty + 2;
     uint64_t* k_empty = k_full + DQ_KST;
     uint64_t* v_full = k_empty + DQ_KST;
     uint64_t* v_empty = v_full + 2;
@@ -84,26 +87,21 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int blk = blockIdx.x / n_heads, head = blockIdx.x - blk * n_heads;
-    const int seq = blk_seq[blk];
-    const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
-    const int qrow0 = blk_row0[blk];
-    const int qrows = min(BQ, s1 - qrow0);
-    const int nkb = (s1 - s0 + BKV - 1) / BKV;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tq);
         ptx::prefetch_tmap(&tk);
         ptx::prefetch_tmap(&tv);
         ptx::prefetch_tmap(&tdo);
-        ptx::mbar_init(qo_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&qo_full[i], 1);
+            ptx::mbar_init(&qo_empty[i], 1);
+            ptx::mbar_init(&v_full[i], 1);
+            ptx::mbar_init(&v_empty[i], 1);
+        }
         for (int i = 0; i < DQ_KST; ++i) {
             ptx::mbar_init(&k_full[i], 1);
             ptx::mbar_init(&k_empty[i], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(&v_full[i], 1);
-            ptx::mbar_init(&v_empty[i], 1);
         }
         ptx::mbar_init(sdp_full, 1);
         ptx::mbar_init(s_free, 256);
@@ -122,17 +120,27 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant_
 
     if (warp == 0) {
         if (lane == 0) {
-            ptx::mbar_expect_tx(qo_full, 2 * TILE_BYTES);
-            ptx::tma_load_3d(Qs, &tq, qo_full, 0, qrow0, head);
-            ptx::tma_load_3d(dOs, &tdo, qo_full, 0, qrow0, head);
-            for (int j = 0; j < nkb; ++j) {
-                const int kst = j % DQ_KST, vst = j & 1;
-                ptx::mbar_wait(&k_empty[kst], (static_cast<uint32_t>(j / DQ_KST) & 1u) ^ 1u);
-                ptx::mbar_expect_tx(&k_full[kst], TILE_BYTES);
-                ptx::tma_load_3d(Ks + kst * TILE_BYTES, &tk, &k_full[kst], 0, s0 + j * BKV, head);
-                ptx::mbar_wait(&v_empty[vst], (static_cast<uint32_t>(j >> 1) & 1u) ^ 1u);
-                ptx::mbar_expect_tx(&v_full[vst], TILE_BYTES);
-                ptx::tma_load_3d(Vs + vst * TILE_BYTES, &tv, &v_full[vst], 0, s0 + j * BKV, head);
+            uint32_t qc = 0, kc = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++qc) {
+                const int blk = u / n_heads, head = u - blk * n_heads;
+                const int seq = blk_seq[blk];
+                const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
+                const int nkb = (s1 - s0 + BKV - 1) / BKV;
+                const int qrow0 = blk_row0[blk];
+                const uint32_t qs = qc & 1u;
+                ptx::mbar_wait(&qo_empty[qs], ((qc >> 1) & 1u) ^ 1u);
+                ptx::mbar_expect_tx(&qo_full[qs], 2 * TILE_BYTES);
+                ptx::tma_load_3d(Qs + qs * TILE_BYTES, &tq, &qo_full[qs], 0, qrow0, head);
+                ptx::tma_load_3d(dOs + qs * TILE_BYTES, &tdo, &qo_full[qs], 0, qrow0, head);
+                for (int j = 0; j < nkb; ++j, ++kc) {
+                    const uint32_t kst = kc % DQ_KST, vst = kc & 1u;
+                    ptx::mbar_wait(&k_empty[kst], ((kc / DQ_KST) & 1u) ^ 1u);
+                    ptx::mbar_expect_tx(&k_full[kst], TILE_BYTES);
+                    ptx::tma_load_3d(Ks + kst * TILE_BYTES, &tk, &k_full[kst], 0, s0 + j * BKV, head);
+                    ptx::mbar_wait(&v_empty[vst], ((kc >> 1) & 1u) ^ 1u);
+                    ptx::mbar_expect_tx(&v_full[vst], TILE_BYTES);
+                    ptx::tma_load_3d(Vs + vst * TILE_BYTES, &tv, &v_full[vst], 0, s0 + j * BKV, head);
+                }
             }
         }
     } else if (warp == 1) {
@@ -142,38 +150,48 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant_
             const int ks_s = (hd + 15) >> 4;
             const uint32_t t_s = tmem_base + DQ_COL_S, t_dp = tmem_base + DQ_COL_DP, t_ds = tmem_base + DQ_COL_DS,
                            t_dq = tmem_base + DQ_COL_DQ;
-            const uint32_t qa = ptx::smem_u32(Qs), oa = ptx::smem_u32(dOs);
-            auto issue_sdp = [&](int j) {
-                const int kst = j % DQ_KST, st = j & 1;
-                ptx::mbar_wait(&k_full[kst], static_cast<uint32_t>(j / DQ_KST) & 1u);
-                ptx::mbar_wait(&v_full[st], static_cast<uint32_t>(j >> 1) & 1u);
-                if (j > 0) ptx::mbar_wait(s_free, static_cast<uint32_t>(j - 1) & 1u);
-                ptx::tc_fence_after();
-                const uint32_t kb = ptx::smem_u32(Ks + kst * TILE_BYTES), vb = ptx::smem_u32(Vs + st * TILE_BYTES);
-                for (int k = 0; k < ks_s; ++k)
-                    ptx::umma_bf16(t_s, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024),
-                                   ptx::make_smem_desc_sw128(kb + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
-                for (int k = 0; k < ks_s; ++k)
-                    ptx::umma_bf16(t_dp, ptx::make_smem_desc_sw128(oa + k * 32, 16, 1024),
-                                   ptx::make_smem_desc_sw128(vb + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
-                ptx::umma_commit(&v_empty[st]);
-                ptx::umma_commit(sdp_full);
-            };
-            ptx::mbar_wait(qo_full, 0);
-            issue_sdp(0);
-            for (int j = 0; j < nkb; ++j) {
-                if (j + 1 < nkb) issue_sdp(j + 1);
-                const int st = j % DQ_KST;
-                const int kvalid = min(BKV, s1 - (s0 + j * BKV));
-                const int ks_o = (kvalid + 15) >> 4;
-                ptx::mbar_wait(ds_full, static_cast<uint32_t>(j) & 1u);
-                ptx::tc_fence_after();
-                const uint32_t kb = ptx::smem_u32(Ks + st * TILE_BYTES);
-                for (int k = 0; k < ks_o; ++k)
-                    ptx::umma_bf16_ts(t_dq, t_ds + k * 8, ptx::make_smem_desc_sw128(kb + k * 2048, 8192, 1024), idesc_a,
-                                      (j != 0 || k != 0) ? 1u : 0u);
-                ptx::umma_commit(&k_empty[st]);
-                ptx::umma_commit(dq_done);
+            uint32_t qc = 0, g0 = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++qc) {
+                const int blk = u / n_heads;
+                const int seq = blk_seq[blk];
+                const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
+                const int nkb = (s1 - s0 + BKV - 1) / BKV;
+                const uint32_t qs = qc & 1u;
+                const uint32_t qa = ptx::smem_u32(Qs + qs * TILE_BYTES), oa = ptx::smem_u32(dOs + qs * TILE_BYTES);
+                auto issue_sdp = [&](int j) {
+                    const uint32_t g = g0 + j, kst = g % DQ_KST, vst = g & 1u;
+                    ptx::mbar_wait(&k_full[kst], (g / DQ_KST) & 1u);
+                    ptx::mbar_wait(&v_full[vst], (g >> 1) & 1u);
+                    if (g > 0) ptx::mbar_wait(s_free, (g - 1) & 1u);
+                    ptx::tc_fence_after();
+                    const uint32_t kb = ptx::smem_u32(Ks + kst * TILE_BYTES), vb = ptx::smem_u32(Vs + vst * TILE_BYTES);
+                    for (int k = 0; k < ks_s; ++k)
+                        ptx::umma_bf16(t_s, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                                       ptx::make_smem_desc_sw128(kb + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+                    for (int k = 0; k < ks_s; ++k)
+                        ptx::umma_bf16(t_dp, ptx::make_smem_desc_sw128(oa + k * 32, 16, 1024),
+                                       ptx::make_smem_desc_sw128(vb + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+                    ptx::umma_commit(&v_empty[vst]);
+                    if (j == nkb - 1) ptx::umma_commit(&qo_empty[qs]);       // last products that read Q / dO of this unit
+                    ptx::umma_commit(sdp_full);
+                };
+                ptx::mbar_wait(&qo_full[qs], (qc >> 1) & 1u);
+                issue_sdp(0);
+                for (int j = 0; j < nkb; ++j) {
+                    if (j + 1 < nkb) issue_sdp(j + 1);
+                    const uint32_t g = g0 + j, kst = g % DQ_KST;
+                    const int kvalid = min(BKV, s1 - (s0 + j * BKV));
+                    const int ks_o = (kvalid + 15) >> 4;
+                    ptx::mbar_wait(ds_full, g & 1u);
+                    ptx::tc_fence_after();
+                    const uint32_t kb = ptx::smem_u32(Ks + kst * TILE_BYTES);
+                    for (int k = 0; k < ks_o; ++k)
+                        ptx::umma_bf16_ts(t_dq, t_ds + k * 8, ptx::make_smem_desc_sw128(kb + k * 2048, 8192, 1024), idesc_a,
+                                          (j != 0 || k != 0) ? 1u : 0u);
+                    ptx::umma_commit(&k_empty[kst]);
+                    ptx::umma_commit(dq_done);
+                }
+                g0 += nkb;
             }
         }
     } else {
@@ -186,84 +204,95 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant_
         const uint32_t thr = adrop::thr8_of(drop_p);
         const float inv_keep = thr ? adrop::inv_keep_of(thr) : 1.f;
         const uint32_t K8 = (256u - thr) * 0x00010001u;
-        const bool row_ok = row < qrows;
-        const size_t gidx = static_cast<size_t>(qrow0 + (row_ok ? row : 0)) * n_heads + head;
-        const float lse2 = row_ok ? lse[gidx] * LOG2E : INFINITY;       // invalid rows: P = 0
-        const float delta_s = row_ok ? delta[gidx] / inv_keep : 0.f;    // dS = ik * P (keep ? dP : 0  -  delta / ik)
-        const uint32_t rk = thr ? adrop::row_key(seed, qrow0 + row, head) : 0u;
         const float scale_log2 = scale * LOG2E;
-        for (int j = 0; j < nkb; ++j) {
-            const int kvalid = min(BKV, s1 - (s0 + j * BKV)) - ch * 64;   // valid keys among this half's 64 columns
-            uint32_t rs[64], rd[64];
-            ptx::mbar_wait(sdp_full, static_cast<uint32_t>(j) & 1u);
-            ptx::tc_fence_after();
-            ptx::tmem_ld_32x32b_x32(t_s, reinterpret_cast<uint32_t(&)[32]>(rs[0]));
-            ptx::tmem_ld_32x32b_x32(t_s + 32, reinterpret_cast<uint32_t(&)[32]>(rs[32]));
-            ptx::tmem_ld_32x32b_x32(t_dp, reinterpret_cast<uint32_t(&)[32]>(rd[0]));
-            ptx::tmem_ld_32x32b_x32(t_dp + 32, reinterpret_cast<uint32_t(&)[32]>(rd[32]));
-            ptx::tmem_ld_wait();
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(s_free);
-            uint32_t pk[32];
-            const uint32_t sd = thr ? adrop::stream_seed(rk, static_cast<uint32_t>(j) * 2u + ch) : 0u;
-#pragma unroll
-            for (int g4 = 0; g4 < 16; ++g4) {
-                uint32_t e = 0x01000100u, o = 0x01000100u;
-                if (thr) {
-                    const uint32_t t = adrop::draw(sd, g4 >> 1, g4 & 1);
-                    e = ((t & 0x00FF00FFu) + K8) & 0x01000100u;
-                    o = (((t >> 8) & 0x00FF00FFu) + K8) & 0x01000100u;
-                }
-                float ds[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int i = 4 * g4 + c;
-                    const float p = ptx::ex2_approx(fmaf(__uint_as_float(rs[i]), scale_log2, -lse2));
-                    // keys (0,1) of the group sit in the even bytes (bits 8 / 24 of e), (2,3) in the odd ones
-                    const uint32_t bit = (c == 0) ? (e & 0x100u) : (c == 1) ? (e & 0x1000000u) : (c == 2) ? (o & 0x100u)
-                                                                                                           : (o & 0x1000000u);
-                    const float dpe = bit ? __uint_as_float(rd[i]) : 0.f;
-                    ds[c] = p * (dpe - delta_s);
-                }
-                pk[2 * g4] = pack2(ds[0], ds[1]);
-                pk[2 * g4 + 1] = pack2(ds[2], ds[3]);
-            }
-            if (kvalid < 64) {                          // last key tile of the clip: columns beyond it contribute nothing
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (2 * i >= kvalid) pk[i] = 0u;
-                    else if (2 * i + 1 >= kvalid) pk[i] &= 0x0000FFFFu;
-                }
-            }
-            if (j > 0) {
-                ptx::mbar_wait(dq_done, static_cast<uint32_t>(j - 1) & 1u);   // the previous dS has been consumed
+        uint32_t g = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int blk = u / n_heads, head = u - blk * n_heads;
+            const int seq = blk_seq[blk];
+            const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
+            const int qrow0 = blk_row0[blk];
+            const int qrows = min(BQ, s1 - qrow0);
+            const int nkb = (s1 - s0 + BKV - 1) / BKV;
+            const bool row_ok = row < qrows;
+            const size_t gidx = static_cast<size_t>(qrow0 + (row_ok ? row : 0)) * n_heads + head;
+            const float lse2 = row_ok ? lse[gidx] * LOG2E : INFINITY;       // invalid rows: P = 0
+            const float delta_s = row_ok ? delta[gidx] / inv_keep : 0.f;    // dS = ik * P (keep ? dP : 0  -  delta / ik)
+            const uint32_t rk = thr ? adrop::row_key(seed, qrow0 + row, head) : 0u;
+            for (int j = 0; j < nkb; ++j, ++g) {
+                const int kvalid = min(BKV, s1 - (s0 + j * BKV)) - ch * 64;   // valid keys among this half's 64 columns
+                uint32_t rs[64], rd[64];
+                ptx::mbar_wait(sdp_full, g & 1u);
                 ptx::tc_fence_after();
+                ptx::tmem_ld_32x32b_x32(t_s, reinterpret_cast<uint32_t(&)[32]>(rs[0]));
+                ptx::tmem_ld_32x32b_x32(t_s + 32, reinterpret_cast<uint32_t(&)[32]>(rs[32]));
+                ptx::tmem_ld_32x32b_x32(t_dp, reinterpret_cast<uint32_t(&)[32]>(rd[0]));
+                ptx::tmem_ld_32x32b_x32(t_dp + 32, reinterpret_cast<uint32_t(&)[32]>(rd[32]));
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(s_free);
+                uint32_t pk[32];
+                const uint32_t sd = thr ? adrop::stream_seed(rk, static_cast<uint32_t>(j) * 2u + ch) : 0u;
+#pragma unroll
+                for (int g4 = 0; g4 < 16; ++g4) {
+                    uint32_t e = 0x01000100u, o = 0x01000100u;
+                    if (thr) {
+                        const uint32_t t = adrop::draw(sd, g4 >> 1, g4 & 1);
+                        e = ((t & 0x00FF00FFu) + K8) & 0x01000100u;
+                        o = (((t >> 8) & 0x00FF00FFu) + K8) & 0x01000100u;
+                    }
+                    float ds[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int i = 4 * g4 + c;
+                        const float p = ptx::ex2_approx(fmaf(__uint_as_float(rs[i]), scale_log2, -lse2));
+                        // keys (0,1) of the group sit in the even bytes (bits 8 / 24 of e), (2,3) in the odd ones
+                        const uint32_t bit = (c == 0) ? (e & 0x100u) : (c == 1) ? (e & 0x1000000u) : (c == 2) ? (o & 0x100u)
+                                                                                                               : (o & 0x1000000u);
+                        const float dpe = bit ? __uint_as_float(rd[i]) : 0.f;
+                        ds[c] = p * (dpe - delta_s);
+                    }
+                    pk[2 * g4] = pack2(ds[0], ds[1]);
+                    pk[2 * g4 + 1] = pack2(ds[2], ds[3]);
+                }
+                if (kvalid < 64) {                          // last key tile of the clip: columns beyond it contribute nothing
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (2 * i >= kvalid) pk[i] = 0u;
+                        else if (2 * i + 1 >= kvalid) pk[i] &= 0x0000FFFFu;
+                    }
+                }
+                if (j > 0) {
+                    ptx::mbar_wait(dq_done, (g - 1) & 1u);   // the previous dS has been consumed
+                    ptx::tc_fence_after();
+                }
+                ptx::tmem_st_32x32b_x32(t_ds, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(ds_full);
             }
-            ptx::tmem_st_32x32b_x32(t_ds, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(ds_full);
-        }
-        ptx::mbar_wait(dq_done, static_cast<uint32_t>(nkb - 1) & 1u);
-        ptx::tc_fence_after();
-        if (ch == 0) {
-            uint32_t o[HDN];
+            // epilogue (warpgroup 0; warpgroup 1 moves on, but the next unit's first dQ MMA needs ALL 256 ds_full
+            // arrivals, i.e. it comes after these loads of the accumulator)
+            ptx::mbar_wait(dq_done, (g - 1) & 1u);
+            ptx::tc_fence_after();
+            if (ch == 0) {
+                uint32_t o[HDN];
 #pragma unroll
-            for (int c = 0; c < HDN / 32; ++c)
-                ptx::tmem_ld_32x32b_x32(t_dq + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
-            ptx::tmem_ld_wait();
-            if (row_ok) {
-                const float f = scale * inv_keep;
-                __nv_bfloat16* dst = dq + static_cast<size_t>(qrow0 + row) * lddq + head * hd;
+                for (int c = 0; c < HDN / 32; ++c)
+                    ptx::tmem_ld_32x32b_x32(t_dq + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
+                ptx::tmem_ld_wait();
+                if (row_ok) {
+                    const float f = scale * inv_keep;
+                    __nv_bfloat16* dst = dq + static_cast<size_t>(qrow0 + row) * lddq + head * hd;
 #pragma unroll
-                for (int c = 0; c < HDN / 8; ++c) {
-                    if (c * 8 < hd) {
-                        uint4 u;
-                        u.x = pack2(__uint_as_float(o[c * 8]) * f, __uint_as_float(o[c * 8 + 1]) * f);
-                        u.y = pack2(__uint_as_float(o[c * 8 + 2]) * f, __uint_as_float(o[c * 8 + 3]) * f);
-                        u.z = pack2(__uint_as_float(o[c * 8 + 4]) * f, __uint_as_float(o[c * 8 + 5]) * f);
-                        u.w = pack2(__uint_as_float(o[c * 8 + 6]) * f, __uint_as_float(o[c * 8 + 7]) * f);
-                        *reinterpret_cast<uint4*>(dst + c * 8) = u;
+                    for (int c = 0; c < HDN / 8; ++c) {
+                        if (c * 8 < hd) {
+                            uint4 v4;
+                            v4.x = pack2(__uint_as_float(o[c * 8]) * f, __uint_as_float(o[c * 8 + 1]) * f);
+                            v4.y = pack2(__uint_as_float(o[c * 8 + 2]) * f, __uint_as_float(o[c * 8 + 3]) * f);
+                            v4.z = pack2(__uint_as_float(o[c * 8 + 4]) * f, __uint_as_float(o[c * 8 + 5]) * f);
+                            v4.w = pack2(__uint_as_float(o[c * 8 + 6]) * f, __uint_as_float(o[c * 8 + 7]) * f);
+                            *reinterpret_cast<uint4*>(dst + c * 8) = v4;
+                        }
                     }
                 }
             }
@@ -283,27 +312,28 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant_
 constexpr int KV_COL_S = 0, KV_COL_DP = 128, KV_COL_P = 256, KV_COL_DS = 320, KV_COL_DV = 384, KV_COL_DK = 448;
 constexpr int KV_QST = 3;   // Q_i / dO_i feed the S-type products (early) AND the accumulating ones (late): 3 ring stages
 constexpr int KV_AUX_BYTES = KV_QST * 128 * 4 * 6;   // per ring stage: lse2, delta, 4 dropout seed rows (2 key blocks x 2 h)
-constexpr int KV_SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_QST) + KV_AUX_BYTES + 256 + 1024;
+constexpr int KV_SMEM_BYTES = TILE_BYTES * (4 + 2 * KV_QST) + KV_AUX_BYTES + 256 + 1024;   // K[2], V[2], Q[3], dO[3]
 
 template <int HDN>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
                    const int32_t* __restrict__ seq_off, const int32_t* __restrict__ blk_seq,
-                   const int32_t* __restrict__ blk_row0, int n_heads, int hd, float scale,
+                   const int32_t* __restrict__ blk_row0, int n_units, int n_heads, int hd, float scale,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dk, int lddk,
                    __nv_bfloat16* __restrict__ dv, int lddv, float drop_p, unsigned long long seed) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-    uint8_t* Ks = smem;
-    uint8_t* Vs = Ks + TILE_BYTES;
-    uint8_t* Qs = Vs + TILE_BYTES;                // [KV_QST]
+    uint8_t* Ks = smem;                           // [2]
+    uint8_t* Vs = Ks + 2 * TILE_BYTES;            // [2]
+    uint8_t* Qs = Vs + 2 * TILE_BYTES;            // [KV_QST]
     uint8_t* dOs = Qs + KV_QST * TILE_BYTES;      // [KV_QST]
     float* aux = reinterpret_cast<float*>(dOs + KV_QST * TILE_BYTES);   // [KV_QST stages][6][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(aux) + KV_AUX_BYTES);
-    uint64_t* kv_full = bars;
-    uint64_t* qo_full = bars + 1;            // [KV_QST]
+    uint64_t* kv_full = bars;                // [2]
+    uint64_t* kv_empty = kv_full + 2;        // [2]
+    uint64_t* qo_full = kv_empty + 2;        // [KV_QST]
     uint64_t* qo_empty = qo_full + KV_QST;   // [KV_QST]
     uint64_t* sdp_full = qo_empty + KV_QST;
     uint64_t* s_free = sdp_full + 1;
@@ -312,12 +342,6 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int blk = blockIdx.x / n_heads, head = blockIdx.x - blk * n_heads;
-    const int seq = blk_seq[blk];
-    const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
-    const int krow0 = blk_row0[blk];
-    const int krows = min(BKV, s1 - krow0);
-    const int nqb = (s1 - s0 + BQ - 1) / BQ;
     const uint32_t thr = adrop::thr8_of(drop_p);
     const float inv_keep = thr ? adrop::inv_keep_of(thr) : 1.f;
 
@@ -326,7 +350,10 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         ptx::prefetch_tmap(&tk);
         ptx::prefetch_tmap(&tv);
         ptx::prefetch_tmap(&tdo);
-        ptx::mbar_init(kv_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&kv_full[i], 1);
+            ptx::mbar_init(&kv_empty[i], 1);
+        }
         for (int i = 0; i < KV_QST; ++i) {
             ptx::mbar_init(&qo_full[i], 33);      // expect_tx arrival of lane 0 + 32 lanes that staged lse / delta / seeds
             ptx::mbar_init(&qo_empty[i], 257);    // tcgen05.commit of the accumulating MMAs + 256 softmax threads
@@ -348,41 +375,50 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 
     if (warp == 0) {
         // ================================ producer: TMA tiles + per-query scalars ================================
-        if (lane == 0) {
-            ptx::mbar_expect_tx(kv_full, 2 * TILE_BYTES);
-            ptx::tma_load_3d(Ks, &tk, kv_full, 0, krow0, head);
-            ptx::tma_load_3d(Vs, &tv, kv_full, 0, krow0, head);
-        }
-        const uint32_t kb64 = static_cast<uint32_t>(krow0 - s0) >> 6;        // first 64-key block of this tile
-        for (int i = 0; i < nqb; ++i) {
-            const int st = i % KV_QST;
-            const uint32_t ph = static_cast<uint32_t>(i / KV_QST) & 1u;
-            ptx::mbar_wait(&qo_empty[st], ph ^ 1u);
-            const int qb = s0 + i * BQ;
+        uint32_t uc = 0, qc = 0;                         // units / query tiles issued so far
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
+            const int blk = u / n_heads, head = u - blk * n_heads;
+            const int seq = blk_seq[blk];
+            const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
+            const int krow0 = blk_row0[blk];
+            const int nqb = (s1 - s0 + BQ - 1) / BQ;
+            const uint32_t ks = uc & 1u;
+            ptx::mbar_wait(&kv_empty[ks], ((uc >> 1) & 1u) ^ 1u);
             if (lane == 0) {
-                ptx::mbar_expect_tx(&qo_full[st], 2 * TILE_BYTES);
-                ptx::tma_load_3d(Qs + st * TILE_BYTES, &tq, &qo_full[st], 0, qb, head);
-                ptx::tma_load_3d(dOs + st * TILE_BYTES, &tdo, &qo_full[st], 0, qb, head);
+                ptx::mbar_expect_tx(&kv_full[ks], 2 * TILE_BYTES);
+                ptx::tma_load_3d(Ks + ks * TILE_BYTES, &tk, &kv_full[ks], 0, krow0, head);
+                ptx::tma_load_3d(Vs + ks * TILE_BYTES, &tv, &kv_full[ks], 0, krow0, head);
             }
-            float* a = aux + st * 6 * 128;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int c = r * 32 + lane, q = qb + c;
-                const bool ok = q < s1;
-                const size_t gi = static_cast<size_t>(ok ? q : s0) * n_heads + head;
-                a[c] = ok ? lse[gi] * LOG2E : INFINITY;                       // invalid query columns: P = 0
-                a[128 + c] = ok ? delta[gi] / inv_keep : 0.f;
-                if (thr) {
-                    const uint32_t rk = adrop::row_key(seed, q, head);
-                    const uint32_t sa = adrop::stream_seed(rk, kb64), sb = adrop::stream_seed(rk, kb64 + 1u);
-                    uint32_t* u = reinterpret_cast<uint32_t*>(a);
-                    u[256 + c] = sa;                    // key block 0, h = 0
-                    u[384 + c] = sa + adrop::DELTA;     // key block 0, h = 1
-                    u[512 + c] = sb;                    // key block 1, h = 0
-                    u[640 + c] = sb + adrop::DELTA;     // key block 1, h = 1
+            const uint32_t kb64 = static_cast<uint32_t>(krow0 - s0) >> 6;        // first 64-key block of this tile
+            for (int i = 0; i < nqb; ++i, ++qc) {
+                const uint32_t st = qc % KV_QST, ph = (qc / KV_QST) & 1u;
+                ptx::mbar_wait(&qo_empty[st], ph ^ 1u);
+                const int qb = s0 + i * BQ;
+                if (lane == 0) {
+                    ptx::mbar_expect_tx(&qo_full[st], 2 * TILE_BYTES);
+                    ptx::tma_load_3d(Qs + st * TILE_BYTES, &tq, &qo_full[st], 0, qb, head);
+                    ptx::tma_load_3d(dOs + st * TILE_BYTES, &tdo, &qo_full[st], 0, qb, head);
                 }
+                float* a = aux + st * 6 * 128;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int c = r * 32 + lane, q = qb + c;
+                    const bool ok = q < s1;
+                    const size_t gi = static_cast<size_t>(ok ? q : s0) * n_heads + head;
+                    a[c] = ok ? lse[gi] * LOG2E : INFINITY;                       // invalid query columns: P = 0
+                    a[128 + c] = ok ? delta[gi] / inv_keep : 0.f;
+                    if (thr) {
+                        const uint32_t rk = adrop::row_key(seed, q, head);
+                        const uint32_t sa = adrop::stream_seed(rk, kb64), sb = adrop::stream_seed(rk, kb64 + 1u);
+                        uint32_t* w = reinterpret_cast<uint32_t*>(a);
+                        w[256 + c] = sa;                    // key block 0, h = 0
+                        w[384 + c] = sa + adrop::DELTA;     // key block 0, h = 1
+                        w[512 + c] = sb;                    // key block 1, h = 0
+                        w[640 + c] = sb + adrop::DELTA;     // key block 1, h = 1
+                    }
+                }
+                ptx::mbar_arrive(&qo_full[st]);
             }
-            ptx::mbar_arrive(&qo_full[st]);
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -391,39 +427,49 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             const int ks_s = (hd + 15) >> 4;
             const uint32_t t_s = tmem_base + KV_COL_S, t_dp = tmem_base + KV_COL_DP, t_p = tmem_base + KV_COL_P,
                            t_ds = tmem_base + KV_COL_DS, t_dv = tmem_base + KV_COL_DV, t_dk = tmem_base + KV_COL_DK;
-            const uint32_t ka = ptx::smem_u32(Ks), va = ptx::smem_u32(Vs);
-            auto issue_sdp = [&](int i) {
-                const int st = i % KV_QST;
-                ptx::mbar_wait(&qo_full[st], static_cast<uint32_t>(i / KV_QST) & 1u);
-                if (i > 0) ptx::mbar_wait(s_free, static_cast<uint32_t>(i - 1) & 1u);
-                ptx::tc_fence_after();
-                const uint32_t qb = ptx::smem_u32(Qs + st * TILE_BYTES), ob = ptx::smem_u32(dOs + st * TILE_BYTES);
-                for (int k = 0; k < ks_s; ++k)
-                    ptx::umma_bf16(t_s, ptx::make_smem_desc_sw128(ka + k * 32, 16, 1024),
-                                   ptx::make_smem_desc_sw128(qb + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
-                for (int k = 0; k < ks_s; ++k)
-                    ptx::umma_bf16(t_dp, ptx::make_smem_desc_sw128(va + k * 32, 16, 1024),
-                                   ptx::make_smem_desc_sw128(ob + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
-                ptx::umma_commit(sdp_full);
-            };
-            ptx::mbar_wait(kv_full, 0);
-            issue_sdp(0);
-            for (int i = 0; i < nqb; ++i) {
-                if (i + 1 < nqb) issue_sdp(i + 1);
-                const int st = i % KV_QST;
-                const int qvalid = min(BQ, s1 - (s0 + i * BQ));
-                const int ks_o = (qvalid + 15) >> 4;
-                ptx::mbar_wait(pds_full, static_cast<uint32_t>(i) & 1u);
-                ptx::tc_fence_after();
-                const uint32_t qb = ptx::smem_u32(Qs + st * TILE_BYTES), ob = ptx::smem_u32(dOs + st * TILE_BYTES);
-                for (int k = 0; k < ks_o; ++k)
-                    ptx::umma_bf16_ts(t_dv, t_p + k * 8, ptx::make_smem_desc_sw128(ob + k * 2048, 8192, 1024), idesc_a,
-                                      (i != 0 || k != 0) ? 1u : 0u);
-                for (int k = 0; k < ks_o; ++k)
-                    ptx::umma_bf16_ts(t_dk, t_ds + k * 8, ptx::make_smem_desc_sw128(qb + k * 2048, 8192, 1024), idesc_a,
-                                      (i != 0 || k != 0) ? 1u : 0u);
-                ptx::umma_commit(&qo_empty[st]);
-                ptx::umma_commit(acc_done);
+            uint32_t uc = 0, g0 = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uc) {
+                const int blk = u / n_heads;
+                const int seq = blk_seq[blk];
+                const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
+                const int nqb = (s1 - s0 + BQ - 1) / BQ;
+                const uint32_t ks = uc & 1u;
+                const uint32_t ka = ptx::smem_u32(Ks + ks * TILE_BYTES), va = ptx::smem_u32(Vs + ks * TILE_BYTES);
+                auto issue_sdp = [&](int i) {
+                    const uint32_t g = g0 + i, st = g % KV_QST;
+                    ptx::mbar_wait(&qo_full[st], (g / KV_QST) & 1u);
+                    if (g > 0) ptx::mbar_wait(s_free, (g - 1) & 1u);
+                    ptx::tc_fence_after();
+                    const uint32_t qb = ptx::smem_u32(Qs + st * TILE_BYTES), ob = ptx::smem_u32(dOs + st * TILE_BYTES);
+                    for (int k = 0; k < ks_s; ++k)
+                        ptx::umma_bf16(t_s, ptx::make_smem_desc_sw128(ka + k * 32, 16, 1024),
+                                       ptx::make_smem_desc_sw128(qb + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+                    for (int k = 0; k < ks_s; ++k)
+                        ptx::umma_bf16(t_dp, ptx::make_smem_desc_sw128(va + k * 32, 16, 1024),
+                                       ptx::make_smem_desc_sw128(ob + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+                    if (i == nqb - 1) ptx::umma_commit(&kv_empty[ks]);     // last products that read this unit's K / V
+                    ptx::umma_commit(sdp_full);
+                };
+                ptx::mbar_wait(&kv_full[ks], (uc >> 1) & 1u);
+                issue_sdp(0);
+                for (int i = 0; i < nqb; ++i) {
+                    if (i + 1 < nqb) issue_sdp(i + 1);
+                    const uint32_t g = g0 + i, st = g % KV_QST;
+                    const int qvalid = min(BQ, s1 - (s0 + i * BQ));
+                    const int ks_o = (qvalid + 15) >> 4;
+                    ptx::mbar_wait(pds_full, g & 1u);
+                    ptx::tc_fence_after();
+                    const uint32_t qb = ptx::smem_u32(Qs + st * TILE_BYTES), ob = ptx::smem_u32(dOs + st * TILE_BYTES);
+                    for (int k = 0; k < ks_o; ++k)
+                        ptx::umma_bf16_ts(t_dv, t_p + k * 8, ptx::make_smem_desc_sw128(ob + k * 2048, 8192, 1024), idesc_a,
+                                          (i != 0 || k != 0) ? 1u : 0u);
+                    for (int k = 0; k < ks_o; ++k)
+                        ptx::umma_bf16_ts(t_dk, t_ds + k * 8, ptx::make_smem_desc_sw128(qb + k * 2048, 8192, 1024), idesc_a,
+                                          (i != 0 || k != 0) ? 1u : 0u);
+                    ptx::umma_commit(&qo_empty[st]);
+                    ptx::umma_commit(acc_done);
+                }
+                g0 += nqb;
             }
         }
     } else {
@@ -445,81 +491,91 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         const int sh = 8 * (((k64 & 1) << 1) | ((k64 >> 1) & 1));
         const uint32_t byte_mask = 0xFFu << sh, thr_sh = thr << sh;
         const int seed_row = 256 + ((row >> 6) * 2 + ((k64 >> 2) & 1)) * 128;      // which of the 4 staged seed rows
-        for (int i = 0; i < nqb; ++i) {
-            const int st = i % KV_QST;
-            uint32_t rs[64], rd[64];
-            ptx::mbar_wait(sdp_full, static_cast<uint32_t>(i) & 1u);
-            ptx::tc_fence_after();
-            ptx::tmem_ld_32x32b_x32(t_s, reinterpret_cast<uint32_t(&)[32]>(rs[0]));
-            ptx::tmem_ld_32x32b_x32(t_s + 32, reinterpret_cast<uint32_t(&)[32]>(rs[32]));
-            ptx::tmem_ld_32x32b_x32(t_dp, reinterpret_cast<uint32_t(&)[32]>(rd[0]));
-            ptx::tmem_ld_32x32b_x32(t_dp + 32, reinterpret_cast<uint32_t(&)[32]>(rd[32]));
-            ptx::tmem_ld_wait();
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(s_free);
-            ptx::mbar_wait(&qo_full[st], static_cast<uint32_t>(i / KV_QST) & 1u);  // lse / delta / seeds of this tile
-            const float* a = aux + st * 6 * 128 + ch * 64;
-            const uint32_t* sdrow = reinterpret_cast<const uint32_t*>(aux + st * 6 * 128) + seed_row + ch * 64;
-            uint32_t pp[32], pd[32];
-#pragma unroll
-            for (int g4 = 0; g4 < 16; ++g4) {
-                const float4 l4 = *reinterpret_cast<const float4*>(a + 4 * g4);
-                const float4 d4 = *reinterpret_cast<const float4*>(a + 128 + 4 * g4);
-                uint4 s4 = make_uint4(0u, 0u, 0u, 0u);
-                if (thr) s4 = *reinterpret_cast<const uint4*>(sdrow + 4 * g4);
-                const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
-                const uint32_t sv[4] = {s4.x, s4.y, s4.z, s4.w};
-                float p[4], ds[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int col = 4 * g4 + c;
-                    const float pr = ptx::ex2_approx(fmaf(__uint_as_float(rs[col]), scale_log2, -lv[c]));
-                    bool kept = true;
-                    if (thr) {
-                        const uint32_t s = sv[c] * la + lc;
-                        kept = ((s ^ (s >> 16)) & byte_mask) >= thr_sh;
-                    }
-                    p[c] = kept ? pr : 0.f;
-                    ds[c] = pr * ((kept ? __uint_as_float(rd[col]) : 0.f) - dl[c]);
-                }
-                pp[2 * g4] = pack2(p[0], p[1]);
-                pp[2 * g4 + 1] = pack2(p[2], p[3]);
-                pd[2 * g4] = pack2(ds[0], ds[1]);
-                pd[2 * g4 + 1] = pack2(ds[2], ds[3]);
-            }
-            ptx::mbar_arrive(&qo_empty[st]);                                       // the staged scalars have been read
-            if (i > 0) {
-                ptx::mbar_wait(acc_done, static_cast<uint32_t>(i - 1) & 1u);       // previous P~ / dS consumed
+        uint32_t g = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int blk = u / n_heads, head = u - blk * n_heads;
+            const int seq = blk_seq[blk];
+            const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
+            const int krow0 = blk_row0[blk];
+            const int krows = min(BKV, s1 - krow0);
+            const int nqb = (s1 - s0 + BQ - 1) / BQ;
+            for (int i = 0; i < nqb; ++i, ++g) {
+                const uint32_t st = g % KV_QST;
+                uint32_t rs[64], rd[64];
+                ptx::mbar_wait(sdp_full, g & 1u);
                 ptx::tc_fence_after();
+                ptx::tmem_ld_32x32b_x32(t_s, reinterpret_cast<uint32_t(&)[32]>(rs[0]));
+                ptx::tmem_ld_32x32b_x32(t_s + 32, reinterpret_cast<uint32_t(&)[32]>(rs[32]));
+                ptx::tmem_ld_32x32b_x32(t_dp, reinterpret_cast<uint32_t(&)[32]>(rd[0]));
+                ptx::tmem_ld_32x32b_x32(t_dp + 32, reinterpret_cast<uint32_t(&)[32]>(rd[32]));
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(s_free);
+                ptx::mbar_wait(&qo_full[st], (g / KV_QST) & 1u);                   // lse / delta / seeds of this tile
+                const float* a = aux + st * 6 * 128 + ch * 64;
+                const uint32_t* sdrow = reinterpret_cast<const uint32_t*>(aux + st * 6 * 128) + seed_row + ch * 64;
+                uint32_t pp[32], pd[32];
+#pragma unroll
+                for (int g4 = 0; g4 < 16; ++g4) {
+                    const float4 l4 = *reinterpret_cast<const float4*>(a + 4 * g4);
+                    const float4 d4 = *reinterpret_cast<const float4*>(a + 128 + 4 * g4);
+                    uint4 s4 = make_uint4(0u, 0u, 0u, 0u);
+                    if (thr) s4 = *reinterpret_cast<const uint4*>(sdrow + 4 * g4);
+                    const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+                    const uint32_t sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                    float p[4], ds[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int col = 4 * g4 + c;
+                        const float pr = ptx::ex2_approx(fmaf(__uint_as_float(rs[col]), scale_log2, -lv[c]));
+                        bool kept = true;
+                        if (thr) {
+                            const uint32_t sx = sv[c] * la + lc;
+                            kept = ((sx ^ (sx >> 16)) & byte_mask) >= thr_sh;
+                        }
+                        p[c] = kept ? pr : 0.f;
+                        ds[c] = pr * ((kept ? __uint_as_float(rd[col]) : 0.f) - dl[c]);
+                    }
+                    pp[2 * g4] = pack2(p[0], p[1]);
+                    pp[2 * g4 + 1] = pack2(p[2], p[3]);
+                    pd[2 * g4] = pack2(ds[0], ds[1]);
+                    pd[2 * g4 + 1] = pack2(ds[2], ds[3]);
+                }
+                ptx::mbar_arrive(&qo_empty[st]);                                   // the staged scalars have been read
+                if (i > 0) {
+                    ptx::mbar_wait(acc_done, (g - 1) & 1u);                        // previous P~ / dS consumed
+                    ptx::tc_fence_after();
+                }
+                ptx::tmem_st_32x32b_x32(t_p, reinterpret_cast<const uint32_t(&)[32]>(pp[0]));
+                ptx::tmem_st_32x32b_x32(t_ds, reinterpret_cast<const uint32_t(&)[32]>(pd[0]));
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(pds_full);
             }
-            ptx::tmem_st_32x32b_x32(t_p, reinterpret_cast<const uint32_t(&)[32]>(pp[0]));
-            ptx::tmem_st_32x32b_x32(t_ds, reinterpret_cast<const uint32_t(&)[32]>(pd[0]));
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(pds_full);
-        }
-        ptx::mbar_wait(acc_done, static_cast<uint32_t>(nqb - 1) & 1u);
-        ptx::tc_fence_after();
-        // warpgroup 0 stores dV, warpgroup 1 stores dK
-        uint32_t o[HDN];
-        const uint32_t t_acc = ch == 0 ? t_dv : t_dk;
+            ptx::mbar_wait(acc_done, (g - 1) & 1u);
+            ptx::tc_fence_after();
+            // warpgroup 0 stores dV, warpgroup 1 stores dK (the next unit's first accumulating MMA needs all 256
+            // pds_full arrivals, so it comes after both warpgroups have read their accumulator)
+            uint32_t o[HDN];
+            const uint32_t t_acc = ch == 0 ? t_dv : t_dk;
 #pragma unroll
-        for (int c = 0; c < HDN / 32; ++c)
-            ptx::tmem_ld_32x32b_x32(t_acc + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
-        ptx::tmem_ld_wait();
-        if (row < krows) {
-            const float f = ch == 0 ? inv_keep : scale * inv_keep;
-            __nv_bfloat16* dst = (ch == 0 ? dv + static_cast<size_t>(krow0 + row) * lddv
-                                          : dk + static_cast<size_t>(krow0 + row) * lddk) + head * hd;
+            for (int c = 0; c < HDN / 32; ++c)
+                ptx::tmem_ld_32x32b_x32(t_acc + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
+            ptx::tmem_ld_wait();
+            if (row < krows) {
+                const float f = ch == 0 ? inv_keep : scale * inv_keep;
+                __nv_bfloat16* dst = (ch == 0 ? dv + static_cast<size_t>(krow0 + row) * lddv
+                                              : dk + static_cast<size_t>(krow0 + row) * lddk) + head * hd;
 #pragma unroll
-            for (int c = 0; c < HDN / 8; ++c) {
-                if (c * 8 < hd) {
-                    uint4 u;
-                    u.x = pack2(__uint_as_float(o[c * 8]) * f, __uint_as_float(o[c * 8 + 1]) * f);
-                    u.y = pack2(__uint_as_float(o[c * 8 + 2]) * f, __uint_as_float(o[c * 8 + 3]) * f);
-                    u.z = pack2(__uint_as_float(o[c * 8 + 4]) * f, __uint_as_float(o[c * 8 + 5]) * f);
-                    u.w = pack2(__uint_as_float(o[c * 8 + 6]) * f, __uint_as_float(o[c * 8 + 7]) * f);
-                    *reinterpret_cast<uint4*>(dst + c * 8) = u;
+                for (int c = 0; c < HDN / 8; ++c) {
+                    if (c * 8 < hd) {
+                        uint4 v4;
+                        v4.x = pack2(__uint_as_float(o[c * 8]) * f, __uint_as_float(o[c * 8 + 1]) * f);
+                        v4.y = pack2(__uint_as_float(o[c * 8 + 2]) * f, __uint_as_float(o[c * 8 + 3]) * f);
+                        v4.z = pack2(__uint_as_float(o[c * 8 + 4]) * f, __uint_as_float(o[c * 8 + 5]) * f);
+                        v4.w = pack2(__uint_as_float(o[c * 8 + 6]) * f, __uint_as_float(o[c * 8 + 7]) * f);
+                        *reinterpret_cast<uint4*>(dst + c * 8) = v4;
+                    }
                 }
             }
         }
@@ -572,20 +628,23 @@ extern "C" int b200vsgg_attn_tc_bwd(const void* q, int32_t ldq, const void* k, i
         head_dim, delta);
     const long long units = static_cast<long long>(n_blocks) * n_heads;
     if (units > 0x7fffffffLL) return set_error(B200VSGG_ERR_BAD_ARG, "attn_tc_bwd: too many (tile, head) units");
-    const unsigned grid = static_cast<unsigned>(units);
+    // persistent: one CTA per SM walks the unit list (B200VSGG_ATTN_PERSIST=0: one unit per CTA, for A/B timing)
+    static const bool persist = []() { const char* e = getenv("B200VSGG_ATTN_PERSIST"); return !(e && e[0] == '0'); }();
+    const unsigned grid = static_cast<unsigned>((!persist || units < num_sms()) ? units : num_sms());
+    const int n_units = static_cast<int>(units);
     if (head_dim <= 32) {
         atc::attn_tc_dq_kernel<32><<<grid, atc::BWD_THREADS, atc::DQ_SMEM_BYTES, s>>>(
-            tq, tk, tv, tdo, seq_off, blk_seq, blk_row0, n_heads, head_dim, scale, lse, delta,
+            tq, tk, tv, tdo, seq_off, blk_seq, blk_row0, n_units, n_heads, head_dim, scale, lse, delta,
             reinterpret_cast<__nv_bfloat16*>(dq), lddq, drop_p, seed);
         atc::attn_tc_dkv_kernel<32><<<grid, atc::BWD_THREADS, atc::KV_SMEM_BYTES, s>>>(
-            tq, tk, tv, tdo, seq_off, blk_seq, blk_row0, n_heads, head_dim, scale, lse, delta,
+            tq, tk, tv, tdo, seq_off, blk_seq, blk_row0, n_units, n_heads, head_dim, scale, lse, delta,
             reinterpret_cast<__nv_bfloat16*>(dk), lddk, reinterpret_cast<__nv_bfloat16*>(dv), lddv, drop_p, seed);
     } else {
         atc::attn_tc_dq_kernel<64><<<grid, atc::BWD_THREADS, atc::DQ_SMEM_BYTES, s>>>(
-            tq, tk, tv, tdo, seq_off, blk_seq, blk_row0, n_heads, head_dim, scale, lse, delta,
+            tq, tk, tv, tdo, seq_off, blk_seq, blk_row0, n_units, n_heads, head_dim, scale, lse, delta,
             reinterpret_cast<__nv_bfloat16*>(dq), lddq, drop_p, seed);
         atc::attn_tc_dkv_kernel<64><<<grid, atc::BWD_THREADS, atc::KV_SMEM_BYTES, s>>>(
-            tq, tk, tv, tdo, seq_off, blk_seq, blk_row0, n_heads, head_dim, scale, lse, delta,
+            tq, tk, tv, tdo, seq_off, blk_seq, blk_row0, n_units, n_heads, head_dim, scale, lse, delta,
             reinterpret_cast<__nv_bfloat16*>(dk), lddk, reinterpret_cast<__nv_bfloat16*>(dv), lddv, drop_p, seed);
     }
     VSGG_CUDA_CHECK_LAUNCH();
