@@ -477,6 +477,32 @@ def teatgt_section(args, dev, rank, world, peaks):
 
 
 
+def pin_to_gpu_numa_node(local_rank):
+    """Run this rank's host thread (and therefore first-touch its pinned staging buffers) on the NUMA node its GPU hangs
+    off: at N >= 4 the staging of all ranks otherwise sits on node 0 and the far-socket GPUs copy across the socket
+    link (round 1: e2e 67 -> 125 -> 157 ms per step at N = 1 / 4 / 8).  Best effort; returns what was done."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"gpu_pci": bus, "numa_node": node, "pinned": False, "why": "single-node host or node unknown"}
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"gpu_pci": bus, "numa_node": node, "pinned": False, "why": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, allowed)
+        return {"gpu_pci": bus, "numa_node": node, "pinned": True, "cpus": len(allowed)}
+    except Exception as ex:
+        return {"pinned": False, "why": "%s: %s" % (type(ex).__name__, ex)}
+
+
 def workload_config(args, world):
     return {"workload": "TEMPURA PredCLS fwd+bwd, %d synthetic AG videos per GPU (%d frames, 6-10 pairs/frame), "
                         "BASELINE configs[1]%s" % (args.videos, args.frames,
@@ -520,13 +546,12 @@ def main():
         run_reference_arm(args)
         return
 
-    import torch
-    import torch.distributed as dist
-    from b200vsgg import ddp, ops, synthetic, tempura
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    from b200vsgg import ddp, ops, synthetic, tempura
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
@@ -534,6 +559,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    numa_info = (pin_to_gpu_numa_node(local_rank) if world > 1 else
+                 {"pinned": False, "why": "single rank: the host threads keep every core (CPU baseline runs in this process)"})
 
     # ---- model (random init of the reference architecture) and this rank's shard of videos
     torch.manual_seed(1123)
@@ -546,6 +574,7 @@ def main():
     vids = [rank * args.videos + v for v in range(args.videos)]
     batch = build_batch(vids, args.frames, dev)
     n_pairs = int(batch["pair_idx"].shape[0])
+    ddp.broadcast_state(model)            # every rank starts from rank 0's parameters and buffers
     sync = ddp.GradSync(list(model.parameters())[::-1]).attach(model) if world > 1 else None
     # TEMPURA_train.py:111,224-225: AdamW(lr, weight_decay=0.1) after clip_grad_norm_(5) — fused, 2 launches
     from b200vsgg.optim import FusedAdamW
@@ -605,6 +634,17 @@ def main():
     launches = ops.launch_count - launches0
     gemm_prof, ops.gemm_profile = ops.gemm_profile, None
     clock_info = clocks.stop()
+    comm = None
+    if sync is not None:
+        # what the post-backward exchange costs ON the compute stream: waits for the layer-bucket all-reduces issued
+        # during backward + the bucketed rest (copy in, all-reduce, copy out); everything else overlapped
+        ev = sync.comm_events[-args.steps:]
+        exposed = sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev))
+        comm = {"comm_exposed_ms_per_step": max_over_ranks(exposed),
+                "layer_buckets": len(sync._layer_flat), "layer_bucket_mb": sum(t.numel() * 4 for t in sync._layer_flat) / 1e6,
+                "note": "CUDA events around GradSync.sync() on the compute stream, max over ranks"}
+        sync.comm_events = []
+        ddp.sync_buffers(model)           # BatchNorm running statistics: averaged over the ranks (outside the timed region)
     total_pairs = sum_over_ranks(float(n_pairs))
     value = total_pairs * args.steps / (ms_total * 1e-3)
     loss_val = float(loss.item())
@@ -654,71 +694,94 @@ def main():
                                     "tflops": 2.0 * M * N * K * cnt / (ms * 1e-3) / 1e12}) + "\n")
 
     # ============================== end-to-end (host inputs) ==============================
-    e2e = None
+    # Two hand-off contracts, same step, same videos:
+    #   reference_fp32_nchw   what tools/utils/object_detector.py:372-396 produces today: union_feat fp32 [N,1024,7,7],
+    #                         spatial_masks fp32 [N,2,27,27] (3.55 GB per 64-video step: PCIe-bound)
+    #   producer_bf16_nhwc    SURVEY.md §8 (f).4: the detector emits what the path consumes — union_feat bf16 channels-
+    #                         last rows, bf16 masks (tempura.to_producer_contract): half the bytes, no layout kernel,
+    #                         bit-identical outputs (tests/test_tempura_gpu.py)
+    # `e2e` (the contract's headline key) is the reference contract; `e2e_producer_contract` sits beside it.
+    e2e = e2e_fast = None
     if not args.no_e2e:
+        fast_dev = tempura.to_producer_contract({"union_feat": batch["union_feat"], "spatial_masks": batch["spatial_masks"]})
+        fast_host = {k: fast_dev[k].cpu().pin_memory() for k in ("union_feat", "spatial_masks")}
+        del fast_dev
         host = {k: batch[k].cpu().pin_memory() for k in TENSOR_KEYS if k in batch}
         gt_host = tuple(t.cpu().pin_memory() for t in batch["gt_tensors"])
-        h2d = sum(t.numel() * t.element_size() for t in host.values()) + sum(t.numel() * t.element_size() for t in gt_host)
-        bufs = []
-        for _ in range(2):
-            bufs.append(({k: torch.empty_like(batch[k]) for k in host}, tuple(torch.empty_like(t) for t in batch["gt_tensors"])))
+        meta = {k: batch[k] for k in ("video_frames", "frame_counts_host", "pair_idx_host", "video_size")}
+        gt_like = batch["gt_tensors"]
+        small_like = {k: batch[k] for k in host if k not in ("union_feat", "spatial_masks")}
         del batch["union_feat"], batch["spatial_masks"]
+        torch.cuda.empty_cache()
         copy_stream = torch.cuda.Stream(device=dev)
-        ready = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
 
-        def issue_copy(slot):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[slot])
-                dst, gdst = bufs[slot]
-                for k, t in host.items():
-                    # bulk tensors go in 16 MB slices: the small (pageable) index uploads that the step issues on
-                    # the compute stream share the H2D copy engine and would otherwise wait for the whole 3.3 GB
-                    n, chunk = t.numel(), (16 << 20) // t.element_size()
-                    if n <= chunk:
-                        dst[k].copy_(t, non_blocking=True)
-                    else:
-                        df, sf = dst[k].view(-1), t.view(-1)
-                        for i in range(0, n, chunk):
-                            df[i:i + chunk].copy_(sf[i:i + chunk], non_blocking=True)
-                for d, s in zip(gdst, gt_host):
-                    d.copy_(s, non_blocking=True)
-                ready[slot].record(copy_stream)
+        def run_e2e(host_set):
+            h2d = sum(t.numel() * t.element_size() for t in host_set.values()) + sum(t.numel() * t.element_size() for t in gt_host)
+            bufs = [({k: torch.empty(t.shape, dtype=t.dtype, device=dev) for k, t in host_set.items()},
+                     tuple(torch.empty_like(t) for t in gt_like)) for _ in range(2)]
+            ready = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_loop(n):
-            for s in range(2):
-                consumed[s].record()
-            issue_copy(0)
-            last = None
-            for i in range(n):
-                slot = i & 1
-                if i + 1 < n:
-                    issue_copy(slot ^ 1)
-                torch.cuda.current_stream().wait_event(ready[slot])
-                dst, gdst = bufs[slot]
-                entry = dict(dst)
-                entry["video_frames"] = batch["video_frames"]
-                entry["frame_counts_host"] = batch["frame_counts_host"]
-                entry["pair_idx_host"] = batch["pair_idx_host"]
-                entry["video_size"] = batch["video_size"]
-                entry["gt_tensors"] = gdst
-                loss = run_step(entry)
-                consumed[slot].record()
-                last = float(loss.item())  # device -> host read of the step's result
-            return last
+            def issue_copy(slot):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[slot])
+                    dst, gdst = bufs[slot]
+                    for k, t in host_set.items():
+                        # one cudaMemcpyAsync per 64 MB slice (index vectors no longer use the copy engine: the model
+                        # uploads them with a kernel that reads pinned memory, so nothing small queues behind these)
+                        n, chunk = t.numel(), (64 << 20) // t.element_size()
+                        if n <= chunk:
+                            dst[k].copy_(t, non_blocking=True)
+                        else:
+                            df, sf = dst[k].view(-1), t.view(-1)
+                            for i in range(0, n, chunk):
+                                df[i:i + chunk].copy_(sf[i:i + chunk], non_blocking=True)
+                    for d, s_ in zip(gdst, gt_host):
+                        d.copy_(s_, non_blocking=True)
+                    ready[slot].record(copy_stream)
 
-        e2e_loop(max(args.warmup, 3))
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        e2e_loop(args.steps)
-        t1.record()
-        barrier()
-        e2e_ms = max_over_ranks(t0.elapsed_time(t1))
-        e2e = {"value": total_pairs * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
-               "how": "model.forward(entry)+loss+backward on pinned-host inputs, H2D double-buffered on a copy stream"}
+            def loop(n):
+                for s_ in range(2):
+                    consumed[s_].record()
+                issue_copy(0)
+                last = None
+                for i in range(n):
+                    slot = i & 1
+                    if i + 1 < n:
+                        issue_copy(slot ^ 1)
+                    torch.cuda.current_stream().wait_event(ready[slot])
+                    dst, gdst = bufs[slot]
+                    entry = dict(dst)
+                    entry.update(meta)
+                    entry["gt_tensors"] = gdst
+                    loss_ = run_step(entry)
+                    consumed[slot].record()
+                    last = float(loss_.item())  # device -> host read of the step's result
+                return last
+
+            loop(max(args.warmup, 3))
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            loop(args.steps)
+            t1.record()
+            barrier()
+            ms = max_over_ranks(t0.elapsed_time(t1))
+            del bufs
+            torch.cuda.empty_cache()
+            return {"value": total_pairs * args.steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms / args.steps,
+                    "h2d_gb_per_s_per_gpu": h2d / (ms / args.steps * 1e-3) / 1e9}
+
+        e2e = run_e2e(host)
+        e2e["contract"] = "reference_fp32_nchw (tools/utils/object_detector.py:372-396 as is)"
+        e2e["how"] = "model.forward(entry)+loss+backward+clip+AdamW on pinned-host inputs, H2D double-buffered on a copy stream"
+        host_fast = dict(host)
+        host_fast.update(fast_host)
+        del host["union_feat"], host["spatial_masks"]
+        e2e_fast = run_e2e(host_fast)
+        e2e_fast["contract"] = "producer_bf16_nhwc (SURVEY 8(f).4: union_feat bf16 [N,7,7,1024], masks bf16; outputs bit-identical)"
+        e2e_fast["numa"] = numa_info
 
     # ============================== CPU baseline (rank 0, N = 1) ==============================
     cpu = None
@@ -758,7 +821,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
-                "clocks": clock_info, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "clocks": clock_info, "e2e": e2e, "e2e_producer_contract": e2e_fast, "comm": comm,
+                "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu, "library_baseline": lib, "teatgt": teat, "loss": loss_val,
                 "model_tflops": 1.138e9 * value / 1e12}
         print(json.dumps(line), flush=True)

@@ -206,6 +206,9 @@ int b200vsgg_nhwc_to_nchw_f32(const float* in, int32_t n, int32_t channels, int3
  */
 /* masks fp32 [n,2,27,27] -> bf16 rows [n*196, ld]; column c*49+kh*7+kw for the 98 taps, zero up to ld (ld>=104). */
 int b200vsgg_mask_im2col(const float* masks, int32_t n, void* out, int32_t ld, void* stream);
+/* Same for the producer-side hand-off ((f).4, tools/utils/object_detector.py:372-380 emitting what the path consumes):
+ * masks bf16 [n,2,27,27].  The im2col rows are bf16 either way, so nothing is lost against the fp32 hand-off. */
+int b200vsgg_mask_im2col_bf16(const void* masks, int32_t n, void* out, int32_t ld, void* stream);
 /* Segmented column statistics: chunk table int32 [n_chunks,3] = (row_begin,row_end,group);
  * sum1[g,c] += sum_r a[r,c]; sum2[g,c] += sum_r a[r,c]*b[r,c] (b, sum2 nullable; b is bf16, or b == a for
  * sums of squares of either type). */

@@ -44,6 +44,7 @@ SIGNATURES = {
     "b200vsgg_nchw_to_nhwc_f32": [vp, i32, i32, i32, vp, vp],
     "b200vsgg_nhwc_to_nchw_f32": [vp, i32, i32, i32, vp, vp],
     "b200vsgg_mask_im2col": [vp, i32, vp, i32, vp],
+    "b200vsgg_mask_im2col_bf16": [vp, i32, vp, i32, vp],
     "b200vsgg_seg_colstats": [vp, i32, i32, vp, i32, i32, vp, i32, vp, vp, vp],
     "b200vsgg_seg_affine": [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp],
     "b200vsgg_bn_pool_fwd": [vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp],

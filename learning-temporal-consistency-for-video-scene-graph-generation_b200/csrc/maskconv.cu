@@ -25,12 +25,13 @@ static inline int blocks_for(long long items, int per_block) {
 // One CTA per pair: the 5.8 kB of masks are staged in shared memory, then 196 x ld outputs are
 // written with 16-byte stores.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mask_im2col_kernel(const float* __restrict__ masks, int n,
+template <typename T>   // float: the reference's fp32 hand-off; __nv_bfloat16: the producer-side bf16 hand-off ((f).4)
+__global__ void __launch_bounds__(256) mask_im2col_kernel(const T* __restrict__ masks, int n,
                                                           __nv_bfloat16* __restrict__ out, int ld) {
     __shared__ float sm[2 * 27 * 27];
     const int p = blockIdx.x;
-    const float* src = masks + static_cast<size_t>(p) * (2 * 27 * 27);
-    for (int i = threadIdx.x; i < 2 * 27 * 27; i += blockDim.x) sm[i] = src[i];
+    const T* src = masks + static_cast<size_t>(p) * (2 * 27 * 27);
+    for (int i = threadIdx.x; i < 2 * 27 * 27; i += blockDim.x) sm[i] = static_cast<float>(src[i]);
     __syncthreads();
     const int vec_per_row = ld >> 3;
     __nv_bfloat16* dst = out + static_cast<size_t>(p) * 196 * ld;
@@ -387,7 +388,16 @@ using namespace vsgg;
 extern "C" int b200vsgg_mask_im2col(const float* masks, int32_t n, void* out, int32_t ld, void* stream) {
     if (!masks || !out || n < 0 || ld < 104 || (ld & 7)) return set_error(B200VSGG_ERR_BAD_ARG, "mask_im2col: bad arg");
     if (n == 0) return 0;
-    mask_im2col_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(masks, n, (__nv_bfloat16*)out, ld);
+    mask_im2col_kernel<float><<<n, 256, 0, (cudaStream_t)stream>>>(masks, n, (__nv_bfloat16*)out, ld);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200vsgg_mask_im2col_bf16(const void* masks, int32_t n, void* out, int32_t ld, void* stream) {
+    if (!masks || !out || n < 0 || ld < 104 || (ld & 7)) return set_error(B200VSGG_ERR_BAD_ARG, "mask_im2col_bf16: bad arg");
+    if (n == 0) return 0;
+    mask_im2col_kernel<__nv_bfloat16><<<n, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)masks, n,
+                                                                          (__nv_bfloat16*)out, ld);
     VSGG_CUDA_CHECK_LAUNCH();
     return 0;
 }

@@ -367,9 +367,11 @@ def nhwc_to_nchw_f32(x, n, c, hw_shape):
 # spatial-mask branch (lib/tempura.py:466-474), channels-last
 # ------------------------------------------------------------------------------------------------
 def mask_im2col(masks, out):
-    assert masks.dtype == torch.float32 and masks.is_contiguous() and masks.shape[1:] == (2, 27, 27)
+    """masks fp32 (the reference's hand-off) or bf16 (producer-side hand-off, (f).4) [n,2,27,27] -> im2col rows."""
+    assert masks.dtype in (torch.float32, torch.bfloat16) and masks.is_contiguous() and masks.shape[1:] == (2, 27, 27)
     assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.shape[0] == masks.shape[0] * 196
-    check(_lib.lib().b200vsgg_mask_im2col(_ptr(masks), masks.shape[0], _ptr(out), out.shape[1], _stream()), "mask_im2col")
+    fn = _lib.lib().b200vsgg_mask_im2col if masks.dtype == torch.float32 else _lib.lib().b200vsgg_mask_im2col_bf16
+    check(fn(_ptr(masks), masks.shape[0], _ptr(out), out.shape[1], _stream()), "mask_im2col")
     _count()
 
 
@@ -658,57 +660,72 @@ def graph_small_fwd(nodes, upper, counts, dim, heads, depth, params, pool_w, poo
 
 
 class _UploadRing:
-    """Pinned staging ring (default 64 MB).  upload(): memcpy into the ring on the host, then a kernel on the
-    current stream reads it over PCIe (b200vsgg_upload).  A slot is reused only after the event recorded behind
-    its last reader has completed."""
+    """Pinned staging ring (default 64 MB) of ONE device.  upload(): memcpy into the ring on the host, then a kernel on
+    the current stream reads it over PCIe (b200vsgg_upload).  A slot is reused only after the event recorded behind its
+    last reader has completed: on wrap-around every outstanding event is synchronised, and the event list is only
+    ever trimmed after synchronising what is dropped — readers may sit on any stream of the device."""
 
     def __init__(self, nbytes=64 << 20):
         self.buf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         self.np = self.buf.numpy()
         self.pos = 0
-        self.events = []          # (end_offset, event) in issue order
+        self.events = []          # events in issue order (one per upload)
 
     def _reserve(self, n):
-        if n > self.buf.numel():
-            raise RuntimeError("upload of %d bytes exceeds the pinned ring" % n)
         if self.pos + n > self.buf.numel():
             self.pos = 0
-            for _, ev in self.events:          # wrap-around: everything issued so far must have been read
+            for ev in self.events:             # wrap-around: everything issued so far must have been read
                 ev.synchronize()
             self.events = []
         start = self.pos
         self.pos += n
         return start
 
+    def _trim(self):
+        if len(self.events) > 4096:            # completed long ago in practice; synchronise before forgetting them
+            for ev in self.events[:-2048]:
+                ev.synchronize()
+            self.events = self.events[-2048:]
 
-_ring = None
+
+_rings = {}                       # device index -> _UploadRing
+_ring_lock = __import__("threading").Lock()
 
 
 def upload(arr, device, dtype=None):
-    """numpy array -> device tensor of the same shape/dtype (or `dtype`), without using the DMA copy engine."""
+    """numpy array -> device tensor of the same shape/dtype (or `dtype`), without using the DMA copy engine.
+    Thread-safe; arrays larger than the ring take a one-off pinned staging buffer."""
     import numpy as np
-    global _ring
     a = np.ascontiguousarray(arr if dtype is None else np.asarray(arr).astype(dtype))
     t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].reshape(-1)).dtype, device=device)
     nbytes = a.nbytes
     if nbytes == 0:
         return t
-    if torch.device(device).type != "cuda":
+    dev = torch.device(device)
+    if dev.type != "cuda":
         t.copy_(torch.from_numpy(a))
         return t
-    if _ring is None:
-        _ring = _UploadRing()
     padded = (nbytes + 15) // 16 * 16
     out = t if nbytes == padded and t.data_ptr() % 16 == 0 else None
-    start = _ring._reserve(padded)
-    _ring.np[start:start + nbytes] = a.reshape(-1).view(np.uint8)
     dst = out if out is not None else torch.empty(padded, dtype=torch.uint8, device=device)
-    check(_lib.lib().b200vsgg_upload(C.c_void_p(_ring.buf.data_ptr() + start), _ptr(dst), padded, _stream()), "upload")
-    ev = torch.cuda.Event()
-    ev.record()
-    _ring.events.append((start + padded, ev))
-    if len(_ring.events) > 4096:
-        _ring.events = _ring.events[-2048:]
+    with _ring_lock:
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        ring = _rings.get(idx)
+        if ring is None:
+            ring = _rings[idx] = _UploadRing()
+        if padded > ring.buf.numel():                         # oversized: one-off pinned buffer, freed once it was read
+            stage = torch.empty(padded, dtype=torch.uint8).pin_memory()
+            stage.numpy()[:nbytes] = a.reshape(-1).view(np.uint8)
+            check(_lib.lib().b200vsgg_upload(C.c_void_p(stage.data_ptr()), _ptr(dst), padded, _stream()), "upload")
+            torch.cuda.current_stream().synchronize()
+        else:
+            start = ring._reserve(padded)
+            ring.np[start:start + nbytes] = a.reshape(-1).view(np.uint8)
+            check(_lib.lib().b200vsgg_upload(C.c_void_p(ring.buf.data_ptr() + start), _ptr(dst), padded, _stream()), "upload")
+            ev = torch.cuda.Event()
+            ev.record()
+            ring.events.append(ev)
+            ring._trim()
     _count()
     if out is None:
         t = dst[:nbytes].view(t.dtype).view(a.shape)

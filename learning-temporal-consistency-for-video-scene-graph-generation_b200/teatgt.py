@@ -221,15 +221,21 @@ class TeatPlan:
         nm = (torch.from_numpy(deg).clip(1) ** -0.5).numpy().astype(np.float64)   # float32 values, like the reference
         L = np.eye(nmaxc)[None] - nm[:, :, None] * A * nm[:, None, :]
 
-        def solve(n):
-            idx = np.nonzero(nodes_pc == n)[0]
+        def solve(job):
+            n, idx = job
             _, vec = np.linalg.eigh(L[idx][:, :n, :n])
             vec = vec.astype(np.float32)
             k = min(lap_k, int(n))
             for j, cl in enumerate(idx):
                 ev_all[self.clip_node_off[cl]:self.clip_node_off[cl + 1], :k] = vec[j, :, :k]
 
-        sizes = [int(n) for n in np.unique(nodes_pc)]
+        # jobs = (node count, chunk of clips with that count): equal-cost chunks (~n^3 each) so that ONE node count
+        # shared by every clip (the long-clip config: 416 clips x 165 nodes) still spreads over all host threads
+        sizes = []
+        for n in np.unique(nodes_pc):
+            idx = np.nonzero(nodes_pc == n)[0]
+            per = max(1, int(4e6 // max(1, int(n) ** 3)))
+            sizes += [(int(n), idx[i:i + per]) for i in range(0, idx.shape[0], per)]
         if eig_backend == "device":
             pad = np.arange(nmaxc)[None, :] >= nodes_pc[:, None]            # padded rows/cols: isolated, eigenvalue 10
             Lp = L.copy()
@@ -242,8 +248,8 @@ class TeatPlan:
             kk = np.minimum(lap_k, nodes_pc)[self.clip_of_node]            # columns >= n_c belong to the padding
             ev_all[np.arange(kp)[None, :] >= kk[:, None]] = 0.0
         elif len(sizes) <= 2 or eig_threads <= 1:
-            for n in sizes:
-                solve(n)
+            for job in sizes:
+                solve(job)
         else:
             with ThreadPoolExecutor(eig_threads) as pool:
                 list(pool.map(solve, sizes))
@@ -300,7 +306,8 @@ class TEAT_GT(nn.Module):
         self.lap_k = args.lap_node_id_k
         self.eig_dropout = float(getattr(args, "lap_node_id_eig_dropout", 0.0))
         self.dropout_p = 0.1            # dropout = attention_dropout = activation_dropout = 0.1 (models/tokengt.py:69-71)
-        self.eig_threads = 8
+        import os as _os
+        self.eig_threads = max(1, min(32, _os.cpu_count() or 8))
         self.eig_backend = "host"        # "device": batched cuSOLVER eigh (fast mode, see TeatPlan.build_graph)
         self.compute_consistency = True  # phase='train' fills structure_temp_loss / semantic_temp_loss (R1-R3)
         self.last_plan = None

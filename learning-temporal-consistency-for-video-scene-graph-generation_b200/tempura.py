@@ -236,6 +236,22 @@ def collate_entries(entries):
     return out
 
 
+def to_producer_contract(entry):
+    """The entry dict as a B200-aware detector would hand it over (the reference produces it at
+    tools/utils/object_detector.py:372-396 as fp32 NCHW): `union_feat` bf16 channels-last [N,7,7,1024] — the rows the
+    union_func1 GEMM consumes, so the model runs no layout pass — and `spatial_masks` bf16 [N,2,27,27].  Half the bytes
+    of the fp32 hand-off; the model's outputs are bit-identical (the fp32 path rounds to bf16 at the same point)."""
+    out = dict(entry)
+    uf = entry["union_feat"]
+    if uf.dtype != torch.bfloat16:
+        if uf.is_cuda:
+            out["union_feat"] = ops.nchw_to_nhwc_bf16(uf.contiguous()).view(uf.shape[0], 7, 7, 1024)
+        else:
+            out["union_feat"] = uf.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    out["spatial_masks"] = entry["spatial_masks"].to(torch.bfloat16).contiguous()
+    return out
+
+
 class _GemmNT(torch.autograd.Function):
     """y = a @ b^T through b200vsgg_gemm_bf16 (bf16 operands, fp32 out), differentiable in both."""
 
@@ -374,6 +390,17 @@ class TEMPURA(nn.Module):
                    l.multihead2.out_proj.bias, l.linear1.weight, l.linear1.bias, l.linear2.weight, l.linear2.bias,
                    l.norm3.weight, l.norm3.bias]
         return ps
+
+    def grad_layer_groups(self):
+        """Parameter groups whose gradients the hand-written backward finishes together (one transformer layer's four
+        weight matrices), last layer first = the order backward produces them: ddp.GradSync gives each group one flat
+        buffer that the backward writes into and all-reduces it with ONE collective when the layer is done."""
+        g = self.glocal_transformer
+        groups = [[l.multihead2.in_proj_weight, l.multihead2.out_proj.weight, l.linear1.weight, l.linear2.weight]
+                  for l in reversed(list(g.global_attention.layers))]
+        groups += [[l.self_attn.in_proj_weight, l.self_attn.out_proj.weight, l.linear1.weight, l.linear2.weight]
+                   for l in reversed(list(g.local_attention.layers))]
+        return groups
 
     def _hallucinate(self, feat):
         """memory_hallucinator (tools/utils/transformer.py:143-175), joint memory, late fusion."""
@@ -733,7 +760,15 @@ class _PathRunner:
         so = new(featb.shape[0], 1024, f32)
         ops.gemm(featb, W["so"], bias=b_so, out_f32=so)
         # ---- P3: union_func1 as GEMM over NHWC rows, mask branch added in the epilogue (:548)
-        ub = ops.nchw_to_nhwc_bf16(e["union_feat"].contiguous())
+        uf = e["union_feat"]
+        if uf.dtype == torch.bfloat16:
+            # producer-side hand-off ((f).4): the ROIAlign already emitted bf16 channels-last rows [N,7,7,1024] /
+            # [49N,1024] — exactly the A operand of the union_func1 GEMM: no layout pass, half the H2D bytes
+            assert uf.is_contiguous() and uf.numel() == N * 49 * 1024 and uf.shape[-1] == 1024, \
+                "bf16 union_feat must be channels-last [N,7,7,1024] or [49N,1024]"
+            ub = uf.view(N * 49, 1024)
+        else:
+            ub = ops.nchw_to_nhwc_bf16(uf.contiguous())
         cm_rows = self._mask_branch_fwd(P, W)
         vrp = new(N * 49, 256, bf16)
         ops.gemm(ub, W["union"], bias=P["union_b"].detach(), residual=cm_rows, out_bf16=vrp)
@@ -830,24 +865,31 @@ class _PathRunner:
         zeros = lambda *s: torch.zeros(*s, device=dev, dtype=f32)
         G = {}  # grads by the names of _unpack
         hook = getattr(model, "_grad_ready_hook", None)   # ddp.GradSync: start all-reducing finished gradients
+        galloc = getattr(model, "_grad_alloc", None)      # ddp.GradSync: persistent per-layer gradient buffers
 
         def ready(*tensors):
             if hook is not None:
                 hook(tensors)
+
+        def gnew(param, r, c):
+            """fp32 [r, c] gradient buffer of `param`: its view inside the layer's all-reduce bucket when data
+            parallel (autograd adopts it as .grad — no copies around the collective), else a fresh tensor."""
+            v = galloc(param) if galloc is not None else None
+            return v if v is not None else new(r, c, f32)
 
         def ffn_and_norm_bwd(dy32, R, L, i, rows, norm_g, norm_mean, norm_rstd, pre_norm, gkey, bkey, site):
             """Backward of  y = t + drop(W2 drop(relu(W1 t + b1)) + b2),  t = LN(pre_norm).
             Returns (d_pre_norm fp32, bf16(dropout_mask * d_pre_norm)) and fills weight grads."""
             dyb = ops.cast_bf16(dy32, drop_p=p, seed=self._seed(site + 3))
             gL = G.setdefault(i, {})
-            gL["w2"] = new(D_MODEL, FFN_DIM, f32)
+            gL["w2"] = gnew(L["w2"], D_MODEL, FFN_DIM)
             ops.gemm(dyb, R["h"], a_mn=True, b_mn=True, out_f32=gL["w2"])
             gL["b2"] = zeros(1, D_MODEL)
             ops.colsum(dyb, gL["b2"])
             dz = new(rows, FFN_DIM, bf16)
             ops.gemm(dyb, W["%dw2" % i], b_mn=True, mask_src=R["h"], mask_mode=ops.MASK_RELU,
                      alpha=(1.0 / (1.0 - p)) if p > 0 else 1.0, out_bf16=dz)
-            gL["w1"] = new(FFN_DIM, D_MODEL, f32)
+            gL["w1"] = gnew(L["w1"], FFN_DIM, D_MODEL)
             ops.gemm(dz, R["tb"], a_mn=True, b_mn=True, out_f32=gL["w1"])
             gL["b1"] = zeros(1, FFN_DIM)
             ops.colsum(dz, gL["b1"])
@@ -863,7 +905,7 @@ class _PathRunner:
         def attn_block_bwd(du, dub, R, L, i, rows, seg_off, n_seg, max_len, site):
             """Backward of u = x + drop(Wo attn(q,k,v) + bo); returns dqkv bf16 [rows, 3D]."""
             gL = G[i]
-            gL["out_w"] = new(D_MODEL, D_MODEL, f32)
+            gL["out_w"] = gnew(L["out_w"], D_MODEL, D_MODEL)
             ops.gemm(dub, R["ctxb"], a_mn=True, b_mn=True, out_f32=gL["out_w"])
             gL["out_b"] = zeros(1, D_MODEL)
             ops.colsum(dub, gL["out_b"])
@@ -891,7 +933,7 @@ class _PathRunner:
             du, dub = ffn_and_norm_bwd(dy, R, L, i, M2, "g3", R["m3"], R["r3"], R["u"], "g3", "be3", site)
             dqkv = attn_block_bwd(du, dub, R, L, i, M2, plan.win_off, plan.W, plan.max_win_len, site)
             gL = G[i]
-            gL["in_w"] = new(3 * D_MODEL, D_MODEL, f32)
+            gL["in_w"] = gnew(L["in_w"], 3 * D_MODEL, D_MODEL)
             ops.gemm(dqkv[:, :2 * D_MODEL], R["gpb"], a_mn=True, b_mn=True, out_f32=gL["in_w"][:2 * D_MODEL])
             ops.gemm(dqkv[:, 2 * D_MODEL:], R["gb"], a_mn=True, b_mn=True, out_f32=gL["in_w"][2 * D_MODEL:])
             # position embedding: d pos[k] = (sum over tokens with position k of [dq|dk]) @ W_qk
@@ -921,7 +963,7 @@ class _PathRunner:
             ops.layernorm_bwd(dy, R["v"], L["g2"].detach(), R["m2"], R["r2"], dv, None, 0.0, 0, G[i]["g2"], G[i]["be2"])
             du, dub = ffn_and_norm_bwd(dv, R, L, i, N, "g1", R["m1"], R["r1"], R["u"], "g1", "be1", site)
             dqkv = attn_block_bwd(du, dub, R, L, i, N, plan.frame_off, plan.F, plan.max_frame_len, site)
-            G[i]["in_w"] = new(3 * D_MODEL, D_MODEL, f32)
+            G[i]["in_w"] = gnew(L["in_w"], 3 * D_MODEL, D_MODEL)
             ops.gemm(dqkv, R["xb"], a_mn=True, b_mn=True, out_f32=G[i]["in_w"])
             dx = new(N, D_MODEL, f32)
             ops.gemm(dqkv, W["%din_w" % i], b_mn=True, residual=du, out_f32=dx)
@@ -994,21 +1036,35 @@ class _RelLossFn(torch.autograd.Function):
         return da * ga, ds * gs, dc * gc, None, None, None, None
 
 
-def gt_label_csr(entry, device):
+def gt_label_csr(entry, device, num_classes=None):
     """Ragged predicate labels as the dataloader yields them (lists of class ids per pair) -> what the loss kernel
     consumes: attention class index int64 [N] and CSR (offsets int32 [N+1], ids int32) for spatial / contacting.
-    Replaces the per-pair Python loop that builds multi-hot matrices (TEMPURA_train.py:181-187)."""
+    Replaces the per-pair Python loop that builds multi-hot matrices (TEMPURA_train.py:181-187).
+    num_classes = (attention, spatial, contacting) class counts: labels are validated on the host like the
+    reference path does implicitly (nn.CrossEntropyLoss / the index assignment into the multi-hot matrix raise on
+    out-of-range ids) — the kernel only clamps for memory safety."""
     import itertools
+    for a in entry["attention_gt"]:
+        if isinstance(a, (list, tuple)) and len(a) != 1:
+            raise ValueError("attention_gt must hold exactly one class per pair (TEMPURA_train.py:183), got %r" % (a,))
     att = np.fromiter((a[0] if isinstance(a, (list, tuple)) else int(a) for a in entry["attention_gt"]), dtype=np.int64)
 
-    def csr(lists):
+    def check(ids, C, what):
+        if num_classes is not None and ids.size and (ids.min() < 0 or ids.max() >= C):
+            raise IndexError("%s label out of range: ids span [%d, %d], the head has %d classes"
+                             % (what, int(ids.min()), int(ids.max()), C))
+
+    def csr(lists, C, what):
         lens = np.fromiter((len(l) for l in lists), dtype=np.int64, count=len(lists))
         off = np.zeros(len(lists) + 1, dtype=np.int32)
         off[1:] = np.cumsum(lens)
         idx = np.fromiter(itertools.chain.from_iterable(lists), dtype=np.int32, count=int(off[-1]))
+        check(idx, C, what)
         return ops.upload(off, device), ops.upload(idx, device)
 
-    return ops.upload(att, device), csr(entry["spatial_gt"]), csr(entry["contacting_gt"])
+    ca, cs, cc = num_classes if num_classes is not None else (0, 0, 0)
+    check(att, ca, "attention")
+    return ops.upload(att, device), csr(entry["spatial_gt"], cs, "spatial"), csr(entry["contacting_gt"], cc, "contacting")
 
 
 def tempura_loss(pred, plan=None, eos_coef=1.0):
@@ -1022,7 +1078,7 @@ def tempura_loss(pred, plan=None, eos_coef=1.0):
     if "gt_tensors" in pred:  # label tensors prepared by the data loader (same values as below)
         att, spa, con = pred["gt_tensors"]
     elif dist_a.is_cuda:      # ragged label lists go to the loss kernel as CSR, no multi-hot matrices
-        att, spa, con = gt_label_csr(pred, dev)
+        att, spa, con = gt_label_csr(pred, dev, (dist_a.shape[1], dist_s.shape[1], dist_c.shape[1]))
     else:
         att = torch.tensor([a[0] if isinstance(a, (list, tuple)) else int(a) for a in pred["attention_gt"]], device=dev)
         spa = torch.zeros(N, dist_s.shape[1])

@@ -28,6 +28,10 @@ pytestmark = pytest.mark.gpu
 # ~1.4 bf16 ulp after 5 residual blocks; 32-frame videos have 31 windows whose errors the 'latter' gather picks the
 # worst of).  The head GEMM itself is split-precision (error 1e-6), nothing else on the path is discretionary.
 DIST_TOL = 1.25e-3
+# Train mode adds the GMM sampling term mu + sqrt(var) * eps with |eps| up to ~4.5 over 16 k x 26 x 6 draws: the same
+# relative error on sqrt(var) is multiplied by eps, and the split-K partial sums of the BatchNorm statistics arrive in a
+# run-dependent order, so the worst element moves between runs (measured 1.16e-3 .. 1.3e-3).  Asserted: 2e-3.
+DIST_TOL_TRAIN = 2e-3
 FEAT_REL_TOL = 3e-2
 KW = dict(mode="predcls", attention_class_num=3, spatial_class_num=6, contact_class_num=17, enc_layer_num=1,
           dec_layer_num=3, obj_mem_compute=False, rel_mem_compute="joint", mem_fusion="late", selection="manual",
@@ -151,8 +155,9 @@ def test_fullsize_predcls_matches_oracle_on_sampled_videos(cuda_lib):
             for tag, got, ref in (("eval", ev[k][sl], ref_ev[k]), ("train", tr[k][sl], ref_tr[k])):
                 err = (got - ref).abs().max().item()
                 worst[(tag, k)] = max(worst.get((tag, k), 0.0), err)
-                assert err <= DIST_TOL, (tag, k, v, err)
-                d, t_ = check_full_ranking(got, ref, DIST_TOL)
+                tol = DIST_TOL if tag == "eval" else DIST_TOL_TRAIN
+                assert err <= tol, (tag, k, v, err)
+                d, t_ = check_full_ranking(got, ref, tol)
                 decided += d
                 total += t_
         ref = ref_ev["rel_features"]

@@ -289,3 +289,46 @@ def test_consistency_regulariser_extension_matches_oracle_restatement(cuda_lib):
         err = (gs - rs).abs().max().item()
         print(key, "pairs", rs.numel(), "max-abs err %.3e of max %.3e" % (err, rs.abs().max().item()))
         assert err <= rtol * rs.abs().max().item() + 1e-6, (key, err, gs[:6], rs[:6])
+
+
+def test_producer_side_bf16_handoff_is_bit_identical(pair):
+    """(f).4: union_feat as bf16 channels-last rows + bf16 masks (what a B200-aware ROIAlign would emit) gives exactly
+    the outputs and gradients of the reference's fp32 NCHW hand-off — the fp32 path rounds to bf16 at the same point —
+    with half the input bytes and no layout kernel."""
+    from b200vsgg import ops, synthetic, tempura
+    m, _ = pair
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    entries = [synthetic.make_video_entry(50 + i, f, (2, 6), device="cuda") for i, f in enumerate((5, 9))]
+    batch = tempura.collate_entries(entries)
+    fast = tempura.to_producer_contract(batch)
+    assert fast["union_feat"].dtype == torch.bfloat16 and fast["union_feat"].shape[1:] == (7, 7, 1024)
+    assert fast["union_feat"].numel() * 2 + fast["spatial_masks"].numel() * 2 == \
+        (batch["union_feat"].numel() * 4 + batch["spatial_masks"].numel() * 4) // 2
+    m.train()
+    m.dropout_p = 0.0
+    N = batch["pair_idx"].shape[0]
+    g = torch.Generator().manual_seed(1)
+    m.gmm_eps = {"attention": torch.randn(6, N, 3, generator=g), "spatial": torch.randn(6, N, 6, generator=g),
+                 "contacting": torch.randn(6, N, 17, generator=g)}
+    outs, grads, launches = [], [], []
+    for e in (batch, fast):
+        m.load_state_dict(state)
+        m.zero_grad(set_to_none=True)
+        n0 = ops.launch_count
+        pred = m(dict(e), phase="train")
+        loss = sum(tempura.tempura_loss(pred, m.last_plan).values())
+        loss.backward()
+        launches.append(ops.launch_count - n0)
+        outs.append([pred[k].detach().clone() for k in ("attention_distribution", "spatial_distribution",
+                                                         "contacting_distribution", "rel_features")])
+        grads.append({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    m.dropout_p, m.gmm_eps = 0.1, None
+    m.load_state_dict(state)
+    m.eval()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    # split-K partial sums arrive in a run-dependent order (TMA reduce-add): gradients agree to fp32 rounding
+    for n in grads[0]:
+        d = (grads[0][n] - grads[1][n]).abs().max().item()
+        assert d <= 1e-5 * grads[0][n].abs().max().item() + 1e-9, (n, d)
+    assert launches[1] < launches[0]                       # the NCHW -> NHWC layout kernel is gone
