@@ -699,7 +699,7 @@ def main():
     #                         spatial_masks fp32 [N,2,27,27] (3.55 GB per 64-video step: PCIe-bound)
     #   producer_bf16_nhwc    SURVEY.md §8 (f).4: the detector emits what the path consumes — union_feat bf16 channels-
     #                         last rows, bf16 masks (tempura.to_producer_contract): half the bytes, no layout kernel,
-    #                         bit-identical outputs (tests/test_tempura_gpu.py)
+    #                         same bf16 operands in every GEMM (tests/test_tempura_gpu.py)
     # `e2e` (the contract's headline key) is the reference contract; `e2e_producer_contract` sits beside it.
     e2e = e2e_fast = None
     if not args.no_e2e:
@@ -780,7 +780,7 @@ def main():
         host_fast.update(fast_host)
         del host["union_feat"], host["spatial_masks"]
         e2e_fast = run_e2e(host_fast)
-        e2e_fast["contract"] = "producer_bf16_nhwc (SURVEY 8(f).4: union_feat bf16 [N,7,7,1024], masks bf16; outputs bit-identical)"
+        e2e_fast["contract"] = "producer_bf16_nhwc (SURVEY 8(f).4: union_feat bf16 [N,7,7,1024], masks bf16; same bf16 operands in every GEMM)"
         e2e_fast["numa"] = numa_info
 
     # ============================== CPU baseline (rank 0, N = 1) ==============================

@@ -8,6 +8,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "../../include/b200vsgg.h"
 #include "common.cuh"
@@ -349,6 +352,40 @@ static inline PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
+// Host-side cache of encoded tensor maps: a training step issues ~90 GEMMs with 2-4 maps each, and from the second step
+// on every (pointer, shape, pitch, box) repeats (the caching allocator hands the same blocks back), so the driver's
+// cuTensorMapEncodeTiled is paid once per distinct operand instead of ~350 times per step.  A map only depends on the
+// key fields, so a stale pointer that happens to be reused with the same geometry yields the correct map anyway.
+struct TmapKey {
+    uint64_t base, d0, d1, ld, box, kind;
+    bool operator==(const TmapKey& o) const {
+        return base == o.base && d0 == o.d0 && d1 == o.d1 && ld == o.ld && box == o.box && kind == o.kind;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = k.base * 0x9E3779B97F4A7C15ull;
+        for (uint64_t v : {k.d0, k.d1, k.ld, k.box, k.kind}) h = (h ^ (h >> 29)) * 0xBF58476D1CE4E5B9ull + v;
+        return static_cast<size_t>(h ^ (h >> 32));
+    }
+};
+static inline bool tmap_cache_get(const TmapKey& k, CUtensorMap* out, const CUtensorMap* put) {
+    static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    static std::mutex mu;
+    static const bool off = []() { const char* e = getenv("B200VSGG_NO_TMAP_CACHE"); return e && e[0] == '1'; }();
+    if (off) return false;
+    std::lock_guard<std::mutex> lock(mu);
+    if (put != nullptr) {
+        if (cache.size() >= 8192) cache.clear();
+        cache.emplace(k, *put);
+        return true;
+    }
+    auto it = cache.find(k);
+    if (it == cache.end()) return false;
+    *out = it->second;
+    return true;
+}
+
 // Output tensor maps of the TMA-store epilogue: 32 x 32 boxes of a row-major [M, N] matrix (pitch ld elements).
 static inline int make_tmap_out(CUtensorMap* tm, const void* base, bool is_f32, uint64_t N, uint64_t M, uint64_t ld) {
     PFN_encodeTiled enc = get_encode_fn();
@@ -356,6 +393,8 @@ static inline int make_tmap_out(CUtensorMap* tm, const void* base, bool is_f32, 
     const uint64_t es = is_f32 ? 4 : 2;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || ((ld * es) & 15u) != 0)
         return set_error(B200VSGG_ERR_BAD_ARG, "gemm output must be 16-byte aligned with a 16-byte multiple pitch");
+    const TmapKey key{reinterpret_cast<uint64_t>(base), N, M, ld, 32, is_f32 ? 1ull : 2ull};
+    if (tmap_cache_get(key, tm, nullptr)) return 0;
     cuuint64_t dims[2] = {N, M};
     cuuint64_t strides[1] = {ld * es};
     cuuint32_t box[2] = {32, 32};
@@ -365,6 +404,7 @@ static inline int make_tmap_out(CUtensorMap* tm, const void* base, bool is_f32, 
                      is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(B200VSGG_ERR_TMAP, "cuTensorMapEncodeTiled failed for a GEMM output");
+    tmap_cache_get(key, nullptr, tm);
     return 0;
 }
 
@@ -375,6 +415,9 @@ static inline int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t inn
     if (enc == nullptr) return set_error(B200VSGG_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
     if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || ((ld * 2) & 15u) != 0)
         return set_error(B200VSGG_ERR_BAD_ARG, "gemm operand must be 16-byte aligned with ld % 8 == 0");
+    const TmapKey key{reinterpret_cast<uint64_t>(base), inner, outer, ld,
+                      (static_cast<uint64_t>(box_inner) << 32) | box_outer, swizzle128 ? 3ull : 4ull};
+    if (tmap_cache_get(key, tm, nullptr)) return 0;
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {ld * 2};
     cuuint32_t box[2] = {box_inner, box_outer};
@@ -389,6 +432,7 @@ static inline int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t inn
                  (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
         return set_error(B200VSGG_ERR_TMAP, msg);
     }
+    tmap_cache_get(key, nullptr, tm);
     return 0;
 }
 

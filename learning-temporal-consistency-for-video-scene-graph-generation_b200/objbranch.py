@@ -478,10 +478,9 @@ def run_object_branch(oc, entry, phase, frames_per_video, heads_fn, dropout_p, g
     if getattr(oc, "_debug", False):      # parity debugging: expose the branch's intermediate tensors
         oc._debug_last = dict(y=y, tokens=x32)
     if oc.obj_head == "gmm":
-        Wp, bp_ = oc.decoder_lin.packed()
         eps = [gmm_eps.get("object")] if gmm_eps else [None]
         hseed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        (dist,) = heads_fn(y.float(), Wp, bp_, 1, oc.GMM_K, [oc.decoder_lin.num_classes], [True], eps, hseed)
+        (dist,) = heads_fn([oc.decoder_lin], y.float(), 1, eps, hseed)
         entry["distribution"] = dist
     else:
         lin = oc.decoder_lin[0]

@@ -219,6 +219,39 @@ def split3_bf16(x, out=None):
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# bf16 operand copies of weights, refreshed only when a parameter changed
+# ------------------------------------------------------------------------------------------------
+_NO_WCACHE = bool(int(__import__("os").environ.get("B200VSGG_NO_WCACHE", "0")))
+
+
+def cached_weight(tag, params, build):
+    """`build()` -> tensor derived from the parameters `params` (bf16 copy, packed / permuted / split-precision layout),
+    memoised until one of them changes.  The memo lives ON the first parameter object (so it dies with the model and
+    can never be hit by another model whose tensors reuse the same addresses) and is validated by the identity of the
+    other parameters plus (`_version`, data_ptr) of each: torch bumps `_version` on every in-place update
+    (optimizer.step, load_state_dict, .copy_); b200vsgg.optim.FusedAdamW writes parameters from its own kernel and bumps
+    the counters explicitly.  Inference and the repeated forwards of a training step therefore cast each weight once per
+    optimiser step instead of once per call.  The returned tensor is read-only (saved activations may alias it)."""
+    import weakref
+    if _NO_WCACHE:
+        with torch.no_grad():
+            return build()
+    p0 = params[0]
+    memo = p0.__dict__.get("_b200vsgg_wcache")
+    if memo is None:
+        memo = p0.__dict__["_b200vsgg_wcache"] = {}
+    stamp = tuple((p._version, p.data_ptr()) for p in params)
+    hit = memo.get(tag)
+    if hit is not None and hit[0] == stamp and len(hit[1]) == len(params) - 1 and \
+            all(r() is p for r, p in zip(hit[1], params[1:])):
+        return hit[2]
+    with torch.no_grad():
+        t = build()
+    memo[tag] = (stamp, tuple(weakref.ref(p) for p in params[1:]), t)
+    return t
+
+
 _uniform_chunks = {}
 
 

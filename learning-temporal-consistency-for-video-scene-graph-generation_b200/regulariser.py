@@ -92,7 +92,7 @@ def run_compact(gt, x, node_off, upper, nmax):
     R, dim = x.shape
     dev = x.device
     inner = gt.heads * gt.dim_head
-    bf = lambda w: ops.cast_bf16(w.detach().contiguous())
+    bf = lambda w: ops.cached_weight("gt", (w,), lambda: ops.cast_bf16(w.detach().contiguous()))
     x = x.contiguous().clone()
     xn = torch.empty(R, dim, device=dev, dtype=torch.bfloat16)
     qkv = torch.empty(R, 3 * inner, device=dev)
@@ -103,8 +103,11 @@ def run_compact(gt, x, node_off, upper, nmax):
         pre, gate = attn_block
         a = pre.fn
         ops.layernorm_fwd(x, pre.norm.weight.detach(), pre.norm.bias.detach(), 1e-5, None, xn)
-        ops.gemm(xn, bf(torch.cat([a.to_q.weight, a.to_kv.weight], 0)),
-                 bias=torch.cat([a.to_q.bias, a.to_kv.bias]).detach(), out_f32=qkv)
+        wqkv = ops.cached_weight("gt_qkv", (a.to_q.weight, a.to_kv.weight),
+                                 lambda: ops.cast_bf16(torch.cat([a.to_q.weight, a.to_kv.weight], 0).detach().contiguous()))
+        bqkv = ops.cached_weight("gt_bqkv", (a.to_q.bias, a.to_kv.bias),
+                                 lambda: torch.cat([a.to_q.bias, a.to_kv.bias]).detach().clone())
+        ops.gemm(xn, wqkv, bias=bqkv, out_f32=qkv)
         ops.graph_attn_core(qkv, node_off, upper, nmax, a.edges_to_kv.weight.detach()[:, 0].contiguous(),
                             a.edges_to_kv.bias.detach().contiguous(), att)
         ops.gemm(att, bf(a.to_out.weight), bias=a.to_out.bias.detach(), out_f32=o)

@@ -32,6 +32,14 @@ FFN_DIM = 2048
 HEAD_COLS_PAD = 8  # packed head GEMM width is rounded up to a multiple of 8
 
 
+def _fgemm(*args, **kw):
+    """Forward-path GEMM: never split-K.  Split-K partial tiles are summed in arrival order (TMA reduce-add), and a
+    last-bit difference in a forward activation flips bf16 roundings downstream until, four layers later, two runs of
+    the same input differ by a third of the total bf16 error (measured 3e-4 on the distributions).  Without it the eval
+    forward is bit-reproducible; only tiny batches (< 148 output tiles) lose speed, the benchmark shapes never split."""
+    return ops.gemm(*args, split_k=1, **kw)
+
+
 # ================================================================================================
 # parameter containers (names/shapes/initialisation order follow the reference)
 # ================================================================================================
@@ -51,12 +59,17 @@ class GMMHead(nn.Module):
     def softmax(self):
         return self.rel_type == "attention" or self.rel_type is None
 
-    def packed(self):
-        """([K*(2C+1), hid] weight, [K*(2C+1)] bias) in the kernel's column order mu|var|pi."""
+    def packed_order(self):
+        """The head's Linear layers in the kernel's column order mu_1..K | var_1..K | pi_1..K."""
         K = self.k
         order = ["mu_%d" % (i + 1) for i in range(K)] + ["var_%d" % (i + 1) for i in range(K)] + \
                 ["pi_%d" % (i + 1) for i in range(K)]
-        return (torch.cat([self.heads[n].weight for n in order], 0), torch.cat([self.heads[n].bias for n in order], 0))
+        return [self.heads[n] for n in order]
+
+    def packed(self):
+        """([K*(2C+1), hid] weight, [K*(2C+1)] bias) in the kernel's column order mu|var|pi."""
+        lins = self.packed_order()
+        return (torch.cat([l.weight for l in lins], 0), torch.cat([l.bias for l in lins], 0))
 
 
 class _SpatialLayer(nn.Module):
@@ -183,7 +196,7 @@ class ObjectClassifier(nn.Module):
         fpv = entry.get("video_frames")
         if fpv is None:
             fpv = np.asarray([entry["human_idx"].shape[0] if "human_idx" in entry else int(entry["boxes"][-1, 0].item()) + 1])
-        return run_object_branch(self, entry, phase, fpv, _HeadsFn.apply, self.dropout_p, self.gmm_eps)
+        return run_object_branch(self, entry, phase, fpv, apply_heads, self.dropout_p, self.gmm_eps)
 
 
 # ================================================================================================
@@ -240,7 +253,7 @@ def to_producer_contract(entry):
     """The entry dict as a B200-aware detector would hand it over (the reference produces it at
     tools/utils/object_detector.py:372-396 as fp32 NCHW): `union_feat` bf16 channels-last [N,7,7,1024] — the rows the
     union_func1 GEMM consumes, so the model runs no layout pass — and `spatial_masks` bf16 [N,2,27,27].  Half the bytes
-    of the fp32 hand-off; the model's outputs are bit-identical (the fp32 path rounds to bf16 at the same point)."""
+    of the fp32 hand-off; every GEMM sees the same bf16 operands (the fp32 path rounds to bf16 at the same point)."""
     out = dict(entry)
     uf = entry["union_feat"]
     if uf.dtype != torch.bfloat16:
@@ -260,7 +273,7 @@ class _GemmNT(torch.autograd.Function):
         ab, bb = ops.cast_bf16(a.contiguous()), ops.cast_bf16(b.contiguous())
         ctx.save_for_backward(ab, bb)
         out = torch.empty(a.shape[0], b.shape[0], device=a.device)
-        ops.gemm(ab, bb, out_f32=out)
+        _fgemm(ab, bb, out_f32=out)
         return out
 
     @staticmethod
@@ -269,8 +282,8 @@ class _GemmNT(torch.autograd.Function):
         M, N = g.shape
         K = ab.shape[1]
         Np = (N + 7) // 8 * 8  # TMA row pitch must be a multiple of 16 bytes
-        gb = torch.zeros(M, Np, device=g.device, dtype=torch.bfloat16)
-        ops.cast_bf16(g.contiguous(), out=gb[:, :N])
+        # (the cast kernel works on 4-column vectors: pad first when N is not a multiple of 8, e.g. the 26 memory slots)
+        gb = ops.cast_bf16(F.pad(g, (0, Np - N)).contiguous() if Np != N else g.contiguous())
         da = db = None
         if ctx.needs_input_grad[0]:
             da = torch.empty(M, K, device=g.device)
@@ -490,15 +503,11 @@ class TEMPURA(nn.Module):
         if cons_prep is not None:
             self._consistency(entry, plan, mixed.detach(), cons_prep)
         heads = [self.a_rel_compress, self.s_rel_compress, self.c_rel_compress]
-        packed = [h.packed() for h in heads]
-        Wp = torch.cat([w for w, _ in packed], 0)
-        bp = torch.cat([b for _, b in packed], 0)
         mode = 2 if unc else (1 if phase == "train" else 0)
         eps = self.gmm_eps or {}
         eps_list = [eps.get(n) for n in ("attention", "spatial", "contacting")]
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        res = _HeadsFn.apply(mixed, Wp, bp, mode, self.GMM_K, [h.num_classes for h in heads],
-                             [h.softmax for h in heads], eps_list, seed)
+        res = apply_heads(heads, mixed, mode, eps_list, seed)
         if not unc:
             entry["attention_distribution"], entry["spatial_distribution"], entry["contacting_distribution"] = res[:3]
         else:
@@ -510,28 +519,48 @@ class TEMPURA(nn.Module):
 # ================================================================================================
 # heads: packed GEMM + fused mixture epilogue
 # ================================================================================================
+def apply_heads(heads, feat, mode, eps_list, seed):
+    """All mixture heads of `heads` (GMMHead containers) on `feat` [N, hid]: ONE packed GEMM + one epilogue kernel
+    (tools/utils/gmm_heads.py:37-76 does 3K tiny Linears per head).  The 2 x 3K x len(heads) Linear parameters go to the
+    autograd function individually — no differentiable torch.cat whose backward would split the packed gradient with
+    one small kernel per Linear; the packed bf16 operand is memoised per parameter version."""
+    lins = [l for h in heads for l in h.packed_order()]
+    return _HeadsFn.apply(feat, mode, heads[0].k, [h.num_classes for h in heads], [h.softmax for h in heads], eps_list,
+                          seed, len(lins), *[l.weight for l in lins], *[l.bias for l in lins])
+
+
 class _HeadsFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feat, Wp, bp, mode, K, Cs, softmaxes, eps_list, seed):
+    def forward(ctx, feat, mode, K, Cs, softmaxes, eps_list, seed, n_lin, *params):
+        ws, bs = params[:n_lin], params[n_lin:]
         N = feat.shape[0]
-        cols = Wp.shape[0]
+        K_in = ws[0].shape[1]
+        cols = sum(w.shape[0] for w in ws)
         cols_pad = (cols + HEAD_COLS_PAD - 1) // HEAD_COLS_PAD * HEAD_COLS_PAD
         dev = feat.device
+
         # Split-precision product (SURVEY.md "fp32-accumulated logits ... max-abs <= 1e-3"): the head logits feed
         # softmax / sigmoid outputs that are compared at 1e-3, and a plain bf16 x bf16 product costs ~6e-4 of that
         # budget by itself (tools/parity_breakdown.py).  x = hi + lo, W = hi + lo, z = hi.hi + lo.hi + hi.lo as ONE
         # tcgen05 GEMM with K' = 3K over [hi|lo|hi] x [W_hi|W_hi|W_lo] — 0.3 % of the step's flops.
-        K_in = Wp.shape[1]
+        def pack_w():
+            Wf = torch.zeros(cols_pad, K_in, device=dev)
+            Wf[:cols] = torch.cat([w.detach() for w in ws], 0)
+            Wb = Wf.to(torch.bfloat16)
+            return torch.cat([Wb, Wb, (Wf - Wb.float()).to(torch.bfloat16)], 1).contiguous()
+
+        def pack_b():
+            bias = torch.zeros(cols_pad, device=dev)
+            bias[:cols] = torch.cat([b.detach() for b in bs])
+            return bias
+
+        Wb3 = ops.cached_weight("heads_w", ws, pack_w)
+        bias = ops.cached_weight("heads_b", bs, pack_b)
+        Wb = Wb3[:, :K_in]                                   # bf16(W): operand of the input-gradient GEMM
         fb3 = ops.split3_bf16(feat.contiguous())
         fb = fb3[:, :K_in]                                   # bf16(feat): operand of the weight-gradient GEMM
-        Wf = torch.zeros(cols_pad, K_in, device=dev)
-        Wf[:cols] = Wp.detach()
-        Wb = Wf.to(torch.bfloat16)
-        Wb3 = torch.cat([Wb, Wb, (Wf - Wb.float()).to(torch.bfloat16)], 1)
-        bias = torch.zeros(cols_pad, device=dev)
-        bias[:cols] = bp
         z = torch.empty(N, cols_pad, device=dev)
-        ops.gemm(fb3, Wb3, bias=bias, out_f32=z)
+        _fgemm(fb3, Wb3, bias=bias, out_f32=z)
         bases, b = [], 0
         for C in Cs:
             bases.append(b)
@@ -543,7 +572,7 @@ class _HeadsFn(torch.autograd.Function):
                       out2=outs2[i]) for i in range(len(Cs))]
         ops.gmm_head_fwd(z, K, specs, mode, seed)
         ctx.save_for_backward(fb, Wb, z)
-        ctx.meta = (mode, K, Cs, softmaxes, eps_dev, seed, bases, cols, cols_pad)
+        ctx.meta = (mode, K, Cs, softmaxes, eps_dev, seed, bases, cols, cols_pad, n_lin, [w.shape[0] for w in ws])
         if mode == 2:
             ctx.mark_non_differentiable(*outs, *outs2)
             return (*outs, *outs2)
@@ -552,7 +581,7 @@ class _HeadsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         fb, Wb, z = ctx.saved_tensors
-        mode, K, Cs, softmaxes, eps_dev, seed, bases, cols, cols_pad = ctx.meta
+        mode, K, Cs, softmaxes, eps_dev, seed, bases, cols, cols_pad, n_lin, rows_of = ctx.meta
         N = fb.shape[0]
         dev = fb.device
         douts = [(g if g is not None else torch.zeros(N, C, device=dev)).contiguous().float()
@@ -561,19 +590,20 @@ class _HeadsFn(torch.autograd.Function):
                  for i in range(len(Cs))]
         dz = torch.empty(N, cols_pad, device=dev, dtype=torch.bfloat16)
         ops.gmm_head_bwd(z, K, specs, mode, dz, seed)
-        dfeat = dW = db = None
+        dfeat = None
+        dws, dbs = [None] * n_lin, [None] * n_lin
         if ctx.needs_input_grad[0]:
             dfeat = torch.empty(N, Wb.shape[1], device=dev)
             ops.gemm(dz, Wb, b_mn=True, out_f32=dfeat)
-        if ctx.needs_input_grad[1]:
+        if any(ctx.needs_input_grad[8:8 + n_lin]):
             dWp = torch.empty(cols_pad, Wb.shape[1], device=dev)
             ops.gemm(dz, fb, a_mn=True, b_mn=True, out_f32=dWp)
-            dW = dWp[:cols]
-        if ctx.needs_input_grad[2]:
+            dws = list(torch.split(dWp[:cols], rows_of, 0))              # views: no copies, no kernels
+        if any(ctx.needs_input_grad[8 + n_lin:]):
             dbp = torch.zeros(1, cols_pad, device=dev)
             ops.colsum(dz, dbp)
-            db = dbp[0, :cols]
-        return dfeat, dW, db, None, None, None, None, None, None
+            dbs = list(torch.split(dbp[0, :cols], rows_of, 0))
+        return (dfeat, None, None, None, None, None, None, None, *dws, *dbs)
 
 
 # ================================================================================================
@@ -664,7 +694,7 @@ class _PathRunner:
         ops.mask_im2col(e["spatial_masks"].contiguous(), A1)
         y1 = torch.empty(N * 196, 128, device=dev, dtype=bf16)
         y1f = torch.empty(N * 196, 128, device=dev, dtype=torch.float32)
-        ops.gemm(A1, W["c1x"], bias=P["c1_b"].detach(), act=ops.ACT_RELU, out_bf16=y1, out_f32=y1f, a_k_period=128)
+        _fgemm(A1, W["c1x"], bias=P["c1_b"].detach(), act=ops.ACT_RELU, out_bf16=y1, out_f32=y1f, a_k_period=128)
         sc1, sh1 = self._bn_tables(y1f, 196, model.conv[2], P["bn1_g"], P["bn1_b"], "bn1")
         z = torch.empty(N * 49, 128, device=dev, dtype=bf16)
         arg = torch.empty(N * 49, 128, device=dev, dtype=torch.uint8)
@@ -673,7 +703,7 @@ class _PathRunner:
         A2 = torch.empty(N * 49, 1152, device=dev, dtype=bf16)
         ops.im2col3x3(z, N, 7, 128, A2)
         y2 = torch.empty(N * 49, 256, device=dev, dtype=bf16)
-        ops.gemm(A2, W["c2"], bias=P["c2_b"].detach(), act=ops.ACT_RELU, out_bf16=y2)
+        _fgemm(A2, W["c2"], bias=P["c2_b"].detach(), act=ops.ACT_RELU, out_bf16=y2)
         sc2, sh2 = self._bn_tables(y2, 49, model.conv[6], P["bn2_g"], P["bn2_b"], "bn2")
         cm = torch.empty(N * 49, 256, device=dev, dtype=bf16)
         ops.seg_affine(None, y2, None, sc2, sh2, plan.video_of_pair32, 49, cm)
@@ -740,25 +770,26 @@ class _PathRunner:
         bf16, f32 = torch.bfloat16, torch.float32
         new = lambda r, c, dt: torch.empty(r, c, device=dev, dtype=dt)
 
-        # ---- weights in bf16 (K-major [out, in]); the same copies serve dgrad via MN-major B
-        W = {"so": self._bf(torch.cat([P["subj_w"], P["obj_w"]], 0)),
-             "union": self._bf(P["union_w"]),
+        # ---- weights in bf16 (K-major [out, in]); the same copies serve dgrad via MN-major B.  Memoised per parameter
+        #      version (ops.cached_weight): cast once per optimiser step, not once per forward
+        cw = ops.cached_weight
+        W = {"so": cw("so", (P["subj_w"], P["obj_w"]), lambda: self._bf(torch.cat([P["subj_w"], P["obj_w"]], 0))),
+             "union": cw("union", (P["union_w"],), lambda: self._bf(P["union_w"])),
              # vr_fc consumes vr in (h, w, c) order instead of the reference's (c, h, w): permute columns
-             "vr": self._bf(P["vr_w"].detach().view(512, 256, 49).permute(0, 2, 1).reshape(512, 12544)),
-             # conv1 taps in (c, kh, kw) order padded 98 -> 104; conv2 taps in (kh, kw, c) order
-             "c1": self._bf(F.pad(P["c1_w"].detach().reshape(128, 98), (0, 6))),
-             "c1x": _split_bf16(F.pad(P["c1_w"].detach().reshape(128, 98), (0, 30))),
-             "c2": self._bf(P["c2_w"].detach().permute(0, 2, 3, 1).reshape(256, 1152))}
-        b_so = torch.cat([P["subj_b"], P["obj_b"]]).detach()
+             "vr": cw("vr", (P["vr_w"],), lambda: self._bf(P["vr_w"].detach().view(512, 256, 49).permute(0, 2, 1).reshape(512, 12544))),
+             # conv1 taps in (c, kh, kw) order, weights as bf16 hi | lo halves; conv2 taps in (kh, kw, c) order
+             "c1x": cw("c1x", (P["c1_w"],), lambda: _split_bf16(F.pad(P["c1_w"].detach().reshape(128, 98), (0, 30)))),
+             "c2": cw("c2", (P["c2_w"],), lambda: self._bf(P["c2_w"].detach().permute(0, 2, 3, 1).reshape(256, 1152)))}
+        b_so = cw("b_so", (P["subj_b"], P["obj_b"]), lambda: torch.cat([P["subj_b"], P["obj_b"]]).detach().clone())
         for i, L in enumerate(P["enc"] + P["dec"]):
             for n in ("in_w", "out_w", "w1", "w2"):
-                W["%d%s" % (i, n)] = self._bf(L[n])
+                W["%d%s" % (i, n)] = cw("layer", (L[n],), lambda w=L[n]: self._bf(w))
         S["W"] = W
 
         # ---- P1/P2: subj_fc|obj_fc over all boxes, then gather  (lib/tempura.py:537-544)
         featb = ops.cast_bf16(e["features"].contiguous())
         so = new(featb.shape[0], 1024, f32)
-        ops.gemm(featb, W["so"], bias=b_so, out_f32=so)
+        _fgemm(featb, W["so"], bias=b_so, out_f32=so)
         # ---- P3: union_func1 as GEMM over NHWC rows, mask branch added in the epilogue (:548)
         uf = e["union_feat"]
         if uf.dtype == torch.bfloat16:
@@ -771,12 +802,12 @@ class _PathRunner:
             ub = ops.nchw_to_nhwc_bf16(uf.contiguous())
         cm_rows = self._mask_branch_fwd(P, W)
         vrp = new(N * 49, 256, bf16)
-        ops.gemm(ub, W["union"], bias=P["union_b"].detach(), residual=cm_rows, out_bf16=vrp)
+        _fgemm(ub, W["union"], bias=P["union_b"].detach(), residual=cm_rows, out_bf16=vrp)
         del cm_rows
         # ---- P5: vr_fc straight into the token buffer (:549)
         tok = new(N, D_MODEL, f32)
         tokb = new(N, D_MODEL, bf16)
-        ops.gemm(vrp.view(N, 12544), W["vr"], bias=P["vr_b"].detach(), out_f32=tok[:, 1024:1536])
+        _fgemm(vrp.view(N, 12544), W["vr"], bias=P["vr_b"].detach(), out_f32=tok[:, 1024:1536])
         # ---- P6: gather + label embeddings + concat (:554-563)
         ops.pair_concat_fwd(so, e["pair_idx"].contiguous(), e["pred_labels"].contiguous(), P["emb1"].detach().contiguous(),
                             P["emb2"].detach().contiguous(), tok, tokb)
@@ -788,21 +819,21 @@ class _PathRunner:
         site = 0
         for i, L in enumerate(P["enc"]):
             qkv = new(N, 3 * D_MODEL, bf16)
-            ops.gemm(xb, W["%din_w" % i], bias=L["in_b"].detach(), out_bf16=qkv)
+            _fgemm(xb, W["%din_w" % i], bias=L["in_b"].detach(), out_bf16=qkv)
             ctxb = new(N, D_MODEL, bf16)
             ops.attn_small_fwd(qkv[:, :D_MODEL], qkv[:, D_MODEL:2 * D_MODEL], qkv[:, 2 * D_MODEL:], plan.frame_off,
                                plan.F, plan.max_frame_len, N_HEADS, HEAD_DIM, ctxb, p, self._seed(site))
             u = new(N, D_MODEL, f32)
-            ops.gemm(ctxb, W["%dout_w" % i], bias=L["out_b"].detach(), residual=x32, out_f32=u, dropout_p=p,
+            _fgemm(ctxb, W["%dout_w" % i], bias=L["out_b"].detach(), residual=x32, out_f32=u, dropout_p=p,
                      seed=self._seed(site + 1))
             t32, tb = new(N, D_MODEL, f32), new(N, D_MODEL, bf16)
             m1, r1 = torch.empty(N, device=dev), torch.empty(N, device=dev)
             ops.layernorm_fwd(u, L["g1"].detach(), L["be1"].detach(), 1e-5, t32, tb, mean=m1, rstd=r1)
             h = new(N, FFN_DIM, bf16)
-            ops.gemm(tb, W["%dw1" % i], bias=L["b1"].detach(), act=ops.ACT_RELU, out_bf16=h, dropout_p=p,
+            _fgemm(tb, W["%dw1" % i], bias=L["b1"].detach(), act=ops.ACT_RELU, out_bf16=h, dropout_p=p,
                      seed=self._seed(site + 2))
             v = new(N, D_MODEL, f32)
-            ops.gemm(h, W["%dw2" % i], bias=L["b2"].detach(), residual=t32, out_f32=v, dropout_p=p,
+            _fgemm(h, W["%dw2" % i], bias=L["b2"].detach(), residual=t32, out_f32=v, dropout_p=p,
                      seed=self._seed(site + 3))
             y32, yb = new(N, D_MODEL, f32), new(N, D_MODEL, bf16)
             m2, r2 = torch.empty(N, device=dev), torch.empty(N, device=dev)
@@ -824,22 +855,22 @@ class _PathRunner:
             i = self.n_enc + j
             qkv = new(M2, 3 * D_MODEL, bf16)
             in_b = L["in_b"].detach()
-            ops.gemm(gpb, W["%din_w" % i][:2 * D_MODEL], bias=in_b[:2 * D_MODEL], out_bf16=qkv[:, :2 * D_MODEL])
-            ops.gemm(gb, W["%din_w" % i][2 * D_MODEL:], bias=in_b[2 * D_MODEL:], out_bf16=qkv[:, 2 * D_MODEL:])
+            _fgemm(gpb, W["%din_w" % i][:2 * D_MODEL], bias=in_b[:2 * D_MODEL], out_bf16=qkv[:, :2 * D_MODEL])
+            _fgemm(gb, W["%din_w" % i][2 * D_MODEL:], bias=in_b[2 * D_MODEL:], out_bf16=qkv[:, 2 * D_MODEL:])
             ctxb = new(M2, D_MODEL, bf16)
             ops.attn_small_fwd(qkv[:, :D_MODEL], qkv[:, D_MODEL:2 * D_MODEL], qkv[:, 2 * D_MODEL:], plan.win_off,
                                plan.W, plan.max_win_len, N_HEADS, HEAD_DIM, ctxb, p, self._seed(site))
             u = new(M2, D_MODEL, f32)
-            ops.gemm(ctxb, W["%dout_w" % i], bias=L["out_b"].detach(), residual=g32, out_f32=u, dropout_p=p,
+            _fgemm(ctxb, W["%dout_w" % i], bias=L["out_b"].detach(), residual=g32, out_f32=u, dropout_p=p,
                      seed=self._seed(site + 1))
             t32, tb = new(M2, D_MODEL, f32), new(M2, D_MODEL, bf16)
             m3, r3 = torch.empty(M2, device=dev), torch.empty(M2, device=dev)
             ops.layernorm_fwd(u, L["g3"].detach(), L["be3"].detach(), 1e-5, t32, tb, mean=m3, rstd=r3)
             h = new(M2, FFN_DIM, bf16)
-            ops.gemm(tb, W["%dw1" % i], bias=L["b1"].detach(), act=ops.ACT_RELU, out_bf16=h, dropout_p=p,
+            _fgemm(tb, W["%dw1" % i], bias=L["b1"].detach(), act=ops.ACT_RELU, out_bf16=h, dropout_p=p,
                      seed=self._seed(site + 2))
             y32 = new(M2, D_MODEL, f32)
-            ops.gemm(h, W["%dw2" % i], bias=L["b2"].detach(), residual=t32, out_f32=y32, dropout_p=p,
+            _fgemm(h, W["%dw2" % i], bias=L["b2"].detach(), residual=t32, out_f32=y32, dropout_p=p,
                      seed=self._seed(site + 3))
             if self.save:
                 S["dec%d" % j] = dict(gb=gb, gpb=gpb, qkv=qkv, ctxb=ctxb, u=u, m3=m3, r3=r3, tb=tb, h=h, site=site)
@@ -862,7 +893,21 @@ class _PathRunner:
         N, M2, p = plan.N, plan.M2, self.p
         bf16, f32 = torch.bfloat16, torch.float32
         new = lambda r, c, dt: torch.empty(r, c, device=dev, dtype=dt)
-        zeros = lambda *s: torch.zeros(*s, device=dev, dtype=f32)
+        # every small zero-initialised accumulator of this backward (bias / LayerNorm / embedding gradients, ~60 of
+        # them) is a 256-byte aligned slice of ONE buffer cleared by one fill
+        pool = torch.zeros(1 << 18, device=dev, dtype=f32)
+        pool_pos = [0]
+
+        def zeros(*shape):
+            n = 1
+            for d in shape:
+                n *= d
+            a = pool_pos[0]
+            if n > (1 << 16) or a + n > pool.numel():
+                return torch.zeros(*shape, device=dev, dtype=f32)
+            pool_pos[0] = a + (n + 63) // 64 * 64
+            return pool[a:a + n].view(*shape)
+
         G = {}  # grads by the names of _unpack
         hook = getattr(model, "_grad_ready_hook", None)   # ddp.GradSync: start all-reducing finished gradients
         galloc = getattr(model, "_grad_alloc", None)      # ddp.GradSync: persistent per-layer gradient buffers

@@ -17,6 +17,11 @@ def _bf(w):
     return ops.cast_bf16(w.detach().reshape(w.shape[0], -1).contiguous())
 
 
+def _bfc(tag, *ws):
+    """bf16 copy of one weight (or of several stacked along rows), memoised per parameter version."""
+    return ops.cached_weight(tag, ws, lambda: _bf(ws[0] if len(ws) == 1 else torch.cat(ws, 0)))
+
+
 def _new(rows, cols, dtype, dev):
     return torch.empty(rows, cols, device=dev, dtype=dtype)
 
@@ -59,8 +64,8 @@ class PreLNAttention(torch.autograd.Function):
         h = _new(T, d, BF16, dev)
         mean, rstd = torch.empty(T, device=dev), torch.empty(T, device=dev)
         ops.layernorm_fwd(x, g.detach(), b.detach(), 1e-5, None, h, mean=mean, rstd=rstd)
-        wqkv = _bf(torch.cat([wq, wk, wv], 0))
-        bqkv = torch.cat([bq, bk, bv]).detach()
+        wqkv = _bfc("qkv", wq, wk, wv)
+        bqkv = ops.cached_weight("bqkv", (bq, bk, bv), lambda: torch.cat([bq, bk, bv]).detach().clone())
         qkv = _new(T, 3 * d, BF16, dev)
         ops.gemm(h, wqkv, bias=bqkv, out_bf16=qkv)
         att = _new(T, d, BF16, dev)
@@ -68,7 +73,7 @@ class PreLNAttention(torch.autograd.Function):
         # tcgen05 / TMEM / TMA forward; it writes the lse and uses the dropout mask function the backward kernels expect
         ops.attn_tc_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], plan.seq_off, plan.blk_seq128, plan.blk_row0_128,
                         n_heads, hd, att, lse, p_attn, seed, flops=4.0 * plan.sum_t2 * d)
-        wob = _bf(wo)
+        wob = _bfc("w", wo)
         y = _new(T, d, F32, dev)
         ops.gemm(att, wob, bias=bo.detach(), residual=x, out_f32=y, dropout_p=p_out, seed=seed + 1)
         ctx.save_for_backward(x, g, mean, rstd, h, qkv, att, lse, wqkv, wob)
@@ -116,7 +121,7 @@ class PreLNFeedForward(torch.autograd.Function):
         h = _new(T, d, BF16, dev)
         mean, rstd = torch.empty(T, device=dev), torch.empty(T, device=dev)
         ops.layernorm_fwd(x, g.detach(), b.detach(), 1e-5, None, h, mean=mean, rstd=rstd)
-        w1b, w2b = _bf(w1), _bf(w2)
+        w1b, w2b = _bfc("w", w1), _bfc("w", w2)
         z = _new(T, ffn, BF16, dev)
         ops.gemm(h, w1b, bias=b1.detach(), out_bf16=z)
         a = ops.act_dropout(z, ops.ACT_GELU, p_act, seed)
@@ -158,7 +163,7 @@ class NodeTokens(torch.autograd.Function):
     def forward(ctx, feat_b, w_s, b_s, w_o, b_o, embed, labels, feat_row, is_person):
         dev = feat_b.device
         h1 = w_s.shape[0]
-        wso = _bf(torch.cat([w_s, w_o], 0))
+        wso = _bfc("so", w_s, w_o)
         so = _new(feat_b.shape[0], 2 * h1, F32, dev)
         ops.gemm(feat_b, wso, bias=torch.cat([b_s, b_o]).detach(), out_f32=so)
         n = feat_row.numel()
@@ -193,7 +198,7 @@ class AssembleTokens(torch.autograd.Function):
     def forward(ctx, tok, tokb, evb, wa, ba, wl, temp, eemb, order, graph_tok, null_tok, desc, lap_k):
         dev = tok.device
         n, d = tokb.shape[0], wa.shape[0]
-        wab = _bf(wa)
+        wab = _bfc("w", wa)
         kp = evb.shape[1]                                    # eigenvector columns padded to a multiple of 8
         wlu = torch.zeros(d, kp, device=dev, dtype=BF16)
         wlv = torch.zeros(d, kp, device=dev, dtype=BF16)
@@ -246,7 +251,7 @@ class NodeHead(torch.autograd.Function):
         n, d = node_rows.numel(), x.shape[1]
         xn = _new(n, d, BF16, dev)
         ops.gather_rows(x, node_rows, out_bf16=xn)
-        wtb = _bf(wt)
+        wtb = _bfc("w", wt)
         z = _new(n, d, BF16, dev)
         ops.gemm(xn, wtb, bias=bt.detach(), out_bf16=z)
         a32 = ops.act_dropout(z, ops.ACT_GELU).float()

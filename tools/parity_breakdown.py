@@ -28,8 +28,7 @@ for v in range(int(sys.argv[1]) if len(sys.argv) > 1 else 8):
         feat_o = ref["global_output"]
         heads = (o.a_rel_compress, o.s_rel_compress, o.c_rel_compress)
         up = [h(feat_c, "test") for h in heads]
-        res = tempura._HeadsFn.apply(feat_o.cuda(), *[torch.cat(x, 0) for x in zip(*[h.packed() for h in (m.a_rel_compress, m.s_rel_compress, m.c_rel_compress)])],
-                                     0, 6, [3, 6, 17], [True, False, False], [None] * 3, 0)
+        res = tempura.apply_heads([m.a_rel_compress, m.s_rel_compress, m.c_rel_compress], feat_o.cuda(), 0, [None] * 3, 0)
     fe = (feat_c - feat_o).abs()
     print("video %d: feature err max %.3e (rel to max|ref| %.2e, rel-L2 %.2e)" % (
         v, fe.max().item(), fe.max().item() / feat_o.abs().max().item(), fe.norm().item() / feat_o.norm().item()))
