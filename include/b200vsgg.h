@@ -230,6 +230,15 @@ int b200vsgg_pool_bwd(const void* dz, const uint8_t* argmax, int32_t n, int32_t 
 int b200vsgg_im2col3x3(const void* z, int32_t n, int32_t hw, int32_t channels, void* out, void* stream);
 int b200vsgg_col2im3x3(const void* dcol, int32_t n, int32_t hw, int32_t channels, void* dz, void* stream);
 
+/* Relationship contrastive loss of the trainers (TEMPURA_train.py:103,209-212; TEATGT_train.py:81,176-179):
+ * pytorch_metric_learning ContrastiveLoss(pos_margin, neg_margin) on L2-normalised embeddings x fp32 [N,C] (C <= 32: the
+ * spatial / contacting distributions) with integer labels, all pairs inside each segment [seg_off[v], seg_off[v+1]) (the
+ * reference's call = one video), AvgNonZeroReducer per group.  loss fp32 [n_seg]; dx (nullable) fp32 [N,C] = gradient of
+ * loss[v] w.r.t. the segment's rows times grad_scale[0] (nullable = 1).  max_rows = longest segment (shared memory). */
+int b200vsgg_contrastive_loss(const float* x, const int32_t* label, const int32_t* seg_off, int32_t n_seg, int32_t max_rows,
+                              int32_t C, float pos_margin, float neg_margin, float* loss, float* dx, const float* grad_scale,
+                              void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * TEAT-GT / TokenGT path (lib/teatgt.py, tools/TokenGT/tokengt).
  */

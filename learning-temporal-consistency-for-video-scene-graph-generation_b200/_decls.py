@@ -70,6 +70,7 @@ SIGNATURES = {
     "b200vsgg_obj_tokens_fwd": [C.POINTER(ObjTokens), vp, vp, vp],
     "b200vsgg_obj_tokens_bwd": [C.POINTER(ObjTokens), vp, vp, vp, vp, vp, vp, vp],
     "b200vsgg_rel_loss": [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "b200vsgg_contrastive_loss": [vp, vp, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp],
     "b200vsgg_graph_small_params_per_layer": [i32, i32],
     "b200vsgg_graph_small_fwd": [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
     "b200vsgg_upload": [vp, vp, i64, vp],

@@ -676,6 +676,19 @@ def rel_loss(att, spa, con, att_label, spa_t, con_t, row_w, want_grad=True):
     return (losses, *grads)
 
 
+def contrastive_loss(x, label, seg_off, max_rows, pos_margin=0.0, neg_margin=1.0, want_grad=True):
+    """b200vsgg_contrastive_loss: per-segment ContrastiveLoss values [n_seg] and d(loss[v])/dx (or None)."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and label.dtype == torch.int32 and seg_off.dtype == torch.int32
+    n_seg = seg_off.numel() - 1
+    loss = torch.empty(n_seg, device=x.device)
+    dx = torch.empty_like(x) if want_grad else None
+    check(_lib.lib().b200vsgg_contrastive_loss(_ptr(x), _ptr(label), _ptr(seg_off), n_seg, int(max_rows), x.shape[1],
+                                                pos_margin, neg_margin, _ptr(loss), _ptr(dx), None, _stream()),
+          "contrastive_loss")
+    _count()
+    return loss, dx
+
+
 def graph_small_fwd(nodes, upper, counts, dim, heads, depth, params, pool_w, pool_b):
     """b200vsgg_graph_small_fwd: nodes fp32 [F, nmax, dim], upper uint8 [F, nmax, nmax], counts int32 [F] -> [F, dim]."""
     F_, nmax = nodes.shape[0], nodes.shape[1]

@@ -1081,6 +1081,41 @@ class _RelLossFn(torch.autograd.Function):
         return da * ga, ds * gs, dc * gc, None, None, None, None
 
 
+class _ContrastiveFn(torch.autograd.Function):
+    """pytorch_metric_learning ContrastiveLoss(pos_margin=0, neg_margin=1) per video, loss and gradient in one launch."""
+
+    @staticmethod
+    def forward(ctx, x, label, seg_off, max_rows):
+        loss, dx = ops.contrastive_loss(x.contiguous().float(), label, seg_off, max_rows, 0.0, 1.0, x.requires_grad)
+        ctx.dx, ctx.seg_off = dx, seg_off
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        rows = torch.repeat_interleave(g, (ctx.seg_off[1:] - ctx.seg_off[:-1]).long())
+        return ctx.dx * rows[:, None], None, None, None
+
+
+def contrastive_relation_losses(pred, plan, spatial_label, contact_label, weight=0.2):
+    """`--use_ctl_loss` of the trainers (TEMPURA_train.py:209-212, TEATGT_train.py:176-179):
+    0.2 * ContrastiveLoss(spatial_distribution, argmax(spatial_label, 1)) and the same for contacting; spatial_label /
+    contact_label are the trainer's multi-hot matrices [N,6] / [N,17] (or int class indices [N]).  With a batch of videos
+    each video is one ContrastiveLoss call (pairs never cross a video) and the results are averaged."""
+    dev = pred["spatial_distribution"].device
+    if plan is not None and plan.V > 1:
+        off = np.asarray(plan.pair_off_video_h, dtype=np.int32)
+    else:
+        off = np.asarray([0, pred["spatial_distribution"].shape[0]], dtype=np.int32)
+    seg_off = ops.upload(off, dev)
+    max_rows = int(np.diff(off).max())
+    out = {}
+    for name, dist, lab in (("spatial_con_loss", pred["spatial_distribution"], spatial_label),
+                            ("contact_con_loss", pred["contacting_distribution"], contact_label)):
+        idx = (lab.argmax(1) if lab.dim() == 2 else lab).to(torch.int32).contiguous()
+        out[name] = weight * _ContrastiveFn.apply(dist, idx, seg_off, max_rows).mean()
+    return out
+
+
 def gt_label_csr(entry, device, num_classes=None):
     """Ragged predicate labels as the dataloader yields them (lists of class ids per pair) -> what the loss kernel
     consumes: attention class index int64 [N] and CSR (offsets int32 [N+1], ids int32) for spatial / contacting.

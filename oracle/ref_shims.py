@@ -248,6 +248,27 @@ def install_graph_transformer():
     _mod("graph_transformer_pytorch", GraphTransformer=GraphTransformer)
 
 
+# ------------------------------------------------------------------------------ pytorch_metric_learning
+def contrastive_loss(embeddings, labels, pos_margin=0.0, neg_margin=1.0):
+    """Restatement of pytorch_metric_learning.losses.ContrastiveLoss(pos_margin, neg_margin) with its defaults
+    (LpDistance(normalize_embeddings=True, p=2, power=1), all pairs i != j of the call, AvgNonZeroReducer per group,
+    the two group means added) — the package is absent from the reference tree and unversioned: PARITY UNPINNED.
+    Call sites: TEMPURA_train.py:103,209-212; TEATGT_train.py:81,176-179."""
+    e = torch.nn.functional.normalize(embeddings, p=2, dim=1)
+    d = torch.cdist(e, e, p=2, compute_mode="donot_use_mm_for_euclid_dist")   # LpDistance -> torch.cdist (gradient 0 at d = 0)
+    n = e.shape[0]
+    off = ~torch.eye(n, dtype=torch.bool)
+    same = labels[:, None] == labels[None, :]
+    pos = torch.relu(d - pos_margin)[same & off]
+    neg = torch.relu(neg_margin - d)[(~same) & off]
+
+    def avg_non_zero(v):
+        nz = v > 0
+        return v[nz].sum() / nz.sum() if nz.any() else v.sum() * 0.0
+
+    return avg_non_zero(pos) + avg_non_zero(neg)
+
+
 # ----------------------------------------------------------------------------- absent native ops
 def install_reference_native_stubs():
     class _InertROIAlign(nn.Module):

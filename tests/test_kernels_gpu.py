@@ -421,3 +421,30 @@ def test_gated_residual_matches_torch(cuda_lib, dim):
     x = res.cuda().contiguous()
     ops.gated_residual(o.cuda().contiguous(), x, w.cuda().contiguous())
     assert (x.cpu() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("C", [6, 17])
+def test_contrastive_loss_matches_oracle_restatement(cuda_lib, C):
+    """b200vsgg_contrastive_loss (loss + gradient, one CTA per video) vs the oracle's restatement of
+    pytorch_metric_learning ContrastiveLoss(pos_margin=0, neg_margin=1) (oracle/ref_shims.py — PARITY UNPINNED: the
+    package is absent from the reference tree) through autograd, three ragged videos."""
+    from b200vsgg import ops
+    from oracle.ref_shims import contrastive_loss
+    g = torch.Generator().manual_seed(C)
+    lens = [37, 260, 5]
+    N = sum(lens)
+    x = torch.sigmoid(torch.randn(N, C, generator=g)).requires_grad_(True)       # the distributions the trainer passes
+    lab = torch.randint(0, C, (N,), generator=g)
+    x.data[3] = x.data[2]                                                          # a coinciding positive pair (d = 0)
+    lab[3] = lab[2]
+    off = [0]
+    for n in lens:
+        off.append(off[-1] + n)
+    ref = torch.stack([contrastive_loss(x[a:b], lab[a:b]) for a, b in zip(off[:-1], off[1:])])
+    w = torch.tensor([1.0, 0.5, 2.0])
+    (ref * w).sum().backward()
+    loss, dx = ops.contrastive_loss(x.detach().cuda().contiguous(), lab.int().cuda(), torch.tensor(off, dtype=torch.int32).cuda(),
+                                    max(lens))
+    assert (loss.cpu() - ref.detach()).abs().max().item() <= 1e-5
+    got = dx.cpu() * torch.repeat_interleave(w, torch.tensor(lens))[:, None]
+    assert (got - x.grad).abs().max().item() <= 1e-5 * max(1.0, x.grad.abs().max().item()) + 1e-7

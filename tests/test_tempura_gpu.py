@@ -353,3 +353,33 @@ def test_producer_side_bf16_handoff_matches_fp32_handoff(pair):
         d = (grads[0][n] - grads[1][n]).norm().item()
         assert d <= (0.15 if n.startswith("conv.") else 6e-2) * grads[0][n].norm().item() + 1e-9, (n, d)
     assert launches[1] < launches[0]                       # the NCHW -> NHWC layout kernel is gone
+
+
+def test_contrastive_relation_losses_batch_equals_per_video_restatement(pair):
+    """`--use_ctl_loss` (TEMPURA_train.py:209-212): 0.2 * ContrastiveLoss on the spatial / contacting distributions with
+    argmax labels, one call per video, averaged over the batch; values and gradients vs the oracle restatement
+    (PARITY UNPINNED: pytorch_metric_learning is absent from the reference tree)."""
+    from b200vsgg import synthetic, tempura
+    from oracle.ref_shims import contrastive_loss
+    m, _ = pair
+    m.eval()
+    m.rel_memory = []
+    entries = [synthetic.make_video_entry(80 + i, f, (2, 6), device="cuda") for i, f in enumerate((4, 7, 3))]
+    gts = [synthetic.build_gt_tensors(e, "cuda") for e in entries]
+    with torch.no_grad():
+        pred = m(tempura.collate_entries(entries), phase="test")
+    spa = pred["spatial_distribution"].detach().clone().requires_grad_(True)
+    con = pred["contacting_distribution"].detach().clone().requires_grad_(True)
+    spa_l, con_l = torch.cat([g[1] for g in gts]), torch.cat([g[2] for g in gts])
+    got = tempura.contrastive_relation_losses({"spatial_distribution": spa, "contacting_distribution": con}, m.last_plan,
+                                              spa_l, con_l)
+    (got["spatial_con_loss"] + got["contact_con_loss"]).backward()
+    sc, cc = spa.detach().cpu().requires_grad_(True), con.detach().cpu().requires_grad_(True)
+    off = [0]
+    for e in entries:
+        off.append(off[-1] + e["pair_idx"].shape[0])
+    ref_s = 0.2 * torch.stack([contrastive_loss(sc[a:b], spa_l.cpu()[a:b].argmax(1)) for a, b in zip(off[:-1], off[1:])]).mean()
+    ref_c = 0.2 * torch.stack([contrastive_loss(cc[a:b], con_l.cpu()[a:b].argmax(1)) for a, b in zip(off[:-1], off[1:])]).mean()
+    (ref_s + ref_c).backward()
+    assert abs(got["spatial_con_loss"].item() - ref_s.item()) <= 1e-5 and abs(got["contact_con_loss"].item() - ref_c.item()) <= 1e-5
+    assert (spa.grad.cpu() - sc.grad).abs().max().item() <= 1e-5 and (con.grad.cpu() - cc.grad).abs().max().item() <= 1e-5
