@@ -211,7 +211,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                 float mx = -INFINITY;
                 if (kvalid == BKV) {
 #pragma unroll
-                    for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                    for (int i = 0; i < 64; ++i)        // three-input maximum (FMNMX3): one issue slot per two scores
+                        mx = fmaxf(fmaxf(mx, __uint_as_float(r[2 * i])), __uint_as_float(r[2 * i + 1]));
                 } else {
 #pragma unroll
                     for (int i = 0; i < 128; ++i) {
@@ -229,14 +230,18 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                     m_ref = mx;
                     rescale = true;
                 }
-                float sum = 0.f;
+                // exponent arguments and the row sum run on the packed fp32x2 pipes (FFMA2 / FADD2): per PAIR of scores
+                // one FFMA2, two MUFU.EX2, one FADD2, one pack — the MUFU, not the issue port, is the limit
+                float sum = 0.f, sum1 = 0.f;
+                const float nm = -m_ref;
                 uint32_t pk[64];
                 if (thr == 0u) {
 #pragma unroll
                     for (int i = 0; i < 64; ++i) {
-                        const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i]), scale_log2, -m_ref));
-                        const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -m_ref));
-                        sum += p0 + p1;
+                        float a0, a1;
+                        ptx::fma2(a0, a1, __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]), scale_log2, scale_log2, nm, nm);
+                        const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);
+                        ptx::add2(sum, sum1, sum, sum1, p0, p1);
                         pk[i] = pack2(p0, p1);
                     }
                 } else {
@@ -244,19 +249,20 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                     const uint32_t sd[2] = {adrop::stream_seed(row_key, kb64), adrop::stream_seed(row_key, kb64 + 1u)};
 #pragma unroll
                     for (int g4 = 0; g4 < 32; ++g4) {                          // groups of four keys
-                        float p[4];
+                        float p[4], a[4];
+                        ptx::fma2(a[0], a[1], __uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1]), scale_log2, scale_log2, nm, nm);
+                        ptx::fma2(a[2], a[3], __uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3]), scale_log2, scale_log2, nm, nm);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            p[e] = ptx::ex2_approx(fmaf(__uint_as_float(r[4 * g4 + e]), scale_log2, -m_ref));
-                            sum += p[e];
-                        }
+                        for (int e = 0; e < 4; ++e) p[e] = ptx::ex2_approx(a[e]);
+                        ptx::add2(sum, sum1, sum, sum1, p[0], p[1]);
+                        ptx::add2(sum, sum1, sum, sum1, p[2], p[3]);
                         uint32_t lo, hi;
                         adrop::keep_masks4(adrop::draw(sd[g4 >> 4], (g4 & 15) >> 1, g4 & 1), K8, lo, hi);
                         pk[2 * g4] = pack2(p[0], p[1]) & lo;
                         pk[2 * g4 + 1] = pack2(p[2], p[3]) & hi;
                     }
                 }
-                l = l * alpha + sum;
+                l = l * alpha + (sum + sum1);
                 if (j > 0) {                                // P and O are free once the previous P V has retired
                     ptx::mbar_wait(o_done, (g - 1) & 1u);
                     ptx::tc_fence_after();

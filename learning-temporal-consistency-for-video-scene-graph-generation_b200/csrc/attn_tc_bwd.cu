@@ -218,6 +218,7 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant_
             const float lse2 = row_ok ? lse[gidx] * LOG2E : INFINITY;       // invalid rows: P = 0
             const float delta_s = row_ok ? delta[gidx] / inv_keep : 0.f;    // dS = ik * P (keep ? dP : 0  -  delta / ik)
             const uint32_t rk = thr ? adrop::row_key(seed, qrow0 + row, head) : 0u;
+            const float nlse = -lse2, ndelta = -delta_s;
             for (int j = 0; j < nkb; ++j, ++g) {
                 const int kvalid = min(BKV, s1 - (s0 + j * BKV)) - ch * 64;   // valid keys among this half's 64 columns
                 uint32_t rs[64], rd[64];
@@ -240,17 +241,21 @@ attn_tc_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant_
                         e = ((t & 0x00FF00FFu) + K8) & 0x01000100u;
                         o = (((t >> 8) & 0x00FF00FFu) + K8) & 0x01000100u;
                     }
-                    float ds[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int i = 4 * g4 + c;
-                        const float p = ptx::ex2_approx(fmaf(__uint_as_float(rs[i]), scale_log2, -lse2));
-                        // keys (0,1) of the group sit in the even bytes (bits 8 / 24 of e), (2,3) in the odd ones
-                        const uint32_t bit = (c == 0) ? (e & 0x100u) : (c == 1) ? (e & 0x1000000u) : (c == 2) ? (o & 0x100u)
-                                                                                                               : (o & 0x1000000u);
-                        const float dpe = bit ? __uint_as_float(rd[i]) : 0.f;
-                        ds[c] = p * (dpe - delta_s);
-                    }
+                    // packed fp32x2 pipes (FFMA2 / FADD2 / FMUL2): one issue slot per pair of keys for the exponent
+                    // argument, the (dP - delta) term and the product
+                    float ds[4], a[4], dpe[4];
+                    const int i0 = 4 * g4;
+                    ptx::fma2(a[0], a[1], __uint_as_float(rs[i0]), __uint_as_float(rs[i0 + 1]), scale_log2, scale_log2, nlse, nlse);
+                    ptx::fma2(a[2], a[3], __uint_as_float(rs[i0 + 2]), __uint_as_float(rs[i0 + 3]), scale_log2, scale_log2, nlse, nlse);
+                    // keys (0,1) of the group sit in the even bytes (bits 8 / 24 of e), (2,3) in the odd ones
+                    dpe[0] = (e & 0x100u) ? __uint_as_float(rd[i0]) : 0.f;
+                    dpe[1] = (e & 0x1000000u) ? __uint_as_float(rd[i0 + 1]) : 0.f;
+                    dpe[2] = (o & 0x100u) ? __uint_as_float(rd[i0 + 2]) : 0.f;
+                    dpe[3] = (o & 0x1000000u) ? __uint_as_float(rd[i0 + 3]) : 0.f;
+                    ptx::add2(dpe[0], dpe[1], dpe[0], dpe[1], ndelta, ndelta);
+                    ptx::add2(dpe[2], dpe[3], dpe[2], dpe[3], ndelta, ndelta);
+                    ptx::mul2(ds[0], ds[1], ptx::ex2_approx(a[0]), ptx::ex2_approx(a[1]), dpe[0], dpe[1]);
+                    ptx::mul2(ds[2], ds[3], ptx::ex2_approx(a[2]), ptx::ex2_approx(a[3]), dpe[2], dpe[3]);
                     pk[2 * g4] = pack2(ds[0], ds[1]);
                     pk[2 * g4 + 1] = pack2(ds[2], ds[3]);
                 }
@@ -523,19 +528,25 @@ attn_tc_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                     if (thr) s4 = *reinterpret_cast<const uint4*>(sdrow + 4 * g4);
                     const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
                     const uint32_t sv[4] = {s4.x, s4.y, s4.z, s4.w};
-                    float p[4], ds[4];
+                    float p[4], ds[4], a[4], pr[4], dpe[4];
+                    const int c0 = 4 * g4;
+                    ptx::fma2(a[0], a[1], __uint_as_float(rs[c0]), __uint_as_float(rs[c0 + 1]), scale_log2, scale_log2, -lv[0], -lv[1]);
+                    ptx::fma2(a[2], a[3], __uint_as_float(rs[c0 + 2]), __uint_as_float(rs[c0 + 3]), scale_log2, scale_log2, -lv[2], -lv[3]);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const int col = 4 * g4 + c;
-                        const float pr = ptx::ex2_approx(fmaf(__uint_as_float(rs[col]), scale_log2, -lv[c]));
+                        pr[c] = ptx::ex2_approx(a[c]);
                         bool kept = true;
                         if (thr) {
                             const uint32_t sx = sv[c] * la + lc;
                             kept = ((sx ^ (sx >> 16)) & byte_mask) >= thr_sh;
                         }
-                        p[c] = kept ? pr : 0.f;
-                        ds[c] = pr * ((kept ? __uint_as_float(rd[col]) : 0.f) - dl[c]);
+                        p[c] = kept ? pr[c] : 0.f;
+                        dpe[c] = kept ? __uint_as_float(rd[c0 + c]) : 0.f;
                     }
+                    ptx::add2(dpe[0], dpe[1], dpe[0], dpe[1], -dl[0], -dl[1]);
+                    ptx::add2(dpe[2], dpe[3], dpe[2], dpe[3], -dl[2], -dl[3]);
+                    ptx::mul2(ds[0], ds[1], pr[0], pr[1], dpe[0], dpe[1]);
+                    ptx::mul2(ds[2], ds[3], pr[2], pr[3], dpe[2], dpe[3]);
                     pp[2 * g4] = pack2(p[0], p[1]);
                     pp[2 * g4 + 1] = pack2(p[2], p[3]);
                     pd[2 * g4] = pack2(ds[0], ds[1]);
