@@ -14,6 +14,7 @@
 // this kernel is therefore HBM bytes.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <algorithm>
 #include <cstdint>
 
 #include "../../include/b200vsgg.h"
@@ -609,6 +610,284 @@ attn_mma_bwd2_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// QUAD kernels for 17..32-token segments (the 2-frame temporal windows): one 128-thread CTA per (segment, head) unit,
+// several CTAs per SM.  The warp-pair kernels above ran 4..6 warps per SM and spent ~14 us per unit on a chain of
+// dependent steps executed by two warps (ncu: 5 % active warps, 10 % of DRAM bandwidth).  Here
+//   * operand tiles have only as many rows as the longest segment of the launch (rounded to 8; ldmatrix row
+//     addresses are clamped), so 3 (backward) / 5 (forward) CTAs = 12 / 20 warps fit per SM;
+//   * S = Q K^T (and dP = dO V^T) are split by OUTPUT block: warp w owns the 16x16 block (w>>1, w&1) over the whole
+//     head dimension — no partial sums to exchange, deterministic;
+//   * softmax / dropout / dS run once per row (warp = row, lane = key) on the fp32 scores in shared memory, instead
+//     of redundantly in every warp's fragment layout;
+//   * the output products are split by head-dimension column group (warp w: groups w and w+4), their results are
+//     written IN PLACE over the B operand they were computed from (dQ over K, dK over Q, dV over dO, O over V: a
+//     warp only ever touches its own columns), and rows leave the CTA as 16-byte stores (lane = aligned chunk;
+//     the two chunks a head shares with its neighbours use masked 4-byte stores).
+// ------------------------------------------------------------------------------------------------
+constexpr int AW_SP = 36;   // pitch (floats) of the fp32 score tiles
+constexpr int AW_TP = 80;   // pitch (bytes) of the bf16 [32][32] probability tiles: 5 chunks (odd) -> conflict-free ldmatrix
+
+// Stage one operand tile (lane = chunk, warps stride over the rows); returns nothing, caller waits.
+__device__ __forceinline__ void aw_stage(uint8_t* tile, const __nv_bfloat16* src, int ld, const HeadGeom& g, int warp, int lane) {
+    if (lane < g.nch) {
+        const __nv_bfloat16* sp = src + static_cast<size_t>(g.row0 + warp) * ld + (g.c_lo + lane) * 8;
+        uint32_t dp = s_u32(tile) + warp * AM_PITCH_B + lane * 16;
+        for (int r = warp; r < g.L; r += 4) {
+            cp_async16(dp, sp);
+            sp += static_cast<size_t>(4) * ld;
+            dp += 4 * AM_PITCH_B;
+        }
+    }
+}
+// Zero the foreign columns of the chunks THIS thread staged (first / last chunk of its rows) and the pad chunk.
+__device__ __forceinline__ void aw_fix_slop(uint8_t* tile, const HeadGeom& g, int hd, int warp, int lane) {
+    const int last = g.nch - 1;
+    if (lane != 0 && lane != last) return;
+    const int end = g.phase + hd - last * 8;          // valid elements of the last chunk (2..8, even)
+    for (int r = warp; r < g.L; r += 4) {
+        uint32_t* row = reinterpret_cast<uint32_t*>(tile + r * AM_PITCH_B);
+        if (lane == 0)
+            for (int e = 0; e < g.phase; e += 2) row[e >> 1] = 0u;
+        if (lane == last) {
+            for (int e = end; e < 8; e += 2) row[last * 4 + (e >> 1)] = 0u;
+            *reinterpret_cast<uint4*>(tile + r * AM_PITCH_B + g.nch * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+// Warp w computes the 16x16 block (mt = w>>1, key half nh = w&1) of A . B^T over all k-steps and writes it to the
+// fp32 tile S (rows = A rows, columns = B rows).  Row addresses are clamped to the allocated tile rows.
+__device__ __forceinline__ void aw_block_product(float* S, const uint8_t* A, const uint8_t* B, int ksteps, int L, int rows_alloc,
+                                                 int warp, int lane) {
+    const int mt = warp >> 1, nh = warp & 1;
+    if (mt * 16 >= L || nh * 16 >= L) return;
+    const int ar = min(mt * 16 + (lane & 15), rows_alloc - 1);
+    const int br = min(nh * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, rows_alloc - 1);
+    const uint32_t a_base = s_u32(A) + ar * AM_PITCH_B + (lane >> 4) * 16;
+    const uint32_t b_base = s_u32(B) + br * AM_PITCH_B + ((lane >> 3) & 1) * 16;
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 4
+    for (int ks = 0; ks < ksteps; ++ks) {
+        uint32_t a[4], b[4];
+        ldsm_x4(a, a_base + ks * 32);
+        ldsm_x4(b, b_base + ks * 32);
+        mma_bf16(acc[0], a, b[0], b[1]);
+        mma_bf16(acc[1], a, b[2], b[3]);
+    }
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        float* d = S + (mt * 16 + gq) * AW_SP + (nh * 2 + t) * 8 + tq * 2;
+        *reinterpret_cast<float2*>(d) = make_float2(acc[t][0], acc[t][1]);
+        *reinterpret_cast<float2*>(d + 8 * AW_SP) = make_float2(acc[t][2], acc[t][3]);
+    }
+}
+// A fragments of a [32][32] bf16 tile T (pitch AW_TP): plain (rows of T are the output rows) or transposed.
+__device__ __forceinline__ void aw_load_a(uint32_t (&a)[2][2][4], const uint8_t* T, bool transposed, int lane) {
+    if (!transposed) {
+        const uint32_t base = s_u32(T) + (lane & 15) * AW_TP + (lane >> 4) * 16;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) ldsm_x4(a[mt][kk], base + mt * 16 * AW_TP + kk * 32);
+    } else {
+        const uint32_t base = s_u32(T) + ((lane & 7) + ((lane >> 4) & 1) * 8) * AW_TP + ((lane >> 3) & 1) * 16;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) ldsm_x4_t(a[mt][kk], base + kk * 16 * AW_TP + mt * 32);
+    }
+}
+// out[:, columns of group dg] = scale * A . Bt for this warp's column groups, written over Bt's own columns.
+__device__ __forceinline__ void aw_out_product_inplace(const uint32_t (&a)[2][2][4], uint8_t* Bt, int ngroups, int L, int rows_alloc,
+                                                       float out_scale, int warp, int lane) {
+    const int gq = lane >> 2, tq = lane & 3;
+    const int k0 = min(lane & 15, rows_alloc - 1), k1 = min(16 + (lane & 15), rows_alloc - 1);
+    const uint32_t b0 = s_u32(Bt) + k0 * AM_PITCH_B + (lane >> 4) * 16;
+    const uint32_t b1 = s_u32(Bt) + k1 * AM_PITCH_B + (lane >> 4) * 16;
+    const bool two_m = L > 16, two_k = L > 16;
+    for (int dg = warp; dg < ngroups; dg += 4) {
+        float o[2][4][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[mt][j][e] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            if (kk == 1 && !two_k) break;
+#pragma unroll
+            for (int dp = 0; dp < 2; ++dp) {
+                uint32_t b[4];
+                ldsm_x4_t(b, (kk ? b1 : b0) + (dg * 4 + dp * 2) * 16);
+                mma_bf16(o[0][dp * 2], a[0][kk], b[0], b[1]);
+                mma_bf16(o[0][dp * 2 + 1], a[0][kk], b[2], b[3]);
+                if (two_m) {
+                    mma_bf16(o[1][dp * 2], a[1][kk], b[0], b[1]);
+                    mma_bf16(o[1][dp * 2 + 1], a[1][kk], b[2], b[3]);
+                }
+            }
+        }
+        __syncwarp();      // every lane's ldmatrix of these columns has executed before they are overwritten
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int r0 = mt * 16 + gq, r1 = r0 + 8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint8_t* d = Bt + (dg * 4 + j) * 16 + tq * 4;
+                if (r0 < L) *reinterpret_cast<uint32_t*>(d + r0 * AM_PITCH_B) = pack_bf16(o[mt][j][0] * out_scale, o[mt][j][1] * out_scale);
+                if (r1 < L) *reinterpret_cast<uint32_t*>(d + r1 * AM_PITCH_B) = pack_bf16(o[mt][j][2] * out_scale, o[mt][j][3] * out_scale);
+            }
+        }
+    }
+}
+// Rows [0,L) of a tile -> global rows, columns of the head only: 16-byte stores for chunks inside the head.
+__device__ __forceinline__ void aw_store_tile(const uint8_t* tile, __nv_bfloat16* out, int ldo, const HeadGeom& g, int hd, bool vec,
+                                              int warp, int lane) {
+    if (lane >= g.nch) return;
+    const int gc = (g.c_lo + lane) * 8;                            // first global column of this lane's chunk
+    const int lo = max(g.col0, gc) - gc, hi = min(g.col0 + hd, gc + 8) - gc;
+    const bool whole = vec && lo == 0 && hi == 8;
+    for (int r = warp; r < g.L; r += 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(tile + r * AM_PITCH_B + lane * 16);
+        __nv_bfloat16* dst = out + static_cast<size_t>(g.row0 + r) * ldo + gc;
+        if (whole) {
+            *reinterpret_cast<uint4*>(dst) = v;
+        } else {
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (2 * e >= lo && 2 * e < hi) *reinterpret_cast<uint32_t*>(dst + 2 * e) = w[e];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+attn_win_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
+                    const __nv_bfloat16* __restrict__ v, int ldv, const int32_t* __restrict__ seg_off, int n_units,
+                    int n_heads, int hd, float scale, __nv_bfloat16* __restrict__ ctx, int ldc, float drop_p,
+                    unsigned long long seed, int rows_alloc, int vec) {
+    extern __shared__ __align__(16) uint8_t am_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int TILE = rows_alloc * AM_PITCH_B;
+    uint8_t* Qs = am_smem;
+    uint8_t* Ks = Qs + TILE;
+    uint8_t* Vs = Ks + TILE;
+    float* S = reinterpret_cast<float*>(Vs + TILE);
+    uint8_t* Tp = reinterpret_cast<uint8_t*>(S + 32 * AW_SP);
+    for (int i = threadIdx.x; i < 3 * TILE / 16; i += 128) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        HeadGeom g;
+        int head;
+        if (!head_geom(seg_off, unit, n_heads, hd, g, head)) continue;      // uniform in the CTA
+        aw_stage(Qs, q, ldq, g, warp, lane);
+        aw_stage(Ks, k, ldk, g, warp, lane);
+        aw_stage(Vs, v, ldv, g, warp, lane);
+        cp_async_wait_all();
+        aw_fix_slop(Qs, g, hd, warp, lane);
+        __syncthreads();
+        aw_block_product(S, Qs, Ks, (g.nch + 1) >> 1, g.L, rows_alloc, warp, lane);
+        __syncthreads();
+        // softmax + dropout, one row per warp pass, lane = key
+        for (int i = warp; i < 32; i += 4) {
+            float pv = 0.f;
+            if (i < g.L) {
+                const float sv = lane < g.L ? S[i * AW_SP + lane] * scale : -INFINITY;
+                const float mx = warp_max(sv);
+                const float ex = __expf(sv - mx);
+                const float inv = 1.f / warp_sum(ex);
+                pv = lane < g.L ? ex * inv * am_drop_factor(thr, inv_keep, seed, g.row0 + i, head, lane) : 0.f;
+            }
+            *reinterpret_cast<__nv_bfloat16*>(Tp + i * AW_TP + lane * 2) = __float2bfloat16_rn(pv);
+        }
+        __syncthreads();
+        uint32_t pa[2][2][4];
+        aw_load_a(pa, Tp, false, lane);
+        aw_out_product_inplace(pa, Vs, (g.nch + 3) >> 2, g.L, rows_alloc, 1.f, warp, lane);
+        __syncthreads();
+        aw_store_tile(Vs, ctx, ldc, g, hd, vec != 0, warp, lane);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(128)
+attn_win_bwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
+                    const __nv_bfloat16* __restrict__ v, int ldv, const __nv_bfloat16* __restrict__ dctx, int ldc,
+                    const int32_t* __restrict__ seg_off, int n_units, int n_heads, int hd, float scale,
+                    __nv_bfloat16* __restrict__ dq, int lddq, __nv_bfloat16* __restrict__ dk, int lddk,
+                    __nv_bfloat16* __restrict__ dv, int lddv, float drop_p, unsigned long long seed, int rows_alloc, int vec) {
+    extern __shared__ __align__(16) uint8_t am_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int TILE = rows_alloc * AM_PITCH_B;
+    uint8_t* Qs = am_smem;
+    uint8_t* Ks = Qs + TILE;
+    uint8_t* Vs = Ks + TILE;
+    uint8_t* Os = Vs + TILE;
+    float* S = reinterpret_cast<float*>(Os + TILE);
+    float* D = S + 32 * AW_SP;
+    uint8_t* Tp = reinterpret_cast<uint8_t*>(D + 32 * AW_SP);
+    uint8_t* Tds = Tp + 32 * AW_TP;
+    for (int i = threadIdx.x; i < 4 * TILE / 16; i += 128) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        HeadGeom g;
+        int head;
+        if (!head_geom(seg_off, unit, n_heads, hd, g, head)) continue;
+        aw_stage(Qs, q, ldq, g, warp, lane);
+        aw_stage(Ks, k, ldk, g, warp, lane);
+        aw_stage(Vs, v, ldv, g, warp, lane);
+        aw_stage(Os, dctx, ldc, g, warp, lane);
+        cp_async_wait_all();
+        aw_fix_slop(Qs, g, hd, warp, lane);
+        aw_fix_slop(Os, g, hd, warp, lane);
+        __syncthreads();
+        const int ksteps = (g.nch + 1) >> 1;
+        aw_block_product(S, Qs, Ks, ksteps, g.L, rows_alloc, warp, lane);       // S  = Q K^T
+        aw_block_product(D, Os, Vs, ksteps, g.L, rows_alloc, warp, lane);       // dP = dO V^T
+        __syncthreads();
+        // P, dropout, dS = P o (f dP - rowsum(P o f dP)): one row per warp pass, lane = key
+        for (int i = warp; i < 32; i += 4) {
+            float pt = 0.f, ds = 0.f;
+            if (i < g.L) {
+                const bool ok = lane < g.L;
+                const float sv = ok ? S[i * AW_SP + lane] * scale : -INFINITY;
+                const float mx = warp_max(sv);
+                const float ex = __expf(sv - mx);
+                const float inv = 1.f / warp_sum(ex);
+                const float f = ok ? am_drop_factor(thr, inv_keep, seed, g.row0 + i, head, lane) : 0.f;
+                const float pe = ok ? ex * inv : 0.f;
+                const float dpe = ok ? D[i * AW_SP + lane] * f : 0.f;
+                const float delta = warp_sum(pe * dpe);
+                pt = pe * f;
+                ds = pe * (dpe - delta);
+            }
+            *reinterpret_cast<__nv_bfloat16*>(Tp + i * AW_TP + lane * 2) = __float2bfloat16_rn(pt);
+            *reinterpret_cast<__nv_bfloat16*>(Tds + i * AW_TP + lane * 2) = __float2bfloat16_rn(ds);
+        }
+        __syncthreads();
+        const int ngroups = (g.nch + 3) >> 2;
+        uint32_t a[2][2][4];
+        aw_load_a(a, Tds, false, lane);
+        aw_out_product_inplace(a, Ks, ngroups, g.L, rows_alloc, scale, warp, lane);      // dQ = scale dS K     (over K)
+        aw_load_a(a, Tds, true, lane);
+        aw_out_product_inplace(a, Qs, ngroups, g.L, rows_alloc, scale, warp, lane);      // dK = scale dS^T Q   (over Q)
+        aw_load_a(a, Tp, true, lane);
+        aw_out_product_inplace(a, Os, ngroups, g.L, rows_alloc, 1.f, warp, lane);        // dV = P~^T dO        (over dO)
+        __syncthreads();
+        aw_store_tile(Ks, dq, lddq, g, hd, vec != 0, warp, lane);
+        aw_store_tile(Qs, dk, lddk, g, hd, vec != 0, warp, lane);
+        aw_store_tile(Os, dv, lddv, g, hd, vec != 0, warp, lane);
+        __syncthreads();
+    }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename Kern>
@@ -657,15 +936,16 @@ int attn_mma_fwd_try(const void* q, int ldq, const void* k, int ldk, const void*
             (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, seg_off, n_units,
             n_heads, hd, scale, (__nv_bfloat16*)ctx, ldc, drop_p, seed);
     } else {
-        constexpr int PAIRS = 3;      // 3 warp pairs x (3 tiles + exchange) = 176 KB
-        const size_t smem = (size_t)PAIRS * (3 * 32 * AM_PITCH_B + AM_PAIR_X);
+        const int rows = (max_len + 7) & ~7;
+        const size_t smem = (size_t)3 * rows * AM_PITCH_B + 32 * AW_SP * 4 + 32 * AW_TP;
         static size_t cur = 0;
-        if ((rc = ensure_smem(attn_mma_fwd2_kernel, smem, cur))) return rc;
-        int grid = (n_units + PAIRS - 1) / PAIRS;
-        if (grid > am_num_sms()) grid = am_num_sms();
-        attn_mma_fwd2_kernel<<<grid, PAIRS * 64, smem, stream>>>(
+        if ((rc = ensure_smem(attn_win_fwd_kernel, smem, cur))) return rc;
+        const int per_sm = (int)std::min<size_t>(8, (227 * 1024) / (smem + 1024));
+        int grid = std::min(n_units, am_num_sms() * per_sm);
+        const int vec = (aligned16(ctx) && (ldc & 7) == 0) ? 1 : 0;
+        attn_win_fwd_kernel<<<grid, 128, smem, stream>>>(
             (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, seg_off, n_units,
-            n_heads, hd, scale, (__nv_bfloat16*)ctx, ldc, drop_p, seed);
+            n_heads, hd, scale, (__nv_bfloat16*)ctx, ldc, drop_p, seed, rows, vec);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
@@ -698,16 +978,17 @@ int attn_mma_bwd_try(const void* q, int ldq, const void* k, int ldk, const void*
             (const __nv_bfloat16*)dctx, ldc, seg_off, n_units, n_heads, hd, scale, (__nv_bfloat16*)dq, lddq,
             (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, drop_p, seed);
     } else {
-        constexpr int PAIRS = 2, LP = 32;   // 2 warp pairs x (4 tiles + 2 small tiles + 2 exchanges) = 177 KB
-        const size_t smem = (size_t)PAIRS * (4 * LP * AM_PITCH_B + 2 * LP * (LP + 8) * 2 + 2 * AM_PAIR_X);
+        const int rows = (max_len + 7) & ~7;
+        const size_t smem = (size_t)4 * rows * AM_PITCH_B + 2 * 32 * AW_SP * 4 + 2 * 32 * AW_TP;
         static size_t cur = 0;
-        if ((rc = ensure_smem(attn_mma_bwd2_kernel, smem, cur))) return rc;
-        int grid = (n_units + PAIRS - 1) / PAIRS;
-        if (grid > am_num_sms()) grid = am_num_sms();
-        attn_mma_bwd2_kernel<<<grid, PAIRS * 64, smem, stream>>>(
+        if ((rc = ensure_smem(attn_win_bwd_kernel, smem, cur))) return rc;
+        const int per_sm = (int)std::min<size_t>(8, (227 * 1024) / (smem + 1024));
+        int grid = std::min(n_units, am_num_sms() * per_sm);
+        const int vec = (aligned16(dq) && aligned16(dk) && aligned16(dv) && ((lddq | lddk | lddv) & 7) == 0) ? 1 : 0;
+        attn_win_bwd_kernel<<<grid, 128, smem, stream>>>(
             (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv,
             (const __nv_bfloat16*)dctx, ldc, seg_off, n_units, n_heads, hd, scale, (__nv_bfloat16*)dq, lddq,
-            (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, drop_p, seed);
+            (__nv_bfloat16*)dk, lddk, (__nv_bfloat16*)dv, lddv, drop_p, seed, rows, vec);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));

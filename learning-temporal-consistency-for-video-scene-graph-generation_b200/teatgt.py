@@ -386,6 +386,11 @@ class TEAT_GT(nn.Module):
         K = int(getattr(self, "pipeline_chunks", 4))
         if fpv is None or len(fpv) < 2 or K < 2 or self.mode != "predcls" or "indices" in entry:
             return None
+        # measured (tools/bench_teatgt.py --chunks, profiles/r02_teat_chunks.jsonl): a 64 x 32-frame TRAINING batch is
+        # launch-bound on the host — 4 chunks = 4x the launches: 212 -> 244 ms per step — while long clips, whose host
+        # graph build takes 0.7 s, gain 21 % (2.45 -> 1.94 s).  Split only when the host work is worth hiding.
+        if int(entry["pair_idx"].shape[0]) < int(getattr(self, "pipeline_min_pairs", 40000)):
+            return None
         fpv = np.asarray(fpv, dtype=np.int64)
         V = fpv.shape[0]
         K = min(K, V)

@@ -186,6 +186,37 @@ def test_attn_small_fwd_bwd(cuda_lib, H, hd, lens):
         assert (got.float() - want).abs().max().item() < tol
 
 
+def test_attn_window_kernels_with_unaligned_outputs(cuda_lib):
+    """17..32-token segments take the quad kernels; outputs whose rows are only 4-byte aligned (column views at an odd
+    pair offset) must take the masked 4-byte store path and give the same numbers as the 16-byte path."""
+    from b200vsgg import ops
+    H, hd, lens = 8, 242, [20, 17, 32, 24, 18]
+    D, M = H * hd, sum(lens)
+    seg = [0]
+    for n in lens:
+        seg.append(seg[-1] + n)
+    g = _gen(M + 1)
+    qkv = torch.randn(M, 3 * D, generator=g, device=DEV).bfloat16()
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    dctx = torch.randn(M, D, generator=g, device=DEV).bfloat16()
+    seg_off = torch.tensor(seg, dtype=torch.int32, device=DEV)
+    res = []
+    for shift in (0, 2):
+        cbuf = torch.full((M, D + 8), 7.0, device=DEV, dtype=torch.bfloat16)
+        gbuf = torch.full((M, 3 * (D + 8)), 7.0, device=DEV, dtype=torch.bfloat16)
+        ctx = cbuf[:, shift:shift + D]
+        dq, dk, dv = (gbuf[:, i * (D + 8) + shift:i * (D + 8) + shift + D] for i in range(3))
+        ops.attn_small_fwd(q, k, v, seg_off, len(lens), max(lens), H, hd, ctx, 0.1, 11)
+        ops.attn_small_bwd(q, k, v, dctx, seg_off, len(lens), max(lens), H, hd, dq, dk, dv, 0.1, 11)
+        res.append([t.clone() for t in (ctx, dq, dk, dv)])
+        # nothing outside the views was touched
+        pad = torch.ones(D + 8, dtype=torch.bool, device=DEV)
+        pad[shift:shift + D] = False
+        assert (cbuf[:, pad] == 7.0).all() and (gbuf.view(M, 3, D + 8)[:, :, pad] == 7.0).all()
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
 def test_attn_dropout_consistency(cuda_lib):
     """With dropout the forward is a function of (seed) only, and backward uses the same mask:
     d(ctx)/d(v) for an all-ones upstream equals column sums of the dropped P."""

@@ -278,6 +278,7 @@ def test_video_chunk_pipeline_equals_single_pass(pair):
     m.train()
     m.dropout_p, m.eig_dropout = 0.0, 0.0
     res = {}
+    m.pipeline_min_pairs = 0          # force the chunked path on this small batch
     for chunks in (1, 4):
         m.pipeline_chunks = chunks
         m.zero_grad(set_to_none=True)
@@ -290,6 +291,7 @@ def test_video_chunk_pipeline_equals_single_pass(pair):
                            edges=[plan.clip_edge_index(c) for c in range(plan.n_clips)], T=plan.T, loss=loss.item(),
                            grads={n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
     m.pipeline_chunks = 4
+    del m.pipeline_min_pairs
     m.dropout_p, m.eig_dropout = 0.1, 0.2
     m.eval()
     a, b = res[1], res[4]

@@ -20,6 +20,7 @@ ap.add_argument("--eig", default="host", choices=["host", "device"])
 ap.add_argument("--mode", default="predcls", choices=["predcls", "sgcls"],
                 help="sgcls = BASELINE configs[2]: object branch + 6-layer/16-head encoder (teatgt_config.py:11-14)")
 ap.add_argument("--pairs", default="6,10", help="pairs per frame: 'lo,hi' or a single number (configs[4]: 32)")
+ap.add_argument("--chunks", type=int, default=None, help="TEAT_GT.pipeline_chunks (video chunks of the host/device pipeline)")
 a = ap.parse_args()
 ppf = tuple(int(x) for x in a.pairs.split(",")) if "," in a.pairs else int(a.pairs)
 sgcls = a.mode == "sgcls"
@@ -31,6 +32,9 @@ m = teatgt.TEAT_GT(mode=a.mode, attention_class_num=3, spatial_class_num=6, cont
 synthetic.teatgt_seeded_init_(m, 1123)
 m = m.to(dev)
 m.eig_backend = a.eig
+if a.chunks is not None:
+    m.pipeline_chunks = a.chunks
+    m.pipeline_min_pairs = 0
 if not sgcls:
     for p in m.object_classifier.parameters():
         p.requires_grad_(False)
@@ -85,6 +89,7 @@ dt = (time.perf_counter() - t0) / a.steps
 plan = m.last_plan
 print(json.dumps({"workload": "TEAT-GT %s %s, %d videos x %d frames x %s pairs/frame" % (a.mode, "inference" if a.infer else "fwd+bwd", a.videos, a.frames, a.pairs),
                   "boxes": int(batch["labels"].shape[0]),
-                  "eig_backend": a.eig, "pairs_per_s": N / dt, "ms_per_step": dt * 1e3, "pairs": N, "clips": plan.n_clips, "tokens": plan.T,
+                  "eig_backend": a.eig, "pipeline_chunks": m.pipeline_chunks, "host_graph_ms": getattr(m, "last_host_graph_ms", None),
+                  "pairs_per_s": N / dt, "ms_per_step": dt * 1e3, "pairs": N, "clips": plan.n_clips, "tokens": plan.T,
                   "max_tokens_per_clip": plan.max_T, "launches_per_step": (ops.launch_count - l0) // a.steps,
                   "loss": float(loss)}))
