@@ -629,32 +629,60 @@ attn_mma_bwd2_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
 constexpr int AW_SP = 36;   // pitch (floats) of the fp32 score tiles
 constexpr int AW_TP = 80;   // pitch (bytes) of the bf16 [32][32] probability tiles: 5 chunks (odd) -> conflict-free ldmatrix
 
-// Stage one operand tile (lane = chunk, warps stride over the rows); returns nothing, caller waits.
+__device__ __forceinline__ void cp_async16_pred(uint32_t dst, const void* src, bool p) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.cg.shared.global [%0], [%1], 16;\n}\n"
+                 ::"r"(dst), "l"(src), "r"(static_cast<int>(p)));
+}
+__device__ __forceinline__ void st_shared_pred(uint32_t dst, uint32_t v, bool p) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p st.shared.b32 [%0], %1;\n}\n" ::"r"(dst), "r"(v),
+                 "r"(static_cast<int>(p)) : "memory");
+}
+// Stage one operand tile (lane = chunk, warps stride over the rows: at most 8 rows per warp).  One 64-bit address per
+// operand, then a running pointer and predicated copies: no branches, no per-row multiplications.
 __device__ __forceinline__ void aw_stage(uint8_t* tile, const __nv_bfloat16* src, int ld, const HeadGeom& g, int warp, int lane) {
-    if (lane < g.nch) {
-        const __nv_bfloat16* sp = src + static_cast<size_t>(g.row0 + warp) * ld + (g.c_lo + lane) * 8;
-        uint32_t dp = s_u32(tile) + warp * AM_PITCH_B + lane * 16;
-        for (int r = warp; r < g.L; r += 4) {
-            cp_async16(dp, sp);
-            sp += static_cast<size_t>(4) * ld;
-            dp += 4 * AM_PITCH_B;
+    const char* sp = reinterpret_cast<const char*>(src + static_cast<size_t>(g.row0 + warp) * ld + (g.c_lo + lane) * 8);
+    const size_t step = static_cast<size_t>(ld) * 8;             // four rows, in bytes
+    const uint32_t dp = s_u32(tile) + warp * AM_PITCH_B + lane * 16;
+    const int n = lane < g.nch ? g.L - warp : 0;                 // row warp + 4t is staged  <=>  4t < n
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        cp_async16_pred(dp + t * 4 * AM_PITCH_B, sp, 4 * t < n);
+        sp += step;
+    }
+}
+// Zero the foreign columns of the chunks THIS thread staged (first / last chunk of its rows) and the pad chunk: word masks,
+// no loops over elements.
+__device__ __forceinline__ void aw_fix_slop(uint8_t* tile, const HeadGeom& g, int hd, int warp, int lane) {
+    const int last = g.nch - 1;
+    const bool is_last = lane == last;
+    if (!(is_last || (lane == 0 && g.phase > 0))) return;
+    const int end = g.phase + hd - last * 8;          // valid elements of the last chunk (2..8, even)
+    uint32_t m[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+        m[w] = ((lane != 0 || 2 * w >= g.phase) && (!is_last || 2 * w < end)) ? 0xffffffffu : 0u;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int r = warp + 4 * t;
+        if (r < g.L) {
+            uint4* p = reinterpret_cast<uint4*>(tile + r * AM_PITCH_B + lane * 16);
+            uint4 v = *p;
+            v.x &= m[0]; v.y &= m[1]; v.z &= m[2]; v.w &= m[3];
+            *p = v;
+            if (is_last) p[1] = make_uint4(0u, 0u, 0u, 0u);
         }
     }
 }
-// Zero the foreign columns of the chunks THIS thread staged (first / last chunk of its rows) and the pad chunk.
-__device__ __forceinline__ void aw_fix_slop(uint8_t* tile, const HeadGeom& g, int hd, int warp, int lane) {
-    const int last = g.nch - 1;
-    if (lane != 0 && lane != last) return;
-    const int end = g.phase + hd - last * 8;          // valid elements of the last chunk (2..8, even)
-    for (int r = warp; r < g.L; r += 4) {
-        uint32_t* row = reinterpret_cast<uint32_t*>(tile + r * AM_PITCH_B);
-        if (lane == 0)
-            for (int e = 0; e < g.phase; e += 2) row[e >> 1] = 0u;
-        if (lane == last) {
-            for (int e = end; e < 8; e += 2) row[last * 4 + (e >> 1)] = 0u;
-            *reinterpret_cast<uint4*>(tile + r * AM_PITCH_B + g.nch * 16) = make_uint4(0u, 0u, 0u, 0u);
-        }
-    }
+// Dropout factors of 4 consecutive keys of one (query row, head) from ONE 64-bit hash (16 bits per key): the quad kernels'
+// own stream — forward and backward of this kernel family regenerate the same mask, nothing else needs to agree with it.
+__device__ __forceinline__ void aw_drop4(float (&f)[4], uint32_t thr16, float inv_keep, unsigned long long seed, int row,
+                                         int head, int key0) {
+    const unsigned long long z = hash_u64(seed, (static_cast<unsigned long long>(row) * 64ull + head) * 16ull + (key0 >> 2));
+    const uint32_t lo = static_cast<uint32_t>(z), hi = static_cast<uint32_t>(z >> 32);
+    f[0] = (lo & 0xffffu) >= thr16 ? inv_keep : 0.f;
+    f[1] = (lo >> 16) >= thr16 ? inv_keep : 0.f;
+    f[2] = (hi & 0xffffu) >= thr16 ? inv_keep : 0.f;
+    f[3] = (hi >> 16) >= thr16 ? inv_keep : 0.f;
 }
 // Warp w computes the 16x16 block (mt = w>>1, key half nh = w&1) of A . B^T over all k-steps and writes it to the
 // fp32 tile S (rows = A rows, columns = B rows).  Row addresses are clamped to the allocated tile rows.
@@ -707,6 +735,8 @@ __device__ __forceinline__ void aw_out_product_inplace(const uint32_t (&a)[2][2]
     const uint32_t b0 = s_u32(Bt) + k0 * AM_PITCH_B + (lane >> 4) * 16;
     const uint32_t b1 = s_u32(Bt) + k1 * AM_PITCH_B + (lane >> 4) * 16;
     const bool two_m = L > 16, two_k = L > 16;
+    const uint32_t d0 = s_u32(Bt) + gq * AM_PITCH_B + tq * 4;
+    const bool v0 = gq < L, v1 = gq + 8 < L, v2 = gq + 16 < L, v3 = gq + 24 < L;
     for (int dg = warp; dg < ngroups; dg += 4) {
         float o[2][4][4];
 #pragma unroll
@@ -731,14 +761,14 @@ __device__ __forceinline__ void aw_out_product_inplace(const uint32_t (&a)[2][2]
             }
         }
         __syncwarp();      // every lane's ldmatrix of these columns has executed before they are overwritten
+        const uint32_t d = d0 + dg * 64;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const int r0 = mt * 16 + gq, r1 = r0 + 8;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint8_t* d = Bt + (dg * 4 + j) * 16 + tq * 4;
-                if (r0 < L) *reinterpret_cast<uint32_t*>(d + r0 * AM_PITCH_B) = pack_bf16(o[mt][j][0] * out_scale, o[mt][j][1] * out_scale);
-                if (r1 < L) *reinterpret_cast<uint32_t*>(d + r1 * AM_PITCH_B) = pack_bf16(o[mt][j][2] * out_scale, o[mt][j][3] * out_scale);
+        for (int j = 0; j < 4; ++j) {
+            st_shared_pred(d + j * 16, pack_bf16(o[0][j][0] * out_scale, o[0][j][1] * out_scale), v0);
+            st_shared_pred(d + j * 16 + 8 * AM_PITCH_B, pack_bf16(o[0][j][2] * out_scale, o[0][j][3] * out_scale), v1);
+            if (two_m) {
+                st_shared_pred(d + j * 16 + 16 * AM_PITCH_B, pack_bf16(o[1][j][0] * out_scale, o[1][j][1] * out_scale), v2);
+                st_shared_pred(d + j * 16 + 24 * AM_PITCH_B, pack_bf16(o[1][j][2] * out_scale, o[1][j][3] * out_scale), v3);
             }
         }
     }
@@ -764,7 +794,34 @@ __device__ __forceinline__ void aw_store_tile(const uint8_t* tile, __nv_bfloat16
     }
 }
 
-__global__ void __launch_bounds__(128)
+// Softmax of row i of the fp32 score tile for the 8 keys [c0, c0+8) of this thread (4 threads share a row): e[] holds the
+// probabilities, exactly 0 for keys / rows outside the segment.  Branch-free: invalid rows reduce over -inf safely.
+__device__ __forceinline__ void aw_softmax_row(float (&e)[8], const float* S, int i, int c0, int L, float scale) {
+    const float4 s0 = *reinterpret_cast<const float4*>(S + i * AW_SP + c0);
+    const float4 s1 = *reinterpret_cast<const float4*>(S + i * AW_SP + c0 + 4);
+    const float sr[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const bool row_ok = i < L;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        e[t] = (row_ok && c0 + t < L) ? sr[t] * scale : -INFINITY;
+        mx = fmaxf(mx, e[t]);
+    }
+    mx = quad_max(mx);
+    if (!row_ok) mx = 0.f;
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        e[t] = __expf(e[t] - mx);          // exp(-inf) = 0 for the masked keys
+        sum += e[t];
+    }
+    sum = quad_sum(sum);
+    const float inv = row_ok ? 1.f / sum : 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) e[t] *= inv;
+}
+
+__global__ void __launch_bounds__(128, 5)
 attn_win_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
                     const __nv_bfloat16* __restrict__ v, int ldv, const int32_t* __restrict__ seg_off, int n_units,
                     int n_heads, int hd, float scale, __nv_bfloat16* __restrict__ ctx, int ldc, float drop_p,
@@ -779,12 +836,31 @@ attn_win_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
     uint8_t* Tp = reinterpret_cast<uint8_t*>(S + 32 * AW_SP);
     for (int i = threadIdx.x; i < 3 * TILE / 16; i += 128) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    // 16-bit keep threshold; the scale is the reciprocal of the keep probability actually realised
+    const uint32_t thr16 = drop_p > 0.f ? min(65535u, static_cast<uint32_t>(drop_p * 65536.f + 0.5f)) : 0u;
+    const float inv_keep = 65536.f / static_cast<float>(65536u - thr16);
+    int nseg = blockIdx.x / n_heads;
+    int nr0 = blockIdx.x < n_units ? __ldg(seg_off + nseg) : 0, nr1 = blockIdx.x < n_units ? __ldg(seg_off + nseg + 1) : 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        // this unit's segment bounds were fetched one iteration ago; fetch the next unit's now (their latency was
+        // fully exposed at the top of every unit)
         HeadGeom g;
-        int head;
-        if (!head_geom(seg_off, unit, n_heads, hd, g, head)) continue;      // uniform in the CTA
+        const int seg = nseg, head = unit - seg * n_heads;
+        g.row0 = nr0;
+        g.L = nr1 - nr0;
+        {
+            const int nu = unit + gridDim.x;
+            nseg = nu / n_heads;
+            if (nu < n_units) {
+                nr0 = __ldg(seg_off + nseg);
+                nr1 = __ldg(seg_off + nseg + 1);
+            }
+        }
+        if (g.L <= 0) continue;                                             // uniform in the CTA
+        g.col0 = head * hd;
+        g.c_lo = g.col0 >> 3;
+        g.phase = g.col0 & 7;
+        g.nch = ((g.col0 + hd - 1) >> 3) - g.c_lo + 1;
         aw_stage(Qs, q, ldq, g, warp, lane);
         aw_stage(Ks, k, ldk, g, warp, lane);
         aw_stage(Vs, v, ldv, g, warp, lane);
@@ -793,17 +869,24 @@ attn_win_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
         __syncthreads();
         aw_block_product(S, Qs, Ks, (g.nch + 1) >> 1, g.L, rows_alloc, warp, lane);
         __syncthreads();
-        // softmax + dropout, one row per warp pass, lane = key
-        for (int i = warp; i < 32; i += 4) {
-            float pv = 0.f;
-            if (i < g.L) {
-                const float sv = lane < g.L ? S[i * AW_SP + lane] * scale : -INFINITY;
-                const float mx = warp_max(sv);
-                const float ex = __expf(sv - mx);
-                const float inv = 1.f / warp_sum(ex);
-                pv = lane < g.L ? ex * inv * am_drop_factor(thr, inv_keep, seed, g.row0 + i, head, lane) : 0.f;
+        // softmax + dropout: 4 threads per row (8 keys each), all 32 rows in one pass, quad shuffles
+        {
+            const int i = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 8;
+            float e[8];
+            aw_softmax_row(e, S, i, c0, g.L, scale);
+            if (thr16 && i < g.L) {
+#pragma unroll
+                for (int h4 = 0; h4 < 2; ++h4) {
+                    float f[4];
+                    aw_drop4(f, thr16, inv_keep, seed, g.row0 + i, head, c0 + 4 * h4);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) e[4 * h4 + t] *= f[t];
+                }
             }
-            *reinterpret_cast<__nv_bfloat16*>(Tp + i * AW_TP + lane * 2) = __float2bfloat16_rn(pv);
+            uint32_t pk[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) pk[t] = pack_bf16(e[2 * t], e[2 * t + 1]);
+            *reinterpret_cast<uint4*>(Tp + i * AW_TP + c0 * 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
         __syncthreads();
         uint32_t pa[2][2][4];
@@ -815,7 +898,7 @@ attn_win_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 attn_win_bwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
                     const __nv_bfloat16* __restrict__ v, int ldv, const __nv_bfloat16* __restrict__ dctx, int ldc,
                     const int32_t* __restrict__ seg_off, int n_units, int n_heads, int hd, float scale,
@@ -834,12 +917,31 @@ attn_win_bwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
     uint8_t* Tds = Tp + 32 * AW_TP;
     for (int i = threadIdx.x; i < 4 * TILE / 16; i += 128) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
+    // 16-bit keep threshold; the scale is the reciprocal of the keep probability actually realised
+    const uint32_t thr16 = drop_p > 0.f ? min(65535u, static_cast<uint32_t>(drop_p * 65536.f + 0.5f)) : 0u;
+    const float inv_keep = 65536.f / static_cast<float>(65536u - thr16);
+    int nseg = blockIdx.x / n_heads;
+    int nr0 = blockIdx.x < n_units ? __ldg(seg_off + nseg) : 0, nr1 = blockIdx.x < n_units ? __ldg(seg_off + nseg + 1) : 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        // this unit's segment bounds were fetched one iteration ago; fetch the next unit's now (their latency was
+        // fully exposed at the top of every unit)
         HeadGeom g;
-        int head;
-        if (!head_geom(seg_off, unit, n_heads, hd, g, head)) continue;
+        const int seg = nseg, head = unit - seg * n_heads;
+        g.row0 = nr0;
+        g.L = nr1 - nr0;
+        {
+            const int nu = unit + gridDim.x;
+            nseg = nu / n_heads;
+            if (nu < n_units) {
+                nr0 = __ldg(seg_off + nseg);
+                nr1 = __ldg(seg_off + nseg + 1);
+            }
+        }
+        if (g.L <= 0) continue;                                             // uniform in the CTA
+        g.col0 = head * hd;
+        g.c_lo = g.col0 >> 3;
+        g.phase = g.col0 & 7;
+        g.nch = ((g.col0 + hd - 1) >> 3) - g.c_lo + 1;
         aw_stage(Qs, q, ldq, g, warp, lane);
         aw_stage(Ks, k, ldk, g, warp, lane);
         aw_stage(Vs, v, ldv, g, warp, lane);
@@ -852,24 +954,43 @@ attn_win_bwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
         aw_block_product(S, Qs, Ks, ksteps, g.L, rows_alloc, warp, lane);       // S  = Q K^T
         aw_block_product(D, Os, Vs, ksteps, g.L, rows_alloc, warp, lane);       // dP = dO V^T
         __syncthreads();
-        // P, dropout, dS = P o (f dP - rowsum(P o f dP)): one row per warp pass, lane = key
-        for (int i = warp; i < 32; i += 4) {
-            float pt = 0.f, ds = 0.f;
-            if (i < g.L) {
-                const bool ok = lane < g.L;
-                const float sv = ok ? S[i * AW_SP + lane] * scale : -INFINITY;
-                const float mx = warp_max(sv);
-                const float ex = __expf(sv - mx);
-                const float inv = 1.f / warp_sum(ex);
-                const float f = ok ? am_drop_factor(thr, inv_keep, seed, g.row0 + i, head, lane) : 0.f;
-                const float pe = ok ? ex * inv : 0.f;
-                const float dpe = ok ? D[i * AW_SP + lane] * f : 0.f;
-                const float delta = warp_sum(pe * dpe);
-                pt = pe * f;
-                ds = pe * (dpe - delta);
+        // P, dropout, dS = P o (f dP - rowsum(P o f dP)): 4 threads per row (8 keys each), all rows in one pass
+        {
+            const int i = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 8;
+            float e[8], dpe[8];
+            aw_softmax_row(e, S, i, c0, g.L, scale);
+            const float4 d0 = *reinterpret_cast<const float4*>(D + i * AW_SP + c0);
+            const float4 d1 = *reinterpret_cast<const float4*>(D + i * AW_SP + c0 + 4);
+            const float dr[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            float delta = 0.f;
+            uint32_t pk[4], dk_[4];
+            float pt[8], fk[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) fk[t] = 1.f;
+            if (thr16 && i < g.L) {
+                float f[4];
+                aw_drop4(f, thr16, inv_keep, seed, g.row0 + i, head, c0);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) fk[t] = f[t];
+                aw_drop4(f, thr16, inv_keep, seed, g.row0 + i, head, c0 + 4);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) fk[4 + t] = f[t];
             }
-            *reinterpret_cast<__nv_bfloat16*>(Tp + i * AW_TP + lane * 2) = __float2bfloat16_rn(pt);
-            *reinterpret_cast<__nv_bfloat16*>(Tds + i * AW_TP + lane * 2) = __float2bfloat16_rn(ds);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const bool ok = i < g.L && c0 + t < g.L;
+                dpe[t] = ok ? dr[t] * fk[t] : 0.f;      // e[t] is already 0 outside the segment
+                pt[t] = e[t] * fk[t];
+                delta += e[t] * dpe[t];
+            }
+            delta = quad_sum(delta);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                pk[t] = pack_bf16(pt[2 * t], pt[2 * t + 1]);
+                dk_[t] = pack_bf16(e[2 * t] * (dpe[2 * t] - delta), e[2 * t + 1] * (dpe[2 * t + 1] - delta));
+            }
+            *reinterpret_cast<uint4*>(Tp + i * AW_TP + c0 * 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(Tds + i * AW_TP + c0 * 2) = make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]);
         }
         __syncthreads();
         const int ngroups = (g.nch + 3) >> 2;

@@ -61,6 +61,12 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // Counter-based 32-bit hash (splitmix64 finaliser) used for dropout masks: the same (seed, index)
 // gives the same bit in forward and backward, so masks are never stored.
+__host__ __device__ __forceinline__ unsigned long long hash_u64(unsigned long long seed, unsigned long long idx) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
 __host__ __device__ __forceinline__ uint32_t hash_u32(unsigned long long seed, unsigned long long idx) {
     unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1ull);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
