@@ -1,6 +1,7 @@
 // Variable-length multi-head attention over SHORT segments (one frame's pairs / one 2-frame window,
 // <= 32 tokens) with head_dim <= 248 — nn.MultiheadAttention of tools/utils/transformer.py:23,50 on
-// exactly the rows the reference keeps.  One WARP owns one (segment, head) unit:
+// exactly the rows the reference keeps.  Segments of <= 16 tokens: one WARP owns one (segment, head) unit; 17..32 tokens:
+// one 4-warp CTA per unit (the QUAD kernels at the end of this file).  In both:
 //   * Q/K/V (and dO) head slices are staged with 16-byte cp.async of the ALIGNED chunks that cover
 //     the head's columns (head_dim 242 puts head h at a 4-byte-aligned offset h*484 B; the chunk
 //     grid is kept, the few foreign columns at either end are zeroed in the contraction operands
@@ -392,229 +393,10 @@ attn_mma_bwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
 
 
 // ------------------------------------------------------------------------------------------------
-// Warp-PAIR variants for 17..32-token segments (the 2-frame temporal windows).  With one warp per unit the three /
-// four 17 KB operand tiles allow only 4 (forward) / 3 (backward) warps per SM: ncu showed 6 % / 4.7 % active warps,
-// 9 % tensor pipe, 16 % / 11.5 % of DRAM bandwidth — latency-bound with nothing to hide it.  Here two warps share
-// one unit's tiles and split the HEAD DIMENSION: each contracts half of the d-chunks for S = Q K^T (and dP = dO V^T),
-// the partial scores are exchanged through shared memory (C-fragment layout, identical in both warps), softmax is
-// done redundantly, and each warp then produces half of the output columns of P V (dQ, dK, dV).  Every product is
-// split evenly and 6 / 4 warps fit per SM.  Measured (31.8 k window tokens, dropout 0.1, tools/attn_bench.py): forward
-// 0.353 -> 0.293 ms, backward 0.870 -> 0.734 ms together with the add-only cp.async addressing of stage_tile.  The unit
-// time is still dominated by staging (issue + exposed latency, nothing prefetched) and the 4-byte output stores,
-// not by the MMAs; the next step is TMA slab staging with a prefetched second buffer.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
-
-template <int MT, int NT>
-__device__ __forceinline__ void pair_exchange_add(float (&s)[MT][NT][4], float* X, int pw, int lane, int pair) {
-    float* mine = X + pw * (MT * NT * 4 * 32);
-    const float* other = X + (pw ^ 1) * (MT * NT * 4 * 32);
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) mine[((mt * NT + nt) * 4 + e) * 32 + lane] = s[mt][nt][e];
-    pair_sync(pair);
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) s[mt][nt][e] += other[((mt * NT + nt) * 4 + e) * 32 + lane];
-}
-
-constexpr int AM_PAIR_LP = 32;
-constexpr int AM_PAIR_X = 2 * (AM_PAIR_LP / 16) * (AM_PAIR_LP / 8) * 4 * 32 * 4;   // bytes: two warps' partial scores
-
-__global__ void __launch_bounds__(192)
-attn_mma_fwd2_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
-                     const __nv_bfloat16* __restrict__ v, int ldv, const int32_t* __restrict__ seg_off, int n_units,
-                     int n_heads, int hd, float scale, __nv_bfloat16* __restrict__ ctx, int ldc, float drop_p,
-                     unsigned long long seed) {
-    constexpr int LP = AM_PAIR_LP, MT = LP / 16, NT = LP / 8, KK = LP / 16;
-    constexpr int TILE = LP * AM_PITCH_B;
-    constexpr int PER_PAIR = 3 * TILE + AM_PAIR_X;
-    extern __shared__ __align__(16) uint8_t am_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = warp >> 1, pw = warp & 1, pairs = blockDim.x >> 6, l2 = pw * 32 + lane;
-    uint8_t* Qs = am_smem + pair * PER_PAIR;
-    uint8_t* Ks = Qs + TILE;
-    uint8_t* Vs = Ks + TILE;
-    float* X = reinterpret_cast<float*>(Vs + TILE);
-    for (int i = l2; i < 3 * TILE / 16; i += 64) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0u, 0u, 0u, 0u);
-    pair_sync(pair);
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
-    const int gq = lane >> 2, tq = lane & 3;
-    for (int unit = blockIdx.x * pairs + pair; unit < n_units; unit += gridDim.x * pairs) {
-        HeadGeom g;
-        int head;
-        if (!head_geom(seg_off, unit, n_heads, hd, g, head)) continue;      // uniform within the pair
-        stage_tile(Qs, q, ldq, g, l2, 64);
-        stage_tile(Ks, k, ldk, g, l2, 64);
-        stage_tile(Vs, v, ldv, g, l2, 64);
-        cp_async_wait_all();
-        pair_sync(pair);
-        if (pw == 0) zero_slop(Qs, g, hd, lane);
-        pair_sync(pair);
-        float s[MT][NT][4];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
-        const int ksteps = (g.nch + 1) >> 1, kh = ksteps >> 1;
-        qk_product<MT, NT>(s, Qs, Ks, pw ? ksteps : kh, lane, pw ? kh : 0);
-        pair_exchange_add<MT, NT>(s, X, pw, lane, pair);
-        softmax_rows<MT, NT>(s, scale, g.L, lane);
-        uint32_t pa[MT][KK][4];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int kk = 0; kk < KK; ++kk) {
-#pragma unroll
-                for (int sub = 0; sub < 2; ++sub) {
-                    const int nt = 2 * kk + sub;
-                    float p[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int row = mt * 16 + gq + (e >> 1) * 8, col = nt * 8 + tq * 2 + (e & 1);
-                        p[e] = (row < g.L && col < g.L)
-                                   ? s[mt][nt][e] * am_drop_factor(thr, inv_keep, seed, g.row0 + row, head, col) : 0.f;
-                    }
-                    pa[mt][kk][sub * 2] = pack_bf16(p[0], p[1]);
-                    pa[mt][kk][sub * 2 + 1] = pack_bf16(p[2], p[3]);
-                }
-            }
-        const int ngroups = (g.nch + 3) >> 2, gh = (ngroups + 1) >> 1;
-        av_product_store<MT, KK>(pa, Vs, g, hd, 1.f, ctx, ldc, lane, pw ? gh : 0, pw ? ngroups : gh);
-        pair_sync(pair);          // tiles and the exchange buffer are reused by the next unit
-    }
-}
-
-__global__ void __launch_bounds__(128)
-attn_mma_bwd2_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
-                     const __nv_bfloat16* __restrict__ v, int ldv, const __nv_bfloat16* __restrict__ dctx, int ldc,
-                     const int32_t* __restrict__ seg_off, int n_units, int n_heads, int hd, float scale,
-                     __nv_bfloat16* __restrict__ dq, int lddq, __nv_bfloat16* __restrict__ dk, int lddk,
-                     __nv_bfloat16* __restrict__ dv, int lddv, float drop_p, unsigned long long seed) {
-    constexpr int LP = AM_PAIR_LP, MT = LP / 16, NT = LP / 8, KK = LP / 16;
-    constexpr int TILE = LP * AM_PITCH_B;
-    constexpr int TP = (LP + 8) * 2;
-    constexpr int SMALL = LP * TP;
-    constexpr int PER_PAIR = 4 * TILE + 2 * SMALL + 2 * AM_PAIR_X;
-    extern __shared__ __align__(16) uint8_t am_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = warp >> 1, pw = warp & 1, pairs = blockDim.x >> 6, l2 = pw * 32 + lane;
-    uint8_t* Qs = am_smem + pair * PER_PAIR;
-    uint8_t* Ks = Qs + TILE;
-    uint8_t* Vs = Ks + TILE;
-    uint8_t* Os = Vs + TILE;
-    uint8_t* Tds = Os + TILE;
-    uint8_t* Tp = Tds + SMALL;
-    float* Xp = reinterpret_cast<float*>(Tp + SMALL);
-    float* Xd = Xp + AM_PAIR_X / 4;
-    for (int i = l2; i < (4 * TILE + 2 * SMALL) / 16; i += 64) reinterpret_cast<uint4*>(Qs)[i] = make_uint4(0u, 0u, 0u, 0u);
-    pair_sync(pair);
-    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-    const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
-    const int gq = lane >> 2, tq = lane & 3;
-    for (int unit = blockIdx.x * pairs + pair; unit < n_units; unit += gridDim.x * pairs) {
-        HeadGeom g;
-        int head;
-        if (!head_geom(seg_off, unit, n_heads, hd, g, head)) continue;
-        stage_tile(Qs, q, ldq, g, l2, 64);
-        stage_tile(Ks, k, ldk, g, l2, 64);
-        stage_tile(Vs, v, ldv, g, l2, 64);
-        stage_tile(Os, dctx, ldc, g, l2, 64);
-        cp_async_wait_all();
-        pair_sync(pair);
-        if (pw == 0) zero_slop(Qs, g, hd, lane); else zero_slop(Os, g, hd, lane);
-        pair_sync(pair);
-        const int ksteps = (g.nch + 1) >> 1, kh = ksteps >> 1;
-        float p[MT][NT][4], dp[MT][NT][4];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { p[mt][nt][e] = 0.f; dp[mt][nt][e] = 0.f; }
-        qk_product<MT, NT>(p, Qs, Ks, pw ? ksteps : kh, lane, pw ? kh : 0);
-        qk_product<MT, NT>(dp, Os, Vs, pw ? ksteps : kh, lane, pw ? kh : 0);
-        pair_exchange_add<MT, NT>(p, Xp, pw, lane, pair);
-        pair_exchange_add<MT, NT>(dp, Xd, pw, lane, pair);
-        softmax_rows<MT, NT>(p, scale, g.L, lane);
-        // identical in both warps from here to the products: both write the same values into the small tiles
-        uint32_t dsa[MT][KK][4];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            float delta[2] = {0.f, 0.f};
-            const int r0 = mt * 16 + gq;
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                float pt[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int row = r0 + (e >> 1) * 8, col = nt * 8 + tq * 2 + (e & 1);
-                    const bool ok = row < g.L && col < g.L;
-                    const float f = ok ? am_drop_factor(thr, inv_keep, seed, g.row0 + row, head, col) : 0.f;
-                    const float pe = ok ? p[mt][nt][e] : 0.f;
-                    const float dpe = ok ? dp[mt][nt][e] * f : 0.f;
-                    delta[e >> 1] += pe * dpe;
-                    p[mt][nt][e] = pe;
-                    dp[mt][nt][e] = dpe;
-                    pt[e] = pe * f;
-                }
-                const int c = nt * 8 + tq * 2;
-                if (pw == 0) {
-                    *reinterpret_cast<uint32_t*>(Tp + r0 * TP + c * 2) = pack_bf16(pt[0], pt[1]);
-                    *reinterpret_cast<uint32_t*>(Tp + (r0 + 8) * TP + c * 2) = pack_bf16(pt[2], pt[3]);
-                }
-            }
-            delta[0] = quad_sum(delta[0]);
-            delta[1] = quad_sum(delta[1]);
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                float ds[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) ds[e] = p[mt][nt][e] * (dp[mt][nt][e] - delta[e >> 1]);
-                const uint32_t d01 = pack_bf16(ds[0], ds[1]), d23 = pack_bf16(ds[2], ds[3]);
-                dsa[mt][nt >> 1][(nt & 1) * 2] = d01;
-                dsa[mt][nt >> 1][(nt & 1) * 2 + 1] = d23;
-                const int c = nt * 8 + tq * 2;
-                if (pw == 1) {
-                    *reinterpret_cast<uint32_t*>(Tds + r0 * TP + c * 2) = d01;
-                    *reinterpret_cast<uint32_t*>(Tds + (r0 + 8) * TP + c * 2) = d23;
-                }
-            }
-        }
-        pair_sync(pair);
-        const int ngroups = (g.nch + 3) >> 2, gh = (ngroups + 1) >> 1;
-        const int dg0 = pw ? gh : 0, dg1 = pw ? ngroups : gh;
-        av_product_store<MT, KK>(dsa, Ks, g, hd, scale, dq, lddq, lane, dg0, dg1);          // dQ = scale * dS K
-        uint32_t ta[MT][KK][4];
-        const uint32_t t_off = ((lane & 7) + ((lane >> 4) & 1) * 8) * TP + ((lane >> 3) & 1) * 16;
-#pragma unroll
-        for (int jt = 0; jt < MT; ++jt)
-#pragma unroll
-            for (int it = 0; it < KK; ++it) ldsm_x4_t(ta[jt][it], s_u32(Tds) + t_off + it * 16 * TP + jt * 32);
-        av_product_store<MT, KK>(ta, Qs, g, hd, scale, dk, lddk, lane, dg0, dg1);           // dK = scale * dS^T Q
-#pragma unroll
-        for (int jt = 0; jt < MT; ++jt)
-#pragma unroll
-            for (int it = 0; it < KK; ++it) ldsm_x4_t(ta[jt][it], s_u32(Tp) + t_off + it * 16 * TP + jt * 32);
-        av_product_store<MT, KK>(ta, Os, g, hd, 1.f, dv, lddv, lane, dg0, dg1);             // dV = P~^T dO
-        pair_sync(pair);
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------------
 // QUAD kernels for 17..32-token segments (the 2-frame temporal windows): one 128-thread CTA per (segment, head) unit,
-// several CTAs per SM.  The warp-pair kernels above ran 4..6 warps per SM and spent ~14 us per unit on a chain of
-// dependent steps executed by two warps (ncu: 5 % active warps, 10 % of DRAM bandwidth).  Here
+// several CTAs per SM.  Their predecessors (one warp, then a warp pair per unit with 32-row tiles) ran 4..6 warps per SM
+// and spent ~14 us per unit on a chain of dependent steps (ncu: 5 % active warps, 10 % of DRAM bandwidth; 0.29 / 0.73 ms
+// per layer forward / backward at the headline shape).  Here (0.12 / 0.27 ms, profiles/r02_ncu_window_attention_*.txt)
 //   * operand tiles have only as many rows as the longest segment of the launch (rounded to 8; ldmatrix row
 //     addresses are clamped), so 3 (backward) / 5 (forward) CTAs = 12 / 20 warps fit per SM;
 //   * S = Q K^T (and dP = dO V^T) are split by OUTPUT block: warp w owns the 16x16 block (w>>1, w&1) over the whole
@@ -629,13 +411,8 @@ attn_mma_bwd2_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
 constexpr int AW_SP = 36;   // pitch (floats) of the fp32 score tiles
 constexpr int AW_TP = 80;   // pitch (bytes) of the bf16 [32][32] probability tiles: 5 chunks (odd) -> conflict-free ldmatrix
 
-__device__ __forceinline__ void cp_async16_pred(uint32_t dst, const void* src, bool p) {
-    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.cg.shared.global [%0], [%1], 16;\n}\n"
-                 ::"r"(dst), "l"(src), "r"(static_cast<int>(p)));
-}
-__device__ __forceinline__ void st_shared_pred(uint32_t dst, uint32_t v, bool p) {
-    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p st.shared.b32 [%0], %1;\n}\n" ::"r"(dst), "r"(v),
-                 "r"(static_cast<int>(p)) : "memory");
+__device__ __forceinline__ void st_shared_u32(uint32_t dst, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(v) : "memory");
 }
 // Stage one operand tile (lane = chunk, warps stride over the rows: at most 8 rows per warp).  One 64-bit address per
 // operand, then a running pointer and predicated copies: no branches, no per-row multiplications.
@@ -646,7 +423,7 @@ __device__ __forceinline__ void aw_stage(uint8_t* tile, const __nv_bfloat16* src
     const int n = lane < g.nch ? g.L - warp : 0;                 // row warp + 4t is staged  <=>  4t < n
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-        cp_async16_pred(dp + t * 4 * AM_PITCH_B, sp, 4 * t < n);
+        if (4 * t < n) cp_async16(dp + t * 4 * AM_PITCH_B, sp);
         sp += step;
     }
 }
@@ -727,9 +504,9 @@ __device__ __forceinline__ void aw_load_a(uint32_t (&a)[2][2][4], const uint8_t*
             for (int kk = 0; kk < 2; ++kk) ldsm_x4_t(a[mt][kk], base + kk * 16 * AW_TP + mt * 32);
     }
 }
-// out[:, columns of group dg] = scale * A . Bt for this warp's column groups, written over Bt's own columns.
+// out[:, columns of group dg] = A . Bt for this warp's column groups, written over Bt's own columns.
 __device__ __forceinline__ void aw_out_product_inplace(const uint32_t (&a)[2][2][4], uint8_t* Bt, int ngroups, int L, int rows_alloc,
-                                                       float out_scale, int warp, int lane) {
+                                                       int warp, int lane) {
     const int gq = lane >> 2, tq = lane & 3;
     const int k0 = min(lane & 15, rows_alloc - 1), k1 = min(16 + (lane & 15), rows_alloc - 1);
     const uint32_t b0 = s_u32(Bt) + k0 * AM_PITCH_B + (lane >> 4) * 16;
@@ -764,11 +541,11 @@ __device__ __forceinline__ void aw_out_product_inplace(const uint32_t (&a)[2][2]
         const uint32_t d = d0 + dg * 64;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            st_shared_pred(d + j * 16, pack_bf16(o[0][j][0] * out_scale, o[0][j][1] * out_scale), v0);
-            st_shared_pred(d + j * 16 + 8 * AM_PITCH_B, pack_bf16(o[0][j][2] * out_scale, o[0][j][3] * out_scale), v1);
+            if (v0) st_shared_u32(d + j * 16, pack_bf16(o[0][j][0], o[0][j][1]));
+            if (v1) st_shared_u32(d + j * 16 + 8 * AM_PITCH_B, pack_bf16(o[0][j][2], o[0][j][3]));
             if (two_m) {
-                st_shared_pred(d + j * 16 + 16 * AM_PITCH_B, pack_bf16(o[1][j][0] * out_scale, o[1][j][1] * out_scale), v2);
-                st_shared_pred(d + j * 16 + 24 * AM_PITCH_B, pack_bf16(o[1][j][2] * out_scale, o[1][j][3] * out_scale), v3);
+                if (v2) st_shared_u32(d + j * 16 + 16 * AM_PITCH_B, pack_bf16(o[1][j][0], o[1][j][1]));
+                if (v3) st_shared_u32(d + j * 16 + 24 * AM_PITCH_B, pack_bf16(o[1][j][2], o[1][j][3]));
             }
         }
     }
@@ -891,7 +668,7 @@ attn_win_fwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
         __syncthreads();
         uint32_t pa[2][2][4];
         aw_load_a(pa, Tp, false, lane);
-        aw_out_product_inplace(pa, Vs, (g.nch + 3) >> 2, g.L, rows_alloc, 1.f, warp, lane);
+        aw_out_product_inplace(pa, Vs, (g.nch + 3) >> 2, g.L, rows_alloc, warp, lane);
         __syncthreads();
         aw_store_tile(Vs, ctx, ldc, g, hd, vec != 0, warp, lane);
         __syncthreads();
@@ -987,7 +764,8 @@ attn_win_bwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 pk[t] = pack_bf16(pt[2 * t], pt[2 * t + 1]);
-                dk_[t] = pack_bf16(e[2 * t] * (dpe[2 * t] - delta), e[2 * t + 1] * (dpe[2 * t + 1] - delta));
+                // the softmax scale of dQ / dK is folded into dS here
+                dk_[t] = pack_bf16(e[2 * t] * scale * (dpe[2 * t] - delta), e[2 * t + 1] * scale * (dpe[2 * t + 1] - delta));
             }
             *reinterpret_cast<uint4*>(Tp + i * AW_TP + c0 * 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(Tds + i * AW_TP + c0 * 2) = make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]);
@@ -996,11 +774,11 @@ attn_win_bwd_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfl
         const int ngroups = (g.nch + 3) >> 2;
         uint32_t a[2][2][4];
         aw_load_a(a, Tds, false, lane);
-        aw_out_product_inplace(a, Ks, ngroups, g.L, rows_alloc, scale, warp, lane);      // dQ = scale dS K     (over K)
+        aw_out_product_inplace(a, Ks, ngroups, g.L, rows_alloc, warp, lane);      // dQ = (scale dS) K     (over K)
         aw_load_a(a, Tds, true, lane);
-        aw_out_product_inplace(a, Qs, ngroups, g.L, rows_alloc, scale, warp, lane);      // dK = scale dS^T Q   (over Q)
+        aw_out_product_inplace(a, Qs, ngroups, g.L, rows_alloc, warp, lane);      // dK = (scale dS)^T Q   (over Q)
         aw_load_a(a, Tp, true, lane);
-        aw_out_product_inplace(a, Os, ngroups, g.L, rows_alloc, 1.f, warp, lane);        // dV = P~^T dO        (over dO)
+        aw_out_product_inplace(a, Os, ngroups, g.L, rows_alloc, warp, lane);      // dV = P~^T dO          (over dO)
         __syncthreads();
         aw_store_tile(Ks, dq, lddq, g, hd, vec != 0, warp, lane);
         aw_store_tile(Qs, dk, lddk, g, hd, vec != 0, warp, lane);

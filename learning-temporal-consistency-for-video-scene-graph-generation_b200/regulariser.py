@@ -219,4 +219,9 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
     pv = up_(np.concatenate(pv).astype(np.int32))
     s = ops.consistency_kl(sym.contiguous(), pu, pv)
     m = ops.consistency_kl(sem.contiguous(), pu, pv)
+    # the reference keeps a pair only if its score is >= 0 (lib/teatgt.py:327-333): a data-dependent length, hence a host
+    # synchronisation — ONE flag for both branches; the usual case (no negative rounding residue) returns the kernels'
+    # outputs as they are, without any gather
+    if bool((torch.cat([s, m]) >= 0).all()):          # (NaN >= 0 is False: dropped like in the reference)
+        return s, m
     return s[s >= 0], m[m >= 0]

@@ -500,8 +500,6 @@ class TEMPURA(nn.Module):
         entry["rel_features"] = rel_features
         entry["rel_mem_features"] = mem_features
 
-        if cons_prep is not None:
-            self._consistency(entry, plan, mixed.detach(), cons_prep)
         heads = [self.a_rel_compress, self.s_rel_compress, self.c_rel_compress]
         mode = 2 if unc else (1 if phase == "train" else 0)
         eps = self.gmm_eps or {}
@@ -513,6 +511,10 @@ class TEMPURA(nn.Module):
         else:
             (entry["attention_al_uc"], entry["spatial_al_uc"], entry["contacting_al_uc"],
              entry["attention_ep_uc"], entry["spatial_ep_uc"], entry["contacting_ep_uc"]) = res
+        if cons_prep is not None:
+            # LAST: the regulariser ends with a data-dependent filter (KL >= 0, lib/teatgt.py:327-333) that synchronises
+            # the host; everything else of the forward is already queued behind it on the device by then
+            self._consistency(entry, plan, mixed.detach(), cons_prep)
         return entry
 
 
