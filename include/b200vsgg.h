@@ -381,6 +381,26 @@ int b200vsgg_graph_small_fwd(const float* nodes, const uint8_t* upper, const int
  * input prefetch. h_pinned_src must stay untouched until the kernel has run. */
 int b200vsgg_upload(const void* h_pinned_src, void* dst, int64_t bytes, void* stream);
 
+/* Recall@K matching of one video (tools/utils/evaluation_recall.py:119-276: evaluate_from_dict,
+ * evaluate_recall, _triplet, _compute_pred_matches), one CTA per frame.
+ *   pair_idx int64 [N,2] box rows, frame_off int32 [F+1] pair offsets of the frames, att/spa/con fp32 distributions
+ *   [N,na]/[N,ns]/[N,nc], pred_boxes fp32 rows of 4 coordinates with row pitch box_ld floats, pred_classes int64 [O],
+ *   obj_scores fp32 [O]; ground truth concatenated over frames: gt_boxes fp64 [B,4], gt_classes int32 [B],
+ *   gt_box_off int32 [F+1], gt_rels int32 [G,3] = (subject, object: frame-local box index; predicate id),
+ *   gt_rel_off int32 [F+1].
+ * mode 0 = "with" constraint (argmax predicate per relation row), 1 = "no" constraint (top-100 of score x object scores),
+ * 2 = "semi" (attention rows: argmax; other rows: every predicate above semi_thr).  Scores are float64 built with the
+ * reference's dtypes; ties: position-descending (a stable ascending argsort reversed).
+ * hits uint8 [G,4]: ground-truth relation matched within the first 10 / 20 / 50 / 100 candidates (class triplet equal,
+ * both IoUs >= iou_thr, +1 pixel convention).  *status is set to 1 if a frame exceeds the on-chip tables (> 42 pairs):
+ * its hits are 0 and the caller evaluates that frame on the host. */
+int b200vsgg_eval_recall(const int64_t* pair_idx, const int32_t* frame_off, int32_t n_frames, const float* att, int32_t na,
+                         const float* spa, int32_t ns, const float* con, int32_t nc, const float* pred_boxes, int32_t box_ld,
+                         const int64_t* pred_classes, const float* obj_scores, const double* gt_boxes,
+                         const int32_t* gt_classes, const int32_t* gt_box_off, const int32_t* gt_rels,
+                         const int32_t* gt_rel_off, int32_t mode, double semi_thr, double iou_thr, uint8_t* hits,
+                         int32_t* status, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused multi-tensor optimiser step: tools/utils/AdamW.py:53-113 (weight decay before the moment update) with
  * torch.nn.utils.clip_grad_norm_ (TEMPURA_train.py:224) folded in.  `tensors` is a DEVICE array; the work is

@@ -11,8 +11,13 @@ The ORDER of the candidate triplets is produced by the same numpy calls on array
 reference builds them (float32 scores concatenated with float64 zero blocks), so ties resolve identically and the
 results are bit-identical (tests/test_evaluator.py, golden values from the unmodified reference).
 
-Not a CUDA kernel: after the single transfer the work is a few kB of integer/float data per frame — the measured
-cost is the per-frame synchronisation and Python overhead this removes.  `bbox_overlaps`
+Two backends, identical results (tests/test_evaluator.py on the host, tests/test_evaluator_gpu.py on a B200):
+`backend="host"` (default) — after the single transfer the frames are numpy array expressions; `backend="cuda"` — the
+candidate ranking and the ground-truth matching of ALL frames of the video run in one launch of
+`b200vsgg_eval_recall` (csrc/evaluator.cu, one CTA per frame, float64 scores with the reference's dtypes) and only the
+[ground-truth relation x 4] hit flags come back.  Frames whose outcome depends on numpy's ordering of exactly tied
+scores (the no-constraint mode with fewer than four pairs: zero-score entries enter its top-100 list) and frames beyond
+the kernel's on-chip tables take the host path.  `bbox_overlaps`
 (tools/utils/fpn/box_intersections_cpu, a Cython file absent from the reference tree) is restated with the
 Fast-R-CNN definition (+1 pixel convention).
 """
@@ -35,7 +40,11 @@ def bbox_overlaps(boxes, query_boxes):
 
 class BasicSceneGraphEvaluator:
     def __init__(self, mode, AG_object_classes, AG_all_predicates, AG_attention_predicates, AG_spatial_predicates,
-                 AG_contacting_predicates, iou_threshold=0.5, constraint=False, semithreshold=None, output_dir="output/"):
+                 AG_contacting_predicates, iou_threshold=0.5, constraint=False, semithreshold=None, output_dir="output/",
+                 backend="host"):
+        if backend not in ("host", "cuda"):
+            raise ValueError("backend must be 'host' or 'cuda'")
+        self.backend = backend
         self.AG_object_classes = AG_object_classes
         self.AG_all_predicates = AG_all_predicates
         self.AG_attention_predicates = AG_attention_predicates
@@ -102,6 +111,8 @@ class BasicSceneGraphEvaluator:
         return gt_boxes, gt_classes, np.array(rels)
 
     def evaluate_scene_graph(self, gt, pred):
+        if self.backend == "cuda":
+            return self._evaluate_scene_graph_cuda(gt, pred)
         mode = self.mode
         host = lambda t: t.detach().cpu().numpy()
         pair_idx, im_idx = host(pred["pair_idx"]), host(pred["im_idx"])
@@ -186,6 +197,13 @@ class BasicSceneGraphEvaluator:
             ok = same & (bbox_overlaps(gt_tb[:, :4], p_tb[:, :4]) >= self.iou_threshold) \
                       & (bbox_overlaps(gt_tb[:, 4:], p_tb[:, 4:]) >= self.iou_threshold)
             hit_at = {k: ok[:, :k].any(1) for k in ks}
+        self._record(gt_rels, hit_at)
+
+    def _record(self, gt_rels, hit_at):
+        """Per-frame bookkeeping (evaluation_recall.py:236-262) from the hit flags of the frame's ground-truth relations."""
+        mode = self.mode
+        ks = list(self.result_dict[mode + "_recall"].keys())
+        num_gt = gt_rels.shape[0]
         labels = gt_rels[:, 2].astype(np.int64)
         count = np.bincount(labels, minlength=self.tot_all_predicates)
         rd = self.result_dict
@@ -200,3 +218,74 @@ class BasicSceneGraphEvaluator:
                 cd[k] = [0] * self.tot_all_predicates
             cd[k] = [int(a + b) for a, b in zip(cd[k], count)]
             rd[mode + "_recall"][k].append(float(hits.sum()) / float(num_gt))
+
+    # --------------------------------------------------------------------------------------------
+    def _evaluate_scene_graph_cuda(self, gt, pred):
+        """One launch + one read-back per video (see the module docstring)."""
+        from . import ops
+        mode, method = self.mode, self.constraint
+        dev = pred["pair_idx"].device
+        if dev.type != "cuda":
+            raise RuntimeError("backend='cuda' needs the prediction tensors on a CUDA device")
+        F_ = len(gt)
+        frames = [self._gt_frame(fg) for fg in gt]
+        for _, _, rels in frames:
+            assert rels.shape[0] != 0
+        box_off = np.concatenate([[0], np.cumsum([b.shape[0] for b, _, _ in frames])]).astype(np.int32)
+        rel_off = np.concatenate([[0], np.cumsum([r.shape[0] for _, _, r in frames])]).astype(np.int32)
+        gt_boxes = np.concatenate([b for b, _, _ in frames]).astype(np.float64)
+        gt_classes = np.concatenate([c for _, c, _ in frames]).astype(np.int32)
+        gt_rels = np.concatenate([r for _, _, r in frames]).astype(np.int32)
+        if mode == "predcls":
+            classes, scores = pred["labels"], pred["scores"]
+        else:
+            classes, scores = pred["pred_labels"], pred["pred_scores"]
+        frame_off = ops.frame_offsets(pred["im_idx"].contiguous(), F_)
+        kmode = {"no": 1, "semi": 2}.get(method, 0)
+        hits, status = ops.eval_recall(
+            pred["pair_idx"], frame_off, F_, pred["attention_distribution"], pred["spatial_distribution"],
+            pred["contacting_distribution"], pred["boxes"], classes, scores, ops.upload(gt_boxes.reshape(-1), dev),
+            ops.upload(gt_classes, dev), ops.upload(box_off, dev), ops.upload(gt_rels.reshape(-1), dev),
+            ops.upload(rel_off, dev), kmode, float(self.semithreshold if self.semithreshold is not None else 0.0),
+            float(self.iou_threshold))
+        packed = torch.cat([hits.reshape(-1), status.view(torch.uint8), frame_off.view(torch.uint8)]).cpu().numpy()   # ONE read-back
+        G = int(rel_off[-1])
+        hits_h = packed[:4 * G].reshape(G, 4).astype(bool)
+        too_big = bool(packed[4 * G:4 * G + 4].view(np.int32)[0])
+        counts = np.diff(packed[4 * G + 4:].view(np.int32))
+        n_pred = pred["attention_distribution"].shape[1] + pred["spatial_distribution"].shape[1] + \
+            pred["contacting_distribution"].shape[1]
+        host_frames = [i for i in range(F_) if (method == "no" and counts[i] * n_pred < 100) or (too_big and counts[i] > 42)]
+        host_pred = None
+        if host_frames or (method == "no" and mode != "predcls"):
+            host = lambda t: t.detach().cpu().numpy()
+            host_pred = dict(pair_idx=host(pred["pair_idx"]), im_idx=host(pred["im_idx"]),
+                             att=host(pred["attention_distribution"]), spa=host(pred["spatial_distribution"]),
+                             con=host(pred["contacting_distribution"]), boxes=host(pred["boxes"][:, 1:]).astype(float),
+                             classes=host(classes), scores=host(scores))
+        counter = 0
+        ks = list(self.result_dict[mode + "_recall"].keys())
+        for idx, (gt_b, gt_c, gt_r) in enumerate(frames):
+            if method == "no" and mode != "predcls":
+                n_box = len(gt[idx])
+                self.gt_obj_list.append({"boxes": torch.tensor(gt_b), "labels": torch.tensor(gt_c)})
+                self.pred_obj_list.append({
+                    "boxes": pred["boxes"][counter:counter + n_box, 1:].cpu().clone(),
+                    "scores": pred["pred_scores"][counter:counter + n_box].cpu().clone(),
+                    "labels": pred["pred_labels"][counter:counter + n_box].cpu().clone()})
+                counter += n_box
+            if idx in host_frames:
+                hp = host_pred
+                sel = hp["im_idx"] == idx
+                p = hp["pair_idx"][sel]
+                n = p.shape[0]
+                na, ns, nc = hp["att"].shape[1], hp["spa"].shape[1], hp["con"].shape[1]
+                rels_i = np.concatenate((p, p[:, ::-1], p), axis=0)
+                rel_scores = np.concatenate((
+                    np.concatenate((hp["att"][sel], np.zeros([n, ns]), np.zeros([n, nc])), axis=1),
+                    np.concatenate((np.zeros([n, na]), hp["spa"][sel], np.zeros([n, nc])), axis=1),
+                    np.concatenate((np.zeros([n, na]), np.zeros([n, ns]), hp["con"][sel]), axis=1)), axis=0)
+                self._evaluate_frame(gt_r, gt_b.astype(float), gt_c, rels_i, rel_scores, hp["boxes"], hp["classes"], hp["scores"])
+                continue
+            h = hits_h[rel_off[idx]:rel_off[idx + 1]]
+            self._record(gt_r, {k: h[:, j] for j, k in enumerate(ks)})

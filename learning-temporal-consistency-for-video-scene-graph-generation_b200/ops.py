@@ -789,3 +789,24 @@ def adamw_clip_step(tensors, chunk_tensor, chunk_off, chunk_elems, sq_norm, max_
                                                chunk_elems, _ptr(sq_norm), max_norm, lr, beta1, beta2, eps, weight_decay,
                                                _stream()), "adamw_clip_step")
     _count()
+
+
+def eval_recall(pair_idx, frame_off, n_frames, att, spa, con, boxes5, classes, scores, gt_boxes, gt_classes, gt_box_off,
+                gt_rels, gt_rel_off, mode, semi_thr, iou_thr):
+    """b200vsgg_eval_recall: Recall@K hit flags [G,4] (K = 10/20/50/100) of every ground-truth relation of one video and a
+    status word (1: a frame exceeded the kernel's tables).  boxes5 = pred['boxes'] [O,5] (column 0 is the frame index)."""
+    dev = pair_idx.device
+    G = gt_rels.numel() // 3
+    hits = torch.empty(G, 4, dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    pi = pair_idx.contiguous().to(torch.int64)
+    a, s_, c = (t.detach().contiguous().float() for t in (att, spa, con))
+    b5 = boxes5.detach().contiguous().float()
+    cl = classes.contiguous().to(torch.int64)
+    sc = scores.detach().contiguous().float()
+    check(_lib.lib().b200vsgg_eval_recall(
+        _ptr(pi), _ptr(frame_off), n_frames, _ptr(a), a.shape[1], _ptr(s_), s_.shape[1], _ptr(c), c.shape[1],
+        b5.data_ptr() + 4, b5.stride(0), _ptr(cl), _ptr(sc), _ptr(gt_boxes), _ptr(gt_classes), _ptr(gt_box_off),
+        _ptr(gt_rels), _ptr(gt_rel_off), mode, semi_thr, iou_thr, _ptr(hits), _ptr(status), _stream()), "eval_recall")
+    _count()
+    return hits, status

@@ -521,19 +521,29 @@ class TEMPURA(nn.Module):
 # ================================================================================================
 # heads: packed GEMM + fused mixture epilogue
 # ================================================================================================
+DIRECT_HEAD_GRADS = True       # see _HeadsFn.backward
+
+
 def apply_heads(heads, feat, mode, eps_list, seed):
     """All mixture heads of `heads` (GMMHead containers) on `feat` [N, hid]: ONE packed GEMM + one epilogue kernel
     (tools/utils/gmm_heads.py:37-76 does 3K tiny Linears per head).  The 2 x 3K x len(heads) Linear parameters go to the
     autograd function individually — no differentiable torch.cat whose backward would split the packed gradient with
     one small kernel per Linear; the packed bf16 operand is memoised per parameter version."""
     lins = [l for h in heads for l in h.packed_order()]
+    params = [l.weight for l in lins] + [l.bias for l in lins]
+    direct = DIRECT_HEAD_GRADS and torch.is_grad_enabled() and all(p.is_leaf for p in params)
     return _HeadsFn.apply(feat, mode, heads[0].k, [h.num_classes for h in heads], [h.softmax for h in heads], eps_list,
-                          seed, len(lins), *[l.weight for l in lins], *[l.bias for l in lins])
+                          seed, len(lins), tuple(params) if direct else None, *(params[:1] if direct else params))
 
 
 class _HeadsFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feat, mode, K, Cs, softmaxes, eps_list, seed, n_lin, *params):
+    def forward(ctx, feat, mode, K, Cs, softmaxes, eps_list, seed, n_lin, holder, *params):
+        # holder: the 2 * n_lin parameters as a plain tuple (no autograd edges; `params` is then only the first weight,
+        # which keeps the node connected to the graph) — see backward
+        direct = holder is not None
+        if direct:
+            params = holder
         ws, bs = params[:n_lin], params[n_lin:]
         N = feat.shape[0]
         K_in = ws[0].shape[1]
@@ -574,6 +584,7 @@ class _HeadsFn(torch.autograd.Function):
                       out2=outs2[i]) for i in range(len(Cs))]
         ops.gmm_head_fwd(z, K, specs, mode, seed)
         ctx.save_for_backward(fb, Wb, z)
+        ctx.params, ctx.direct = params, direct
         ctx.meta = (mode, K, Cs, softmaxes, eps_dev, seed, bases, cols, cols_pad, n_lin, [w.shape[0] for w in ws])
         if mode == 2:
             ctx.mark_non_differentiable(*outs, *outs2)
@@ -597,15 +608,34 @@ class _HeadsFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dfeat = torch.empty(N, Wb.shape[1], device=dev)
             ops.gemm(dz, Wb, b_mn=True, out_f32=dfeat)
-        if any(ctx.needs_input_grad[8:8 + n_lin]):
+        params, ctx.params = ctx.params, None
+        need = [p.requires_grad for p in params] if ctx.direct else list(ctx.needs_input_grad[9:])
+        if any(need[:n_lin]):
             dWp = torch.empty(cols_pad, Wb.shape[1], device=dev)
             ops.gemm(dz, fb, a_mn=True, b_mn=True, out_f32=dWp)
             dws = list(torch.split(dWp[:cols], rows_of, 0))              # views: no copies, no kernels
-        if any(ctx.needs_input_grad[8 + n_lin:]):
+        if any(need[n_lin:]):
             dbp = torch.zeros(1, cols_pad, device=dev)
             ops.colsum(dz, dbp)
             dbs = list(torch.split(dbp[0, :cols], rows_of, 0))
-        return (dfeat, None, None, None, None, None, None, None, *dws, *dbs)
+        if ctx.direct:
+            # 2 x 3K x 3 = 108 small Linear parameters: as autograd inputs they cost 108 AccumulateGrad node evaluations
+            # (~0.4-0.5 ms of host time) exactly where the device has nothing queued yet (the forward ends with the
+            # regulariser's host synchronisation, and the heads' backward kernels are tiny).  They are therefore NOT inputs
+            # of this node (only the first weight is, to keep it in the graph); their gradients are accumulated here with
+            # AccumulateGrad's semantics (adopt when .grad is None, add otherwise).  tempura.DIRECT_HEAD_GRADS = False
+            # restores plain autograd inputs for wrappers that hook these parameters' graph nodes (torch DDP);
+            # b200vsgg.ddp.GradSync reads .grad and is unaffected.
+            with torch.no_grad():
+                for i, (p_, g_) in enumerate(zip(params, list(dws) + list(dbs))):
+                    if i == 0 or g_ is None or not need[i]:
+                        continue
+                    if p_.grad is None:
+                        p_.grad = g_
+                    else:
+                        p_.grad.add_(g_)
+            return (dfeat,) + (None,) * 8 + (dws[0] if need[0] else None,)
+        return (dfeat, None, None, None, None, None, None, None, None, *dws, *dbs)
 
 
 # ================================================================================================

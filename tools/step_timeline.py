@@ -90,15 +90,16 @@ def main():
         lines.append("  %8.1f   %-60s -> %s" % (g, p[:60], n[:80]))
         if g >= 30.0:
             # host activity during the gap: the longest CPU-side events that overlap it (what the host was busy with)
-            ov = []
+            ov = {}
             for c in cpu:
                 a, b = c.time_range.start, c.time_range.end
                 o = min(b, gb) - max(a, ga)
-                if o > 0.2 * g:
-                    ov.append((b - a, o, c.name))
-            ov.sort(key=lambda x: x[0])
-            for d, o, name in ov[:6]:
-                lines.append("               host: %-50s dur %.0f us (overlap %.0f us)" % (name[:50], d, o))
+                if o > 0:
+                    r = ov.setdefault(c.name[:60], [0.0, 0])
+                    r[0] += o
+                    r[1] += 1
+            for name, (o, cnt) in sorted(ov.items(), key=lambda kv: -kv[1][0])[:8]:
+                lines.append("               host: %-60s x%-4d overlap %.0f us" % (name, cnt, o))
     # aggregate gap time by the kernel that follows
     agg = {}
     for g, p, n, _, _ in gaps:
