@@ -381,6 +381,12 @@ int b200vsgg_graph_small_fwd(const float* nodes, const uint8_t* upper, const int
  * input prefetch. h_pinned_src must stay untouched until the kernel has run. */
 int b200vsgg_upload(const void* h_pinned_src, void* dst, int64_t bytes, void* stream);
 
+/* Eval-time temporal-consistency score (tools/utils/temporal_consistency.py:45-66): for each interval
+ * [s, e) of pair rows, KLDivLoss(batchmean)(log_softmax(one_hot(gt[s:e])), softmax(dist[s:e])).  dist fp32 [N,n_classes]
+ * (n_classes <= 32), gt int32 [N], intervals int32 [I,2], out fp32 [I].  One warp per interval. */
+int b200vsgg_interval_kl(const float* dist, int32_t n_classes, const int32_t* gt, const int32_t* intervals,
+                         int32_t n_intervals, float* out, void* stream);
+
 /* Recall@K matching of one video (tools/utils/evaluation_recall.py:119-276: evaluate_from_dict,
  * evaluate_recall, _triplet, _compute_pred_matches), one CTA per frame.
  *   pair_idx int64 [N,2] box rows, frame_off int32 [F+1] pair offsets of the frames, att/spa/con fp32 distributions

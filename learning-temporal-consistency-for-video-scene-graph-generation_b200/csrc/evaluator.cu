@@ -201,7 +201,47 @@ eval_recall_kernel(const long long* __restrict__ pair_idx, const int32_t* __rest
     }
 }
 
+// Eval-time temporal-consistency score (tools/utils/temporal_consistency.py:45-66): for every interval [s, e) of pairs
+//   KLDivLoss(batchmean)(input = log_softmax(one_hot(gt)), target = softmax(dist))
+//     = 1/(e-s) * sum_rows sum_c q_c (log q_c - p_c),   q = softmax(dist row),
+//       p_c = [c == gt] - log(e^1 + C - 1)                                   (log_softmax of a one-hot row).
+// One warp per interval, lane = class (C <= 32), warp-shuffle reductions.
+__global__ void __launch_bounds__(128)
+interval_kl_kernel(const float* __restrict__ dist, int C, const int32_t* __restrict__ gt, const int32_t* __restrict__ itv,
+                   int n_itv, float* __restrict__ out) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_itv) return;
+    const int s = itv[2 * w], e = itv[2 * w + 1];
+    const float lse_onehot = logf(expf(1.f) + static_cast<float>(C - 1));
+    float acc = 0.f;
+    for (int r = s; r < e; ++r) {
+        const float x = lane < C ? dist[static_cast<size_t>(r) * C + lane] : -INFINITY;
+        const float mx = warp_max(x);
+        const float ex = lane < C ? expf(x - mx) : 0.f;
+        const float sum = warp_sum(ex);
+        if (lane < C) {
+            const float q = ex / sum;
+            const float logq = (x - mx) - logf(sum);
+            const float p = (lane == gt[r] ? 1.f : 0.f) - lse_onehot;
+            acc += q > 0.f ? q * (logq - p) : 0.f;             // xlogy convention of F.kl_div for q == 0
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[w] = acc / static_cast<float>(e - s);
+}
+
 }  // namespace vsgg
+
+extern "C" int b200vsgg_interval_kl(const float* dist, int32_t n_classes, const int32_t* gt, const int32_t* intervals,
+                                    int32_t n_intervals, float* out, void* stream) {
+    using namespace vsgg;
+    if (!dist || !gt || !intervals || !out || n_classes < 1 || n_classes > 32)
+        return set_error(B200VSGG_ERR_BAD_ARG, "interval_kl: bad arg (1 <= classes <= 32)");
+    if (n_intervals <= 0) return 0;
+    interval_kl_kernel<<<(n_intervals + 3) / 4, 128, 0, (cudaStream_t)stream>>>(dist, n_classes, gt, intervals, n_intervals, out);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int b200vsgg_eval_recall(const int64_t* pair_idx, const int32_t* frame_off, int32_t n_frames, const float* att,
                                     int32_t na, const float* spa, int32_t ns, const float* con, int32_t nc,

@@ -810,3 +810,13 @@ def eval_recall(pair_idx, frame_off, n_frames, att, spa, con, boxes5, classes, s
         _ptr(gt_rels), _ptr(gt_rel_off), mode, semi_thr, iou_thr, _ptr(hits), _ptr(status), _stream()), "eval_recall")
     _count()
     return hits, status
+
+
+def interval_kl(dist, gt, intervals):
+    """b200vsgg_interval_kl: temporal-consistency score of each interval [s, e) of pair rows -> fp32 [I] (device)."""
+    d = dist.detach().contiguous().float()
+    out = torch.empty(intervals.shape[0], dtype=torch.float32, device=d.device)
+    check(_lib.lib().b200vsgg_interval_kl(_ptr(d), d.shape[1], _ptr(gt), _ptr(intervals), intervals.shape[0], _ptr(out),
+                                           _stream()), "interval_kl")
+    _count()
+    return out

@@ -38,11 +38,36 @@ def find_consecutive_duplicates(target_bool, gt_tensor, pred_tensor=None, window
     return out
 
 
-def evaluate_temp_cons(pred, temp_cons_eval_spatial, temp_cons_eval_contact, mode):
+def evaluate_temp_cons(pred, temp_cons_eval_spatial, temp_cons_eval_contact, mode, backend="host"):
+    """backend="host": everything on the host, bit-identical to the reference.  backend="cuda": the runs are still found on
+    the host (they depend on the ground-truth label lists only) but all intervals of the video are scored by ONE launch
+    per predicate group (b200vsgg_interval_kl) on the device-resident distributions — no transfer of the distributions, one
+    small read-back; equal to the host scores to fp32 rounding (tests/test_evaluator_gpu.py)."""
     if mode == "sgdet":
         return None, None
     spatial_gt = np.asarray([i[0] for i in pred["spatial_gt"]], dtype=np.int64)
     contact_gt = np.asarray([i[0] for i in pred["contacting_gt"]], dtype=np.int64)
+    if backend == "cuda":
+        from . import ops
+        dev = pred["spatial_distribution"].device
+        if dev.type != "cuda":
+            raise RuntimeError("backend='cuda' needs the distributions on a CUDA device")
+        labels = pred["pred_labels"].detach().cpu().numpy()
+        obj_cls = labels[labels != 1]
+        itv_s, itv_c = [], []
+        for cls in np.unique(obj_cls):
+            itv_s += find_consecutive_duplicates(obj_cls == cls, spatial_gt)
+            itv_c += find_consecutive_duplicates(obj_cls == cls, contact_gt)
+        outs = []
+        for itv, gt, key in ((itv_s, spatial_gt, "spatial_distribution"), (itv_c, contact_gt, "contacting_distribution")):
+            if itv:
+                outs.append(ops.interval_kl(pred[key], ops.upload(gt.astype(np.int32), dev),
+                                            ops.upload(np.asarray(itv, dtype=np.int32), dev)))
+            else:
+                outs.append(torch.zeros(0, device=dev))
+        both = torch.cat(outs).to(temp_cons_eval_spatial.device)                 # one read-back
+        return (torch.cat([temp_cons_eval_spatial, both[:len(itv_s)]]),
+                torch.cat([temp_cons_eval_contact.to(both.device), both[len(itv_s):]]))
     spatial_pred = pred["spatial_distribution"].detach().float().cpu()
     contact_pred = pred["contacting_distribution"].detach().float().cpu()
     labels = pred["pred_labels"].detach().cpu().numpy()

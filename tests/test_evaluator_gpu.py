@@ -61,3 +61,20 @@ def test_cuda_evaluator_equals_host_backend_on_larger_videos(cuda_lib, mode, con
     assert dev.calc_mrecall() == host.calc_mrecall()
     if constraint == "no" and mode != "predcls":
         assert len(dev.gt_obj_list) == len(host.gt_obj_list) and len(dev.pred_obj_list) == len(host.pred_obj_list)
+
+
+def test_cuda_temporal_consistency_score_matches_reference_golden(cuda_lib):
+    """backend="cuda" of evaluate_temp_cons (b200vsgg_interval_kl): the same intervals as the unmodified reference (their
+    count is part of the golden record) and scores equal to its values to fp32 rounding (2e-6 absolute: the device sums a
+    row's classes with warp shuffles, the reference with ATen's reduction order)."""
+    from make_golden_eval import TC_CASES, tc_prediction
+    from b200vsgg import temporal_consistency as tc
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "temporal_consistency.pt"), weights_only=False)
+    s, c = torch.tensor([]), torch.tensor([])
+    for vid, frames in TC_CASES:
+        pred = _cuda(tc_prediction(vid, frames))
+        s, c = tc.evaluate_temp_cons(pred, s, c, "predcls", backend="cuda")
+        ref_s, ref_c = gold["after_%d" % vid]
+        assert s.shape == ref_s.shape and c.shape == ref_c.shape, (vid, s.shape, ref_s.shape)
+        assert (s.cpu() - ref_s).abs().max().item() <= 2e-6 and (c.cpu() - ref_c).abs().max().item() <= 2e-6
+    assert s.numel() > 0 and c.numel() > 0
