@@ -381,6 +381,13 @@ int b200vsgg_graph_small_fwd(const float* nodes, const uint8_t* upper, const int
  * input prefetch. h_pinned_src must stay untouched until the kernel has run. */
 int b200vsgg_upload(const void* h_pinned_src, void* dst, int64_t bytes, void* stream);
 
+/* Class-memory accumulation of the trainers' uncertainty / memory bookkeeping (SURVEY.md 8(f).4;
+ * tools/utils/Memory.py:53-117 `rel_memory[rel] += batch_unc.T @ rel_features`, fed by tools/utils/Uncertainty.py:105-178
+ * which writes every video's features to .npy files): A[ent_cls[e], :] += ent_w[e] * feat[ent_row[e], :] for the
+ * (row, class, weight) entries of one step; feat fp32 [N,D] with row pitch ldf, A fp32 [n_classes, D] (n_classes <= 40). */
+int b200vsgg_class_memory_accumulate(const float* feat, int32_t ldf, int32_t D, const int32_t* ent_row, const int32_t* ent_cls,
+                                     const float* ent_w, int32_t n_ent, int32_t n_classes, float* A, void* stream);
+
 /* Eval-time temporal-consistency score (tools/utils/temporal_consistency.py:45-66): for each interval
  * [s, e) of pair rows, KLDivLoss(batchmean)(log_softmax(one_hot(gt[s:e])), softmax(dist[s:e])).  dist fp32 [N,n_classes]
  * (n_classes <= 32), gt int32 [N], intervals int32 [I,2], out fp32 [I].  One warp per interval. */

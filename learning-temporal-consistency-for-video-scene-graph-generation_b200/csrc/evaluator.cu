@@ -8,6 +8,7 @@
 // Integer / double work, a few kB per frame: bounded by latency, not by any roofline; the point is ONE launch and ONE
 // small read-back per video instead of ~20 host synchronisations per frame.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdint>
 
 #include "../../include/b200vsgg.h"
@@ -230,7 +231,43 @@ interval_kl_kernel(const float* __restrict__ dist, int C, const int32_t* __restr
     if (lane == 0) out[w] = acc / static_cast<float>(e - s);
 }
 
+// Class-memory accumulation (tools/utils/Memory.py:53-117: rel_memory[rel] += batch_unc^T . rel_features per video, from
+// .npy files written every step): A[cls, :] += w_e * F[row_e, :] over the (row, class, weight) entries of a step, with
+// the features still resident on the device.  grid = (column chunks of 128, entry slices); a CTA keeps its [C][128]
+// partial sums in shared memory (thread = column: no conflicts) and adds them to A once at the end.
+constexpr int CM_MAX_CLASSES = 40;
+__global__ void __launch_bounds__(128)
+class_memory_accumulate_kernel(const float* __restrict__ feat, int ldf, int D, const int32_t* __restrict__ ent_row,
+                               const int32_t* __restrict__ ent_cls, const float* __restrict__ ent_w, int n_ent, int C,
+                               float* __restrict__ A) {
+    __shared__ float acc[CM_MAX_CLASSES][128];
+    const int tx = threadIdx.x, col = blockIdx.x * 128 + tx;
+    for (int k = 0; k < C; ++k) acc[k][tx] = 0.f;
+    const int per = (n_ent + gridDim.y - 1) / gridDim.y;
+    const int e0 = blockIdx.y * per, e1 = min(n_ent, e0 + per);
+    if (col < D)
+        for (int e = e0; e < e1; ++e)
+            acc[ent_cls[e]][tx] = fmaf(ent_w[e], feat[static_cast<size_t>(ent_row[e]) * ldf + col], acc[ent_cls[e]][tx]);
+    if (col < D && e1 > e0)
+        for (int k = 0; k < C; ++k)
+            if (acc[k][tx] != 0.f) atomicAdd(A + static_cast<size_t>(k) * D + col, acc[k][tx]);
+}
+
 }  // namespace vsgg
+
+extern "C" int b200vsgg_class_memory_accumulate(const float* feat, int32_t ldf, int32_t D, const int32_t* ent_row,
+                                                const int32_t* ent_cls, const float* ent_w, int32_t n_ent, int32_t n_classes,
+                                                float* A, void* stream) {
+    using namespace vsgg;
+    if (!feat || !ent_row || !ent_cls || !ent_w || !A || D <= 0 || n_classes < 1 || n_classes > CM_MAX_CLASSES)
+        return set_error(B200VSGG_ERR_BAD_ARG, "class_memory_accumulate: bad arg (1 <= classes <= 40)");
+    if (n_ent <= 0) return 0;
+    dim3 grid((D + 127) / 128, (unsigned)std::min(64, (n_ent + 63) / 64));
+    class_memory_accumulate_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(feat, ldf, D, ent_row, ent_cls, ent_w, n_ent,
+                                                                         n_classes, A);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int b200vsgg_interval_kl(const float* dist, int32_t n_classes, const int32_t* gt, const int32_t* intervals,
                                     int32_t n_intervals, float* out, void* stream) {

@@ -820,3 +820,13 @@ def interval_kl(dist, gt, intervals):
                                            _stream()), "interval_kl")
     _count()
     return out
+
+
+def class_memory_accumulate(feat, ent_row, ent_cls, ent_w, A):
+    """b200vsgg_class_memory_accumulate: A[ent_cls[e]] += ent_w[e] * feat[ent_row[e]] (fp32, in place)."""
+    f = feat.detach()
+    assert f.dtype == torch.float32 and f.stride(1) == 1 and A.dtype == torch.float32 and A.is_contiguous()
+    check(_lib.lib().b200vsgg_class_memory_accumulate(_ptr(f), f.stride(0), f.shape[1], _ptr(ent_row), _ptr(ent_cls),
+                                                       _ptr(ent_w), ent_row.numel(), A.shape[0], _ptr(A), _stream()),
+          "class_memory_accumulate")
+    _count()
