@@ -277,3 +277,52 @@ def test_attn_rows_kernel_matches_torch(cuda_lib, hd, n_heads, lens):
     rhs = (rowsum[:, :, None] * doc.float().view(M, n_heads, hd)).sum(0)
     assert (lhs - rhs).abs().max().item() <= 3e-2 * rhs.abs().max().item()
     assert 0.5 < rowsum.mean().item() < 1.5 and (rowsum == 0).float().mean().item() < 0.5
+
+
+@pytest.mark.parametrize("selection", ["manual"])
+def test_object_memory_with_tracking_matches_oracle(cuda_lib, selection):
+    """Object-memory hallucinator of the tracking branch (lib/tempura.py:160-183,213-222: single-head attention of the
+    class-sequence features over the per-class object memory, blended by the fixed selector — the reference's LEARNED
+    selector is nn.Linear(1024, 1) (lib/tempura.py:101) and cannot take the 2376-wide tracking features at all) with a NON-EMPTY
+    memory bank: object_mem_features and the object distribution vs the CPU oracle, and the gradients of the memory
+    attention / selector / sequence encoder vs the oracle's autograd."""
+    from b200vsgg import objbranch, synthetic, tempura
+    from oracle.tempura_oracle import TempuraOracle, object_loss, tempura_losses
+    gold = torch.load(os.path.join(GOLDEN, "sgcls_track_gmm.pt"), weights_only=False)
+    kw = dict(gold["model_kw"], obj_mem_compute=True, selection=selection)
+    classes = synthetic.ag_object_classes()
+    m = tempura.TEMPURA(obj_classes=classes, **kw)
+    synthetic.seeded_init_(m)
+    o = TempuraOracle(obj_classes=classes, dropout=0.0, **kw)
+    o.load_state_dict(m.state_dict(), strict=True)
+    bank = 0.5 * torch.randn(len(classes) - 1, 2376, generator=torch.Generator().manual_seed(77))
+    m.object_classifier.obj_memory = bank.cuda()
+    o.object_classifier.obj_memory = bank.clone()
+    vid = gold["case"]["video_index"]
+    entry = synthetic.add_sgcls_inputs(synthetic.make_video_entry(**gold["case"]), vid)
+    objbranch.get_sequence(entry, None, None, "sgcls")
+    m, o = m.cuda().train(), o.train()
+    m.dropout_p = m.object_classifier.dropout_p = 0.0
+    m.gmm_eps = gold["eps"]
+    att, spa, con = synthetic.build_gt_tensors(entry)
+    po = o(_clone(entry), phase="train", eps=gold["eps"])
+    (sum(tempura_losses(po, att, spa, con).values()) + object_loss(po, 0.5)).backward()
+    pm = m(_clone(entry, "cuda"), phase="train")
+    sum(tempura.tempura_loss(pm, m.last_plan, eos_coef=0.5).values()).backward()
+    # the memory changed the features (the test would be vacuous otherwise)
+    assert (po["object_mem_features"] - po["object_features"]).abs().max().item() > 1e-2
+    ref = po["object_mem_features"].detach()
+    err = (pm["object_mem_features"].float().cpu() - ref).abs().max().item()
+    assert err <= FEAT_REL_TOL * ref.abs().max().item(), err
+    assert (pm["distribution"].float().cpu() - po["distribution"].detach()).abs().max().item() <= DIST_TOL
+    og = dict(o.named_parameters())
+    checked = 0
+    for pname, p in m.named_parameters():
+        if not (pname.startswith("object_classifier.mem_attention") or pname.startswith("object_classifier.selector")):
+            continue
+        r = og[pname].grad
+        assert r is not None and p.grad is not None, pname
+        rel = (p.grad.float().cpu() - r).norm().item() / max(r.norm().item(), 1e-12)
+        assert rel <= GATED_GRAD_REL_TOL, (pname, rel)
+        checked += 1
+    assert checked >= (2 if selection == "manual" else 4)
