@@ -409,6 +409,46 @@ __global__ void colsum_kernel(const T* __restrict__ x, int ld_x, int rows, int c
     }
 }
 
+// Vectorised variant for bf16 rows (cols % 8 == 0, 16-byte aligned): thread = 8 columns (one 16-byte load per row),
+// block = 32 column vectors x 8 row phases, grid = (ceil(cols/256), row slabs).  The scalar kernel above reads 2 bytes per
+// thread and reached 1.4 TB/s on the [31.8 k, 3872] position-embedding sums of the decoder backward (0.26 ms per layer).
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, int ld_x, int rows, int cols,
+                                                         const int32_t* __restrict__ group_idx, int n_groups,
+                                                         float* __restrict__ out) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = (blockIdx.x * 32 + tx) * 8;
+    const int rows_per_slab = (rows + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per_slab, r1 = min(rows, r0 + rows_per_slab);
+    float acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+    if (col < cols) {
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += 8) {
+            float v[8];
+            load_bf16x8(x + static_cast<size_t>(r) * ld_x + col, v);
+            const bool g1 = group_idx != nullptr && __ldg(group_idx + r) != 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[0][j] += g1 ? 0.f : v[j];
+                acc[1][j] += g1 ? v[j] : 0.f;
+            }
+        }
+    }
+    __shared__ float red[2][8][32][9];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[0][ty][tx][j] = acc[0][j]; red[1][ty][tx][j] = acc[1][j]; }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 256 * n_groups; o += 256) {
+        const int g = o >> 8, c = o & 255;
+        float sum = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) sum += red[g][y][c >> 3][c & 7];
+        const int gc = blockIdx.x * 256 + c;
+        if (gc < cols) atomicAdd(out + static_cast<size_t>(g) * cols + gc, sum);
+    }
+}
+
 }  // namespace vsgg
 
 using namespace vsgg;
@@ -544,6 +584,16 @@ extern "C" int b200vsgg_colsum(const void* x, int32_t x_is_bf16, int32_t ld_x, i
                                const int32_t* group_idx, int32_t n_groups, float* out, void* stream) {
     if (!x || !out || n_groups < 1 || n_groups > 2) return set_error(B200VSGG_ERR_BAD_ARG, "colsum: bad arg");
     if (rows == 0) return 0;
+    if (x_is_bf16 && (cols & 7) == 0 && (ld_x & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+        int slabs = (rows + 127) / 128;
+        const int col_blocks = (cols + 255) / 256;
+        const int want = (148 * 4 + col_blocks - 1) / col_blocks;            // ~4 CTAs per SM in flight
+        if (slabs > want) slabs = want;
+        colsum_vec_kernel<<<dim3(col_blocks, slabs), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld_x, rows, cols,
+                                                                                      group_idx, n_groups, out);
+        VSGG_CUDA_CHECK_LAUNCH();
+        return 0;
+    }
     dim3 block(64, 4);
     int slabs = (rows + 255) / 256;
     if (slabs > 64) slabs = 64;

@@ -979,7 +979,7 @@ class _PathRunner:
                               gL[gkey], gL[bkey])
             return du, dub
 
-        def attn_block_bwd(du, dub, R, L, i, rows, seg_off, n_seg, max_len, site):
+        def attn_block_bwd(du, dub, R, L, i, rows, seg_off, n_seg, max_len, site, pos_groups=False):
             """Backward of u = x + drop(Wo attn(q,k,v) + bo); returns dqkv bf16 [rows, 3D]."""
             gL = G[i]
             gL["out_w"] = gnew(L["out_w"], D_MODEL, D_MODEL)
@@ -993,31 +993,34 @@ class _PathRunner:
             ops.attn_small_bwd(qkv[:, :D_MODEL], qkv[:, D_MODEL:2 * D_MODEL], qkv[:, 2 * D_MODEL:], dctx, seg_off, n_seg,
                                max_len, N_HEADS, HEAD_DIM, dqkv[:, :D_MODEL], dqkv[:, D_MODEL:2 * D_MODEL],
                                dqkv[:, 2 * D_MODEL:], p, self._seed(site))
-            gL["in_b"] = zeros(1, 3 * D_MODEL)
-            ops.colsum(dqkv, gL["in_b"])
+            if not pos_groups:
+                gL["in_b"] = zeros(1, 3 * D_MODEL)
+                ops.colsum(dqkv, gL["in_b"])
             return dqkv
 
         # ---- T5 backward: scatter d_out into window-token rows
         dy = new(M2, D_MODEL, f32)
         ops.gather2_sum_rows(d_out, plan.inv_latter2, out_f32=dy)
         # ---- T4 backward
-        dpos_qk = zeros(2, 2 * D_MODEL)  # per layer: column sums of [dq|dk] grouped by position id
         G["pos"] = zeros(2, D_MODEL)
         for j in reversed(range(self.n_dec)):
             i = self.n_enc + j
             L, R = P["dec"][j], S["dec%d" % j]
             site = R["site"]
             du, dub = ffn_and_norm_bwd(dy, R, L, i, M2, "g3", R["m3"], R["r3"], R["u"], "g3", "be3", site)
-            dqkv = attn_block_bwd(du, dub, R, L, i, M2, plan.win_off, plan.W, plan.max_win_len, site)
+            dqkv = attn_block_bwd(du, dub, R, L, i, M2, plan.win_off, plan.W, plan.max_win_len, site, pos_groups=True)
             gL = G[i]
             gL["in_w"] = gnew(L["in_w"], 3 * D_MODEL, D_MODEL)
             ops.gemm(dqkv[:, :2 * D_MODEL], R["gpb"], a_mn=True, b_mn=True, out_f32=gL["in_w"][:2 * D_MODEL])
             ops.gemm(dqkv[:, 2 * D_MODEL:], R["gb"], a_mn=True, b_mn=True, out_f32=gL["in_w"][2 * D_MODEL:])
-            # position embedding: d pos[k] = (sum over tokens with position k of [dq|dk]) @ W_qk
-            dpos_qk.zero_()
-            ops.colsum(dqkv[:, :2 * D_MODEL], dpos_qk, plan.win_pos, 2)
+            # ONE pass over dqkv gives its column sums per position id: their total is the in_proj bias gradient, the
+            # [dq|dk] part per position feeds the position embedding: d pos[k] = (sum over tokens with position k) @ W_qk
+            by_pos = zeros(2, 3 * D_MODEL)
+            ops.colsum(dqkv, by_pos, plan.win_pos, 2)
+            gL["in_b"] = by_pos.sum(0, keepdim=True)
+            dpos_qk = by_pos[:, :2 * D_MODEL]
             dposb = torch.zeros(8, 2 * D_MODEL, device=dev, dtype=bf16)
-            ops.cast_bf16(dpos_qk, out=dposb[:2])
+            dposb[:2] = dpos_qk
             dpos_l = new(8, D_MODEL, f32)
             ops.gemm(dposb, W["%din_w" % i][:2 * D_MODEL], b_mn=True, out_f32=dpos_l)
             G["pos"] += dpos_l[:2]
