@@ -36,11 +36,32 @@ namespace vsgg {
 namespace atc {
 
 constexpr int KV_STAGES = 2;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;           // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quadrant)
 constexpr int TMEM_COLS = 256;
 constexpr int COL_S = 0, COL_P = 128, COL_O = 192;
-constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 256 + 1024;   // tiles + barriers + alignment slack
+constexpr int XCH_BYTES = 2 * 2 * 128 * 4 + 128 * 4;   // row-maximum exchange (double-buffered, two halves) + row sums
+constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 256 + XCH_BYTES + 1024;   // tiles + barriers + exchange + slack
 constexpr float RESCALE_THRESHOLD = 8.f;   // log2 domain: P stays below 2^8, exact in fp32 sums and fine in bf16
+
+// Work-unit metadata (clip bounds, first query row): three DEPENDENT global loads whose latency (~1 k cycles) was exposed
+// at the top of every unit in every role — a unit of a 250-600-token clip is only 2..5 key blocks long.  Each role now
+// fetches the NEXT unit's metadata while it works on the current one.
+struct UnitMeta {
+    int s0, s1, qrow0, head;
+};
+__device__ __forceinline__ UnitMeta load_unit_meta(int u, int n_units, int n_heads, const int32_t* __restrict__ seq_off,
+                                                   const int32_t* __restrict__ blk_seq, const int32_t* __restrict__ blk_row0) {
+    UnitMeta m{0, 0, 0, 0};
+    if (u < n_units) {
+        const int blk = u / n_heads;
+        m.head = u - blk * n_heads;
+        const int seq = __ldg(blk_seq + blk);
+        m.qrow0 = __ldg(blk_row0 + blk);
+        m.s0 = __ldg(seq_off + seq);
+        m.s1 = __ldg(seq_off + seq + 1);
+    }
+    return m;
+}
 
 template <int HDN>   // accumulator width of O: 32 (head_dim <= 32) or 64
 __global__ void __launch_bounds__(THREADS, 2)
@@ -67,6 +88,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     uint64_t* p_full = s_free + 1;
     uint64_t* o_done = p_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+    float* xmax = reinterpret_cast<float*>(bars + 32);     // [2 (buffer)][2 (half)][128 rows]
+    float* xsum = xmax + 2 * 2 * 128;                       // [128 rows]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -85,8 +108,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             ptx::mbar_init(&v_empty[i], 1);
         }
         ptx::mbar_init(s_full, 1);
-        ptx::mbar_init(s_free, 128);
-        ptx::mbar_init(p_full, 128);
+        ptx::mbar_init(s_free, 256);
+        ptx::mbar_init(p_full, 256);
         ptx::mbar_init(o_done, 1);
         ptx::fence_mbar_init();
     }
@@ -107,15 +130,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         // ================================ TMA producer ================================
         if (lane == 0) {
             uint32_t qc = 0, kc = 0;                          // units / key tiles issued so far
+            UnitMeta nxt = load_unit_meta(blockIdx.x, n_units, n_heads, seq_off, blk_seq, blk_row0);
             for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++qc) {
-                const int blk = u / n_heads, head = u - blk * n_heads;
-                const int seq = blk_seq[blk];
-                const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
+                const UnitMeta cur = nxt;
+                nxt = load_unit_meta(u + gridDim.x, n_units, n_heads, seq_off, blk_seq, blk_row0);
+                const int head = cur.head, s0 = cur.s0, s1 = cur.s1;
                 const int nkb = (s1 - s0 + BKV - 1) / BKV;
                 const uint32_t qs = qc & 1u;
                 ptx::mbar_wait(&q_empty[qs], ((qc >> 1) & 1u) ^ 1u);
                 ptx::mbar_expect_tx(&q_full[qs], TILE_BYTES);
-                ptx::tma_load_3d(Qs + qs * TILE_BYTES, &tq, &q_full[qs], 0, blk_row0[blk], head);
+                ptx::tma_load_3d(Qs + qs * TILE_BYTES, &tq, &q_full[qs], 0, cur.qrow0, head);
                 for (int j = 0; j < nkb; ++j, ++kc) {
                     const uint32_t st = kc % KV_STAGES, ph = (kc / KV_STAGES) & 1u;
                     ptx::mbar_wait(&k_empty[st], ph ^ 1u);
@@ -135,10 +159,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             const int ks_s = (hd + 15) >> 4;                                       // k-steps over head_dim
             const uint32_t t_s = tmem_base + COL_S, t_p = tmem_base + COL_P, t_o = tmem_base + COL_O;
             uint32_t qc = 0, g0 = 0;                          // units done, key tiles done before this unit
+            UnitMeta nxt = load_unit_meta(blockIdx.x, n_units, n_heads, seq_off, blk_seq, blk_row0);
             for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++qc) {
-                const int blk = u / n_heads;
-                const int seq = blk_seq[blk];
-                const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
+                const UnitMeta cur = nxt;
+                nxt = load_unit_meta(u + gridDim.x, n_units, n_heads, seq_off, blk_seq, blk_row0);
+                const int s0 = cur.s0, s1 = cur.s1;
                 const int nkb = (s1 - s0 + BKV - 1) / BKV;
                 const uint32_t qs = qc & 1u;
                 const uint32_t qa = ptx::smem_u32(Qs + qs * TILE_BYTES);
@@ -176,51 +201,62 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             }
         }
     } else {
-        // ================================ softmax warps: thread = query row ================================
+        // ================ softmax warps: TWO threads per query row, 64 of the tile's 128 keys each ================
+        // Warps w and w + 4 may access the same TMEM lane quadrant (w % 4): the first four softmax warps own columns
+        // [0,64) of S, the other four [64,128).  With one thread per row (128 live score registers, 168 registers per
+        // thread) only 4 softmax warps x 2 CTAs ran per SM and ncu showed the issue slots half empty (stalls: fixed-
+        // latency dependencies and TMEM loads with nothing else to issue); eight warps per CTA at <= 102 registers double
+        // the warps that can hide them.  The row maximum is exchanged through shared memory (double-buffered, one
+        // 64-thread named barrier per block); the row sums are combined once per unit.
         const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+        const int ch = (warp - 2) >> 2;                 // column half
         const int row = quad * 32 + lane;               // row of the tile
         const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t t_s = tmem_base + lane_addr + COL_S, t_p = tmem_base + lane_addr + COL_P,
+        const uint32_t t_s = tmem_base + lane_addr + COL_S + ch * 64, t_p = tmem_base + lane_addr + COL_P + ch * 32,
                        t_o = tmem_base + lane_addr + COL_O;
         // attention dropout (attn_dropout.cuh): one LCG draw per four keys, SWAR compare, the keep masks are ANDed into
         // the packed bf16 pairs; the 1/(1-p) of the survivors is folded into the final normalisation of O
         const uint32_t thr = adrop::thr8_of(drop_p);
         const float inv_keep = thr ? adrop::inv_keep_of(thr) : 1.f;
         const uint32_t K8 = (256u - thr) * 0x00010001u;
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory"); };
         uint32_t g = 0;                                 // key tiles processed so far (barrier phases)
+        UnitMeta nxt = load_unit_meta(blockIdx.x, n_units, n_heads, seq_off, blk_seq, blk_row0);
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const int blk = u / n_heads, head = u - blk * n_heads;
-            const int seq = blk_seq[blk];
-            const int s0 = seq_off[seq], s1 = seq_off[seq + 1];
-            const int qrow0 = blk_row0[blk];
+            const UnitMeta cur = nxt;
+            nxt = load_unit_meta(u + gridDim.x, n_units, n_heads, seq_off, blk_seq, blk_row0);
+            const int head = cur.head, s0 = cur.s0, s1 = cur.s1, qrow0 = cur.qrow0;
             const int qrows = min(BQ, s1 - qrow0);
             const int nkb = (s1 - s0 + BKV - 1) / BKV;
             const uint32_t row_key = thr ? adrop::row_key(seed, qrow0 + row, head) : 0u;
             float m_ref = 0.f, l = 0.f;
             for (int j = 0; j < nkb; ++j, ++g) {
-                const int kvalid = min(BKV, s1 - (s0 + j * BKV));
-                uint32_t r[128];
+                const int kvalid = min(BKV, s1 - (s0 + j * BKV)) - ch * 64;      // valid keys among this half's 64 columns
+                uint32_t r[64];
                 ptx::mbar_wait(s_full, g & 1u);
                 ptx::tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    ptx::tmem_ld_32x32b_x32(t_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(r[c * 32]));
+                ptx::tmem_ld_32x32b_x32(t_s, reinterpret_cast<uint32_t(&)[32]>(r[0]));
+                ptx::tmem_ld_32x32b_x32(t_s + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(s_free);                   // the next S MMA may overwrite the buffer
                 float mx = -INFINITY;
-                if (kvalid == BKV) {
+                if (kvalid >= 64) {
 #pragma unroll
-                    for (int i = 0; i < 64; ++i)        // three-input maximum (FMNMX3): one issue slot per two scores
+                    for (int i = 0; i < 32; ++i)        // three-input maximum (FMNMX3): one issue slot per two scores
                         mx = fmaxf(fmaxf(mx, __uint_as_float(r[2 * i])), __uint_as_float(r[2 * i + 1]));
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 128; ++i) {
+                    for (int i = 0; i < 64; ++i) {
                         if (i >= kvalid) r[i] = 0xff800000u;   // -inf: keys beyond the clip
                         mx = fmaxf(mx, __uint_as_float(r[i]));
                     }
                 }
-                mx *= scale_log2;
+                // full-row maximum: exchange with the thread that owns the other 64 columns of this row
+                float* xb = xmax + (g & 1u) * 256;
+                xb[ch * 128 + row] = mx;
+                pair_sync();
+                mx = fmaxf(mx, xb[(ch ^ 1) * 128 + row]) * scale_log2;
                 float alpha = 1.f;
                 bool rescale = false;
                 if (j == 0) {
@@ -231,13 +267,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                     rescale = true;
                 }
                 // exponent arguments and the row sum run on the packed fp32x2 pipes (FFMA2 / FADD2): per PAIR of scores
-                // one FFMA2, two MUFU.EX2, one FADD2, one pack — the MUFU, not the issue port, is the limit
+                // one FFMA2, two MUFU.EX2, one FADD2, one pack
                 float sum = 0.f, sum1 = 0.f;
                 const float nm = -m_ref;
-                uint32_t pk[64];
+                uint32_t pk[32];
                 if (thr == 0u) {
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) {
+                    for (int i = 0; i < 32; ++i) {
                         float a0, a1;
                         ptx::fma2(a0, a1, __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]), scale_log2, scale_log2, nm, nm);
                         const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);
@@ -245,10 +281,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                         pk[i] = pack2(p0, p1);
                     }
                 } else {
-                    const uint32_t kb64 = static_cast<uint32_t>(j) * 2u;      // key block of 64 relative to the clip start
-                    const uint32_t sd[2] = {adrop::stream_seed(row_key, kb64), adrop::stream_seed(row_key, kb64 + 1u)};
+                    // key block of 64 relative to the clip start: the same streams as the one-thread-per-row version
+                    const uint32_t sd = adrop::stream_seed(row_key, static_cast<uint32_t>(j) * 2u + static_cast<uint32_t>(ch));
 #pragma unroll
-                    for (int g4 = 0; g4 < 32; ++g4) {                          // groups of four keys
+                    for (int g4 = 0; g4 < 16; ++g4) {                          // groups of four keys
                         float p[4], a[4];
                         ptx::fma2(a[0], a[1], __uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1]), scale_log2, scale_log2, nm, nm);
                         ptx::fma2(a[2], a[3], __uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3]), scale_log2, scale_log2, nm, nm);
@@ -257,16 +293,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                         ptx::add2(sum, sum1, sum, sum1, p[0], p[1]);
                         ptx::add2(sum, sum1, sum, sum1, p[2], p[3]);
                         uint32_t lo, hi;
-                        adrop::keep_masks4(adrop::draw(sd[g4 >> 4], (g4 & 15) >> 1, g4 & 1), K8, lo, hi);
+                        adrop::keep_masks4(adrop::draw(sd, g4 >> 1, g4 & 1), K8, lo, hi);
                         pk[2 * g4] = pack2(p[0], p[1]) & lo;
                         pk[2 * g4 + 1] = pack2(p[2], p[3]) & hi;
                     }
                 }
-                l = l * alpha + (sum + sum1);
+                l = l * alpha + (sum + sum1);               // this half's share of the row sum
                 if (j > 0) {                                // P and O are free once the previous P V has retired
                     ptx::mbar_wait(o_done, (g - 1) & 1u);
                     ptx::tc_fence_after();
-                    if (__any_sync(0xffffffffu, rescale)) {
+                    if (ch == 0 && __any_sync(0xffffffffu, rescale)) {          // one of the row's two threads rescales O
                         uint32_t o[HDN];
 #pragma unroll
                         for (int c = 0; c < HDN / 32; ++c)
@@ -281,37 +317,43 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                 }
                 // (j == 0: the previous unit's epilogue below already waited for its last P V)
                 ptx::tmem_st_32x32b_x32(t_p, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
-                ptx::tmem_st_32x32b_x32(t_p + 32, reinterpret_cast<const uint32_t(&)[32]>(pk[32]));
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(p_full);
             }
-            // ---- epilogue: O / l -> bf16 context rows, log-sum-exp for the backward.  The next unit's first P V comes
-            //      after this thread's next p_full arrival, i.e. after these loads of O.
+            // ---- epilogue: O / l -> bf16 context rows, log-sum-exp for the backward (the half-0 thread of each row; the
+            //      other half hands over its share of the row sum).  The next unit's first P V comes after BOTH threads'
+            //      next p_full arrival, i.e. after these loads of O.
+            if (ch == 1) xsum[row] = l;
+            pair_sync();
             ptx::mbar_wait(o_done, (g - 1) & 1u);
             ptx::tc_fence_after();
-            uint32_t o[HDN];
+            if (ch == 0) {
+                l += xsum[row];
+                uint32_t o[HDN];
 #pragma unroll
-            for (int c = 0; c < HDN / 32; ++c)
-                ptx::tmem_ld_32x32b_x32(t_o + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
-            ptx::tmem_ld_wait();
-            if (row < qrows) {
-                const float inv = inv_keep / l;
-                const size_t grow = static_cast<size_t>(qrow0 + row);
-                __nv_bfloat16* dst = ctx + grow * ldc + head * hd;
+                for (int c = 0; c < HDN / 32; ++c)
+                    ptx::tmem_ld_32x32b_x32(t_o + c * 32, reinterpret_cast<uint32_t(&)[32]>(o[c * 32]));
+                ptx::tmem_ld_wait();
+                if (row < qrows) {
+                    const float inv = inv_keep / l;
+                    const size_t grow = static_cast<size_t>(qrow0 + row);
+                    __nv_bfloat16* dst = ctx + grow * ldc + head * hd;
 #pragma unroll
-                for (int c = 0; c < HDN / 8; ++c) {
-                    if (c * 8 < hd) {
-                        uint4 v4;
-                        v4.x = pack2(__uint_as_float(o[c * 8]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
-                        v4.y = pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
-                        v4.z = pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
-                        v4.w = pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
-                        *reinterpret_cast<uint4*>(dst + c * 8) = v4;
+                    for (int c = 0; c < HDN / 8; ++c) {
+                        if (c * 8 < hd) {
+                            uint4 v4;
+                            v4.x = pack2(__uint_as_float(o[c * 8]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
+                            v4.y = pack2(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
+                            v4.z = pack2(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
+                            v4.w = pack2(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
+                            *reinterpret_cast<uint4*>(dst + c * 8) = v4;
+                        }
                     }
+                    if (lse != nullptr) lse[grow * n_heads + head] = (m_ref + __log2f(l)) * 0.6931471805599453f;
                 }
-                if (lse != nullptr) lse[grow * n_heads + head] = (m_ref + __log2f(l)) * 0.6931471805599453f;
             }
+            pair_sync();        // xsum[row] may be rewritten by the next unit only after it was read
         }
     }
     // ================================ teardown ================================
