@@ -36,7 +36,7 @@ namespace vsgg {
 namespace atc {
 
 constexpr int KV_STAGES = 2;
-constexpr int THREADS = 320;           // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quadrant)
+constexpr int threads_of(int nh) { return 64 + 128 * nh; }   // TMA warp, MMA warp, 4 * nh softmax warps
 constexpr int TMEM_COLS = 256;
 constexpr int COL_S = 0, COL_P = 128, COL_O = 192;
 constexpr int XCH_BYTES = 2 * 2 * 128 * 4 + 128 * 4;   // row-maximum exchange (double-buffered, two halves) + row sums
@@ -63,8 +63,10 @@ __device__ __forceinline__ UnitMeta load_unit_meta(int u, int n_units, int n_hea
     return m;
 }
 
-template <int HDN>   // accumulator width of O: 32 (head_dim <= 32) or 64
-__global__ void __launch_bounds__(THREADS, 2)
+// HDN: accumulator width of O, 32 (head_dim <= 32) or 64.  NH: softmax threads per query row (1: a thread owns the whole
+// 128-key row of S; 2: two threads own 64 keys each — see the softmax section).
+template <int HDN, int NH>
+__global__ void __launch_bounds__(threads_of(NH), 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const int32_t* __restrict__ seq_off,
                    const int32_t* __restrict__ blk_seq, const int32_t* __restrict__ blk_row0, int n_units, int n_heads,
@@ -108,8 +110,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             ptx::mbar_init(&v_empty[i], 1);
         }
         ptx::mbar_init(s_full, 1);
-        ptx::mbar_init(s_free, 256);
-        ptx::mbar_init(p_full, 256);
+        ptx::mbar_init(s_free, 128 * NH);
+        ptx::mbar_init(p_full, 128 * NH);
         ptx::mbar_init(o_done, 1);
         ptx::fence_mbar_init();
     }
@@ -201,25 +203,30 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             }
         }
     } else {
-        // ================ softmax warps: TWO threads per query row, 64 of the tile's 128 keys each ================
-        // Warps w and w + 4 may access the same TMEM lane quadrant (w % 4): the first four softmax warps own columns
-        // [0,64) of S, the other four [64,128).  With one thread per row (128 live score registers, 168 registers per
-        // thread) only 4 softmax warps x 2 CTAs ran per SM and ncu showed the issue slots half empty (stalls: fixed-
-        // latency dependencies and TMEM loads with nothing else to issue); eight warps per CTA at <= 102 registers double
-        // the warps that can hide them.  The row maximum is exchanged through shared memory (double-buffered, one
-        // 64-thread named barrier per block); the row sums are combined once per unit.
+        // ================ softmax warps: NH threads per query row, 128 / NH of the tile's keys each ================
+        // NH = 1: thread = query row (tcgen05.ld 32x32b: lane = row), the row maximum and the row sum are thread-local.
+        // NH = 2: warps w and w + 4 may access the same TMEM lane quadrant (w % 4): the first four softmax warps own
+        // columns [0,64) of S, the other four [64,128); the row maximum is exchanged through shared memory (double-
+        // buffered, one 64-thread named barrier per block), the row sums are combined once per unit.  Measured on B200
+        // (tools/attn_tc_profile.py): 32 heads x 24 — 2.28 -> 2.16 ms with dropout, 2.13 -> 1.89 ms without (the 168-
+        // register single thread per row left the issue slots half empty); 16 heads x 48 — the O rescale / epilogue
+        // state of the 64-wide accumulator spills at the 96-register budget of NH = 2 and the kernel gets SLOWER
+        // (4.85 -> 6.1 ms per layer of the SGCls config), so that width keeps NH = 1.
+        constexpr int CW = 128 / NH;                    // score columns per thread
         const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
-        const int ch = (warp - 2) >> 2;                 // column half
+        const int ch = (warp - 2) >> 2;                 // column part (0 for NH = 1)
         const int row = quad * 32 + lane;               // row of the tile
         const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t t_s = tmem_base + lane_addr + COL_S + ch * 64, t_p = tmem_base + lane_addr + COL_P + ch * 32,
+        const uint32_t t_s = tmem_base + lane_addr + COL_S + ch * CW, t_p = tmem_base + lane_addr + COL_P + ch * (CW / 2),
                        t_o = tmem_base + lane_addr + COL_O;
         // attention dropout (attn_dropout.cuh): one LCG draw per four keys, SWAR compare, the keep masks are ANDed into
         // the packed bf16 pairs; the 1/(1-p) of the survivors is folded into the final normalisation of O
         const uint32_t thr = adrop::thr8_of(drop_p);
         const float inv_keep = thr ? adrop::inv_keep_of(thr) : 1.f;
         const uint32_t K8 = (256u - thr) * 0x00010001u;
-        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory"); };
+        auto pair_sync = [&]() {
+            if (NH == 2) asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory");
+        };
         uint32_t g = 0;                                 // key tiles processed so far (barrier phases)
         UnitMeta nxt = load_unit_meta(blockIdx.x, n_units, n_heads, seq_off, blk_seq, blk_row0);
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -231,32 +238,35 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             const uint32_t row_key = thr ? adrop::row_key(seed, qrow0 + row, head) : 0u;
             float m_ref = 0.f, l = 0.f;
             for (int j = 0; j < nkb; ++j, ++g) {
-                const int kvalid = min(BKV, s1 - (s0 + j * BKV)) - ch * 64;      // valid keys among this half's 64 columns
-                uint32_t r[64];
+                const int kvalid = min(BKV, s1 - (s0 + j * BKV)) - ch * CW;      // valid keys among this thread's columns
+                uint32_t r[CW];
                 ptx::mbar_wait(s_full, g & 1u);
                 ptx::tc_fence_after();
-                ptx::tmem_ld_32x32b_x32(t_s, reinterpret_cast<uint32_t(&)[32]>(r[0]));
-                ptx::tmem_ld_32x32b_x32(t_s + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
+#pragma unroll
+                for (int c = 0; c < CW / 32; ++c)
+                    ptx::tmem_ld_32x32b_x32(t_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(r[c * 32]));
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(s_free);                   // the next S MMA may overwrite the buffer
                 float mx = -INFINITY;
-                if (kvalid >= 64) {
+                if (kvalid >= CW) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)        // three-input maximum (FMNMX3): one issue slot per two scores
+                    for (int i = 0; i < CW / 2; ++i)    // three-input maximum (FMNMX3): one issue slot per two scores
                         mx = fmaxf(fmaxf(mx, __uint_as_float(r[2 * i])), __uint_as_float(r[2 * i + 1]));
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) {
+                    for (int i = 0; i < CW; ++i) {
                         if (i >= kvalid) r[i] = 0xff800000u;   // -inf: keys beyond the clip
                         mx = fmaxf(mx, __uint_as_float(r[i]));
                     }
                 }
-                // full-row maximum: exchange with the thread that owns the other 64 columns of this row
-                float* xb = xmax + (g & 1u) * 256;
-                xb[ch * 128 + row] = mx;
-                pair_sync();
-                mx = fmaxf(mx, xb[(ch ^ 1) * 128 + row]) * scale_log2;
+                if (NH == 2) {      // full-row maximum: exchange with the thread that owns the other 64 columns of this row
+                    float* xb = xmax + (g & 1u) * 256;
+                    xb[ch * 128 + row] = mx;
+                    pair_sync();
+                    mx = fmaxf(mx, xb[(ch ^ 1) * 128 + row]);
+                }
+                mx *= scale_log2;
                 float alpha = 1.f;
                 bool rescale = false;
                 if (j == 0) {
@@ -270,10 +280,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                 // one FFMA2, two MUFU.EX2, one FADD2, one pack
                 float sum = 0.f, sum1 = 0.f;
                 const float nm = -m_ref;
-                uint32_t pk[32];
+                uint32_t pk[CW / 2];
                 if (thr == 0u) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
+                    for (int i = 0; i < CW / 2; ++i) {
                         float a0, a1;
                         ptx::fma2(a0, a1, __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]), scale_log2, scale_log2, nm, nm);
                         const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);
@@ -281,10 +291,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                         pk[i] = pack2(p0, p1);
                     }
                 } else {
-                    // key block of 64 relative to the clip start: the same streams as the one-thread-per-row version
-                    const uint32_t sd = adrop::stream_seed(row_key, static_cast<uint32_t>(j) * 2u + static_cast<uint32_t>(ch));
+                    // one stream per key block of 64 relative to the clip start, whichever thread draws from it
+                    uint32_t sdv[CW / 64];
 #pragma unroll
-                    for (int g4 = 0; g4 < 16; ++g4) {                          // groups of four keys
+                    for (int c = 0; c < CW / 64; ++c)
+                        sdv[c] = adrop::stream_seed(row_key, static_cast<uint32_t>(j) * 2u + static_cast<uint32_t>(ch * (CW / 64) + c));
+#pragma unroll
+                    for (int g4 = 0; g4 < CW / 4; ++g4) {                      // groups of four keys
+                        const uint32_t sd = sdv[g4 >> 4];
                         float p[4], a[4];
                         ptx::fma2(a[0], a[1], __uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1]), scale_log2, scale_log2, nm, nm);
                         ptx::fma2(a[2], a[3], __uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3]), scale_log2, scale_log2, nm, nm);
@@ -293,7 +307,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                         ptx::add2(sum, sum1, sum, sum1, p[0], p[1]);
                         ptx::add2(sum, sum1, sum, sum1, p[2], p[3]);
                         uint32_t lo, hi;
-                        adrop::keep_masks4(adrop::draw(sd, g4 >> 1, g4 & 1), K8, lo, hi);
+                        adrop::keep_masks4(adrop::draw(sd, (g4 & 15) >> 1, g4 & 1), K8, lo, hi);
                         pk[2 * g4] = pack2(p[0], p[1]) & lo;
                         pk[2 * g4 + 1] = pack2(p[2], p[3]) & hi;
                     }
@@ -316,7 +330,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
                     }
                 }
                 // (j == 0: the previous unit's epilogue below already waited for its last P V)
-                ptx::tmem_st_32x32b_x32(t_p, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
+#pragma unroll
+                for (int c = 0; c < CW / 64; ++c)
+                    ptx::tmem_st_32x32b_x32(t_p + c * 32, reinterpret_cast<const uint32_t(&)[32]>(pk[c * 32]));
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(p_full);
@@ -324,12 +340,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             // ---- epilogue: O / l -> bf16 context rows, log-sum-exp for the backward (the half-0 thread of each row; the
             //      other half hands over its share of the row sum).  The next unit's first P V comes after BOTH threads'
             //      next p_full arrival, i.e. after these loads of O.
-            if (ch == 1) xsum[row] = l;
+            if (NH == 2 && ch == 1) xsum[row] = l;
             pair_sync();
             ptx::mbar_wait(o_done, (g - 1) & 1u);
             ptx::tc_fence_after();
             if (ch == 0) {
-                l += xsum[row];
+                if (NH == 2) l += xsum[row];
                 uint32_t o[HDN];
 #pragma unroll
                 for (int c = 0; c < HDN / 32; ++c)
@@ -388,15 +404,15 @@ extern "C" int b200vsgg_attn_tc_fwd(const void* q, int32_t ldq, const void* k, i
     if (units > 0x7fffffffLL) return set_error(B200VSGG_ERR_BAD_ARG, "attn_tc_fwd: too many (tile, head) units");
     static bool attr_set = false;
     if (!attr_set) {     // both instantiations share one function-pointer type: set the attribute on each explicitly
-        cudaError_t e = cudaFuncSetAttribute(atc::attn_tc_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(atc::attn_tc_fwd_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              atc::SMEM_BYTES);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(atc::attn_tc_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            e = cudaFuncSetAttribute(atc::attn_tc_fwd_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      atc::SMEM_BYTES);
         if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
         attr_set = true;
     }
-    auto launch = [&](auto kern) -> int {
+    auto launch = [&](auto kern, int threads) -> int {
         // Persistent (two CTAs per SM walk the unit list) when the softmax warps carry the dropout work; one unit per
         // CTA otherwise.  Measured on B200 (tools/flash_bench.py, 32 heads x 24): training p = 0.1  1.90 -> 1.78 ms at the
         // AG shapes; inference p = 0  1.50 ms per-unit vs 1.76 ms persistent (2.97 vs 3.38 ms on long clips) — with the
@@ -405,12 +421,12 @@ extern "C" int b200vsgg_attn_tc_fwd(const void* q, int32_t ldq, const void* k, i
         static const int force = []() { const char* e = getenv("B200VSGG_ATTN_PERSIST"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
         const bool persist = force >= 0 ? force == 1 : drop_p > 0.f;
         const long long resident = persist ? 2LL * num_sms() : units;
-        kern<<<static_cast<unsigned>(units < resident ? units : resident), atc::THREADS, atc::SMEM_BYTES, (cudaStream_t)stream>>>(
+        kern<<<static_cast<unsigned>(units < resident ? units : resident), threads, atc::SMEM_BYTES, (cudaStream_t)stream>>>(
             tq, tk, tv, seq_off, blk_seq, blk_row0, static_cast<int>(units), n_heads, head_dim, scale_log2,
             reinterpret_cast<__nv_bfloat16*>(ctx), ldc, lse, drop_p, seed);
         return 0;
     };
-    rc = head_dim <= 32 ? launch(atc::attn_tc_fwd_kernel<32>) : launch(atc::attn_tc_fwd_kernel<64>);
+    rc = head_dim <= 32 ? launch(atc::attn_tc_fwd_kernel<32, 2>, atc::threads_of(2)) : launch(atc::attn_tc_fwd_kernel<64, 1>, atc::threads_of(1));
     if (rc) return rc;
     VSGG_CUDA_CHECK_LAUNCH();
     return 0;
