@@ -488,7 +488,27 @@ def pin_to_gpu_numa_node(local_rank):
         with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
             node = int(f.read().strip())
         if node < 0:
-            return {"gpu_pci": bus, "numa_node": node, "pinned": False, "why": "single-node host or node unknown"}
+            # containers often hide the PCI device's numa_node; NVML still knows which CPUs sit next to the GPU
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+                except TypeError:
+                    h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+                words = (os.cpu_count() + 63) // 64
+                mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+                cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+                allowed = os.sched_getaffinity(0) & cpus
+                if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+                    os.sched_setaffinity(0, allowed)
+                    return {"gpu_pci": bus, "numa_node": node, "pinned": True, "cpus": len(allowed),
+                            "how": "nvmlDeviceGetCpuAffinity"}
+                return {"gpu_pci": bus, "numa_node": node, "pinned": False,
+                        "why": "NVML reports every allowed CPU as local to this GPU (single-node host)"}
+            except Exception as ex:
+                return {"gpu_pci": bus, "numa_node": node, "pinned": False,
+                        "why": "node unknown in sysfs; NVML affinity unavailable (%s)" % type(ex).__name__}
         with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
             cpus = set()
             for part in f.read().strip().split(","):
