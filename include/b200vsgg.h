@@ -315,6 +315,12 @@ int b200vsgg_act_dropout_bf16(const void* x, int32_t ld_x, int64_t rows, int32_t
 int b200vsgg_consistency_kl(const float* g, int32_t d, const int32_t* pair_u, const int32_t* pair_v, int32_t n_pairs,
                             float* out, void* stream);
 
+/* GlobalAttentionPooling of the regulariser (lib/teatgt.py:319-320, dgl.nn.GlobalAttentionPooling with gate_nn =
+ * Linear(d, 1)): per frame a = softmax_i(w . x_i + b), out[f] = sum_i a_i x_i.  x fp32 [rows, d] compact node rows,
+ * node_off int32 [frames+1], max_nodes <= 64, out fp32 [frames, d].  One CTA per frame. */
+int b200vsgg_attn_pool(const float* x, int32_t d, const int32_t* node_off, int32_t n_frames, int32_t max_nodes,
+                       const float* w, const float* b, float* out, void* stream);
+
 /* Per-frame graph attention core of the regulariser's GraphTransformer (8 heads x 64, rotary q/k, per-edge
  * key/value offsets from the adjacency; lib/teatgt.py:316-317 via graph_transformer_pytorch): qkv fp32
  * [rows, >= 1536] = q | k | v of the compact node rows, node_off int32 [frames+1], upper = uint8 predicate

@@ -74,6 +74,7 @@ SIGNATURES = {
     "b200vsgg_graph_small_params_per_layer": [i32, i32],
     "b200vsgg_graph_small_fwd": [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
     "b200vsgg_upload": [vp, vp, i64, vp],
+    "b200vsgg_attn_pool": [vp, i32, vp, i32, i32, vp, vp, vp, vp],
     "b200vsgg_class_memory_accumulate": [vp, i32, i32, vp, vp, vp, i32, i32, vp, vp],
     "b200vsgg_interval_kl": [vp, i32, vp, vp, i32, vp, vp],
     "b200vsgg_eval_recall": [vp, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, C.c_double,

@@ -191,6 +191,48 @@ extern "C" int b200vsgg_gated_residual(const float* o, float* res, const float* 
     return 0;
 }
 
+// GlobalAttentionPooling over compact node rows (dgl.nn.GlobalAttentionPooling as lib/teatgt.py:319-320 uses it): per frame
+// gate_i = w . x_i + b, a = softmax_i(gate), out = sum_i a_i x_i.  One CTA per frame (<= 64 nodes): a warp per node for
+// the gate dot products, then every thread owns output columns.
+namespace vsgg {
+constexpr int POOL_MAX_NODES = 64;
+__global__ void __launch_bounds__(256)
+attn_pool_kernel(const float* __restrict__ x, int D, const int32_t* __restrict__ node_off, const float* __restrict__ w,
+                 const float* __restrict__ b, float* __restrict__ out) {
+    __shared__ float gate[POOL_MAX_NODES];
+    const int f = blockIdx.x, r0 = node_off[f], n = node_off[f + 1] - r0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < n; i += 8) {
+        const float* xi = x + static_cast<size_t>(r0 + i) * D;
+        float acc = 0.f;
+        for (int d = lane; d < D; d += 32) acc = fmaf(xi[d], __ldg(w + d), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) gate[i] = acc + __ldg(b);
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int i = 0; i < n; ++i) mx = fmaxf(mx, gate[i]);
+    float den = 0.f;
+    for (int i = 0; i < n; ++i) den += __expf(gate[i] - mx);
+    const float inv = n > 0 ? 1.f / den : 0.f;
+    for (int d = threadIdx.x; d < D; d += 256) {
+        float acc = 0.f;
+        for (int i = 0; i < n; ++i) acc = fmaf(__expf(gate[i] - mx) * inv, x[static_cast<size_t>(r0 + i) * D + d], acc);
+        out[static_cast<size_t>(f) * D + d] = acc;
+    }
+}
+}  // namespace vsgg
+
+extern "C" int b200vsgg_attn_pool(const float* x, int32_t d, const int32_t* node_off, int32_t n_frames, int32_t max_nodes,
+                                  const float* w, const float* b, float* out, void* stream) {
+    if (!x || !node_off || !w || !b || !out || d <= 0 || max_nodes > vsgg::POOL_MAX_NODES)
+        return set_error(B200VSGG_ERR_BAD_ARG, "attn_pool: bad arg (<= 64 nodes per frame)");
+    if (n_frames <= 0) return 0;
+    vsgg::attn_pool_kernel<<<n_frames, 256, 0, (cudaStream_t)stream>>>(x, d, node_off, w, b, out);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int b200vsgg_consistency_kl(const float* g, int32_t d, const int32_t* pair_u, const int32_t* pair_v,
                                        int32_t n_pairs, float* out, void* stream) {
     if (!g || !pair_u || !pair_v || !out || d <= 0) return set_error(B200VSGG_ERR_BAD_ARG, "consistency_kl: bad arg");

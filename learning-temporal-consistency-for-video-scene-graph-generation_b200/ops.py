@@ -830,3 +830,14 @@ def class_memory_accumulate(feat, ent_row, ent_cls, ent_w, A):
                                                        _ptr(ent_w), ent_row.numel(), A.shape[0], _ptr(A), _stream()),
           "class_memory_accumulate")
     _count()
+
+
+def attn_pool(x, node_off, n_frames, max_nodes, w, b):
+    """b200vsgg_attn_pool: per-frame attention pooling of compact node rows -> fp32 [frames, d]."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and node_off.dtype == torch.int32
+    out = torch.empty(n_frames, x.shape[1], device=x.device, dtype=torch.float32)
+    check(_lib.lib().b200vsgg_attn_pool(_ptr(x), x.shape[1], _ptr(node_off), n_frames, max_nodes,
+                                         _ptr(w.detach().reshape(-1).contiguous().float()),
+                                         _ptr(b.detach().reshape(-1).contiguous().float()), _ptr(out), _stream()), "attn_pool")
+    _count()
+    return out

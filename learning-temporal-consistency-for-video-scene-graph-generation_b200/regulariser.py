@@ -120,13 +120,10 @@ def run_compact(gt, x, node_off, upper, nmax):
     return x
 
 
-def _pool_compact(x, frame_of_row, n_frames, gate_nn):
-    """GlobalAttentionPooling over compact rows: per-frame softmax of gate_nn(x), weighted sum -> [frames, dim]."""
-    logit = gate_nn(x).squeeze(-1)
-    mx = torch.full((n_frames,), float("-inf"), device=x.device).scatter_reduce(0, frame_of_row, logit, "amax")
-    w = torch.exp(logit - mx[frame_of_row])
-    den = torch.zeros(n_frames, device=x.device).index_add_(0, frame_of_row, w)
-    return torch.zeros(n_frames, x.shape[1], device=x.device).index_add_(0, frame_of_row, (w / den[frame_of_row])[:, None] * x)
+def _pool_compact(x, node_off, n_frames, nmax, gate_nn):
+    """GlobalAttentionPooling over compact rows: per-frame softmax of gate_nn(x), weighted sum -> [frames, dim]
+    (b200vsgg_attn_pool, one CTA per frame)."""
+    return ops.attn_pool(x.contiguous(), node_off, n_frames, nmax, gate_nn.weight, gate_nn.bias)
 
 
 @torch.no_grad()
@@ -141,7 +138,6 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
     counts_h = np.diff(plan.node_off_h)
     n_nodes = int(plan.node_off_h[-1])
     up_ = lambda a: ops.upload(a, dev)
-    frame_of_row = up_(np.repeat(np.arange(F_), counts_h))
     # ---- R2 first (device only, asynchronous): semantic nodes = the clip's hidden rows [0:n_f] (`savor` quirk)
     if clip_first_row is None:
         clip_first_row = plan.clip_node_off[plan.clip_of_frame]
@@ -160,7 +156,7 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
                            "take <= %d nodes per frame, structure width <= 16, semantic width %% 8 == 0 (no eager "
                            "fallback)" % (nmax, gat.dim, hidden.shape[1], min(MAX_NODES_STRUCT, MAX_NODES_SEM)))
     sem_rows = run_compact(gat_semantic, x, plan.node_off, spatial_flags, nmax)
-    sem = _pool_compact(sem_rows, frame_of_row, F_, gate_sem_nn)
+    sem = _pool_compact(sem_rows, plan.node_off, F_, nmax, gate_sem_nn)
     # ---- R1: per-frame Laplacian eigenvectors on the host (the reference's LAPACK call), grouped by node count;
     #      this runs while the device works on the semantic branch
     if flags_host is not None:        # (pinned host copy, event): the D2H was issued before the main path
