@@ -315,6 +315,26 @@ int b200vsgg_act_dropout_bf16(const void* x, int32_t ld_x, int64_t rows, int32_t
 int b200vsgg_consistency_kl(const float* g, int32_t d, const int32_t* pair_u, const int32_t* pair_v, int32_t n_pairs,
                             float* out, void* stream);
 
+/* Backward kernels of the DIFFERENTIABLE consistency mode (the reference detaches the two loss vectors,
+ * lib/teatgt.py:350-351 — `differentiable_consistency=True` is the "fixed" behaviour behind a flag).  All recompute their
+ * forward quantities from the saved inputs.
+ *   consistency_kl_bwd : dg [frames, d] += gradient of out[p] = KL / (v - u) scaled by gout[p] (0 = pair dropped)
+ *   attn_pool_bwd      : dx [rows, d] and dgate [rows] (gate-logit gradients: dw = weighted_colsum(x, dgate))
+ *   weighted_colsum    : out[c] += sum_r wgt[r] * x[r, c]   (x fp32 or bf16)
+ *   gated_residual_bwd : d_o, d_res [rows, dim] and da [rows] (dw1 = weighted_colsum(o, da), dw2 = ...(res, da), dw3 = dw1 - dw2)
+ *   graph_attn_core_bwd: dqkv fp32 [rows, 1536] from dout fp32 [rows, 512]; dwe / dbe [512] += (edges_to_kv gradients) */
+int b200vsgg_consistency_kl_bwd(const float* g, int32_t d, const int32_t* pair_u, const int32_t* pair_v, const float* gout,
+                                int32_t n_pairs, float* dg, void* stream);
+int b200vsgg_attn_pool_bwd(const float* x, int32_t d, const int32_t* node_off, int32_t n_frames, int32_t max_nodes,
+                           const float* w, const float* b, const float* dout, float* dx, float* dgate, void* stream);
+int b200vsgg_weighted_colsum(const void* x, int32_t x_is_bf16, int32_t ld, int32_t rows, int32_t cols, const float* wgt,
+                             float* out, void* stream);
+int b200vsgg_gated_residual_bwd(const float* o, const float* res, const float* w, const float* dx, int32_t rows, int32_t dim,
+                                float* d_o, float* d_res, float* da, void* stream);
+int b200vsgg_graph_attn_core_bwd(const float* qkv, int32_t ld, const int32_t* node_off, const uint8_t* upper, int32_t nmax,
+                                 const float* we, const float* be, const float* dout, int32_t ldd, int32_t n_frames,
+                                 float* dqkv, int32_t ldg, float* dwe, float* dbe, void* stream);
+
 /* GlobalAttentionPooling of the regulariser (lib/teatgt.py:319-320, dgl.nn.GlobalAttentionPooling with gate_nn =
  * Linear(d, 1)): per frame a = softmax_i(w . x_i + b), out[f] = sum_i a_i x_i.  x fp32 [rows, d] compact node rows,
  * node_off int32 [frames+1], max_nodes <= 64, out fp32 [frames, d].  One CTA per frame. */

@@ -74,6 +74,11 @@ SIGNATURES = {
     "b200vsgg_graph_small_params_per_layer": [i32, i32],
     "b200vsgg_graph_small_fwd": [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
     "b200vsgg_upload": [vp, vp, i64, vp],
+    "b200vsgg_consistency_kl_bwd": [vp, i32, vp, vp, vp, i32, vp, vp],
+    "b200vsgg_attn_pool_bwd": [vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp],
+    "b200vsgg_weighted_colsum": [vp, i32, i32, i32, i32, vp, vp, vp],
+    "b200vsgg_gated_residual_bwd": [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp],
+    "b200vsgg_graph_attn_core_bwd": [vp, i32, vp, vp, i32, vp, vp, vp, i32, i32, vp, i32, vp, vp, vp],
     "b200vsgg_attn_pool": [vp, i32, vp, i32, i32, vp, vp, vp, vp],
     "b200vsgg_class_memory_accumulate": [vp, i32, i32, vp, vp, vp, i32, i32, vp, vp],
     "b200vsgg_interval_kl": [vp, i32, vp, vp, i32, vp, vp],

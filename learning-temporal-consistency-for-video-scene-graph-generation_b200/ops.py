@@ -841,3 +841,36 @@ def attn_pool(x, node_off, n_frames, max_nodes, w, b):
                                          _ptr(b.detach().reshape(-1).contiguous().float()), _ptr(out), _stream()), "attn_pool")
     _count()
     return out
+
+
+# ---- backward kernels of the differentiable consistency mode (regulariser.py) --------------------------------------
+def consistency_kl_bwd(g, pair_u, pair_v, gout, dg):
+    check(_lib.lib().b200vsgg_consistency_kl_bwd(_ptr(g), g.shape[1], _ptr(pair_u), _ptr(pair_v), _ptr(gout), pair_u.numel(),
+                                                  _ptr(dg), _stream()), "consistency_kl_bwd")
+    _count()
+
+
+def attn_pool_bwd(x, node_off, n_frames, max_nodes, w, b, dout, dx, dgate):
+    check(_lib.lib().b200vsgg_attn_pool_bwd(_ptr(x), x.shape[1], _ptr(node_off), n_frames, max_nodes, _ptr(w), _ptr(b),
+                                             _ptr(dout), _ptr(dx), _ptr(dgate), _stream()), "attn_pool_bwd")
+    _count()
+
+
+def weighted_colsum(x, wgt, out):
+    assert x.stride(1) == 1 and wgt.dtype == torch.float32 and out.dtype == torch.float32
+    check(_lib.lib().b200vsgg_weighted_colsum(_ptr(x), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), x.shape[0],
+                                               x.shape[1], _ptr(wgt), _ptr(out), _stream()), "weighted_colsum")
+    _count()
+
+
+def gated_residual_bwd(o, res, w, dx, d_o, d_res, da):
+    check(_lib.lib().b200vsgg_gated_residual_bwd(_ptr(o), _ptr(res), _ptr(w), _ptr(dx), o.shape[0], o.shape[1], _ptr(d_o),
+                                                  _ptr(d_res), _ptr(da), _stream()), "gated_residual_bwd")
+    _count()
+
+
+def graph_attn_core_bwd(qkv, node_off, upper, nmax, we, be, dout, dqkv, dwe, dbe):
+    check(_lib.lib().b200vsgg_graph_attn_core_bwd(_ptr(qkv), qkv.stride(0), _ptr(node_off), _ptr(upper), nmax, _ptr(we),
+                                                   _ptr(be), _ptr(dout), dout.stride(0), node_off.numel() - 1, _ptr(dqkv),
+                                                   dqkv.stride(0), _ptr(dwe), _ptr(dbe), _stream()), "graph_attn_core_bwd")
+    _count()

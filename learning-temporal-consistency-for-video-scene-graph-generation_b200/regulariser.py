@@ -120,15 +120,207 @@ def run_compact(gt, x, node_off, upper, nmax):
     return x
 
 
+# ================================================================================================
+# differentiable mode: the same launch sequence with saved activations and a hand-orchestrated backward
+# ================================================================================================
+_PER_LAYER = 18      # parameters per GraphTransformer layer, in the order of `_layer_params`
+
+
+def _layer_params(gt):
+    out = []
+    for attn_block, ff_block in gt.layers:
+        pre, gate = attn_block
+        a = pre.fn
+        pre2, gate2 = ff_block
+        out += [pre.norm.weight, pre.norm.bias, a.to_q.weight, a.to_q.bias, a.to_kv.weight, a.to_kv.bias,
+                a.edges_to_kv.weight, a.edges_to_kv.bias, a.to_out.weight, a.to_out.bias, gate.proj[0].weight,
+                pre2.norm.weight, pre2.norm.bias, pre2.fn[0].weight, pre2.fn[0].bias, pre2.fn[2].weight, pre2.fn[2].bias,
+                gate2.proj[0].weight]
+    return out
+
+
+class _GraphTransformerFn(torch.autograd.Function):
+    """`run_compact` with gradients: forward = the same kernels (GELU applied by a separate pass so that the pre-activation
+    is kept), backward = GatedResidual / GraphTransformer-attention backward kernels of csrc/consistency.cu, the LayerNorm
+    backward and the tcgen05 GEMM in its dgrad / wgrad roles."""
+
+    @staticmethod
+    def forward(ctx, x, node_off, upper, nmax, heads, dim_head, *params):
+        R, dim = x.shape
+        dev = x.device
+        inner = heads * dim_head
+        bf = lambda w: ops.cast_bf16(w.detach().contiguous())
+        f32 = lambda *shape: torch.empty(*shape, device=dev)
+        b16 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.bfloat16)
+        x = x.detach().contiguous().clone()
+        saved = []
+        for li in range(len(params) // _PER_LAYER):
+            (ln1w, ln1b, qw, qb, kvw, kvb, ew, eb, ow, ob, g1, ln2w, ln2b, f1w, f1b, f2w, f2b, g2) = \
+                params[li * _PER_LAYER:(li + 1) * _PER_LAYER]
+            x_in = x.clone()
+            xn, mean1, rstd1 = b16(R, dim), f32(R), f32(R)
+            ops.layernorm_fwd(x, ln1w.detach(), ln1b.detach(), 1e-5, None, xn, mean=mean1, rstd=rstd1)
+            wqkv = bf(torch.cat([qw, kvw], 0))
+            qkv = f32(R, 3 * inner)
+            ops.gemm(xn, wqkv, bias=torch.cat([qb, kvb]).detach().clone(), out_f32=qkv)
+            att = b16(R, inner)
+            we, be = ew.detach()[:, 0].contiguous(), eb.detach().contiguous()
+            ops.graph_attn_core(qkv, node_off, upper, nmax, we, be, att)
+            wo = bf(ow)
+            o1 = f32(R, dim)
+            ops.gemm(att, wo, bias=ob.detach(), out_f32=o1)
+            ops.gated_residual(o1, x, g1.detach().reshape(-1).contiguous())          # x <- gate(o1, x_in)
+            x_mid = x.clone()
+            xn2, mean2, rstd2 = b16(R, dim), f32(R), f32(R)
+            ops.layernorm_fwd(x, ln2w.detach(), ln2b.detach(), 1e-5, None, xn2, mean=mean2, rstd=rstd2)
+            w1, w2 = bf(f1w), bf(f2w)
+            z = b16(R, 4 * dim)
+            ops.gemm(xn2, w1, bias=f1b.detach(), out_bf16=z)
+            hid = ops.act_dropout(z, ops.ACT_GELU)
+            o2 = f32(R, dim)
+            ops.gemm(hid, w2, bias=f2b.detach(), out_f32=o2)
+            ops.gated_residual(o2, x, g2.detach().reshape(-1).contiguous())          # x <- gate(o2, x_mid)
+            saved.append(dict(x_in=x_in, xn=xn, mean1=mean1, rstd1=rstd1, wqkv=wqkv, qkv=qkv, att=att, we=we, be=be, wo=wo,
+                              o1=o1, x_mid=x_mid, xn2=xn2, mean2=mean2, rstd2=rstd2, w1=w1, w2=w2, z=z, hid=hid, o2=o2))
+        ctx.saved, ctx.geom, ctx.params = saved, (node_off, upper, nmax, heads, dim_head), params
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        node_off, upper, nmax, heads, dim_head = ctx.geom
+        params, saved = ctx.params, ctx.saved
+        ctx.saved = None
+        dev = dx.device
+        inner = heads * dim_head
+        R, dim = dx.shape
+        f32 = lambda *shape: torch.empty(*shape, device=dev)
+        zeros = lambda *shape: torch.zeros(*shape, device=dev)
+        grads = [None] * len(params)
+        dx = dx.contiguous().float()
+
+        def gate_bwd(o, res, gw, dxx):
+            d_o, d_res, da = f32(R, dim), f32(R, dim), f32(R)
+            ops.gated_residual_bwd(o, res, gw.detach().reshape(-1).contiguous(), dxx, d_o, d_res, da)
+            dw1, dw2 = zeros(dim), zeros(dim)
+            ops.weighted_colsum(o, da, dw1)
+            ops.weighted_colsum(res, da, dw2)
+            return d_o, d_res, torch.cat([dw1, dw2, dw1 - dw2]).view(1, 3 * dim)
+
+        def linear_bwd(dy32, x_b, w_b, n_out, k_in, mask=None):
+            """dy fp32 [R, n_out] of y = x W^T + b -> (dW, db, dx fp32 or bf16-masked)."""
+            dyb = ops.cast_bf16(dy32)
+            dW = f32(n_out, k_in)
+            ops.gemm(dyb, x_b, a_mn=True, b_mn=True, out_f32=dW)
+            db = zeros(1, n_out)
+            ops.colsum(dyb, db)
+            return dyb, dW, db[0]
+
+        for li in reversed(range(len(saved))):
+            S = saved[li]
+            base = li * _PER_LAYER
+            (ln1w, ln1b, qw, qb, kvw, kvb, ew, eb, ow, ob, g1, ln2w, ln2b, f1w, f1b, f2w, f2b, g2) = params[base:base + _PER_LAYER]
+            # ---- x_out = gate2(o2, x_mid)
+            d_o2, d_mid_skip, grads[base + 17] = gate_bwd(S["o2"], S["x_mid"], g2, dx)
+            # ---- o2 = gelu(z) W2^T + b2,  z = LN2(x_mid) W1^T + b1
+            d_o2b, grads[base + 15], grads[base + 16] = linear_bwd(d_o2, S["hid"], S["w2"], dim, 4 * dim)
+            dz = torch.empty(R, 4 * dim, device=dev, dtype=torch.bfloat16)
+            ops.gemm(d_o2b, S["w2"], b_mn=True, mask_src=S["z"], mask_mode=ops.MASK_GELU, out_bf16=dz)
+            dW1 = f32(4 * dim, dim)
+            ops.gemm(dz, S["xn2"], a_mn=True, b_mn=True, out_f32=dW1)
+            db1 = zeros(1, 4 * dim)
+            ops.colsum(dz, db1)
+            grads[base + 13], grads[base + 14] = dW1, db1[0]
+            dxn2 = f32(R, dim)
+            ops.gemm(dz, S["w1"], b_mn=True, out_f32=dxn2)
+            d_mid, dg2, dbt2 = f32(R, dim), zeros(dim), zeros(dim)
+            ops.layernorm_bwd(dxn2, S["x_mid"], ln2w.detach(), S["mean2"], S["rstd2"], d_mid, None, 0.0, 0, dg2, dbt2,
+                              base=d_mid_skip)
+            grads[base + 11], grads[base + 12] = dg2, dbt2
+            # ---- x_mid = gate1(o1, x_in)
+            d_o1, d_in_skip, grads[base + 10] = gate_bwd(S["o1"], S["x_in"], g1, d_mid)
+            # ---- o1 = att Wo^T + bo
+            d_o1b, grads[base + 8], grads[base + 9] = linear_bwd(d_o1, S["att"], S["wo"], dim, inner)
+            datt = f32(R, inner)
+            ops.gemm(d_o1b, S["wo"], b_mn=True, out_f32=datt)
+            # ---- attention core
+            dqkv, dwe, dbe = f32(R, 3 * inner), zeros(inner), zeros(inner)
+            ops.graph_attn_core_bwd(S["qkv"], node_off, upper, nmax, S["we"], S["be"], datt, dqkv, dwe, dbe)
+            grads[base + 6], grads[base + 7] = dwe.view(inner, 1), dbe
+            # ---- qkv = LN1(x_in) Wqkv^T + bqkv
+            dqkvb, dWqkv, dbqkv = linear_bwd(dqkv, S["xn"], S["wqkv"], 3 * inner, dim)
+            grads[base + 2], grads[base + 3] = dWqkv[:inner], dbqkv[:inner]
+            grads[base + 4], grads[base + 5] = dWqkv[inner:], dbqkv[inner:]
+            dxn = f32(R, dim)
+            ops.gemm(dqkvb, S["wqkv"], b_mn=True, out_f32=dxn)
+            d_in, dg1, dbt1 = f32(R, dim), zeros(dim), zeros(dim)
+            ops.layernorm_bwd(dxn, S["x_in"], ln1w.detach(), S["mean1"], S["rstd1"], d_in, None, 0.0, 0, dg1, dbt1,
+                              base=d_in_skip)
+            grads[base + 0], grads[base + 1] = dg1, dbt1
+            dx = d_in
+            saved[li] = None
+        return (dx, None, None, None, None, None, *grads)
+
+
+class _AttnPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, node_off, n_frames, nmax, w, b):
+        x = x.contiguous()
+        ctx.save_for_backward(x, node_off, w, b)
+        ctx.geom = (n_frames, nmax)
+        return ops.attn_pool(x, node_off, n_frames, nmax, w, b)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, node_off, w, b = ctx.saved_tensors
+        n_frames, nmax = ctx.geom
+        dx, dgate = torch.empty_like(x), torch.zeros(x.shape[0], device=x.device)
+        wv, bv = w.detach().reshape(-1).contiguous().float(), b.detach().reshape(-1).contiguous().float()
+        ops.attn_pool_bwd(x, node_off, n_frames, nmax, wv, bv, dout.contiguous().float(), dx, dgate)
+        dw = torch.zeros(x.shape[1], device=x.device)
+        ops.weighted_colsum(x, dgate, dw)
+        return dx, None, None, None, dw.view_as(w), dgate.sum().view_as(b)
+
+
+class _ConsistencyKLFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, pu, pv):
+        g = g.contiguous()
+        ctx.save_for_backward(g, pu, pv)
+        return ops.consistency_kl(g, pu, pv)
+
+    @staticmethod
+    def backward(ctx, gout):
+        g, pu, pv = ctx.saved_tensors
+        dg = torch.zeros_like(g)
+        ops.consistency_kl_bwd(g, pu, pv, gout.contiguous().float(), dg)
+        return dg, None, None
+
+
+def run_compact_differentiable(gt, x, node_off, upper, nmax):
+    return _GraphTransformerFn.apply(x, node_off, upper, nmax, gt.heads, gt.dim_head, *_layer_params(gt))
+
+
 def _pool_compact(x, node_off, n_frames, nmax, gate_nn):
     """GlobalAttentionPooling over compact rows: per-frame softmax of gate_nn(x), weighted sum -> [frames, dim]
     (b200vsgg_attn_pool, one CTA per frame)."""
     return ops.attn_pool(x.contiguous(), node_off, n_frames, nmax, gate_nn.weight, gate_nn.bias)
 
 
-@torch.no_grad()
 def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_flags, hidden, clip_first_row=None,
-                       clip_rows=None, flags_host=None):
+                       clip_rows=None, flags_host=None, differentiable=False):
+    """differentiable=False (default, the reference's behaviour: both vectors detached).  differentiable=True: the SEMANTIC
+    loss vector carries gradients into gat_semantic, gate_sem_nn and `hidden` (pass it un-detached); the structure branch
+    reads constant Laplacian eigenvectors and stays detached (its single-CTA kernel has no backward)."""
+    if not differentiable:
+        with torch.no_grad():
+            return _consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_flags, hidden.detach(),
+                                       clip_first_row, clip_rows, flags_host, False)
+    return _consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_flags, hidden, clip_first_row,
+                               clip_rows, flags_host, True)
+
+
+def _consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_flags, hidden, clip_first_row, clip_rows,
+                        flags_host, differentiable):
     """Returns (structure_temp_loss [P], semantic_temp_loss [P']) for the batch described by `plan`
     (teatgt.TeatPlan); spatial_flags uint8 [F, nmax, nmax] on the DEVICE (b200vsgg_teat_pair_flags); hidden
     [rows, d_sem] = per-clip feature rows (TEAT-GT: node order, the default; clip_first_row / clip_rows [F] override
@@ -155,8 +347,12 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
         raise RuntimeError("consistency regulariser: a frame has %d nodes / widths (%d, %d); the on-chip graph kernels "
                            "take <= %d nodes per frame, structure width <= 16, semantic width %% 8 == 0 (no eager "
                            "fallback)" % (nmax, gat.dim, hidden.shape[1], min(MAX_NODES_STRUCT, MAX_NODES_SEM)))
-    sem_rows = run_compact(gat_semantic, x, plan.node_off, spatial_flags, nmax)
-    sem = _pool_compact(sem_rows, plan.node_off, F_, nmax, gate_sem_nn)
+    if differentiable:
+        sem_rows = run_compact_differentiable(gat_semantic, x, plan.node_off, spatial_flags, nmax)
+        sem = _AttnPoolFn.apply(sem_rows, plan.node_off, F_, nmax, gate_sem_nn.weight, gate_sem_nn.bias)
+    else:
+        sem_rows = run_compact(gat_semantic, x, plan.node_off, spatial_flags, nmax)
+        sem = _pool_compact(sem_rows, plan.node_off, F_, nmax, gate_sem_nn)
     # ---- R1: per-frame Laplacian eigenvectors on the host (the reference's LAPACK call), grouped by node count;
     #      this runs while the device works on the semantic branch
     if flags_host is not None:        # (pinned host copy, event): the D2H was issued before the main path
@@ -213,8 +409,9 @@ def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_fl
         f0 += int(nf)
     pu = up_(np.concatenate(pu).astype(np.int32))
     pv = up_(np.concatenate(pv).astype(np.int32))
-    s = ops.consistency_kl(sym.contiguous(), pu, pv)
-    m = ops.consistency_kl(sem.contiguous(), pu, pv)
+    with torch.no_grad():
+        s = ops.consistency_kl(sym.contiguous(), pu, pv)
+    m = _ConsistencyKLFn.apply(sem, pu, pv) if differentiable else ops.consistency_kl(sem.contiguous(), pu, pv)
     # the reference keeps a pair only if its score is >= 0 (lib/teatgt.py:327-333): a data-dependent length, hence a host
     # synchronisation — ONE flag for both branches; the usual case (no negative rounding residue) returns the kernels'
     # outputs as they are, without any gather

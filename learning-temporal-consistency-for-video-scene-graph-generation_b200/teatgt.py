@@ -331,6 +331,7 @@ class TEAT_GT(nn.Module):
         self.eig_threads = max(1, min(32, _os.cpu_count() or 8))
         self.eig_backend = "host"        # "device": batched cuSOLVER eigh (fast mode, see TeatPlan.build_graph)
         self.compute_consistency = True  # phase='train' fills structure_temp_loss / semantic_temp_loss (R1-R3)
+        self.differentiable_consistency = False   # True: the semantic loss carries gradients (regulariser.py)
         self.pipeline_chunks = 4         # PredCLS batches: video chunks whose host graph build overlaps the device
         self.last_plan = None
 
@@ -526,9 +527,12 @@ class TEAT_GT(nn.Module):
         out["contacting_distribution"] = torch.sigmoid(g[:, 9:])
         out["hidden_x"] = hidden                     # [nodes, 768] (extension: what the regulariser consumes)
         if phase == "train" and self.compute_consistency:
-            # R1-R3, detached like the reference (lib/teatgt.py:350-351)
+            # R1-R3, detached like the reference (lib/teatgt.py:350-351) unless `differentiable_consistency` is set
+            # (then the semantic loss back-propagates into gat_semantic / gate_sem_nn / the encoder)
+            diff = bool(getattr(self, "differentiable_consistency", False)) and torch.is_grad_enabled()
             out["structure_temp_loss"], out["semantic_temp_loss"] = consistency_losses(
-                self.gat, self.gat_semantic, self.gate_nn, self.gate_sem_nn, plan, sp, hidden.detach())
+                self.gat, self.gat_semantic, self.gate_nn, self.gate_sem_nn, plan, sp, hidden if diff else hidden.detach(),
+                differentiable=diff)
         else:
             out["structure_temp_loss"] = torch.zeros(0, device=dev)
             out["semantic_temp_loss"] = torch.zeros(0, device=dev)

@@ -456,7 +456,7 @@ class TEMPURA(nn.Module):
         ev.record()
         return tp, sp, (host, ev)
 
-    def _consistency(self, entry, plan, rel_feats, prep):
+    def _consistency(self, entry, plan, rel_feats, prep, differentiable=False):
         """EXTENSION, see __init__: structure / semantic temporal-consistency losses (detached, like
         lib/teatgt.py:350-351) over 5-frame clips.  Graph nodes per frame = person + objects with spatial edges
         by box-centre distance (lib/teatgt.py:199-209); the semantic branch reads the clip's relation-feature
@@ -468,7 +468,8 @@ class TEMPURA(nn.Module):
         clip_pair_off = np.concatenate([[0], np.cumsum(pairs_pc)])
         entry["structure_temp_loss"], entry["semantic_temp_loss"] = consistency_losses(
             self.gat, self.gat_semantic, self.gate_nn, self.gate_sem_nn, tp, sp, rel_feats,
-            clip_first_row=clip_pair_off[clips], clip_rows=pairs_pc[clips], flags_host=flags_host)
+            clip_first_row=clip_pair_off[clips], clip_rows=pairs_pc[clips], flags_host=flags_host,
+            differentiable=differentiable)
 
     # ------------------------------------------------------------------------------------------
     def forward(self, entry, phase="train", unc=False):
@@ -514,7 +515,8 @@ class TEMPURA(nn.Module):
         if cons_prep is not None:
             # LAST: the regulariser ends with a data-dependent filter (KL >= 0, lib/teatgt.py:327-333) that synchronises
             # the host; everything else of the forward is already queued behind it on the device by then
-            self._consistency(entry, plan, mixed.detach(), cons_prep)
+            diff = bool(getattr(self, "differentiable_consistency", False)) and torch.is_grad_enabled()
+            self._consistency(entry, plan, mixed if diff else mixed.detach(), cons_prep, differentiable=diff)
         return entry
 
 

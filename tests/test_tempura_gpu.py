@@ -396,3 +396,68 @@ def test_contrastive_relation_losses_batch_equals_per_video_restatement(pair):
     (ref_s + ref_c).backward()
     assert abs(got["spatial_con_loss"].item() - ref_s.item()) <= 1e-5 and abs(got["contact_con_loss"].item() - ref_c.item()) <= 1e-5
     assert (spa.grad.cpu() - sc.grad).abs().max().item() <= 1e-5 and (con.grad.cpu() - cc.grad).abs().max().item() <= 1e-5
+
+
+def test_differentiable_consistency_gradients_match_oracle_autograd(cuda_lib):
+    """`differentiable_consistency=True` (the reference detaches both vectors, lib/teatgt.py:350-351): the
+    semantic temporal-consistency loss back-propagates through attention pooling, the 4-layer GraphTransformer (hand-written
+    backward kernels + tcgen05 dgrad / wgrad GEMMs) into gat_semantic / gate_sem_nn — compared with autograd through the
+    oracle's restatement fed with the CUDA path's own relation features (PARITY UNPINNED like the forward) — and on into the
+    relation path (some transformer weight must receive a gradient from this loss alone).  rel-L2 <= 8e-2 per tensor (bf16
+    GEMM operands through four layers at width 1936)."""
+    import torch.nn as nn
+    from b200vsgg import synthetic, tempura
+    from oracle import ref_shims
+    from oracle.teatgt_oracle import tempura_consistency
+    gold = torch.load(os.path.join(GOLDEN, "tempura_small.pt"), weights_only=False)
+    classes = synthetic.ag_object_classes()
+    m = tempura.TEMPURA(obj_classes=classes, consistency_regulariser=True, **gold["model_kw"])
+    synthetic.seeded_init_(m, 3)
+    gat = ref_shims.GraphTransformer(dim=10, depth=4, edge_dim=1, with_feedforwards=True, gated_residual=True, rel_pos_emb=True)
+    gat_sem = ref_shims.GraphTransformer(dim=1936, depth=4, edge_dim=1, with_feedforwards=True, gated_residual=True,
+                                         rel_pos_emb=True)
+    gate_nn, gate_sem_nn = nn.Linear(10, 1), nn.Linear(1936, 1)
+    gat.load_state_dict(m.gat.state_dict(), strict=True)
+    gat_sem.load_state_dict(m.gat_semantic.state_dict(), strict=True)
+    gate_nn.load_state_dict(m.gate_nn.state_dict())
+    gate_sem_nn.load_state_dict(m.gate_sem_nn.state_dict())
+    m = m.cuda().train()
+    m.dropout_p = 0.0
+    m.differentiable_consistency = True
+    cases = [(70, 9, (2, 5)), (71, 6, (1, 4))]
+    entries = [synthetic.make_video_entry(*c) for c in cases]
+    out = m(tempura.collate_entries([_clone(e, "cuda") for e in entries]), phase="train")
+    assert out["semantic_temp_loss"].requires_grad and not out["structure_temp_loss"].requires_grad
+    (1000.0 * out["semantic_temp_loss"].sum()).backward()
+    feats = out["rel_mem_features"].detach().float().cpu().requires_grad_(True)
+    total, p0 = 0.0, 0
+    for e in entries:
+        n = e["pair_idx"].shape[0]
+        e = dict(e, pred_labels=e["labels"])
+        _, m_ = tempura_consistency(e, feats[p0:p0 + n], gat, gat_sem, gate_nn, gate_sem_nn)
+        total = total + sum(m_)
+        p0 += n
+    (1000.0 * total).backward()
+    ref = dict(("gat_semantic." + k, v) for k, v in gat_sem.named_parameters())
+    ref.update(("gate_sem_nn." + k, v) for k, v in gate_sem_nn.named_parameters())
+    got = dict(m.named_parameters())
+    errs = []
+    for name, r in ref.items():
+        g = got[name].grad
+        assert g is not None, name
+        rn = r.grad.norm().item()
+        if name == "gate_sem_nn.bias" or rn < 1e-9:
+            # structurally zero: a bias added to every gate logit of a frame cancels in the softmax — what both sides
+            # hold there is rounding residue of different summation orders
+            assert g.norm().item() <= 1e-3 * got["gate_sem_nn.weight"].grad.norm().item() + 1e-6, (name, g.norm().item())
+            continue
+        errs.append(((g.float().cpu() - r.grad).norm().item() / rn, name))
+    errs.sort(reverse=True)
+    print("largest differentiable-consistency gradient rel-L2 errors:", errs[:6])
+    assert len(errs) >= 60
+    for rel, name in errs:
+        assert rel <= 8e-2, (name, rel, errs[:6])
+    # the loss reaches the relation path itself
+    w = m.glocal_transformer.global_attention.layers[0].linear1.weight.grad if hasattr(m.glocal_transformer, "global_attention") else None
+    assert w is not None and w.abs().max().item() > 0
+    assert all(p.grad is None for n_, p in m.named_parameters() if n_.startswith("gat.") or n_.startswith("gate_nn."))
