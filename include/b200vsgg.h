@@ -335,6 +335,23 @@ int b200vsgg_graph_attn_core_bwd(const float* qkv, int32_t ld, const int32_t* no
                                  const float* we, const float* be, const float* dout, int32_t ldd, int32_t n_frames,
                                  float* dqkv, int32_t ldg, float* dwe, float* dbe, void* stream);
 
+/* SIMT fp32 helpers for the 10-wide structure branch of the regulariser in differentiable mode (its linears have K = 10 or
+ * N = 10; the default detached mode runs the whole branch in one launch, b200vsgg_graph_small_fwd):
+ *   simt_linear : y[r,o] = act(sum_i x[r,i] * w[o*so + i*si] + b[o])  (so/si select W or W^T; act 0 / 2 = GELU;
+ *                 z_out optionally receives the pre-activation)
+ *   simt_wgrad  : dw[o,i] += sum_r dy[r,o] x[r,i]
+ *   gelu_bwd    : dz = dy * gelu'(z)
+ *   ln_small_*  : LayerNorm over d <= 32 columns, forward (saves mean / rstd) and backward (dx = base + ..., dgamma/dbeta +=) */
+int b200vsgg_simt_linear(const float* x, int32_t ldx, const float* w, int32_t so, int32_t si, const float* b, int64_t rows,
+                         int32_t n_out, int32_t n_in, int32_t act, float* y, int32_t ldy, float* z_out, void* stream);
+int b200vsgg_simt_wgrad(const float* dy, int32_t ldd, const float* x, int32_t ldx, int32_t rows, int32_t n_out, int32_t n_in,
+                        float* dw, void* stream);
+int b200vsgg_gelu_bwd(const float* dy, const float* z, int64_t n, float* dz, void* stream);
+int b200vsgg_ln_small_fwd(const float* x, const float* g, const float* b, int32_t rows, int32_t d, float* y, float* mean,
+                          float* rstd, void* stream);
+int b200vsgg_ln_small_bwd(const float* dy, const float* x, const float* g, const float* mean, const float* rstd,
+                          const float* base, int32_t rows, int32_t d, float* dx, float* dgamma, float* dbeta, void* stream);
+
 /* GlobalAttentionPooling of the regulariser (lib/teatgt.py:319-320, dgl.nn.GlobalAttentionPooling with gate_nn =
  * Linear(d, 1)): per frame a = softmax_i(w . x_i + b), out[f] = sum_i a_i x_i.  x fp32 [rows, d] compact node rows,
  * node_off int32 [frames+1], max_nodes <= 64, out fp32 [frames, d].  One CTA per frame. */
@@ -347,6 +364,9 @@ int b200vsgg_attn_pool(const float* x, int32_t d, const int32_t* node_off, int32
  * matrices of b200vsgg_teat_pair_flags; out bf16 [rows, 512]. */
 int b200vsgg_graph_attn_core(const float* qkv, int32_t ld, const int32_t* node_off, const uint8_t* upper, int32_t nmax,
                              const float* we, const float* be, int32_t n_frames, void* out, int32_t ldo, void* stream);
+/* Same, fp32 output (the structure branch of the differentiable mode keeps fp32 throughout). */
+int b200vsgg_graph_attn_core_f32(const float* qkv, int32_t ld, const int32_t* node_off, const uint8_t* upper, int32_t nmax,
+                                 const float* we, const float* be, int32_t n_frames, float* out, int32_t ldo, void* stream);
 /* GatedResidual: res <- o*g + res*(1-g), g = sigmoid(W [o, res, o-res]); w fp32 [3*dim]. */
 int b200vsgg_gated_residual(const float* o, float* res, const float* w, int32_t rows, int32_t dim, void* stream);
 

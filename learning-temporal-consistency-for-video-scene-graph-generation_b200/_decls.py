@@ -64,6 +64,7 @@ SIGNATURES = {
     "b200vsgg_teat_assemble_fwd": [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "b200vsgg_teat_assemble_bwd": [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "b200vsgg_graph_attn_core": [vp, i32, vp, vp, i32, vp, vp, i32, vp, i32, vp],
+    "b200vsgg_graph_attn_core_f32": [vp, i32, vp, vp, i32, vp, vp, i32, vp, i32, vp],
     "b200vsgg_gated_residual": [vp, vp, vp, i32, i32, vp],
     "b200vsgg_grad_sqnorm": [vp, vp, vp, i32, i32, vp, vp],
     "b200vsgg_adamw_clip_step": [vp, vp, vp, i32, i32, vp, f32, f32, f32, f32, f32, f32, vp],
@@ -79,6 +80,11 @@ SIGNATURES = {
     "b200vsgg_weighted_colsum": [vp, i32, i32, i32, i32, vp, vp, vp],
     "b200vsgg_gated_residual_bwd": [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp],
     "b200vsgg_graph_attn_core_bwd": [vp, i32, vp, vp, i32, vp, vp, vp, i32, i32, vp, i32, vp, vp, vp],
+    "b200vsgg_simt_linear": [vp, i32, vp, i32, i32, vp, i64, i32, i32, i32, vp, i32, vp, vp],
+    "b200vsgg_simt_wgrad": [vp, i32, vp, i32, i32, i32, i32, vp, vp],
+    "b200vsgg_gelu_bwd": [vp, vp, i64, vp, vp],
+    "b200vsgg_ln_small_fwd": [vp, vp, vp, i32, i32, vp, vp, vp, vp],
+    "b200vsgg_ln_small_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp],
     "b200vsgg_attn_pool": [vp, i32, vp, i32, i32, vp, vp, vp, vp],
     "b200vsgg_class_memory_accumulate": [vp, i32, i32, vp, vp, vp, i32, i32, vp, vp],
     "b200vsgg_interval_kl": [vp, i32, vp, vp, i32, vp, vp],

@@ -3,6 +3,7 @@
 // per-frame graph embeddings g [frames, D].  One warp per pair: both rows are read once with 128-bit
 // loads, the two log-sum-exps and the weighted difference are warp-shuffle reductions.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdint>
 
 #include "../../include/b200vsgg.h"
@@ -52,11 +53,12 @@ __global__ void consistency_kl_kernel(const float* __restrict__ g, int D, const 
 // shared memory; every dot product is a warp-shuffle reduction.  A is given as the upper-triangular
 // predicate matrices of b200vsgg_teat_pair_flags (A = U + U^T).
 // ------------------------------------------------------------------------------------------------
+template <bool OUT_F32>
 __global__ void __launch_bounds__(256) graph_attn_core_kernel(const float* __restrict__ qkv, int ld,
                                                               const int32_t* __restrict__ node_off,
                                                               const uint8_t* __restrict__ upper, int nmax,
                                                               const float* __restrict__ we, const float* __restrict__ be,
-                                                              int n_frames, __nv_bfloat16* __restrict__ out, int ldo) {
+                                                              int n_frames, void* __restrict__ out_, int ldo) {
     extern __shared__ float gsm[];
     constexpr int H = 8, DH = 64, INNER = H * DH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -112,8 +114,12 @@ __global__ void __launch_bounds__(256) graph_attn_core_kernel(const float* __res
         }
         ox += pa * w2.x + b2.x;
         oy += pa * w2.y + b2.y;
-        *reinterpret_cast<__nv_bfloat162*>(out + static_cast<size_t>(r0 + i) * ldo + head * DH + d0) =
-            __floats2bfloat162_rn(ox, oy);
+        if (OUT_F32)
+            *reinterpret_cast<float2*>(reinterpret_cast<float*>(out_) + static_cast<size_t>(r0 + i) * ldo + head * DH + d0) =
+                make_float2(ox, oy);
+        else
+            *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(out_) + static_cast<size_t>(r0 + i) * ldo +
+                                               head * DH + d0) = __floats2bfloat162_rn(ox, oy);
     }
 }
 
@@ -161,23 +167,38 @@ __global__ void gated_residual_kernel(const float* __restrict__ o, float* __rest
 
 using namespace vsgg;
 
-extern "C" int b200vsgg_graph_attn_core(const float* qkv, int32_t ld, const int32_t* node_off, const uint8_t* upper,
-                                        int32_t nmax, const float* we, const float* be, int32_t n_frames, void* out,
-                                        int32_t ldo, void* stream) {
+static int graph_attn_core_launch(const float* qkv, int32_t ld, const int32_t* node_off, const uint8_t* upper, int32_t nmax,
+                                  const float* we, const float* be, int32_t n_frames, void* out, int32_t ldo, bool out_f32,
+                                  void* stream) {
     if (!qkv || !node_off || !upper || !we || !be || !out || nmax <= 0 || nmax > 32 || (ld & 1) || (ldo & 1))
         return set_error(B200VSGG_ERR_BAD_ARG, "graph_attn_core: bad arg (<= 32 nodes per frame)");
     if (n_frames == 0) return 0;
     const size_t smem = 8ull * 2 * nmax * 64 * sizeof(float);
-    static size_t cur = 48 * 1024;
-    if (smem > cur) {
-        cudaError_t e = cudaFuncSetAttribute(graph_attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t cur[2] = {48 * 1024, 48 * 1024};
+    if (smem > cur[out_f32]) {
+        cudaError_t e = out_f32 ? cudaFuncSetAttribute(graph_attn_core_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                : cudaFuncSetAttribute(graph_attn_core_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error((int)e, cudaGetErrorString(e));
-        cur = smem;
+        cur[out_f32] = smem;
     }
-    graph_attn_core_kernel<<<n_frames, 256, smem, (cudaStream_t)stream>>>(qkv, ld, node_off, upper, nmax, we, be, n_frames,
-                                                                          (__nv_bfloat16*)out, ldo);
+    if (out_f32)
+        graph_attn_core_kernel<true><<<n_frames, 256, smem, (cudaStream_t)stream>>>(qkv, ld, node_off, upper, nmax, we, be, n_frames, out, ldo);
+    else
+        graph_attn_core_kernel<false><<<n_frames, 256, smem, (cudaStream_t)stream>>>(qkv, ld, node_off, upper, nmax, we, be, n_frames, out, ldo);
     VSGG_CUDA_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int b200vsgg_graph_attn_core(const float* qkv, int32_t ld, const int32_t* node_off, const uint8_t* upper,
+                                        int32_t nmax, const float* we, const float* be, int32_t n_frames, void* out,
+                                        int32_t ldo, void* stream) {
+    return graph_attn_core_launch(qkv, ld, node_off, upper, nmax, we, be, n_frames, out, ldo, false, stream);
+}
+
+extern "C" int b200vsgg_graph_attn_core_f32(const float* qkv, int32_t ld, const int32_t* node_off, const uint8_t* upper,
+                                            int32_t nmax, const float* we, const float* be, int32_t n_frames, float* out,
+                                            int32_t ldo, void* stream) {
+    return graph_attn_core_launch(qkv, ld, node_off, upper, nmax, we, be, n_frames, out, ldo, true, stream);
 }
 
 extern "C" int b200vsgg_gated_residual(const float* o, float* res, const float* w, int32_t rows, int32_t dim,
@@ -471,6 +492,155 @@ graph_attn_core_bwd_kernel(const float* __restrict__ qkv, int ld, const int32_t*
 }
 
 }  // namespace vsgg
+
+// ------------------------------------------------------------------------------------------------
+// SIMT fp32 helpers for the 10-wide STRUCTURE branch in differentiable mode: its linears have K = 10 or N = 10 (nothing a
+// 128-wide tensor-core tile can use) and its LayerNorms have 10 columns.  The default (detached) mode runs the whole
+// branch in ONE launch (graph_small.cu); these kernels exist so that the same network can be evaluated layer by layer
+// with saved activations when its gradient is wanted.
+// ------------------------------------------------------------------------------------------------
+namespace vsgg {
+
+// y[r, o] = act(sum_i x[r, i] * W(o, i) + b[o]),  W(o, i) = w[o * so + i * si]  (so / si choose W or W^T: forward / dgrad)
+__global__ void __launch_bounds__(256)
+simt_linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, int so, int si,
+                   const float* __restrict__ b, long long rows, int n_out, int n_in, int act, float* __restrict__ y, int ldy,
+                   float* __restrict__ z_out) {
+    const long long total = rows * n_out;
+    for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
+        const long long r = idx / n_out;
+        const int o = static_cast<int>(idx - r * n_out);
+        const float* xr = x + r * ldx;
+        float acc = b != nullptr ? __ldg(b + o) : 0.f;
+        for (int i = 0; i < n_in; ++i) acc = fmaf(xr[i], __ldg(w + static_cast<size_t>(o) * so + static_cast<size_t>(i) * si), acc);
+        if (z_out != nullptr) z_out[r * ldy + o] = acc;
+        if (act == 2) acc = 0.5f * acc * (1.f + erff(acc * 0.70710678118654752f));
+        y[r * ldy + o] = acc;
+    }
+}
+
+// dW[o, i] += sum_r dy[r, o] * x[r, i]   (grid.y slabs of rows, one atomic per output and slab)
+__global__ void __launch_bounds__(256)
+simt_wgrad_kernel(const float* __restrict__ dy, int ldd, const float* __restrict__ x, int ldx, int rows, int n_out, int n_in,
+                  float* __restrict__ dw) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= n_out * n_in) return;
+    const int o = idx / n_in, i = idx - o * n_in;
+    const int per = (rows + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+    float acc = 0.f;
+    for (int r = r0; r < r1; ++r) acc = fmaf(dy[static_cast<size_t>(r) * ldd + o], x[static_cast<size_t>(r) * ldx + i], acc);
+    atomicAdd(dw + idx, acc);
+}
+
+// dz = dy * gelu'(z)  (exact erf GELU)
+__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, long long n, float* __restrict__ dz) {
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
+        const float v = z[i];
+        const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752f));
+        dz[i] = dy[i] * (cdf + v * 0.3989422804014327f * __expf(-0.5f * v * v));
+    }
+}
+
+// LayerNorm over <= 32 columns, thread = row
+__global__ void ln_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                                    int rows, int D, float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float* xr = x + static_cast<size_t>(r) * D;
+    float m = 0.f;
+    for (int c = 0; c < D; ++c) m += xr[c];
+    m /= D;
+    float v = 0.f;
+    for (int c = 0; c < D; ++c) { const float d = xr[c] - m; v += d * d; }
+    const float rs = rsqrtf(v / D + 1e-5f);
+    mean[r] = m;
+    rstd[r] = rs;
+    for (int c = 0; c < D; ++c) y[static_cast<size_t>(r) * D + c] = (xr[c] - m) * rs * __ldg(g + c) + __ldg(b + c);
+}
+// dx = base + rstd * (g dy - mean_c(g dy) - xhat mean_c(g dy xhat));  dgamma += sum_r dy xhat,  dbeta += sum_r dy
+__global__ void __launch_bounds__(256)
+ln_small_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ g,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ base, int rows,
+                    int D, float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float sg[32], sb[32];
+    if (threadIdx.x < 32) { sg[threadIdx.x] = 0.f; sb[threadIdx.x] = 0.f; }
+    __syncthreads();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) {
+        const float m = mean[r], rs = rstd[r];
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = 0; c < D; ++c) {
+            const float xh = (x[static_cast<size_t>(r) * D + c] - m) * rs, gd = __ldg(g + c) * dy[static_cast<size_t>(r) * D + c];
+            s1 += gd;
+            s2 += gd * xh;
+        }
+        s1 /= D;
+        s2 /= D;
+        for (int c = 0; c < D; ++c) {
+            const float d = dy[static_cast<size_t>(r) * D + c];
+            const float xh = (x[static_cast<size_t>(r) * D + c] - m) * rs;
+            const float v = rs * (__ldg(g + c) * d - s1 - xh * s2);
+            dx[static_cast<size_t>(r) * D + c] = v + (base != nullptr ? base[static_cast<size_t>(r) * D + c] : 0.f);
+            atomicAdd(&sg[c], d * xh);
+            atomicAdd(&sb[c], d);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < D) { atomicAdd(dgamma + threadIdx.x, sg[threadIdx.x]); atomicAdd(dbeta + threadIdx.x, sb[threadIdx.x]); }
+}
+
+}  // namespace vsgg
+
+extern "C" int b200vsgg_simt_linear(const float* x, int32_t ldx, const float* w, int32_t so, int32_t si, const float* b,
+                                    int64_t rows, int32_t n_out, int32_t n_in, int32_t act, float* y, int32_t ldy, float* z_out,
+                                    void* stream) {
+    if (!x || !w || !y || n_out <= 0 || n_in <= 0) return set_error(B200VSGG_ERR_BAD_ARG, "simt_linear: bad arg");
+    if (rows == 0) return 0;
+    const long long total = rows * n_out;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+    vsgg::simt_linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, so, si, b, rows, n_out, n_in, act, y, ldy, z_out);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200vsgg_simt_wgrad(const float* dy, int32_t ldd, const float* x, int32_t ldx, int32_t rows, int32_t n_out,
+                                   int32_t n_in, float* dw, void* stream) {
+    if (!dy || !x || !dw || n_out <= 0 || n_in <= 0) return set_error(B200VSGG_ERR_BAD_ARG, "simt_wgrad: bad arg");
+    if (rows == 0) return 0;
+    dim3 grid((n_out * n_in + 255) / 256, std::max(1, std::min(64, rows / 128)));
+    vsgg::simt_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, ldd, x, ldx, rows, n_out, n_in, dw);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200vsgg_gelu_bwd(const float* dy, const float* z, int64_t n, float* dz, void* stream) {
+    if (!dy || !z || !dz) return set_error(B200VSGG_ERR_BAD_ARG, "gelu_bwd: bad arg");
+    if (n == 0) return 0;
+    vsgg::gelu_bwd_kernel<<<static_cast<int>(std::min<long long>((n + 255) / 256, 148LL * 16)), 256, 0, (cudaStream_t)stream>>>(dy, z, n, dz);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200vsgg_ln_small_fwd(const float* x, const float* g, const float* b, int32_t rows, int32_t d, float* y,
+                                     float* mean, float* rstd, void* stream) {
+    if (!x || !g || !b || !y || !mean || !rstd || d < 1 || d > 32) return set_error(B200VSGG_ERR_BAD_ARG, "ln_small_fwd: bad arg (d <= 32)");
+    if (rows == 0) return 0;
+    vsgg::ln_small_fwd_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, g, b, rows, d, y, mean, rstd);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200vsgg_ln_small_bwd(const float* dy, const float* x, const float* g, const float* mean, const float* rstd,
+                                     const float* base, int32_t rows, int32_t d, float* dx, float* dgamma, float* dbeta,
+                                     void* stream) {
+    if (!dy || !x || !g || !mean || !rstd || !dx || !dgamma || !dbeta || d < 1 || d > 32)
+        return set_error(B200VSGG_ERR_BAD_ARG, "ln_small_bwd: bad arg (d <= 32)");
+    if (rows == 0) return 0;
+    vsgg::ln_small_bwd_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dy, x, g, mean, rstd, base, rows, d, dx, dgamma, dbeta);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int b200vsgg_attn_pool_bwd(const float* x, int32_t d, const int32_t* node_off, int32_t n_frames, int32_t max_nodes,
                                       const float* w, const float* b, const float* dout, float* dx, float* dgate,

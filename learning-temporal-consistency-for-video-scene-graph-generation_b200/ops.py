@@ -592,10 +592,10 @@ def consistency_kl(g, pair_u, pair_v):
 
 def graph_attn_core(qkv, node_off, upper, nmax, we, be, out):
     assert qkv.dtype == torch.float32 and qkv.stride(1) == 1 and upper.dtype == torch.uint8 and upper.is_contiguous()
-    assert we.is_contiguous() and be.is_contiguous() and out.dtype == torch.bfloat16
-    check(_lib.lib().b200vsgg_graph_attn_core(_ptr(qkv), qkv.stride(0), _ptr(node_off), _ptr(upper), nmax, _ptr(_f32(we)),
-                                               _ptr(_f32(be)), node_off.numel() - 1, _ptr(out), out.stride(0), _stream()),
-          "graph_attn_core")
+    assert we.is_contiguous() and be.is_contiguous() and out.dtype in (torch.bfloat16, torch.float32)
+    fn = _lib.lib().b200vsgg_graph_attn_core if out.dtype == torch.bfloat16 else _lib.lib().b200vsgg_graph_attn_core_f32
+    check(fn(_ptr(qkv), qkv.stride(0), _ptr(node_off), _ptr(upper), nmax, _ptr(_f32(we)), _ptr(_f32(be)),
+             node_off.numel() - 1, _ptr(out), out.stride(0), _stream()), "graph_attn_core")
     _count()
 
 
@@ -874,3 +874,49 @@ def graph_attn_core_bwd(qkv, node_off, upper, nmax, we, be, dout, dqkv, dwe, dbe
                                                    _ptr(be), _ptr(dout), dout.stride(0), node_off.numel() - 1, _ptr(dqkv),
                                                    dqkv.stride(0), _ptr(dwe), _ptr(dbe), _stream()), "graph_attn_core_bwd")
     _count()
+
+
+def simt_linear(x, w, b=None, transposed=False, act=ACT_NONE, want_z=False):
+    """fp32 y = act(x @ W^T + b) (transposed=False, w [out, in]) or x @ W (transposed=True: the dgrad of that linear)."""
+    assert x.dtype == torch.float32 and x.stride(1) == 1 and w.dtype == torch.float32 and w.is_contiguous()
+    n_out, n_in = (w.shape[1], w.shape[0]) if transposed else (w.shape[0], w.shape[1])
+    assert x.shape[1] == n_in
+    so, si = (1, w.shape[1]) if transposed else (w.shape[1], 1)
+    y = torch.empty(x.shape[0], n_out, device=x.device)
+    z = torch.empty_like(y) if want_z else None
+    check(_lib.lib().b200vsgg_simt_linear(_ptr(x), x.stride(0), _ptr(w), so, si, _ptr(b), x.shape[0], n_out, n_in, act, _ptr(y),
+                                           n_out, _ptr(z), _stream()), "simt_linear")
+    _count()
+    return (y, z) if want_z else y
+
+
+def simt_wgrad(dy, x):
+    dw = torch.zeros(dy.shape[1], x.shape[1], device=x.device)
+    check(_lib.lib().b200vsgg_simt_wgrad(_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), x.shape[0], dy.shape[1], x.shape[1],
+                                          _ptr(dw), _stream()), "simt_wgrad")
+    _count()
+    return dw
+
+
+def gelu_bwd(dy, z):
+    dz = torch.empty_like(z)
+    check(_lib.lib().b200vsgg_gelu_bwd(_ptr(dy), _ptr(z), z.numel(), _ptr(dz), _stream()), "gelu_bwd")
+    _count()
+    return dz
+
+
+def ln_small_fwd(x, g, b):
+    y, mean, rstd = torch.empty_like(x), torch.empty(x.shape[0], device=x.device), torch.empty(x.shape[0], device=x.device)
+    check(_lib.lib().b200vsgg_ln_small_fwd(_ptr(x), _ptr(g), _ptr(b), x.shape[0], x.shape[1], _ptr(y), _ptr(mean), _ptr(rstd),
+                                            _stream()), "ln_small_fwd")
+    _count()
+    return y, mean, rstd
+
+
+def ln_small_bwd(dy, x, g, mean, rstd, base=None):
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(x.shape[1], device=x.device), torch.zeros(x.shape[1], device=x.device)
+    check(_lib.lib().b200vsgg_ln_small_bwd(_ptr(dy), _ptr(x), _ptr(g), _ptr(mean), _ptr(rstd), _ptr(base), x.shape[0],
+                                            x.shape[1], _ptr(dx), _ptr(dg), _ptr(db), _stream()), "ln_small_bwd")
+    _count()
+    return dx, dg, db

@@ -2,7 +2,9 @@
 lib/teatgt.py:285-334, 350-351 of the reference), batched over every frame of every clip.
 
 As released, the reference detaches both loss vectors (`torch.tensor(list_of_scalars)`,
-lib/teatgt.py:350-351), so they carry no gradient; this implementation is forward-only to match.
+lib/teatgt.py:350-351), so they carry no gradient; that is the default here too.  `differentiable=True`
+(`model.differentiable_consistency`) evaluates the same networks layer by layer with saved
+activations and a hand-orchestrated backward (second half of this file).
 
 Per frame: spatial-only graph -> normalised Laplacian -> eigenvectors (host LAPACK, the reference's call
 :300) -> first 10 columns -> GraphTransformer(dim 10) -> attention pooling -> structure embedding [10];
@@ -261,6 +263,92 @@ class _GraphTransformerFn(torch.autograd.Function):
         return (dx, None, None, None, None, None, *grads)
 
 
+class _SmallGraphTransformerFn(torch.autograd.Function):
+    """The 10-wide STRUCTURE branch, layer by layer in fp32 with saved activations (SIMT linears / LayerNorms of
+    csrc/consistency.cu around the same attention-core and gated-residual kernels).  Only the differentiable mode uses it;
+    the default mode evaluates the branch in one launch (b200vsgg_graph_small_fwd).  The node features are constants
+    (Laplacian eigenvectors), so no gradient is returned for them."""
+
+    @staticmethod
+    def forward(ctx, x, node_off, upper, nmax, heads, dim_head, *params):
+        R, dim = x.shape
+        inner = heads * dim_head
+        x = x.detach().contiguous().float().clone()
+        saved = []
+        for li in range(len(params) // _PER_LAYER):
+            (ln1w, ln1b, qw, qb, kvw, kvb, ew, eb, ow, ob, g1, ln2w, ln2b, f1w, f1b, f2w, f2b, g2) = \
+                [t.detach().contiguous().float() for t in params[li * _PER_LAYER:(li + 1) * _PER_LAYER]]
+            x_in = x.clone()
+            xn, mean1, rstd1 = ops.ln_small_fwd(x, ln1w, ln1b)
+            wqkv = torch.cat([qw, kvw], 0).contiguous()
+            qkv = ops.simt_linear(xn, wqkv, torch.cat([qb, kvb]).contiguous())
+            att = torch.empty(R, inner, device=x.device)
+            we, be = ew[:, 0].contiguous(), eb
+            ops.graph_attn_core(qkv, node_off, upper, nmax, we, be, att)
+            o1 = ops.simt_linear(att, ow, ob)
+            ops.gated_residual(o1, x, g1.reshape(-1).contiguous())
+            x_mid = x.clone()
+            xn2, mean2, rstd2 = ops.ln_small_fwd(x, ln2w, ln2b)
+            hid, z = ops.simt_linear(xn2, f1w, f1b, act=ops.ACT_GELU, want_z=True)
+            o2 = ops.simt_linear(hid, f2w, f2b)
+            ops.gated_residual(o2, x, g2.reshape(-1).contiguous())
+            saved.append(dict(x_in=x_in, xn=xn, mean1=mean1, rstd1=rstd1, wqkv=wqkv, qkv=qkv, att=att, we=we, be=be, ow=ow,
+                              o1=o1, g1=g1, x_mid=x_mid, xn2=xn2, mean2=mean2, rstd2=rstd2, f1w=f1w, f2w=f2w, z=z, hid=hid,
+                              o2=o2, g2=g2, ln1w=ln1w, ln2w=ln2w))
+        ctx.saved, ctx.geom, ctx.n_params = saved, (node_off, upper, nmax, heads, dim_head), len(params)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        node_off, upper, nmax, heads, dim_head = ctx.geom
+        saved = ctx.saved
+        ctx.saved = None
+        dev = dx.device
+        inner = heads * dim_head
+        R, dim = dx.shape
+        zeros = lambda *shape: torch.zeros(*shape, device=dev)
+        grads = [None] * ctx.n_params
+        dx = dx.contiguous().float()
+
+        def colsum(t):
+            out = zeros(1, t.shape[1])
+            ops.colsum(t.contiguous(), out)
+            return out[0]
+
+        def gate_bwd(o, res, gw, dxx):
+            d_o, d_res, da = torch.empty_like(o), torch.empty_like(o), torch.empty(R, device=dev)
+            ops.gated_residual_bwd(o, res, gw.reshape(-1).contiguous(), dxx, d_o, d_res, da)
+            dw1, dw2 = zeros(dim), zeros(dim)
+            ops.weighted_colsum(o, da, dw1)
+            ops.weighted_colsum(res, da, dw2)
+            return d_o, d_res, torch.cat([dw1, dw2, dw1 - dw2]).view(1, 3 * dim)
+
+        for li in reversed(range(len(saved))):
+            S = saved[li]
+            base = li * _PER_LAYER
+            d_o2, d_mid_skip, grads[base + 17] = gate_bwd(S["o2"], S["x_mid"], S["g2"], dx)
+            grads[base + 15], grads[base + 16] = ops.simt_wgrad(d_o2, S["hid"]), colsum(d_o2)
+            dz = ops.gelu_bwd(ops.simt_linear(d_o2, S["f2w"], transposed=True), S["z"])
+            grads[base + 13], grads[base + 14] = ops.simt_wgrad(dz, S["xn2"]), colsum(dz)
+            dxn2 = ops.simt_linear(dz, S["f1w"], transposed=True)
+            d_mid, grads[base + 11], grads[base + 12] = ops.ln_small_bwd(dxn2, S["x_mid"], S["ln2w"], S["mean2"], S["rstd2"],
+                                                                         base=d_mid_skip)
+            d_o1, d_in_skip, grads[base + 10] = gate_bwd(S["o1"], S["x_in"], S["g1"], d_mid)
+            grads[base + 8], grads[base + 9] = ops.simt_wgrad(d_o1, S["att"]), colsum(d_o1)
+            datt = ops.simt_linear(d_o1, S["ow"], transposed=True)
+            dqkv, dwe, dbe = torch.empty(R, 3 * inner, device=dev), zeros(inner), zeros(inner)
+            ops.graph_attn_core_bwd(S["qkv"], node_off, upper, nmax, S["we"], S["be"], datt, dqkv, dwe, dbe)
+            grads[base + 6], grads[base + 7] = dwe.view(inner, 1), dbe
+            dWqkv, dbqkv = ops.simt_wgrad(dqkv, S["xn"]), colsum(dqkv)
+            grads[base + 2], grads[base + 3] = dWqkv[:inner], dbqkv[:inner]
+            grads[base + 4], grads[base + 5] = dWqkv[inner:], dbqkv[inner:]
+            dxn = ops.simt_linear(dqkv, S["wqkv"], transposed=True)
+            dx, grads[base + 0], grads[base + 1] = ops.ln_small_bwd(dxn, S["x_in"], S["ln1w"], S["mean1"], S["rstd1"],
+                                                                    base=d_in_skip)
+            saved[li] = None
+        return (None, None, None, None, None, None, *grads)
+
+
 class _AttnPoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, node_off, n_frames, nmax, w, b):
@@ -308,9 +396,9 @@ def _pool_compact(x, node_off, n_frames, nmax, gate_nn):
 
 def consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_flags, hidden, clip_first_row=None,
                        clip_rows=None, flags_host=None, differentiable=False):
-    """differentiable=False (default, the reference's behaviour: both vectors detached).  differentiable=True: the SEMANTIC
-    loss vector carries gradients into gat_semantic, gate_sem_nn and `hidden` (pass it un-detached); the structure branch
-    reads constant Laplacian eigenvectors and stays detached (its single-CTA kernel has no backward)."""
+    """differentiable=False (default, the reference's behaviour: both vectors detached).  differentiable=True: both loss
+    vectors carry gradients — the semantic one into gat_semantic, gate_sem_nn and `hidden` (pass it un-detached), the
+    structure one into gat and gate_nn (its node features are constant Laplacian eigenvectors)."""
     if not differentiable:
         with torch.no_grad():
             return _consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_flags, hidden.detach(),
@@ -392,9 +480,16 @@ def _consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_f
     counts = up_(counts_h)
     nodes = up_(ev)
     # R1 in one launch: 4-layer GraphTransformer(dim 10) + attention pooling, one CTA per frame
-    sym = ops.graph_small_fwd(nodes, spatial_flags.contiguous(), counts.int(), gat.dim, gat.heads, len(gat.layers),
-                              pack_small_params(gat), gate_nn.weight.detach().reshape(-1).contiguous(),
-                              gate_nn.bias.detach().contiguous())
+    if differentiable:
+        # same network, layer by layer with saved activations: compact node rows in frame order
+        rows = ev[np.arange(nmax)[None, :] < counts_h[:, None]]
+        st_rows = _SmallGraphTransformerFn.apply(up_(rows), plan.node_off, spatial_flags.contiguous(), nmax, gat.heads,
+                                                 gat.dim_head, *_layer_params(gat))
+        sym = _AttnPoolFn.apply(st_rows, plan.node_off, F_, nmax, gate_nn.weight, gate_nn.bias)
+    else:
+        sym = ops.graph_small_fwd(nodes, spatial_flags.contiguous(), counts.int(), gat.dim, gat.heads, len(gat.layers),
+                                  pack_small_params(gat), gate_nn.weight.detach().reshape(-1).contiguous(),
+                                  gate_nn.bias.detach().contiguous())
     # ---- R3: all frame pairs u < v inside each clip, reference order
     pu, pv = [], []
     frames_pc = np.bincount(plan.clip_of_frame, minlength=plan.n_clips)
@@ -409,9 +504,10 @@ def _consistency_losses(gat, gat_semantic, gate_nn, gate_sem_nn, plan, spatial_f
         f0 += int(nf)
     pu = up_(np.concatenate(pu).astype(np.int32))
     pv = up_(np.concatenate(pv).astype(np.int32))
-    with torch.no_grad():
-        s = ops.consistency_kl(sym.contiguous(), pu, pv)
-    m = _ConsistencyKLFn.apply(sem, pu, pv) if differentiable else ops.consistency_kl(sem.contiguous(), pu, pv)
+    if differentiable:
+        s, m = _ConsistencyKLFn.apply(sym, pu, pv), _ConsistencyKLFn.apply(sem, pu, pv)
+    else:
+        s, m = ops.consistency_kl(sym.contiguous(), pu, pv), ops.consistency_kl(sem.contiguous(), pu, pv)
     # the reference keeps a pair only if its score is >= 0 (lib/teatgt.py:327-333): a data-dependent length, hence a host
     # synchronisation — ONE flag for both branches; the usual case (no negative rounding residue) returns the kernels'
     # outputs as they are, without any gather

@@ -309,3 +309,41 @@ def test_video_chunk_pipeline_equals_single_pass(pair):
         if ref > 1e-7 and not n.endswith("k_proj.bias"):
             tol = QK_GRAD_REL_TOL if (".q_proj." in n or ".k_proj." in n) else GRAD_REL_TOL
             assert (g - b["grads"][n]).norm().item() <= tol * ref, n
+
+
+def test_differentiable_consistency_reaches_the_encoder(pair):
+    """TEAT-GT with `differentiable_consistency=True`: the two loss vectors keep the detached mode's values,
+    carry gradients into gat / gat_semantic / the gates, and the semantic one reaches the TokenGT encoder through hidden_x
+    (the numeric gradient check against the oracle's autograd lives in tests/test_tempura_gpu.py, same kernels)."""
+    from b200vsgg import tempura
+    m, _ = pair
+    e = _entry(dict(video_index=91, num_frames=9, pairs_per_frame=(2, 5)), "cuda")
+    m.train()
+    m.dropout_p, m.eig_dropout = 0.0, 0.0
+    try:
+        with torch.no_grad():
+            det = m(tempura.collate_entries([dict(e)]), phase="train")
+        m.differentiable_consistency = True
+        m.zero_grad(set_to_none=True)
+        out = m(tempura.collate_entries([dict(e)]), phase="train")
+        for key, rtol in (("structure_temp_loss", 2e-3), ("semantic_temp_loss", 5e-2)):
+            assert out[key].requires_grad
+            # pairs with coinciding embeddings (KL = +-1e-11) fall on either side of the reference's `>= 0` filter:
+            # compare the values above a floor, which keep their order
+            a, b = out[key].detach(), det[key]
+            floor = 1e-3 * b.abs().max().item()
+            a, b = a[a > floor], b[b > floor]
+            assert a.shape == b.shape and a.numel() > 0, (key, a.shape, b.shape)
+            assert (a - b).abs().max().item() <= rtol * b.abs().max().item() + 1e-7, key
+        (out["semantic_temp_loss"].sum() + out["structure_temp_loss"].sum()).backward()
+        named = dict(m.named_parameters())
+        for prefix in ("gat.", "gat_semantic.", "gate_nn.weight", "gate_sem_nn.weight"):
+            gs = [p.grad for n, p in named.items() if n.startswith(prefix)]
+            assert gs and all(g is not None and torch.isfinite(g).all().item() for g in gs), prefix
+            assert max(g.abs().max().item() for g in gs) > 0, prefix
+        enc = [p.grad for n, p in named.items() if n.startswith("TokenGT_encoder.") and p.grad is not None]
+        assert enc and max(g.abs().max().item() for g in enc) > 0
+    finally:
+        m.differentiable_consistency = False
+        m.dropout_p, m.eig_dropout = 0.1, 0.2
+        m.eval()

@@ -399,12 +399,12 @@ def test_contrastive_relation_losses_batch_equals_per_video_restatement(pair):
 
 
 def test_differentiable_consistency_gradients_match_oracle_autograd(cuda_lib):
-    """`differentiable_consistency=True` (the reference detaches both vectors, lib/teatgt.py:350-351): the
-    semantic temporal-consistency loss back-propagates through attention pooling, the 4-layer GraphTransformer (hand-written
-    backward kernels + tcgen05 dgrad / wgrad GEMMs) into gat_semantic / gate_sem_nn — compared with autograd through the
-    oracle's restatement fed with the CUDA path's own relation features (PARITY UNPINNED like the forward) — and on into the
-    relation path (some transformer weight must receive a gradient from this loss alone).  rel-L2 <= 8e-2 per tensor (bf16
-    GEMM operands through four layers at width 1936)."""
+    """`differentiable_consistency=True` (the reference detaches both vectors, lib/teatgt.py:350-351): both
+    temporal-consistency losses back-propagate through the pairwise KL, attention pooling and the 4-layer GraphTransformers
+    (hand-written backward kernels; tcgen05 dgrad / wgrad GEMMs for the 1936-wide semantic branch, fp32 SIMT kernels for the
+    10-wide structure branch) into gat / gate_nn / gat_semantic / gate_sem_nn — compared with autograd through the oracle's
+    restatement fed with the CUDA path's own relation features (PARITY UNPINNED like the forward) — and on into the relation
+    path (some transformer weight must receive a gradient from these losses alone)."""
     import torch.nn as nn
     from b200vsgg import synthetic, tempura
     from oracle import ref_shims
@@ -427,37 +427,52 @@ def test_differentiable_consistency_gradients_match_oracle_autograd(cuda_lib):
     cases = [(70, 9, (2, 5)), (71, 6, (1, 4))]
     entries = [synthetic.make_video_entry(*c) for c in cases]
     out = m(tempura.collate_entries([_clone(e, "cuda") for e in entries]), phase="train")
-    assert out["semantic_temp_loss"].requires_grad and not out["structure_temp_loss"].requires_grad
-    (1000.0 * out["semantic_temp_loss"].sum()).backward()
+    assert out["semantic_temp_loss"].requires_grad and out["structure_temp_loss"].requires_grad
+    # same VALUES as the default (detached, fused) evaluation of the two branches
+    m.differentiable_consistency = False
+    with torch.no_grad():
+        det = m(tempura.collate_entries([_clone(e, "cuda") for e in entries]), phase="train")
+    m.differentiable_consistency = True
+    for key, rtol in (("structure_temp_loss", 2e-3), ("semantic_temp_loss", 5e-2)):
+        a, b = out[key].detach(), det[key]
+        assert not b.requires_grad
+        floor = 1e-3 * b.abs().max().item()         # values at +-1e-11 fall on either side of the `>= 0` filter
+        a, b = a[a > floor], b[b > floor]
+        assert a.shape == b.shape and a.numel() > 0, (key, a.shape, b.shape)
+        assert (a - b).abs().max().item() <= rtol * b.abs().max().item() + 1e-7, key
+    (1000.0 * (out["semantic_temp_loss"].sum() + out["structure_temp_loss"].sum())).backward()
     feats = out["rel_mem_features"].detach().float().cpu().requires_grad_(True)
     total, p0 = 0.0, 0
     for e in entries:
         n = e["pair_idx"].shape[0]
         e = dict(e, pred_labels=e["labels"])
-        _, m_ = tempura_consistency(e, feats[p0:p0 + n], gat, gat_sem, gate_nn, gate_sem_nn)
-        total = total + sum(m_)
+        s_, m_ = tempura_consistency(e, feats[p0:p0 + n], gat, gat_sem, gate_nn, gate_sem_nn)
+        total = total + sum(m_) + sum(s_)
         p0 += n
     (1000.0 * total).backward()
     ref = dict(("gat_semantic." + k, v) for k, v in gat_sem.named_parameters())
     ref.update(("gate_sem_nn." + k, v) for k, v in gate_sem_nn.named_parameters())
+    ref.update(("gat." + k, v) for k, v in gat.named_parameters())
+    ref.update(("gate_nn." + k, v) for k, v in gate_nn.named_parameters())
     got = dict(m.named_parameters())
     errs = []
     for name, r in ref.items():
         g = got[name].grad
         assert g is not None, name
         rn = r.grad.norm().item()
-        if name == "gate_sem_nn.bias" or rn < 1e-9:
+        if name in ("gate_sem_nn.bias", "gate_nn.bias") or rn < 1e-9:
             # structurally zero: a bias added to every gate logit of a frame cancels in the softmax — what both sides
             # hold there is rounding residue of different summation orders
-            assert g.norm().item() <= 1e-3 * got["gate_sem_nn.weight"].grad.norm().item() + 1e-6, (name, g.norm().item())
+            wname = name.replace(".bias", ".weight")
+            assert g.norm().item() <= 1e-3 * got[wname].grad.norm().item() + 1e-6, (name, g.norm().item())
             continue
         errs.append(((g.float().cpu() - r.grad).norm().item() / rn, name))
     errs.sort(reverse=True)
     print("largest differentiable-consistency gradient rel-L2 errors:", errs[:6])
-    assert len(errs) >= 60
+    assert len(errs) >= 120
     for rel, name in errs:
-        assert rel <= 8e-2, (name, rel, errs[:6])
+        # semantic branch: bf16 GEMM operands through four layers at width 1936; structure branch: fp32 SIMT kernels
+        assert rel <= (8e-2 if name.startswith(("gat_semantic.", "gate_sem_nn.")) else 5e-3), (name, rel, errs[:6])
     # the loss reaches the relation path itself
     w = m.glocal_transformer.global_attention.layers[0].linear1.weight.grad if hasattr(m.glocal_transformer, "global_attention") else None
     assert w is not None and w.abs().max().item() > 0
-    assert all(p.grad is None for n_, p in m.named_parameters() if n_.startswith("gat.") or n_.startswith("gate_nn."))
