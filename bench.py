@@ -577,6 +577,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL's CTAs cannot co-reside with the persistent 148-CTA GEMMs (~200 KB of shared memory each): every channel it
+        # opens takes an SM away from the GEMM wave that starts next.  16 CTAs move the 0.37 GB of layer buckets well inside
+        # the backward they overlap with; measured on one 8 x B200 box, same session (profiles/r02_n8_nccl_ctas.txt):
+        # default 47.8 ms/step, 8 CTAs 46.3, 16 CTAs 45.0.
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
