@@ -64,16 +64,19 @@ template <bool A_BF16, bool B_IS_A>
 __global__ void __launch_bounds__(256) seg_colstats_kernel(const void* __restrict__ a_, int lda,
                                                            const __nv_bfloat16* __restrict__ b, int ldb, int cols,
                                                            const int32_t* __restrict__ chunks,
-                                                           float* __restrict__ sum1, float* __restrict__ sum2) {
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int col = (blockIdx.x * 32 + tx) * 8;
+                                                           float* __restrict__ sum1, float* __restrict__ sum2, int cvecs) {
+    // cvecs = column vectors (of 8) per block: 32 for wide matrices; 16 / 8 for the 128- / 64-column activations of the
+    // mask branch, so that all 256 threads load (with a fixed 32 x 8 shape half of them idled on 128 columns: the two
+    // largest launches of the step ran at 58 % of the HBM peak)
+    const int tx = threadIdx.x % cvecs, ty = threadIdx.x / cvecs, phases = 256 / cvecs;
+    const int col = (blockIdx.x * cvecs + tx) * 8;
     const int r0 = chunks[blockIdx.y * 3 + 0], r1 = chunks[blockIdx.y * 3 + 1], g = chunks[blockIdx.y * 3 + 2];
     float s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
     if (col < cols) {
 #pragma unroll 4
-        for (int r = r0 + ty; r < r1; r += 8) {
+        for (int r = r0 + ty; r < r1; r += phases) {
             float av[8], bv[8];
             if (A_BF16) {
                 load_bf16x8(reinterpret_cast<const __nv_bfloat16*>(a_) + static_cast<size_t>(r) * lda + col, av);
@@ -96,18 +99,18 @@ __global__ void __launch_bounds__(256) seg_colstats_kernel(const void* __restric
             }
         }
     }
-    __shared__ float red[2][8][32][9];
+    __shared__ float red[2][256][9];          // [which][phase * cvecs + column vector][element]
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { red[0][ty][tx][j] = s1[j]; red[1][ty][tx][j] = s2[j]; }
+    for (int j = 0; j < 8; ++j) { red[0][threadIdx.x][j] = s1[j]; red[1][threadIdx.x][j] = s2[j]; }
     __syncthreads();
-    // 256 threads reduce 2 x 256 columns over the 8 phases
-    for (int o = threadIdx.x; o < 512; o += 256) {
-        const int which = o >> 8, c = o & 255;
+    // reduce 2 x (cvecs * 8) columns over the row phases
+    const int bcols = cvecs * 8;
+    for (int o = threadIdx.x; o < 2 * bcols; o += 256) {
+        const int which = o / bcols, c = o - which * bcols;
         const int cx = c >> 3, cj = c & 7;
         float s = 0.f;
-#pragma unroll
-        for (int y = 0; y < 8; ++y) s += red[which][y][cx][cj];
-        const int gc = blockIdx.x * 256 + c;
+        for (int y = 0; y < phases; ++y) s += red[which][y * cvecs + cx][cj];
+        const int gc = blockIdx.x * bcols + c;
         if (gc < cols) {
             if (which == 0) atomicAdd(sum1 + static_cast<size_t>(g) * cols + gc, s);
             else if (sum2 != nullptr && (B_IS_A || b != nullptr)) atomicAdd(sum2 + static_cast<size_t>(g) * cols + gc, s);
@@ -409,14 +412,15 @@ extern "C" int b200vsgg_seg_colstats(const void* a, int32_t a_is_bf16, int32_t l
         return set_error(B200VSGG_ERR_BAD_ARG, "seg_colstats: bad arg (cols % 8 == 0 required)");
     if (n_chunks == 0) return 0;
     if (n_chunks > 65535) return set_error(B200VSGG_ERR_BAD_ARG, "seg_colstats: more than 65535 chunks");
-    dim3 grid((cols + 255) / 256, n_chunks);
+    const int cvecs = cols >= 256 ? 32 : (cols > 64 ? 16 : 8);
+    dim3 grid((cols + cvecs * 8 - 1) / (cvecs * 8), n_chunks);
     const __nv_bfloat16* bb = (const __nv_bfloat16*)b;
     cudaStream_t st = (cudaStream_t)stream;
     const bool same = (b == a);
-    if (a_is_bf16 && same) seg_colstats_kernel<true, true><<<grid, 256, 0, st>>>(a, lda, bb, ldb, cols, chunks, sum1, sum2);
-    else if (a_is_bf16) seg_colstats_kernel<true, false><<<grid, 256, 0, st>>>(a, lda, bb, ldb, cols, chunks, sum1, sum2);
-    else if (same) seg_colstats_kernel<false, true><<<grid, 256, 0, st>>>(a, lda, bb, ldb, cols, chunks, sum1, sum2);
-    else seg_colstats_kernel<false, false><<<grid, 256, 0, st>>>(a, lda, bb, ldb, cols, chunks, sum1, sum2);
+    if (a_is_bf16 && same) seg_colstats_kernel<true, true><<<grid, 256, 0, st>>>(a, lda, bb, ldb, cols, chunks, sum1, sum2, cvecs);
+    else if (a_is_bf16) seg_colstats_kernel<true, false><<<grid, 256, 0, st>>>(a, lda, bb, ldb, cols, chunks, sum1, sum2, cvecs);
+    else if (same) seg_colstats_kernel<false, true><<<grid, 256, 0, st>>>(a, lda, bb, ldb, cols, chunks, sum1, sum2, cvecs);
+    else seg_colstats_kernel<false, false><<<grid, 256, 0, st>>>(a, lda, bb, ldb, cols, chunks, sum1, sum2, cvecs);
     VSGG_CUDA_CHECK_LAUNCH();
     return 0;
 }
