@@ -5,6 +5,7 @@
 // statistics (the reference's batch IS one video, so statistics are segmented by video), the fused
 // BN-apply + max-pool, and the BN/ReLU backward.  All tensors are NHWC rows, bf16, 128-bit accesses.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cuda_bf16.h>
 #include <cstdint>
 
@@ -35,6 +36,33 @@ __global__ void __launch_bounds__(256) mask_im2col_kernel(const T* __restrict__ 
     __syncthreads();
     const int vec_per_row = ld >> 3;
     __nv_bfloat16* dst = out + static_cast<size_t>(p) * 196 * ld;
+    if (256 % vec_per_row == 0) {
+        // a thread keeps ONE column vector for all its rows: the (channel, kh, kw) decomposition of its 8 columns is done
+        // once instead of per element (the divisions were ~25 integer instructions per element: the kernel was ALU-bound
+        // at 29 % of its store bandwidth)
+        const int v = threadIdx.x % vec_per_row, rstep = 256 / vec_per_row;
+        int off[8], kh[8], kw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = v * 8 + j;
+            const int c = col / 49, r = col - c * 49;
+            kh[j] = col < 98 ? r / 7 : 100;                      // 100: never inside the image -> 0
+            kw[j] = r - (r / 7) * 7;
+            off[j] = c * 729 + kh[j] * 27 + kw[j];
+        }
+        for (int row = threadIdx.x / vec_per_row; row < 196; row += rstep) {
+            const int oh = row / 14, ow = row - oh * 14;
+            const int h0 = oh * 2 - 3, w0 = ow * 2 - 3, base = h0 * 27 + w0;
+            float vals[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned ih = static_cast<unsigned>(h0 + kh[j]), iw = static_cast<unsigned>(w0 + kw[j]);
+                vals[j] = (ih < 27u && iw < 27u) ? sm[base + off[j]] : 0.f;
+            }
+            store_bf16x8(dst + static_cast<size_t>(row) * ld + v * 8, vals);
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < 196 * vec_per_row; i += blockDim.x) {
         const int row = i / vec_per_row, v = i - row * vec_per_row;
         const int oh = row / 14, ow = row - oh * 14;
@@ -356,6 +384,27 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __r
     }
 }
 
+// Same, for C / 8 in {8, 16, 32} and fewer than 2^32 / 9 rows: VEC lanes copy the C contiguous channels of one (row, tap)
+// — 32-bit index arithmetic, one division by 9 and two by hw per (row, tap) instead of five 64-bit div / mod per 16 bytes
+// (the kernel above was ALU-bound at 43 % of its store bandwidth).
+template <int VEC>
+__global__ void __launch_bounds__(256) im2col3x3_fast_kernel(const __nv_bfloat16* __restrict__ z, unsigned rows, int hw,
+                                                             __nv_bfloat16* __restrict__ out) {
+    constexpr int C = VEC * 8, PER = 256 / VEC;              // (row, tap) items per block iteration
+    const unsigned sub = threadIdx.x / VEC, lane = threadIdx.x % VEC;
+    const unsigned total = rows * 9u;
+    for (unsigned j = blockIdx.x * PER + sub; j < total; j += gridDim.x * PER) {
+        const unsigned row = j / 9u, k = j - row * 9u;
+        const unsigned prow = row / hw, ow = row - prow * hw;           // prow = p * hw + oh
+        const unsigned oh = prow % hw;
+        const int ih = static_cast<int>(oh) - 1 + static_cast<int>(k / 3u), iw = static_cast<int>(ow) - 1 + static_cast<int>(k % 3u);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (ih >= 0 && ih < hw && iw >= 0 && iw < hw)
+            v = *reinterpret_cast<const uint4*>(z + (static_cast<size_t>(row) + (ih - static_cast<int>(oh)) * hw + (iw - static_cast<int>(ow))) * C + lane * 8);
+        *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * (9 * C) + k * C + lane * 8) = v;
+    }
+}
+
 // dz[n,h,w,c] = sum_k dcol[n, h-kh+1, w-kw+1, k*C + c]  (transpose of im2col3x3, as a gather).
 __global__ void __launch_bounds__(256) col2im3x3_kernel(const __nv_bfloat16* __restrict__ dcol, int n, int hw, int C,
                                                         __nv_bfloat16* __restrict__ dz) {
@@ -478,6 +527,16 @@ extern "C" int b200vsgg_im2col3x3(const void* z, int32_t n, int32_t hw, int32_t 
     if (!z || !out || channels <= 0 || (channels & 7) || hw <= 0) return set_error(B200VSGG_ERR_BAD_ARG, "im2col3x3: bad arg");
     if (n == 0) return 0;
     const long long items = static_cast<long long>(n) * hw * hw * 9 * (channels >> 3);
+    const long long rows = static_cast<long long>(n) * hw * hw;
+    const int vec = channels >> 3;
+    if (rows * 9 < 0xffffffffLL && (vec == 8 || vec == 16 || vec == 32)) {
+        const int grid = static_cast<int>(std::min<long long>((rows * 9 * vec + 255) / 256, 148LL * 64));
+        if (vec == 8) im2col3x3_fast_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, (unsigned)rows, hw, (__nv_bfloat16*)out);
+        else if (vec == 16) im2col3x3_fast_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, (unsigned)rows, hw, (__nv_bfloat16*)out);
+        else im2col3x3_fast_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, (unsigned)rows, hw, (__nv_bfloat16*)out);
+        VSGG_CUDA_CHECK_LAUNCH();
+        return 0;
+    }
     im2col3x3_kernel<<<blocks_for(items, 256 * 4), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, n, hw,
                                                                                    channels, (__nv_bfloat16*)out);
     VSGG_CUDA_CHECK_LAUNCH();
