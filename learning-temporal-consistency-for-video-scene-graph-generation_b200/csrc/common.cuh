@@ -59,6 +59,19 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// q = i / d, r = i % d for grid-stride indices.  `small` (uniform: the whole index space fits 32 bits) selects 32-bit
+// arithmetic: the 64-bit division sequence is ~60 instructions and made several 16-byte-per-thread kernels ALU-bound.
+__device__ __forceinline__ void divmod_idx(long long i, int d, bool small, long long& q, int& r) {
+    if (small) {
+        const unsigned iu = static_cast<unsigned>(i), qq = iu / static_cast<unsigned>(d);
+        q = qq;
+        r = static_cast<int>(iu - qq * static_cast<unsigned>(d));
+    } else {
+        q = i / d;
+        r = static_cast<int>(i - q * d);
+    }
+}
+
 // Counter-based 32-bit hash (splitmix64 finaliser) used for dropout masks: the same (seed, index)
 // gives the same bit in forward and backward, so masks are never stored.
 __host__ __device__ __forceinline__ unsigned long long hash_u64(unsigned long long seed, unsigned long long idx) {

@@ -160,11 +160,15 @@ __global__ void __launch_bounds__(256) seg_affine_kernel(const __nv_bfloat16* __
                                                          __nv_bfloat16* __restrict__ out) {
     const int vec_per_row = cols >> 3;
     const long long total = rows * vec_per_row;
+    const bool small = total <= 0xffffffffLL;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long r = i / vec_per_row;
-        const int c = static_cast<int>(i - r * vec_per_row) * 8;
-        const int g = __ldg(group_of_unit + r / rows_per_unit);
+        long long r, unit;
+        int c, rem;
+        divmod_idx(i, vec_per_row, small, r, c);
+        c *= 8;
+        divmod_idx(r, rows_per_unit, small, unit, rem);
+        const int g = __ldg(group_of_unit + unit);
         const size_t off = static_cast<size_t>(r) * cols + c;
         const size_t koff = static_cast<size_t>(g) * cols + c;
         float av[8], bv[8], o[8];
@@ -210,13 +214,16 @@ __global__ void __launch_bounds__(256) bn_pool_fwd_kernel(const TY* __restrict__
     const int hout = (hin + 1) / 2;
     const int vec = C >> 3;
     const long long total = static_cast<long long>(n) * hout * hout * vec;
+    const bool small = total <= 0xffffffffLL;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % vec) * 8;
-        long long t = i / vec;
-        const int ow = static_cast<int>(t % hout); t /= hout;
-        const int oh = static_cast<int>(t % hout);
-        const int p = static_cast<int>(t / hout);
+        long long t, t2, t3;
+        int c, ow, oh;
+        divmod_idx(i, vec, small, t, c);
+        c *= 8;
+        divmod_idx(t, hout, small, t2, ow);
+        divmod_idx(t2, hout, small, t3, oh);
+        const int p = static_cast<int>(t3);
         const int g = __ldg(group_of_unit + p);
         float sc[8], sh[8], best[8];
         int arg[8];
@@ -271,13 +278,16 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const __nv_bfloat16* __re
     const int hout = (hin + 1) / 2;
     const int vec = C >> 3;
     const long long total = static_cast<long long>(n) * hin * hin * vec;
+    const bool small = total <= 0xffffffffLL;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % vec) * 8;
-        long long t = i / vec;
-        const int iw = static_cast<int>(t % hin); t /= hin;
-        const int ih = static_cast<int>(t % hin);
-        const int p = static_cast<int>(t / hin);
+        long long t, t2, t3;
+        int c, iw, ih;
+        divmod_idx(i, vec, small, t, c);
+        c *= 8;
+        divmod_idx(t, hin, small, t2, iw);
+        divmod_idx(t2, hin, small, t3, ih);
+        const int p = static_cast<int>(t3);
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -316,13 +326,16 @@ __global__ void __launch_bounds__(256) pool_bwd2x2_kernel(const __nv_bfloat16* _
                                                           __nv_bfloat16* __restrict__ dy) {
     const int hout = hin >> 1, vec = C >> 3;
     const long long total = static_cast<long long>(n) * hout * hout * vec;
+    const bool small = total <= 0xffffffffLL;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % vec) * 8;
-        long long t = i / vec;
-        const int b = static_cast<int>(t % hout); t /= hout;
-        const int a = static_cast<int>(t % hout);
-        const int p = static_cast<int>(t / hout);
+        long long t, t2, t3;
+        int c, b, a;
+        divmod_idx(i, vec, small, t, c);
+        c *= 8;
+        divmod_idx(t, hout, small, t2, b);
+        divmod_idx(t2, hout, small, t3, a);
+        const int p = static_cast<int>(t3);
         float acc[2][2][8];
 #pragma unroll
         for (int dh = 0; dh < 2; ++dh)
@@ -368,6 +381,7 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const __nv_bfloat16* __r
                                                         __nv_bfloat16* __restrict__ out) {
     const int vec = C >> 3;
     const long long total = static_cast<long long>(n) * hw * hw * 9 * vec;
+    const bool small = total <= 0xffffffffLL;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int c = static_cast<int>(i % vec) * 8;
@@ -410,13 +424,16 @@ __global__ void __launch_bounds__(256) col2im3x3_kernel(const __nv_bfloat16* __r
                                                         __nv_bfloat16* __restrict__ dz) {
     const int vec = C >> 3;
     const long long total = static_cast<long long>(n) * hw * hw * vec;
+    const bool small = total <= 0xffffffffLL;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % vec) * 8;
-        long long t = i / vec;
-        const int w = static_cast<int>(t % hw); t /= hw;
-        const int h = static_cast<int>(t % hw);
-        const int p = static_cast<int>(t / hw);
+        long long t, t2, t3;
+        int c, w, h;
+        divmod_idx(i, vec, small, t, c);
+        c *= 8;
+        divmod_idx(t, hw, small, t2, w);
+        divmod_idx(t2, hw, small, t3, h);
+        const int p = static_cast<int>(t3);
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;

@@ -332,9 +332,13 @@ __global__ void cast_dropout_kernel(const float* __restrict__ x, int ld_x, int r
     const uint32_t thr = drop_p > 0.f ? static_cast<uint32_t>(drop_p * 4294967296.0) : 0u;
     const int nvec = cols >> 2;
     const long long total = static_cast<long long>(rows) * nvec;
+    const bool small = total <= 0xffffffffLL;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int r = static_cast<int>(i / nvec), c = static_cast<int>(i % nvec);
+        long long rq;
+        int c;
+        divmod_idx(i, nvec, small, rq, c);
+        const int r = static_cast<int>(rq);
         const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * ld_x + c * 4);
         float a[4] = {v.x, v.y, v.z, v.w};
         if (thr) {
@@ -356,9 +360,13 @@ __global__ void split3_bf16_kernel(const float* __restrict__ x, int ld_x, int ro
                                    __nv_bfloat16* __restrict__ out, int ld_o) {
     const int nvec = cols >> 2;
     const long long total = static_cast<long long>(rows) * nvec;
+    const bool small = total <= 0xffffffffLL;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int r = static_cast<int>(i / nvec), c = static_cast<int>(i % nvec);
+        long long rq;
+        int c;
+        divmod_idx(i, nvec, small, rq, c);
+        const int r = static_cast<int>(rq);
         const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * ld_x + c * 4);
         float hi[4] = {v.x, v.y, v.z, v.w}, lo[4];
 #pragma unroll
