@@ -534,18 +534,21 @@ def apply_heads(heads, feat, mode, eps_list, seed):
     lins = [l for h in heads for l in h.packed_order()]
     params = [l.weight for l in lins] + [l.bias for l in lins]
     direct = DIRECT_HEAD_GRADS and torch.is_grad_enabled() and all(p.is_leaf for p in params)
+    anchor = next((i for i, p in enumerate(params) if p.requires_grad), 0)
     return _HeadsFn.apply(feat, mode, heads[0].k, [h.num_classes for h in heads], [h.softmax for h in heads], eps_list,
-                          seed, len(lins), tuple(params) if direct else None, *(params[:1] if direct else params))
+                          seed, len(lins), (tuple(params), anchor) if direct else None,
+                          *(params[anchor:anchor + 1] if direct else params))
 
 
 class _HeadsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, mode, K, Cs, softmaxes, eps_list, seed, n_lin, holder, *params):
-        # holder: the 2 * n_lin parameters as a plain tuple (no autograd edges; `params` is then only the first weight,
-        # which keeps the node connected to the graph) — see backward
+        # holder: (the 2 * n_lin parameters as a plain tuple, index of the anchor) — no autograd edges; `params` is then only
+        # the anchor (the first trainable parameter), which keeps the node connected to the graph — see backward
         direct = holder is not None
+        ctx.anchor = 0
         if direct:
-            params = holder
+            params, ctx.anchor = holder
         ws, bs = params[:n_lin], params[n_lin:]
         N = feat.shape[0]
         K_in = ws[0].shape[1]
@@ -629,14 +632,15 @@ class _HeadsFn(torch.autograd.Function):
             # restores plain autograd inputs for wrappers that hook these parameters' graph nodes (torch DDP);
             # b200vsgg.ddp.GradSync reads .grad and is unaffected.
             with torch.no_grad():
-                for i, (p_, g_) in enumerate(zip(params, list(dws) + list(dbs))):
-                    if i == 0 or g_ is None or not need[i]:
+                allg = list(dws) + list(dbs)
+                for i, (p_, g_) in enumerate(zip(params, allg)):
+                    if i == ctx.anchor or g_ is None or not need[i]:
                         continue
                     if p_.grad is None:
                         p_.grad = g_
                     else:
                         p_.grad.add_(g_)
-            return (dfeat,) + (None,) * 8 + (dws[0] if need[0] else None,)
+            return (dfeat,) + (None,) * 8 + (allg[ctx.anchor] if need[ctx.anchor] else None,)
         return (dfeat, None, None, None, None, None, None, None, None, *dws, *dbs)
 
 

@@ -123,3 +123,52 @@ def test_simt_linear_wgrad_and_small_layernorm(cuda_lib):
     _close(dx, xr.grad + base)
     _close(dg, gr.grad, 1e-4)
     _close(db, br.grad, 1e-4)
+
+
+def test_graph_attn_core_fwd_bwd(cuda_lib):
+    """Attention core of graph_transformer_pytorch.Attention (8 heads x 64, rotary by node index, per-edge key / value
+    offsets e_ij = A_ij we + be) per frame: forward (fp32 output variant) and the hand-written backward against autograd
+    through a direct torch restatement."""
+    from b200vsgg import ops
+    g = torch.Generator(device=DEV).manual_seed(5)
+    counts, nmax, H, DH = [4, 9, 1, 11, 6], 12, 8, 64
+    inner = H * DH
+    off = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device=DEV)
+    R = int(off[-1])
+    qkv = torch.randn(R, 3 * inner, generator=g, device=DEV)
+    upper = torch.zeros(len(counts), nmax, nmax, dtype=torch.uint8, device=DEV)
+    for f, n in enumerate(counts):
+        u = (torch.rand(n, n, generator=g, device=DEV) < 0.5).triu(1)
+        upper[f, :n, :n] = u.to(torch.uint8)
+    we, be = 0.3 * torch.randn(inner, generator=g, device=DEV), 0.3 * torch.randn(inner, generator=g, device=DEV)
+    out = torch.empty(R, inner, device=DEV)
+    ops.graph_attn_core(qkv, off, upper, nmax, we, be, out)
+    dout = torch.randn(R, inner, generator=g, device=DEV)
+    dqkv, dwe, dbe = torch.empty(R, 3 * inner, device=DEV), torch.zeros(inner, device=DEV), torch.zeros(inner, device=DEV)
+    ops.graph_attn_core_bwd(qkv, off, upper, nmax, we, be, dout, dqkv, dwe, dbe)
+
+    qr, wr, br = (t.clone().requires_grad_(True) for t in (qkv, we, be))
+    inv_freq = 10000.0 ** (-torch.arange(0, DH, 2, device=DEV).float() / DH)
+
+    def rot(x, n):                                     # x [n, H, DH]: rotate the pairs (2l, 2l+1) by position * inv_freq[l]
+        ang = torch.arange(n, device=DEV).float()[:, None] * inv_freq[None]
+        cs, sn = ang.cos()[:, None, :], ang.sin()[:, None, :]
+        x0, x1 = x[..., 0::2], x[..., 1::2]
+        return torch.stack([x0 * cs - x1 * sn, x1 * cs + x0 * sn], -1).flatten(-2)
+
+    refs = []
+    for f, n in enumerate(counts):
+        a, b = int(off[f]), int(off[f + 1])
+        q, k, v = (qr[a:b, i * inner:(i + 1) * inner].view(n, H, DH) for i in range(3))
+        q, k = rot(q, n), rot(k, n)
+        A = (upper[f, :n, :n] + upper[f, :n, :n].t()).float()
+        e = A[:, :, None, None] * wr.view(H, DH) + br.view(H, DH)                    # [i, j, H, DH]
+        sim = torch.einsum("ihd,ijhd->hij", q, k[None] + e) / 8.0
+        p = sim.softmax(-1)
+        refs.append(torch.einsum("hij,ijhd->ihd", p, v[None] + e).reshape(n, inner))
+    ref = torch.cat(refs)
+    ref.backward(dout)
+    _close(out, ref, 2e-4)
+    _close(dqkv, qr.grad, 2e-4)
+    _close(dwe, wr.grad, 2e-4)
+    _close(dbe, br.grad, 2e-4)
