@@ -472,8 +472,10 @@ def run_object_branch(oc, entry, phase, frames_per_video, heads_fn, dropout_p, g
                                training)
         entry["object_features"] = y.float()
         if oc.mem_compute and len(oc.obj_memory) != 0:
-            raise NotImplementedError("object memory without tracking is not on the accelerated path")
-        entry["object_mem_features"] = entry["object_features"]
+            # lib/tempura.py:217-221: without tracking the memory hallucinator works on the 1024-wide `intermediate`
+            # output (single-head attention over the class memory through the C-ABI GEMM, blended by the selector)
+            y = oc.hallucinate(y.float())
+        entry["object_mem_features"] = y.float()
 
     if getattr(oc, "_debug", False):      # parity debugging: expose the branch's intermediate tensors
         oc._debug_last = dict(y=y, tokens=x32)

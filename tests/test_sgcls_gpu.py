@@ -326,3 +326,48 @@ def test_object_memory_with_tracking_matches_oracle(cuda_lib, selection):
         assert rel <= GATED_GRAD_REL_TOL, (pname, rel)
         checked += 1
     assert checked >= (2 if selection == "manual" else 4)
+
+
+@pytest.mark.parametrize("selection", ["manual", "learned"])
+def test_object_memory_without_tracking_matches_oracle(cuda_lib, selection):
+    """Object memory of the NON-tracking branch (lib/tempura.py:217-221: hallucinator on the 1024-wide `intermediate`
+    output; here the learned selector nn.Linear(1024, 1) fits) with a non-empty bank: features, distribution and the
+    gradients of the memory attention / selector vs the CPU oracle."""
+    from b200vsgg import objbranch, synthetic, tempura
+    from oracle.tempura_oracle import TempuraOracle, object_loss, tempura_losses
+    gold = torch.load(os.path.join(GOLDEN, "sgcls_notrack_gmm.pt"), weights_only=False)
+    kw = dict(gold["model_kw"], obj_mem_compute=True, selection=selection)
+    classes = synthetic.ag_object_classes()
+    m = tempura.TEMPURA(obj_classes=classes, **kw)
+    synthetic.seeded_init_(m)
+    o = TempuraOracle(obj_classes=classes, dropout=0.0, **kw)
+    o.load_state_dict(m.state_dict(), strict=True)
+    bank = 0.5 * torch.randn(len(classes) - 1, 1024, generator=torch.Generator().manual_seed(78))
+    m.object_classifier.obj_memory = bank.cuda()
+    o.object_classifier.obj_memory = bank.clone()
+    vid = gold["case"]["video_index"]
+    entry = synthetic.add_sgcls_inputs(synthetic.make_video_entry(**gold["case"]), vid)
+    objbranch.get_sequence(entry, None, None, "sgcls")
+    m, o = m.cuda().train(), o.train()
+    m.dropout_p = m.object_classifier.dropout_p = 0.0
+    m.gmm_eps = gold["eps"]
+    att, spa, con = synthetic.build_gt_tensors(entry)
+    po = o(_clone(entry), phase="train", eps=gold["eps"])
+    (sum(tempura_losses(po, att, spa, con).values()) + object_loss(po, 0.5)).backward()
+    pm = m(_clone(entry, "cuda"), phase="train")
+    sum(tempura.tempura_loss(pm, m.last_plan, eos_coef=0.5).values()).backward()
+    assert (po["object_mem_features"] - po["object_features"]).abs().max().item() > 1e-2
+    ref = po["object_mem_features"].detach()
+    assert (pm["object_mem_features"].float().cpu() - ref).abs().max().item() <= FEAT_REL_TOL * ref.abs().max().item()
+    assert (pm["distribution"].float().cpu() - po["distribution"].detach()).abs().max().item() <= DIST_TOL
+    og = dict(o.named_parameters())
+    checked = 0
+    for pname, p in m.named_parameters():
+        if not (pname.startswith("object_classifier.mem_attention") or pname.startswith("object_classifier.selector")):
+            continue
+        r = og[pname].grad
+        assert r is not None and p.grad is not None, pname
+        rel = (p.grad.float().cpu() - r).norm().item() / max(r.norm().item(), 1e-12)
+        assert rel <= GATED_GRAD_REL_TOL, (pname, rel)
+        checked += 1
+    assert checked >= (2 if selection == "manual" else 4)
