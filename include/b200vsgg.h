@@ -178,7 +178,8 @@ int b200vsgg_attn_rows_bwd(const void* q, int32_t ldq, const void* k, int32_t ld
 typedef struct b200vsgg_gmm_head {
     int32_t col_base;
     int32_t num_classes;
-    int32_t softmax;   /* 1: softmax over classes (attention head), 0: sigmoid */
+    int32_t softmax;   /* 1: softmax over classes (attention / object head), 0: sigmoid, 2: like 1 but in mode 0 the first
+                          (background) class is dropped before the softmax and `out` is [N, C-1] (object head, test phase) */
     const float* eps;  /* [K, N, C] or NULL */
     float* out;        /* [N, C] */
     float* out2;       /* [N, C], mode 2 only */

@@ -103,16 +103,19 @@ __global__ void gmm_head_fwd_kernel(const float* __restrict__ z, const GmmParams
         }
         return;
     }
+    // softmax == 2 (object head, test phase, gmm_heads.py:63-64 `mu[..., 1:]`): the background class is dropped BEFORE the
+    // activation and the output has C - 1 columns
+    const int c0 = (hd.softmax == 2 && p.mode == 0) ? 1 : 0, Cc = C - c0;
     for (int k = 0; k < K; ++k) {
-        for (int c = 0; c < C; ++c) {
-            float l = zr[k * C + c];
+        for (int c = 0; c < Cc; ++c) {
+            float l = zr[k * C + c0 + c];
             if (p.mode == 1) l += sqrtf(sigmoidf_(zr[K * C + k * C + c])) * fetch_eps(p, hd, head, k, n, c);
             logit[c] = l;
         }
-        act_component(logit, C, hd.softmax, a);
-        for (int c = 0; c < C; ++c) acc[c] += pi[k] * a[c];
+        act_component(logit, Cc, hd.softmax, a);
+        for (int c = 0; c < Cc; ++c) acc[c] += pi[k] * a[c];
     }
-    for (int c = 0; c < C; ++c) hd.out[static_cast<size_t>(n) * C + c] = acc[c];
+    for (int c = 0; c < Cc; ++c) hd.out[static_cast<size_t>(n) * Cc + c] = acc[c];
 }
 
 // Backward of the train/test mixture output w.r.t. the packed logits z.  Writes dz (bf16, the A

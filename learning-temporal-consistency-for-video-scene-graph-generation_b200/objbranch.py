@@ -412,7 +412,7 @@ def box_center_size(boxes):
     return torch.cat((boxes[:, 1:3] + 0.5 * wh, wh), 1)
 
 
-def run_object_branch(oc, entry, phase, frames_per_video, heads_fn, dropout_p, gmm_eps=None):
+def run_object_branch(oc, entry, phase, frames_per_video, heads_fn, dropout_p, gmm_eps=None, unc=False):
     """ObjectClassifier.forward for mode='sgcls', phase='train' (lib/tempura.py:249-255 -> classify :185-241).
     `oc` is the parameter container (tempura.ObjectClassifier); returns entry with `distribution`,
     `object_features`, `object_mem_features`, `pred_labels`."""
@@ -479,7 +479,14 @@ def run_object_branch(oc, entry, phase, frames_per_video, heads_fn, dropout_p, g
 
     if getattr(oc, "_debug", False):      # parity debugging: expose the branch's intermediate tensors
         oc._debug_last = dict(y=y, tokens=x32)
-    if oc.obj_head == "gmm":
+    if oc.obj_head == "gmm" and unc:
+        # lib/tempura.py:226-228 (the trainer's uncertainty pass, Uncertainty.py:100): test-phase distribution (mixture of
+        # the means, background class dropped) + aleatoric / epistemic uncertainties of the object head
+        with torch.no_grad():
+            (dist,) = heads_fn([oc.decoder_lin], y.float(), 0, [None], 0, skip_first=True)
+            al, ep = heads_fn([oc.decoder_lin], y.float(), 2, [None], 0)
+        entry["distribution"], entry["obj_al_uc"], entry["obj_ep_uc"] = dist, al, ep
+    elif oc.obj_head == "gmm":
         eps = [gmm_eps.get("object")] if gmm_eps else [None]
         hseed = int(torch.randint(0, 2 ** 62, (1,)).item())
         (dist,) = heads_fn([oc.decoder_lin], y.float(), 1, eps, hseed)

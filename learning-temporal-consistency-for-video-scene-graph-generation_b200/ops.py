@@ -337,7 +337,7 @@ def _gmm_heads_array(specs):
     for i, s in enumerate(specs):
         arr[i].col_base = s["col_base"]
         arr[i].num_classes = s["num_classes"]
-        arr[i].softmax = 1 if s["softmax"] else 0
+        arr[i].softmax = int(s["softmax"])        # 0 sigmoid, 1 softmax, 2 softmax without the background class (mode 0)
         for f in ("eps", "out", "out2", "dout"):
             t = s.get(f)
             if t is not None:

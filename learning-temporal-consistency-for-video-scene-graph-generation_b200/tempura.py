@@ -188,15 +188,16 @@ class ObjectClassifier(nn.Module):
         if self.mode == "predcls":
             entry["pred_labels"] = entry["labels"]
             return entry
-        if self.mode != "sgcls" or phase != "train" or unc:
+        if self.mode != "sgcls" or phase != "train":
             raise NotImplementedError(
-                "object branch: only mode='sgcls', phase='train', unc=False is on the accelerated path — the test-time "
-                "relabel / NMS / ROIAlign tail (lib/tempura.py:257-307, :310-421) needs the reference's absent CUDA ops")
+                "object branch: only mode='sgcls', phase='train' (with or without unc) is on the accelerated path — the "
+                "test-time relabel / NMS / ROIAlign tail (lib/tempura.py:257-307, :310-421) needs the reference's absent "
+                "CUDA ops")
         from .objbranch import run_object_branch
         fpv = entry.get("video_frames")
         if fpv is None:
             fpv = np.asarray([entry["human_idx"].shape[0] if "human_idx" in entry else int(entry["boxes"][-1, 0].item()) + 1])
-        return run_object_branch(self, entry, phase, fpv, apply_heads, self.dropout_p, self.gmm_eps)
+        return run_object_branch(self, entry, phase, fpv, apply_heads, self.dropout_p, self.gmm_eps, unc=unc)
 
 
 # ================================================================================================
@@ -526,7 +527,7 @@ class TEMPURA(nn.Module):
 DIRECT_HEAD_GRADS = True       # see _HeadsFn.backward
 
 
-def apply_heads(heads, feat, mode, eps_list, seed):
+def apply_heads(heads, feat, mode, eps_list, seed, skip_first=False):
     """All mixture heads of `heads` (GMMHead containers) on `feat` [N, hid]: ONE packed GEMM + one epilogue kernel
     (tools/utils/gmm_heads.py:37-76 does 3K tiny Linears per head).  The 2 x 3K x len(heads) Linear parameters go to the
     autograd function individually — no differentiable torch.cat whose backward would split the packed gradient with
@@ -535,7 +536,9 @@ def apply_heads(heads, feat, mode, eps_list, seed):
     params = [l.weight for l in lins] + [l.bias for l in lins]
     direct = DIRECT_HEAD_GRADS and torch.is_grad_enabled() and all(p.is_leaf for p in params)
     anchor = next((i for i, p in enumerate(params) if p.requires_grad), 0)
-    return _HeadsFn.apply(feat, mode, heads[0].k, [h.num_classes for h in heads], [h.softmax for h in heads], eps_list,
+    # skip_first (mode 0 only): the object head's test-phase output drops the background class (gmm_heads.py:63-64)
+    softmaxes = [2 if (skip_first and mode == 0 and h.softmax) else h.softmax for h in heads]
+    return _HeadsFn.apply(feat, mode, heads[0].k, [h.num_classes for h in heads], softmaxes, eps_list,
                           seed, len(lins), (tuple(params), anchor) if direct else None,
                           *(params[anchor:anchor + 1] if direct else params))
 
@@ -582,7 +585,7 @@ class _HeadsFn(torch.autograd.Function):
         for C in Cs:
             bases.append(b)
             b += K * (2 * C + 1)
-        outs = [torch.empty(N, C, device=dev) for C in Cs]
+        outs = [torch.empty(N, C - (1 if (mode == 0 and sm == 2) else 0), device=dev) for C, sm in zip(Cs, softmaxes)]
         outs2 = [torch.empty(N, C, device=dev) for C in Cs] if mode == 2 else [None] * len(Cs)
         eps_dev = [e.to(dev, torch.float32).contiguous() if e is not None else None for e in eps_list]
         specs = [dict(col_base=bases[i], num_classes=Cs[i], softmax=softmaxes[i], eps=eps_dev[i], out=outs[i],

@@ -371,3 +371,26 @@ def test_object_memory_without_tracking_matches_oracle(cuda_lib, selection):
         assert rel <= GATED_GRAD_REL_TOL, (pname, rel)
         checked += 1
     assert checked >= (2 if selection == "manual" else 4)
+
+
+@pytest.mark.parametrize("name", ["sgcls_track_gmm", "sgcls_notrack_gmm"])
+def test_uncertainty_pass_matches_oracle(cuda_lib, name):
+    """`model(entry, unc=True)` in eval mode — the call of the trainer's uncertainty bookkeeping (tools/utils/Uncertainty.py:
+    95-100; lib/tempura.py:226-228 for the object head): test-phase object distribution (background class dropped before the
+    softmax: 36 columns), aleatoric / epistemic uncertainties of the object head and of the three relation heads vs the CPU
+    oracle."""
+    gold, entry, m, o = _setup(name)
+    m.eval()
+    o.eval()
+    with torch.no_grad():
+        out = m(_clone(entry, "cuda"), phase="train", unc=True)
+        ref = o(_clone(entry), phase="train", unc=True)
+    assert out["distribution"].shape == ref["distribution"].shape and out["distribution"].shape[1] == 36
+    for k in ("distribution", "obj_al_uc", "obj_ep_uc", "attention_al_uc", "spatial_al_uc", "contacting_al_uc",
+              "attention_ep_uc", "spatial_ep_uc", "contacting_ep_uc"):
+        err = (out[k].float().cpu() - ref[k]).abs().max().item()
+        # object uncertainties: sums of sigmoid(variance logit) read off the bf16 `intermediate` output (1024-wide, un-
+        # normalised in the non-tracking branch: measured 1.7e-2 there, < 4e-3 with tracking); values live in [0, 1]
+        tol = 2.5e-2 if k in ("obj_al_uc", "obj_ep_uc") else DIST_TOL
+        assert err <= tol, (k, err)
+    assert torch.equal(out["pred_labels"].cpu(), entry["labels"])
