@@ -16,8 +16,9 @@ normaliser of the relation memories is `sum(exp(al_list + al_list))` — a LIST 
 `2 * sum_j exp(al_jk)`; weight types 'al' / 'ep' normalise by `sum_j exp(u_jk)`; `None` / 'simple' use weight 1 and
 'simple' alone divides by the label count (Memory.py:119-133).  Entries whose uncertainty is exactly 0.0 are skipped like
 the reference's `np.where(batch_unc != 0)`.
-Only the relation memories are built here (PredCLS trains with `obj_mem_compute=False`; the object memory needs the
-object branch's `object_features`, same arithmetic, `update_objects`)."""
+Only the relation memories are built here: PredCLS trains with `obj_mem_compute=False`, and the reference's object-memory
+branch with uncertainty weights cannot run as released (tools/utils/Memory.py:90-94 multiplies by `obj_features`, which
+that branch never loads), so there is no reference behaviour to reproduce for it."""
 import numpy as np
 import torch
 
