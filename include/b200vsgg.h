@@ -98,6 +98,16 @@ int b200vsgg_gather2_sum_rows(const float* src, int32_t ld_src, const int32_t* i
                               int32_t ld_base, int32_t rows, int32_t cols, float* out_f32, int32_t ld_f32,
                               void* out_bf16, int32_t ld_bf16, void* stream);
 
+/* bf16 forms of the two gathers above (rows move between the pair layout [N,.] and the window layout [M2,.] of the
+ * temporal decoder, tools/utils/transformer.py:203-215,236-242, without a detour through fp32):
+ *   gather_rows_bf16       out[t,:] = idx[t] >= 0 ? src[idx[t],:] : 0   (idx NULL = identity; negative = zero row)
+ *   gather2_sum_rows_bf16  out[n,:] = bf16(sum_{k<2, idx2[2n+k] >= 0} float(src[idx2[2n+k],:]))
+ * cols, ld_src, ld_out % 8 == 0, pointers 16-byte aligned. */
+int b200vsgg_gather_rows_bf16(const void* src, int32_t ld_src, const int32_t* idx, int32_t rows, int32_t cols, void* out,
+                              int32_t ld_out, void* stream);
+int b200vsgg_gather2_sum_rows_bf16(const void* src, int32_t ld_src, const int32_t* idx2, int32_t rows, int32_t cols,
+                                   void* out, int32_t ld_out, void* stream);
+
 /* Pair-token gather/concat (lib/tempura.py:537-563): tok[n] = so[pair_idx[n,0],0:512] |
  * so[pair_idx[n,1],512:1024] | (vr_fc output already in tok_f32[:,1024:1536]) |
  * embed1[labels[pair_idx[n,0]]] | embed2[labels[pair_idx[n,1]]];  writes fp32 and bf16 [N,1936].

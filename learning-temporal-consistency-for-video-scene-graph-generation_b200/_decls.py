@@ -24,6 +24,8 @@ SIGNATURES = {
     "b200vsgg_frame_offsets": [vp, i32, i32, vp, vp],
     "b200vsgg_gather_rows": [vp, i32, vp, vp, vp, i32, i32, vp, i32, vp, i32, vp, i32, vp],
     "b200vsgg_gather2_sum_rows": [vp, i32, vp, vp, i32, i32, i32, vp, i32, vp, i32, vp],
+    "b200vsgg_gather_rows_bf16": [vp, i32, vp, i32, i32, vp, i32, vp],
+    "b200vsgg_gather2_sum_rows_bf16": [vp, i32, vp, i32, i32, vp, i32, vp],
     "b200vsgg_pair_concat_fwd": [vp, vp, vp, vp, vp, i32, vp, vp, vp],
     "b200vsgg_pair_concat_bwd": [vp, vp, vp, i32, vp, vp, vp, vp],
     "b200vsgg_layernorm_fwd": [vp, i32, vp, vp, i32, i32, f32, vp, i32, vp, i32, vp, vp, vp, i32, vp, vp, vp],

@@ -99,6 +99,50 @@ __global__ void gather2_sum_rows_kernel(const float* __restrict__ src, int ld_sr
 }
 
 // ------------------------------------------------------------------------------------------------
+// bf16 forms of the two gathers (16-byte chunks, one warp per row).  They move rows between the PAIR layout [N, .] and
+// the WINDOW layout [M2, .] of the temporal decoder without a detour through fp32:
+//   gather_rows_bf16       out[t,:] = idx[t] >= 0 ? src[idx[t],:] : 0        (negative index = zero row)
+//   gather2_sum_rows_bf16  out[n,:] = bf16(sum_{k<2, idx2[2n+k] >= 0} float(src[idx2[2n+k],:]))
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, int ld_src, const int32_t* __restrict__ idx,
+                                        int rows, int cols, __nv_bfloat16* __restrict__ out, int ld_out) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+        const int s = idx ? __ldg(idx + r) : r;
+        const __nv_bfloat16* sp = src + static_cast<size_t>(s < 0 ? 0 : s) * ld_src;
+        __nv_bfloat16* op = out + static_cast<size_t>(r) * ld_out;
+        for (int c = lane * 8; c < cols; c += 256) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (s >= 0) v = *reinterpret_cast<const uint4*>(sp + c);
+            *reinterpret_cast<uint4*>(op + c) = v;
+        }
+    }
+}
+
+__global__ void gather2_sum_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, int ld_src,
+                                             const int32_t* __restrict__ idx2, int rows, int cols,
+                                             __nv_bfloat16* __restrict__ out, int ld_out) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+        const int i0 = __ldg(idx2 + 2 * r), i1 = __ldg(idx2 + 2 * r + 1);
+        __nv_bfloat16* op = out + static_cast<size_t>(r) * ld_out;
+        for (int c = lane * 8; c < cols; c += 256) {
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (i0 >= 0) load_bf16x8(src + static_cast<size_t>(i0) * ld_src + c, v);
+            if (i1 >= 0) {
+                float a[8];
+                load_bf16x8(src + static_cast<size_t>(i1) * ld_src + c, a);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += a[k];
+            }
+            store_bf16x8(op + c, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // pair_concat: the [N,1936] pair token (lib/tempura.py:537-563).
 //   cols [0,512)      = so[pair_idx[n,0], 0:512]        (subj_fc output of the person box)
 //   cols [512,1024)   = so[pair_idx[n,1], 512:1024]     (obj_fc output of the object box)
@@ -494,6 +538,33 @@ extern "C" int b200vsgg_gather2_sum_rows(const float* src, int32_t ld_src, const
     if (rows == 0) return 0;
     gather2_sum_rows_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(
         src, ld_src, idx2, base, ld_base, rows, cols, out_f32, ld_f32, (__nv_bfloat16*)out_bf16, ld_bf16);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}
+
+static bool bf16_rows_ok(const void* src, int32_t ld_src, const void* out, int32_t ld_out, int32_t cols) {
+    return src && out && cols > 0 && !(cols & 7) && !(ld_src & 7) && !(ld_out & 7) &&
+           !(reinterpret_cast<uintptr_t>(src) & 15u) && !(reinterpret_cast<uintptr_t>(out) & 15u);
+}
+
+extern "C" int b200vsgg_gather_rows_bf16(const void* src, int32_t ld_src, const int32_t* idx, int32_t rows, int32_t cols,
+                                         void* out, int32_t ld_out, void* stream) {
+    if (rows < 0 || !bf16_rows_ok(src, ld_src, out, ld_out, cols))
+        return set_error(B200VSGG_ERR_BAD_ARG, "gather_rows_bf16: cols / strides % 8 != 0 or pointers not 16-byte aligned");
+    if (rows == 0) return 0;
+    gather_rows_bf16_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, ld_src, idx, rows, cols, (__nv_bfloat16*)out, ld_out);
+    VSGG_CUDA_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int b200vsgg_gather2_sum_rows_bf16(const void* src, int32_t ld_src, const int32_t* idx2, int32_t rows,
+                                              int32_t cols, void* out, int32_t ld_out, void* stream) {
+    if (!idx2 || rows < 0 || !bf16_rows_ok(src, ld_src, out, ld_out, cols))
+        return set_error(B200VSGG_ERR_BAD_ARG, "gather2_sum_rows_bf16: cols / strides % 8 != 0 or pointers not 16-byte aligned");
+    if (rows == 0) return 0;
+    gather2_sum_rows_bf16_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, ld_src, idx2, rows, cols, (__nv_bfloat16*)out, ld_out);
     VSGG_CUDA_CHECK_LAUNCH();
     return 0;
 }

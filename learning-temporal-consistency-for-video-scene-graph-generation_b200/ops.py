@@ -158,6 +158,29 @@ def gather2_sum_rows(src, idx2, base=None, out_f32=None, out_bf16=None):
     _count()
 
 
+def gather_rows_bf16(src, idx, out, rows=None):
+    """out[t] = src[idx[t]] for bf16 rows; a negative index yields a zero row (idx None = identity copy)."""
+    _bf(src), _bf(out)
+    assert idx is None or (idx.dtype == torch.int32 and idx.is_contiguous())
+    assert src.dim() == 2 and out.dim() == 2 and src.stride(1) == 1 and out.stride(1) == 1 and out.shape[1] == src.shape[1]
+    rows = rows if rows is not None else (idx.numel() if idx is not None else src.shape[0])
+    assert out.shape[0] == rows
+    check(_lib.lib().b200vsgg_gather_rows_bf16(_ptr(src), src.stride(0), _ptr(idx), rows, src.shape[1], _ptr(out),
+                                               out.stride(0), _stream()), "gather_rows_bf16")
+    _count()
+
+
+def gather2_sum_rows_bf16(src, idx2, out):
+    """out[n] = bf16(sum of the <= 2 bf16 rows src[idx2[n, k]] with idx2[n, k] >= 0), accumulated in fp32."""
+    _bf(src), _bf(out)
+    assert idx2.dtype == torch.int32 and idx2.is_contiguous() and idx2.dim() == 2 and idx2.shape[1] == 2
+    assert src.dim() == 2 and out.dim() == 2 and src.stride(1) == 1 and out.stride(1) == 1 and out.shape[1] == src.shape[1]
+    assert out.shape[0] == idx2.shape[0]
+    check(_lib.lib().b200vsgg_gather2_sum_rows_bf16(_ptr(src), src.stride(0), _ptr(idx2), idx2.shape[0], src.shape[1],
+                                                    _ptr(out), out.stride(0), _stream()), "gather2_sum_rows_bf16")
+    _count()
+
+
 def pair_concat_fwd(so, pair_idx, labels, embed1, embed2, tok_f32, tok_bf16):
     assert so.is_contiguous() and so.shape[1] == 1024 and pair_idx.dtype == torch.int64 and pair_idx.is_contiguous()
     assert labels.dtype == torch.int64 and tok_f32.is_contiguous() and tok_bf16.is_contiguous()

@@ -16,7 +16,7 @@ class SegmentPlan:
     win_first[W]     first frame of window w             win_off[W+1]    window-token offsets
     win_src[M2]      pair row feeding window token t     win_pos[M2]     0 = former frame, 1 = latter
     latter_src[N]    window token that yields pair n's output ('latter' mode)
-    inv_latter2[M2,2] (pair n or -1, -1): backward of the latter gather
+    inv_latter2[M2,2] (pair n or -1, -1): backward of the latter gather      inv_latter[M2] its first column
     pair_win2[N,2]   window tokens that read pair n (former, latter), -1 if none
     video_of_pair[N] video id per pair (int64, for per-video BatchNorm statistics / losses)
     """
@@ -76,6 +76,7 @@ class SegmentPlan:
         self.win_pos_h = win_pos.astype(i32)
         self.latter_src_h = latter_src.astype(i32)
         self.inv_latter2_h = inv.astype(i32)
+        self.inv_latter_h = inv[:, 0].astype(i32)
         self.pair_win2_h = np.stack([former_tok, latter_tok], 1).astype(i32)
         self.video_of_pair_h = video_of_frame[frame_of_pair].astype(np.int64)
         self.video_of_pair32_h = self.video_of_pair_h.astype(i32)
@@ -83,7 +84,7 @@ class SegmentPlan:
         self.device = None
         self._chunks = {}
 
-    _DEVICE_FIELDS = ("frame_off", "win_off", "win_src", "win_pos", "latter_src", "inv_latter2", "pair_win2",
+    _DEVICE_FIELDS = ("frame_off", "win_off", "win_src", "win_pos", "latter_src", "inv_latter2", "inv_latter", "pair_win2",
                       "video_of_pair32", "video_of_pair")
 
     def stat_chunks(self, rows_per_pair, chunk_rows=2048):

@@ -31,6 +31,19 @@ HEAD_DIM = D_MODEL // N_HEADS
 FFN_DIM = 2048
 HEAD_COLS_PAD = 8  # packed head GEMM width is rounded up to a multiple of 8
 
+# Two result-preserving savings in the temporal decoder ("legal algebraic savings"; window tokens are
+# M2 ~ 1.94 N rows because every interior frame lives in two windows):
+#   DEC_FIRST_ON_PAIRS  the window tokens of the FIRST decoder layer are copies of pair rows (transformer.py:203-215), so
+#                       its q/k/v projections run once over the N pair rows — q, k = (x + pos) Wqk = x Wqk + pos Wqk — and
+#                       are gathered into the windows; the backward sums the <= 2 window copies of dqkv before its GEMMs.
+#   DEC_LATTER_ONLY     the 'latter' read-out (transformer.py:236-242) keeps N of the LAST layer's M2 output rows; the
+#                       others never reach an output or a loss, so after the attention (whose keys / values need every
+#                       row) out-proj, LayerNorm and the FFN run on the N kept rows only.  Bit-identical outputs.
+# Environment B200VSGG_DEC_FIRST_ON_PAIRS=0 / B200VSGG_DEC_LATTER_ONLY=0 restore the dense M2-row schedule (A/B timing).
+import os as _os
+DEC_FIRST_ON_PAIRS = _os.environ.get("B200VSGG_DEC_FIRST_ON_PAIRS", "1") != "0"
+DEC_LATTER_ONLY = _os.environ.get("B200VSGG_DEC_LATTER_ONLY", "1") != "0"
+
 
 def _fgemm(*args, **kw):
     """Forward-path GEMM: never split-K.  Split-K partial tiles are summed in arrival order (TMA reduce-add), and a
@@ -305,6 +318,18 @@ def _split_bf16(w):
     hi = w.to(torch.bfloat16)
     lo = (w - hi.float()).to(torch.bfloat16)
     return torch.cat([hi, lo], 1).contiguous()
+
+
+def _pos_rows_times_wt(pos, w_bf16):
+    """[2, in] fp32 position rows times a bf16 [out, in] weight slice -> [2, out] fp32 on the tcgen05 GEMM; the rows
+    enter as bf16 hi + lo parts (rows 0-1 / 2-3 of an 8-row operand), so only the weight is rounded."""
+    hi = pos.to(torch.bfloat16)
+    a = torch.zeros(8, pos.shape[1], device=pos.device, dtype=torch.bfloat16)
+    a[0:2] = hi
+    a[2:4] = (pos - hi.float()).to(torch.bfloat16)
+    out = torch.empty(8, w_bf16.shape[0], device=pos.device, dtype=torch.float32)
+    ops.gemm(a, w_bf16, out_f32=out, split_k=1)
+    return (out[0:2] + out[2:4]).contiguous()
 
 
 def _bn_train_stats(s1, s2, cnt, bn):
@@ -888,41 +913,75 @@ class _PathRunner:
 
         # ---- T3: 2-frame windows + position embedding (transformer.py:203-215)
         pos = P["pos"].detach().contiguous()
-        g32, gb, gpb = new(M2, D_MODEL, f32), new(M2, D_MODEL, bf16), new(M2, D_MODEL, bf16)
-        ops.gather_rows(local, plan.win_src, add_table=pos, add_idx=plan.win_pos, out_f32=g32, out_bf16=gb,
-                        out_bf16_added=gpb)
+        D2 = 2 * D_MODEL
+        on_pairs = DEC_FIRST_ON_PAIRS and self.n_dec > 0
+        latter_only = DEC_LATTER_ONLY and self.n_dec > 0
+        S["dec_flags"] = (on_pairs, latter_only)
+        g32 = new(M2, D_MODEL, f32)
+        gb = gpb = None
+        if on_pairs:
+            ops.gather_rows(local, plan.win_src, out_f32=g32)
+        else:
+            gb, gpb = new(M2, D_MODEL, bf16), new(M2, D_MODEL, bf16)
+            ops.gather_rows(local, plan.win_src, add_table=pos, add_idx=plan.win_pos, out_f32=g32, out_bf16=gb,
+                            out_bf16_added=gpb)
         # ---- T4: temporal decoder, sequences = windows (transformer.py:33-58,220)
         for j, L in enumerate(P["dec"]):
             i = self.n_enc + j
+            first, last = on_pairs and j == 0, latter_only and j + 1 == self.n_dec
+            w_in = W["%din_w" % i]
             qkv = new(M2, 3 * D_MODEL, bf16)
             in_b = L["in_b"].detach()
-            _fgemm(gpb, W["%din_w" % i][:2 * D_MODEL], bias=in_b[:2 * D_MODEL], out_bf16=qkv[:, :2 * D_MODEL])
-            _fgemm(gb, W["%din_w" % i][2 * D_MODEL:], bias=in_b[2 * D_MODEL:], out_bf16=qkv[:, 2 * D_MODEL:])
+            if first:
+                # window token = pair row (+ position row): project the N pair rows, gather into the windows; the
+                # position term enters as pos @ Wqk^T (2 rows, memoised per optimiser step) and q, k are rounded once
+                qk_n, v_n = new(N, D2, f32), new(N, D_MODEL, bf16)
+                _fgemm(xb, w_in[:D2], bias=in_b[:D2], out_f32=qk_n)
+                _fgemm(xb, w_in[D2:], bias=in_b[D2:], out_bf16=v_n)
+                pos_qk = cw("pos_qk", (L["in_w"], P["pos"]), lambda: _pos_rows_times_wt(pos, w_in[:D2]))
+                ops.gather_rows(qk_n, plan.win_src, add_table=pos_qk, add_idx=plan.win_pos, out_bf16_added=qkv[:, :D2])
+                ops.gather_rows_bf16(v_n, plan.win_src, qkv[:, D2:])
+                del qk_n, v_n
+            else:
+                _fgemm(gpb, w_in[:D2], bias=in_b[:D2], out_bf16=qkv[:, :D2])
+                _fgemm(gb, w_in[D2:], bias=in_b[D2:], out_bf16=qkv[:, D2:])
             ctxb = new(M2, D_MODEL, bf16)
-            ops.attn_small_fwd(qkv[:, :D_MODEL], qkv[:, D_MODEL:2 * D_MODEL], qkv[:, 2 * D_MODEL:], plan.win_off,
+            ops.attn_small_fwd(qkv[:, :D_MODEL], qkv[:, D_MODEL:D2], qkv[:, D2:], plan.win_off,
                                plan.W, plan.max_win_len, N_HEADS, HEAD_DIM, ctxb, p, self._seed(site))
-            u = new(M2, D_MODEL, f32)
-            _fgemm(ctxb, W["%dout_w" % i], bias=L["out_b"].detach(), residual=g32, out_f32=u, dropout_p=p,
+            rows, res = M2, g32
+            if last:
+                # only the rows the 'latter' read-out keeps go through out-proj / LayerNorm / FFN
+                rows = N
+                ctx_all, ctxb, res = ctxb, new(N, D_MODEL, bf16), new(N, D_MODEL, f32)
+                ops.gather_rows_bf16(ctx_all, plan.latter_src, ctxb)
+                ops.gather_rows(g32, plan.latter_src, out_f32=res)
+                del ctx_all
+            u = new(rows, D_MODEL, f32)
+            _fgemm(ctxb, W["%dout_w" % i], bias=L["out_b"].detach(), residual=res, out_f32=u, dropout_p=p,
                      seed=self._seed(site + 1))
-            t32, tb = new(M2, D_MODEL, f32), new(M2, D_MODEL, bf16)
-            m3, r3 = torch.empty(M2, device=dev), torch.empty(M2, device=dev)
+            t32, tb = new(rows, D_MODEL, f32), new(rows, D_MODEL, bf16)
+            m3, r3 = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
             ops.layernorm_fwd(u, L["g3"].detach(), L["be3"].detach(), 1e-5, t32, tb, mean=m3, rstd=r3)
-            h = new(M2, FFN_DIM, bf16)
+            h = new(rows, FFN_DIM, bf16)
             _fgemm(tb, W["%dw1" % i], bias=L["b1"].detach(), act=ops.ACT_RELU, out_bf16=h, dropout_p=p,
                      seed=self._seed(site + 2))
-            y32 = new(M2, D_MODEL, f32)
+            y32 = new(rows, D_MODEL, f32)
             _fgemm(h, W["%dw2" % i], bias=L["b2"].detach(), residual=t32, out_f32=y32, dropout_p=p,
                      seed=self._seed(site + 3))
             if self.save:
-                S["dec%d" % j] = dict(gb=gb, gpb=gpb, qkv=qkv, ctxb=ctxb, u=u, m3=m3, r3=r3, tb=tb, h=h, site=site)
+                S["dec%d" % j] = dict(gb=gb, gpb=gpb, xb=xb if first else None, qkv=qkv, ctxb=ctxb, u=u, m3=m3, r3=r3,
+                                      tb=tb, h=h, site=site)
             g32 = y32
             if j + 1 < self.n_dec:
                 gb, gpb = new(M2, D_MODEL, bf16), new(M2, D_MODEL, bf16)
                 ops.gather_rows(g32, None, rows=M2, add_table=pos, add_idx=plan.win_pos, out_bf16=gb, out_bf16_added=gpb)
             site += 4
         # ---- T5: 'latter' scatter-back as a gather (transformer.py:236-242)
-        out = new(N, D_MODEL, f32)
-        ops.gather_rows(g32, plan.latter_src, out_f32=out)
+        if latter_only:
+            out = g32                 # the last layer already ran on the kept rows, in pair order
+        else:
+            out = new(N, D_MODEL, f32)
+            ops.gather_rows(g32, plan.latter_src, out_f32=out)
         return out, local
 
     # ------------------------------------------------------------------------------ backward
@@ -988,15 +1047,21 @@ class _PathRunner:
                               gL[gkey], gL[bkey])
             return du, dub
 
-        def attn_block_bwd(du, dub, R, L, i, rows, seg_off, n_seg, max_len, site, pos_groups=False):
-            """Backward of u = x + drop(Wo attn(q,k,v) + bo); returns dqkv bf16 [rows, 3D]."""
+        def attn_block_bwd(du, dub, R, L, i, rows, seg_off, n_seg, max_len, site, pos_groups=False, expand=None):
+            """Backward of u = x + drop(Wo attn(q,k,v) + bo); returns dqkv bf16 [rows, 3D].  `expand` (int32 [rows], -1 =
+            none): du / dub / R["ctxb"] hold only the kept rows of a pruned last layer; the context gradient is spread
+            back over all `rows` attention rows (zero where the output was dropped)."""
             gL = G[i]
             gL["out_w"] = gnew(L["out_w"], D_MODEL, D_MODEL)
             ops.gemm(dub, R["ctxb"], a_mn=True, b_mn=True, out_f32=gL["out_w"])
             gL["out_b"] = zeros(1, D_MODEL)
             ops.colsum(dub, gL["out_b"])
-            dctx = new(rows, D_MODEL, bf16)
+            dctx = new(dub.shape[0], D_MODEL, bf16)
             ops.gemm(dub, W["%dout_w" % i], b_mn=True, out_bf16=dctx)
+            if expand is not None:
+                dctx_kept, dctx = dctx, new(rows, D_MODEL, bf16)
+                ops.gather_rows_bf16(dctx_kept, expand, dctx)
+                del dctx_kept
             qkv = R["qkv"]
             dqkv = new(rows, 3 * D_MODEL, bf16)
             ops.attn_small_bwd(qkv[:, :D_MODEL], qkv[:, D_MODEL:2 * D_MODEL], qkv[:, 2 * D_MODEL:], dctx, seg_off, n_seg,
@@ -1007,39 +1072,62 @@ class _PathRunner:
                 ops.colsum(dqkv, gL["in_b"])
             return dqkv
 
-        # ---- T5 backward: scatter d_out into window-token rows
-        dy = new(M2, D_MODEL, f32)
-        ops.gather2_sum_rows(d_out, plan.inv_latter2, out_f32=dy)
+        # ---- T5 backward: scatter d_out into window-token rows (a pruned last layer consumes d_out as it is)
+        on_pairs, latter_only = S["dec_flags"]
+        D2 = 2 * D_MODEL
+        if latter_only:
+            dy = d_out.contiguous()
+        else:
+            dy = new(M2, D_MODEL, f32)
+            ops.gather2_sum_rows(d_out, plan.inv_latter2, out_f32=dy)
+        dlocal = None
         # ---- T4 backward
         G["pos"] = zeros(2, D_MODEL)
         for j in reversed(range(self.n_dec)):
             i = self.n_enc + j
             L, R = P["dec"][j], S["dec%d" % j]
             site = R["site"]
-            du, dub = ffn_and_norm_bwd(dy, R, L, i, M2, "g3", R["m3"], R["r3"], R["u"], "g3", "be3", site)
-            dqkv = attn_block_bwd(du, dub, R, L, i, M2, plan.win_off, plan.W, plan.max_win_len, site, pos_groups=True)
+            first, last = on_pairs and j == 0, latter_only and j + 1 == self.n_dec
+            du, dub = ffn_and_norm_bwd(dy, R, L, i, N if last else M2, "g3", R["m3"], R["r3"], R["u"], "g3", "be3", site)
+            dqkv = attn_block_bwd(du, dub, R, L, i, M2, plan.win_off, plan.W, plan.max_win_len, site, pos_groups=True,
+                                  expand=plan.inv_latter if last else None)
+            if last:        # residual path of the kept rows, back in window-token order
+                du_kept, du = du, new(M2, D_MODEL, f32)
+                ops.gather2_sum_rows(du_kept, plan.inv_latter2, out_f32=du)
+                del du_kept
             gL = G[i]
             gL["in_w"] = gnew(L["in_w"], 3 * D_MODEL, D_MODEL)
-            ops.gemm(dqkv[:, :2 * D_MODEL], R["gpb"], a_mn=True, b_mn=True, out_f32=gL["in_w"][:2 * D_MODEL])
-            ops.gemm(dqkv[:, 2 * D_MODEL:], R["gb"], a_mn=True, b_mn=True, out_f32=gL["in_w"][2 * D_MODEL:])
+            w_in = W["%din_w" % i]
             # ONE pass over dqkv gives its column sums per position id: their total is the in_proj bias gradient, the
             # [dq|dk] part per position feeds the position embedding: d pos[k] = (sum over tokens with position k) @ W_qk
             by_pos = zeros(2, 3 * D_MODEL)
             ops.colsum(dqkv, by_pos, plan.win_pos, 2)
             gL["in_b"] = by_pos.sum(0, keepdim=True)
-            dpos_qk = by_pos[:, :2 * D_MODEL]
-            dposb = torch.zeros(8, 2 * D_MODEL, device=dev, dtype=bf16)
+            dpos_qk = by_pos[:, :D2]
+            dposb = torch.zeros(8, D2, device=dev, dtype=bf16)
             dposb[:2] = dpos_qk
             dpos_l = new(8, D_MODEL, f32)
-            ops.gemm(dposb, W["%din_w" % i][:2 * D_MODEL], b_mn=True, out_f32=dpos_l)
+            ops.gemm(dposb, w_in[:D2], b_mn=True, out_f32=dpos_l)
             G["pos"] += dpos_l[:2]
-            dx = new(M2, D_MODEL, f32)
-            ops.gemm(dqkv, W["%din_w" % i], b_mn=True, residual=du, out_f32=dx)
-            dy = dx
+            if first:
+                # the projections ran on the N pair rows: sum the <= 2 window copies of every pair row first
+                dqkv_n, du_n = new(N, 3 * D_MODEL, bf16), new(N, D_MODEL, f32)
+                ops.gather2_sum_rows_bf16(dqkv, plan.pair_win2, dqkv_n)
+                ops.gather2_sum_rows(du, plan.pair_win2, out_f32=du_n)
+                ops.gemm(dqkv_n, R["xb"], a_mn=True, b_mn=True, out_f32=gL["in_w"])
+                dlocal = new(N, D_MODEL, f32)
+                ops.gemm(dqkv_n, w_in, b_mn=True, residual=du_n, out_f32=dlocal)
+            else:
+                ops.gemm(dqkv[:, :D2], R["gpb"], a_mn=True, b_mn=True, out_f32=gL["in_w"][:D2])
+                ops.gemm(dqkv[:, D2:], R["gb"], a_mn=True, b_mn=True, out_f32=gL["in_w"][D2:])
+                dx = new(M2, D_MODEL, f32)
+                ops.gemm(dqkv, w_in, b_mn=True, residual=du, out_f32=dx)
+                dy = dx
             ready(gL["in_w"], gL["out_w"], gL["w1"], gL["w2"])
         # ---- T3 backward: each pair row was read by <= 2 windows
-        dlocal = new(N, D_MODEL, f32)
-        ops.gather2_sum_rows(dy, plan.pair_win2, out_f32=dlocal)
+        if dlocal is None:
+            dlocal = new(N, D_MODEL, f32)
+            ops.gather2_sum_rows(dy, plan.pair_win2, out_f32=dlocal)
         # ---- T2 backward
         dy = dlocal
         for i in reversed(range(self.n_enc)):

@@ -53,6 +53,35 @@ def test_gather_rows_and_sum(cuda_lib):
     assert torch.allclose(out, ref2, rtol=0, atol=1e-6)
 
 
+def test_gather_rows_bf16_and_sum_bit_exact(cuda_lib):
+    """bf16 row gathers of the temporal decoder (pair layout <-> window layout): copies are bit-exact, a negative index is
+    a zero row, outputs may be column slices of a wider buffer; the two-source sum equals fp32 addition rounded once."""
+    from b200vsgg import ops
+    g = _gen(11)
+    src = torch.randn(60, 1936, generator=g, device=DEV).bfloat16()
+    idx = torch.randint(-1, 60, (131,), generator=g, device=DEV).int()
+    wide = torch.full((131, 3 * 1936), 7.0, device=DEV, dtype=torch.bfloat16)
+    ops.gather_rows_bf16(src, idx, wide[:, 2 * 1936:])
+    ref = src[idx.clamp(min=0).long()] * (idx >= 0).unsqueeze(1)
+    assert torch.equal(wide[:, 2 * 1936:], ref.bfloat16())
+    assert (wide[:, :2 * 1936] == 7.0).all()                       # neighbours of the slice untouched
+    same = torch.empty_like(src)
+    ops.gather_rows_bf16(src, None, same)
+    assert torch.equal(same, src)
+    src3 = torch.randn(90, 5808, generator=g, device=DEV).bfloat16()
+    idx2 = torch.stack([torch.randint(-1, 90, (47,), generator=g, device=DEV),
+                        torch.randint(-1, 90, (47,), generator=g, device=DEV)], 1).int().contiguous()
+    out = torch.empty(47, 5808, device=DEV, dtype=torch.bfloat16)
+    ops.gather2_sum_rows_bf16(src3, idx2, out)
+    acc = torch.zeros(47, 5808, device=DEV)
+    for k in range(2):
+        m = idx2[:, k] >= 0
+        acc[m] += src3[idx2[m, k].long()].float()
+    assert torch.equal(out, acc.bfloat16())
+    with pytest.raises(Exception):
+        ops.gather_rows_bf16(src[:, :1932], idx, torch.empty(131, 1932, device=DEV, dtype=torch.bfloat16))   # cols % 8
+
+
 def test_pair_concat_fwd_bwd(cuda_lib):
     from b200vsgg import ops, synthetic
     e = synthetic.make_video_entry(2, 5, (2, 6), device=DEV)

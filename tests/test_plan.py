@@ -72,6 +72,7 @@ def test_plan_single_video_bit_exact(counts):
     for n, t in enumerate(plan.latter_src_h):
         assert inv[t, 0] == n
     assert (inv[:, 1] == -1).all() and (inv[:, 0] >= 0).sum() == plan.N
+    assert np.array_equal(plan.inv_latter_h, inv[:, 0]) and plan.inv_latter_h.dtype == np.int32
     for n in range(plan.N):
         for t in plan.pair_win2_h[n]:
             if t >= 0:
