@@ -533,7 +533,20 @@ def workload_config(args, world):
             "consistency_regulariser": ("off" if getattr(args, "no_consistency", False) else
                                         "on: TEAT-GT regulariser R1-R3 on TEMPURA's graphs, detached as in the reference "
                                         "(lib/teatgt.py:350-351); extension, the reference's TEMPURA never fills these keys"),
-            "optimizer_in_step": "fused AdamW + clip_grad_norm_(5) (tools/utils/AdamW.py semantics) after the all-reduce"}
+            "optimizer_in_step": "fused AdamW + clip_grad_norm_(5) (tools/utils/AdamW.py semantics) after the all-reduce",
+            "decoder_row_savings": _decoder_savings_note()}
+
+
+def _decoder_savings_note():
+    """Which of the two result-preserving row savings of the temporal decoder are active (b200vsgg.tempura)."""
+    try:
+        from b200vsgg import tempura
+    except Exception:
+        return None
+    on = [n for n, f in (("layer-1 q/k/v projections on the N pair rows", tempura.DEC_FIRST_ON_PAIRS),
+                         ("last layer after the attention on the N 'latter' rows", tempura.DEC_LATTER_ONLY)) if f]
+    return ("; ".join(on) + " (same outputs; model_tflops still counts the dense reference algorithm)") if on else \
+        "off (dense M2-row schedule)"
 
 
 # ------------------------------------------------------------------------------------------------
