@@ -57,21 +57,42 @@ class ObjSeqPlan:
 
     def __init__(self, indices, box_frames):
         bf = np.asarray(box_frames)
-        seqs = [np.asarray(ix.cpu() if torch.is_tensor(ix) else ix, dtype=np.int64) for ix in indices[1:]]
-        singles = np.asarray(indices[0].cpu() if torch.is_tensor(indices[0]) else indices[0], dtype=np.int64).reshape(-1)
+        # ONE device->host read for all class sequences (a batch of 64 videos holds ~850 of them: one `.cpu()` each was
+        # ~850 stream synchronisations per forward); lengths come from the shapes, which live on the host
+        seq_lens = [int(ix.shape[0]) for ix in indices[1:]]
+        parts = [ix for ix in indices[1:]] + [indices[0]]
+        parts = [t for t in parts if int(t.shape[0]) > 0]
+        if parts and all(torch.is_tensor(t) for t in parts):
+            same = all(t.dtype == parts[0].dtype and t.device == parts[0].device and t.dim() == 1 for t in parts)
+            if not same:
+                dev0 = next((t.device for t in parts if t.is_cuda), torch.device("cpu"))
+                parts = [t.reshape(-1).long().to(dev0) for t in parts]
+            src = torch.cat(parts).cpu().numpy().astype(np.int64)
+        elif parts:
+            src = np.concatenate([np.asarray(t.cpu() if torch.is_tensor(t) else t, dtype=np.int64).reshape(-1)
+                                  for t in parts])
+        else:
+            src = np.zeros(0, np.int64)
         O = bf.shape[0]
-        lens = [len(s) for s in seqs] + [1] * len(singles)
-        src = np.concatenate(seqs + [singles]) if (seqs or len(singles)) else np.zeros(0, np.int64)
+        n_seq_rows = int(sum(seq_lens))
+        n_single = src.shape[0] - n_seq_rows
+        lens = seq_lens + [1] * n_single
         assert src.shape[0] == O and np.array_equal(np.sort(src), np.arange(O)), \
             "entry['indices'] must partition the boxes (tools/utils/ds_track.py:25-37)"
+        # position of a sequence row (lib/tempura.py:191-195) — reference: unique(sorted) counts of the sequence's frame
+        # ids, then rank k repeated count_k times, assigned in sequence order (rows are frame-sorted because boxes are).
+        # All sequences at once: sort the frame ids inside every segment, dense-rank them, keep the sequence order.
         pos = np.zeros(O, dtype=np.int64)
-        r = 0
-        for s in seqs:
-            # reference: unique(sorted) counts of the frame ids, then rank k repeated count_k times, assigned in
-            # sequence order (rows are frame-sorted because boxes are)
-            _, counts = np.unique(bf[s], return_counts=True)
-            pos[r:r + len(s)] = np.repeat(np.arange(len(counts)), counts)
-            r += len(s)
+        if n_seq_rows:
+            seg = np.repeat(np.arange(len(seq_lens)), seq_lens)
+            f = bf[src[:n_seq_rows]]
+            order = np.lexsort((f, seg))
+            fs = f[order]
+            new = np.ones(n_seq_rows, dtype=np.int64)
+            new[1:] = (fs[1:] != fs[:-1]) | (seg[1:] != seg[:-1])
+            rank = np.cumsum(new) - 1
+            seg_start = np.concatenate([[0], np.cumsum(seq_lens)[:-1]])
+            pos[:n_seq_rows] = rank - np.repeat(rank[seg_start], seq_lens)
         off = np.zeros(len(lens) + 1, dtype=np.int64)
         off[1:] = np.cumsum(lens)
         inv = np.empty(O, dtype=np.int64)

@@ -191,3 +191,39 @@ def test_gt_label_csr_equals_trainer_multi_hot(monkeypatch):
         rows = torch.repeat_interleave(torch.arange(ref.shape[0]), torch.diff(off.long()))
         dense[rows, idx.long()] = 1
         assert torch.equal(dense, ref)
+
+
+def test_object_sequence_plan_vectorised_equals_per_sequence_loop():
+    """ObjSeqPlan computes the positions of all class sequences at once (segment-wise sort + dense rank, one device->host
+    read); here against the reference's per-sequence construction (lib/tempura.py:191-195: unique(sorted) counts of the
+    sequence's frame ids, rank k repeated count_k times) on random partitions, frame-sorted and not, tensor / numpy /
+    mixed-dtype index lists."""
+    import torch
+    from b200vsgg import objbranch
+    rng = np.random.default_rng(0)
+    for trial in range(120):
+        O = int(rng.integers(2, 120))
+        bf = np.sort(rng.integers(0, 12, O)) if trial % 3 else rng.integers(0, 12, O)
+        perm = rng.permutation(O)
+        k = min(O - 1, int(rng.integers(0, 10)))
+        cuts = np.sort(rng.choice(np.arange(1, O), size=k, replace=False)) if k else np.array([], dtype=np.int64)
+        groups = np.split(perm, cuts)
+        singles = [g for g in groups if len(g) == 1]
+        seqs = [np.sort(g) if trial % 2 else g for g in groups if len(g) > 1]
+        first = torch.as_tensor(np.concatenate(singles)) if singles else torch.tensor([])
+        pos = np.zeros(O, dtype=np.int64)
+        r = 0
+        for s in seqs:
+            _, counts = np.unique(bf[s], return_counts=True)
+            pos[r:r + len(s)] = np.repeat(np.arange(len(counts)), counts)
+            r += len(s)
+        src = np.concatenate(seqs + [np.asarray(first, dtype=np.int64)])
+        lens = [len(s) for s in seqs] + [1] * len(first)
+        for ind in ([first] + [torch.as_tensor(g) for g in seqs], [np.asarray(first)] + seqs,
+                    [first.int() if len(first) else first] + [torch.as_tensor(g) for g in seqs]):
+            plan = objbranch.ObjSeqPlan(ind, bf)
+            assert np.array_equal(plan.seq_src_h, src.astype(np.int32)), trial
+            assert np.array_equal(plan.pos_h, pos.astype(np.int32)), trial
+            assert np.array_equal(plan.seq_off_h, np.concatenate([[0], np.cumsum(lens)]).astype(np.int32))
+            assert np.array_equal(plan.inv_h[plan.seq_src_h], np.arange(O))
+            assert plan.max_len == max(lens) and plan.S == len(lens) and plan.max_pos == int(pos.max())
