@@ -343,6 +343,7 @@ class TEAT_GT(nn.Module):
         self.compute_consistency = True  # phase='train' fills structure_temp_loss / semantic_temp_loss (R1-R3)
         self.differentiable_consistency = False   # True: the semantic loss carries gradients (regulariser.py)
         self.pipeline_chunks = 4         # PredCLS batches: video chunks whose host graph build overlaps the device
+        self.background_graph = True     # SGCls-train: host graph build on a worker thread beside the object branch
         self.last_plan = None
 
     # ------------------------------------------------------------------------------------------
@@ -362,7 +363,7 @@ class TEAT_GT(nn.Module):
             entry["pred_labels"] = entry["labels"]
             # ... on a worker thread (numpy / LAPACK release the GIL), so that neither the host side of the object branch
             # (sequence plan, ~120 launches) nor its device work waits for the 35-45 ms graph build, and vice versa
-            pr = self._prepare(entry, phase, slot=0, background=bool(getattr(self, "background_graph", True)))
+            pr = self._prepare(entry, phase, slot=0, background=bool(self.background_graph))
             entry = self.object_classifier(entry, phase=phase, unc=unc)
             out = self._finish(pr, phase)
             self.last_plan = out.pop("_plan")
