@@ -116,3 +116,52 @@ def test_sgcls_oracle_matches_reference_golden():
         out = o(e, phase="train")
     for k in ("distribution", "attention_distribution", "spatial_distribution", "contacting_distribution"):
         assert (out[k] - gold["train/" + k]).abs().max().item() <= 2e-5, k
+
+
+def test_worker_thread_graph_build_equals_inline_build_and_propagates_errors():
+    """SGCls-train hands TeatPlan.build_graph to a worker thread (TEAT_GT._prepare(background=True) -> _build_graph_job,
+    joined in _finish).  The job on the pool yields the same plan arrays as the inline call, and what build_graph raises
+    (an edge-less clip: the reference's stale-variable fallback, lib/teatgt.py:229-234, is not reproduced) reaches the
+    caller through the future."""
+    from b200vsgg import teatgt
+    rng = np.random.default_rng(3)
+    counts = rng.integers(2, 7, size=14)
+    pair_idx, base = [], 0
+    for c in counts:                                    # person row first, then its objects (object_detector.py:324-341)
+        pair_idx += [(base, base + 1 + i) for i in range(c)]
+        base += c + 1
+    pair_idx = np.asarray(pair_idx, dtype=np.int64)
+
+    def predicates(plan, density):
+        nn_ = np.diff(plan.node_off_h)
+        sp = np.zeros((plan.F, plan.nmax, plan.nmax), dtype=np.uint8)
+        tp = np.zeros_like(sp)
+        for f in range(plan.F):
+            n = nn_[f]
+            sp[f, :n, :n] = np.triu(rng.random((n, n)) < density, 1)
+            sp[f, 0, 1] = density > 0                   # at least one edge per frame keeps every clip connected
+            if plan.has_prev_h[f]:
+                tp[f, :nn_[f - 1], :n] = rng.random((nn_[f - 1], n)) < 0.3 * density
+        return sp, tp
+
+    class _Ready:                                       # stands in for the CUDA event of the predicate copy
+        def synchronize(self):
+            pass
+
+    stub = types.SimpleNamespace(lap_k=8, eig_threads=2, eig_backend="host")
+    inline = teatgt.TeatPlan(counts, [8, 6], pair_idx)
+    sp, tp = predicates(inline, 0.7)
+    inline.build_graph(sp, tp, 8, 2, "host")
+    threaded = teatgt.TeatPlan(counts, [8, 6], pair_idx)
+    pr = dict(plan=threaded, sp_h=torch.from_numpy(sp), tp_h=torch.from_numpy(tp), ev=_Ready())
+    ms = teatgt._graph_pool().submit(teatgt.TEAT_GT._build_graph_job, stub, pr).result(timeout=60)
+    assert ms >= 0.0
+    for name in ("seq_off_h", "desc_h", "node_tok_h", "eigvec_h"):
+        assert np.array_equal(getattr(threaded, name), getattr(inline, name)), name
+    assert threaded.T == inline.T and threaded.max_T == inline.max_T
+    for a, b in zip(threaded.edges, inline.edges):
+        assert np.array_equal(a, b)
+    empty = teatgt.TeatPlan(counts, [8, 6], pair_idx)
+    pr = dict(plan=empty, sp_h=torch.from_numpy(np.zeros_like(sp)), tp_h=torch.from_numpy(np.zeros_like(tp)), ev=_Ready())
+    with pytest.raises(RuntimeError, match="edge-less clip"):
+        teatgt._graph_pool().submit(teatgt.TEAT_GT._build_graph_job, stub, pr).result(timeout=60)
