@@ -73,3 +73,55 @@ def test_oracle_forward_and_gradients_equal_live_reference(ref_and_oracle, case)
         scale = g.abs().max().item()
         assert (g - go[n]).abs().max().item() <= 2e-4 * scale + 1e-7, n
     ref.eval(), orc.eval()
+
+
+# ------------------------------------------------------------------------------------------------
+# TEAT-GT (PredCLS classifier path, lib/teatgt.py:98-283): phase='test' like the fixtures — the train-only regulariser
+# runs through third-party packages that are absent here (unpinned) — but with autograd on, so that the oracle's
+# gradients are pinned as well.  Cases: one full clip, a trailing one-frame clip, one pair per frame.
+# ------------------------------------------------------------------------------------------------
+TEAT_CASES = [(41, 5, (2, 4)), (42, 6, (1, 3)), (43, 11, 1)]
+
+
+@pytest.fixture(scope="module")
+def teat_ref_and_oracle():
+    import types
+    from b200vsgg import synthetic
+    from oracle import make_golden_teatgt as mg
+    from oracle.teatgt_oracle import TeatgtOracle
+    ref_mod = mg.import_reference_teatgt()
+    classes = synthetic.ag_object_classes()
+    args = types.SimpleNamespace(**dict(mg.ARGS, encoder_layers=3))      # 3 of the 12 identical layers: same code, 4x faster
+    ref = ref_mod.TEAT_GT(obj_classes=classes, args=args, **mg.MODEL_KW)
+    synthetic.teatgt_seeded_init_(ref, synthetic.BASE_SEED)
+    orc = TeatgtOracle(obj_classes=classes, args=args, **mg.MODEL_KW)
+    orc.load_state_dict(ref.state_dict(), strict=True)
+    return ref.eval(), orc.eval()
+
+
+@pytest.mark.parametrize("case", TEAT_CASES, ids=["5f_one_clip", "6f_trailing_1-frame_clip", "11f_1p"])
+def test_teatgt_oracle_forward_and_gradients_equal_live_reference(teat_ref_and_oracle, case):
+    import torch.nn.functional as F
+    from b200vsgg import synthetic
+    ref, orc = teat_ref_and_oracle
+    vid, frames, ppf = case
+    entry = synthetic.make_video_entry(vid, frames, ppf)
+    for k in ("union_feat", "spatial_masks"):
+        entry.pop(k)
+    att, spa, con = synthetic.build_gt_tensors(entry)
+    outs = []
+    for model in (ref, orc):
+        model.zero_grad()
+        pred = model({k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in entry.items()}, phase="test")
+        loss = (F.cross_entropy(pred["attention_distribution"], att) + F.binary_cross_entropy(pred["spatial_distribution"], spa)
+                + F.binary_cross_entropy(pred["contacting_distribution"], con))
+        loss.backward()
+        outs.append((pred, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    (r, gr), (o, go) = outs
+    for k in ("attention_distribution", "spatial_distribution", "contacting_distribution"):
+        assert (r[k] - o[k]).abs().max().item() <= 2e-5, k
+    assert len(gr) > 40
+    for n, g in gr.items():
+        assert n in go, n
+        scale = g.abs().max().item()
+        assert (g - go[n]).abs().max().item() <= 5e-4 * scale + 1e-7, n
