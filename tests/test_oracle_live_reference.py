@@ -125,3 +125,58 @@ def test_teatgt_oracle_forward_and_gradients_equal_live_reference(teat_ref_and_o
         assert n in go, n
         scale = g.abs().max().item()
         assert (g - go[n]).abs().max().item() <= 5e-4 * scale + 1e-7, n
+
+
+# ------------------------------------------------------------------------------------------------
+# SGCls, phase='train' (object branch S1: lib/tempura.py:185-255 with the reference's own get_sequence,
+# tools/utils/ds_track.py:18-39): forward, object + relation loss gradients.  lib/tempura.py:201 hard-codes
+# `masks.cuda()`; Tensor.cuda is the identity for the duration of the test (as in oracle/make_golden_sgcls.py).
+# ------------------------------------------------------------------------------------------------
+SGCLS_CASES = [(51, 3, 1, dict(tracking=True, obj_head="gmm")), (52, 8, (1, 6), dict(tracking=True, obj_head="linear")),
+               (53, 4, (2, 3), dict(tracking=False, obj_head="gmm"))]
+
+
+@pytest.mark.parametrize("case", SGCLS_CASES, ids=["3f_1p_track_gmm", "8f_1-6p_track_linear", "4f_notrack_gmm"])
+def test_sgcls_oracle_forward_and_gradients_equal_live_reference(monkeypatch, case):
+    from b200vsgg import synthetic
+    from oracle import make_golden
+    from oracle.make_golden import clone_entry
+    from oracle.make_golden_sgcls import zero_dropout
+    from oracle.tempura_oracle import TempuraOracle, get_sequence, object_loss, tempura_losses
+    torch.backends.mha.set_fastpath_enabled(False)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    ref_mod = make_golden.import_reference_tempura()
+    from tools.utils.ds_track import get_sequence as ref_get_sequence          # the reference's own, unmodified
+    vid, frames, ppf, over = case
+    kw = dict(make_golden.MODEL_KW, mode="sgcls", **over)
+    classes = synthetic.ag_object_classes()
+    ref = ref_mod.TEMPURA(obj_classes=classes, **kw)
+    synthetic.seeded_init_(ref)
+    orc = TempuraOracle(obj_classes=classes, **kw)
+    orc.load_state_dict(ref.state_dict(), strict=True)
+    entry = synthetic.add_sgcls_inputs(synthetic.make_video_entry(vid, frames, ppf), vid)
+    e_ref, e_orc = clone_entry(entry), clone_entry(entry)
+    ref_get_sequence(e_ref, None, None, "sgcls")
+    get_sequence(e_orc, "sgcls")
+    assert len(e_ref["indices"]) == len(e_orc["indices"])
+    for a, b in zip(e_ref["indices"], e_orc["indices"]):
+        assert torch.equal(torch.as_tensor(a).long(), torch.as_tensor(b).long())
+    att, spa, con = synthetic.build_gt_tensors(entry)
+    ref.train(), orc.train()
+    zero_dropout(ref, orc)
+    outs = []
+    for model, e in ((ref, e_ref), (orc, e_orc)):
+        model.zero_grad()
+        torch.manual_seed(99)
+        pred = model(clone_entry(e), phase="train")
+        loss = sum(tempura_losses(pred, att, spa, con).values()) + object_loss(pred)
+        loss.backward()
+        outs.append((pred, float(loss.detach()), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    (r, lr, gr), (o, lo, go) = outs
+    for k in ("distribution", "attention_distribution", "spatial_distribution", "contacting_distribution"):
+        assert (r[k] - o[k]).abs().max().item() <= 2e-5, k
+    assert abs(lr - lo) <= 1e-5 * max(1.0, abs(lr))
+    assert gr.keys() == go.keys() and len(gr) > 150
+    for n, g in gr.items():
+        scale = g.abs().max().item()
+        assert (g - go[n]).abs().max().item() <= 5e-4 * scale + 1e-7, n
