@@ -180,3 +180,39 @@ def test_sgcls_oracle_forward_and_gradients_equal_live_reference(monkeypatch, ca
     for n, g in gr.items():
         scale = g.abs().max().item()
         assert (g - go[n]).abs().max().item() <= 5e-4 * scale + 1e-7, n
+
+
+# ------------------------------------------------------------------------------------------------
+# Evaluator (f).3: the product's host backend (it runs on the CPU) against the UNMODIFIED reference evaluator run live on
+# seeds and shapes the fixture does not hold: one pair per frame (no-constraint candidate lists shorter than K), many pairs
+# per frame, a long video.  Tables must be identical, recalls equal as floats (as in tests/test_evaluator.py).
+# ------------------------------------------------------------------------------------------------
+EVAL_CASES = [(61, 3, 1), (62, 10, (1, 2)), (63, 7, (6, 10)), (64, 24, (2, 5))]
+
+
+@pytest.mark.parametrize("mode", ["predcls", "sgcls"])
+@pytest.mark.parametrize("constraint,semi", [("with", None), ("semi", 0.9), ("no", None)])
+def test_evaluator_host_backend_equals_live_reference(mode, constraint, semi):
+    import sys
+    import types
+    from oracle.make_golden_eval import evaluator_kwargs, synthetic_prediction
+    from b200vsgg import evaluator as mine
+    for n in ("h5py", "dill", "tools.utils.fpn", "tools.utils.fpn.box_intersections_cpu"):
+        sys.modules.setdefault(n, types.ModuleType(n))
+    m = types.ModuleType("tools.utils.fpn.box_intersections_cpu.bbox")
+    m.bbox_overlaps = mine.bbox_overlaps                       # absent Cython helper: Fast R-CNN definition (unpinned)
+    sys.modules["tools.utils.fpn.box_intersections_cpu.bbox"] = m
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import tools.utils.evaluation_recall as ref
+    ev_ref = ref.BasicSceneGraphEvaluator(mode=mode, constraint=constraint, semithreshold=semi, **evaluator_kwargs())
+    ev = mine.BasicSceneGraphEvaluator(mode=mode, constraint=constraint, semithreshold=semi, **evaluator_kwargs())
+    for vid, frames, ppf in EVAL_CASES:
+        pred, gt = synthetic_prediction(vid, frames, ppf, mode)
+        ev_ref.evaluate_scene_graph(gt, {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in pred.items()})
+        ev.evaluate_scene_graph(gt, pred)
+    for k in (10, 20, 50, 100):
+        assert ev.result_dict[mode + "_recall"][k] == ev_ref.result_dict[mode + "_recall"][k], k
+        assert list(ev.result_dict[mode + "_recall_count"][k]) == list(ev_ref.result_dict[mode + "_recall_count"][k]), k
+        assert list(ev.result_dict[mode + "_recall_hit"][k]) == list(ev_ref.result_dict[mode + "_recall_hit"][k]), k
+    assert ev.calc_mrecall() == ev_ref.calc_mrecall()
